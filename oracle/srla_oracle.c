@@ -9,11 +9,17 @@
  * whole .srl streams byte for byte with the compiled reference (oracle/_ref/libsrla_ref.so) and
  * with the committed reference-generated fixtures in tests/golden/.
  *
- * Known, documented deviations from the reference (both are "uninitialised memory" corners):
+ * Known, documented deviations from the reference (all are "uninitialised / stale memory" corners
+ * where the reference's own output depends on what earlier calls left in its scratch buffers):
  *  - odd block length: the reference's Welch window leaves the middle sample of its scratch buffer
  *    stale (lpc.c:260-264); here the middle sample is windowed like every other one.
  *  - LTP pitch search may read autocorrelation lags 263/264 that the reference never writes
- *    (lpc.c:1497-1513 with lag buffer from lpc.c:330-376); here they read as 0.0.
+ *    (lpc.c:1497-1513 with lag buffer from lpc.c:330-376); here they read as 0.0, which is what a
+ *    handle created on zeroed memory (a fresh `srla` CLI process) sees.
+ *  - LTP enabled and block length n with FFT size N = 2^ceil(log2 n) < 263: the reference copies
+ *    lags N..262 from beyond the transformed region of its FFT buffer (lpc.c:371-373), i.e. stale
+ *    data of the previous call; here those lags are 0.0.  Byte parity is only claimed for LTP
+ *    blocks of at least 263 samples; shorter ones are covered by decoder round trips.
  *
  * Floating point: compile with -ffp-contract=off (oracle/Makefile does); the reference is built as
  * ISO C90, i.e. without FMA contraction, and byte-identical output needs the same roundings.

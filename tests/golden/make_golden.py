@@ -1,0 +1,56 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libsrla_ref.so, built by
+`make -C oracle ref` from /root/reference).  Run in the build container only; the fixtures are
+committed because /root/reference does not exist on the GPU box.
+
+Each fixture holds the PCM input (so no libm/numpy version can change it), the encode parameters
+and the byte stream the reference produced (its handle created on a zeroed work area, i.e. what
+a fresh `srla` CLI process emits).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from helpers import ref_encode, ref_decode, reference_test_signals  # noqa: E402
+from srla_b200.synth import synth_stereo  # noqa: E402
+
+
+def save(name, pcm, **kw):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+    srl = ref_encode(pcm, **kw)
+    assert np.array_equal(ref_decode(srl), pcm), name
+    store = pcm.astype(np.int16) if kw.get("bps", 16) <= 16 else pcm
+    keys = sorted(kw)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pcm=store,
+                        srl=np.frombuffer(srl, dtype=np.uint8),
+                        param_names=np.array(keys), param_values=np.array([kw[k] for k in keys], dtype=np.int64))
+    print(f"{name}: {pcm.shape} -> {len(srl)} bytes")
+
+
+def main():
+    s16 = synth_stereo(4096 * 3 + 2304, seed=1234)
+    save("config1_mono_m0", s16[:1, :4096], preset=0, max_block=4096)
+    save("stereo16_m4_b4096", s16, preset=4, max_block=4096)
+    save("stereo16_m2_b4096", s16[:, :9000], preset=2, max_block=4096)
+    save("stereo16_m6_b4096", s16[:, :8192], preset=6, max_block=4096)
+    s24 = synth_stereo(8192 * 2 + 1000, seed=77, bits=24)
+    save("stereo24_m4_b8192_ltp3", s24, bps=24, preset=4, max_block=8192, ltp=3)
+    save("stereo16_m4_v2_l4", synth_stereo(20000, seed=99), preset=4, max_block=4096, min_block=1024, lookahead=16384)
+    save("mono16_m4_shifted", (synth_stereo(10000, seed=5)[:1] >> 3) << 3, preset=4, max_block=4096)
+    three = synth_stereo(6000, seed=11, channels=3)
+    save("three_ch_m3", three, preset=3, max_block=2048)
+    # the reference's own round-trip matrix generators (test/srla_encode_decode/main.cpp:51-208), its
+    # block configuration (min 512 / max 1024 / look-ahead 2048, preset 0), with and without LTP
+    for name, sig in reference_test_signals(n=8500, bps=16, nch=2).items():
+        for ltp in (0, 3):
+            save(f"refgen_{name}_ltp{ltp}", sig, preset=0, min_block=512, max_block=1024, lookahead=2048, ltp=ltp, rate=44100)
+    for name, sig in reference_test_signals(n=4000, bps=24, nch=1, seed=3).items():
+        save(f"refgen24_{name}", sig, bps=24, preset=4, max_block=1024, ltp=3, rate=44100)
+
+
+if __name__ == "__main__":
+    main()

@@ -128,7 +128,14 @@ def api_encode_whole(lib: C.CDLL, pcm: np.ndarray, bps=16, rate=48000, max_block
     min_block = max_block if min_block is None else min_block
     lookahead = (4 * max_block if min_block != max_block else max_block) if lookahead is None else lookahead
     cfg = SRLAEncoderConfig(max_channels, min_block, max_block, lookahead, max_params)
-    enc = lib.SRLAEncoder_Create(C.byref(cfg), None, 0)
+    # Caller-provided, ZEROED work area: the reference reads two autocorrelation lags it never
+    # writes during the LTP pitch search (lpc.c:1497-1513); a fresh CLI process sees zero pages
+    # there, a recycled heap does not.  Zeroing makes the reference deterministic and equal to
+    # what the `srla` CLI produces.
+    work_size = lib.SRLAEncoder_CalculateWorkSize(C.byref(cfg))
+    assert work_size > 0, "SRLAEncoder_CalculateWorkSize failed"
+    work = np.zeros(work_size + 64, dtype=np.uint8)
+    enc = lib.SRLAEncoder_Create(C.byref(cfg), work.ctypes.data, work_size)
     assert enc, "SRLAEncoder_Create failed"
     try:
         prm = make_param(nch, bps, rate, min_block, max_block, lookahead, ltp, preset)
@@ -279,3 +286,18 @@ def reference_test_signals(n=8500, bps=16, nch=2, seed=0):
     imp = np.zeros((nch, n)); imp[:, ::100] = 1
     out["mini_impulse"] = imp
     return {k: np.round(v).astype(np.int32) for k, v in out.items()}
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    """-> (pcm int32 [ch, n], kwargs for *_encode, reference .srl bytes)"""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    kw = {str(k): int(v) for k, v in zip(z["param_names"], z["param_values"])}
+    return z["pcm"].astype(np.int32), kw, z["srl"].tobytes()
