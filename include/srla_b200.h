@@ -101,7 +101,7 @@ int32_t SRLAEncoder_CalculateWorkSize(const struct SRLAEncoderConfig *config);
 /* include/srla_encoder.h:50 (srla_encoder.c:549-694): (work == NULL && work_size == 0) => the
  * handle allocates for itself and Destroy frees; otherwise the caller owns `work`.
  * NULL on bad arguments, short work area, or when no CUDA device is usable.
- * Capacity limit of this implementation: max_num_samples_per_block <= 16384. */
+ * Capacity limit of this implementation: max_num_samples_per_block <= 8192. */
 struct SRLAEncoder *SRLAEncoder_Create(const struct SRLAEncoderConfig *config, void *work, int32_t work_size);
 
 /* include/srla_encoder.h:53 (srla_encoder.c:697-707) */
@@ -154,11 +154,15 @@ SRLAApiResult SRLAB200_EncodeStreamsDevice(
     struct SRLAEncoder *encoder, const struct SRLAB200Stream *streams, uint32_t num_streams,
     uint8_t *d_out, uint64_t out_capacity, uint64_t *stream_offsets);
 
-/* Same, but PCM and output are HOST buffers: PCM is packed/copied to the device through pinned
- * staging, results are copied back.  sample_bytes/pcm describe host memory here. */
+/* Same, but PCM and output are HOST buffers (ideally pinned): PCM is copied to the device, results
+ * are copied back.  sample_bytes/pcm describe host memory here. */
 SRLAApiResult SRLAB200_EncodeStreamsHost(
     struct SRLAEncoder *encoder, const struct SRLAB200Stream *streams, uint32_t num_streams,
     uint8_t *out, uint64_t out_capacity, uint64_t *stream_offsets);
+
+/* Upper bound of the encoded size of a stream of num_samples samples per channel under the
+ * handle's current parameters (header + every block stored raw). */
+uint64_t SRLAB200_MaxEncodedSize(const struct SRLAEncoder *encoder, uint32_t num_samples);
 
 /* Statistics of the most recent encode call on this handle. */
 struct SRLAB200Stats {
@@ -179,17 +183,17 @@ SRLAApiResult SRLAB200_GetStats(const struct SRLAEncoder *encoder, struct SRLAB2
 /* Device selection for handles created afterwards by this thread (default: current CUDA device). */
 SRLAApiResult SRLAB200_SetDevice(int device_ordinal);
 
+/* Run the handle's kernels on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL
+ * restores the handle's own stream).  Lets a host framework time the kernels with its own events. */
+SRLAApiResult SRLAB200_SetStream(struct SRLAEncoder *encoder, void *cuda_stream);
+
 /* Library identification string ("srla_b200 <ver> sm_100a ..."). */
 const char *SRLAB200_Version(void);
 
-/* ---- stage-level entry points used by the parity tests (host buffers in/out, run on the GPU) ---- */
+/* ---- stage-level entry point used by the parity tests (host buffers in/out, runs on the GPU) ---- */
 
-/* Welch-windowed circular autocorrelation exactly as the reference's FFT path computes it
- * (lpc.c:236-272, 330-376): x[n] doubles -> r[0..max_lag].  n <= 16384. */
-SRLAApiResult SRLAB200_TestAutocorr(const double *x, uint32_t n, double *r, uint32_t max_lag);
-
-/* Analysis of one candidate channel (srla_encoder.c:966-1205): sig[n] in -> pre-emphasised signal
- * out, residual[n] out, and the decisions in `result` (layout: struct SRLAB200ChannelResult). */
+/* Analysis of one candidate channel (srla_encoder.c:966-1205) under the handle's current bit depth,
+ * preset and LTP order: sig[n] in, residual[n] out, and the decisions in `result`. */
 struct SRLAB200ChannelResult {
     int32_t  pre_coef, pre_prev;
     uint32_t order, rshift, use_sum;
@@ -199,6 +203,7 @@ struct SRLAB200ChannelResult {
     uint32_t code_type, porder, residual_bits, total_bits;
     double   autocorr[SRLA_MAX_COEFFICIENT_ORDER + 1];
     double   error_vars[SRLA_MAX_COEFFICIENT_ORDER + 1];
+    double   lpc_double[SRLA_MAX_COEFFICIENT_ORDER];
 };
 SRLAApiResult SRLAB200_TestAnalyseChannel(
     struct SRLAEncoder *encoder, const int32_t *sig, uint32_t n, int32_t *residual,

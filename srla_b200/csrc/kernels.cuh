@@ -1,0 +1,1205 @@
+/*
+ * kernels.cuh -- the sm_100a CUDA kernels of the SRLA encode path.
+ *
+ *   lshift_or_kernel / lshift_finish_kernel   whole-stream OR reduce -> trailing-zero shift   (A0)
+ *   analyse_kernel<BPT>     one CTA per (block, candidate channel): the complete analysis of
+ *                           srla_encoder.c:966-1205 with the block resident in shared memory  (A2-A8, A11)
+ *   decide_kernel           block type, stereo method, exact block size                       (A1, A2)
+ *   scan_kernel             output offsets of the blocks / streams
+ *   emit_kernel             one CTA per block: header, side information, Rice codes, Fletcher (A1, A9, A10)
+ *
+ * Floating point: this translation unit MUST be compiled with -fmad=false.  The reference is ISO C90
+ * (no FMA contraction); byte-identical output needs every double operation rounded separately and
+ * in the reference's order.  Division and sqrt are IEEE (nvcc defaults -prec-div/-prec-sqrt=true).
+ */
+#ifndef SRLA_B200_KERNELS_CUH
+#define SRLA_B200_KERNELS_CUH
+
+#include <cfloat>
+#include <cuda_runtime.h>
+
+#include "types.h"
+
+namespace srla {
+
+/* ------------------------------------------------------------------------------------------------
+ * small helpers
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t zigzag32(int32_t v) { return ((uint32_t)v << 1) ^ (uint32_t)(v >> 31); }   /* srla_utility.h:31 */
+__device__ __forceinline__ int32_t asr32(int32_t v, uint32_t s) { return (s >= 32u) ? (v >> 31) : (v >> s); }
+__device__ __forceinline__ double round_half_away(double d) { return (d >= 0.0) ? floor(d + 0.5) : -floor(-d + 0.5); } /* srla_utility.c:22 */
+__device__ __forceinline__ uint32_t ceil_pow2_u32(uint32_t v) { return (v <= 1u) ? 1u : (1u << (32 - __clz(v - 1u))); }
+
+__device__ __forceinline__ int32_t load_sample(const StreamDev &st, uint32_t ch, uint32_t idx)
+{
+    const unsigned long long at = (unsigned long long)ch * st.stride + idx;
+    return (st.sample_bytes == 2u) ? (int32_t)__ldg(reinterpret_cast<const short *>(st.pcm) + at)
+                                   : __ldg(reinterpret_cast<const int32_t *>(st.pcm) + at);
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { v += __shfl_xor_sync(0xffffffffu, v, o); }
+    return v;
+}
+
+/* inclusive block scan of one uint32 per thread; returns the inclusive prefix, *total = block sum.
+ * scratch: kWarps + 1 words */
+__device__ __forceinline__ uint32_t block_scan_inclusive(uint32_t v, uint32_t *scratch, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) { x += y; } }
+    __syncthreads();                       /* scratch may still be read from a previous call */
+    if (lane == 31) { scratch[warp] = x; }
+    __syncthreads();
+    uint32_t base = 0, sum = 0;
+    #pragma unroll
+    for (int w = 0; w < kWarps; ++w) { const uint32_t s = scratch[w]; if (w < warp) { base += s; } sum += s; }
+    *total = sum;
+    return x + base;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * A0: trailing-zero shift of a whole stream (srla_utility.c:177-203)
+ * grid.x = chunks, grid.y = stream
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void lshift_or_kernel(StreamDev *streams, uint32_t nch)
+{
+    StreamDev &st = streams[blockIdx.y];
+    const unsigned long long total = (unsigned long long)st.num_samples;
+    uint32_t acc = 0;
+    for (uint32_t c = 0; c < nch; ++c) {
+        if (st.sample_bytes == 2u) {
+            const short *base = reinterpret_cast<const short *>(st.pcm) + (unsigned long long)c * st.stride;
+            /* 16-byte vector body when the channel start is aligned, scalar head/tail otherwise */
+            const unsigned long long mis = ((reinterpret_cast<unsigned long long>(base) + 15ull) & ~15ull) - reinterpret_cast<unsigned long long>(base);
+            unsigned long long head = mis / 2ull; if (head > total) { head = total; }
+            const unsigned long long nvec = (total - head) / 8ull;
+            const int4 *v = reinterpret_cast<const int4 *>(base + head);
+            for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (unsigned long long)gridDim.x * blockDim.x) {
+                const int4 q = __ldg(v + i);
+                uint32_t m = (uint32_t)(q.x | q.y | q.z | q.w);
+                acc |= (m & 0xffffu) | (m >> 16);
+            }
+            if (blockIdx.x == 0) {
+                for (unsigned long long i = threadIdx.x; i < head; i += blockDim.x) { acc |= (uint32_t)(int32_t)base[i]; }
+                for (unsigned long long i = head + nvec * 8ull + threadIdx.x; i < total; i += blockDim.x) { acc |= (uint32_t)(int32_t)base[i]; }
+            }
+        } else {
+            const int32_t *base = reinterpret_cast<const int32_t *>(st.pcm) + (unsigned long long)c * st.stride;
+            const unsigned long long mis = ((reinterpret_cast<unsigned long long>(base) + 15ull) & ~15ull) - reinterpret_cast<unsigned long long>(base);
+            unsigned long long head = mis / 4ull; if (head > total) { head = total; }
+            const unsigned long long nvec = (total - head) / 4ull;
+            const int4 *v = reinterpret_cast<const int4 *>(base + head);
+            for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (unsigned long long)gridDim.x * blockDim.x) {
+                const int4 q = __ldg(v + i);
+                acc |= (uint32_t)(q.x | q.y | q.z | q.w);
+            }
+            if (blockIdx.x == 0) {
+                for (unsigned long long i = threadIdx.x; i < head; i += blockDim.x) { acc |= (uint32_t)base[i]; }
+                for (unsigned long long i = head + nvec * 4ull + threadIdx.x; i < total; i += blockDim.x) { acc |= (uint32_t)base[i]; }
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc |= __shfl_xor_sync(0xffffffffu, acc, o); }
+    if ((threadIdx.x & 31) == 0 && acc) { atomicOr(&st.or_mask, acc); }
+}
+
+__global__ void lshift_finish_kernel(StreamDev *streams, uint32_t num_streams)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < num_streams) {
+        /* int16 lanes were folded into the low half: sign extension bits do not add low set bits */
+        const uint32_t m = streams[s].or_mask;
+        streams[s].lshift = m ? (uint32_t)(__ffs((int)m) - 1) : 0u;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FFT exactly as the reference evaluates it (libs/fft/src/fft.c:71-128, 147-198).
+ * The Stockham stages are executed IN PLACE: every thread first pulls the four inputs of its
+ * butterflies into registers, the CTA synchronises, then the outputs are stored.  Each output is
+ * the same expression tree as in the reference, with the host-tabulated twiddle sequence.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+template <int BPT>
+__device__ __forceinline__ void complex_fft_inplace(double2 *x, const int M, const bool inverse, const LaunchParams &p)
+{
+    const int tid = threadIdx.x;
+    const int quarter_m = M >> 2;
+    int nn = M, lgs = 0;
+    while (nn > 2) {
+        const int lgn = 31 - __clz(nn);
+        const double2 *tw = p.tw_complex + p.tw_complex_off[lgn];
+        double2 a[BPT], b[BPT], c[BPT], d[BPT];
+        #pragma unroll
+        for (int it = 0; it < BPT; ++it) {
+            const int bf = tid + it * kThreads;
+            if (bf < quarter_m) { a[it] = x[bf]; b[it] = x[bf + quarter_m]; c[it] = x[bf + 2 * quarter_m]; d[it] = x[bf + 3 * quarter_m]; }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int it = 0; it < BPT; ++it) {
+            const int bf = tid + it * kThreads;
+            if (bf < quarter_m) {
+                const int pp = bf >> lgs, q = bf & ((1 << lgs) - 1);
+                double2 w1 = __ldg(tw + 3 * pp), w2 = __ldg(tw + 3 * pp + 1), w3 = __ldg(tw + 3 * pp + 2);
+                if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+                const double2 apc = cadd(a[it], c[it]), amc = csub(a[it], c[it]), bpd = cadd(b[it], d[it]);
+                const double2 bmd = csub(b[it], d[it]);
+                /* j * (b - d), j = (0, -flag): forward (0,+1) -> (-im, re); inverse (0,-1) -> (im, -re).
+                 * (the reference's 0.0 * x terms only affect the sign of zeros) */
+                const double2 jbmd = inverse ? make_double2(bmd.y, -bmd.x) : make_double2(-bmd.y, bmd.x);
+                const int o = q + ((4 * pp) << lgs);
+                x[o]                = cadd(apc, bpd);
+                x[o + (1 << lgs)]   = cmul(w1, csub(amc, jbmd));
+                x[o + (2 << lgs)]   = cmul(w2, csub(apc, bpd));
+                x[o + (3 << lgs)]   = cmul(w3, cadd(amc, jbmd));
+            }
+        }
+        __syncthreads();
+        nn >>= 2; lgs += 2;
+    }
+    if (nn == 2) {
+        const int s = 1 << lgs;        /* == M / 2 */
+        for (int q = tid; q < s; q += kThreads) {
+            const double2 a = x[q], b = x[q + s];
+            x[q] = cadd(a, b);
+            x[q + s] = csub(a, b);
+        }
+        __syncthreads();
+    }
+}
+
+/* Welch window (lpc.c:252-266) + autocorrelation through the FFT (lpc.c:330-376).
+ * sig[n] int32 in shared memory -> lags[0..nlags) (lags >= N read as 0.0).  buf: N doubles. */
+template <int BPT>
+__device__ void welch_autocorr(const int32_t *sig, const uint32_t n, double *buf, double *lags, const uint32_t nlags,
+                               const Job &job, const LaunchParams &p)
+{
+    const int tid = threadIdx.x;
+    const uint32_t N = ceil_pow2_u32(n);
+    const double unit = p.unit, div = job.welch_div;
+    for (uint32_t i = tid; i < N; i += kThreads) {
+        double v = 0.0;
+        if (i < n) {
+            const uint32_t s = (i < (n >> 1)) ? i : (n - 1u - i);
+            const double w = div * (double)s * (double)(n - 1u - s);
+            v = ((double)sig[i] * unit) * w;
+        }
+        buf[i] = v;
+    }
+    __syncthreads();
+    if (N >= 2u) {
+        double2 *cx = reinterpret_cast<double2 *>(buf);
+        const int M = (int)(N >> 1);
+        complex_fft_inplace<BPT>(cx, M, false, p);
+        /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three
+         * only touch the element pair (i, N/2 - i) */
+        {
+            const int lgN = 31 - __clz((int)N);
+            const double2 *tw = p.tw_real + p.tw_real_off[lgN];
+            const uint32_t quarter = N >> 2;
+            for (uint32_t i = 1u + tid; i <= quarter; i += kThreads) {
+                const double2 w = __ldg(tw + (i - 1u));
+                const double wr = w.x, wi_f = w.y, wi_b = -w.y;
+                const uint32_t lo = i, hi = (N >> 1) - i;
+                const double2 xl = cx[lo], xh = cx[hi];
+                /* forward, flag = -1: c2 = -0.5 */
+                double f1, f2, f3, f4;
+                {
+                    const double c2 = -0.5;
+                    const double h1r = 0.5 * (xl.x + xh.x);
+                    const double h1i = 0.5 * (xl.y - xh.y);
+                    const double h2r = -c2 * (xl.y + xh.y);
+                    const double h2i = c2 * (xl.x - xh.x);
+                    f1 = h1r + (wr * h2r) - (wi_f * h2i);
+                    f2 = h1i + (wr * h2i) + (wi_f * h2r);
+                    f3 = h1r - (wr * h2r) + (wi_f * h2i);
+                    f4 = -h1i + (wr * h2i) + (wi_f * h2r);
+                }
+                /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
+                double p_lo, p_hi;
+                if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
+                else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
+                /* inverse, flag = +1: c2 = +0.5, imaginary parts are 0.0 */
+                {
+                    const double c2 = 0.5;
+                    const double zl = 0.0, zh = 0.0;
+                    const double h1r = 0.5 * (p_lo + p_hi);
+                    const double h1i = 0.5 * (zl - zh);
+                    const double h2r = -c2 * (zl + zh);
+                    const double h2i = c2 * (p_lo - p_hi);
+                    const double g1 = h1r + (wr * h2r) - (wi_b * h2i);
+                    const double g2 = h1i + (wr * h2i) + (wi_b * h2r);
+                    const double g3 = h1r - (wr * h2r) + (wi_b * h2i);
+                    const double g4 = -h1i + (wr * h2i) + (wi_b * h2r);
+                    if (lo != hi) { cx[lo] = make_double2(g1, g2); }
+                    cx[hi] = make_double2(g3, g4);
+                }
+            }
+            if (tid == 0) {
+                const double2 dc = cx[0];
+                const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
+                const double q0 = f0 * f0, q1 = f1 * f1;
+                cx[0] = make_double2(0.5 * (q0 + q1), 0.5 * (q0 - q1));
+            }
+            __syncthreads();
+        }
+        complex_fft_inplace<BPT>(cx, M, true, p);
+    }
+    const double scale = job.ac_scale;
+    for (uint32_t i = tid; i < nlags; i += kThreads) { lags[i] = (i < N) ? buf[i] * scale : 0.0; }
+    __syncthreads();
+}
+
+/* correctly rounded s^-1/2 (the reference calls glibc pow(s, -0.5), lpc.c:591) */
+__device__ __forceinline__ double inv_sqrt_cr(double s)
+{
+    const double y = 1.0 / sqrt(s);
+    const double t = y * y, tl = __fma_rn(y, y, -t);
+    const double q = s * t, ql = __fma_rn(s, t, -q);
+    const double e = ((1.0 - q) - ql) - s * tl;          /* 1 - s*y^2 to ~2^-100 */
+    return __fma_rn(0.5 * y, e, y);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Levinson-Durbin, all orders (lpc.c:379-441).  Executed by warp 0.  The reflection numerator is
+ * the reference's sequential dot product (same summation order), evaluated redundantly by all lanes.
+ * rows: if tri != NULL every order's vector a[0..m] is kept at tri + (m-1)(m+2)/2, else ping-pong
+ * in rowbuf and only the vector of order `stop` survives (returned pointer).
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t tri_offset(uint32_t m) { return (m - 1u) * (m + 2u) / 2u + (m - 1u); } /* row m has m+2 slots (a[0..m], trailing 0) */
+
+__device__ double *levinson_warp(const double *r, const uint32_t stop, double *tri, double *rowbuf, const uint32_t rowlen, double *err)
+{
+    const int lane = threadIdx.x & 31;
+    double *prev = tri ? tri + tri_offset(1) : rowbuf;
+    if (fabs(r[0]) < (double)FLT_EPSILON) {
+        for (uint32_t i = lane; i <= stop; i += 32) { err[i] = r[0]; }
+        /* all coefficient vectors are zero */
+        if (tri) { for (uint32_t i = lane; i < tri_offset(stop + 1u); i += 32) { tri[i] = 0.0; } }
+        else { for (uint32_t i = lane; i < rowlen; i += 32) { rowbuf[i] = 0.0; } }
+        __syncwarp();
+        return tri ? tri + tri_offset(stop) : rowbuf;
+    }
+    double e = r[0];
+    {
+        const double a1 = -r[1] / r[0];
+        const double e1 = e + r[1] * a1;
+        if (lane == 0) { prev[0] = 1.0; prev[1] = a1; prev[2] = 0.0; err[0] = e; err[1] = e1; }
+        e = e1;
+    }
+    __syncwarp();
+    for (uint32_t k = 1; k < stop; ++k) {
+        double acc = 0.0;
+        {
+            const double *rr = r + k + 1;
+            uint32_t i = 0;
+            for (; i + 4 <= k + 1; i += 4) {
+                const double m0 = prev[i] * rr[-(int)i], m1 = prev[i + 1] * rr[-(int)i - 1];
+                const double m2 = prev[i + 2] * rr[-(int)i - 2], m3 = prev[i + 3] * rr[-(int)i - 3];
+                acc += m0; acc += m1; acc += m2; acc += m3;
+            }
+            for (; i <= k; ++i) { acc += prev[i] * rr[-(int)i]; }
+        }
+        const double refl = acc / (-e);
+        const double e_next = e * (1.0 - refl * refl);
+        double *next = tri ? tri + tri_offset(k + 1u) : ((prev == rowbuf) ? rowbuf + rowlen : rowbuf);
+        for (uint32_t i = lane; i <= k + 1u; i += 32) { next[i] = prev[i] + refl * prev[k + 1u - i]; }
+        if (lane == 0) { next[k + 2u] = 0.0; err[k + 1u] = e_next; }
+        e = e_next;
+        prev = next;
+        __syncwarp();
+    }
+    return prev;
+}
+
+/* geometric-distribution entropy (srla_encoder.c:873-885) */
+__device__ __forceinline__ double geometric_entropy(double mean_abs, uint32_t bps)
+{
+    const double int_mean = mean_abs * (double)(1 << (bps - 1u));
+    const double rho = 1.0 / (1.0 + int_mean);
+    const double inv = 1.0 - rho;
+    if (mean_abs < 1e-16) { return 0.0; }
+    return -(inv * (log(inv) * 1.4426950408889634) + rho * (log(rho) * 1.4426950408889634)) / rho;
+}
+
+/* LTP pitch pick (lpc.c:1473-1555): serial, one thread */
+__device__ int detect_pitch(const double *r, uint32_t *period)
+{
+    const uint32_t lo = kLtpMinPeriod, hi = kLtpMaxPeriod;
+    uint32_t cand[20], ncand = 0, i = lo;
+    double best_peak = 0.0;
+    while (i < hi && ncand < 20) {
+        uint32_t start, end, arg = 0; double peak = 0.0;
+        for (start = i; start < hi; start++) { if (r[start - 1] < 0.0 && r[start] > 0.0) { break; } }
+        for (end = start + 1; end < hi - 1; end++) { if (r[end] > 0.0 && r[end + 1] < 0.0) { break; } }
+        for (uint32_t j = start; j <= end; j++) {
+            if (r[j] > r[j - 1] && r[j] > r[j + 1] && r[j] > peak) { arg = j; peak = r[j]; }
+        }
+        if (arg) { cand[ncand++] = arg; if (peak > best_peak) { best_peak = peak; } }
+        i = end + 1;
+    }
+    if (!ncand || best_peak < 0.1 * r[0]) { return 0; }
+    for (uint32_t k = 0; k < ncand; k++) { if (r[cand[k]] >= 0.9 * best_peak) { *period = cand[k]; return 1; } }
+    return 0;
+}
+
+/* 3-tap (or 1-tap) normal equations by Cholesky (lpc.c:573-631, 1558-1649) + 6-bit quantisation
+ * (srla_encoder.c:1032-1047).  returns 0 ok / 1 the reference would fail.  serial, one thread. */
+__device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, int32_t *qcoef)
+{
+    double A[3][3], inv_diag[3], sol[3];
+    uint32_t period = 0;
+    const int dim = (int)order;
+    *period_out = 0;
+    if (fabs(r[0]) <= (double)FLT_MIN) { return 0; }                 /* lpc.c:1602 */
+    if (!detect_pitch(r, &period)) { return 0; }
+    if (period < order / 2u + 1u) { return 0; }
+    r[0] *= (1.0 + 1e-5);
+    for (int i = 0; i < dim; i++) { for (int j = 0; j < dim; j++) { A[i][j] = r[(i > j) ? i - j : j - i]; } }
+    for (int i = 0; i < dim; i++) {
+        double s = A[i][i];
+        for (int k = i - 1; k >= 0; k--) { s -= A[i][k] * A[i][k]; }
+        if (s <= 0.0) { return 1; }
+        inv_diag[i] = inv_sqrt_cr(s);
+        for (int j = i + 1; j < dim; j++) {
+            s = A[i][j];
+            for (int k = i - 1; k >= 0; k--) { s -= A[i][k] * A[j][k]; }
+            A[j][i] = s * inv_diag[i];
+        }
+    }
+    const double *rhs = &r[period - order / 2u];
+    for (int i = 0; i < dim; i++) {
+        double s = rhs[i];
+        for (int j = i - 1; j >= 0; j--) { s -= A[i][j] * sol[j]; }
+        sol[i] = s * inv_diag[i];
+    }
+    for (int i = dim - 1; i >= 0; i--) {
+        double s = sol[i];
+        for (int j = i + 1; j < dim; j++) { s -= A[j][i] * sol[j]; }
+        sol[i] = s * inv_diag[i];
+    }
+    for (int i = 0; i < dim; i++) {
+        int32_t v = (int32_t)round_half_away(sol[i] * 32.0);
+        if (v < -32) { v = -32; }
+        if (v > 31) { v = 31; }
+        qcoef[dim - 1 - i] = v;
+    }
+    *period_out = period;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * analyse_kernel: one CTA per (job, candidate)
+ * ---------------------------------------------------------------------------------------------- */
+template <int BPT>
+__global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const AnalyseLayout L = make_analyse_layout(p.nmax, p.fft_max, p.max_order, p.ltp_order);
+    double   *region_d = reinterpret_cast<double *>(smem + L.region_off);
+    int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
+    int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;     /* 4 ints of front padding */
+    double   *lags     = reinterpret_cast<double *>(smem + L.lags_off);
+    double   *rowbuf   = reinterpret_cast<double *>(smem + L.row_off);
+    double   *err      = reinterpret_cast<double *>(smem + L.err_off);
+    int32_t  *coef_s   = reinterpret_cast<int32_t *>(smem + L.coef_off);
+    uint8_t  *ktab     = smem + L.ktab_off;
+    unsigned long long *red64 = reinterpret_cast<unsigned long long *>(smem + L.red_off);
+    uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
+    __shared__ int32_t  sh_i[16];
+    __shared__ uint32_t sh_u[16];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
+    const Job job = p.jobs[job_id];
+    const StreamDev st = p.streams[job.stream];
+    const uint32_t n = job.nsmpl, bps = p.bps, P = p.max_order;
+    const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+    CandOut *out = p.cand + (size_t)job_id * p.ncand + cand;
+    const uint32_t first_ch = (p.nch >= 2u) ? 2u : 0u;
+    const bool is_ms = (p.nch >= 2u) && (cand < 2u);
+
+    /* ---- load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) ---- */
+    int nz = 0;
+    for (uint32_t i = tid; i < n; i += kThreads) {
+        int32_t v;
+        if (is_ms) {
+            const int32_t l = asr32(load_sample(st, 0, job.offset + i), lshift);
+            const int32_t r = asr32(load_sample(st, 1, job.offset + i), lshift);
+            const int32_t side = (int32_t)((uint32_t)r - (uint32_t)l);
+            v = (cand == 1u) ? side : (int32_t)((uint32_t)l + (uint32_t)(side >> 1));
+        } else {
+            const int32_t raw = load_sample(st, cand - first_ch, job.offset + i);
+            nz |= raw;
+            v = asr32(raw, lshift);
+        }
+        region_i[i] = v;
+    }
+    nz = __syncthreads_or(nz);
+    if (n <= P) {                                   /* RAW block (srla_encoder.c:777-779): nothing to analyse */
+        if (tid == 0) { out->nonzero = (nz != 0); out->status = 0; out->total_bits = 0; out->residual_bits = 0; out->order = 0; }
+        return;
+    }
+
+    /* ---- pre-emphasis coefficient (srla_utility.c:214-257): r0, r1 as exact integers ---- */
+    {
+        long long r0 = 0, r1 = 0;
+        for (uint32_t i = tid; i < n; i += kThreads) {
+            const long long a = region_i[i];
+            r0 += a * a;
+            if (i + 1u < n) { r1 += a * (long long)region_i[i + 1u]; }
+        }
+        r0 = warp_sum_ll(r0); r1 = warp_sum_ll(r1);
+        if (lane == 0) { red64[2 * warp] = (unsigned long long)r0; red64[2 * warp + 1] = (unsigned long long)r1; }
+        __syncthreads();
+        if (tid == 0) {
+            long long s0 = 0, s1 = 0;
+            for (int w = 0; w < kWarps; ++w) { s0 += (long long)red64[2 * w]; s1 += (long long)red64[2 * w + 1]; }
+            int32_t c = 0;
+            if (s0 != 0) {
+                double d0 = (double)s0, d1 = (double)s1;
+                double v = (d1 / d0) * 16.0;
+                bool exact = (s0 < (1ll << 53));
+                if (!exact) {
+                    /* the reference's sequential double sums round above 2^53 (relative error
+                     * <= n * 2^-53 each); only a value this close to a rounding boundary can differ */
+                    const double frac = fabs(v) - floor(fabs(v));
+                    if (fabs(frac - 0.5) < 1e-7) {
+                        double q0 = 0.0, q1 = 0.0;
+                        for (uint32_t i = 0; i + 1u < n; ++i) { const double a = region_i[i], b = region_i[i + 1u]; q0 += a * a; q1 += a * b; }
+                        { const double a = region_i[n - 1u]; q0 += a * a; }
+                        v = (q1 / q0) * 16.0;
+                    }
+                }
+                c = (int32_t)round_half_away(v);
+                if (c < -16) { c = -16; }
+                if (c > 15) { c = 15; }
+            }
+            sh_i[0] = c;
+        }
+        __syncthreads();
+    }
+    const int32_t pre_coef = sh_i[0];
+    const int32_t pre_prev = region_i[0];
+    /* pre-emphasis (srla_utility.c:342-358), filter memory seeded with the first sample */
+    for (uint32_t i = tid; i < n; i += kThreads) {
+        const int32_t cur = region_i[i], prv = region_i[(i == 0u) ? 0u : i - 1u];
+        sig[i] = (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)pre_coef) >> 4));
+    }
+    if (tid < 4) { sig[-1 - tid] = 0; }
+    for (uint32_t i = n + tid; i < round_up_u32(n, 4) + 4u; i += kThreads) { sig[i] = 0; }
+    __syncthreads();
+
+    /* ---- long-term prediction (srla_encoder.c:1008-1058) ---- */
+    uint32_t ltp_period = 0;
+    if (p.ltp_order > 0u) {
+        welch_autocorr<BPT>(sig, n, region_d, lags, kLtpLags, job, p);
+        if (tid == 0) {
+            /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
+            for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
+            uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
+            const int rc = ltp_solve(lags, p.ltp_order, &period, q);
+            sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
+        }
+        __syncthreads();
+        ltp_period = sh_u[0];
+        if (sh_u[1]) { if (tid == 0) { out->status = 1; out->nonzero = (nz != 0); } return; }
+        if (ltp_period > 0u) {
+            /* srla_lpc_predict.c:267-294 */
+            const uint32_t half_order = p.ltp_order >> 1;
+            const int32_t c0 = sh_i[1], c1 = sh_i[2], c2 = sh_i[3];
+            for (uint32_t i = tid; i < n; i += kThreads) {
+                int32_t v = sig[i];
+                if (i >= ltp_period + half_order + 1u) {
+                    const int32_t *x = sig + (i - ltp_period - half_order);
+                    uint32_t acc = 16u;
+                    acc += (uint32_t)c0 * (uint32_t)x[0];
+                    if (p.ltp_order > 1u) { acc += (uint32_t)c1 * (uint32_t)x[1]; acc += (uint32_t)c2 * (uint32_t)x[2]; }
+                    v = (int32_t)((uint32_t)v - (uint32_t)((int32_t)acc >> 5));
+                }
+                region_i[i] = v;
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < n; i += kThreads) { sig[i] = region_i[i]; }
+            __syncthreads();
+        }
+    }
+
+    /* ---- LPC: autocorrelation, Levinson-Durbin, order choice, quantisation ---- */
+    uint32_t order = 0, rshift = 0;
+    if (P > 0u) {
+        welch_autocorr<BPT>(sig, n, region_d, lags, P + 1u, job, p);
+        const uint32_t tri_len = tri_offset(P + 1u);
+        double *tri = (tri_len * 8u <= L.region_bytes) ? region_d : nullptr;
+        const uint32_t rowlen = round_up_u32(P + 4u, 2);
+        if (warp == 0) {
+            if (lane == 0) { lags[0] *= (1.0 + 1e-5); }          /* ridge, lpc.c:483 */
+            __syncwarp();
+            levinson_warp(lags, P, tri, rowbuf, rowlen, err);
+        }
+        __syncthreads();
+        /* error variances x window gain (lpc.c:493), estimated bits per order (srla_encoder.c:934-957) */
+        double my_cost = (double)FLT_MAX; uint32_t my_arg = 0;
+        if (warp == 0) {
+            for (uint32_t k = 1u + lane; k <= P; k += 32) {
+                const double ev = err[k] * job.welch_gain;
+                const double mean_abs = 2.0 * sqrt(ev / 2.0);
+                double bits = geometric_entropy(mean_abs, bps) * (double)n;
+                bits += (double)(8u * k);
+                if (my_cost > bits) { my_cost = bits; my_arg = k; }
+            }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double oc = __shfl_xor_sync(0xffffffffu, my_cost, o);
+                const uint32_t oa = __shfl_xor_sync(0xffffffffu, my_arg, o);
+                if (oa != 0u && (my_arg == 0u || oc < my_cost || (oc == my_cost && oa < my_arg))) { my_cost = oc; my_arg = oa; }
+            }
+            if (lane == 0) { sh_u[2] = my_arg; }
+        }
+        __syncthreads();
+        order = sh_u[2];
+        if (p.diag) {
+            CandDiag *dg = p.diag + (size_t)job_id * p.ncand + cand;
+            for (uint32_t i = tid; i <= P; i += kThreads) { dg->autocorr[i] = lags[i]; dg->error_vars[i] = err[i] * job.welch_gain; }
+        }
+        if (order > 0u) {
+            const double *row;
+            if (tri) { row = tri + tri_offset(order); }
+            else {
+                if (warp == 0) { double *rp = levinson_warp(lags, order, nullptr, rowbuf, rowlen, err); if (lane == 0) { sh_u[3] = (uint32_t)(rp - rowbuf); } }
+                __syncthreads();
+                row = rowbuf + sh_u[3];
+            }
+            /* quantisation with error feedback from the tail (lpc.c:1341-1405), reversed for the FIR */
+            if (warp == 0) {
+                double peak = 0.0;
+                for (uint32_t i = lane; i < order; i += 32) { const double a = fabs(row[1u + i]); if (peak < a) { peak = a; } }
+                #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const double q = __shfl_xor_sync(0xffffffffu, peak, o); if (peak < q) { peak = q; } }
+                const uint32_t p4 = round_up_u32(order, 4);
+                if (peak <= 0.0078125) {
+                    for (uint32_t i = lane; i < p4; i += 32) { coef_s[i] = 0; }
+                    if (lane == 0) { sh_u[4] = 8u; }
+                } else {
+                    int exponent;
+                    (void)frexp(peak, &exponent);
+                    uint32_t rs = (uint32_t)(7 - exponent);
+                    if (rs >= 16u) { rs = 15u; }
+                    if (lane == 0) {
+                        const double scale = (double)(1u << rs);
+                        double carry = 0.0;
+                        for (uint32_t i = 0; i < p4 - order; ++i) { coef_s[i] = 0; }
+                        for (int i = (int)order - 1; i >= 0; --i) {
+                            carry += row[1 + i] * scale;
+                            int32_t v = (int32_t)round_half_away(carry);
+                            if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
+                            carry -= (double)v;
+                            /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
+                            coef_s[(p4 - order) + (order - 1u - (uint32_t)i)] = v;
+                        }
+                        sh_u[4] = rs;
+                    }
+                }
+            }
+            __syncthreads();
+            rshift = sh_u[4];
+            if (p.diag) {
+                CandDiag *dg = p.diag + (size_t)job_id * p.ncand + cand;
+                for (uint32_t i = tid; i < order; i += kThreads) { dg->lpc_double[i] = row[1u + i]; }
+            }
+            __syncthreads();          /* `row` may live in the region that the residual overwrites next */
+        }
+    }
+
+    /* ---- FIR residual (srla_lpc_predict.c:236-264), int32 wrapping ---- */
+    int32_t *res_s = region_i;
+    int32_t *res_g = p.residual ? p.residual + ((size_t)job_id * p.ncand + cand) * p.res_stride : nullptr;
+    if (order > 0u) {
+        const uint32_t p4 = round_up_u32(order, 4);
+        const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
+        const uint32_t groups = (n + 3u) >> 2;
+        const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
+        for (uint32_t g = tid; g < groups; g += kThreads) {
+            const uint32_t n0 = g << 2;
+            int32_t r[4];
+            if (n0 >= p4) {
+                uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
+                const int4 *xp = reinterpret_cast<const int4 *>(sig + n0 - p4);
+                int4 w0 = xp[0];
+                for (uint32_t m = 0; m < (p4 >> 2); ++m) {
+                    const int4 w1 = xp[m + 1u];
+                    const int4 cf = coef4[m];
+                    a0 += (uint32_t)cf.x * (uint32_t)w0.x + (uint32_t)cf.y * (uint32_t)w0.y + (uint32_t)cf.z * (uint32_t)w0.z + (uint32_t)cf.w * (uint32_t)w0.w;
+                    a1 += (uint32_t)cf.x * (uint32_t)w0.y + (uint32_t)cf.y * (uint32_t)w0.z + (uint32_t)cf.z * (uint32_t)w0.w + (uint32_t)cf.w * (uint32_t)w1.x;
+                    a2 += (uint32_t)cf.x * (uint32_t)w0.z + (uint32_t)cf.y * (uint32_t)w0.w + (uint32_t)cf.z * (uint32_t)w1.x + (uint32_t)cf.w * (uint32_t)w1.y;
+                    a3 += (uint32_t)cf.x * (uint32_t)w0.w + (uint32_t)cf.y * (uint32_t)w1.x + (uint32_t)cf.z * (uint32_t)w1.y + (uint32_t)cf.w * (uint32_t)w1.z;
+                    w0 = w1;
+                }
+                r[0] = (int32_t)((uint32_t)w0.x + (uint32_t)asr32((int32_t)a0, rshift));
+                r[1] = (int32_t)((uint32_t)w0.y + (uint32_t)asr32((int32_t)a1, rshift));
+                r[2] = (int32_t)((uint32_t)w0.z + (uint32_t)asr32((int32_t)a2, rshift));
+                r[3] = (int32_t)((uint32_t)w0.w + (uint32_t)asr32((int32_t)a3, rshift));
+            } else {
+                const int32_t *cf = coef_s + (p4 - order);
+                #pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t i = n0 + t;
+                    int32_t v = 0;
+                    if (i < n) {
+                        if (i == 0u) { v = sig[0]; }
+                        else if (i < order) { v = (int32_t)((uint32_t)sig[i] - (uint32_t)sig[i - 1u]); }
+                        else {
+                            uint32_t acc = half;
+                            for (uint32_t j = 0; j < order; ++j) { acc += (uint32_t)cf[j] * (uint32_t)sig[i - order + j]; }
+                            v = (int32_t)((uint32_t)sig[i] + (uint32_t)asr32((int32_t)acc, rshift));
+                        }
+                    }
+                    r[t] = v;
+                }
+            }
+            *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+        }
+    } else {
+        for (uint32_t i = tid; i < n; i += kThreads) { res_s[i] = sig[i]; }
+    }
+    __syncthreads();
+    if (res_g) { for (uint32_t i = tid; i < n; i += kThreads) { res_g[i] = res_s[i]; } }
+
+    /* ---- residual coder search (srla_coder.c:349-483) ---- */
+    uint32_t max_porder = 0;
+    while (max_porder < (uint32_t)kLog2MaxParts && (n % (2u << max_porder)) == 0u) { max_porder++; }
+    const uint32_t nparts = 1u << max_porder, per = n >> max_porder;
+    uint32_t *u = reinterpret_cast<uint32_t *>(region_i);
+    double *mean = reinterpret_cast<double *>(smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16));   /* heap layout: level l at (1<<l)-1 */
+    uint32_t any = 0;
+    for (uint32_t i = tid; i < n; i += kThreads) { const uint32_t v = zigzag32(res_s[i]); u[i] = v; any |= v; }
+    any = (uint32_t)__syncthreads_or((int)(any != 0u));
+    uint32_t code_type, best_porder = 0, residual_bits;
+    if (!any) {
+        code_type = kCodeAllZero; residual_bits = 2u;
+    } else {
+        /* finest partition means: exact integer sums / per */
+        if (per <= 32u) {
+            for (uint32_t q = tid; q < nparts; q += kThreads) {
+                unsigned long long s = 0;
+                const uint32_t *up = u + q * per;
+                for (uint32_t i = 0; i < per; ++i) { s += up[i]; }
+                mean[(nparts - 1u) + q] = (double)s / (double)per;
+            }
+        } else {
+            for (uint32_t q = warp; q < nparts; q += kWarps) {
+                unsigned long long s = 0;
+                const uint32_t *up = u + q * per;
+                for (uint32_t i = lane; i < per; i += 32) { s += up[i]; }
+                s = (unsigned long long)warp_sum_ll((long long)s);
+                if (lane == 0) { mean[(nparts - 1u) + q] = (double)s / (double)per; }
+            }
+        }
+        __syncthreads();
+        for (int lvl = (int)max_porder - 1; lvl >= 0; --lvl) {
+            const uint32_t cnt = 1u << lvl, base = cnt - 1u, child = 2u * cnt - 1u;
+            for (uint32_t q = tid; q < cnt; q += kThreads) { mean[base + q] = (mean[child + 2u * q] + mean[child + 2u * q + 1u]) / 2.0; }
+            __syncthreads();
+        }
+        code_type = (mean[0] < 2.0) ? kCodeRice : kCodeRecursiveRice;
+        /* coding parameter of every partition at every level */
+        for (uint32_t e = tid; e < 2u * nparts - 1u; e += kThreads) {
+            const double m = mean[e];
+            uint32_t k;
+            if (code_type == kCodeRice) {
+                k = 0;
+                #pragma unroll 1
+                for (int j = 1; j < 32; ++j) { if (m >= __ldg(p.rice_threshold + j)) { k = (uint32_t)j; } }   /* srla_coder.c:262-287 via host-libm thresholds */
+            } else {
+                const double g = 0.66794162356 * (1.0 + m);                                                 /* srla_coder.c:298-324 */
+                const uint32_t golomb = (uint32_t)((1.0 > g) ? 1.0 : g);
+                k = 31u - (uint32_t)__clz((int)golomb);
+            }
+            ktab[e] = (uint8_t)k;
+        }
+        __syncthreads();
+        /* bits of every partition order */
+        uint32_t acc[kLog2MaxParts + 1];
+        #pragma unroll
+        for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = 0; }
+        const bool per_pow2 = (per & (per - 1u)) == 0u;
+        const uint32_t per_shift = 31u - (uint32_t)__clz((int)per);
+        for (uint32_t i = tid; i < n; i += kThreads) {
+            const uint32_t v = u[i];
+            const uint32_t q = per_pow2 ? (i >> per_shift) : (i / per);
+            #pragma unroll
+            for (int l = 0; l <= kLog2MaxParts; ++l) {
+                if ((uint32_t)l <= max_porder) {
+                    const uint32_t k = ktab[((1u << l) - 1u) + (q >> (max_porder - (uint32_t)l))];
+                    if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
+                    else {
+                        const uint32_t k1 = k + 1u;
+                        const int32_t over = (int32_t)v - (int32_t)(1u << k1);
+                        acc[l] += (k1 + 1u) + ((uint32_t)((over > 0) ? over : 0) >> k);
+                    }
+                }
+            }
+        }
+        #pragma unroll
+        for (int l = 0; l <= kLog2MaxParts; ++l) {
+            if ((uint32_t)l <= max_porder) {
+                const uint32_t cnt = 1u << l, base = cnt - 1u;
+                for (uint32_t q = tid; q < cnt; q += kThreads) {
+                    const uint32_t k = ktab[base + q];
+                    acc[l] += (q == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)ktab[base + q - 1u]) + 1u);
+                }
+            }
+        }
+        #pragma unroll
+        for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = warp_sum_u32(acc[l]); }
+        if (lane == 0) {
+            #pragma unroll
+            for (int l = 0; l <= kLog2MaxParts; ++l) { red32[warp * 12 + l] = acc[l]; }
+        }
+        __syncthreads();
+        uint32_t best_bits = 0xffffffffu;
+        for (uint32_t l = 0; l <= max_porder; ++l) {
+            uint32_t bits = (uint32_t)kLog2MaxParts;
+            #pragma unroll
+            for (int w = 0; w < kWarps; ++w) { bits += red32[w * 12 + l]; }
+            if (bits < best_bits) { best_bits = bits; best_porder = l; }
+        }
+        residual_bits = best_bits + 2u;
+        for (uint32_t q = tid; q < (1u << best_porder); q += kThreads) { out->kparam[q] = ktab[((1u << best_porder) - 1u) + q]; }
+    }
+
+    /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */
+    if (warp == 0) {
+        uint32_t plain_bits = 0, sum_bits = 0, bad = 0;
+        const uint32_t p4 = round_up_u32(order, 4);
+        const int32_t *cf = coef_s + (p4 - order);
+        for (uint32_t i = lane; i < order; i += 32) {
+            const int32_t c = cf[i];
+            const uint32_t len = __ldg(p.huff_len + zigzag32(c));
+            plain_bits += len;
+            if (i == 0u) { sum_bits += len; }
+            else {
+                const uint32_t sym = zigzag32(c + cf[i - 1u]);
+                if (sym >= 256u) { bad = 1; } else { sum_bits += __ldg(p.huff_len + 256 + sym); }
+            }
+            out->coef[i] = (int16_t)c;
+        }
+        plain_bits = warp_sum_u32(plain_bits); sum_bits = warp_sum_u32(sum_bits); bad = warp_sum_u32(bad);
+        if (lane == 0) {
+            uint32_t use_sum = 0, coef_bits = 0;
+            if (order > 0u) {
+                /* the reference's early exits are equivalent to: every symbol valid and the summed form strictly shorter */
+                use_sum = (!bad && (order == 1u || sum_bits < plain_bits)) ? 1u : 0u;
+                coef_bits = use_sum ? sum_bits : plain_bits;
+            }
+            uint32_t bits = residual_bits;
+            bits += bps + 1u + 5u;
+            bits += 8u + 4u + 1u;
+            bits += coef_bits;
+            bits += 1u;
+            if (ltp_period > 0u) { bits += 1u + 8u + p.ltp_order * 6u; }
+            out->pre_coef = pre_coef; out->pre_prev = pre_prev;
+            out->order = order; out->rshift = rshift; out->use_sum = use_sum; out->coef_bits = coef_bits;
+            out->ltp_period = ltp_period;
+            out->ltp_coef[0] = (ltp_period > 0u) ? sh_i[1] : 0;
+            out->ltp_coef[1] = (ltp_period > 0u) ? sh_i[2] : 0;
+            out->ltp_coef[2] = (ltp_period > 0u) ? sh_i[3] : 0;
+            out->code_type = code_type; out->porder = best_porder;
+            out->residual_bits = residual_bits; out->total_bits = bits;
+            out->nonzero = (nz != 0); out->status = 0;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * decide_kernel: one thread per job (srla_encoder.c:766-796, 1276-1327, 1477-1546, 1608-1611)
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void decide_kernel(const __grid_constant__ LaunchParams p)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= p.num_jobs) { return; }
+    const Job job = p.jobs[j];
+    const CandOut *c = p.cand + (size_t)j * p.ncand;
+    JobOut o;
+    const uint32_t nch = p.nch, n = job.nsmpl, first_ch = (nch >= 2u) ? 2u : 0u;
+    const uint32_t raw_bits = p.bps * n * nch;
+    o.status = 0; o.method = 0; o.pad = 0; o.out_offset = 0;
+    for (uint32_t ch = 0; ch < (uint32_t)kMaxChannels; ++ch) { o.cand_of_channel[ch] = first_ch + ch; }
+    uint32_t type = kBlockCompress;
+    if (n <= p.max_order) { type = kBlockRaw; }
+    else {
+        uint32_t nz = 0;
+        for (uint32_t ch = 0; ch < nch; ++ch) { nz |= c[first_ch + ch].nonzero; }
+        if (!nz) { type = kBlockSilent; }
+    }
+    uint32_t est_type = type;
+    uint32_t emitted_bits = 0, payload_bits = 0;
+    if (type == kBlockCompress) {
+        for (uint32_t k = 0; k < p.ncand; ++k) { if (c[k].status) { o.status = 1; } }
+        if (nch >= 2u) {
+            const uint32_t M = c[0].total_bits, S = c[1].total_bits, Lb = c[2].total_bits, R = c[3].total_bits;
+            const uint32_t cost[4] = { Lb + R, M + S, Lb + S, S + R };
+            uint32_t best = 0;
+            for (uint32_t m = 1; m < 4; ++m) { if (cost[best] > cost[m]) { best = m; } }
+            o.method = best;
+            if (best == 1u) { o.cand_of_channel[0] = 0; o.cand_of_channel[1] = 1; }
+            else if (best == 2u) { o.cand_of_channel[1] = 1; }
+            else if (best == 3u) { o.cand_of_channel[0] = 1; }
+            payload_bits = cost[best];
+        } else {
+            payload_bits = c[0].total_bits;
+        }
+        payload_bits = (payload_bits + 2u + 7u) & ~7u;
+        emitted_bits = 2u;
+        for (uint32_t ch = 0; ch < nch; ++ch) { emitted_bits += c[o.cand_of_channel[ch]].total_bits; }
+        emitted_bits = (emitted_bits + 7u) & ~7u;
+        if (emitted_bits >= raw_bits) { type = kBlockRaw; }
+        if (payload_bits >= raw_bits) { est_type = kBlockRaw; }
+    }
+    o.type = type;
+    o.bytes = 11u + ((type == kBlockCompress) ? emitted_bits / 8u : (type == kBlockRaw) ? raw_bits / 8u : 0u);
+    o.estimate_bytes = 11u + ((est_type == kBlockCompress) ? payload_bits / 8u : (est_type == kBlockRaw) ? raw_bits / 8u : 0u);
+    p.jobout[j] = o;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * scan_kernel: single CTA; block offsets in job order, 30-byte stream headers in front of the
+ * first block of every stream.  running[0] carries the offset across launches.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ LaunchParams p)
+{
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { carry = p.running[0]; }
+    __syncthreads();
+    for (uint32_t base = 0; base < p.num_jobs; base += 1024u) {
+        const uint32_t j = base + tid;
+        unsigned long long mine = 0, hdr = 0;
+        if (j < p.num_jobs) {
+            hdr = (p.emit_stream_header && (p.jobs[j].flags & kJobFirstOfStream)) ? 30ull : 0ull;
+            mine = (unsigned long long)p.jobout[j].bytes + hdr;
+        }
+        unsigned long long x = mine;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) { x += y; } }
+        if (lane == 31) { warp_tot[warp] = x; }
+        __syncthreads();
+        unsigned long long pre = carry;
+        for (int w = 0; w < warp; ++w) { pre += warp_tot[w]; }
+        if (j < p.num_jobs) {
+            const unsigned long long start = pre + x - mine;     /* where the (optional) stream header begins */
+            p.jobout[j].out_offset = start + hdr;
+            if (p.jobs[j].flags & kJobFirstOfStream) { p.stream_begin[p.jobs[j].stream] = start; }
+        }
+        __syncthreads();
+        if (tid == 1023) { carry = pre + x; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        p.running[0] = carry;
+        if (carry > p.out_capacity) { p.running[1] = 1ull; }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * emit_kernel: one CTA per job.  The block is assembled in shared memory as big-endian 32-bit
+ * words (bit 31 of word 0 is the first bit of the block), then copied out.
+ * ---------------------------------------------------------------------------------------------- */
+struct BitCursor {
+    uint32_t *words;          /* staging */
+    uint32_t lo_excl, hi_excl;/* words in [lo_excl, hi_excl) are owned exclusively by this thread */
+    uint32_t cur;             /* word index being accumulated */
+    uint32_t acc;             /* bits of that word */
+    __device__ __forceinline__ void init(uint32_t *w, uint32_t start_bit, uint32_t end_bit)
+    {
+        words = w; lo_excl = (start_bit + 31u) >> 5; hi_excl = end_bit >> 5; cur = start_bit >> 5; acc = 0;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (acc) {
+            if (cur >= lo_excl && cur < hi_excl) { words[cur] = acc; } else { atomicOr(words + cur, acc); }
+        }
+    }
+    __device__ __forceinline__ void seek_word(uint32_t w) { if (w != cur) { flush(); cur = w; acc = 0; } }
+    /* put the low nbits of value (nbits <= 32) at absolute bit position pos */
+    __device__ __forceinline__ void put(uint32_t pos, uint32_t value, uint32_t nbits)
+    {
+        if (nbits == 0u) { return; }
+        if (nbits < 32u) { value &= (1u << nbits) - 1u; }
+        const uint32_t w = pos >> 5, off = pos & 31u;
+        seek_word(w);
+        const uint32_t room = 32u - off;
+        if (nbits <= room) { acc |= value << (room - nbits); }
+        else {
+            acc |= value >> (nbits - room);
+            seek_word(w + 1u);
+            acc |= value << (32u - (nbits - room));
+        }
+    }
+};
+
+/* length in bits of the code of u with parameter k (srla_coder.c:165-190) */
+__device__ __forceinline__ uint32_t code_len(uint32_t u, uint32_t k, uint32_t code_type)
+{
+    if (code_type == kCodeRice) { return 1u + k + (u >> k); }
+    const uint32_t k1 = k + 1u, pivot = 1u << k1;
+    return (u < pivot) ? (k1 + 1u) : (2u + ((u - pivot) >> k) + k);
+}
+__device__ __forceinline__ uint32_t emit_code(BitCursor &bc, uint32_t pos, uint32_t u, uint32_t k, uint32_t code_type)
+{
+    if (code_type == kCodeRice) {
+        const uint32_t q = u >> k;
+        bc.put(pos + q, (1u << k) | (u & ((1u << k) - 1u)), k + 1u);
+        return q + 1u + k;
+    }
+    const uint32_t k1 = k + 1u, pivot = 1u << k1;
+    if (u < pivot) { bc.put(pos, pivot | u, k1 + 1u); return k1 + 1u; }
+    const uint32_t z = u - pivot, q = 1u + (z >> k);
+    bc.put(pos + q, (1u << k) | (z & ((1u << k) - 1u)), k + 1u);
+    return q + 1u + k;
+}
+
+__global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *words = reinterpret_cast<uint32_t *>(smem);
+    __shared__ uint32_t scan_scratch[kWarps + 1];
+    __shared__ uint32_t fl_lo[kWarps], fl_hi[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t j = blockIdx.x;
+    const Job job = p.jobs[j];
+    const JobOut jo = p.jobout[j];
+    const StreamDev st = p.streams[job.stream];
+    const uint32_t n = job.nsmpl, nch = p.nch, bps = p.bps;
+    const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+    const uint32_t nbytes = jo.bytes;
+    const bool fits = (jo.out_offset + nbytes <= p.out_capacity) && (nbytes <= p.emit_smem_bytes) && (jo.status == 0u);
+
+    /* stream header (srla_encoder.c:85-165) */
+    if (p.emit_stream_header && (job.flags & kJobFirstOfStream) && tid == 0 && jo.out_offset >= 30ull && jo.out_offset <= p.out_capacity) {
+        uint8_t *h = p.out + (jo.out_offset - 30ull);
+        const uint32_t ns = st.num_samples;
+        h[0] = '1'; h[1] = '2'; h[2] = '4'; h[3] = '9';
+        h[4] = 0; h[5] = 0; h[6] = 0; h[7] = 10;
+        h[8] = 0; h[9] = 0; h[10] = 0; h[11] = 18;
+        h[12] = (uint8_t)(nch >> 8); h[13] = (uint8_t)nch;
+        h[14] = (uint8_t)(ns >> 24); h[15] = (uint8_t)(ns >> 16); h[16] = (uint8_t)(ns >> 8); h[17] = (uint8_t)ns;
+        h[18] = (uint8_t)(p.sampling_rate >> 24); h[19] = (uint8_t)(p.sampling_rate >> 16); h[20] = (uint8_t)(p.sampling_rate >> 8); h[21] = (uint8_t)p.sampling_rate;
+        h[22] = (uint8_t)(bps >> 8); h[23] = (uint8_t)bps;
+        h[24] = (uint8_t)lshift;
+        h[25] = (uint8_t)(p.max_block >> 24); h[26] = (uint8_t)(p.max_block >> 16); h[27] = (uint8_t)(p.max_block >> 8); h[28] = (uint8_t)p.max_block;
+        h[29] = (uint8_t)p.preset;
+    }
+    if (!fits) { return; }
+
+    const uint32_t nwords = (nbytes + 3u) >> 2;
+    for (uint32_t w = tid; w < nwords + 1u; w += kThreads) { words[w] = 0u; }
+    __syncthreads();
+
+    if (jo.type == kBlockRaw) {
+        /* interleaved big-endian zig-zag samples of the UNSHIFTED input (srla_encoder.c:799-858) */
+        const uint32_t bytes_per = bps >> 3;
+        uint8_t *bytes = smem;      /* staged as plain bytes, converted below */
+        (void)bytes;
+        for (uint32_t e = tid; e < n * nch; e += kThreads) {
+            const uint32_t i = e / nch, ch = e % nch;
+            const uint32_t v = zigzag32(load_sample(st, ch, job.offset + i));
+            const uint32_t bytepos = 11u + e * bytes_per;
+            for (uint32_t b = 0; b < bytes_per; ++b) {
+                const uint32_t byte = (v >> (8u * (bytes_per - 1u - b))) & 0xffu;
+                const uint32_t at = bytepos + b;
+                atomicOr(words + (at >> 2), byte << (24u - 8u * (at & 3u)));
+            }
+        }
+    } else if (jo.type == kBlockCompress) {
+        const CandOut *cands = p.cand + (size_t)j * p.ncand;
+        const uint32_t base_bit = 88u;
+        /* section 1: method, pre-emphasis state (srla_encoder.c:1369-1386) */
+        if (tid == 0) {
+            BitCursor bc; bc.init(words, 0u, 0u);
+            uint32_t pos = base_bit;
+            bc.put(pos, jo.method, 2u); pos += 2u;
+            for (uint32_t ch = 0; ch < nch; ++ch) {
+                const CandOut &c = cands[jo.cand_of_channel[ch]];
+                /* bps + 1 may be 33 bits only for bps 32 which the format's raw blocks exclude */
+                bc.put(pos, zigzag32(c.pre_prev), bps + 1u); pos += bps + 1u;
+                bc.put(pos, zigzag32(c.pre_coef), 5u); pos += 5u;
+            }
+            bc.flush();
+        }
+        uint32_t pos = base_bit + 2u + nch * (bps + 1u + 5u);
+        /* section 2: LPC parameters, Huffman-coded coefficients (srla_encoder.c:1388-1419) */
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            const CandOut &c = cands[jo.cand_of_channel[ch]];
+            const uint32_t order = c.order;
+            if (tid == 0) {
+                BitCursor bc; bc.init(words, 0u, 0u);
+                bc.put(pos, order, 8u); bc.put(pos + 8u, c.rshift, 4u); bc.put(pos + 12u, c.use_sum, 1u);
+                bc.flush();
+            }
+            uint32_t code = 0, len = 0;
+            if ((uint32_t)tid < order) {
+                const int32_t cf = c.coef[tid];
+                uint32_t sym, table = 0;
+                if (tid == 0 || !c.use_sum) { sym = zigzag32(cf); } else { sym = zigzag32(cf + (int32_t)c.coef[tid - 1]); table = 256u; }
+                code = __ldg(p.huff_code + table + sym); len = __ldg(p.huff_len + table + sym);
+            }
+            uint32_t total;
+            const uint32_t incl = block_scan_inclusive(len, scan_scratch, &total);
+            if (len) { BitCursor bc; bc.init(words, 0u, 0u); bc.put(pos + 13u + incl - len, code, len); bc.flush(); }
+            pos += 13u + total;
+        }
+        /* section 3: LTP parameters (srla_encoder.c:1421-1438) */
+        if (tid == 0) {
+            BitCursor bc; bc.init(words, 0u, 0u);
+            uint32_t q = pos;
+            for (uint32_t ch = 0; ch < nch; ++ch) {
+                const CandOut &c = cands[jo.cand_of_channel[ch]];
+                bc.put(q, c.ltp_period != 0u, 1u); q += 1u;
+                if (c.ltp_period) {
+                    bc.put(q, (p.ltp_order - 1u) / 2u, 1u); q += 1u;
+                    bc.put(q, c.ltp_period - (uint32_t)kLtpMinPeriod, 8u); q += 8u;
+                    for (uint32_t t = 0; t < p.ltp_order; ++t) { bc.put(q, zigzag32(c.ltp_coef[t]), 6u); q += 6u; }
+                }
+            }
+            bc.flush();
+        }
+        for (uint32_t ch = 0; ch < nch; ++ch) { const CandOut &c = cands[jo.cand_of_channel[ch]]; pos += 1u + (c.ltp_period ? (1u + 8u + 6u * p.ltp_order) : 0u); }
+        __syncthreads();
+        /* section 4: residual codes (srla_coder.c:486-595) */
+        const uint32_t chunk = (n + kThreads - 1u) / kThreads;
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            const uint32_t cidx = jo.cand_of_channel[ch];
+            const CandOut &c = cands[cidx];
+            const uint32_t code_type = c.code_type;
+            if (tid == 0) {
+                BitCursor bc; bc.init(words, 0u, 0u);
+                bc.put(pos, code_type, 2u);
+                if (code_type != kCodeAllZero) { bc.put(pos + 2u, c.porder, 10u); }
+                bc.flush();
+            }
+            if (code_type == kCodeAllZero) { pos += 2u; __syncthreads(); continue; }
+            const int32_t *res = p.residual + ((size_t)j * p.ncand + cidx) * p.res_stride;
+            const uint32_t plen = n >> c.porder;
+            const uint32_t i0 = (uint32_t)tid * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
+            /* pass 1: bits of this thread's samples (+ parameter fields of partitions starting here) */
+            uint32_t mybits = 0;
+            if (i0 < n) {
+                uint32_t part = i0 / plen, next_start = part * plen;
+                if (next_start < i0) { part++; next_start += plen; }
+                uint32_t cur_part = i0 / plen;
+                uint32_t k = c.kparam[cur_part];
+                for (uint32_t i = i0; i < i1; ++i) {
+                    if (i == next_start) {
+                        cur_part = part; k = c.kparam[cur_part];
+                        mybits += (cur_part == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)c.kparam[cur_part - 1u]) + 1u);
+                        part++; next_start += plen;
+                    }
+                    mybits += code_len(zigzag32(__ldg(res + i)), k, code_type);
+                }
+            }
+            uint32_t total;
+            const uint32_t incl = block_scan_inclusive(mybits, scan_scratch, &total);
+            /* pass 2: emit */
+            if (i0 < n && mybits) {
+                const uint32_t start = pos + 12u + incl - mybits;
+                BitCursor bc; bc.init(words, start, start + mybits);
+                uint32_t at = start;
+                uint32_t part = i0 / plen, next_start = part * plen;
+                if (next_start < i0) { part++; next_start += plen; }
+                uint32_t cur_part = i0 / plen;
+                uint32_t k = c.kparam[cur_part];
+                for (uint32_t i = i0; i < i1; ++i) {
+                    if (i == next_start) {
+                        cur_part = part; k = c.kparam[cur_part];
+                        if (cur_part == 0u) { bc.put(at, k, 5u); at += 5u; }
+                        else { const uint32_t run = zigzag32((int32_t)k - (int32_t)c.kparam[cur_part - 1u]); bc.put(at + run, 1u, 1u); at += run + 1u; }
+                        part++; next_start += plen;
+                    }
+                    at += emit_code(bc, at, zigzag32(__ldg(res + i)), k, code_type);
+                }
+                bc.flush();
+            }
+            pos += 12u + total;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    /* block header (srla_encoder.c:1585-1595, 1629-1636): sync, size, checksum, type, nsmpl */
+    if (tid == 0) {
+        const uint32_t size_field = nbytes - 11u + 5u;
+        words[0] = 0xFFFF0000u | (size_field >> 16);
+        words[1] = (size_field << 16);                       /* checksum patched below */
+        words[2] |= (jo.type << 24) | ((n & 0xffffu) << 8);
+    }
+    __syncthreads();
+    /* Fletcher-16 over bytes [8, nbytes) (srla_utility.c:36-60): lo = sum d, hi = sum (L - i) d, mod 255 */
+    {
+        const uint32_t Lb = nbytes - 8u;
+        uint32_t lo = 0, hi = 0;
+        for (uint32_t i = tid; i < Lb; i += kThreads) {
+            const uint32_t at = 8u + i;
+            const uint32_t d = (words[at >> 2] >> (24u - 8u * (at & 3u))) & 0xffu;
+            lo += d;
+            hi = (hi + ((Lb - i) % 255u) * d) % 255u;
+        }
+        lo %= 255u;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+        if (lane == 0) { fl_lo[warp] = lo % 255u; fl_hi[warp] = hi % 255u; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0, b = 0;
+            for (int w = 0; w < kWarps; ++w) { a += fl_lo[w]; b += fl_hi[w]; }
+            a %= 255u; b %= 255u;
+            words[1] |= (b << 8) | a;
+        }
+        __syncthreads();
+    }
+    /* copy out: byte b of the block = big-endian byte b of the staging words */
+    {
+        uint8_t *dst = p.out + jo.out_offset;
+        const uint32_t mis = (uint32_t)((4u - (reinterpret_cast<unsigned long long>(dst) & 3ull)) & 3ull);
+        const uint32_t head = (mis < nbytes) ? mis : nbytes;
+        const uint32_t body_words = (nbytes - head) >> 2;
+        const uint32_t tail_at = head + (body_words << 2);
+        if ((uint32_t)tid < head) { dst[tid] = (uint8_t)(words[tid >> 2] >> (24u - 8u * (tid & 3u))); }
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint32_t w = tid; w < body_words; w += kThreads) {
+            const uint32_t s = head + (w << 2);
+            const uint32_t be = __funnelshift_l(words[(s >> 2) + 1u], words[s >> 2], 8u * (s & 3u));
+            dst32[w] = __byte_perm(be, 0u, 0x0123);
+        }
+        if ((uint32_t)tid < nbytes - tail_at) { const uint32_t at = tail_at + tid; dst[at] = (uint8_t)(words[at >> 2] >> (24u - 8u * (at & 3u))); }
+    }
+    /* statistics */
+    if (p.stats && tid == 0) {
+        atomicAdd(p.stats + 256 + 4 + jo.type, 1u);
+        if (jo.type == kBlockCompress) {
+            atomicAdd(p.stats + 256 + jo.method, 1u);
+            const CandOut *cands = p.cand + (size_t)j * p.ncand;
+            for (uint32_t ch = 0; ch < nch; ++ch) { atomicAdd(p.stats + (cands[jo.cand_of_channel[ch]].order & 255u), 1u); }
+        }
+    }
+}
+
+} // namespace srla
+#endif

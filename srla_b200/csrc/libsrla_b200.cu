@@ -1,0 +1,915 @@
+/*
+ * libsrla_b200.cu -- host runtime and C ABI of the B200-native SRLA encode path.
+ *
+ * Exports the encoder half of the reference's public API (include/srla_encoder.h) plus the batch
+ * extension declared in include/srla_b200.h.  All signal processing runs in the CUDA kernels of
+ * kernels.cuh; the host side validates arguments exactly like the reference, builds the job list
+ * (one job per block), launches analyse -> decide -> scan -> emit per batch, and -- in variable-block
+ * mode -- runs the reference's shortest-path block division (srla_encoder.c:249-424) on the exact
+ * candidate sizes the GPU computed.
+ *
+ * There is deliberately no CPU encode path in this file: without a CUDA device Create() fails.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/srla_b200.h"
+#include "host_tables.h"
+#include "kernels.cuh"
+
+using namespace srla;
+
+namespace {
+
+const uint32_t kPresetMaxOrder[SRLA_NUM_PARAMETER_PRESETS] = { 0, 8, 16, 32, 64, 128, 255 };   /* srla_internal.c:30-38 */
+const uint32_t kEncoderMagic = 0x53424C41u;
+thread_local int g_device = -1;
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            std::fprintf(stderr, "[srla_b200] %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(e_), \
+                         __FILE__, __LINE__);                                                          \
+            return false;                                                                              \
+        }                                                                                              \
+    } while (0)
+
+/* growable device / pinned-host buffers */
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    bool reserve(size_t bytes)
+    {
+        if (bytes <= cap) { return true; }
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] cudaMalloc(%zu) failed\n", want); p = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) { cudaFree(p); } p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    bool reserve(size_t bytes)
+    {
+        if (bytes <= cap) { return true; }
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] cudaMallocHost(%zu) failed\n", want); p = nullptr; return false; }
+        cap = want;
+        return true;
+    }
+    void release() { if (p) { cudaFreeHost(p); } p = nullptr; cap = 0; }
+};
+
+struct DeviceCtx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_analyse, ev_emit;
+    size_t ev_used = 0;
+    /* tables */
+    DevBuf tw_complex, tw_real, rice_thr, huff_code, huff_len;
+    uint32_t tw_c_off[20], tw_r_off[20];
+    /* work */
+    DevBuf streams, jobs, cand, diag, jobout, residual, misc, stream_begin, pcm, out;
+    PinBuf h_jobs, h_small, h_jobout, h_result;
+    int max_smem_optin = 0;
+    int num_sms = 0;
+};
+
+} // namespace
+
+struct SRLAEncoder {
+    uint32_t magic;
+    struct SRLAEncoderConfig config;
+    struct SRLAEncodeParameter param;
+    int set_parameter;
+    uint32_t max_order;
+    uint8_t offset_lshift;           /* header.offset_lshift of the reference handle */
+    uint8_t alloced_by_own;
+    void *work;
+    DeviceCtx *ctx;
+    struct SRLAB200Stats stats;
+};
+
+namespace {
+
+bool ctx_init(DeviceCtx *c)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        std::fprintf(stderr, "[srla_b200] no CUDA device: the SRLA B200 encode path has no CPU fallback\n");
+        return false;
+    }
+    if (g_device >= 0) { CU_TRY(cudaSetDevice(g_device)); }
+    CU_TRY(cudaGetDevice(&c->device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10) {
+        std::fprintf(stderr, "[srla_b200] device %d is sm_%d%d; this library is built for sm_100a only\n", c->device, prop.major, prop.minor);
+        return false;
+    }
+    c->num_sms = prop.multiProcessorCount;
+    CU_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU_TRY(cudaEventCreate(&c->ev_begin));
+    CU_TRY(cudaEventCreate(&c->ev_end));
+
+    /* host-libm tables (host_tables.h) */
+    std::vector<host::Cx> tab; std::vector<uint32_t> off;
+    const int max_lg = 14;
+    host::build_complex_twiddles(max_lg, tab, off);
+    if (!c->tw_complex.reserve(tab.size() * sizeof(host::Cx))) { return false; }
+    CU_TRY(cudaMemcpy(c->tw_complex.p, tab.data(), tab.size() * sizeof(host::Cx), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 20; i++) { c->tw_c_off[i] = off[i]; }
+    if (!host::build_real_twiddles(max_lg, tab, off)) {
+        std::fprintf(stderr, "[srla_b200] host libm: inverse real-FFT twiddles are not the conjugate of the forward ones\n");
+        return false;
+    }
+    if (!c->tw_real.reserve(tab.size() * sizeof(host::Cx))) { return false; }
+    CU_TRY(cudaMemcpy(c->tw_real.p, tab.data(), tab.size() * sizeof(host::Cx), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 20; i++) { c->tw_r_off[i] = off[i]; }
+    double thr[32];
+    host::build_rice_thresholds(thr);
+    if (!c->rice_thr.reserve(sizeof(thr))) { return false; }
+    CU_TRY(cudaMemcpy(c->rice_thr.p, thr, sizeof(thr), cudaMemcpyHostToDevice));
+    host::HuffTable plain, summed;
+    host::build_format_huffman(plain, summed);
+    uint32_t codes[512]; uint8_t lens[512];
+    for (int i = 0; i < 256; i++) { codes[i] = plain.code[i]; lens[i] = plain.len[i]; codes[256 + i] = summed.code[i]; lens[256 + i] = summed.len[i]; }
+    if (!c->huff_code.reserve(sizeof(codes)) || !c->huff_len.reserve(sizeof(lens))) { return false; }
+    CU_TRY(cudaMemcpy(c->huff_code.p, codes, sizeof(codes), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(c->huff_len.p, lens, sizeof(lens), cudaMemcpyHostToDevice));
+    if (!c->misc.reserve(2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t) + 64)) { return false; }
+    return true;
+}
+
+void ctx_destroy(DeviceCtx *c)
+{
+    if (!c) { return; }
+    cudaSetDevice(c->device);
+    if (c->own_stream) { cudaStreamSynchronize(c->own_stream); }
+    for (auto &e : c->ev_analyse) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : c->ev_emit) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
+    if (c->ev_end) { cudaEventDestroy(c->ev_end); }
+    DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs, &c->cand,
+                       &c->diag, &c->jobout, &c->residual, &c->misc, &c->stream_begin, &c->pcm, &c->out };
+    for (DevBuf *b : bufs) { b->release(); }
+    c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release();
+    if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
+}
+
+bool config_valid(const struct SRLAEncoderConfig *cfg)
+{
+    if (!cfg) { return false; }
+    if (cfg->max_num_samples_per_block == 0 || cfg->min_num_samples_per_block == 0
+        || cfg->max_num_lookahead_samples == 0 || cfg->max_num_channels == 0) { return false; }
+    if (cfg->max_num_parameters > cfg->max_num_samples_per_block) { return false; }
+    if (cfg->min_num_samples_per_block > cfg->max_num_samples_per_block) { return false; }
+    if (cfg->max_num_lookahead_samples < cfg->max_num_samples_per_block) { return false; }
+    return true;
+}
+
+/* per-length constants of a job: host libm pow() for the Welch divisor (lpc.c:259) */
+struct LenConst { double div, gain, scale; };
+LenConst len_const(uint32_t n, std::map<uint32_t, LenConst> &cache)
+{
+    auto it = cache.find(n);
+    if (it != cache.end()) { return it->second; }
+    LenConst lc;
+    lc.div = 4.0 * std::pow((double)(n - 1), -2.0);
+    { const double m = (double)n - 1; lc.gain = (15 * (m - 1) * (m - 1) * (m - 1)) / (8 * m * (m - 2) * (m * m - 2 * m + 2)); }   /* lpc.c:275-290 */
+    lc.scale = 2.0 / n;
+    cache[n] = lc;
+    return lc;
+}
+
+Job make_job(uint32_t stream, uint32_t offset, uint32_t n, uint32_t flags, std::map<uint32_t, LenConst> &cache)
+{
+    Job j; const LenConst lc = len_const(n, cache);
+    j.stream = stream; j.offset = offset; j.nsmpl = n; j.flags = flags;
+    j.welch_div = lc.div; j.welch_gain = lc.gain; j.ac_scale = lc.scale;
+    return j;
+}
+
+uint32_t ceil_pow2_host(uint32_t v) { uint32_t p = 1; while (p < v) { p <<= 1; } return p; }
+
+/* what one call encodes */
+struct Plan {
+    const struct SRLAB200Stream *streams = nullptr;   /* device PCM */
+    uint32_t num_streams = 0;
+    uint32_t nch = 0;
+    bool emit_stream_header = true;
+    bool use_fixed_lshift = false;
+    uint32_t fixed_lshift = 0;
+    bool variable = false;            /* min != max: optimal block division */
+    bool size_only = false;           /* ComputeBlockSize */
+    bool want_diag = false;
+};
+
+struct Runner {
+    SRLAEncoder *enc; DeviceCtx *c;
+    std::map<uint32_t, LenConst> len_cache;
+    uint64_t launches = 0;
+
+    LaunchParams base_params(const Plan &pl, uint32_t nmax) const
+    {
+        LaunchParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.streams = (StreamDev *)c->streams.p;
+        p.num_streams = pl.num_streams;
+        p.nch = pl.nch; p.ncand = (pl.nch >= 2) ? pl.nch + 2 : pl.nch;
+        p.bps = enc->param.bits_per_sample;
+        p.max_order = enc->max_order;
+        p.ltp_order = enc->param.ltp_order;
+        p.nmax = nmax; p.fft_max = ceil_pow2_host(nmax);
+        p.res_stride = round_up_u32(nmax, 4);
+        p.sampling_rate = enc->param.sampling_rate; p.max_block = enc->param.max_num_samples_per_block; p.preset = enc->param.preset;
+        p.fixed_lshift = pl.fixed_lshift; p.use_fixed_lshift = pl.use_fixed_lshift ? 1u : 0u;
+        p.emit_stream_header = pl.emit_stream_header ? 1u : 0u;
+        p.unit = std::ldexp(1.0, -(int)(p.bps - 1));
+        p.tw_complex = (const double2 *)c->tw_complex.p; p.tw_real = (const double2 *)c->tw_real.p;
+        for (int i = 0; i < 20; i++) { p.tw_complex_off[i] = c->tw_c_off[i]; p.tw_real_off[i] = c->tw_r_off[i]; }
+        p.rice_threshold = (const double *)c->rice_thr.p;
+        p.huff_code = (const uint32_t *)c->huff_code.p; p.huff_len = (const uint8_t *)c->huff_len.p;
+        p.running = (unsigned long long *)c->misc.p;
+        p.stats = (uint32_t *)((unsigned char *)c->misc.p + 2 * sizeof(unsigned long long));
+        p.stream_begin = (unsigned long long *)c->stream_begin.p;
+        return p;
+    }
+
+    bool next_events(std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &pool, size_t idx, cudaEvent_t *a, cudaEvent_t *b)
+    {
+        while (pool.size() <= idx) {
+            cudaEvent_t x, y;
+            CU_TRY(cudaEventCreate(&x)); CU_TRY(cudaEventCreate(&y));
+            pool.emplace_back(x, y);
+        }
+        *a = pool[idx].first; *b = pool[idx].second;
+        return true;
+    }
+
+    bool launch_analyse(const LaunchParams &p)
+    {
+        const AnalyseLayout L = make_analyse_layout(p.nmax, p.fft_max, p.max_order, p.ltp_order);
+        if ((int)L.total + 256 > c->max_smem_optin) {
+            std::fprintf(stderr, "[srla_b200] block of %u samples needs %u bytes of shared memory (> %d)\n", p.nmax, L.total, c->max_smem_optin);
+            return false;
+        }
+        const dim3 grid(p.num_jobs * p.ncand), block(kThreads);
+        const uint32_t bpt = (p.fft_max + 2047u) / 2048u;
+        if (bpt <= 1) {
+            CU_TRY(cudaFuncSetAttribute(analyse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            analyse_kernel<1><<<grid, block, L.total, c->stream>>>(p);
+        } else if (bpt == 2) {
+            CU_TRY(cudaFuncSetAttribute(analyse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            analyse_kernel<2><<<grid, block, L.total, c->stream>>>(p);
+        } else if (bpt <= 4) {
+            CU_TRY(cudaFuncSetAttribute(analyse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+            analyse_kernel<4><<<grid, block, L.total, c->stream>>>(p);
+        } else {
+            std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
+            return false;
+        }
+        CU_TRY(cudaGetLastError());
+        launches++;
+        return true;
+    }
+
+    /* upload stream descriptors and compute offset_lshift on the device */
+    bool prepare_streams(const Plan &pl)
+    {
+        const size_t bytes = sizeof(StreamDev) * pl.num_streams;
+        if (!c->streams.reserve(bytes) || !c->h_small.reserve(bytes + 64) || !c->stream_begin.reserve(sizeof(unsigned long long) * (pl.num_streams + 1))) { return false; }
+        StreamDev *h = (StreamDev *)c->h_small.p;
+        uint32_t longest = 0;
+        for (uint32_t s = 0; s < pl.num_streams; s++) {
+            h[s].pcm = pl.streams[s].pcm; h[s].stride = pl.streams[s].channel_stride;
+            h[s].num_samples = pl.streams[s].num_samples; h[s].sample_bytes = pl.streams[s].sample_bytes;
+            h[s].lshift = 0; h[s].or_mask = 0;
+            longest = std::max(longest, h[s].num_samples);
+        }
+        CU_TRY(cudaMemcpyAsync(c->streams.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
+        if (!pl.use_fixed_lshift) {
+            const uint32_t per_cta = 256u * 8u * 16u;
+            uint32_t gx = std::max(1u, std::min((longest + per_cta - 1) / per_cta, 4096u));
+            lshift_or_kernel<<<dim3(gx, pl.num_streams), 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.nch);
+            lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.num_streams);
+            CU_TRY(cudaGetLastError());
+            launches += 2;
+        }
+        return true;
+    }
+
+    /* analyse + decide a list of jobs (already on the device at d_jobs), optionally scan + emit */
+    bool run_batch(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t nmax, bool emit, uint8_t *d_out, uint64_t cap,
+                   bool store_residual, size_t ev_idx)
+    {
+        LaunchParams p = base_params(pl, nmax);
+        p.jobs = d_jobs; p.num_jobs = count;
+        const size_t ncand = p.ncand;
+        if (!c->cand.reserve(sizeof(CandOut) * ncand * count) || !c->jobout.reserve(sizeof(JobOut) * count)) { return false; }
+        if (store_residual && !c->residual.reserve(sizeof(int32_t) * ncand * count * (size_t)p.res_stride)) { return false; }
+        if (pl.want_diag && !c->diag.reserve(sizeof(CandDiag) * ncand * count)) { return false; }
+        p.cand = (CandOut *)c->cand.p; p.jobout = (JobOut *)c->jobout.p;
+        p.residual = store_residual ? (int32_t *)c->residual.p : nullptr;
+        p.diag = pl.want_diag ? (CandDiag *)c->diag.p : nullptr;
+        p.out = d_out; p.out_capacity = cap;
+        const uint32_t raw_max = 11u + (uint32_t)(((uint64_t)p.bps * nmax * p.nch) / 8u);
+        p.emit_smem_bytes = raw_max;
+        cudaEvent_t a0, a1, e0, e1;
+        if (!next_events(c->ev_analyse, ev_idx, &a0, &a1) || !next_events(c->ev_emit, ev_idx, &e0, &e1)) { return false; }
+        CU_TRY(cudaEventRecord(a0, c->stream));
+        if (!launch_analyse(p)) { return false; }
+        CU_TRY(cudaEventRecord(a1, c->stream));
+        CU_TRY(cudaEventRecord(e0, c->stream));
+        decide_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(p);
+        launches++;
+        if (emit) {
+            scan_kernel<<<1, 1024, 0, c->stream>>>(p);
+            const uint32_t smem = round_up_u32(raw_max, 4) + 16u;
+            if ((int)smem > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] block too large for the emit stage (%u bytes)\n", smem); return false; }
+            CU_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            emit_kernel<<<count, kThreads, smem, c->stream>>>(p);
+            launches += 2;
+        }
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(e1, c->stream));
+        return true;
+    }
+
+    uint32_t jobs_per_batch(const Plan &pl, uint32_t nmax) const
+    {
+        const size_t ncand = (pl.nch >= 2) ? pl.nch + 2 : pl.nch;
+        const size_t per_job = sizeof(int32_t) * ncand * round_up_u32(nmax, 4) + sizeof(CandOut) * ncand;
+        size_t budget = (size_t)768 << 20;
+        size_t n = budget / per_job;
+        return (uint32_t)std::max<size_t>(64, std::min<size_t>(n, 65536));
+    }
+
+    /* the reference's block division of one look-ahead chunk from exact candidate sizes
+     * (srla_encoder.c:249-307 dense shortest path, 310-424 graph construction / back trace) */
+    static void shortest_partition(const std::vector<uint32_t> &edge_bytes /* [nodes*nodes], 0 = no edge */, uint32_t nodes,
+                                   uint32_t unit, uint32_t n, std::vector<uint32_t> &parts)
+    {
+        const double BIG = (double)(1UL << 24);
+        std::vector<double> dist(nodes, BIG); std::vector<uint32_t> from(nodes, ~0u); std::vector<uint8_t> done(nodes, 0);
+        dist[0] = 0.0;
+        uint32_t cur = 0;
+        for (;;) {
+            double low = BIG;
+            for (uint32_t i = 0; i < nodes; i++) { if (!done[i] && low > dist[i]) { low = dist[i]; cur = i; } }
+            if (cur == nodes - 1) { break; }
+            for (uint32_t i = 0; i < nodes; i++) {
+                const uint32_t eb = edge_bytes[cur * nodes + i];
+                const double w = eb ? (double)eb : BIG;
+                if (dist[i] > w + dist[cur]) { dist[i] = w + dist[cur]; from[i] = cur; }
+            }
+            done[cur] = 1;
+        }
+        std::vector<uint32_t> rev;
+        for (uint32_t node = nodes - 1; node != 0; node = from[node]) {
+            uint32_t len = (node - from[node]) * unit;
+            if (len > n - from[node] * unit) { len = n - from[node] * unit; }
+            rev.push_back(len);
+        }
+        parts.assign(rev.rbegin(), rev.rend());
+    }
+
+    /* whole call: streams -> output */
+    SRLAApiResult run(const Plan &pl, uint8_t *d_out, uint64_t cap, uint64_t *stream_offsets, uint32_t *single_estimate)
+    {
+        SRLAB200Stats &stt = enc->stats;
+        std::memset(&stt, 0, sizeof(stt));
+        if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        const uint32_t max_block = enc->param.max_num_samples_per_block, min_block = enc->param.min_num_samples_per_block;
+        for (uint32_t s = 0; s < pl.num_streams; s++) {
+            if (pl.streams[s].num_samples == 0) { return SRLA_APIRESULT_INVALID_FORMAT; }        /* srla_encoder.c:107 */
+            if (pl.streams[s].sample_bytes != 2 && pl.streams[s].sample_bytes != 4) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+            if (pl.streams[s].pcm == nullptr) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+            stt.bytes_in += (uint64_t)pl.nch * pl.streams[s].num_samples * pl.streams[s].sample_bytes;
+        }
+        if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
+        if (cudaMemsetAsync(c->misc.p, 0, 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t), c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+
+        std::vector<Job> jobs;
+        size_t ev_idx = 0;
+        if (!pl.variable) {
+            for (uint32_t s = 0; s < pl.num_streams; s++) {
+                const uint32_t total = pl.streams[s].num_samples;
+                for (uint32_t at = 0; at < total; at += max_block) {
+                    jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
+                }
+            }
+        } else {
+            /* pass 1: exact size of every candidate segment of every look-ahead chunk */
+            struct Chunk { uint32_t stream, at, len, nodes, first_job; };
+            std::vector<Chunk> chunks; std::vector<Job> cand_jobs; std::vector<uint32_t> edge_of_job;
+            const uint32_t step = enc->param.num_lookahead_samples;
+            for (uint32_t s = 0; s < pl.num_streams; s++) {
+                const uint32_t total = pl.streams[s].num_samples;
+                for (uint32_t at = 0; at < total; at += step) {
+                    Chunk ch; ch.stream = s; ch.at = at; ch.len = std::min(step, total - at);
+                    ch.nodes = (ch.len + min_block - 1) / min_block + 1; ch.first_job = (uint32_t)cand_jobs.size();
+                    for (uint32_t i = 0; i < ch.nodes; i++) {
+                        for (uint32_t j = i + 1; j < ch.nodes; j++) {
+                            uint32_t len = (j - i) * min_block;
+                            if (len > max_block) { continue; }
+                            if (len > ch.len - i * min_block) { len = ch.len - i * min_block; }
+                            cand_jobs.push_back(make_job(s, at + i * min_block, len, 0u, len_cache));
+                            edge_of_job.push_back(i * ch.nodes + j);
+                        }
+                    }
+                    chunks.push_back(ch);
+                }
+            }
+            stt.num_analysed += cand_jobs.size();
+            std::vector<uint32_t> est(cand_jobs.size());
+            {
+                const size_t bytes = sizeof(Job) * cand_jobs.size();
+                if (!c->jobs.reserve(bytes) || !c->h_jobs.reserve(bytes)) { return SRLA_APIRESULT_NG; }
+                std::memcpy(c->h_jobs.p, cand_jobs.data(), bytes);
+                if (cudaMemcpyAsync(c->jobs.p, c->h_jobs.p, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                const uint32_t per = jobs_per_batch(pl, max_block);
+                for (size_t b = 0; b < cand_jobs.size(); b += per) {
+                    const uint32_t cnt = (uint32_t)std::min<size_t>(per, cand_jobs.size() - b);
+                    if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, max_block, false, nullptr, 0, false, ev_idx++)) { return SRLA_APIRESULT_NG; }
+                    if (!c->h_jobout.reserve(sizeof(JobOut) * cnt)) { return SRLA_APIRESULT_NG; }
+                    if (cudaMemcpyAsync(c->h_jobout.p, c->jobout.p, sizeof(JobOut) * cnt, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
+                        || cudaStreamSynchronize(c->stream) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] size pass failed: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
+                    const JobOut *jo = (const JobOut *)c->h_jobout.p;
+                    for (uint32_t k = 0; k < cnt; k++) { if (jo[k].status) { return SRLA_APIRESULT_NG; } est[b + k] = jo[k].estimate_bytes; }
+                }
+            }
+            /* shortest path per chunk -> final block list */
+            for (const Chunk &ch : chunks) {
+                std::vector<uint32_t> edge((size_t)ch.nodes * ch.nodes, 0u);
+                uint32_t k = ch.first_job;
+                for (uint32_t i = 0; i < ch.nodes; i++) {
+                    for (uint32_t j = i + 1; j < ch.nodes; j++) {
+                        if ((j - i) * min_block > max_block) { continue; }
+                        edge[i * ch.nodes + j] = est[k++];
+                    }
+                }
+                std::vector<uint32_t> parts;
+                shortest_partition(edge, ch.nodes, min_block, ch.len, parts);
+                uint32_t off = 0;
+                for (uint32_t len : parts) {
+                    jobs.push_back(make_job(ch.stream, ch.at + off, len, (ch.at + off == 0) ? kJobFirstOfStream : 0u, len_cache));
+                    off += len;
+                }
+            }
+        }
+        stt.num_analysed += jobs.size();
+        stt.num_blocks = pl.size_only ? 0 : jobs.size();
+
+        uint32_t nmax = 1;
+        for (const Job &j : jobs) { nmax = std::max(nmax, j.nsmpl); }
+        {
+            const size_t bytes = sizeof(Job) * jobs.size();
+            if (!c->jobs.reserve(bytes) || !c->h_jobs.reserve(bytes)) { return SRLA_APIRESULT_NG; }
+            std::memcpy(c->h_jobs.p, jobs.data(), bytes);
+            if (cudaMemcpyAsync(c->jobs.p, c->h_jobs.p, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        }
+        const uint32_t per = jobs_per_batch(pl, nmax);
+        for (size_t b = 0; b < jobs.size(); b += per) {
+            const uint32_t cnt = (uint32_t)std::min<size_t>(per, jobs.size() - b);
+            if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++)) { return SRLA_APIRESULT_NG; }
+        }
+        if (cudaEventRecord(c->ev_end, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+
+        /* results */
+        const size_t small_bytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t);
+        const size_t sb_bytes = sizeof(unsigned long long) * (pl.num_streams + 1);
+        if (!c->h_result.reserve(small_bytes + sb_bytes + sizeof(JobOut) + 64)) { return SRLA_APIRESULT_NG; }
+        unsigned char *hs = (unsigned char *)c->h_result.p;
+        cudaMemcpyAsync(hs, c->misc.p, small_bytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hs + small_bytes, c->stream_begin.p, sb_bytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hs + small_bytes + sb_bytes, c->jobout.p, sizeof(JobOut), cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
+            return SRLA_APIRESULT_NG;
+        }
+        const unsigned long long *running = (const unsigned long long *)hs;
+        const uint32_t *dstats = (const uint32_t *)(hs + 2 * sizeof(unsigned long long));
+        const unsigned long long *sbeg = (const unsigned long long *)(hs + small_bytes);
+        const JobOut *first = (const JobOut *)(hs + small_bytes + sb_bytes);
+        stt.kernel_launches = launches;
+        stt.bytes_out = running[0];
+        for (int i = 0; i < 256; i++) { stt.order_histogram[i] = dstats[i]; }
+        for (int i = 0; i < 4; i++) { stt.method_histogram[i] = dstats[256 + i]; }
+        for (int i = 0; i < 3; i++) { stt.type_histogram[i] = dstats[260 + i]; }
+        cudaEventElapsedTime(&stt.ms_total_device, c->ev_begin, c->ev_end);
+        for (size_t i = 0; i < ev_idx; i++) {
+            float a = 0, e = 0;
+            cudaEventElapsedTime(&a, c->ev_analyse[i].first, c->ev_analyse[i].second);
+            cudaEventElapsedTime(&e, c->ev_emit[i].first, c->ev_emit[i].second);
+            stt.ms_analyse += a; stt.ms_emit += e;
+        }
+        if (single_estimate) { *single_estimate = first->estimate_bytes; if (first->status) { return SRLA_APIRESULT_NG; } }
+        if (pl.size_only) { return SRLA_APIRESULT_OK; }
+        /* any block whose analysis failed the way the reference fails (singular LTP system)? */
+        {
+            /* statuses live in jobout of the last batch only; a failed block is never written, so the
+             * byte count of written block types tells: every job increments exactly one type counter */
+            const uint64_t emitted = (uint64_t)dstats[260] + dstats[261] + dstats[262];
+            if (running[1] == 0 && emitted != jobs.size()) { return SRLA_APIRESULT_NG; }
+        }
+        if (running[1] != 0 || running[0] > cap) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+        if (stream_offsets) {
+            for (uint32_t s = 0; s < pl.num_streams; s++) { stream_offsets[s] = pl.emit_stream_header ? sbeg[s] : 0; }
+            stream_offsets[pl.num_streams] = running[0];
+        }
+        return SRLA_APIRESULT_OK;
+    }
+};
+
+SRLAApiResult check_ready(const SRLAEncoder *e)
+{
+    if (!e || e->magic != kEncoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (e->set_parameter != 1) { return SRLA_APIRESULT_PARAMETER_NOT_SET; }
+    return SRLA_APIRESULT_OK;
+}
+
+uint64_t max_encoded_size(const SRLAEncoder *e, uint32_t num_samples)
+{
+    const uint32_t unit = (e->param.min_num_samples_per_block == e->param.max_num_samples_per_block)
+        ? e->param.max_num_samples_per_block : e->param.min_num_samples_per_block;
+    const uint64_t blocks = ((uint64_t)num_samples + unit - 1) / unit;
+    return 30ull + blocks * 11ull + ((uint64_t)e->param.bits_per_sample * num_samples * e->param.num_channels + 7) / 8 + 64;
+}
+
+/* host PCM (planar pointers) -> device, as one StreamDev-style layout */
+bool upload_planar_int32(DeviceCtx *c, const int32_t *const *input, uint32_t nch, uint32_t n, struct SRLAB200Stream *desc)
+{
+    const uint64_t stride = round_up_u32(n, 8);
+    if (!c->pcm.reserve(sizeof(int32_t) * stride * nch)) { return false; }
+    for (uint32_t ch = 0; ch < nch; ch++) {
+        CU_TRY(cudaMemcpyAsync((int32_t *)c->pcm.p + stride * ch, input[ch], sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    desc->pcm = c->pcm.p; desc->channel_stride = stride; desc->num_samples = n; desc->sample_bytes = 4;
+    return true;
+}
+
+} // namespace
+
+/* ================================================================================================
+ * Part 1: reference-compatible surface
+ * ============================================================================================== */
+extern "C" {
+
+SRLAApiResult SRLAEncoder_EncodeHeader(const struct SRLAHeader *header, uint8_t *data, uint32_t data_size)
+{
+    if (header == NULL || data == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (data_size < SRLA_HEADER_SIZE) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (header->num_channels == 0 || header->num_samples == 0 || header->sampling_rate == 0 || header->bits_per_sample == 0
+        || header->offset_lshift >= 32 || header->max_num_samples_per_block == 0 || header->preset >= SRLA_NUM_PARAMETER_PRESETS) {
+        return SRLA_APIRESULT_INVALID_FORMAT;
+    }
+    uint8_t *p = data;
+    auto be = [&p](uint32_t v, int nbytes) { for (int i = nbytes - 1; i >= 0; i--) { *p++ = (uint8_t)(v >> (8 * i)); } };
+    *p++ = '1'; *p++ = '2'; *p++ = '4'; *p++ = '9';
+    be(SRLA_FORMAT_VERSION, 4); be(SRLA_CODEC_VERSION, 4);
+    be(header->num_channels, 2); be(header->num_samples, 4); be(header->sampling_rate, 4); be(header->bits_per_sample, 2);
+    be(header->offset_lshift, 1); be(header->max_num_samples_per_block, 4); be(header->preset, 1);
+    return SRLA_APIRESULT_OK;
+}
+
+int32_t SRLAEncoder_CalculateWorkSize(const struct SRLAEncoderConfig *config)
+{
+    if (!config_valid(config)) { return -1; }
+    return (int32_t)(sizeof(struct SRLAEncoder) + 64);
+}
+
+struct SRLAEncoder *SRLAEncoder_Create(const struct SRLAEncoderConfig *config, void *work, int32_t work_size)
+{
+    uint8_t own = 0;
+    if (work == NULL && work_size == 0) {
+        if ((work_size = SRLAEncoder_CalculateWorkSize(config)) < 0) { return NULL; }
+        work = std::malloc((size_t)work_size);
+        own = 1;
+    }
+    if (config == NULL || work == NULL || work_size < SRLAEncoder_CalculateWorkSize(config) || !config_valid(config)) {
+        if (own) { std::free(work); }
+        return NULL;
+    }
+    if (config->max_num_samples_per_block > (uint32_t)kMaxBlock) {
+        std::fprintf(stderr, "[srla_b200] max_num_samples_per_block %u exceeds this implementation's capacity %d\n", config->max_num_samples_per_block, kMaxBlock);
+        if (own) { std::free(work); }
+        return NULL;
+    }
+    uintptr_t at = ((uintptr_t)work + 15u) & ~(uintptr_t)15u;
+    struct SRLAEncoder *e = (struct SRLAEncoder *)at;
+    std::memset(e, 0, sizeof(*e));
+    e->magic = kEncoderMagic;
+    e->config = *config;
+    e->alloced_by_own = own;
+    e->work = work;
+    e->ctx = new (std::nothrow) DeviceCtx();
+    if (!e->ctx || !ctx_init(e->ctx)) {
+        if (e->ctx) { ctx_destroy(e->ctx); delete e->ctx; }
+        e->magic = 0;
+        if (own) { std::free(work); }
+        return NULL;
+    }
+    return e;
+}
+
+void SRLAEncoder_Destroy(struct SRLAEncoder *encoder)
+{
+    if (encoder == NULL || encoder->magic != kEncoderMagic) { return; }
+    ctx_destroy(encoder->ctx);
+    delete encoder->ctx;
+    encoder->ctx = nullptr;
+    encoder->magic = 0;
+    if (encoder->alloced_by_own == 1) { std::free(encoder->work); }
+}
+
+SRLAApiResult SRLAEncoder_SetEncodeParameter(struct SRLAEncoder *encoder, const struct SRLAEncodeParameter *parameter)
+{
+    if (encoder == NULL || parameter == NULL || encoder->magic != kEncoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    /* srla_encoder.c:427-465 */
+    if (parameter->num_channels == 0 || parameter->bits_per_sample == 0 || parameter->sampling_rate == 0
+        || parameter->preset >= SRLA_NUM_PARAMETER_PRESETS) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    /* srla_encoder.c:727-734 */
+    if (parameter->min_num_samples_per_block == 0
+        || parameter->min_num_samples_per_block > parameter->max_num_samples_per_block
+        || parameter->num_lookahead_samples < parameter->max_num_samples_per_block
+        || (parameter->num_lookahead_samples % parameter->min_num_samples_per_block) != 0
+        || (parameter->ltp_order > 0 && (parameter->ltp_order % 2) == 0) || parameter->ltp_order > SRLA_MAX_LTP_ORDER) {
+        return SRLA_APIRESULT_INVALID_FORMAT;
+    }
+    /* this implementation: SVR refinement out of scope; raw blocks exist for 8/16/24 bit only */
+    if (parameter->num_svr_filter_learning_iteration != 0) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (parameter->bits_per_sample != 8 && parameter->bits_per_sample != 16 && parameter->bits_per_sample != 24) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    /* srla_encoder.c:737-742 */
+    if (encoder->config.max_num_samples_per_block < parameter->max_num_samples_per_block
+        || encoder->config.min_num_samples_per_block > parameter->min_num_samples_per_block
+        || encoder->config.max_num_lookahead_samples < parameter->num_lookahead_samples
+        || encoder->config.max_num_channels < parameter->num_channels
+        || parameter->num_channels > SRLA_MAX_NUM_CHANNELS
+        || encoder->config.max_num_parameters < kPresetMaxOrder[parameter->preset]) {
+        return SRLA_APIRESULT_INSUFFICIENT_BUFFER;
+    }
+    encoder->param = *parameter;
+    encoder->max_order = kPresetMaxOrder[parameter->preset];
+    encoder->offset_lshift = 0;
+    encoder->set_parameter = 1;
+    return SRLA_APIRESULT_OK;
+}
+
+static SRLAApiResult single_chunk(struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples,
+                                  uint8_t *data, uint32_t data_size, uint32_t *output_size, bool variable, bool size_only)
+{
+    DeviceCtx *c = encoder->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    struct SRLAB200Stream desc;
+    if (!upload_planar_int32(c, input, encoder->param.num_channels, num_samples, &desc)) { return SRLA_APIRESULT_NG; }
+    Plan pl;
+    pl.streams = &desc; pl.num_streams = 1; pl.nch = encoder->param.num_channels;
+    pl.emit_stream_header = false; pl.use_fixed_lshift = true; pl.fixed_lshift = encoder->offset_lshift;
+    pl.variable = variable; pl.size_only = size_only;
+    Runner r{ encoder, c };
+    const uint64_t cap = max_encoded_size(encoder, num_samples);
+    if (!size_only && !c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
+    uint64_t offs[2] = { 0, 0 };
+    uint32_t est = 0;
+    const SRLAApiResult rc = r.run(pl, size_only ? nullptr : (uint8_t *)c->out.p, size_only ? 0 : cap, offs, size_only ? &est : nullptr);
+    if (rc != SRLA_APIRESULT_OK) { return rc; }
+    if (size_only) { *output_size = est; return SRLA_APIRESULT_OK; }
+    if (offs[1] > data_size) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (cudaMemcpy(data, c->out.p, offs[1], cudaMemcpyDeviceToHost) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    *output_size = (uint32_t)offs[1];
+    return SRLA_APIRESULT_OK;
+}
+
+SRLAApiResult SRLAEncoder_ComputeBlockSize(
+    struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples, uint32_t *output_size)
+{
+    if (encoder == NULL || input == NULL || num_samples == 0 || output_size == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    if (num_samples > encoder->param.max_num_samples_per_block) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    return single_chunk(encoder, input, num_samples, nullptr, 0, output_size, false, true);
+}
+
+SRLAApiResult SRLAEncoder_EncodeBlock(
+    struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples,
+    uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    if (encoder == NULL || input == NULL || num_samples == 0 || data == NULL || data_size == 0 || output_size == NULL) {
+        return SRLA_APIRESULT_INVALID_ARGUMENT;
+    }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    if (num_samples > encoder->param.max_num_samples_per_block) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    return single_chunk(encoder, input, num_samples, data, data_size, output_size, false, false);
+}
+
+SRLAApiResult SRLAEncoder_EncodeOptimalPartitionedBlock(
+    struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples,
+    uint8_t *data, uint32_t data_size, uint32_t *output_size)
+{
+    if (encoder == NULL || input == NULL || data == NULL || output_size == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    if (num_samples == 0 || num_samples > encoder->param.num_lookahead_samples) { return SRLA_APIRESULT_NG; }
+    /* one look-ahead chunk: force a single chunk by planning with step == num_lookahead_samples */
+    return single_chunk(encoder, input, num_samples, data, data_size, output_size, true, false);
+}
+
+SRLAApiResult SRLAEncoder_EncodeWhole(
+    struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples,
+    uint8_t *data, uint32_t data_size, uint32_t *output_size, SRLAEncoder_EncodeBlockCallback encode_callback)
+{
+    if (encoder == NULL || input == NULL || data == NULL || output_size == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    if (num_samples == 0) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (data_size < SRLA_HEADER_SIZE) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    DeviceCtx *c = encoder->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    struct SRLAB200Stream desc;
+    if (!upload_planar_int32(c, input, encoder->param.num_channels, num_samples, &desc)) { return SRLA_APIRESULT_NG; }
+    Plan pl;
+    pl.streams = &desc; pl.num_streams = 1; pl.nch = encoder->param.num_channels;
+    pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
+    Runner r{ encoder, c };
+    const uint64_t cap = max_encoded_size(encoder, num_samples);
+    if (!c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
+    uint64_t offs[2] = { 0, 0 };
+    const SRLAApiResult rc = r.run(pl, (uint8_t *)c->out.p, cap, offs, nullptr);
+    if (rc != SRLA_APIRESULT_OK) { return rc; }
+    if (offs[1] > data_size) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (cudaMemcpy(data, c->out.p, offs[1], cudaMemcpyDeviceToHost) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    *output_size = (uint32_t)offs[1];
+    encoder->offset_lshift = data[24];                        /* the reference keeps it in its header (srla_encoder.c:1732) */
+    if (encode_callback != NULL) {
+        /* replay: one call per top-level step (srla_encoder.c:1756-1783) */
+        const uint32_t step = pl.variable ? encoder->param.num_lookahead_samples : encoder->param.max_num_samples_per_block;
+        uint32_t progress = 0; uint64_t pos = SRLA_HEADER_SIZE;
+        while (progress < num_samples && pos + 11 <= offs[1]) {
+            const uint32_t todo = std::min(step, num_samples - progress);
+            uint32_t got = 0; const uint64_t begin = pos;
+            while (got < todo && pos + 11 <= offs[1]) {
+                const uint32_t size = ((uint32_t)data[pos + 2] << 24) | ((uint32_t)data[pos + 3] << 16) | ((uint32_t)data[pos + 4] << 8) | data[pos + 5];
+                got += ((uint32_t)data[pos + 9] << 8) | data[pos + 10];
+                pos += 6ull + size;
+            }
+            progress += todo;
+            encode_callback(num_samples, progress, data + begin, (uint32_t)(pos - begin));
+        }
+    }
+    return SRLA_APIRESULT_OK;
+}
+
+/* ================================================================================================
+ * Part 2: batch / device-resident extension
+ * ============================================================================================== */
+SRLAApiResult SRLAB200_EncodeStreamsDevice(
+    struct SRLAEncoder *encoder, const struct SRLAB200Stream *streams, uint32_t num_streams,
+    uint8_t *d_out, uint64_t out_capacity, uint64_t *stream_offsets)
+{
+    if (encoder == NULL || streams == NULL || num_streams == 0 || d_out == NULL || stream_offsets == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    Plan pl;
+    pl.streams = streams; pl.num_streams = num_streams; pl.nch = encoder->param.num_channels;
+    pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
+    Runner r{ encoder, encoder->ctx };
+    return r.run(pl, d_out, out_capacity, stream_offsets, nullptr);
+}
+
+SRLAApiResult SRLAB200_EncodeStreamsHost(
+    struct SRLAEncoder *encoder, const struct SRLAB200Stream *streams, uint32_t num_streams,
+    uint8_t *out, uint64_t out_capacity, uint64_t *stream_offsets)
+{
+    if (encoder == NULL || streams == NULL || num_streams == 0 || out == NULL || stream_offsets == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    DeviceCtx *c = encoder->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    const uint32_t nch = encoder->param.num_channels;
+    std::vector<struct SRLAB200Stream> dev(num_streams);
+    uint64_t total_bytes = 0, cap = 0;
+    for (uint32_t s = 0; s < num_streams; s++) {
+        if (streams[s].pcm == NULL || (streams[s].sample_bytes != 2 && streams[s].sample_bytes != 4)) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+        total_bytes += (uint64_t)round_up_u32(streams[s].num_samples, 16) * nch * streams[s].sample_bytes;
+        cap += max_encoded_size(encoder, streams[s].num_samples);
+    }
+    if (!c->pcm.reserve(total_bytes) || !c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
+    uint64_t at = 0;
+    for (uint32_t s = 0; s < num_streams; s++) {
+        const uint64_t stride = round_up_u32(streams[s].num_samples, 16);
+        const uint32_t sb = streams[s].sample_bytes;
+        unsigned char *dst = (unsigned char *)c->pcm.p + at;
+        if (streams[s].channel_stride == stride) {
+            if (cudaMemcpyAsync(dst, streams[s].pcm, stride * nch * sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        } else {
+            for (uint32_t ch = 0; ch < nch; ch++) {
+                if (cudaMemcpyAsync(dst + stride * ch * sb, (const unsigned char *)streams[s].pcm + streams[s].channel_stride * ch * sb,
+                                    (size_t)streams[s].num_samples * sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+            }
+        }
+        dev[s].pcm = dst; dev[s].channel_stride = stride; dev[s].num_samples = streams[s].num_samples; dev[s].sample_bytes = sb;
+        at += stride * nch * sb;
+    }
+    Plan pl;
+    pl.streams = dev.data(); pl.num_streams = num_streams; pl.nch = nch;
+    pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
+    Runner r{ encoder, c };
+    const SRLAApiResult rc = r.run(pl, (uint8_t *)c->out.p, cap, stream_offsets, nullptr);
+    if (rc != SRLA_APIRESULT_OK) { return rc; }
+    if (stream_offsets[num_streams] > out_capacity) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (cudaMemcpyAsync(out, c->out.p, stream_offsets[num_streams], cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
+        || cudaStreamSynchronize(c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    return SRLA_APIRESULT_OK;
+}
+
+uint64_t SRLAB200_MaxEncodedSize(const struct SRLAEncoder *encoder, uint32_t num_samples)
+{
+    if (encoder == NULL || encoder->magic != kEncoderMagic || encoder->set_parameter != 1) { return 0; }
+    return max_encoded_size(encoder, num_samples);
+}
+
+SRLAApiResult SRLAB200_GetStats(const struct SRLAEncoder *encoder, struct SRLAB200Stats *stats)
+{
+    if (encoder == NULL || stats == NULL || encoder->magic != kEncoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    *stats = encoder->stats;
+    return SRLA_APIRESULT_OK;
+}
+
+SRLAApiResult SRLAB200_SetDevice(int device_ordinal)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device_ordinal < 0 || device_ordinal >= count) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    g_device = device_ordinal;
+    return SRLA_APIRESULT_OK;
+}
+
+SRLAApiResult SRLAB200_SetStream(struct SRLAEncoder *encoder, void *cuda_stream)
+{
+    if (encoder == NULL || encoder->magic != kEncoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    encoder->ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : encoder->ctx->own_stream;
+    return SRLA_APIRESULT_OK;
+}
+
+const char *SRLAB200_Version(void) { return "srla_b200 0.1 sm_100a (format 10 / codec 18)"; }
+
+SRLAApiResult SRLAB200_TestAnalyseChannel(
+    struct SRLAEncoder *encoder, const int32_t *sig, uint32_t n, int32_t *residual, struct SRLAB200ChannelResult *result)
+{
+    if (encoder == NULL || sig == NULL || n == 0 || residual == NULL || result == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    if (n > encoder->param.max_num_samples_per_block || n <= encoder->max_order) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    DeviceCtx *c = encoder->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    struct SRLAB200Stream desc;
+    const int32_t *rows[1] = { sig };
+    if (!upload_planar_int32(c, rows, 1, n, &desc)) { return SRLA_APIRESULT_NG; }
+    Plan pl;
+    pl.streams = &desc; pl.num_streams = 1; pl.nch = 1; pl.emit_stream_header = false; pl.use_fixed_lshift = true; pl.fixed_lshift = 0;
+    pl.want_diag = true;
+    Runner r{ encoder, c };
+    std::memset(&encoder->stats, 0, sizeof(encoder->stats));
+    if (!r.prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
+    Job job = make_job(0, 0, n, 0, r.len_cache);
+    if (!c->jobs.reserve(sizeof(Job))) { return SRLA_APIRESULT_NG; }
+    if (cudaMemcpyAsync(c->jobs.p, &job, sizeof(Job), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0)) { return SRLA_APIRESULT_NG; }
+    CandOut co; CandDiag dg;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess
+        || cudaMemcpy(&co, c->cand.p, sizeof(co), cudaMemcpyDeviceToHost) != cudaSuccess
+        || cudaMemcpy(&dg, c->diag.p, sizeof(dg), cudaMemcpyDeviceToHost) != cudaSuccess
+        || cudaMemcpy(residual, c->residual.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        std::fprintf(stderr, "[srla_b200] TestAnalyseChannel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return SRLA_APIRESULT_NG;
+    }
+    if (co.status) { return SRLA_APIRESULT_NG; }
+    std::memset(result, 0, sizeof(*result));
+    result->pre_coef = co.pre_coef; result->pre_prev = co.pre_prev;
+    result->order = co.order; result->rshift = co.rshift; result->use_sum = co.use_sum;
+    for (uint32_t i = 0; i < co.order && i < SRLA_MAX_COEFFICIENT_ORDER; i++) { result->coef[i] = co.coef[i]; }
+    result->ltp_period = co.ltp_period;
+    for (int i = 0; i < 3; i++) { result->ltp_coef[i] = co.ltp_coef[i]; }
+    result->code_type = co.code_type; result->porder = co.porder; result->residual_bits = co.residual_bits; result->total_bits = co.total_bits;
+    for (uint32_t i = 0; i <= encoder->max_order; i++) { result->autocorr[i] = dg.autocorr[i]; result->error_vars[i] = dg.error_vars[i]; }
+    for (uint32_t i = 0; i < co.order; i++) { result->lpc_double[i] = dg.lpc_double[i]; }
+    return SRLA_APIRESULT_OK;
+}
+
+} /* extern "C" */

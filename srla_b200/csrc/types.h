@@ -9,19 +9,21 @@
 #define SRLA_B200_TYPES_H
 
 #include <stdint.h>
+#include <vector_types.h>   /* double2 (CUDA toolkit header, host-safe) */
 
 namespace srla {
 
-constexpr int kThreads        = 256;   /* threads per CTA in every kernel                      */
+constexpr int kThreads        = 256;   /* threads per CTA in the analyse / emit kernels        */
+constexpr int kWarps          = kThreads / 32;
 constexpr int kMaxOrder       = 255;   /* SRLA_MAX_COEFFICIENT_ORDER                           */
 constexpr int kMaxChannels    = 8;
 constexpr int kMaxCand        = kMaxChannels + 2;
-constexpr int kMaxBlock       = 16384; /* capacity of the shared-memory resident pipeline       */
+constexpr int kMaxBlock       = 8192;  /* capacity of the shared-memory resident pipeline       */
 constexpr int kLog2MaxParts   = 10;    /* srla_coder.c:18                                       */
 constexpr int kMaxParts       = 1 << kLog2MaxParts;
 constexpr int kLtpMinPeriod   = 8;     /* srla_internal.h:31-35                                 */
 constexpr int kLtpMaxPeriod   = 8 + 256 - 2;
-constexpr int kLtpLags        = kLtpMaxPeriod + 3;  /* lags the pitch search may touch (0..264)   */
+constexpr int kLtpLags        = kLtpMaxPeriod + 4;  /* lags the pitch search may touch (0..265)  */
 
 enum BlockType { kBlockCompress = 0, kBlockSilent = 1, kBlockRaw = 2 };
 enum CodeType  { kCodeRice = 0, kCodeRecursiveRice = 1, kCodeAllZero = 2 };
@@ -32,7 +34,7 @@ struct StreamDev {
     unsigned long long stride;
     uint32_t num_samples;
     uint32_t sample_bytes;     /* 2: int16_t, 4: int32_t                                  */
-    uint32_t lshift;           /* common trailing-zero shift (written by lshift_finish_kernel or host) */
+    uint32_t lshift;           /* common trailing-zero shift (srla_utility.c:177-203)      */
     uint32_t or_mask;          /* scratch of the OR-reduction                              */
 };
 
@@ -59,6 +61,14 @@ struct CandOut {
     uint32_t status;           /* 0 ok, 1: reference would fail the encode (singular LTP system) */
     int16_t  coef[256];        /* FIR order                                                */
     uint8_t  kparam[kMaxParts];/* coding parameter per partition at `porder`               */
+    /* diagnostics for the stage-level parity tests (written only when LaunchParams.diag) */
+};
+
+/* optional diagnostics of one candidate (stage-level parity tests) */
+struct CandDiag {
+    double autocorr[kMaxOrder + 1];   /* after the ridge scaling of lag 0 */
+    double error_vars[kMaxOrder + 1]; /* window-compensated               */
+    double lpc_double[kMaxOrder + 1]; /* un-quantised coefficients of the chosen order */
 };
 
 /* block-level decision */
@@ -75,12 +85,13 @@ struct JobOut {
 
 /* parameters shared by all jobs of a launch */
 struct LaunchParams {
-    const StreamDev *streams;
+    StreamDev       *streams;
     const Job       *jobs;
     CandOut         *cand;           /* [job][cand]                                        */
+    CandDiag        *diag;           /* [job][cand] or NULL                                */
     JobOut          *jobout;         /* [job]                                              */
-    int32_t         *residual;       /* [job][cand][res_stride]                            */
-    uint32_t num_jobs;
+    int32_t         *residual;       /* [job][cand][res_stride] or NULL (size-only pass)   */
+    uint32_t num_jobs, num_streams;
     uint32_t nch, ncand, bps;
     uint32_t max_order;              /* preset's maximum LPC order                         */
     uint32_t ltp_order;
@@ -88,20 +99,71 @@ struct LaunchParams {
     uint32_t nmax;                   /* longest job of this launch                         */
     uint32_t fft_max;                /* next power of two >= nmax                          */
     uint32_t sampling_rate, max_block, preset;   /* stream header fields                   */
+    uint32_t fixed_lshift;           /* used when use_fixed_lshift (single-block API)       */
+    uint32_t use_fixed_lshift;
+    uint32_t emit_stream_header;
+    uint32_t emit_smem_bytes;        /* staging capacity of the emit kernel                 */
+    double   unit;                   /* 2^-(bps-1)                                         */
     /* tables in device memory */
-    const double2 *tw_complex;       /* per stage size: {w1,w2,w3}[ns/4]                   */
-    const uint32_t *tw_complex_off;  /* [log2(ns)] -> offset in double2 units              */
-    const double2 *tw_real;          /* per real size N: {wr,wi}[N/4] forward; inverse conjugates wi */
-    const uint32_t *tw_real_off;     /* [log2(N)]                                          */
-    const double  *rice_threshold;   /* [32] smallest mean with k >= j (plain Rice)        */
+    const double2  *tw_complex;      /* per stage size: {w1,w2,w3}[ns/4]                   */
+    const double2  *tw_real;         /* per real size N: {wr,wi}[N/4] forward; inverse conjugates wi */
+    uint32_t tw_complex_off[20];     /* [log2(ns)] -> offset in double2 units              */
+    uint32_t tw_real_off[20];        /* [log2(N)]                                          */
+    const double   *rice_threshold;  /* [32] smallest mean with k >= j (plain Rice)        */
+    const uint32_t *huff_code;       /* [2][256] plain, summed                             */
+    const uint8_t  *huff_len;        /* [2][256]                                           */
     /* output */
     uint8_t  *out;
     unsigned long long out_capacity;
     unsigned long long *running;     /* [0] bytes emitted so far, [1] overflow flag        */
     unsigned long long *stream_begin;/* [num_streams+1] byte offset where each stream starts */
     uint32_t *stats;                 /* order[256], method[4], type[3]                      */
-    uint32_t emit_stream_header;
 };
+
+/* shared-memory layout of the analyse kernel (identical on host and device) */
+struct AnalyseLayout {
+    uint32_t region_off, region_bytes; /* FFT buffer / residual + mean pyramid (time-shared)   */
+    uint32_t sig_off;                  /* int32: 4 pad + nmax rounded up to 4                  */
+    uint32_t lags_off, nlags;          /* doubles                                              */
+    uint32_t row_off;                  /* 2 x (P + 4) doubles                                  */
+    uint32_t err_off;                  /* P + 2 doubles                                        */
+    uint32_t coef_off;                 /* int32 x (roundup4(P) + 4)                            */
+    uint32_t ktab_off;                 /* 2048 bytes                                           */
+    uint32_t red_off;                  /* 1024 bytes of reduction scratch                      */
+    uint32_t total;
+};
+
+#if defined(__CUDACC__)
+#define SRLA_HD __host__ __device__
+#else
+#define SRLA_HD
+#endif
+
+SRLA_HD inline uint32_t round_up_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+SRLA_HD inline AnalyseLayout make_analyse_layout(uint32_t nmax, uint32_t fft_max, uint32_t P, uint32_t ltp)
+{
+    AnalyseLayout L;
+    const uint32_t n4 = round_up_u32(nmax, 4);
+    const uint32_t parts = (nmax < (uint32_t)kMaxParts) ? nmax : (uint32_t)kMaxParts;
+    uint32_t fft_bytes = 8u * fft_max;
+    uint32_t rice_bytes = 4u * n4 + 16u * round_up_u32(parts, 2) + 16u;
+    uint32_t off = 0;
+    L.region_off = off;
+    L.region_bytes = round_up_u32((fft_bytes > rice_bytes) ? fft_bytes : rice_bytes, 16);
+    off += L.region_bytes;
+    L.sig_off = off; off += 4u * (n4 + 4u) + 16u;   /* + one spare int4 for the FIR look-ahead load */
+    L.nlags = (P + 2 > (ltp ? (uint32_t)kLtpLags : 0u)) ? P + 2 : (uint32_t)kLtpLags;
+    L.nlags = round_up_u32(L.nlags, 2);
+    L.lags_off = off; off += 8u * L.nlags;
+    L.row_off = off; off += 8u * 2u * round_up_u32(P + 4, 2);
+    L.err_off = off; off += 8u * round_up_u32(P + 2, 2);
+    L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
+    L.ktab_off = off; off += 2048u;
+    L.red_off = off; off += 1024u;
+    L.total = off;
+    return L;
+}
 
 } // namespace srla
 #endif

@@ -1,0 +1,201 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI of libsrla_b200.so, against
+ * the CPU oracle (oracle/srla_oracle.c) on the same seeded inputs,
+ * the committed reference-generated golden fixtures (tests/golden/*.npz),
+ * the compiled reference itself when oracle/_ref travelled to the box (decode round trip).
+Integer / byte results must be bit-exact; the FP64 LPC stage is compared at 1e-10 relative
+(BASELINE.json north_star) and exactly on the integers derived from it.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (golden_names, have_ref, load_golden, oracle_analyse, oracle_encode, ref_decode,
+                     reference_test_signals, walk_blocks)
+from srla_b200 import encoder as E
+from srla_b200.synth import synth_stereo
+
+pytestmark = pytest.mark.gpu
+
+
+def _first_diff(a: bytes, b: bytes) -> str:
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return f"first difference at byte {i} (lens {len(a)} vs {len(b)})"
+    return f"prefix equal, lens {len(a)} vs {len(b)}"
+
+
+# ---- stage level ------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,preset,bps,ltp", [(4096, 4, 16, 0), (2304, 4, 16, 0), (1024, 2, 16, 0), (8192, 4, 24, 3),
+                                              (4096, 6, 16, 0), (1000, 1, 16, 3), (4096, 5, 24, 0), (513, 3, 8, 0)])
+def test_channel_analysis_matches_oracle(n, preset, bps, ltp):
+    """pre-emphasis, (LTP,) autocorrelation, Levinson-Durbin, order, quantised coefficients, FIR residual,
+    Rice search of ONE candidate channel (srla_encoder.c:966-1205)"""
+    x = synth_stereo(n, seed=100 + n + preset, bits=bps)[0]
+    want, _sig, want_res = oracle_analyse(x, bps=bps, preset=preset, ltp=ltp)
+    with E.Encoder(max_block=8192) as enc:
+        assert enc.set_parameter(1, bps, 48000, 8192, 8192, 8192, ltp, preset) == E.OK
+        got, got_res = enc.analyse_channel(x)
+    P = E.PRESET_MAX_ORDER[preset]
+    # FP64 stage: 1e-10 relative tolerance (north_star); in practice bit-identical
+    ac_w = np.array(want.autocorr[:P + 1]); ac_g = np.array(got.autocorr[:P + 1])
+    assert np.max(np.abs(ac_w - ac_g)) <= 1e-10 * abs(ac_w[0])
+    ev_w = np.array(want.error_vars[:P + 1]); ev_g = np.array(got.error_vars[:P + 1])
+    assert np.max(np.abs(ev_w - ev_g)) <= 1e-10 * abs(ev_w[0])
+    # integers: exact
+    for f in ("pre_coef", "pre_prev", "order", "rshift", "use_sum", "ltp_period", "code_type", "porder",
+              "residual_bits", "total_bits"):
+        assert getattr(got, f) == getattr(want, f), f
+    assert list(got.coef[:want.order]) == list(want.coef[:want.order])
+    assert list(got.ltp_coef) == list(want.ltp_coef)
+    lp_w = np.array(want.lpc_double[:want.order]); lp_g = np.array(got.lpc_double[:want.order])
+    if want.order:
+        assert np.max(np.abs(lp_w - lp_g)) <= 1e-10 * max(1.0, np.max(np.abs(lp_w)))
+    assert np.array_equal(got_res, want_res)
+
+
+# ---- whole streams vs oracle --------------------------------------------------------------------
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(preset=4, max_block=4096)),
+    (2, dict(preset=0, max_block=4096)),
+    (3, dict(preset=5, max_block=2048)),
+    (4, dict(preset=4, max_block=4096, ltp=3)),
+    (5, dict(preset=4, max_block=4096, min_block=2048, lookahead=8192)),
+    (6, dict(preset=1, max_block=1024, min_block=512, lookahead=2048, ltp=3)),
+    (7, dict(preset=6, max_block=4096)),
+    (8, dict(preset=3, max_block=8192)),
+])
+def test_stream_matches_oracle_16bit(seed, kw):
+    pcm = synth_stereo(30000, seed=seed)
+    got = E.encode(pcm, **kw)
+    want = oracle_encode(pcm, **kw)
+    assert got == want, _first_diff(got, want)
+
+
+@pytest.mark.parametrize("bits,nch", [(8, 2), (24, 2), (24, 1), (16, 5), (16, 1), (16, 8)])
+def test_stream_matches_oracle_widths_and_channels(bits, nch):
+    pcm = synth_stereo(20000, seed=40 + bits + nch, bits=bits, channels=nch)
+    kw = dict(bps=bits, preset=4, max_block=4096, ltp=3 if bits == 24 else 0)
+    got = E.encode(pcm, **kw)
+    want = oracle_encode(pcm, **kw)
+    assert got == want, _first_diff(got, want)
+
+
+def test_loud_24bit_8192_preemphasis_sums_round():
+    """loud 24-bit / 8192: the reference's double pre-emphasis sums exceed 2^53 and round"""
+    pcm = synth_stereo(8192 * 3, seed=9, bits=24)
+    pcm = np.clip(pcm.astype(np.int64) * 3 // 2, -(1 << 23), (1 << 23) - 1).astype(np.int32)
+    kw = dict(bps=24, preset=4, max_block=8192)
+    got = E.encode(pcm, **kw)
+    want = oracle_encode(pcm, **kw)
+    assert got == want, _first_diff(got, want)
+
+
+# ---- golden fixtures (reference-generated) ------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_stream_matches_golden(name):
+    pcm, kw, srl = load_golden(name)
+    got = E.encode(pcm, **kw)
+    assert got == srl, _first_diff(got, srl)
+
+
+# ---- the reference's own edge cases ---------------------------------------------------------------
+@pytest.mark.parametrize("name", ["silence", "pos_const", "neg_const", "nyquist", "mini_impulse", "white", "sine440"])
+@pytest.mark.parametrize("bps", [8, 16, 24])
+def test_reference_generators(name, bps):
+    """generator families of test/srla_encode_decode/main.cpp:51-208 in its block configuration"""
+    sig = reference_test_signals(n=8500, bps=bps, nch=2)[name]
+    kw = dict(bps=bps, preset=0, min_block=512, max_block=1024, lookahead=2048, rate=44100)
+    got = E.encode(sig, **kw)
+    want = oracle_encode(sig, **kw)
+    assert got == want, _first_diff(got, want)
+    if have_ref():
+        assert np.array_equal(ref_decode(got), sig)
+
+
+def test_short_and_ragged_streams():
+    """streams shorter than a block, a block shorter than the LPC order (RAW), a 2-sample stream"""
+    base = synth_stereo(5000, seed=77)
+    for n in (2, 7, 50, 64, 65, 300, 4095, 4097):
+        pcm = base[:, :n].copy()
+        got = E.encode(pcm, preset=4, max_block=4096)
+        want = oracle_encode(pcm, preset=4, max_block=4096)
+        assert got == want, (n, _first_diff(got, want))
+
+
+def test_trailing_zero_shift_and_silent_blocks():
+    pcm = (synth_stereo(4096 * 3, seed=5) >> 4) << 4
+    pcm[:, 4096:8192] = 0                                   # one SILENT block
+    got = E.encode(pcm, preset=4, max_block=4096)
+    want = oracle_encode(pcm, preset=4, max_block=4096)
+    assert got == want, _first_diff(got, want)
+    assert got[24] == 4
+    types = [t for _pos, _size, t, _n in walk_blocks(got)]
+    assert types == [0, 1, 0]
+
+
+def test_incompressible_noise_falls_back_to_raw():
+    rng = np.random.default_rng(3)
+    pcm = rng.integers(-32768, 32768, size=(2, 8192), dtype=np.int32)
+    got = E.encode(pcm, preset=4, max_block=4096)
+    want = oracle_encode(pcm, preset=4, max_block=4096)
+    assert got == want, _first_diff(got, want)
+    assert [t for _p, _s, t, _n in walk_blocks(got)] == [2, 2]
+
+
+# ---- API behaviour (test/srla_encoder/srla_encoder_test.cpp) ----------------------------------------
+def test_block_api_and_compute_block_size():
+    """EncodeBlock output_size == ComputeBlockSize (srla_encoder_test.cpp:398-407); EncodeBlock == the
+    block inside an EncodeWhole stream; EncodeOptimalPartitionedBlock == the variable-mode chunk"""
+    pcm = synth_stereo(4096, seed=21)
+    with E.Encoder(max_block=4096) as enc:
+        assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+        blk = enc.encode_block(pcm)
+        assert enc.compute_block_size(pcm) == len(blk)
+        whole = enc.encode_whole(pcm)
+        assert whole[30:] == blk
+    with E.Encoder(max_block=4096, min_block=1024, lookahead=16384) as enc:
+        assert enc.set_parameter(2, 16, 48000, 1024, 4096, 16384, 0, 4) == E.OK
+        pcm = synth_stereo(16384, seed=22)
+        chunk = enc.encode_block(pcm, optimal_partition=True)
+        whole = enc.encode_whole(pcm)
+        assert whole[30:] == chunk
+        assert whole == oracle_encode(pcm, preset=4, max_block=4096, min_block=1024, lookahead=16384)
+
+
+def test_callback_sequence():
+    pcm = synth_stereo(10000, seed=23)
+    calls = []
+    out = E.encode(pcm, preset=4, max_block=4096, callback=lambda n, prog, ptr, size: calls.append((n, prog, size)))
+    blocks = list(walk_blocks(out))
+    assert [c[1] for c in calls] == [4096, 8192, 10000]
+    assert [c[2] for c in calls] == [6 + size for _pos, size, _t, _n in blocks]
+    assert all(c[0] == 10000 for c in calls)
+
+
+def test_batch_host_api_matches_per_stream_encode():
+    """SRLAB200_EncodeStreamsHost on int16 host buffers: every stream equals its own EncodeWhole"""
+    streams = [synth_stereo(n, seed=200 + i) for i, n in enumerate((9000, 4096, 12345, 100))]
+    with E.Encoder(max_block=4096) as enc:
+        assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+        out, offs = enc.encode_streams_host([s.astype(np.int16) for s in streams])
+        st = enc.stats()
+        for i, s in enumerate(streams):
+            got = out[offs[i]:offs[i + 1]].tobytes()
+            want = oracle_encode(s, preset=4, max_block=4096)
+            assert got == want, (i, _first_diff(got, want))
+        assert st.num_blocks == sum((s.shape[1] + 4095) // 4096 for s in streams)
+        assert st.bytes_out == offs[-1]
+        assert st.kernel_launches >= 4
+
+
+def test_full_size_roundtrip_property():
+    """BASELINE config-2 scale (size-independent property): 2 000 stereo blocks of 4096 at mode 4 decode
+    sample-exactly with the reference decoder, and every block checksum verifies"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not present")
+    tile = synth_stereo(4096 * 50, seed=31)
+    pcm = np.concatenate([np.roll(tile, 37 * k, axis=1) for k in range(8)], axis=1)[:, :4096 * 400]
+    got = E.encode(pcm, preset=4, max_block=4096)
+    assert np.array_equal(ref_decode(got), pcm)
