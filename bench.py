@@ -1,0 +1,396 @@
+#!/usr/bin/env python3
+"""bench.py -- SRLA encode throughput on B200 (BASELINE.json: "encode Msamples/sec at mode 4 / block 4096").
+
+A "step" is one pass of the hot path over the whole workload (configs[1]: 10 000 stereo 16-bit blocks of
+4096 samples, mode 4, fixed blocks).  Per rank:
+
+  value  device-resident: PCM already in HBM, SRLAB200_EncodeStreamsDevice, output left in HBM
+  e2e    the same workload through SRLAB200_EncodeStreamsHost with pinned HOST int16 PCM in and a pinned
+         host byte buffer out (H2D + kernels + D2H inside the timed region)
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libsrla_ref.so, built from /root/reference
+by oracle/Makefile; falls back to our C port oracle/liboracle.so) on the host cores, one handle per thread.
+Multi-GPU: the path shards by independent streams/blocks -- every rank encodes its own copy of the workload
+(weak scaling), no data-path collective; torch.distributed carries only the barrier and the max-over-ranks
+timing.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 4096
+PRESET = 4
+RATE = 48000
+CHANNELS = 2
+BITS = 16
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+class _Param(C.Structure):
+    _fields_ = [("num_channels", C.c_uint16), ("bits_per_sample", C.c_uint16), ("sampling_rate", C.c_uint32),
+                ("min_num_samples_per_block", C.c_uint32), ("max_num_samples_per_block", C.c_uint32),
+                ("num_lookahead_samples", C.c_uint32), ("ltp_order", C.c_uint32),
+                ("num_svr_filter_learning_iteration", C.c_uint32), ("preset", C.c_uint8)]
+
+
+class _Config(C.Structure):
+    _fields_ = [("max_num_channels", C.c_uint32), ("min_num_samples_per_block", C.c_uint32),
+                ("max_num_samples_per_block", C.c_uint32), ("max_num_lookahead_samples", C.c_uint32),
+                ("max_num_parameters", C.c_uint32)]
+
+
+class _SoParams(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("num_channels", "bits_per_sample", "sampling_rate", "min_block", "max_block",
+                                          "lookahead", "ltp_order", "preset", "offset_lshift")]
+
+
+class CpuEncoder:
+    """The reference's own CPU implementation of the path (kind 'reference'), or our C port of it
+    (kind 'port') when oracle/_ref was not built.  Used ONLY as the measured CPU baseline."""
+
+    def __init__(self):
+        ref = os.path.join(ROOT, "oracle", "_ref", "libsrla_ref.so")
+        port = os.path.join(ROOT, "oracle", "liboracle.so")
+        if os.path.exists(ref):
+            self.kind, self.lib = "reference", C.CDLL(ref)
+            PP = C.POINTER(C.POINTER(C.c_int32))
+            self.lib.SRLAEncoder_Create.restype = C.c_void_p
+            self.lib.SRLAEncoder_Create.argtypes = [C.POINTER(_Config), C.c_void_p, C.c_int32]
+            self.lib.SRLAEncoder_SetEncodeParameter.argtypes = [C.c_void_p, C.POINTER(_Param)]
+            self.lib.SRLAEncoder_EncodeWhole.argtypes = [C.c_void_p, PP, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+            self.lib.SRLAEncoder_Destroy.argtypes = [C.c_void_p]
+        else:
+            if not os.path.exists(port):
+                subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+            self.kind, self.lib = "port", C.CDLL(port)
+            self.lib.so_encode_whole_flat.argtypes = [C.POINTER(_SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+
+    def make_handle(self):
+        if self.kind != "reference":
+            return None
+        cfg = _Config(8, BLOCK, BLOCK, BLOCK, 255)
+        h = self.lib.SRLAEncoder_Create(C.byref(cfg), None, 0)      # serial: Create rebuilds a static table
+        prm = _Param(CHANNELS, BITS, RATE, BLOCK, BLOCK, BLOCK, 0, 0, PRESET)
+        assert h and self.lib.SRLAEncoder_SetEncodeParameter(h, C.byref(prm)) == 0
+        return h
+
+    def encode(self, handle, pcm32: np.ndarray, out: np.ndarray) -> int:
+        nch, n = pcm32.shape
+        size = C.c_uint32(0)
+        if self.kind == "reference":
+            rows = (C.POINTER(C.c_int32) * nch)()
+            for c in range(nch):
+                rows[c] = C.cast(pcm32[c].ctypes.data, C.POINTER(C.c_int32))
+            rc = self.lib.SRLAEncoder_EncodeWhole(handle, rows, n, out.ctypes.data, out.size, C.byref(size), None)
+        else:
+            prm = _SoParams(nch, BITS, RATE, BLOCK, BLOCK, BLOCK, 0, PRESET, 0)
+            rc = self.lib.so_encode_whole_flat(C.byref(prm), pcm32.ctypes.data, n, out.ctypes.data, out.size, C.byref(size))
+        assert rc == 0, rc
+        return size.value
+
+    def destroy(self, handle):
+        if handle:
+            self.lib.SRLAEncoder_Destroy(handle)
+
+
+def cpu_throughput(pcm16: np.ndarray, blocks_per_thread: int, threads: int, repeats: int = 1):
+    """Each of `threads` host threads encodes its own slice of `blocks_per_thread` blocks of the workload
+    (ctypes releases the GIL).  Returns (channel-samples per second, kind, first slice's bytes)."""
+    enc = CpuEncoder()
+    total_blocks = pcm16.shape[1] // BLOCK
+    slices, handles, outs = [], [], []
+    for t in range(threads):
+        b0 = (t * max(1, total_blocks // threads)) % max(1, total_blocks - blocks_per_thread + 1)
+        slices.append(np.ascontiguousarray(pcm16[:, b0 * BLOCK:(b0 + blocks_per_thread) * BLOCK].astype(np.int32)))
+        handles.append(enc.make_handle())
+        outs.append(np.zeros(slices[-1].size * 4 + 4096, dtype=np.uint8))
+    sizes = [0] * threads
+
+    def work(t):
+        for _ in range(repeats):
+            sizes[t] = enc.encode(handles[t], slices[t], outs[t])
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    for h in handles:
+        enc.destroy(h)
+    samples = sum(s.size for s in slices) * repeats
+    return samples / dt, enc.kind, outs[0][:sizes[0]].tobytes(), slices[0]
+
+
+def run_reference_arm(args, rank: int) -> None:
+    if rank != 0:
+        return
+    from srla_b200.workload import make_blocks_workload
+    threads = os.cpu_count() or 1
+    pcm = make_blocks_workload(min(args.blocks, 2000), BLOCK, CHANNELS, BITS, num_templates=4, template_blocks=125)
+    # calibrate so that the whole --steps/--warmup run stays within a few minutes
+    rate1, kind, _, _ = cpu_throughput(pcm, 32, 1)
+    budget_s = 8.0
+    bpt = int(max(16, min(pcm.shape[1] // BLOCK, rate1 * budget_s / (BLOCK * CHANNELS))))
+    times = []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rate, kind, _, _ = cpu_throughput(pcm, bpt, threads)
+        if step >= args.warmup:
+            times.append((time.perf_counter() - t0, rate))
+    rate = float(np.mean([r for _, r in times]))
+    ms = 1e3 * float(np.mean([t for t, _ in times]))
+    sample = f"{threads} host threads x {bpt} blocks of {BLOCK} stereo 16-bit frames each per step (slices of the config-2 workload)"
+    line = {"impl": "reference", "metric": "encode Msamples/s (mode 4, block 4096, stereo 16-bit; 1 sample = 1 channel-sample)",
+            "value": rate / 1e6, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+            "data": "synthetic", "config": workload_config(args.blocks),
+            "cpu_baseline": {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": rate / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def workload_config(blocks: int):
+    return {"workload": f"configs[1]: {blocks} stereo 16-bit blocks of {BLOCK} samples, mode 4 (-m 4 -B 4096 -V 0), 48 kHz, "
+                        "fixed blocks, LTP off",
+            "blocks": blocks, "block_samples": BLOCK, "channels": CHANNELS, "bits": BITS, "preset": PRESET,
+            "l2_policy": "inputs larger than L2 (163.84 MB int16 PCM + 655 MB residual scratch per step vs 126 MB L2)"}
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
+
+    def _loop(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def load_traffic():
+    """dram bytes per analyse-kernel launch from the committed ncu --set full summary, if present."""
+    path = os.path.join(ROOT, "profiles", "analyse_kernel_full.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=10000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from srla_b200 import encoder as E
+    from srla_b200.workload import make_blocks_workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the SRLA B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- workload: pinned host int16 PCM (one stream of blocks*4096 frames) and its device copy ----
+    pcm_np = make_blocks_workload(args.blocks, BLOCK, CHANNELS, BITS)
+    nsamp = pcm_np.shape[1]
+    stride = (nsamp + 15) // 16 * 16
+    h_pcm = torch.empty((CHANNELS, stride), dtype=torch.int16).pin_memory()
+    h_pcm.zero_()
+    h_pcm[:, :nsamp] = torch.from_numpy(pcm_np)
+    d_pcm = h_pcm.cuda(non_blocking=False)
+
+    E.load_library().SRLAB200_SetDevice(local_rank)
+    enc = E.Encoder(max_channels=CHANNELS, max_block=BLOCK, device=local_rank)
+    assert enc.set_parameter(CHANNELS, BITS, RATE, BLOCK, BLOCK, BLOCK, 0, PRESET) == E.OK
+    stream = torch.cuda.current_stream()
+    enc.set_stream(stream.cuda_stream)
+    cap = enc.max_encoded_size(nsamp)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+
+    dev_desc = (E.SRLAB200Stream * 1)(E.SRLAB200Stream(d_pcm.data_ptr(), stride, nsamp, 2))
+    host_desc = (E.SRLAB200Stream * 1)(E.SRLAB200Stream(h_pcm.data_ptr(), stride, nsamp, 2))
+    offs = (C.c_uint64 * 2)()
+    lib = enc.lib
+
+    def step_device():
+        rc = lib.SRLAB200_EncodeStreamsDevice(enc.handle, dev_desc, 1, d_out.data_ptr(), cap, offs)
+        assert rc == E.OK, rc
+
+    def step_host():
+        rc = lib.SRLAB200_EncodeStreamsHost(enc.handle, host_desc, 1, h_out.data_ptr(), cap, offs)
+        assert rc == E.OK, rc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    an_ms, em_ms, launches = [], [], 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        st = enc.stats()
+        an_ms.append(st.ms_analyse); em_ms.append(st.ms_emit); launches += int(st.kernel_launches)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    st = enc.stats()
+    bytes_out = int(st.bytes_out)
+    samples_per_step = nsamp * CHANNELS
+    value = world * samples_per_step * args.steps / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers ----
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e = timed(step_host, e2e_steps)
+    e2e_value = world * samples_per_step * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    h2d = CHANNELS * stride * 2
+    d2h = int(offs[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (analyse_kernel): algorithmic bytes / measured duration ----
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        peaks = json.load(f)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+    alg_bytes = int(st.bytes_in) + bytes_out              # PCM in (2 B/sample) + encoded bytes out
+    an = float(np.mean(an_ms))
+    achieved = alg_bytes / (an * 1e-3) / 1e9
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "kernel": "analyse_kernel<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": an,
+                "share_of_step": an / (ms_total / args.steps), "emit_ms": float(np.mean(em_ms)),
+                "note": "compute-bound stage (FP64 FFT + int32 FIR + Rice search at ~100 ops/byte): the HBM fraction is "
+                        "expected to be low; see DESIGN.md for the issue-rate ceilings"}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate1, kind, _, _ = cpu_throughput(pcm_np, 32, 1)
+        bpt = int(max(16, min(args.blocks, rate1 * 12.0 / (BLOCK * CHANNELS))))
+        rate, kind, cpu_bytes, cpu_slice = cpu_throughput(pcm_np, bpt, threads)
+        # same bytes as the GPU for that slice?
+        gpu_bytes = E.encode(cpu_slice, bps=BITS, rate=RATE, max_block=BLOCK, preset=PRESET)
+        cpu = {"value": rate / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+               "sample": f"{threads} host threads x {bpt} blocks of {BLOCK} stereo frames (slices of this workload), "
+                         f"single-thread rate {rate1 / 1e6:.2f} Msamples/s",
+               "gpu_output_identical_on_sample": bool(gpu_bytes == cpu_bytes)}
+
+    hist = np.array(st.order_histogram[:], dtype=np.int64)
+    line = {"metric": "encode Msamples/s (mode 4, block 4096, stereo 16-bit; 1 sample = 1 channel-sample)",
+            "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+f64", "data": "synthetic", "config": workload_config(args.blocks),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "SRLAB200_EncodeStreamsHost (pinned int16 host PCM in, pinned host bytes out)"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "stats": {"compression_ratio": bytes_out / float(st.bytes_in), "bytes_out": bytes_out,
+                      "mean_lpc_order": float((hist * np.arange(256)).sum() / max(1, hist.sum())),
+                      "order_histogram_by_16": [int(hist[i:i + 16].sum()) for i in range(0, 80, 16)],
+                      "stereo_methods_LR_MS_LS_SR": list(st.method_histogram[:]),
+                      "block_types_compress_silent_raw": list(st.type_histogram[:])}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
