@@ -173,41 +173,44 @@ def workload_config(blocks: int):
 
 
 class ClockSampler:
+    """nvidia-smi sampling in the background DURING the timed region (B200_PROFILING.md clocks line)."""
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.stop_flag, self.thread = index, [], False, None
-
-    def _loop(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.index, self.proc = index, None
 
     def start(self):
-        self.thread = threading.Thread(target=self._loop, daemon=True)
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)          # let the sampler come up before the timed region starts
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for i, nm in enumerate(names):
                 if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(rows)}
 
 
 def load_traffic():
@@ -224,7 +227,7 @@ def load_traffic():
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=10000)
@@ -306,6 +309,7 @@ def main() -> None:
     sampler = ClockSampler(local_rank)
     sampler.start()
     an_ms, em_ms, launches = [], [], 0
+    k_ms = {"front_kernel": [], "lpc_kernel": [], "residual_kernel": [], "emit_kernel(+decide+scan)": []}
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -313,6 +317,8 @@ def main() -> None:
         step_device()
         st = enc.stats()
         an_ms.append(st.ms_analyse); em_ms.append(st.ms_emit); launches += int(st.kernel_launches)
+        k_ms["front_kernel"].append(st.ms_front); k_ms["lpc_kernel"].append(st.ms_lpc)
+        k_ms["residual_kernel"].append(st.ms_residual); k_ms["emit_kernel(+decide+scan)"].append(st.ms_emit)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -346,14 +352,17 @@ def main() -> None:
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
     alg_bytes = int(st.bytes_in) + bytes_out              # PCM in (2 B/sample) + encoded bytes out
-    an = float(np.mean(an_ms))
+    kernel_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
+    dominant = max(("front_kernel", "lpc_kernel", "residual_kernel"), key=lambda k: kernel_ms[k])
+    an = kernel_ms[dominant]
     achieved = alg_bytes / (an * 1e-3) / 1e9
     traffic = load_traffic()
-    roofline = {"bound": "hbm", "kernel": "analyse_kernel<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "traffic": ((traffic or {}).get(dominant) or {}).get("dram_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": an,
-                "share_of_step": an / (ms_total / args.steps), "emit_ms": float(np.mean(em_ms)),
+                "share_of_step": an / (ms_total / args.steps), "all_kernels_ms": kernel_ms,
+                "whole_step_achieved_gbs": alg_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                 "note": "compute-bound stage (FP64 FFT + int32 FIR + Rice search at ~100 ops/byte): the HBM fraction is "
                         "expected to be low; see DESIGN.md for the issue-rate ceilings"}
 

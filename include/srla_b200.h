@@ -171,12 +171,15 @@ struct SRLAB200Stats {
     uint64_t kernel_launches;     /* CUDA kernels launched by this library                    */
     uint64_t bytes_in;            /* algorithmic input bytes  (channels x samples x width)    */
     uint64_t bytes_out;           /* encoded bytes incl. headers                              */
-    float    ms_analyse;          /* device time of the analysis kernel(s) (CUDA events)      */
+    float    ms_analyse;          /* device time of the three analysis kernels (CUDA events)  */
     float    ms_emit;             /* device time of decide + scan + emit kernels              */
     float    ms_total_device;     /* first kernel start -> last kernel end                    */
     uint32_t order_histogram[256];/* chosen LPC order of every emitted channel                */
     uint32_t method_histogram[4]; /* stereo method of every emitted COMPRESS block            */
     uint32_t type_histogram[3];   /* block types: compress, silent, raw                       */
+    float    ms_front;            /* front_kernel (mid/side, pre-emphasis, LTP, FFT autocorrelation) */
+    float    ms_lpc;              /* lpc_kernel (Levinson-Durbin, order choice, quantisation)  */
+    float    ms_residual;         /* residual_kernel (FIR residual, Rice search)               */
 };
 SRLAApiResult SRLAB200_GetStats(const struct SRLAEncoder *encoder, struct SRLAB200Stats *stats);
 

@@ -2,8 +2,10 @@
  * kernels.cuh -- the sm_100a CUDA kernels of the SRLA encode path.
  *
  *   lshift_or_kernel / lshift_finish_kernel   whole-stream OR reduce -> trailing-zero shift   (A0)
- *   analyse_kernel<BPT>     one CTA per (block, candidate channel): the complete analysis of
- *                           srla_encoder.c:966-1205 with the block resident in shared memory  (A2-A8, A11)
+ *   front_kernel<BPT>       one CTA per (block, candidate channel): mid/side, pre-emphasis, optional LTP,
+ *                           Welch window + FFT autocorrelation, block resident in shared memory (A2-A5, A11)
+ *   lpc_kernel              one warp per candidate: Levinson-Durbin, order choice, quantisation     (A5, A6)
+ *   residual_kernel         one CTA per candidate: int32 FIR residual, Rice search, side-info bits   (A3, A7, A8)
  *   decide_kernel           block type, stereo method, exact block size                       (A1, A2)
  *   scan_kernel             output offsets of the blocks / streams
  *   emit_kernel             one CTA per block: header, side information, Rice codes, Fletcher (A1, A9, A10)
@@ -276,58 +278,6 @@ __device__ __forceinline__ double inv_sqrt_cr(double s)
     return __fma_rn(0.5 * y, e, y);
 }
 
-/* ------------------------------------------------------------------------------------------------
- * Levinson-Durbin, all orders (lpc.c:379-441).  Executed by warp 0.  The reflection numerator is
- * the reference's sequential dot product (same summation order), evaluated redundantly by all lanes.
- * rows: if tri != NULL every order's vector a[0..m] is kept at tri + (m-1)(m+2)/2, else ping-pong
- * in rowbuf and only the vector of order `stop` survives (returned pointer).
- * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t tri_offset(uint32_t m) { return (m - 1u) * (m + 2u) / 2u + (m - 1u); } /* row m has m+2 slots (a[0..m], trailing 0) */
-
-__device__ double *levinson_warp(const double *r, const uint32_t stop, double *tri, double *rowbuf, const uint32_t rowlen, double *err)
-{
-    const int lane = threadIdx.x & 31;
-    double *prev = tri ? tri + tri_offset(1) : rowbuf;
-    if (fabs(r[0]) < (double)FLT_EPSILON) {
-        for (uint32_t i = lane; i <= stop; i += 32) { err[i] = r[0]; }
-        /* all coefficient vectors are zero */
-        if (tri) { for (uint32_t i = lane; i < tri_offset(stop + 1u); i += 32) { tri[i] = 0.0; } }
-        else { for (uint32_t i = lane; i < rowlen; i += 32) { rowbuf[i] = 0.0; } }
-        __syncwarp();
-        return tri ? tri + tri_offset(stop) : rowbuf;
-    }
-    double e = r[0];
-    {
-        const double a1 = -r[1] / r[0];
-        const double e1 = e + r[1] * a1;
-        if (lane == 0) { prev[0] = 1.0; prev[1] = a1; prev[2] = 0.0; err[0] = e; err[1] = e1; }
-        e = e1;
-    }
-    __syncwarp();
-    for (uint32_t k = 1; k < stop; ++k) {
-        double acc = 0.0;
-        {
-            const double *rr = r + k + 1;
-            uint32_t i = 0;
-            for (; i + 4 <= k + 1; i += 4) {
-                const double m0 = prev[i] * rr[-(int)i], m1 = prev[i + 1] * rr[-(int)i - 1];
-                const double m2 = prev[i + 2] * rr[-(int)i - 2], m3 = prev[i + 3] * rr[-(int)i - 3];
-                acc += m0; acc += m1; acc += m2; acc += m3;
-            }
-            for (; i <= k; ++i) { acc += prev[i] * rr[-(int)i]; }
-        }
-        const double refl = acc / (-e);
-        const double e_next = e * (1.0 - refl * refl);
-        double *next = tri ? tri + tri_offset(k + 1u) : ((prev == rowbuf) ? rowbuf + rowlen : rowbuf);
-        for (uint32_t i = lane; i <= k + 1u; i += 32) { next[i] = prev[i] + refl * prev[k + 1u - i]; }
-        if (lane == 0) { next[k + 2u] = 0.0; err[k + 1u] = e_next; }
-        e = e_next;
-        prev = next;
-        __syncwarp();
-    }
-    return prev;
-}
-
 /* geometric-distribution entropy (srla_encoder.c:873-885) */
 __device__ __forceinline__ double geometric_entropy(double mean_abs, uint32_t bps)
 {
@@ -405,57 +355,100 @@ __device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, 
 }
 
 /* ------------------------------------------------------------------------------------------------
- * analyse_kernel: one CTA per (job, candidate)
+ * Candidate signal preparation shared by front_kernel and residual_kernel
+ * ---------------------------------------------------------------------------------------------- */
+/* load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) -> raw[0..n).
+ * returns OR of the unshifted samples of a plain channel candidate (0 for M/S). */
+__device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
+                                              uint32_t lshift, int32_t *raw)
+{
+    const uint32_t n = job.nsmpl;
+    const uint32_t first_ch = (p.nch >= 2u) ? 2u : 0u;
+    int nz = 0;
+    if ((p.nch >= 2u) && (cand < 2u)) {
+        for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+            const int32_t l = asr32(load_sample(st, 0, job.offset + i), lshift);
+            const int32_t r = asr32(load_sample(st, 1, job.offset + i), lshift);
+            const int32_t side = (int32_t)((uint32_t)r - (uint32_t)l);
+            raw[i] = (cand == 1u) ? side : (int32_t)((uint32_t)l + (uint32_t)(side >> 1));
+        }
+    } else {
+        const uint32_t ch = cand - first_ch;
+        for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+            const int32_t v = load_sample(st, ch, job.offset + i);
+            nz |= v;
+            raw[i] = asr32(v, lshift);
+        }
+    }
+    return nz;
+}
+
+/* pre-emphasis (srla_utility.c:342-358), filter memory seeded with the first sample; raw -> sig,
+ * plus the zero padding the FIR's vector loads may touch */
+__device__ __forceinline__ void apply_preemphasis(const int32_t *raw, int32_t *sig, uint32_t n, int32_t pre_coef)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+        const int32_t cur = raw[i], prv = raw[(i == 0u) ? 0u : i - 1u];
+        sig[i] = (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)pre_coef) >> 4));
+    }
+    if (threadIdx.x < 4) { sig[-1 - (int)threadIdx.x] = 0; }
+    for (uint32_t i = n + threadIdx.x; i < round_up_u32(n, 4) + 4u; i += kThreads) { sig[i] = 0; }
+}
+
+/* long-term prediction residual replaces the signal (srla_lpc_predict.c:267-294); tmp: n int32 */
+__device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n, uint32_t ltp_order, uint32_t period,
+                                          int32_t c0, int32_t c1, int32_t c2)
+{
+    const uint32_t half_order = ltp_order >> 1;
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+        int32_t v = sig[i];
+        if (i >= period + half_order + 1u) {
+            const int32_t *x = sig + (i - period - half_order);
+            uint32_t acc = 16u;
+            acc += (uint32_t)c0 * (uint32_t)x[0];
+            if (ltp_order > 1u) { acc += (uint32_t)c1 * (uint32_t)x[1]; acc += (uint32_t)c2 * (uint32_t)x[2]; }
+            v = (int32_t)((uint32_t)v - (uint32_t)((int32_t)acc >> 5));
+        }
+        tmp[i] = v;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += kThreads) { sig[i] = tmp[i]; }
+    __syncthreads();
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * front_kernel: one CTA per (job, candidate).  Pre-emphasis decision, optional LTP analysis, and
+ * the Welch-windowed FFT autocorrelation of the signal the LPC stage sees; lags 0..P go to HBM.
  * ---------------------------------------------------------------------------------------------- */
 template <int BPT>
-__global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const AnalyseLayout L = make_analyse_layout(p.nmax, p.fft_max, p.max_order, p.ltp_order);
+    const FrontLayout L = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
     double   *region_d = reinterpret_cast<double *>(smem + L.region_off);
     int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
     int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;     /* 4 ints of front padding */
     double   *lags     = reinterpret_cast<double *>(smem + L.lags_off);
-    double   *rowbuf   = reinterpret_cast<double *>(smem + L.row_off);
-    double   *err      = reinterpret_cast<double *>(smem + L.err_off);
-    int32_t  *coef_s   = reinterpret_cast<int32_t *>(smem + L.coef_off);
-    uint8_t  *ktab     = smem + L.ktab_off;
-    unsigned long long *red64 = reinterpret_cast<unsigned long long *>(smem + L.red_off);
-    uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
-    __shared__ int32_t  sh_i[16];
-    __shared__ uint32_t sh_u[16];
+    __shared__ unsigned long long red64[2 * kWarps];
+    __shared__ int32_t  sh_i[8];
+    __shared__ uint32_t sh_u[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
     const Job job = p.jobs[job_id];
     const StreamDev st = p.streams[job.stream];
-    const uint32_t n = job.nsmpl, bps = p.bps, P = p.max_order;
+    const uint32_t n = job.nsmpl, P = p.max_order;
     const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
     CandOut *out = p.cand + (size_t)job_id * p.ncand + cand;
-    const uint32_t first_ch = (p.nch >= 2u) ? 2u : 0u;
-    const bool is_ms = (p.nch >= 2u) && (cand < 2u);
 
-    /* ---- load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) ---- */
-    int nz = 0;
-    for (uint32_t i = tid; i < n; i += kThreads) {
-        int32_t v;
-        if (is_ms) {
-            const int32_t l = asr32(load_sample(st, 0, job.offset + i), lshift);
-            const int32_t r = asr32(load_sample(st, 1, job.offset + i), lshift);
-            const int32_t side = (int32_t)((uint32_t)r - (uint32_t)l);
-            v = (cand == 1u) ? side : (int32_t)((uint32_t)l + (uint32_t)(side >> 1));
-        } else {
-            const int32_t raw = load_sample(st, cand - first_ch, job.offset + i);
-            nz |= raw;
-            v = asr32(raw, lshift);
-        }
-        region_i[i] = v;
-    }
+    int nz = load_candidate(st, job, p, cand, lshift, region_i);
     nz = __syncthreads_or(nz);
-    if (n <= P) {                                   /* RAW block (srla_encoder.c:777-779): nothing to analyse */
-        if (tid == 0) { out->nonzero = (nz != 0); out->status = 0; out->total_bits = 0; out->residual_bits = 0; out->order = 0; }
-        return;
+    if (tid == 0) {
+        out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
+        out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
+        out->total_bits = 0; out->residual_bits = 0; out->pre_coef = 0; out->pre_prev = 0;
     }
+    if (n <= P) { return; }                          /* RAW block (srla_encoder.c:777-779): nothing to analyse */
 
     /* ---- pre-emphasis coefficient (srla_utility.c:214-257): r0, r1 as exact integers ---- */
     {
@@ -473,10 +466,8 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
             for (int w = 0; w < kWarps; ++w) { s0 += (long long)red64[2 * w]; s1 += (long long)red64[2 * w + 1]; }
             int32_t c = 0;
             if (s0 != 0) {
-                double d0 = (double)s0, d1 = (double)s1;
-                double v = (d1 / d0) * 16.0;
-                bool exact = (s0 < (1ll << 53));
-                if (!exact) {
+                double v = ((double)s1 / (double)s0) * 16.0;
+                if (s0 >= (1ll << 53)) {
                     /* the reference's sequential double sums round above 2^53 (relative error
                      * <= n * 2^-53 each); only a value this close to a rounding boundary can differ */
                     const double frac = fabs(v) - floor(fabs(v));
@@ -492,22 +483,15 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
                 if (c > 15) { c = 15; }
             }
             sh_i[0] = c;
+            out->pre_coef = c; out->pre_prev = region_i[0];
         }
         __syncthreads();
     }
     const int32_t pre_coef = sh_i[0];
-    const int32_t pre_prev = region_i[0];
-    /* pre-emphasis (srla_utility.c:342-358), filter memory seeded with the first sample */
-    for (uint32_t i = tid; i < n; i += kThreads) {
-        const int32_t cur = region_i[i], prv = region_i[(i == 0u) ? 0u : i - 1u];
-        sig[i] = (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)pre_coef) >> 4));
-    }
-    if (tid < 4) { sig[-1 - tid] = 0; }
-    for (uint32_t i = n + tid; i < round_up_u32(n, 4) + 4u; i += kThreads) { sig[i] = 0; }
+    apply_preemphasis(region_i, sig, n, pre_coef);
     __syncthreads();
 
     /* ---- long-term prediction (srla_encoder.c:1008-1058) ---- */
-    uint32_t ltp_period = 0;
     if (p.ltp_order > 0u) {
         welch_autocorr<BPT>(sig, n, region_d, lags, kLtpLags, job, p);
         if (tid == 0) {
@@ -516,122 +500,185 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
             uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
             const int rc = ltp_solve(lags, p.ltp_order, &period, q);
             sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
+            out->status = (uint32_t)rc;
+            if (!rc && period > 0u) { out->ltp_period = period; out->ltp_coef[0] = q[0]; out->ltp_coef[1] = q[1]; out->ltp_coef[2] = q[2]; }
         }
         __syncthreads();
-        ltp_period = sh_u[0];
-        if (sh_u[1]) { if (tid == 0) { out->status = 1; out->nonzero = (nz != 0); } return; }
-        if (ltp_period > 0u) {
-            /* srla_lpc_predict.c:267-294 */
-            const uint32_t half_order = p.ltp_order >> 1;
-            const int32_t c0 = sh_i[1], c1 = sh_i[2], c2 = sh_i[3];
-            for (uint32_t i = tid; i < n; i += kThreads) {
-                int32_t v = sig[i];
-                if (i >= ltp_period + half_order + 1u) {
-                    const int32_t *x = sig + (i - ltp_period - half_order);
-                    uint32_t acc = 16u;
-                    acc += (uint32_t)c0 * (uint32_t)x[0];
-                    if (p.ltp_order > 1u) { acc += (uint32_t)c1 * (uint32_t)x[1]; acc += (uint32_t)c2 * (uint32_t)x[2]; }
-                    v = (int32_t)((uint32_t)v - (uint32_t)((int32_t)acc >> 5));
-                }
-                region_i[i] = v;
-            }
-            __syncthreads();
-            for (uint32_t i = tid; i < n; i += kThreads) { sig[i] = region_i[i]; }
-            __syncthreads();
-        }
+        if (sh_u[1]) { return; }
+        if (sh_u[0] > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
     }
 
-    /* ---- LPC: autocorrelation, Levinson-Durbin, order choice, quantisation ---- */
-    uint32_t order = 0, rshift = 0;
+    /* ---- autocorrelation of the signal the LPC stage sees (lpc.c:444-483) ---- */
     if (P > 0u) {
-        welch_autocorr<BPT>(sig, n, region_d, lags, P + 1u, job, p);
-        const uint32_t tri_len = tri_offset(P + 1u);
-        double *tri = (tri_len * 8u <= L.region_bytes) ? region_d : nullptr;
-        const uint32_t rowlen = round_up_u32(P + 4u, 2);
-        if (warp == 0) {
-            if (lane == 0) { lags[0] *= (1.0 + 1e-5); }          /* ridge, lpc.c:483 */
-            __syncwarp();
-            levinson_warp(lags, P, tri, rowbuf, rowlen, err);
-        }
-        __syncthreads();
-        /* error variances x window gain (lpc.c:493), estimated bits per order (srla_encoder.c:934-957) */
-        double my_cost = (double)FLT_MAX; uint32_t my_arg = 0;
-        if (warp == 0) {
-            for (uint32_t k = 1u + lane; k <= P; k += 32) {
-                const double ev = err[k] * job.welch_gain;
-                const double mean_abs = 2.0 * sqrt(ev / 2.0);
-                double bits = geometric_entropy(mean_abs, bps) * (double)n;
-                bits += (double)(8u * k);
-                if (my_cost > bits) { my_cost = bits; my_arg = k; }
+        double *g = p.lags + ((size_t)job_id * p.ncand + cand) * p.lag_stride;
+        welch_autocorr<BPT>(sig, n, region_d, g, P + 1u, job, p);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * lpc_kernel: one WARP per candidate.  Ridge, Levinson-Durbin for all orders, order choice,
+ * coefficient quantisation (lpc.c:379-441, 483-493, 1341-1405; srla_encoder.c:934-957, 1104-1108).
+ * The recursion is sequential in the order and its reflection numerators are sequential sums, so a
+ * candidate cannot use more than a warp; many warps per SM hide the dependent FP64 latency.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ double *levinson_warp(const double *r, const uint32_t stop, double *rowbuf, const uint32_t rowlen, double *err)
+{
+    const int lane = threadIdx.x & 31;
+    double *prev = rowbuf;
+    if (fabs(r[0]) < (double)FLT_EPSILON) {
+        for (uint32_t i = lane; i <= stop; i += 32) { err[i] = r[0]; }
+        for (uint32_t i = lane; i < rowlen; i += 32) { rowbuf[i] = 0.0; }      /* all coefficient vectors are zero */
+        __syncwarp();
+        return rowbuf;
+    }
+    double e = r[0];
+    {
+        const double a1 = -r[1] / r[0];
+        const double e1 = e + r[1] * a1;
+        if (lane == 0) { prev[0] = 1.0; prev[1] = a1; prev[2] = 0.0; err[0] = e; err[1] = e1; }
+        e = e1;
+    }
+    __syncwarp();
+    for (uint32_t k = 1; k < stop; ++k) {
+        double acc = 0.0;
+        {
+            const double *rr = r + k + 1;
+            uint32_t i = 0;
+            for (; i + 4 <= k + 1; i += 4) {
+                const double m0 = prev[i] * rr[-(int)i], m1 = prev[i + 1] * rr[-(int)i - 1];
+                const double m2 = prev[i + 2] * rr[-(int)i - 2], m3 = prev[i + 3] * rr[-(int)i - 3];
+                acc += m0; acc += m1; acc += m2; acc += m3;
             }
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double oc = __shfl_xor_sync(0xffffffffu, my_cost, o);
-                const uint32_t oa = __shfl_xor_sync(0xffffffffu, my_arg, o);
-                if (oa != 0u && (my_arg == 0u || oc < my_cost || (oc == my_cost && oa < my_arg))) { my_cost = oc; my_arg = oa; }
-            }
-            if (lane == 0) { sh_u[2] = my_arg; }
+            for (; i <= k; ++i) { acc += prev[i] * rr[-(int)i]; }
         }
-        __syncthreads();
-        order = sh_u[2];
-        if (p.diag) {
-            CandDiag *dg = p.diag + (size_t)job_id * p.ncand + cand;
-            for (uint32_t i = tid; i <= P; i += kThreads) { dg->autocorr[i] = lags[i]; dg->error_vars[i] = err[i] * job.welch_gain; }
-        }
-        if (order > 0u) {
-            const double *row;
-            if (tri) { row = tri + tri_offset(order); }
-            else {
-                if (warp == 0) { double *rp = levinson_warp(lags, order, nullptr, rowbuf, rowlen, err); if (lane == 0) { sh_u[3] = (uint32_t)(rp - rowbuf); } }
-                __syncthreads();
-                row = rowbuf + sh_u[3];
-            }
-            /* quantisation with error feedback from the tail (lpc.c:1341-1405), reversed for the FIR */
-            if (warp == 0) {
-                double peak = 0.0;
-                for (uint32_t i = lane; i < order; i += 32) { const double a = fabs(row[1u + i]); if (peak < a) { peak = a; } }
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { const double q = __shfl_xor_sync(0xffffffffu, peak, o); if (peak < q) { peak = q; } }
-                const uint32_t p4 = round_up_u32(order, 4);
-                if (peak <= 0.0078125) {
-                    for (uint32_t i = lane; i < p4; i += 32) { coef_s[i] = 0; }
-                    if (lane == 0) { sh_u[4] = 8u; }
-                } else {
-                    int exponent;
-                    (void)frexp(peak, &exponent);
-                    uint32_t rs = (uint32_t)(7 - exponent);
-                    if (rs >= 16u) { rs = 15u; }
-                    if (lane == 0) {
-                        const double scale = (double)(1u << rs);
-                        double carry = 0.0;
-                        for (uint32_t i = 0; i < p4 - order; ++i) { coef_s[i] = 0; }
-                        for (int i = (int)order - 1; i >= 0; --i) {
-                            carry += row[1 + i] * scale;
-                            int32_t v = (int32_t)round_half_away(carry);
-                            if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
-                            carry -= (double)v;
-                            /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
-                            coef_s[(p4 - order) + (order - 1u - (uint32_t)i)] = v;
-                        }
-                        sh_u[4] = rs;
-                    }
+        const double refl = acc / (-e);
+        const double e_next = e * (1.0 - refl * refl);
+        double *next = (prev == rowbuf) ? rowbuf + rowlen : rowbuf;
+        for (uint32_t i = lane; i <= k + 1u; i += 32) { next[i] = prev[i] + refl * prev[k + 1u - i]; }
+        if (lane == 0) { next[k + 2u] = 0.0; err[k + 1u] = e_next; }
+        e = e_next;
+        prev = next;
+        __syncwarp();
+    }
+    return prev;
+}
+
+__global__ void __launch_bounds__(kThreads) lpc_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const LpcLayout L = make_lpc_layout(p.max_order);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t idx = blockIdx.x * kWarps + warp;
+    if (idx >= p.num_jobs * p.ncand) { return; }
+    const uint32_t job_id = idx / p.ncand;
+    const uint32_t n = p.jobs[job_id].nsmpl, P = p.max_order, bps = p.bps;
+    CandOut *out = p.cand + idx;
+    if (n <= P || out->status != 0u) { return; }
+    const double welch_gain = p.jobs[job_id].welch_gain;
+    unsigned char *mine = smem + (size_t)warp * L.per_warp;
+    double *r = reinterpret_cast<double *>(mine + L.r_off);
+    double *rowbuf = reinterpret_cast<double *>(mine + L.row_off);
+    double *err = reinterpret_cast<double *>(mine + L.err_off);
+    const double *g = p.lags + (size_t)idx * p.lag_stride;
+    for (uint32_t i = lane; i <= P; i += 32) { double v = g[i]; if (i == 0u) { v *= (1.0 + 1e-5); } r[i] = v; }   /* ridge, lpc.c:483 */
+    __syncwarp();
+    double *row = levinson_warp(r, P, rowbuf, L.rowlen, err);
+    /* error variances x window gain (lpc.c:493), estimated bits per order (srla_encoder.c:934-957) */
+    double my_cost = (double)FLT_MAX; uint32_t my_arg = 0;
+    for (uint32_t k = 1u + lane; k <= P; k += 32) {
+        const double ev = err[k] * welch_gain;
+        const double mean_abs = 2.0 * sqrt(ev / 2.0);
+        double bits = geometric_entropy(mean_abs, bps) * (double)n;
+        bits += (double)(8u * k);
+        if (my_cost > bits) { my_cost = bits; my_arg = k; }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oc = __shfl_xor_sync(0xffffffffu, my_cost, o);
+        const uint32_t oa = __shfl_xor_sync(0xffffffffu, my_arg, o);
+        if (oa != 0u && (my_arg == 0u || oc < my_cost || (oc == my_cost && oa < my_arg))) { my_cost = oc; my_arg = oa; }
+    }
+    const uint32_t order = my_arg;
+    if (p.diag) {
+        CandDiag *dg = p.diag + idx;
+        for (uint32_t i = lane; i <= P; i += 32) { dg->autocorr[i] = r[i]; dg->error_vars[i] = err[i] * welch_gain; }
+    }
+    uint32_t rshift = 0;
+    if (order > 0u) {
+        if (order != P) { __syncwarp(); row = levinson_warp(r, order, rowbuf, L.rowlen, err); }
+        /* quantisation with error feedback from the tail (lpc.c:1341-1405), reversed for the FIR */
+        double peak = 0.0;
+        for (uint32_t i = lane; i < order; i += 32) { const double a = fabs(row[1u + i]); if (peak < a) { peak = a; } }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const double q = __shfl_xor_sync(0xffffffffu, peak, o); if (peak < q) { peak = q; } }
+        if (peak <= 0.0078125) {
+            for (uint32_t i = lane; i < order; i += 32) { out->coef[i] = 0; }
+            rshift = 8u;
+        } else {
+            int exponent;
+            (void)frexp(peak, &exponent);
+            rshift = (uint32_t)(7 - exponent);
+            if (rshift >= 16u) { rshift = 15u; }
+            if (lane == 0) {
+                const double scale = (double)(1u << rshift);
+                double carry = 0.0;
+                for (int i = (int)order - 1; i >= 0; --i) {
+                    carry += row[1 + i] * scale;
+                    int32_t v = (int32_t)round_half_away(carry);
+                    if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
+                    carry -= (double)v;
+                    /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
+                    out->coef[order - 1u - (uint32_t)i] = (int16_t)v;
                 }
             }
-            __syncthreads();
-            rshift = sh_u[4];
-            if (p.diag) {
-                CandDiag *dg = p.diag + (size_t)job_id * p.ncand + cand;
-                for (uint32_t i = tid; i < order; i += kThreads) { dg->lpc_double[i] = row[1u + i]; }
-            }
-            __syncthreads();          /* `row` may live in the region that the residual overwrites next */
+        }
+        if (p.diag) {
+            CandDiag *dg = p.diag + idx;
+            for (uint32_t i = lane; i < order; i += 32) { dg->lpc_double[i] = row[1u + i]; }
         }
     }
+    if (lane == 0) { out->order = order; out->rshift = rshift; }
+}
 
-    /* ---- FIR residual (srla_lpc_predict.c:236-264), int32 wrapping ---- */
+/* ------------------------------------------------------------------------------------------------
+ * residual_kernel: one CTA per (job, candidate).  Rebuilds the candidate signal, runs the int32
+ * FIR (srla_lpc_predict.c:236-264), the residual coder search (srla_coder.c:349-483) and the
+ * side-information accounting (srla_encoder.c:1122-1187).
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ResidLayout L = make_resid_layout(p.nmax, p.max_order);
+    int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
+    int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;
+    int32_t  *coef_s   = reinterpret_cast<int32_t *>(smem + L.coef_off);
+    uint8_t  *ktab     = smem + L.ktab_off;
+    uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
+    const Job job = p.jobs[job_id];
+    const StreamDev st = p.streams[job.stream];
+    const uint32_t n = job.nsmpl, bps = p.bps;
+    const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+    CandOut *out = p.cand + (size_t)job_id * p.ncand + cand;
+    if (n <= p.max_order || out->status != 0u) { return; }
+    const uint32_t order = out->order, rshift = out->rshift, ltp_period = out->ltp_period;
+    const int32_t pre_coef = out->pre_coef;
+
+    /* ---- rebuild the signal the FIR runs on ---- */
+    (void)load_candidate(st, job, p, cand, lshift, region_i);
+    const uint32_t p4 = round_up_u32(order, 4);
+    for (uint32_t i = tid; i < p4; i += kThreads) { coef_s[i] = (i < p4 - order) ? 0 : (int32_t)out->coef[i - (p4 - order)]; }
+    __syncthreads();
+    apply_preemphasis(region_i, sig, n, pre_coef);
+    __syncthreads();
+    if (ltp_period > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, ltp_period, out->ltp_coef[0], out->ltp_coef[1], out->ltp_coef[2]); }
+
+    /* ---- FIR residual, int32 wrapping ---- */
     int32_t *res_s = region_i;
     int32_t *res_g = p.residual ? p.residual + ((size_t)job_id * p.ncand + cand) * p.res_stride : nullptr;
     if (order > 0u) {
-        const uint32_t p4 = round_up_u32(order, 4);
         const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
         const uint32_t groups = (n + 3u) >> 2;
         const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
@@ -674,44 +721,47 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
                 }
             }
             *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+            if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
         }
     } else {
-        for (uint32_t i = tid; i < n; i += kThreads) { res_s[i] = sig[i]; }
+        for (uint32_t i = tid; i < n; i += kThreads) { const int32_t v = sig[i]; res_s[i] = v; if (res_g) { res_g[i] = v; } }
     }
     __syncthreads();
-    if (res_g) { for (uint32_t i = tid; i < n; i += kThreads) { res_g[i] = res_s[i]; } }
 
     /* ---- residual coder search (srla_coder.c:349-483) ---- */
     uint32_t max_porder = 0;
     while (max_porder < (uint32_t)kLog2MaxParts && (n % (2u << max_porder)) == 0u) { max_porder++; }
     const uint32_t nparts = 1u << max_porder, per = n >> max_porder;
-    uint32_t *u = reinterpret_cast<uint32_t *>(region_i);
     double *mean = reinterpret_cast<double *>(smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16));   /* heap layout: level l at (1<<l)-1 */
+    /* finest partition means: exact integer sums / per (srla_coder.c:371-383) */
     uint32_t any = 0;
-    for (uint32_t i = tid; i < n; i += kThreads) { const uint32_t v = zigzag32(res_s[i]); u[i] = v; any |= v; }
+    if (per <= 32u) {
+        for (uint32_t q = tid; q < nparts; q += kThreads) {
+            unsigned long long s = 0;
+            const int32_t *rp = res_s + q * per;
+            if (per == 4u) {
+                const int4 v = *reinterpret_cast<const int4 *>(rp);
+                const uint32_t u0 = zigzag32(v.x), u1 = zigzag32(v.y), u2 = zigzag32(v.z), u3 = zigzag32(v.w);
+                s = (unsigned long long)u0 + u1 + u2 + u3; any |= u0 | u1 | u2 | u3;
+            } else {
+                for (uint32_t i = 0; i < per; ++i) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
+            }
+            mean[(nparts - 1u) + q] = (double)s / (double)per;
+        }
+    } else {
+        for (uint32_t q = warp; q < nparts; q += kWarps) {
+            unsigned long long s = 0;
+            const int32_t *rp = res_s + q * per;
+            for (uint32_t i = lane; i < per; i += 32) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
+            s = (unsigned long long)warp_sum_ll((long long)s);
+            if (lane == 0) { mean[(nparts - 1u) + q] = (double)s / (double)per; }
+        }
+    }
     any = (uint32_t)__syncthreads_or((int)(any != 0u));
     uint32_t code_type, best_porder = 0, residual_bits;
     if (!any) {
         code_type = kCodeAllZero; residual_bits = 2u;
     } else {
-        /* finest partition means: exact integer sums / per */
-        if (per <= 32u) {
-            for (uint32_t q = tid; q < nparts; q += kThreads) {
-                unsigned long long s = 0;
-                const uint32_t *up = u + q * per;
-                for (uint32_t i = 0; i < per; ++i) { s += up[i]; }
-                mean[(nparts - 1u) + q] = (double)s / (double)per;
-            }
-        } else {
-            for (uint32_t q = warp; q < nparts; q += kWarps) {
-                unsigned long long s = 0;
-                const uint32_t *up = u + q * per;
-                for (uint32_t i = lane; i < per; i += 32) { s += up[i]; }
-                s = (unsigned long long)warp_sum_ll((long long)s);
-                if (lane == 0) { mean[(nparts - 1u) + q] = (double)s / (double)per; }
-            }
-        }
-        __syncthreads();
         for (int lvl = (int)max_porder - 1; lvl >= 0; --lvl) {
             const uint32_t cnt = 1u << lvl, base = cnt - 1u, child = 2u * cnt - 1u;
             for (uint32_t q = tid; q < cnt; q += kThreads) { mean[base + q] = (mean[child + 2u * q] + mean[child + 2u * q + 1u]) / 2.0; }
@@ -734,24 +784,63 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
             ktab[e] = (uint8_t)k;
         }
         __syncthreads();
-        /* bits of every partition order */
+        /* bits of every partition order: each thread walks whole finest partitions */
         uint32_t acc[kLog2MaxParts + 1];
         #pragma unroll
         for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = 0; }
-        const bool per_pow2 = (per & (per - 1u)) == 0u;
-        const uint32_t per_shift = 31u - (uint32_t)__clz((int)per);
-        for (uint32_t i = tid; i < n; i += kThreads) {
-            const uint32_t v = u[i];
-            const uint32_t q = per_pow2 ? (i >> per_shift) : (i / per);
-            #pragma unroll
-            for (int l = 0; l <= kLog2MaxParts; ++l) {
-                if ((uint32_t)l <= max_porder) {
-                    const uint32_t k = ktab[((1u << l) - 1u) + (q >> (max_porder - (uint32_t)l))];
-                    if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
+        if (per <= 32u) {
+            for (uint32_t q = tid; q < nparts; q += kThreads) {
+                uint32_t kk[kLog2MaxParts + 1];
+                #pragma unroll
+                for (int l = 0; l <= kLog2MaxParts; ++l) {
+                    kk[l] = ((uint32_t)l <= max_porder) ? ktab[((1u << l) - 1u) + (q >> (max_porder - (uint32_t)l))] : 0u;
+                }
+                const int32_t *rp = res_s + q * per;
+                for (uint32_t i0 = 0; i0 < per; i0 += 4u) {
+                    uint32_t v[4];
+                    if (per == 4u) { const int4 t = *reinterpret_cast<const int4 *>(rp); v[0] = zigzag32(t.x); v[1] = zigzag32(t.y); v[2] = zigzag32(t.z); v[3] = zigzag32(t.w); }
                     else {
-                        const uint32_t k1 = k + 1u;
-                        const int32_t over = (int32_t)v - (int32_t)(1u << k1);
-                        acc[l] += (k1 + 1u) + ((uint32_t)((over > 0) ? over : 0) >> k);
+                        #pragma unroll
+                        for (int t = 0; t < 4; ++t) { v[t] = (i0 + t < per) ? zigzag32(rp[i0 + t]) : 0u; }
+                    }
+                    const uint32_t cnt = (per - i0 < 4u) ? per - i0 : 4u;
+                    #pragma unroll
+                    for (int l = 0; l <= kLog2MaxParts; ++l) {
+                        if ((uint32_t)l <= max_porder) {
+                            const uint32_t k = kk[l];
+                            uint32_t add = 0;
+                            if (code_type == kCodeRice) {
+                                #pragma unroll
+                                for (int t = 0; t < 4; ++t) { if ((uint32_t)t < cnt) { add += 1u + k + (v[t] >> k); } }
+                            } else {
+                                const uint32_t k1 = k + 1u;
+                                #pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    if ((uint32_t)t < cnt) {
+                                        const int32_t over = (int32_t)v[t] - (int32_t)(1u << k1);
+                                        add += (k1 + 1u) + ((uint32_t)((over > 0) ? over : 0) >> k);
+                                    }
+                                }
+                            }
+                            acc[l] += add;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (uint32_t i = tid; i < n; i += kThreads) {
+                const uint32_t v = zigzag32(res_s[i]);
+                const uint32_t q = i / per;
+                #pragma unroll
+                for (int l = 0; l <= kLog2MaxParts; ++l) {
+                    if ((uint32_t)l <= max_porder) {
+                        const uint32_t k = ktab[((1u << l) - 1u) + (q >> (max_porder - (uint32_t)l))];
+                        if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
+                        else {
+                            const uint32_t k1 = k + 1u;
+                            const int32_t over = (int32_t)v - (int32_t)(1u << k1);
+                            acc[l] += (k1 + 1u) + ((uint32_t)((over > 0) ? over : 0) >> k);
+                        }
                     }
                 }
             }
@@ -787,7 +876,6 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
     /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */
     if (warp == 0) {
         uint32_t plain_bits = 0, sum_bits = 0, bad = 0;
-        const uint32_t p4 = round_up_u32(order, 4);
         const int32_t *cf = coef_s + (p4 - order);
         for (uint32_t i = lane; i < order; i += 32) {
             const int32_t c = cf[i];
@@ -798,7 +886,6 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
                 const uint32_t sym = zigzag32(c + cf[i - 1u]);
                 if (sym >= 256u) { bad = 1; } else { sum_bits += __ldg(p.huff_len + 256 + sym); }
             }
-            out->coef[i] = (int16_t)c;
         }
         plain_bits = warp_sum_u32(plain_bits); sum_bits = warp_sum_u32(sum_bits); bad = warp_sum_u32(bad);
         if (lane == 0) {
@@ -814,15 +901,9 @@ __global__ void __launch_bounds__(kThreads) analyse_kernel(const __grid_constant
             bits += coef_bits;
             bits += 1u;
             if (ltp_period > 0u) { bits += 1u + 8u + p.ltp_order * 6u; }
-            out->pre_coef = pre_coef; out->pre_prev = pre_prev;
-            out->order = order; out->rshift = rshift; out->use_sum = use_sum; out->coef_bits = coef_bits;
-            out->ltp_period = ltp_period;
-            out->ltp_coef[0] = (ltp_period > 0u) ? sh_i[1] : 0;
-            out->ltp_coef[1] = (ltp_period > 0u) ? sh_i[2] : 0;
-            out->ltp_coef[2] = (ltp_period > 0u) ? sh_i[3] : 0;
+            out->use_sum = use_sum; out->coef_bits = coef_bits;
             out->code_type = code_type; out->porder = best_porder;
             out->residual_bits = residual_bits; out->total_bits = bits;
-            out->nonzero = (nz != 0); out->status = 0;
         }
     }
 }

@@ -75,13 +75,13 @@ struct DeviceCtx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_analyse, ev_emit;
+    std::vector<cudaEvent_t> ev_pool;      /* per batch: front begin, lpc begin, residual begin, decide begin, end */
     size_t ev_used = 0;
     /* tables */
     DevBuf tw_complex, tw_real, rice_thr, huff_code, huff_len;
     uint32_t tw_c_off[20], tw_r_off[20];
     /* work */
-    DevBuf streams, jobs, cand, diag, jobout, residual, misc, stream_begin, pcm, out;
+    DevBuf streams, jobs, cand, diag, jobout, residual, lags, misc, stream_begin, pcm, out;
     PinBuf h_jobs, h_small, h_jobout, h_result;
     int max_smem_optin = 0;
     int num_sms = 0;
@@ -160,12 +160,11 @@ void ctx_destroy(DeviceCtx *c)
     if (!c) { return; }
     cudaSetDevice(c->device);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); }
-    for (auto &e : c->ev_analyse) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (auto &e : c->ev_emit) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (cudaEvent_t e : c->ev_pool) { cudaEventDestroy(e); }
     if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
     DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs, &c->cand,
-                       &c->diag, &c->jobout, &c->residual, &c->misc, &c->stream_begin, &c->pcm, &c->out };
+                       &c->diag, &c->jobout, &c->residual, &c->lags, &c->misc, &c->stream_begin, &c->pcm, &c->out };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release();
     if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
@@ -250,41 +249,60 @@ struct Runner {
         return p;
     }
 
-    bool next_events(std::vector<std::pair<cudaEvent_t, cudaEvent_t>> &pool, size_t idx, cudaEvent_t *a, cudaEvent_t *b)
+    bool mark(size_t batch, int slot)
     {
-        while (pool.size() <= idx) {
-            cudaEvent_t x, y;
-            CU_TRY(cudaEventCreate(&x)); CU_TRY(cudaEventCreate(&y));
-            pool.emplace_back(x, y);
-        }
-        *a = pool[idx].first; *b = pool[idx].second;
+        const size_t idx = batch * 5 + (size_t)slot;
+        while (c->ev_pool.size() <= idx) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->ev_pool.push_back(e); }
+        CU_TRY(cudaEventRecord(c->ev_pool[idx], c->stream));
         return true;
     }
 
-    bool launch_analyse(const LaunchParams &p)
+    template <typename K>
+    bool prep_kernel(K kernel, uint32_t smem_bytes)
     {
-        const AnalyseLayout L = make_analyse_layout(p.nmax, p.fft_max, p.max_order, p.ltp_order);
-        if ((int)L.total + 256 > c->max_smem_optin) {
-            std::fprintf(stderr, "[srla_b200] block of %u samples needs %u bytes of shared memory (> %d)\n", p.nmax, L.total, c->max_smem_optin);
+        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        return true;
+    }
+
+    /* the three analysis kernels: front (autocorrelation) -> lpc (Levinson-Durbin) -> residual (FIR + Rice search) */
+    bool launch_analyse(const LaunchParams &p, size_t batch)
+    {
+        const FrontLayout FL = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
+        const LpcLayout LL = make_lpc_layout(p.max_order);
+        const ResidLayout RL = make_resid_layout(p.nmax, p.max_order);
+        if ((int)std::max(FL.total, RL.total) + 1024 > c->max_smem_optin) {
+            std::fprintf(stderr, "[srla_b200] block of %u samples needs %u bytes of shared memory (> %d)\n", p.nmax, std::max(FL.total, RL.total), c->max_smem_optin);
             return false;
         }
-        const dim3 grid(p.num_jobs * p.ncand), block(kThreads);
+        const uint32_t ncands = p.num_jobs * p.ncand;
+        const dim3 grid(ncands), block(kThreads);
         const uint32_t bpt = (p.fft_max + 2047u) / 2048u;
         if (bpt <= 1) {
-            CU_TRY(cudaFuncSetAttribute(analyse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-            analyse_kernel<1><<<grid, block, L.total, c->stream>>>(p);
+            if (!prep_kernel(front_kernel<1>, FL.total)) { return false; }
+            front_kernel<1><<<grid, block, FL.total, c->stream>>>(p);
         } else if (bpt == 2) {
-            CU_TRY(cudaFuncSetAttribute(analyse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-            analyse_kernel<2><<<grid, block, L.total, c->stream>>>(p);
+            if (!prep_kernel(front_kernel<2>, FL.total)) { return false; }
+            front_kernel<2><<<grid, block, FL.total, c->stream>>>(p);
         } else if (bpt <= 4) {
-            CU_TRY(cudaFuncSetAttribute(analyse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-            analyse_kernel<4><<<grid, block, L.total, c->stream>>>(p);
+            if (!prep_kernel(front_kernel<4>, FL.total)) { return false; }
+            front_kernel<4><<<grid, block, FL.total, c->stream>>>(p);
         } else {
             std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
             return false;
         }
-        CU_TRY(cudaGetLastError());
         launches++;
+        if (!mark(batch, 1)) { return false; }
+        if (p.max_order > 0) {
+            if (!prep_kernel(lpc_kernel, LL.total)) { return false; }
+            lpc_kernel<<<(ncands + kWarps - 1) / kWarps, block, LL.total, c->stream>>>(p);
+            launches++;
+        }
+        if (!mark(batch, 2)) { return false; }
+        if (!prep_kernel(residual_kernel, RL.total)) { return false; }
+        residual_kernel<<<grid, block, RL.total, c->stream>>>(p);
+        launches++;
+        CU_TRY(cudaGetLastError());
         return true;
     }
 
@@ -323,18 +341,18 @@ struct Runner {
         if (!c->cand.reserve(sizeof(CandOut) * ncand * count) || !c->jobout.reserve(sizeof(JobOut) * count)) { return false; }
         if (store_residual && !c->residual.reserve(sizeof(int32_t) * ncand * count * (size_t)p.res_stride)) { return false; }
         if (pl.want_diag && !c->diag.reserve(sizeof(CandDiag) * ncand * count)) { return false; }
+        p.lag_stride = round_up_u32(p.max_order + 2u, 2);
+        if (!c->lags.reserve(sizeof(double) * ncand * count * (size_t)p.lag_stride)) { return false; }
+        p.lags = (double *)c->lags.p;
         p.cand = (CandOut *)c->cand.p; p.jobout = (JobOut *)c->jobout.p;
         p.residual = store_residual ? (int32_t *)c->residual.p : nullptr;
         p.diag = pl.want_diag ? (CandDiag *)c->diag.p : nullptr;
         p.out = d_out; p.out_capacity = cap;
         const uint32_t raw_max = 11u + (uint32_t)(((uint64_t)p.bps * nmax * p.nch) / 8u);
         p.emit_smem_bytes = raw_max;
-        cudaEvent_t a0, a1, e0, e1;
-        if (!next_events(c->ev_analyse, ev_idx, &a0, &a1) || !next_events(c->ev_emit, ev_idx, &e0, &e1)) { return false; }
-        CU_TRY(cudaEventRecord(a0, c->stream));
-        if (!launch_analyse(p)) { return false; }
-        CU_TRY(cudaEventRecord(a1, c->stream));
-        CU_TRY(cudaEventRecord(e0, c->stream));
+        if (!mark(ev_idx, 0)) { return false; }
+        if (!launch_analyse(p, ev_idx)) { return false; }
+        if (!mark(ev_idx, 3)) { return false; }
         decide_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(p);
         launches++;
         if (emit) {
@@ -346,7 +364,7 @@ struct Runner {
             launches += 2;
         }
         CU_TRY(cudaGetLastError());
-        CU_TRY(cudaEventRecord(e1, c->stream));
+        if (!mark(ev_idx, 4)) { return false; }
         return true;
     }
 
@@ -514,10 +532,10 @@ struct Runner {
         for (int i = 0; i < 3; i++) { stt.type_histogram[i] = dstats[260 + i]; }
         cudaEventElapsedTime(&stt.ms_total_device, c->ev_begin, c->ev_end);
         for (size_t i = 0; i < ev_idx; i++) {
-            float a = 0, e = 0;
-            cudaEventElapsedTime(&a, c->ev_analyse[i].first, c->ev_analyse[i].second);
-            cudaEventElapsedTime(&e, c->ev_emit[i].first, c->ev_emit[i].second);
-            stt.ms_analyse += a; stt.ms_emit += e;
+            float t[4] = { 0, 0, 0, 0 };
+            for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&t[k], c->ev_pool[i * 5 + k], c->ev_pool[i * 5 + k + 1]); }
+            stt.ms_front += t[0]; stt.ms_lpc += t[1]; stt.ms_residual += t[2]; stt.ms_emit += t[3];
+            stt.ms_analyse += t[0] + t[1] + t[2];
         }
         if (single_estimate) { *single_estimate = first->estimate_bytes; if (first->status) { return SRLA_APIRESULT_NG; } }
         if (pl.size_only) { return SRLA_APIRESULT_OK; }

@@ -91,6 +91,8 @@ struct LaunchParams {
     CandDiag        *diag;           /* [job][cand] or NULL                                */
     JobOut          *jobout;         /* [job]                                              */
     int32_t         *residual;       /* [job][cand][res_stride] or NULL (size-only pass)   */
+    double          *lags;           /* [job][cand][lag_stride]: autocorrelation lags 0..P  */
+    uint32_t lag_stride;
     uint32_t num_jobs, num_streams;
     uint32_t nch, ncand, bps;
     uint32_t max_order;              /* preset's maximum LPC order                         */
@@ -120,19 +122,7 @@ struct LaunchParams {
     uint32_t *stats;                 /* order[256], method[4], type[3]                      */
 };
 
-/* shared-memory layout of the analyse kernel (identical on host and device) */
-struct AnalyseLayout {
-    uint32_t region_off, region_bytes; /* FFT buffer / residual + mean pyramid (time-shared)   */
-    uint32_t sig_off;                  /* int32: 4 pad + nmax rounded up to 4                  */
-    uint32_t lags_off, nlags;          /* doubles                                              */
-    uint32_t row_off;                  /* 2 x (P + 4) doubles                                  */
-    uint32_t err_off;                  /* P + 2 doubles                                        */
-    uint32_t coef_off;                 /* int32 x (roundup4(P) + 4)                            */
-    uint32_t ktab_off;                 /* 2048 bytes                                           */
-    uint32_t red_off;                  /* 1024 bytes of reduction scratch                      */
-    uint32_t total;
-};
-
+/* shared-memory layouts (identical on host and device) */
 #if defined(__CUDACC__)
 #define SRLA_HD __host__ __device__
 #else
@@ -141,23 +131,63 @@ struct AnalyseLayout {
 
 SRLA_HD inline uint32_t round_up_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-SRLA_HD inline AnalyseLayout make_analyse_layout(uint32_t nmax, uint32_t fft_max, uint32_t P, uint32_t ltp)
+/* front_kernel: FFT buffer, the pre-emphasised signal, LTP lags */
+struct FrontLayout {
+    uint32_t region_off, region_bytes; /* FFT buffer (doubles) / int32 scratch                 */
+    uint32_t sig_off;                  /* int32: 4 pad + nmax rounded up to 4 + 4              */
+    uint32_t lags_off, nlags;          /* doubles (LTP pitch search only)                      */
+    uint32_t total;
+};
+SRLA_HD inline FrontLayout make_front_layout(uint32_t nmax, uint32_t fft_max, uint32_t ltp)
 {
-    AnalyseLayout L;
+    FrontLayout L;
     const uint32_t n4 = round_up_u32(nmax, 4);
-    const uint32_t parts = (nmax < (uint32_t)kMaxParts) ? nmax : (uint32_t)kMaxParts;
-    uint32_t fft_bytes = 8u * fft_max;
-    uint32_t rice_bytes = 4u * n4 + 16u * round_up_u32(parts, 2) + 16u;
     uint32_t off = 0;
     L.region_off = off;
-    L.region_bytes = round_up_u32((fft_bytes > rice_bytes) ? fft_bytes : rice_bytes, 16);
+    L.region_bytes = round_up_u32((8u * fft_max > 4u * n4) ? 8u * fft_max : 4u * n4, 16);
     off += L.region_bytes;
-    L.sig_off = off; off += 4u * (n4 + 4u) + 16u;   /* + one spare int4 for the FIR look-ahead load */
-    L.nlags = (P + 2 > (ltp ? (uint32_t)kLtpLags : 0u)) ? P + 2 : (uint32_t)kLtpLags;
-    L.nlags = round_up_u32(L.nlags, 2);
+    L.sig_off = off; off += 4u * (n4 + 8u);
+    L.nlags = ltp ? round_up_u32((uint32_t)kLtpLags, 2) : 0u;
     L.lags_off = off; off += 8u * L.nlags;
-    L.row_off = off; off += 8u * 2u * round_up_u32(P + 4, 2);
-    L.err_off = off; off += 8u * round_up_u32(P + 2, 2);
+    L.total = off;
+    return L;
+}
+
+/* lpc_kernel: per warp r[], two coefficient rows, error variances */
+struct LpcLayout {
+    uint32_t r_off, row_off, rowlen, err_off, per_warp, total;
+};
+SRLA_HD inline LpcLayout make_lpc_layout(uint32_t P)
+{
+    LpcLayout L;
+    L.rowlen = round_up_u32(P + 4u, 2);
+    L.r_off = 0;
+    L.row_off = 8u * round_up_u32(P + 2u, 2);
+    L.err_off = L.row_off + 8u * 2u * L.rowlen;
+    L.per_warp = L.err_off + 8u * round_up_u32(P + 2u, 2);
+    L.total = L.per_warp * (uint32_t)kWarps;
+    return L;
+}
+
+/* residual_kernel: signal, residual + mean pyramid, coefficients, parameter table */
+struct ResidLayout {
+    uint32_t region_off, region_bytes; /* int32 residual[n4] then the mean pyramid (doubles)   */
+    uint32_t sig_off;
+    uint32_t coef_off;                 /* int32 x (roundup4(P) + 4)                            */
+    uint32_t ktab_off;                 /* 2048 bytes                                           */
+    uint32_t red_off;                  /* 1024 bytes of reduction scratch                      */
+    uint32_t total;
+};
+SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
+{
+    ResidLayout L;
+    const uint32_t n4 = round_up_u32(nmax, 4);
+    const uint32_t parts = (nmax < (uint32_t)kMaxParts) ? nmax : (uint32_t)kMaxParts;
+    uint32_t off = 0;
+    L.region_off = off;
+    L.region_bytes = round_up_u32(4u * n4 + 16u * round_up_u32(parts, 2) + 16u, 16);
+    off += L.region_bytes;
+    L.sig_off = off; off += 4u * (n4 + 8u);
     L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
     L.ktab_off = off; off += 2048u;
     L.red_off = off; off += 1024u;

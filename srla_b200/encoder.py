@@ -60,7 +60,8 @@ class SRLAB200Stats(C.Structure):
                 ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64),
                 ("ms_analyse", C.c_float), ("ms_emit", C.c_float), ("ms_total_device", C.c_float),
                 ("order_histogram", C.c_uint32 * 256), ("method_histogram", C.c_uint32 * 4),
-                ("type_histogram", C.c_uint32 * 3)]
+                ("type_histogram", C.c_uint32 * 3),
+                ("ms_front", C.c_float), ("ms_lpc", C.c_float), ("ms_residual", C.c_float)]
 
 
 class SRLAB200ChannelResult(C.Structure):
