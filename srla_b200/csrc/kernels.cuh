@@ -4,7 +4,7 @@
  *   lshift_or_kernel / lshift_finish_kernel   whole-stream OR reduce -> trailing-zero shift   (A0)
  *   front_kernel<BPT>       one CTA per (block, candidate channel): mid/side, pre-emphasis, optional LTP,
  *                           Welch window + FFT autocorrelation, block resident in shared memory (A2-A5, A11)
- *   lpc_kernel              one warp per candidate: Levinson-Durbin, order choice, quantisation     (A5, A6)
+ *   lpc_kernel              one thread per candidate: Levinson-Durbin, order choice, quantisation   (A5, A6)
  *   residual_kernel         one CTA per candidate: int32 FIR residual, Rice search, side-info bits   (A3, A7, A8)
  *   decide_kernel           block type, stereo method, exact block size                       (A1, A2)
  *   scan_kernel             output offsets of the blocks / streams
@@ -516,129 +516,131 @@ __global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__
 }
 
 /* ------------------------------------------------------------------------------------------------
- * lpc_kernel: one WARP per candidate.  Ridge, Levinson-Durbin for all orders, order choice,
- * coefficient quantisation (lpc.c:379-441, 483-493, 1341-1405; srla_encoder.c:934-957, 1104-1108).
- * The recursion is sequential in the order and its reflection numerators are sequential sums, so a
- * candidate cannot use more than a warp; many warps per SM hide the dependent FP64 latency.
+ * lpc_kernel: one THREAD per candidate (32 candidates per CTA).  Ridge, Levinson-Durbin for all
+ * orders, order choice, coefficient quantisation (lpc.c:379-441, 483-493, 1341-1405;
+ * srla_encoder.c:934-957, 1104-1108).
+ * The recursion is sequential in the order and its reflection numerators are sequential sums in the
+ * reference's order, so the work of one candidate is a dependent chain: it gets one lane, and the
+ * lags / coefficient vectors of the 32 candidates of a warp are interleaved in shared memory
+ * ([index][lane]) so every access is conflict free.  The coefficient vector is updated in place in
+ * symmetric pairs (new[i], new[k+1-i] depend only on prev[i], prev[k+1-i]).
  * ---------------------------------------------------------------------------------------------- */
-__device__ double *levinson_warp(const double *r, const uint32_t stop, double *rowbuf, const uint32_t rowlen, double *err)
+struct OrderPick { double best; uint32_t arg; };
+__device__ __forceinline__ void consider_order(OrderPick &pk, double err_k, uint32_t k, double gain, uint32_t n, uint32_t bps)
 {
-    const int lane = threadIdx.x & 31;
-    double *prev = rowbuf;
-    if (fabs(r[0]) < (double)FLT_EPSILON) {
-        for (uint32_t i = lane; i <= stop; i += 32) { err[i] = r[0]; }
-        for (uint32_t i = lane; i < rowlen; i += 32) { rowbuf[i] = 0.0; }      /* all coefficient vectors are zero */
-        __syncwarp();
-        return rowbuf;
-    }
-    double e = r[0];
-    {
-        const double a1 = -r[1] / r[0];
-        const double e1 = e + r[1] * a1;
-        if (lane == 0) { prev[0] = 1.0; prev[1] = a1; prev[2] = 0.0; err[0] = e; err[1] = e1; }
-        e = e1;
-    }
-    __syncwarp();
-    for (uint32_t k = 1; k < stop; ++k) {
-        double acc = 0.0;
-        {
-            const double *rr = r + k + 1;
-            uint32_t i = 0;
-            for (; i + 4 <= k + 1; i += 4) {
-                const double m0 = prev[i] * rr[-(int)i], m1 = prev[i + 1] * rr[-(int)i - 1];
-                const double m2 = prev[i + 2] * rr[-(int)i - 2], m3 = prev[i + 3] * rr[-(int)i - 3];
-                acc += m0; acc += m1; acc += m2; acc += m3;
-            }
-            for (; i <= k; ++i) { acc += prev[i] * rr[-(int)i]; }
-        }
-        const double refl = acc / (-e);
-        const double e_next = e * (1.0 - refl * refl);
-        double *next = (prev == rowbuf) ? rowbuf + rowlen : rowbuf;
-        for (uint32_t i = lane; i <= k + 1u; i += 32) { next[i] = prev[i] + refl * prev[k + 1u - i]; }
-        if (lane == 0) { next[k + 2u] = 0.0; err[k + 1u] = e_next; }
-        e = e_next;
-        prev = next;
-        __syncwarp();
-    }
-    return prev;
+    /* srla_encoder.c:938-950 with the window-compensated variance of lpc.c:493 */
+    const double ev = err_k * gain;
+    const double mean_abs = 2.0 * sqrt(ev / 2.0);
+    double bits = geometric_entropy(mean_abs, bps) * (double)n;
+    bits += (double)(8u * k);
+    if (pk.best > bits) { pk.best = bits; pk.arg = k; }
 }
 
-__global__ void __launch_bounds__(kThreads) lpc_kernel(const __grid_constant__ LaunchParams p)
+/* Levinson-Durbin up to order `stop` for this lane's candidate; when pk != NULL every order's
+ * estimated size is considered on the way.  Returns nothing: the vector a[0..stop] is in A. */
+#define LPC_R(i) R[(size_t)(i) * 32u + lane]
+#define LPC_A(i) A[(size_t)(i) * 32u + lane]
+__device__ __forceinline__ void levinson_lane(const double *R, double *A, const uint32_t lane, const uint32_t stop,
+                                              OrderPick *pk, double gain, uint32_t n, uint32_t bps, double *diag_err)
+{
+    const double r0 = LPC_R(0), r1 = LPC_R(1);
+    double e = r0;
+    const double a1 = -r1 / r0;
+    LPC_A(0) = 1.0; LPC_A(1) = a1;
+    e = e + r1 * a1;
+    if (diag_err) { diag_err[0] = r0 * gain; diag_err[1] = e * gain; }
+    if (pk) { consider_order(*pk, e, 1u, gain, n, bps); }
+    for (uint32_t k = 1; k < stop; ++k) {
+        double acc = 0.0;
+        uint32_t i = 0;
+        for (; i + 4u <= k + 1u; i += 4u) {
+            const double m0 = LPC_A(i) * LPC_R(k + 1u - i), m1 = LPC_A(i + 1u) * LPC_R(k - i);
+            const double m2 = LPC_A(i + 2u) * LPC_R(k - 1u - i), m3 = LPC_A(i + 3u) * LPC_R(k - 2u - i);
+            acc += m0; acc += m1; acc += m2; acc += m3;
+        }
+        for (; i <= k; ++i) { acc += LPC_A(i) * LPC_R(k + 1u - i); }
+        const double refl = acc / (-e);
+        e = e * (1.0 - refl * refl);
+        LPC_A(k + 1u) = 0.0;
+        for (uint32_t lo = 0, hi = k + 1u; lo <= hi; ++lo, --hi) {
+            const double t1 = LPC_A(lo), t2 = LPC_A(hi);
+            LPC_A(lo) = t1 + refl * t2;
+            if (hi != lo) { LPC_A(hi) = t2 + refl * t1; }
+            if (hi == 0u) { break; }
+        }
+        if (diag_err) { diag_err[k + 1u] = e * gain; }
+        if (pk) { consider_order(*pk, e, k + 1u, gain, n, bps); }
+    }
+}
+
+__global__ void __launch_bounds__(32) lpc_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const LpcLayout L = make_lpc_layout(p.max_order);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t idx = blockIdx.x * kWarps + warp;
-    if (idx >= p.num_jobs * p.ncand) { return; }
+    const uint32_t P = p.max_order, bps = p.bps;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t total = p.num_jobs * p.ncand;
+    const uint32_t first = blockIdx.x * 32u;
+    double *R = reinterpret_cast<double *>(smem);            /* [P + 2][32] */
+    double *A = R + (size_t)(P + 2u) * 32u;                  /* [P + 3][32] */
+    /* coalesced transpose-load of the 32 candidates' lags */
+    for (uint32_t c = 0; c < 32u && first + c < total; ++c) {
+        const double *g = p.lags + (size_t)(first + c) * p.lag_stride;
+        for (uint32_t i = lane; i <= P; i += 32u) { R[(size_t)i * 32u + c] = g[i]; }
+    }
+    __syncwarp();
+    const uint32_t idx = first + lane;
+    if (idx >= total) { return; }
     const uint32_t job_id = idx / p.ncand;
-    const uint32_t n = p.jobs[job_id].nsmpl, P = p.max_order, bps = p.bps;
+    const uint32_t n = p.jobs[job_id].nsmpl;
     CandOut *out = p.cand + idx;
     if (n <= P || out->status != 0u) { return; }
-    const double welch_gain = p.jobs[job_id].welch_gain;
-    unsigned char *mine = smem + (size_t)warp * L.per_warp;
-    double *r = reinterpret_cast<double *>(mine + L.r_off);
-    double *rowbuf = reinterpret_cast<double *>(mine + L.row_off);
-    double *err = reinterpret_cast<double *>(mine + L.err_off);
-    const double *g = p.lags + (size_t)idx * p.lag_stride;
-    for (uint32_t i = lane; i <= P; i += 32) { double v = g[i]; if (i == 0u) { v *= (1.0 + 1e-5); } r[i] = v; }   /* ridge, lpc.c:483 */
-    __syncwarp();
-    double *row = levinson_warp(r, P, rowbuf, L.rowlen, err);
-    /* error variances x window gain (lpc.c:493), estimated bits per order (srla_encoder.c:934-957) */
-    double my_cost = (double)FLT_MAX; uint32_t my_arg = 0;
-    for (uint32_t k = 1u + lane; k <= P; k += 32) {
-        const double ev = err[k] * welch_gain;
-        const double mean_abs = 2.0 * sqrt(ev / 2.0);
-        double bits = geometric_entropy(mean_abs, bps) * (double)n;
-        bits += (double)(8u * k);
-        if (my_cost > bits) { my_cost = bits; my_arg = k; }
+    const double gain = p.jobs[job_id].welch_gain;
+    CandDiag *dg = p.diag ? p.diag + idx : nullptr;
+    LPC_R(0) = LPC_R(0) * (1.0 + 1e-5);                      /* ridge, lpc.c:483 */
+    if (dg) { for (uint32_t i = 0; i <= P; ++i) { dg->autocorr[i] = LPC_R(i); } }
+
+    OrderPick pk; pk.best = (double)FLT_MAX; pk.arg = 0u;
+    const bool degenerate = fabs(LPC_R(0)) < (double)FLT_EPSILON;      /* lpc.c:399-407: all vectors zero, variances r[0] */
+    if (degenerate) {
+        const double r0 = LPC_R(0);
+        for (uint32_t k = 1; k <= P; ++k) { consider_order(pk, r0, k, gain, n, bps); }
+        if (dg) { for (uint32_t i = 0; i <= P; ++i) { dg->error_vars[i] = r0 * gain; } }
+    } else {
+        levinson_lane(R, A, lane, P, &pk, gain, n, bps, dg ? dg->error_vars : nullptr);
     }
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double oc = __shfl_xor_sync(0xffffffffu, my_cost, o);
-        const uint32_t oa = __shfl_xor_sync(0xffffffffu, my_arg, o);
-        if (oa != 0u && (my_arg == 0u || oc < my_cost || (oc == my_cost && oa < my_arg))) { my_cost = oc; my_arg = oa; }
-    }
-    const uint32_t order = my_arg;
-    if (p.diag) {
-        CandDiag *dg = p.diag + idx;
-        for (uint32_t i = lane; i <= P; i += 32) { dg->autocorr[i] = r[i]; dg->error_vars[i] = err[i] * welch_gain; }
-    }
+    const uint32_t order = pk.arg;
     uint32_t rshift = 0;
     if (order > 0u) {
-        if (order != P) { __syncwarp(); row = levinson_warp(r, order, rowbuf, L.rowlen, err); }
+        if (degenerate) { for (uint32_t i = 0; i <= order; ++i) { LPC_A(i) = 0.0; } }
+        else if (order != P) { levinson_lane(R, A, lane, order, nullptr, gain, n, bps, nullptr); }
         /* quantisation with error feedback from the tail (lpc.c:1341-1405), reversed for the FIR */
         double peak = 0.0;
-        for (uint32_t i = lane; i < order; i += 32) { const double a = fabs(row[1u + i]); if (peak < a) { peak = a; } }
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const double q = __shfl_xor_sync(0xffffffffu, peak, o); if (peak < q) { peak = q; } }
+        for (uint32_t i = 1; i <= order; ++i) { const double v = fabs(LPC_A(i)); if (peak < v) { peak = v; } }
         if (peak <= 0.0078125) {
-            for (uint32_t i = lane; i < order; i += 32) { out->coef[i] = 0; }
+            for (uint32_t i = 0; i < order; ++i) { out->coef[i] = 0; }
             rshift = 8u;
         } else {
             int exponent;
             (void)frexp(peak, &exponent);
             rshift = (uint32_t)(7 - exponent);
             if (rshift >= 16u) { rshift = 15u; }
-            if (lane == 0) {
-                const double scale = (double)(1u << rshift);
-                double carry = 0.0;
-                for (int i = (int)order - 1; i >= 0; --i) {
-                    carry += row[1 + i] * scale;
-                    int32_t v = (int32_t)round_half_away(carry);
-                    if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
-                    carry -= (double)v;
-                    /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
-                    out->coef[order - 1u - (uint32_t)i] = (int16_t)v;
-                }
+            const double scale = (double)(1u << rshift);
+            double carry = 0.0;
+            for (int i = (int)order - 1; i >= 0; --i) {
+                carry += LPC_A(1 + i) * scale;
+                int32_t v = (int32_t)round_half_away(carry);
+                if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
+                carry -= (double)v;
+                /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
+                out->coef[order - 1u - (uint32_t)i] = (int16_t)v;
             }
         }
-        if (p.diag) {
-            CandDiag *dg = p.diag + idx;
-            for (uint32_t i = lane; i < order; i += 32) { dg->lpc_double[i] = row[1u + i]; }
-        }
+        if (dg) { for (uint32_t i = 0; i < order; ++i) { dg->lpc_double[i] = LPC_A(1u + i); } }
     }
-    if (lane == 0) { out->order = order; out->rshift = rshift; }
+    out->order = order; out->rshift = rshift;
 }
+#undef LPC_R
+#undef LPC_A
 
 /* ------------------------------------------------------------------------------------------------
  * residual_kernel: one CTA per (job, candidate).  Rebuilds the candidate signal, runs the int32

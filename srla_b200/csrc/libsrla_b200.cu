@@ -295,7 +295,7 @@ struct Runner {
         if (!mark(batch, 1)) { return false; }
         if (p.max_order > 0) {
             if (!prep_kernel(lpc_kernel, LL.total)) { return false; }
-            lpc_kernel<<<(ncands + kWarps - 1) / kWarps, block, LL.total, c->stream>>>(p);
+            lpc_kernel<<<(ncands + 31u) / 32u, 32, LL.total, c->stream>>>(p);
             launches++;
         }
         if (!mark(batch, 2)) { return false; }

@@ -153,19 +153,12 @@ SRLA_HD inline FrontLayout make_front_layout(uint32_t nmax, uint32_t fft_max, ui
     return L;
 }
 
-/* lpc_kernel: per warp r[], two coefficient rows, error variances */
-struct LpcLayout {
-    uint32_t r_off, row_off, rowlen, err_off, per_warp, total;
-};
+/* lpc_kernel: lags and one coefficient vector of 32 candidates, interleaved [index][lane] */
+struct LpcLayout { uint32_t total; };
 SRLA_HD inline LpcLayout make_lpc_layout(uint32_t P)
 {
     LpcLayout L;
-    L.rowlen = round_up_u32(P + 4u, 2);
-    L.r_off = 0;
-    L.row_off = 8u * round_up_u32(P + 2u, 2);
-    L.err_off = L.row_off + 8u * 2u * L.rowlen;
-    L.per_warp = L.err_off + 8u * round_up_u32(P + 2u, 2);
-    L.total = L.per_warp * (uint32_t)kWarps;
+    L.total = 8u * 32u * ((P + 2u) + (P + 3u));
     return L;
 }
 

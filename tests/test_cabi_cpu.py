@@ -1,0 +1,136 @@
+"""CPU-side checks of the drop-in boundary (no GPU compute):
+ * libsrla_b200.so loads and exports every symbol include/srla_b200.h declares,
+ * host-only entry points behave like the reference (header bytes, config validation),
+ * without a CUDA device the product path FAILS LOUDLY (no CPU fallback),
+ * the sharding helper used by bench.py / multi-GPU runs partitions streams without overlap
+   (world_size-2 gloo test).
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, SoParams, have_ref, oracle_lib, ref_lib
+from srla_b200 import encoder as E
+
+LIB = os.path.join(ROOT, "srla_b200", "libsrla_b200.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__ as g
+        g.build()
+    return E.load_library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = open(os.path.join(ROOT, "include", "srla_b200.h")).read()
+    declared = set(re.findall(r"\b(SRLAEncoder_[A-Za-z]+|SRLAB200_[A-Za-z]+)\s*\(", header))
+    declared.discard("SRLAEncoder_EncodeBlockCallback")
+    assert declared == set(E.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.SRLAB200_Version()
+
+
+def test_library_embeds_sm100a_code_only():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_encode_header_matches_oracle_and_reference(lib):
+    """srla_encoder.c:85-165; signature bytes test/srla_encoder/srla_encoder_test.cpp:63-66"""
+    h = E.SRLAHeader(10, 18, 2, 12345, 48000, 16, 3, 4096, 4)
+    out = np.zeros(30, dtype=np.uint8)
+    assert lib.SRLAEncoder_EncodeHeader(C.byref(h), out.ctypes.data, 30) == E.OK
+    assert out[:4].tobytes() == b"1249"
+    prm = SoParams(2, 16, 48000, 4096, 4096, 4096, 0, 4, 3)
+    want = np.zeros(30, dtype=np.uint8)
+    assert oracle_lib().so_encode_header(C.byref(prm), 12345, want.ctypes.data, 30) == 0
+    assert out.tobytes() == want.tobytes()
+    if have_ref():
+        from helpers import SRLAHeader as RefHeader
+        rh = RefHeader(10, 18, 2, 12345, 48000, 16, 3, 4096, 4)
+        ref = np.zeros(30, dtype=np.uint8)
+        assert ref_lib().SRLAEncoder_EncodeHeader(C.byref(rh), ref.ctypes.data, 30) == 0
+        assert out.tobytes() == ref.tobytes()
+    # error behaviour (srla_encoder_test.cpp:69-113)
+    assert lib.SRLAEncoder_EncodeHeader(None, out.ctypes.data, 30) == E.INVALID_ARGUMENT
+    assert lib.SRLAEncoder_EncodeHeader(C.byref(h), None, 30) == E.INVALID_ARGUMENT
+    assert lib.SRLAEncoder_EncodeHeader(C.byref(h), out.ctypes.data, 29) == E.INSUFFICIENT_BUFFER
+    for field, bad in (("num_channels", 0), ("num_samples", 0), ("sampling_rate", 0), ("bits_per_sample", 0),
+                       ("offset_lshift", 32), ("max_num_samples_per_block", 0), ("preset", 7)):
+        hb = E.SRLAHeader(10, 18, 2, 12345, 48000, 16, 3, 4096, 4)
+        setattr(hb, field, bad)
+        assert lib.SRLAEncoder_EncodeHeader(C.byref(hb), out.ctypes.data, 30) == E.INVALID_FORMAT, field
+
+
+def test_work_size_validation_matches_reference(lib):
+    """srla_encoder.c:468-496 (test/srla_encoder/srla_encoder_test.cpp:118-170)"""
+    good = E.SRLAEncoderConfig(8, 1024, 4096, 16384, 255)
+    assert lib.SRLAEncoder_CalculateWorkSize(C.byref(good)) > 0
+    assert lib.SRLAEncoder_CalculateWorkSize(None) == -1
+    cases = [(0, 1024, 4096, 16384, 255), (8, 0, 4096, 16384, 255), (8, 1024, 0, 16384, 255), (8, 1024, 4096, 0, 255),
+             (8, 1024, 4096, 16384, 5000), (8, 8192, 4096, 16384, 255), (8, 1024, 4096, 2048, 255)]
+    for c in cases:
+        cfg = E.SRLAEncoderConfig(*c)
+        assert lib.SRLAEncoder_CalculateWorkSize(C.byref(cfg)) == -1, c
+        if have_ref():
+            from helpers import SRLAEncoderConfig as RefCfg
+            assert ref_lib().SRLAEncoder_CalculateWorkSize(C.byref(RefCfg(*c))) == -1, c
+
+
+def test_no_cpu_fallback_without_a_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    cfg = E.SRLAEncoderConfig(8, 4096, 4096, 4096, 255)
+    assert not lib.SRLAEncoder_Create(C.byref(cfg), None, 0)
+    with pytest.raises(RuntimeError):
+        E.Encoder()
+    with pytest.raises(Exception):
+        E.encode(np.zeros((2, 4096), dtype=np.int32))
+    # NULL handle behaves like the reference: INVALID_ARGUMENT, Destroy(NULL) is a no-op
+    size = C.c_uint32(0)
+    assert lib.SRLAEncoder_EncodeWhole(None, None, 0, None, 0, C.byref(size), None) == E.INVALID_ARGUMENT
+    assert lib.SRLAEncoder_SetEncodeParameter(None, None) == E.INVALID_ARGUMENT
+    lib.SRLAEncoder_Destroy(None)
+
+
+def test_product_code_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under srla_b200/ or include/ may reference it"""
+    for base, _dirs, files in os.walk(os.path.join(ROOT, "srla_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "liboracle" not in text and "srla_oracle" not in text and "libsrla_ref" not in text, f
+
+
+def test_shard_streams_world2_gloo(tmp_path):
+    """multi-GPU sharding is by whole streams, contiguous ranges, no exchange (DESIGN.md section e)"""
+    script = tmp_path / "shard.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from srla_b200.sharding import shard_range\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "lo, hi = shard_range(1024 + 3, r, w)\n"
+        "t = torch.zeros(1027, dtype=torch.int64); t[lo:hi] = 1\n"
+        "dist.all_reduce(t)\n"
+        "assert bool((t == 1).all()), 'ranges overlap or leave holes'\n"
+        "sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(w)]\n"
+        "dist.all_gather(sizes, torch.tensor([hi - lo]))\n"
+        "assert max(int(s) for s in sizes) - min(int(s) for s in sizes) <= 1\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -199,3 +199,32 @@ def test_full_size_roundtrip_property():
     pcm = np.concatenate([np.roll(tile, 37 * k, axis=1) for k in range(8)], axis=1)[:, :4096 * 400]
     got = E.encode(pcm, preset=4, max_block=4096)
     assert np.array_equal(ref_decode(got), pcm)
+
+
+def test_reference_cli_relinked_against_libsrla_b200(tmp_path):
+    """the unmodified reference CLI (tools/srla_codec), with every SRLAEncoder_* symbol taken from
+    libsrla_b200.so (oracle/Makefile `dropin`), writes the same .srl as the reference CLI, and the
+    reference CLI decodes it back to the same WAV"""
+    import os
+    import subprocess
+    import wave
+    from helpers import ROOT
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "srla_ref")
+    our_cli = os.path.join(ROOT, "oracle", "_ref", "srla_b200_cli")
+    if not (os.path.exists(ref_cli) and os.path.exists(our_cli)):
+        pytest.skip("oracle/_ref CLIs not built")
+    pcm = synth_stereo(48000 * 2 + 777, seed=55)
+    wav = tmp_path / "in.wav"
+    with wave.open(str(wav), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000)
+        w.writeframes(pcm.T.astype("<i2").tobytes())
+    for extra, tag in ((["-m", "4", "-B", "4096", "-V", "0"], "fixed"), (["-m", "4"], "cli_defaults_v1"), (["-m", "2", "-B", "2048", "-V", "0", "-P", "3"], "ltp")):
+        a, b = tmp_path / f"ref_{tag}.srl", tmp_path / f"b200_{tag}.srl"
+        subprocess.run([ref_cli, "-e"] + extra + [str(wav), str(a)], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([our_cli, "-e"] + extra + [str(wav), str(b)], check=True, stdout=subprocess.DEVNULL)
+        assert a.read_bytes() == b.read_bytes(), tag
+    back = tmp_path / "back.wav"
+    subprocess.run([ref_cli, "-d", str(b), str(back)], check=True, stdout=subprocess.DEVNULL)
+    with wave.open(str(back), "rb") as w:
+        got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").reshape(-1, 2).T
+    assert np.array_equal(got, pcm)
