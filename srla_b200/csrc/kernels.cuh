@@ -129,58 +129,160 @@ __global__ void lshift_finish_kernel(StreamDev *streams, uint32_t num_streams)
 
 /* ------------------------------------------------------------------------------------------------
  * FFT exactly as the reference evaluates it (libs/fft/src/fft.c:71-128, 147-198).
- * The Stockham stages are executed IN PLACE: every thread first pulls the four inputs of its
- * butterflies into registers, the CTA synchronises, then the outputs are stored.  Each output is
- * the same expression tree as in the reference, with the host-tabulated twiddle sequence.
+ *
+ * The reference's radix-4 Stockham stages are executed IN PLACE in shared memory: every thread
+ * first pulls all inputs of its work unit into registers, the CTA synchronises, then the outputs
+ * are stored.  TWO consecutive radix-4 stages are fused into one pass over shared memory (a work
+ * unit = 16 points = 4 butterflies of stage t feeding 4 butterflies of stage t+1 in registers; the
+ * trailing radix-4 + radix-2 pair is an 8-point unit), which halves the shared-memory traffic that
+ * bounds this kernel.  Every output is the same expression tree as in the reference, with the
+ * host-tabulated twiddle recurrence.  Complex element i lives at slot fft_slot(i): an XOR swizzle
+ * that keeps both the unit-strided stores of the first pass and all contiguous accesses free of
+ * bank conflicts.
  * ---------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ uint32_t fft_slot(uint32_t i) { return i ^ ((i >> 4) & 7u); }
 
-template <int BPT>
-__device__ __forceinline__ void complex_fft_inplace(double2 *x, const int M, const bool inverse, const LaunchParams &p)
+struct Twiddle3 { double2 w1, w2, w3; };
+__device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t p, bool inverse)
 {
-    const int tid = threadIdx.x;
-    const int quarter_m = M >> 2;
-    int nn = M, lgs = 0;
-    while (nn > 2) {
-        const int lgn = 31 - __clz(nn);
-        const double2 *tw = p.tw_complex + p.tw_complex_off[lgn];
-        double2 a[BPT], b[BPT], c[BPT], d[BPT];
-        #pragma unroll
-        for (int it = 0; it < BPT; ++it) {
-            const int bf = tid + it * kThreads;
-            if (bf < quarter_m) { a[it] = x[bf]; b[it] = x[bf + quarter_m]; c[it] = x[bf + 2 * quarter_m]; d[it] = x[bf + 3 * quarter_m]; }
-        }
-        __syncthreads();
-        #pragma unroll
-        for (int it = 0; it < BPT; ++it) {
-            const int bf = tid + it * kThreads;
-            if (bf < quarter_m) {
-                const int pp = bf >> lgs, q = bf & ((1 << lgs) - 1);
-                double2 w1 = __ldg(tw + 3 * pp), w2 = __ldg(tw + 3 * pp + 1), w3 = __ldg(tw + 3 * pp + 2);
-                if (inverse) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
-                const double2 apc = cadd(a[it], c[it]), amc = csub(a[it], c[it]), bpd = cadd(b[it], d[it]);
-                const double2 bmd = csub(b[it], d[it]);
-                /* j * (b - d), j = (0, -flag): forward (0,+1) -> (-im, re); inverse (0,-1) -> (im, -re).
-                 * (the reference's 0.0 * x terms only affect the sign of zeros) */
-                const double2 jbmd = inverse ? make_double2(bmd.y, -bmd.x) : make_double2(-bmd.y, bmd.x);
-                const int o = q + ((4 * pp) << lgs);
-                x[o]                = cadd(apc, bpd);
-                x[o + (1 << lgs)]   = cmul(w1, csub(amc, jbmd));
-                x[o + (2 << lgs)]   = cmul(w2, csub(apc, bpd));
-                x[o + (3 << lgs)]   = cmul(w3, cadd(amc, jbmd));
+    Twiddle3 t;
+    t.w1 = __ldg(table + 3u * p); t.w2 = __ldg(table + 3u * p + 1u); t.w3 = __ldg(table + 3u * p + 2u);
+    if (inverse) { t.w1.y = -t.w1.y; t.w2.y = -t.w2.y; t.w3.y = -t.w3.y; }      /* the recurrence is sign-symmetric */
+    return t;
+}
+
+/* one radix-4 butterfly, fft.c:93-105 */
+__device__ __forceinline__ void butterfly4(const double2 a, const double2 b, const double2 c, const double2 d, const Twiddle3 &w,
+                                           const bool inverse, double2 &y0, double2 &y1, double2 &y2, double2 &y3)
+{
+    const double2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
+    /* j * (b - d), j = (0, -flag): forward (0,+1) -> (-im, re); inverse (0,-1) -> (im, -re).
+     * (the reference's 0.0 * x terms only affect the sign of zeros) */
+    const double2 jbmd = inverse ? make_double2(bmd.y, -bmd.x) : make_double2(-bmd.y, bmd.x);
+    y0 = cadd(apc, bpd);
+    y1 = cmul(w.w1, csub(amc, jbmd));
+    y2 = cmul(w.w2, csub(apc, bpd));
+    y3 = cmul(w.w3, cadd(amc, jbmd));
+}
+
+/* complex FFT of M points (M a power of two, M/16 <= blockDim.x, M/8 <= blockDim.x when M = 8 * 4^k) */
+__device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inverse, const LaunchParams &p)
+{
+    const uint32_t tid = threadIdx.x;
+    uint32_t nn = M, lgs = 0;
+    /* fused pairs of radix-4 stages */
+    while (nn >= 16u) {
+        const uint32_t units = M >> 4;
+        const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
+        double2 v[4][4];
+        if (tid < units) {
+            #pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) { v[jp][j] = x[fft_slot(tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2))]; }
             }
         }
         __syncthreads();
-        nn >>= 2; lgs += 2;
+        if (tid < units) {
+            const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
+            const double2 *tw_a = p.tw_complex + p.tw_complex_off[lgn];
+            const double2 *tw_b = p.tw_complex + p.tw_complex_off[lgn - 2u];
+            double2 y[4][4];
+            #pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const Twiddle3 w = load_twiddle(tw_a, p0 + (uint32_t)jp * (nn >> 4), inverse);
+                butterfly4(v[jp][0], v[jp][1], v[jp][2], v[jp][3], w, inverse, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
+            }
+            const Twiddle3 w = load_twiddle(tw_b, p0, inverse);
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 z0, z1, z2, z3;
+                butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], w, inverse, z0, z1, z2, z3);
+                const uint32_t o = q + ((uint32_t)j << lgs) + ((16u * p0) << lgs);
+                x[fft_slot(o)]                = z0;
+                x[fft_slot(o + (4u << lgs))]  = z1;
+                x[fft_slot(o + (8u << lgs))]  = z2;
+                x[fft_slot(o + (12u << lgs))] = z3;
+            }
+        }
+        __syncthreads();
+        nn >>= 4; lgs += 4;
     }
-    if (nn == 2) {
-        const int s = 1 << lgs;        /* == M / 2 */
-        for (int q = tid; q < s; q += kThreads) {
-            const double2 a = x[q], b = x[q + s];
-            x[q] = cadd(a, b);
-            x[q + s] = csub(a, b);
+    /* tail passes: up to two work units per thread (all loads precede all stores: in place is safe) */
+    const uint32_t T = blockDim.x;
+    if (nn == 8u) {
+        /* radix-4 stage of size 8 (s = M/8) fused with the final radix-2 stage (fft.c:114-123) */
+        const uint32_t s = M >> 3;
+        double2 v[2][2][4];
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t u = tid + (uint32_t)r * T;
+            if (u < s) {
+                #pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) { v[r][pp][j] = x[fft_slot((uint32_t)pp * s + u + (uint32_t)j * (M >> 2))]; }
+                }
+            }
+        }
+        __syncthreads();
+        const double2 *tw = p.tw_complex + p.tw_complex_off[3];
+        const Twiddle3 w0 = load_twiddle(tw, 0u, inverse), w1 = load_twiddle(tw, 1u, inverse);
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t u = tid + (uint32_t)r * T;
+            if (u < s) {
+                double2 y[2][4];
+                butterfly4(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, inverse, y[0][0], y[0][1], y[0][2], y[0][3]);
+                butterfly4(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, inverse, y[1][0], y[1][1], y[1][2], y[1][3]);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    x[fft_slot(u + (uint32_t)j * s)]            = cadd(y[0][j], y[1][j]);
+                    x[fft_slot(u + (uint32_t)j * s + (M >> 1))] = csub(y[0][j], y[1][j]);
+                }
+            }
+        }
+        __syncthreads();
+    } else if (nn == 4u) {
+        /* single radix-4 stage of size 4 (s = M/4): twiddle index 0 only */
+        const uint32_t s = M >> 2;
+        double2 v[2][4];
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t u = tid + (uint32_t)r * T;
+            if (u < s) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) { v[r][j] = x[fft_slot(u + (uint32_t)j * s)]; }
+            }
+        }
+        __syncthreads();
+        const Twiddle3 w = load_twiddle(p.tw_complex + p.tw_complex_off[2], 0u, inverse);
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t u = tid + (uint32_t)r * T;
+            if (u < s) {
+                double2 y0, y1, y2, y3;
+                butterfly4(v[r][0], v[r][1], v[r][2], v[r][3], w, inverse, y0, y1, y2, y3);
+                x[fft_slot(u)] = y0; x[fft_slot(u + s)] = y1; x[fft_slot(u + 2u * s)] = y2; x[fft_slot(u + 3u * s)] = y3;
+            }
+        }
+        __syncthreads();
+    } else if (nn == 2u) {
+        const uint32_t s = M >> 1;
+        double2 v[2][2];
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t u = tid + (uint32_t)r * T;
+            if (u < s) { v[r][0] = x[fft_slot(u)]; v[r][1] = x[fft_slot(u + s)]; }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t u = tid + (uint32_t)r * T;
+            if (u < s) { x[fft_slot(u)] = cadd(v[r][0], v[r][1]); x[fft_slot(u + s)] = csub(v[r][0], v[r][1]); }
         }
         __syncthreads();
     }
@@ -188,83 +290,100 @@ __device__ __forceinline__ void complex_fft_inplace(double2 *x, const int M, con
 
 /* Welch window (lpc.c:252-266) + autocorrelation through the FFT (lpc.c:330-376).
  * sig[n] int32 in shared memory -> lags[0..nlags) (lags >= N read as 0.0).  buf: N doubles. */
-template <int BPT>
 __device__ void welch_autocorr(const int32_t *sig, const uint32_t n, double *buf, double *lags, const uint32_t nlags,
                                const Job &job, const LaunchParams &p)
 {
-    const int tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t N = ceil_pow2_u32(n);
     const double unit = p.unit, div = job.welch_div;
-    for (uint32_t i = tid; i < N; i += kThreads) {
-        double v = 0.0;
-        if (i < n) {
-            const uint32_t s = (i < (n >> 1)) ? i : (n - 1u - i);
-            const double w = div * (double)s * (double)(n - 1u - s);
-            v = ((double)sig[i] * unit) * w;
+    double2 *cx = reinterpret_cast<double2 *>(buf);
+    if (N < 2u) {
+        if (tid == 0) {
+            const double w = div * 0.0 * (double)(n - 1u);
+            buf[0] = ((double)sig[0] * unit) * w;
         }
-        buf[i] = v;
+        __syncthreads();
+        for (uint32_t i = tid; i < nlags; i += nthreads) { lags[i] = (i < N) ? buf[i] * job.ac_scale : 0.0; }
+        __syncthreads();
+        return;
+    }
+    const uint32_t M = N >> 1;
+    for (uint32_t c = tid; c < M; c += nthreads) {
+        double v[2];
+        #pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const uint32_t i = 2u * c + (uint32_t)t;
+            double r = 0.0;
+            if (i < n) {
+                const uint32_t s = (i < (n >> 1)) ? i : (n - 1u - i);
+                const double w = div * (double)s * (double)(n - 1u - s);
+                r = ((double)sig[i] * unit) * w;
+            }
+            v[t] = r;
+        }
+        cx[fft_slot(c)] = make_double2(v[0], v[1]);
     }
     __syncthreads();
-    if (N >= 2u) {
-        double2 *cx = reinterpret_cast<double2 *>(buf);
-        const int M = (int)(N >> 1);
-        complex_fft_inplace<BPT>(cx, M, false, p);
-        /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three
-         * only touch the element pair (i, N/2 - i) */
-        {
-            const int lgN = 31 - __clz((int)N);
-            const double2 *tw = p.tw_real + p.tw_real_off[lgN];
-            const uint32_t quarter = N >> 2;
-            for (uint32_t i = 1u + tid; i <= quarter; i += kThreads) {
-                const double2 w = __ldg(tw + (i - 1u));
-                const double wr = w.x, wi_f = w.y, wi_b = -w.y;
-                const uint32_t lo = i, hi = (N >> 1) - i;
-                const double2 xl = cx[lo], xh = cx[hi];
-                /* forward, flag = -1: c2 = -0.5 */
-                double f1, f2, f3, f4;
-                {
-                    const double c2 = -0.5;
-                    const double h1r = 0.5 * (xl.x + xh.x);
-                    const double h1i = 0.5 * (xl.y - xh.y);
-                    const double h2r = -c2 * (xl.y + xh.y);
-                    const double h2i = c2 * (xl.x - xh.x);
-                    f1 = h1r + (wr * h2r) - (wi_f * h2i);
-                    f2 = h1i + (wr * h2i) + (wi_f * h2r);
-                    f3 = h1r - (wr * h2r) + (wi_f * h2i);
-                    f4 = -h1i + (wr * h2i) + (wi_f * h2r);
-                }
-                /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
-                double p_lo, p_hi;
-                if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
-                else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
-                /* inverse, flag = +1: c2 = +0.5, imaginary parts are 0.0 */
-                {
-                    const double c2 = 0.5;
-                    const double zl = 0.0, zh = 0.0;
-                    const double h1r = 0.5 * (p_lo + p_hi);
-                    const double h1i = 0.5 * (zl - zh);
-                    const double h2r = -c2 * (zl + zh);
-                    const double h2i = c2 * (p_lo - p_hi);
-                    const double g1 = h1r + (wr * h2r) - (wi_b * h2i);
-                    const double g2 = h1i + (wr * h2i) + (wi_b * h2r);
-                    const double g3 = h1r - (wr * h2r) + (wi_b * h2i);
-                    const double g4 = -h1i + (wr * h2i) + (wi_b * h2r);
-                    if (lo != hi) { cx[lo] = make_double2(g1, g2); }
-                    cx[hi] = make_double2(g3, g4);
-                }
+    complex_fft_inplace(cx, M, false, p);
+    /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three
+     * only touch the element pair (i, N/2 - i) */
+    {
+        const uint32_t lgN = 31u - (uint32_t)__clz((int)N);
+        const double2 *tw = p.tw_real + p.tw_real_off[lgN];
+        const uint32_t quarter = N >> 2;
+        for (uint32_t i = 1u + tid; i <= quarter; i += nthreads) {
+            const double2 w = __ldg(tw + (i - 1u));
+            const double wr = w.x, wi_f = w.y, wi_b = -w.y;
+            const uint32_t lo = i, hi = M - i;
+            const double2 xl = cx[fft_slot(lo)], xh = cx[fft_slot(hi)];
+            /* forward, flag = -1: c2 = -0.5 */
+            double f1, f2, f3, f4;
+            {
+                const double c2 = -0.5;
+                const double h1r = 0.5 * (xl.x + xh.x);
+                const double h1i = 0.5 * (xl.y - xh.y);
+                const double h2r = -c2 * (xl.y + xh.y);
+                const double h2i = c2 * (xl.x - xh.x);
+                f1 = h1r + (wr * h2r) - (wi_f * h2i);
+                f2 = h1i + (wr * h2i) + (wi_f * h2r);
+                f3 = h1r - (wr * h2r) + (wi_f * h2i);
+                f4 = -h1i + (wr * h2i) + (wi_f * h2r);
             }
-            if (tid == 0) {
-                const double2 dc = cx[0];
-                const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
-                const double q0 = f0 * f0, q1 = f1 * f1;
-                cx[0] = make_double2(0.5 * (q0 + q1), 0.5 * (q0 - q1));
+            /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
+            double p_lo, p_hi;
+            if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
+            else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
+            /* inverse, flag = +1: c2 = +0.5, imaginary parts are 0.0 */
+            {
+                const double c2 = 0.5;
+                const double zl = 0.0, zh = 0.0;
+                const double h1r = 0.5 * (p_lo + p_hi);
+                const double h1i = 0.5 * (zl - zh);
+                const double h2r = -c2 * (zl + zh);
+                const double h2i = c2 * (p_lo - p_hi);
+                const double g1 = h1r + (wr * h2r) - (wi_b * h2i);
+                const double g2 = h1i + (wr * h2i) + (wi_b * h2r);
+                const double g3 = h1r - (wr * h2r) + (wi_b * h2i);
+                const double g4 = -h1i + (wr * h2i) + (wi_b * h2r);
+                if (lo != hi) { cx[fft_slot(lo)] = make_double2(g1, g2); }
+                cx[fft_slot(hi)] = make_double2(g3, g4);
             }
-            __syncthreads();
         }
-        complex_fft_inplace<BPT>(cx, M, true, p);
+        if (tid == 0) {
+            const double2 dc = cx[0];
+            const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
+            const double q0 = f0 * f0, q1 = f1 * f1;
+            cx[0] = make_double2(0.5 * (q0 + q1), 0.5 * (q0 - q1));
+        }
+        __syncthreads();
     }
+    complex_fft_inplace(cx, M, true, p);
     const double scale = job.ac_scale;
-    for (uint32_t i = tid; i < nlags; i += kThreads) { lags[i] = (i < N) ? buf[i] * scale : 0.0; }
+    for (uint32_t i = tid; i < nlags; i += nthreads) {
+        double v = 0.0;
+        if (i < N) { const double2 e = cx[fft_slot(i >> 1)]; v = ((i & 1u) ? e.y : e.x) * scale; }
+        lags[i] = v;
+    }
     __syncthreads();
 }
 
@@ -359,22 +478,57 @@ __device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, 
  * ---------------------------------------------------------------------------------------------- */
 /* load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) -> raw[0..n).
  * returns OR of the unshifted samples of a plain channel candidate (0 for M/S). */
+__device__ __forceinline__ int4 load_quad(const StreamDev &st, uint32_t ch, uint32_t idx)
+{
+    const unsigned long long at = (unsigned long long)ch * st.stride + idx;
+    if (st.sample_bytes == 2u) {
+        const int2 v = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const short *>(st.pcm) + at));
+        return make_int4((int32_t)(short)(v.x & 0xffff), v.x >> 16, (int32_t)(short)(v.y & 0xffff), v.y >> 16);
+    }
+    return __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int32_t *>(st.pcm) + at));
+}
+__device__ __forceinline__ bool quad_aligned(const StreamDev &st, uint32_t ch, uint32_t idx)
+{
+    const unsigned long long addr = reinterpret_cast<unsigned long long>(st.pcm) + ((unsigned long long)ch * st.stride + idx) * st.sample_bytes;
+    return (addr & (4ull * st.sample_bytes - 1ull)) == 0ull;
+}
+
 __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
                                               uint32_t lshift, int32_t *raw)
 {
     const uint32_t n = job.nsmpl;
     const uint32_t first_ch = (p.nch >= 2u) ? 2u : 0u;
+    const bool ms = (p.nch >= 2u) && (cand < 2u);
+    const uint32_t ch = ms ? 0u : cand - first_ch;
+    const bool vec = quad_aligned(st, ch, job.offset) && (!ms || quad_aligned(st, 1u, job.offset));
+    const uint32_t nquad = vec ? (n >> 2) : 0u;
     int nz = 0;
-    if ((p.nch >= 2u) && (cand < 2u)) {
-        for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+    if (ms) {
+        for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
+            const int4 lq = load_quad(st, 0, job.offset + 4u * g), rq = load_quad(st, 1, job.offset + 4u * g);
+            const int32_t l[4] = { asr32(lq.x, lshift), asr32(lq.y, lshift), asr32(lq.z, lshift), asr32(lq.w, lshift) };
+            const int32_t r[4] = { asr32(rq.x, lshift), asr32(rq.y, lshift), asr32(rq.z, lshift), asr32(rq.w, lshift) };
+            int32_t o[4];
+            #pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int32_t side = (int32_t)((uint32_t)r[t] - (uint32_t)l[t]);
+                o[t] = (cand == 1u) ? side : (int32_t)((uint32_t)l[t] + (uint32_t)(side >> 1));
+            }
+            *reinterpret_cast<int4 *>(raw + 4u * g) = make_int4(o[0], o[1], o[2], o[3]);
+        }
+        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += blockDim.x) {
             const int32_t l = asr32(load_sample(st, 0, job.offset + i), lshift);
             const int32_t r = asr32(load_sample(st, 1, job.offset + i), lshift);
             const int32_t side = (int32_t)((uint32_t)r - (uint32_t)l);
             raw[i] = (cand == 1u) ? side : (int32_t)((uint32_t)l + (uint32_t)(side >> 1));
         }
     } else {
-        const uint32_t ch = cand - first_ch;
-        for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+        for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
+            const int4 q = load_quad(st, ch, job.offset + 4u * g);
+            nz |= q.x | q.y | q.z | q.w;
+            *reinterpret_cast<int4 *>(raw + 4u * g) = make_int4(asr32(q.x, lshift), asr32(q.y, lshift), asr32(q.z, lshift), asr32(q.w, lshift));
+        }
+        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += blockDim.x) {
             const int32_t v = load_sample(st, ch, job.offset + i);
             nz |= v;
             raw[i] = asr32(v, lshift);
@@ -387,12 +541,12 @@ __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &jo
  * plus the zero padding the FIR's vector loads may touch */
 __device__ __forceinline__ void apply_preemphasis(const int32_t *raw, int32_t *sig, uint32_t n, int32_t pre_coef)
 {
-    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const int32_t cur = raw[i], prv = raw[(i == 0u) ? 0u : i - 1u];
         sig[i] = (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)pre_coef) >> 4));
     }
     if (threadIdx.x < 4) { sig[-1 - (int)threadIdx.x] = 0; }
-    for (uint32_t i = n + threadIdx.x; i < round_up_u32(n, 4) + 4u; i += kThreads) { sig[i] = 0; }
+    for (uint32_t i = n + threadIdx.x; i < round_up_u32(n, 4) + 4u; i += blockDim.x) { sig[i] = 0; }
 }
 
 /* long-term prediction residual replaces the signal (srla_lpc_predict.c:267-294); tmp: n int32 */
@@ -400,7 +554,7 @@ __device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n
                                           int32_t c0, int32_t c1, int32_t c2)
 {
     const uint32_t half_order = ltp_order >> 1;
-    for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         int32_t v = sig[i];
         if (i >= period + half_order + 1u) {
             const int32_t *x = sig + (i - period - half_order);
@@ -412,7 +566,7 @@ __device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n
         tmp[i] = v;
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += kThreads) { sig[i] = tmp[i]; }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { sig[i] = tmp[i]; }
     __syncthreads();
 }
 
@@ -420,8 +574,8 @@ __device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n
  * front_kernel: one CTA per (job, candidate).  Pre-emphasis decision, optional LTP analysis, and
  * the Welch-windowed FFT autocorrelation of the signal the LPC stage sees; lags 0..P go to HBM.
  * ---------------------------------------------------------------------------------------------- */
-template <int BPT>
-__global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__ LaunchParams p)
+template <int kT>
+__global__ void __launch_bounds__(kT, (kT <= 128) ? 3 : 1) front_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FrontLayout L = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
@@ -429,7 +583,7 @@ __global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__
     int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
     int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;     /* 4 ints of front padding */
     double   *lags     = reinterpret_cast<double *>(smem + L.lags_off);
-    __shared__ unsigned long long red64[2 * kWarps];
+    __shared__ unsigned long long red64[2 * (kT / 32)];
     __shared__ int32_t  sh_i[8];
     __shared__ uint32_t sh_u[8];
 
@@ -453,7 +607,7 @@ __global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__
     /* ---- pre-emphasis coefficient (srla_utility.c:214-257): r0, r1 as exact integers ---- */
     {
         long long r0 = 0, r1 = 0;
-        for (uint32_t i = tid; i < n; i += kThreads) {
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
             const long long a = region_i[i];
             r0 += a * a;
             if (i + 1u < n) { r1 += a * (long long)region_i[i + 1u]; }
@@ -463,7 +617,7 @@ __global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__
         __syncthreads();
         if (tid == 0) {
             long long s0 = 0, s1 = 0;
-            for (int w = 0; w < kWarps; ++w) { s0 += (long long)red64[2 * w]; s1 += (long long)red64[2 * w + 1]; }
+            for (int w = 0; w < kT / 32; ++w) { s0 += (long long)red64[2 * w]; s1 += (long long)red64[2 * w + 1]; }
             int32_t c = 0;
             if (s0 != 0) {
                 double v = ((double)s1 / (double)s0) * 16.0;
@@ -493,7 +647,7 @@ __global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__
 
     /* ---- long-term prediction (srla_encoder.c:1008-1058) ---- */
     if (p.ltp_order > 0u) {
-        welch_autocorr<BPT>(sig, n, region_d, lags, kLtpLags, job, p);
+        welch_autocorr(sig, n, region_d, lags, kLtpLags, job, p);
         if (tid == 0) {
             /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
             for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
@@ -511,7 +665,7 @@ __global__ void __launch_bounds__(kThreads) front_kernel(const __grid_constant__
     /* ---- autocorrelation of the signal the LPC stage sees (lpc.c:444-483) ---- */
     if (P > 0u) {
         double *g = p.lags + ((size_t)job_id * p.ncand + cand) * p.lag_stride;
-        welch_autocorr<BPT>(sig, n, region_d, g, P + 1u, job, p);
+        welch_autocorr(sig, n, region_d, g, P + 1u, job, p);
     }
 }
 
@@ -654,7 +808,6 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
     int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
     int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;
     int32_t  *coef_s   = reinterpret_cast<int32_t *>(smem + L.coef_off);
-    uint8_t  *ktab     = smem + L.ktab_off;
     uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -734,17 +887,23 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
     uint32_t max_porder = 0;
     while (max_porder < (uint32_t)kLog2MaxParts && (n % (2u << max_porder)) == 0u) { max_porder++; }
     const uint32_t nparts = 1u << max_porder, per = n >> max_porder;
-    double *mean = reinterpret_cast<double *>(smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16));   /* heap layout: level l at (1<<l)-1 */
+    /* heap layout: level l occupies [(1<<l)-1, (2<<l)-1).  Each slot first holds the partition's mean
+     * (double), then is overwritten by its packed parameters: bits [5j, 5j+5) = parameter of the
+     * enclosing partition at level j, for every j <= l. */
+    double *mean = reinterpret_cast<double *>(smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16));
+    unsigned long long *pack = reinterpret_cast<unsigned long long *>(mean);
     /* finest partition means: exact integer sums / per (srla_coder.c:371-383) */
     uint32_t any = 0;
     if (per <= 32u) {
         for (uint32_t q = tid; q < nparts; q += kThreads) {
             unsigned long long s = 0;
             const int32_t *rp = res_s + q * per;
-            if (per == 4u) {
-                const int4 v = *reinterpret_cast<const int4 *>(rp);
-                const uint32_t u0 = zigzag32(v.x), u1 = zigzag32(v.y), u2 = zigzag32(v.z), u3 = zigzag32(v.w);
-                s = (unsigned long long)u0 + u1 + u2 + u3; any |= u0 | u1 | u2 | u3;
+            if ((per & 3u) == 0u) {
+                for (uint32_t i = 0; i < per; i += 4u) {
+                    const int4 v = *reinterpret_cast<const int4 *>(rp + i);
+                    const uint32_t u0 = zigzag32(v.x), u1 = zigzag32(v.y), u2 = zigzag32(v.z), u3 = zigzag32(v.w);
+                    s += (unsigned long long)u0 + u1 + u2 + u3; any |= u0 | u1 | u2 | u3;
+                }
             } else {
                 for (uint32_t i = 0; i < per; ++i) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
             }
@@ -770,61 +929,61 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
             __syncthreads();
         }
         code_type = (mean[0] < 2.0) ? kCodeRice : kCodeRecursiveRice;
-        /* coding parameter of every partition at every level */
-        for (uint32_t e = tid; e < 2u * nparts - 1u; e += kThreads) {
-            const double m = mean[e];
-            uint32_t k;
-            if (code_type == kCodeRice) {
-                k = 0;
-                #pragma unroll 1
-                for (int j = 1; j < 32; ++j) { if (m >= __ldg(p.rice_threshold + j)) { k = (uint32_t)j; } }   /* srla_coder.c:262-287 via host-libm thresholds */
-            } else {
-                const double g = 0.66794162356 * (1.0 + m);                                                 /* srla_coder.c:298-324 */
-                const uint32_t golomb = (uint32_t)((1.0 > g) ? 1.0 : g);
-                k = 31u - (uint32_t)__clz((int)golomb);
-            }
-            ktab[e] = (uint8_t)k;
-        }
         __syncthreads();
+        /* coding parameter of every partition, top level first, packed with its ancestors' */
+        for (uint32_t lvl = 0; lvl <= max_porder; ++lvl) {
+            const uint32_t cnt = 1u << lvl, base = cnt - 1u;
+            for (uint32_t q = tid; q < cnt; q += kThreads) {
+                const double m = mean[base + q];
+                uint32_t k;
+                if (code_type == kCodeRice) {
+                    k = 0;
+                    #pragma unroll 1
+                    for (int j = 1; j < 32; ++j) { if (m >= __ldg(p.rice_threshold + j)) { k = (uint32_t)j; } }   /* srla_coder.c:262-287 via host-libm thresholds */
+                } else {
+                    const double g = 0.66794162356 * (1.0 + m);                                                 /* srla_coder.c:298-324 */
+                    const uint32_t golomb = (uint32_t)((1.0 > g) ? 1.0 : g);
+                    k = 31u - (uint32_t)__clz((int)golomb);
+                }
+                const unsigned long long parent = lvl ? pack[(cnt >> 1) - 1u + (q >> 1)] : 0ull;
+                pack[base + q] = parent | ((unsigned long long)(k & 31u) << (5u * lvl));
+            }
+            __syncthreads();
+        }
         /* bits of every partition order: each thread walks whole finest partitions */
         uint32_t acc[kLog2MaxParts + 1];
         #pragma unroll
         for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = 0; }
+        const unsigned long long *finest = pack + (nparts - 1u);
         if (per <= 32u) {
             for (uint32_t q = tid; q < nparts; q += kThreads) {
-                uint32_t kk[kLog2MaxParts + 1];
-                #pragma unroll
-                for (int l = 0; l <= kLog2MaxParts; ++l) {
-                    kk[l] = ((uint32_t)l <= max_porder) ? ktab[((1u << l) - 1u) + (q >> (max_porder - (uint32_t)l))] : 0u;
-                }
+                const unsigned long long pk = finest[q];
                 const int32_t *rp = res_s + q * per;
-                for (uint32_t i0 = 0; i0 < per; i0 += 4u) {
-                    uint32_t v[4];
-                    if (per == 4u) { const int4 t = *reinterpret_cast<const int4 *>(rp); v[0] = zigzag32(t.x); v[1] = zigzag32(t.y); v[2] = zigzag32(t.z); v[3] = zigzag32(t.w); }
-                    else {
+                if ((per & 3u) == 0u) {
+                    for (uint32_t i0 = 0; i0 < per; i0 += 4u) {
+                        const int4 t = *reinterpret_cast<const int4 *>(rp + i0);
+                        const uint32_t v0 = zigzag32(t.x), v1 = zigzag32(t.y), v2 = zigzag32(t.z), v3 = zigzag32(t.w);
                         #pragma unroll
-                        for (int t = 0; t < 4; ++t) { v[t] = (i0 + t < per) ? zigzag32(rp[i0 + t]) : 0u; }
-                    }
-                    const uint32_t cnt = (per - i0 < 4u) ? per - i0 : 4u;
-                    #pragma unroll
-                    for (int l = 0; l <= kLog2MaxParts; ++l) {
-                        if ((uint32_t)l <= max_porder) {
-                            const uint32_t k = kk[l];
-                            uint32_t add = 0;
+                        for (int l = 0; l <= kLog2MaxParts; ++l) {
+                            const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
                             if (code_type == kCodeRice) {
-                                #pragma unroll
-                                for (int t = 0; t < 4; ++t) { if ((uint32_t)t < cnt) { add += 1u + k + (v[t] >> k); } }
+                                acc[l] += 4u * (1u + k) + (v0 >> k) + (v1 >> k) + (v2 >> k) + (v3 >> k);
                             } else {
-                                const uint32_t k1 = k + 1u;
-                                #pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    if ((uint32_t)t < cnt) {
-                                        const int32_t over = (int32_t)v[t] - (int32_t)(1u << k1);
-                                        add += (k1 + 1u) + ((uint32_t)((over > 0) ? over : 0) >> k);
-                                    }
-                                }
+                                const int32_t pivot = (int32_t)(2u << k);
+                                acc[l] += 4u * (k + 2u)
+                                        + ((uint32_t)max((int32_t)v0 - pivot, 0) >> k) + ((uint32_t)max((int32_t)v1 - pivot, 0) >> k)
+                                        + ((uint32_t)max((int32_t)v2 - pivot, 0) >> k) + ((uint32_t)max((int32_t)v3 - pivot, 0) >> k);
                             }
-                            acc[l] += add;
+                        }
+                    }
+                } else {
+                    for (uint32_t i = 0; i < per; ++i) {
+                        const uint32_t v = zigzag32(rp[i]);
+                        #pragma unroll
+                        for (int l = 0; l <= kLog2MaxParts; ++l) {
+                            const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
+                            if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
+                            else { acc[l] += (k + 2u) + ((uint32_t)max((int32_t)v - (int32_t)(2u << k), 0) >> k); }
                         }
                     }
                 }
@@ -832,28 +991,25 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
         } else {
             for (uint32_t i = tid; i < n; i += kThreads) {
                 const uint32_t v = zigzag32(res_s[i]);
-                const uint32_t q = i / per;
+                const unsigned long long pk = finest[i / per];
                 #pragma unroll
                 for (int l = 0; l <= kLog2MaxParts; ++l) {
-                    if ((uint32_t)l <= max_porder) {
-                        const uint32_t k = ktab[((1u << l) - 1u) + (q >> (max_porder - (uint32_t)l))];
-                        if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
-                        else {
-                            const uint32_t k1 = k + 1u;
-                            const int32_t over = (int32_t)v - (int32_t)(1u << k1);
-                            acc[l] += (k1 + 1u) + ((uint32_t)((over > 0) ? over : 0) >> k);
-                        }
-                    }
+                    const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
+                    if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
+                    else { acc[l] += (k + 2u) + ((uint32_t)max((int32_t)v - (int32_t)(2u << k), 0) >> k); }
                 }
             }
         }
+        /* levels above max_porder accumulated garbage (their packed fields are 0): ignored below.
+         * parameter fields: 5 bits for the first partition, zig-zag delta + 1 for the others */
         #pragma unroll
         for (int l = 0; l <= kLog2MaxParts; ++l) {
             if ((uint32_t)l <= max_porder) {
                 const uint32_t cnt = 1u << l, base = cnt - 1u;
                 for (uint32_t q = tid; q < cnt; q += kThreads) {
-                    const uint32_t k = ktab[base + q];
-                    acc[l] += (q == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)ktab[base + q - 1u]) + 1u);
+                    const uint32_t k = (uint32_t)(pack[base + q] >> (5 * l)) & 31u;
+                    const uint32_t kprev = q ? ((uint32_t)(pack[base + q - 1u] >> (5 * l)) & 31u) : 0u;
+                    acc[l] += (q == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)kprev) + 1u);
                 }
             }
         }
@@ -872,7 +1028,9 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
             if (bits < best_bits) { best_bits = bits; best_porder = l; }
         }
         residual_bits = best_bits + 2u;
-        for (uint32_t q = tid; q < (1u << best_porder); q += kThreads) { out->kparam[q] = ktab[((1u << best_porder) - 1u) + q]; }
+        for (uint32_t q = tid; q < (1u << best_porder); q += kThreads) {
+            out->kparam[q] = (uint8_t)((pack[((1u << best_porder) - 1u) + q] >> (5u * best_porder)) & 31u);
+        }
     }
 
     /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */

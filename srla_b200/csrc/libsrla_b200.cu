@@ -277,16 +277,13 @@ struct Runner {
         }
         const uint32_t ncands = p.num_jobs * p.ncand;
         const dim3 grid(ncands), block(kThreads);
-        const uint32_t bpt = (p.fft_max + 2047u) / 2048u;
-        if (bpt <= 1) {
-            if (!prep_kernel(front_kernel<1>, FL.total)) { return false; }
-            front_kernel<1><<<grid, block, FL.total, c->stream>>>(p);
-        } else if (bpt == 2) {
-            if (!prep_kernel(front_kernel<2>, FL.total)) { return false; }
-            front_kernel<2><<<grid, block, FL.total, c->stream>>>(p);
-        } else if (bpt <= 4) {
-            if (!prep_kernel(front_kernel<4>, FL.total)) { return false; }
-            front_kernel<4><<<grid, block, FL.total, c->stream>>>(p);
+        if (p.fft_max <= 4096u) {
+            /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
+            if (!prep_kernel(front_kernel<128>, FL.total)) { return false; }
+            front_kernel<128><<<grid, 128, FL.total, c->stream>>>(p);
+        } else if (p.fft_max <= 8192u) {
+            if (!prep_kernel(front_kernel<256>, FL.total)) { return false; }
+            front_kernel<256><<<grid, 256, FL.total, c->stream>>>(p);
         } else {
             std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
             return false;

@@ -167,7 +167,6 @@ struct ResidLayout {
     uint32_t region_off, region_bytes; /* int32 residual[n4] then the mean pyramid (doubles)   */
     uint32_t sig_off;
     uint32_t coef_off;                 /* int32 x (roundup4(P) + 4)                            */
-    uint32_t ktab_off;                 /* 2048 bytes                                           */
     uint32_t red_off;                  /* 1024 bytes of reduction scratch                      */
     uint32_t total;
 };
@@ -182,7 +181,6 @@ SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
     off += L.region_bytes;
     L.sig_off = off; off += 4u * (n4 + 8u);
     L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
-    L.ktab_off = off; off += 2048u;
     L.red_off = off; off += 1024u;
     L.total = off;
     return L;
