@@ -1,7 +1,7 @@
 /*
  * kernels.cuh -- the sm_100a CUDA kernels of the SRLA encode path.
  *
- *   lshift_or_kernel / lshift_finish_kernel   whole-stream OR reduce -> trailing-zero shift   (A0)
+ *   lshift_jobs_kernel / lshift_finish_kernel whole-stream OR reduce -> trailing-zero shift   (A0)
  *   front_kernel<BPT>       one CTA per (block, candidate channel): mid/side, pre-emphasis, optional LTP,
  *                           Welch window + FFT autocorrelation, block resident in shared memory (A2-A5, A11)
  *   lpc_kernel              one thread per candidate: Levinson-Durbin, order choice, quantisation   (A5, A6)
@@ -39,6 +39,21 @@ __device__ __forceinline__ int32_t load_sample(const StreamDev &st, uint32_t ch,
                                    : __ldg(reinterpret_cast<const int32_t *>(st.pcm) + at);
 }
 
+__device__ __forceinline__ int4 load_quad(const StreamDev &st, uint32_t ch, uint32_t idx)
+{
+    const unsigned long long at = (unsigned long long)ch * st.stride + idx;
+    if (st.sample_bytes == 2u) {
+        const int2 v = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const short *>(st.pcm) + at));
+        return make_int4((int32_t)(short)(v.x & 0xffff), v.x >> 16, (int32_t)(short)(v.y & 0xffff), v.y >> 16);
+    }
+    return __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int32_t *>(st.pcm) + at));
+}
+__device__ __forceinline__ bool quad_aligned(const StreamDev &st, uint32_t ch, uint32_t idx)
+{
+    const unsigned long long addr = reinterpret_cast<unsigned long long>(st.pcm) + ((unsigned long long)ch * st.stride + idx) * st.sample_bytes;
+    return (addr & (4ull * st.sample_bytes - 1ull)) == 0ull;
+}
+
 __device__ __forceinline__ long long warp_sum_ll(long long v)
 {
     #pragma unroll
@@ -71,59 +86,40 @@ __device__ __forceinline__ uint32_t block_scan_inclusive(uint32_t v, uint32_t *s
 }
 
 /* ------------------------------------------------------------------------------------------------
- * A0: trailing-zero shift of a whole stream (srla_utility.c:177-203)
- * grid.x = chunks, grid.y = stream
+ * A0: trailing-zero shift of a whole stream (srla_utility.c:177-203).
+ * lshift_jobs_kernel: one CTA per job ORs the job's samples of every channel into its stream's
+ * or_mask (16-byte vector loads where aligned) -- the only purely HBM-bound kernel of the path.
+ * lshift_finish_kernel: or_mask -> trailing zero count; optionally snapshots the value the jobs of
+ * this launch group are about to use (pipelined host path, see Runner::run).
  * ---------------------------------------------------------------------------------------------- */
-__global__ void lshift_or_kernel(StreamDev *streams, uint32_t nch)
+__global__ void __launch_bounds__(256) lshift_jobs_kernel(StreamDev *streams, const Job *jobs, uint32_t nch)
 {
-    StreamDev &st = streams[blockIdx.y];
-    const unsigned long long total = (unsigned long long)st.num_samples;
+    const Job &job = jobs[blockIdx.x];
+    StreamDev &st = streams[job.stream];
+    const uint32_t n = job.nsmpl;
     uint32_t acc = 0;
     for (uint32_t c = 0; c < nch; ++c) {
-        if (st.sample_bytes == 2u) {
-            const short *base = reinterpret_cast<const short *>(st.pcm) + (unsigned long long)c * st.stride;
-            /* 16-byte vector body when the channel start is aligned, scalar head/tail otherwise */
-            const unsigned long long mis = ((reinterpret_cast<unsigned long long>(base) + 15ull) & ~15ull) - reinterpret_cast<unsigned long long>(base);
-            unsigned long long head = mis / 2ull; if (head > total) { head = total; }
-            const unsigned long long nvec = (total - head) / 8ull;
-            const int4 *v = reinterpret_cast<const int4 *>(base + head);
-            for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (unsigned long long)gridDim.x * blockDim.x) {
-                const int4 q = __ldg(v + i);
-                uint32_t m = (uint32_t)(q.x | q.y | q.z | q.w);
-                acc |= (m & 0xffffu) | (m >> 16);
-            }
-            if (blockIdx.x == 0) {
-                for (unsigned long long i = threadIdx.x; i < head; i += blockDim.x) { acc |= (uint32_t)(int32_t)base[i]; }
-                for (unsigned long long i = head + nvec * 8ull + threadIdx.x; i < total; i += blockDim.x) { acc |= (uint32_t)(int32_t)base[i]; }
-            }
-        } else {
-            const int32_t *base = reinterpret_cast<const int32_t *>(st.pcm) + (unsigned long long)c * st.stride;
-            const unsigned long long mis = ((reinterpret_cast<unsigned long long>(base) + 15ull) & ~15ull) - reinterpret_cast<unsigned long long>(base);
-            unsigned long long head = mis / 4ull; if (head > total) { head = total; }
-            const unsigned long long nvec = (total - head) / 4ull;
-            const int4 *v = reinterpret_cast<const int4 *>(base + head);
-            for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (unsigned long long)gridDim.x * blockDim.x) {
-                const int4 q = __ldg(v + i);
-                acc |= (uint32_t)(q.x | q.y | q.z | q.w);
-            }
-            if (blockIdx.x == 0) {
-                for (unsigned long long i = threadIdx.x; i < head; i += blockDim.x) { acc |= (uint32_t)base[i]; }
-                for (unsigned long long i = head + nvec * 4ull + threadIdx.x; i < total; i += blockDim.x) { acc |= (uint32_t)base[i]; }
-            }
+        const bool vec = quad_aligned(st, c, job.offset);
+        const uint32_t nquad = vec ? (n >> 2) : 0u;
+        for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
+            const int4 q = load_quad(st, c, job.offset + 4u * g);
+            acc |= (uint32_t)(q.x | q.y | q.z | q.w);
         }
+        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += blockDim.x) { acc |= (uint32_t)load_sample(st, c, job.offset + i); }
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { acc |= __shfl_xor_sync(0xffffffffu, acc, o); }
     if ((threadIdx.x & 31) == 0 && acc) { atomicOr(&st.or_mask, acc); }
 }
 
-__global__ void lshift_finish_kernel(StreamDev *streams, uint32_t num_streams)
+__global__ void lshift_finish_kernel(StreamDev *streams, uint32_t num_streams, uint32_t *snapshot)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < num_streams) {
-        /* int16 lanes were folded into the low half: sign extension bits do not add low set bits */
         const uint32_t m = streams[s].or_mask;
-        streams[s].lshift = m ? (uint32_t)(__ffs((int)m) - 1) : 0u;
+        const uint32_t sh = m ? (uint32_t)(__ffs((int)m) - 1) : 0u;
+        streams[s].lshift = sh;
+        if (snapshot) { snapshot[s] = sh; }
     }
 }
 
@@ -230,14 +226,15 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
         }
         __syncthreads();
         const double2 *tw = p.tw_complex + p.tw_complex_off[3];
-        const Twiddle3 w0 = load_twiddle(tw, 0u, inverse), w1 = load_twiddle(tw, 1u, inverse);
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
             if (u < s) {
                 double2 y[2][4];
-                butterfly4(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, inverse, y[0][0], y[0][1], y[0][2], y[0][3]);
-                butterfly4(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, inverse, y[1][0], y[1][1], y[1][2], y[1][3]);
+                { const Twiddle3 w0 = load_twiddle(tw, 0u, inverse);
+                  butterfly4(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, inverse, y[0][0], y[0][1], y[0][2], y[0][3]); }
+                { const Twiddle3 w1 = load_twiddle(tw, 1u, inverse);
+                  butterfly4(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, inverse, y[1][0], y[1][1], y[1][2], y[1][3]); }
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     x[fft_slot(u + (uint32_t)j * s)]            = cadd(y[0][j], y[1][j]);
@@ -478,21 +475,6 @@ __device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, 
  * ---------------------------------------------------------------------------------------------- */
 /* load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) -> raw[0..n).
  * returns OR of the unshifted samples of a plain channel candidate (0 for M/S). */
-__device__ __forceinline__ int4 load_quad(const StreamDev &st, uint32_t ch, uint32_t idx)
-{
-    const unsigned long long at = (unsigned long long)ch * st.stride + idx;
-    if (st.sample_bytes == 2u) {
-        const int2 v = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const short *>(st.pcm) + at));
-        return make_int4((int32_t)(short)(v.x & 0xffff), v.x >> 16, (int32_t)(short)(v.y & 0xffff), v.y >> 16);
-    }
-    return __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int32_t *>(st.pcm) + at));
-}
-__device__ __forceinline__ bool quad_aligned(const StreamDev &st, uint32_t ch, uint32_t idx)
-{
-    const unsigned long long addr = reinterpret_cast<unsigned long long>(st.pcm) + ((unsigned long long)ch * st.stride + idx) * st.sample_bytes;
-    return (addr & (4ull * st.sample_bytes - 1ull)) == 0ull;
-}
-
 __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
                                               uint32_t lshift, int32_t *raw)
 {
@@ -575,7 +557,7 @@ __device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n
  * the Welch-windowed FFT autocorrelation of the signal the LPC stage sees; lags 0..P go to HBM.
  * ---------------------------------------------------------------------------------------------- */
 template <int kT>
-__global__ void __launch_bounds__(kT, (kT <= 128) ? 3 : 1) front_kernel(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(kT, (kT <= 128) ? 4 : 2) front_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FrontLayout L = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
@@ -589,8 +571,8 @@ __global__ void __launch_bounds__(kT, (kT <= 128) ? 3 : 1) front_kernel(const __
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
-    const Job job = p.jobs[job_id];
-    const StreamDev st = p.streams[job.stream];
+    const Job &job = p.jobs[job_id];
+    const StreamDev &st = p.streams[job.stream];
     const uint32_t n = job.nsmpl, P = p.max_order;
     const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
     CandOut *out = p.cand + (size_t)job_id * p.ncand + cand;

@@ -74,7 +74,8 @@ struct PinBuf {
 struct DeviceCtx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_upload = nullptr;
+    bool upload_pending = false;
     std::vector<cudaEvent_t> ev_pool;      /* per batch: front begin, lpc begin, residual begin, decide begin, end */
     size_t ev_used = 0;
     /* tables */
@@ -82,7 +83,12 @@ struct DeviceCtx {
     uint32_t tw_c_off[20], tw_r_off[20];
     /* work */
     DevBuf streams, jobs, cand, diag, jobout, residual, lags, misc, stream_begin, pcm, out;
-    PinBuf h_jobs, h_small, h_jobout, h_result;
+    PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox;
+    DevBuf snapshot;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_h2d, ev_grp;
+    std::vector<Job> jobs_scratch;
+    uint32_t smem_set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     int max_smem_optin = 0;
     int num_sms = 0;
 };
@@ -123,8 +129,11 @@ bool ctx_init(DeviceCtx *c)
     CU_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev_begin));
     CU_TRY(cudaEventCreate(&c->ev_end));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
 
     /* host-libm tables (host_tables.h) */
     std::vector<host::Cx> tab; std::vector<uint32_t> off;
@@ -161,8 +170,14 @@ void ctx_destroy(DeviceCtx *c)
     cudaSetDevice(c->device);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); }
     for (cudaEvent_t e : c->ev_pool) { cudaEventDestroy(e); }
+    for (cudaEvent_t e : c->ev_h2d) { cudaEventDestroy(e); }
+    for (cudaEvent_t e : c->ev_grp) { cudaEventDestroy(e); }
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); }
+    if (c->d2h_stream) { cudaStreamDestroy(c->d2h_stream); }
+    c->snapshot.release(); c->h_mailbox.release();
     if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
+    if (c->ev_upload) { cudaEventDestroy(c->ev_upload); }
     DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs, &c->cand,
                        &c->diag, &c->jobout, &c->residual, &c->lags, &c->misc, &c->stream_begin, &c->pcm, &c->out };
     for (DevBuf *b : bufs) { b->release(); }
@@ -182,22 +197,25 @@ bool config_valid(const struct SRLAEncoderConfig *cfg)
 }
 
 /* per-length constants of a job: host libm pow() for the Welch divisor (lpc.c:259) */
-struct LenConst { double div, gain, scale; };
-LenConst len_const(uint32_t n, std::map<uint32_t, LenConst> &cache)
-{
-    auto it = cache.find(n);
-    if (it != cache.end()) { return it->second; }
-    LenConst lc;
-    lc.div = 4.0 * std::pow((double)(n - 1), -2.0);
-    { const double m = (double)n - 1; lc.gain = (15 * (m - 1) * (m - 1) * (m - 1)) / (8 * m * (m - 2) * (m * m - 2 * m + 2)); }   /* lpc.c:275-290 */
-    lc.scale = 2.0 / n;
-    cache[n] = lc;
-    return lc;
-}
+struct LenConst { uint32_t n; double div, gain, scale; };
+struct LenCache {
+    LenConst slot[8]; int used = 0;
+    const LenConst &get(uint32_t n)
+    {
+        for (int i = 0; i < used; i++) { if (slot[i].n == n) { return slot[i]; } }
+        LenConst lc; lc.n = n;
+        lc.div = 4.0 * std::pow((double)(n - 1), -2.0);
+        { const double m = (double)n - 1; lc.gain = (15 * (m - 1) * (m - 1) * (m - 1)) / (8 * m * (m - 2) * (m * m - 2 * m + 2)); }   /* lpc.c:275-290 */
+        lc.scale = 2.0 / n;
+        const int at = (used < 8) ? used++ : (int)(n & 7u);
+        slot[at] = lc;
+        return slot[at];
+    }
+};
 
-Job make_job(uint32_t stream, uint32_t offset, uint32_t n, uint32_t flags, std::map<uint32_t, LenConst> &cache)
+inline Job make_job(uint32_t stream, uint32_t offset, uint32_t n, uint32_t flags, LenCache &cache)
 {
-    Job j; const LenConst lc = len_const(n, cache);
+    Job j; const LenConst &lc = cache.get(n);
     j.stream = stream; j.offset = offset; j.nsmpl = n; j.flags = flags;
     j.welch_div = lc.div; j.welch_gain = lc.gain; j.ac_scale = lc.scale;
     return j;
@@ -205,9 +223,17 @@ Job make_job(uint32_t stream, uint32_t offset, uint32_t n, uint32_t flags, std::
 
 uint32_t ceil_pow2_host(uint32_t v) { uint32_t p = 1; while (p < v) { p <<= 1; } return p; }
 
+/* host-side view of one stream when PCM / output live in host memory */
+struct HostStream { const void *ch[SRLA_MAX_NUM_CHANNELS]; };
+struct HostIO {
+    const HostStream *streams = nullptr;   /* per-channel host pointers of every stream */
+    uint8_t *out = nullptr;                /* host output buffer */
+    uint64_t out_capacity = 0;
+};
+
 /* what one call encodes */
 struct Plan {
-    const struct SRLAB200Stream *streams = nullptr;   /* device PCM */
+    const struct SRLAB200Stream *streams = nullptr;   /* DEVICE PCM layout of every stream */
     uint32_t num_streams = 0;
     uint32_t nch = 0;
     bool emit_stream_header = true;
@@ -216,11 +242,12 @@ struct Plan {
     bool variable = false;            /* min != max: optimal block division */
     bool size_only = false;           /* ComputeBlockSize */
     bool want_diag = false;
+    bool allow_pipeline = true;
 };
 
 struct Runner {
     SRLAEncoder *enc; DeviceCtx *c;
-    std::map<uint32_t, LenConst> len_cache;
+    LenCache len_cache;
     uint64_t launches = 0;
 
     LaunchParams base_params(const Plan &pl, uint32_t nmax) const
@@ -257,11 +284,14 @@ struct Runner {
         return true;
     }
 
+    /* dynamic shared memory opt-in + maximum carve-out, once per (kernel, size) */
     template <typename K>
-    bool prep_kernel(K kernel, uint32_t smem_bytes)
+    bool prep_kernel(K kernel, uint32_t smem_bytes, int slot)
     {
+        if (c->smem_set[slot] == smem_bytes) { return true; }
         CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        c->smem_set[slot] = smem_bytes;
         return true;
     }
 
@@ -279,10 +309,10 @@ struct Runner {
         const dim3 grid(ncands), block(kThreads);
         if (p.fft_max <= 4096u) {
             /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
-            if (!prep_kernel(front_kernel<128>, FL.total)) { return false; }
+            if (!prep_kernel(front_kernel<128>, FL.total, 0)) { return false; }
             front_kernel<128><<<grid, 128, FL.total, c->stream>>>(p);
         } else if (p.fft_max <= 8192u) {
-            if (!prep_kernel(front_kernel<256>, FL.total)) { return false; }
+            if (!prep_kernel(front_kernel<256>, FL.total, 1)) { return false; }
             front_kernel<256><<<grid, 256, FL.total, c->stream>>>(p);
         } else {
             std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
@@ -291,46 +321,46 @@ struct Runner {
         launches++;
         if (!mark(batch, 1)) { return false; }
         if (p.max_order > 0) {
-            if (!prep_kernel(lpc_kernel, LL.total)) { return false; }
+            if (!prep_kernel(lpc_kernel, LL.total, 2)) { return false; }
             lpc_kernel<<<(ncands + 31u) / 32u, 32, LL.total, c->stream>>>(p);
             launches++;
         }
         if (!mark(batch, 2)) { return false; }
-        if (!prep_kernel(residual_kernel, RL.total)) { return false; }
+        if (!prep_kernel(residual_kernel, RL.total, 3)) { return false; }
         residual_kernel<<<grid, block, RL.total, c->stream>>>(p);
         launches++;
         CU_TRY(cudaGetLastError());
         return true;
     }
 
-    /* upload stream descriptors and compute offset_lshift on the device */
+    /* upload stream descriptors (or_mask = 0, lshift = 0) */
     bool prepare_streams(const Plan &pl)
     {
         const size_t bytes = sizeof(StreamDev) * pl.num_streams;
         if (!c->streams.reserve(bytes) || !c->h_small.reserve(bytes + 64) || !c->stream_begin.reserve(sizeof(unsigned long long) * (pl.num_streams + 1))) { return false; }
         StreamDev *h = (StreamDev *)c->h_small.p;
-        uint32_t longest = 0;
         for (uint32_t s = 0; s < pl.num_streams; s++) {
             h[s].pcm = pl.streams[s].pcm; h[s].stride = pl.streams[s].channel_stride;
             h[s].num_samples = pl.streams[s].num_samples; h[s].sample_bytes = pl.streams[s].sample_bytes;
             h[s].lshift = 0; h[s].or_mask = 0;
-            longest = std::max(longest, h[s].num_samples);
         }
         CU_TRY(cudaMemcpyAsync(c->streams.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
-        if (!pl.use_fixed_lshift) {
-            const uint32_t per_cta = 256u * 8u * 16u;
-            uint32_t gx = std::max(1u, std::min((longest + per_cta - 1) / per_cta, 4096u));
-            lshift_or_kernel<<<dim3(gx, pl.num_streams), 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.nch);
-            lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.num_streams);
-            CU_TRY(cudaGetLastError());
-            launches += 2;
-        }
+        return true;
+    }
+
+    /* OR-reduce the samples of `count` jobs into their streams and refresh every stream's shift */
+    bool launch_lshift(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t *d_snapshot)
+    {
+        lshift_jobs_kernel<<<count, 256, 0, c->stream>>>((StreamDev *)c->streams.p, d_jobs, pl.nch);
+        lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.num_streams, d_snapshot);
+        CU_TRY(cudaGetLastError());
+        launches += 2;
         return true;
     }
 
     /* analyse + decide a list of jobs (already on the device at d_jobs), optionally scan + emit */
     bool run_batch(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t nmax, bool emit, uint8_t *d_out, uint64_t cap,
-                   bool store_residual, size_t ev_idx)
+                   bool store_residual, size_t ev_idx, unsigned long long *h_mailbox)
     {
         LaunchParams p = base_params(pl, nmax);
         p.jobs = d_jobs; p.num_jobs = count;
@@ -354,9 +384,10 @@ struct Runner {
         launches++;
         if (emit) {
             scan_kernel<<<1, 1024, 0, c->stream>>>(p);
+            if (h_mailbox) { CU_TRY(cudaMemcpyAsync(h_mailbox, p.running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream)); }
             const uint32_t smem = round_up_u32(raw_max, 4) + 16u;
             if ((int)smem > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] block too large for the emit stage (%u bytes)\n", smem); return false; }
-            CU_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (c->smem_set[4] != smem) { CU_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); c->smem_set[4] = smem; }
             emit_kernel<<<count, kThreads, smem, c->stream>>>(p);
             launches += 2;
         }
@@ -403,8 +434,40 @@ struct Runner {
         parts.assign(rev.rbegin(), rev.rend());
     }
 
-    /* whole call: streams -> output */
-    SRLAApiResult run(const Plan &pl, uint8_t *d_out, uint64_t cap, uint64_t *stream_offsets, uint32_t *single_estimate)
+    bool upload_jobs(const std::vector<Job> &jobs)
+    {
+        const size_t bytes = sizeof(Job) * jobs.size();
+        if (c->upload_pending) { CU_TRY(cudaEventSynchronize(c->ev_upload)); c->upload_pending = false; }   /* the staging buffer is reused */
+        if (!c->jobs.reserve(bytes) || !c->h_jobs.reserve(bytes)) { return false; }
+        std::memcpy(c->h_jobs.p, jobs.data(), bytes);
+        CU_TRY(cudaMemcpyAsync(c->jobs.p, c->h_jobs.p, bytes, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaEventRecord(c->ev_upload, c->stream));
+        c->upload_pending = true;
+        return true;
+    }
+
+    /* host -> device copy of the samples [begin, end) of every channel of stream s */
+    bool h2d_range(const Plan &pl, const HostIO &io, uint32_t s, uint32_t begin, uint32_t end, cudaStream_t on)
+    {
+        const struct SRLAB200Stream &d = pl.streams[s];
+        const size_t sb = d.sample_bytes;
+        for (uint32_t ch = 0; ch < pl.nch; ch++) {
+            unsigned char *dst = (unsigned char *)d.pcm + ((size_t)d.channel_stride * ch + begin) * sb;
+            const unsigned char *src = (const unsigned char *)io.streams[s].ch[ch] + (size_t)begin * sb;
+            CU_TRY(cudaMemcpyAsync(dst, src, (size_t)(end - begin) * sb, cudaMemcpyHostToDevice, on));
+        }
+        return true;
+    }
+
+    /* whole call: streams -> output.
+     * io == NULL: PCM is resident at pl.streams[].pcm and the output stays in d_out.
+     * io != NULL: PCM is copied from host memory into the layout pl.streams[] describes and the output
+     *   is copied back to io->out.  With fixed blocks the work is split into groups whose H2D copy,
+     *   kernels and D2H copy overlap on three streams.  offset_lshift needs the whole stream, so a
+     *   group runs with the shift of the samples seen SO FAR (snapshotted per group); if a later
+     *   group lowers a stream's shift -- essentially never for real audio, whose first odd sample is
+     *   in the first block -- the call is redone unpipelined on the now resident data. */
+    SRLAApiResult run(const Plan &pl, uint8_t *d_out, uint64_t cap, uint64_t *stream_offsets, uint32_t *single_estimate, const HostIO *io)
     {
         SRLAB200Stats &stt = enc->stats;
         std::memset(&stt, 0, sizeof(stt));
@@ -416,23 +479,60 @@ struct Runner {
             if (pl.streams[s].pcm == nullptr) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
             stt.bytes_in += (uint64_t)pl.nch * pl.streams[s].num_samples * pl.streams[s].sample_bytes;
         }
+
+        /* ---- job list ---- */
+        std::vector<Job> &jobs = c->jobs_scratch;
+        jobs.clear();
+        for (uint32_t s = 0; s < pl.num_streams; s++) {          /* fixed tiling: the block list, or the cover used for the shift */
+            const uint32_t total = pl.streams[s].num_samples;
+            for (uint32_t at = 0; at < total; at += max_block) {
+                jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
+            }
+        }
+        const bool pipelined = io && !pl.variable && !pl.size_only && pl.allow_pipeline && !pl.use_fixed_lshift && jobs.size() >= 2048;
+        const uint32_t per_batch = jobs_per_batch(pl, max_block);
+        uint32_t group = per_batch;
+        if (pipelined) { group = std::min<uint32_t>(per_batch, std::max<uint32_t>(1024u, (uint32_t)((jobs.size() + 7) / 8))); }
+        const size_t num_groups = (jobs.size() + group - 1) / group;
+
         if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
         if (cudaMemsetAsync(c->misc.p, 0, 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t), c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
 
-        std::vector<Job> jobs;
-        size_t ev_idx = 0;
-        if (!pl.variable) {
-            for (uint32_t s = 0; s < pl.num_streams; s++) {
-                const uint32_t total = pl.streams[s].num_samples;
-                for (uint32_t at = 0; at < total; at += max_block) {
-                    jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
+        /* ---- host input ---- */
+        std::vector<cudaEvent_t> &h2d_done = c->ev_h2d;
+        if (io) {
+            if (pipelined) {
+                while (h2d_done.size() < num_groups) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } h2d_done.push_back(e); }
+                for (size_t g = 0; g < num_groups; g++) {
+                    const size_t j0 = g * group, j1 = std::min(jobs.size(), j0 + group);
+                    size_t j = j0;
+                    while (j < j1) {                                   /* one contiguous sample range per stream touched */
+                        const uint32_t s = jobs[j].stream, begin = jobs[j].offset;
+                        size_t k = j;
+                        while (k + 1 < j1 && jobs[k + 1].stream == s) { k++; }
+                        if (!h2d_range(pl, *io, s, begin, jobs[k].offset + jobs[k].nsmpl, c->copy_stream)) { return SRLA_APIRESULT_NG; }
+                        j = k + 1;
+                    }
+                    if (cudaEventRecord(h2d_done[g], c->copy_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
                 }
+            } else {
+                for (uint32_t s = 0; s < pl.num_streams; s++) { if (!h2d_range(pl, *io, s, 0, pl.streams[s].num_samples, c->stream)) { return SRLA_APIRESULT_NG; } }
             }
-        } else {
+        }
+
+        size_t ev_idx = 0;
+        uint32_t nmax = 1;
+        if (!pipelined && !pl.use_fixed_lshift) {
+            /* exact offset_lshift of every stream before any analysis */
+            if (!launch_lshift(pl, (const Job *)c->jobs.p, (uint32_t)jobs.size(), nullptr)) { return SRLA_APIRESULT_NG; }
+        }
+
+        if (pl.variable) {
             /* pass 1: exact size of every candidate segment of every look-ahead chunk */
             struct Chunk { uint32_t stream, at, len, nodes, first_job; };
-            std::vector<Chunk> chunks; std::vector<Job> cand_jobs; std::vector<uint32_t> edge_of_job;
+            std::vector<Chunk> chunks; std::vector<Job> cand_jobs;
             const uint32_t step = enc->param.num_lookahead_samples;
             for (uint32_t s = 0; s < pl.num_streams; s++) {
                 const uint32_t total = pl.streams[s].num_samples;
@@ -445,7 +545,6 @@ struct Runner {
                             if (len > max_block) { continue; }
                             if (len > ch.len - i * min_block) { len = ch.len - i * min_block; }
                             cand_jobs.push_back(make_job(s, at + i * min_block, len, 0u, len_cache));
-                            edge_of_job.push_back(i * ch.nodes + j);
                         }
                     }
                     chunks.push_back(ch);
@@ -453,23 +552,18 @@ struct Runner {
             }
             stt.num_analysed += cand_jobs.size();
             std::vector<uint32_t> est(cand_jobs.size());
-            {
-                const size_t bytes = sizeof(Job) * cand_jobs.size();
-                if (!c->jobs.reserve(bytes) || !c->h_jobs.reserve(bytes)) { return SRLA_APIRESULT_NG; }
-                std::memcpy(c->h_jobs.p, cand_jobs.data(), bytes);
-                if (cudaMemcpyAsync(c->jobs.p, c->h_jobs.p, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-                const uint32_t per = jobs_per_batch(pl, max_block);
-                for (size_t b = 0; b < cand_jobs.size(); b += per) {
-                    const uint32_t cnt = (uint32_t)std::min<size_t>(per, cand_jobs.size() - b);
-                    if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, max_block, false, nullptr, 0, false, ev_idx++)) { return SRLA_APIRESULT_NG; }
-                    if (!c->h_jobout.reserve(sizeof(JobOut) * cnt)) { return SRLA_APIRESULT_NG; }
-                    if (cudaMemcpyAsync(c->h_jobout.p, c->jobout.p, sizeof(JobOut) * cnt, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
-                        || cudaStreamSynchronize(c->stream) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] size pass failed: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
-                    const JobOut *jo = (const JobOut *)c->h_jobout.p;
-                    for (uint32_t k = 0; k < cnt; k++) { if (jo[k].status) { return SRLA_APIRESULT_NG; } est[b + k] = jo[k].estimate_bytes; }
-                }
+            if (!upload_jobs(cand_jobs)) { return SRLA_APIRESULT_NG; }
+            for (size_t b = 0; b < cand_jobs.size(); b += per_batch) {
+                const uint32_t cnt = (uint32_t)std::min<size_t>(per_batch, cand_jobs.size() - b);
+                if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, max_block, false, nullptr, 0, false, ev_idx++, nullptr)) { return SRLA_APIRESULT_NG; }
+                if (!c->h_jobout.reserve(sizeof(JobOut) * cnt)) { return SRLA_APIRESULT_NG; }
+                if (cudaMemcpyAsync(c->h_jobout.p, c->jobout.p, sizeof(JobOut) * cnt, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
+                    || cudaStreamSynchronize(c->stream) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] size pass failed: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
+                const JobOut *jo = (const JobOut *)c->h_jobout.p;
+                for (uint32_t k = 0; k < cnt; k++) { if (jo[k].status) { return SRLA_APIRESULT_NG; } est[b + k] = jo[k].estimate_bytes; }
             }
             /* shortest path per chunk -> final block list */
+            jobs.clear();
             for (const Chunk &ch : chunks) {
                 std::vector<uint32_t> edge((size_t)ch.nodes * ch.nodes, 0u);
                 uint32_t k = ch.first_job;
@@ -487,34 +581,61 @@ struct Runner {
                     off += len;
                 }
             }
+            if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
         }
         stt.num_analysed += jobs.size();
         stt.num_blocks = pl.size_only ? 0 : jobs.size();
-
-        uint32_t nmax = 1;
         for (const Job &j : jobs) { nmax = std::max(nmax, j.nsmpl); }
-        {
-            const size_t bytes = sizeof(Job) * jobs.size();
-            if (!c->jobs.reserve(bytes) || !c->h_jobs.reserve(bytes)) { return SRLA_APIRESULT_NG; }
-            std::memcpy(c->h_jobs.p, jobs.data(), bytes);
-            if (cudaMemcpyAsync(c->jobs.p, c->h_jobs.p, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+
+        /* ---- groups: [lshift so far] -> analyse -> decide -> scan -> emit ---- */
+        const size_t groups_now = pl.variable ? (jobs.size() + per_batch - 1) / per_batch : num_groups;
+        const uint32_t group_now = pl.variable ? per_batch : group;
+        std::vector<cudaEvent_t> &grp_done = c->ev_grp;
+        unsigned long long *mailbox = nullptr; uint32_t *d_snap = nullptr;
+        if (pipelined) {
+            while (grp_done.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } grp_done.push_back(e); }
+            if (!c->h_mailbox.reserve(sizeof(unsigned long long) * (groups_now + 1))) { return SRLA_APIRESULT_NG; }
+            mailbox = (unsigned long long *)c->h_mailbox.p;
+            if (!c->snapshot.reserve(sizeof(uint32_t) * groups_now * pl.num_streams)) { return SRLA_APIRESULT_NG; }
+            d_snap = (uint32_t *)c->snapshot.p;
         }
-        const uint32_t per = jobs_per_batch(pl, nmax);
-        for (size_t b = 0; b < jobs.size(); b += per) {
-            const uint32_t cnt = (uint32_t)std::min<size_t>(per, jobs.size() - b);
-            if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++)) { return SRLA_APIRESULT_NG; }
+        for (size_t g = 0; g < groups_now; g++) {
+            const size_t j0 = g * group_now;
+            const uint32_t cnt = (uint32_t)std::min<size_t>(group_now, jobs.size() - j0);
+            if (pipelined) {
+                if (cudaStreamWaitEvent(c->stream, h2d_done[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                if (!launch_lshift(pl, (const Job *)c->jobs.p + j0, cnt, d_snap + g * pl.num_streams)) { return SRLA_APIRESULT_NG; }
+            }
+            if (!run_batch(pl, (const Job *)c->jobs.p + j0, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++,
+                           pipelined ? mailbox + g : nullptr)) { return SRLA_APIRESULT_NG; }
+            if (pipelined && cudaEventRecord(grp_done[g], c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         }
         if (cudaEventRecord(c->ev_end, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
 
-        /* results */
+        /* ---- pipelined device -> host copies of finished groups ---- */
+        bool host_overflow = false;
+        if (pipelined) {
+            unsigned long long prev = 0;
+            for (size_t g = 0; g < groups_now; g++) {
+                if (cudaEventSynchronize(grp_done[g]) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
+                const unsigned long long end = mailbox[g];
+                if (end > io->out_capacity || end > cap) { host_overflow = true; break; }
+                if (end > prev && cudaMemcpyAsync(io->out + prev, d_out + prev, end - prev, cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                prev = end;
+            }
+        }
+
+        /* ---- results ---- */
         const size_t small_bytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t);
         const size_t sb_bytes = sizeof(unsigned long long) * (pl.num_streams + 1);
-        if (!c->h_result.reserve(small_bytes + sb_bytes + sizeof(JobOut) + 64)) { return SRLA_APIRESULT_NG; }
+        const size_t snap_bytes = pipelined ? sizeof(uint32_t) * groups_now * pl.num_streams : 0;
+        if (!c->h_result.reserve(small_bytes + sb_bytes + sizeof(JobOut) + snap_bytes + 64)) { return SRLA_APIRESULT_NG; }
         unsigned char *hs = (unsigned char *)c->h_result.p;
         cudaMemcpyAsync(hs, c->misc.p, small_bytes, cudaMemcpyDeviceToHost, c->stream);
         cudaMemcpyAsync(hs + small_bytes, c->stream_begin.p, sb_bytes, cudaMemcpyDeviceToHost, c->stream);
         cudaMemcpyAsync(hs + small_bytes + sb_bytes, c->jobout.p, sizeof(JobOut), cudaMemcpyDeviceToHost, c->stream);
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        if (pipelined) { cudaMemcpyAsync(hs + small_bytes + sb_bytes + sizeof(JobOut), c->snapshot.p, snap_bytes, cudaMemcpyDeviceToHost, c->stream); }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess || (pipelined && (cudaStreamSynchronize(c->d2h_stream) != cudaSuccess || cudaStreamSynchronize(c->copy_stream) != cudaSuccess))) {
             std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
             return SRLA_APIRESULT_NG;
         }
@@ -522,6 +643,26 @@ struct Runner {
         const uint32_t *dstats = (const uint32_t *)(hs + 2 * sizeof(unsigned long long));
         const unsigned long long *sbeg = (const unsigned long long *)(hs + small_bytes);
         const JobOut *first = (const JobOut *)(hs + small_bytes + sb_bytes);
+        if (pipelined) {
+            /* did every group run with the final shift of the streams it touched? */
+            const uint32_t *snap = (const uint32_t *)(hs + small_bytes + sb_bytes + sizeof(JobOut));
+            const uint32_t *fin = snap + (groups_now - 1) * pl.num_streams;
+            bool redo = false;
+            for (size_t g = 0; g + 1 < groups_now && !redo; g++) {
+                const size_t j0 = g * group_now, j1 = std::min(jobs.size(), j0 + group_now);
+                for (size_t j = j0; j < j1; j++) { const uint32_t s = jobs[j].stream; if (snap[g * pl.num_streams + s] != fin[s]) { redo = true; break; } }
+            }
+            if (redo) {
+                Plan again = pl; again.allow_pipeline = false;
+                Runner r2{ enc, c };
+                const SRLAApiResult rc = r2.run(again, d_out, cap, stream_offsets, single_estimate, nullptr);
+                if (rc != SRLA_APIRESULT_OK) { return rc; }
+                const uint64_t total = enc->stats.bytes_out;
+                if (total > io->out_capacity) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+                if (cudaMemcpy(io->out, d_out, total, cudaMemcpyDeviceToHost) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                return SRLA_APIRESULT_OK;
+            }
+        }
         stt.kernel_launches = launches;
         stt.bytes_out = running[0];
         for (int i = 0; i < 256; i++) { stt.order_histogram[i] = dstats[i]; }
@@ -536,14 +677,17 @@ struct Runner {
         }
         if (single_estimate) { *single_estimate = first->estimate_bytes; if (first->status) { return SRLA_APIRESULT_NG; } }
         if (pl.size_only) { return SRLA_APIRESULT_OK; }
-        /* any block whose analysis failed the way the reference fails (singular LTP system)? */
+        /* a block whose analysis failed the way the reference fails (singular LTP system) is never
+         * written: every emitted job increments exactly one block-type counter */
         {
-            /* statuses live in jobout of the last batch only; a failed block is never written, so the
-             * byte count of written block types tells: every job increments exactly one type counter */
             const uint64_t emitted = (uint64_t)dstats[260] + dstats[261] + dstats[262];
-            if (running[1] == 0 && emitted != jobs.size()) { return SRLA_APIRESULT_NG; }
+            if (running[1] == 0 && !host_overflow && emitted != jobs.size()) { return SRLA_APIRESULT_NG; }
         }
-        if (running[1] != 0 || running[0] > cap) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+        if (running[1] != 0 || running[0] > cap || host_overflow) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+        if (io) {
+            if (running[0] > io->out_capacity) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+            if (!pipelined && cudaMemcpy(io->out, d_out, running[0], cudaMemcpyDeviceToHost) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        }
         if (stream_offsets) {
             for (uint32_t s = 0; s < pl.num_streams; s++) { stream_offsets[s] = pl.emit_stream_header ? sbeg[s] : 0; }
             stream_offsets[pl.num_streams] = running[0];
@@ -702,7 +846,7 @@ static SRLAApiResult single_chunk(struct SRLAEncoder *encoder, const int32_t *co
     if (!size_only && !c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
     uint64_t offs[2] = { 0, 0 };
     uint32_t est = 0;
-    const SRLAApiResult rc = r.run(pl, size_only ? nullptr : (uint8_t *)c->out.p, size_only ? 0 : cap, offs, size_only ? &est : nullptr);
+    const SRLAApiResult rc = r.run(pl, size_only ? nullptr : (uint8_t *)c->out.p, size_only ? 0 : cap, offs, size_only ? &est : nullptr, nullptr);
     if (rc != SRLA_APIRESULT_OK) { return rc; }
     if (size_only) { *output_size = est; return SRLA_APIRESULT_OK; }
     if (offs[1] > data_size) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
@@ -757,19 +901,22 @@ SRLAApiResult SRLAEncoder_EncodeWhole(
     if (data_size < SRLA_HEADER_SIZE) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
     DeviceCtx *c = encoder->ctx;
     if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    const uint32_t nch = encoder->param.num_channels;
+    const uint64_t stride = round_up_u32(num_samples, 16);
+    const uint64_t cap = max_encoded_size(encoder, num_samples);
+    if (!c->pcm.reserve(sizeof(int32_t) * stride * nch) || !c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
     struct SRLAB200Stream desc;
-    if (!upload_planar_int32(c, input, encoder->param.num_channels, num_samples, &desc)) { return SRLA_APIRESULT_NG; }
+    desc.pcm = c->pcm.p; desc.channel_stride = stride; desc.num_samples = num_samples; desc.sample_bytes = 4;
+    HostStream hs;
+    for (uint32_t ch = 0; ch < nch; ch++) { if (input[ch] == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; } hs.ch[ch] = input[ch]; }
+    HostIO io; io.streams = &hs; io.out = data; io.out_capacity = data_size;
     Plan pl;
-    pl.streams = &desc; pl.num_streams = 1; pl.nch = encoder->param.num_channels;
+    pl.streams = &desc; pl.num_streams = 1; pl.nch = nch;
     pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
     Runner r{ encoder, c };
-    const uint64_t cap = max_encoded_size(encoder, num_samples);
-    if (!c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
     uint64_t offs[2] = { 0, 0 };
-    const SRLAApiResult rc = r.run(pl, (uint8_t *)c->out.p, cap, offs, nullptr);
+    const SRLAApiResult rc = r.run(pl, (uint8_t *)c->out.p, cap, offs, nullptr, &io);
     if (rc != SRLA_APIRESULT_OK) { return rc; }
-    if (offs[1] > data_size) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
-    if (cudaMemcpy(data, c->out.p, offs[1], cudaMemcpyDeviceToHost) != cudaSuccess) { return SRLA_APIRESULT_NG; }
     *output_size = (uint32_t)offs[1];
     encoder->offset_lshift = data[24];                        /* the reference keeps it in its header (srla_encoder.c:1732) */
     if (encode_callback != NULL) {
@@ -805,7 +952,7 @@ SRLAApiResult SRLAB200_EncodeStreamsDevice(
     pl.streams = streams; pl.num_streams = num_streams; pl.nch = encoder->param.num_channels;
     pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
     Runner r{ encoder, encoder->ctx };
-    return r.run(pl, d_out, out_capacity, stream_offsets, nullptr);
+    return r.run(pl, d_out, out_capacity, stream_offsets, nullptr, nullptr);
 }
 
 SRLAApiResult SRLAB200_EncodeStreamsHost(
@@ -819,6 +966,7 @@ SRLAApiResult SRLAB200_EncodeStreamsHost(
     if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
     const uint32_t nch = encoder->param.num_channels;
     std::vector<struct SRLAB200Stream> dev(num_streams);
+    std::vector<HostStream> host(num_streams);
     uint64_t total_bytes = 0, cap = 0;
     for (uint32_t s = 0; s < num_streams; s++) {
         if (streams[s].pcm == NULL || (streams[s].sample_bytes != 2 && streams[s].sample_bytes != 4)) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
@@ -830,28 +978,17 @@ SRLAApiResult SRLAB200_EncodeStreamsHost(
     for (uint32_t s = 0; s < num_streams; s++) {
         const uint64_t stride = round_up_u32(streams[s].num_samples, 16);
         const uint32_t sb = streams[s].sample_bytes;
-        unsigned char *dst = (unsigned char *)c->pcm.p + at;
-        if (streams[s].channel_stride == stride) {
-            if (cudaMemcpyAsync(dst, streams[s].pcm, stride * nch * sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-        } else {
-            for (uint32_t ch = 0; ch < nch; ch++) {
-                if (cudaMemcpyAsync(dst + stride * ch * sb, (const unsigned char *)streams[s].pcm + streams[s].channel_stride * ch * sb,
-                                    (size_t)streams[s].num_samples * sb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-            }
-        }
-        dev[s].pcm = dst; dev[s].channel_stride = stride; dev[s].num_samples = streams[s].num_samples; dev[s].sample_bytes = sb;
+        dev[s].pcm = (unsigned char *)c->pcm.p + at; dev[s].channel_stride = stride;
+        dev[s].num_samples = streams[s].num_samples; dev[s].sample_bytes = sb;
+        for (uint32_t ch = 0; ch < nch; ch++) { host[s].ch[ch] = (const unsigned char *)streams[s].pcm + streams[s].channel_stride * ch * sb; }
         at += stride * nch * sb;
     }
+    HostIO io; io.streams = host.data(); io.out = out; io.out_capacity = out_capacity;
     Plan pl;
     pl.streams = dev.data(); pl.num_streams = num_streams; pl.nch = nch;
     pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
     Runner r{ encoder, c };
-    const SRLAApiResult rc = r.run(pl, (uint8_t *)c->out.p, cap, stream_offsets, nullptr);
-    if (rc != SRLA_APIRESULT_OK) { return rc; }
-    if (stream_offsets[num_streams] > out_capacity) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
-    if (cudaMemcpyAsync(out, c->out.p, stream_offsets[num_streams], cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
-        || cudaStreamSynchronize(c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-    return SRLA_APIRESULT_OK;
+    return r.run(pl, (uint8_t *)c->out.p, cap, stream_offsets, nullptr, &io);
 }
 
 uint64_t SRLAB200_MaxEncodedSize(const struct SRLAEncoder *encoder, uint32_t num_samples)
@@ -905,7 +1042,7 @@ SRLAApiResult SRLAB200_TestAnalyseChannel(
     Job job = make_job(0, 0, n, 0, r.len_cache);
     if (!c->jobs.reserve(sizeof(Job))) { return SRLA_APIRESULT_NG; }
     if (cudaMemcpyAsync(c->jobs.p, &job, sizeof(Job), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-    if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0)) { return SRLA_APIRESULT_NG; }
+    if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0, nullptr)) { return SRLA_APIRESULT_NG; }
     CandOut co; CandDiag dg;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess
         || cudaMemcpy(&co, c->cand.p, sizeof(co), cudaMemcpyDeviceToHost) != cudaSuccess

@@ -229,3 +229,32 @@ def test_reference_cli_relinked_against_libsrla_b200(tmp_path):
     with wave.open(str(back), "rb") as w:
         got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").reshape(-1, 2).T
     assert np.array_equal(got, pcm)
+
+
+def test_pipelined_host_path_and_late_shift_change():
+    """>= 2048 blocks take the pipelined host path (H2D / kernels / D2H overlapped in groups that run with
+    the offset shift seen so far).  (a) ordinary signal; (b) every sample of the first half is a multiple of
+    8 and the second half is not: the early groups ran with shift 3, the stream's shift is 0 -> the call
+    must notice and redo; (c) shift 3 throughout."""
+    n = 256 * 2400
+    base = synth_stereo(n, seed=91)
+    kw = dict(preset=2, max_block=256)
+    assert E.encode(base, **kw) == oracle_encode(base, **kw)
+    late = base.copy()
+    late[:, :n // 2] = (late[:, :n // 2] >> 3) << 3
+    late[0, n // 2 + 5] |= 1
+    got, want = E.encode(late, **kw), oracle_encode(late, **kw)
+    assert want[24] == 0 and got == want, _first_diff(got, want)
+    allshift = (base >> 3) << 3
+    got, want = E.encode(allshift, **kw), oracle_encode(allshift, **kw)
+    assert want[24] == 3 and got == want, _first_diff(got, want)
+    # the batch entry with several long int16 streams, one of them silent at the start
+    streams = [base[:, :256 * 1500].astype(np.int16), late[:, 256 * 900:].astype(np.int16), allshift[:, :256 * 700 + 100].astype(np.int16)]
+    streams[2][:, :256 * 300] = 0
+    with E.Encoder(max_block=256) as enc:
+        assert enc.set_parameter(2, 16, 48000, 256, 256, 256, 0, 2) == E.OK
+        out, offs = enc.encode_streams_host(streams)
+        for i, st in enumerate(streams):
+            want = oracle_encode(st.astype(np.int32), **kw)
+            got = out[offs[i]:offs[i + 1]].tobytes()
+            assert got == want, (i, _first_diff(got, want))
