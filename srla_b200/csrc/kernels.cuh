@@ -782,17 +782,329 @@ __global__ void __launch_bounds__(32) lpc_kernel(const __grid_constant__ LaunchP
  * residual_kernel: one CTA per (job, candidate).  Rebuilds the candidate signal, runs the int32
  * FIR (srla_lpc_predict.c:236-264), the residual coder search (srla_coder.c:349-483) and the
  * side-information accounting (srla_encoder.c:1122-1187).
+ *
+ * FIR.  The coefficients are 8-bit and, for 16-bit sources, the pre-emphasised signal almost always
+ * fits 16 bits, so the products are taken two taps at a time with IDP.2A (dp2a: s16 x s8 pairs
+ * accumulated in a wrapping int32 -- the same value mod 2^32 as the reference's int32 multiply-adds).
+ * The signal is repacked once into 16-byte entries Z[j] = { (x[4j],x[4j+1]), (x[4j+2],x[4j+3]),
+ * (x[4j+1],x[4j+2]), (x[4j+3],x[4j+4]) }: even outputs read the first two pair words, odd outputs the
+ * last two, so no output needs a funnel shift.  A thread produces 8 consecutive outputs from a
+ * sliding window of three entries: one LDS.128 per 16 IDP.2A.  Signals that do not fit 16 bits
+ * (24-bit sources, loud side channels) take the int32 IMAD path.
+ *
+ * Rice search.  For blocks of 1024 * {1,2,3,4,8} samples every thread owns four finest partitions;
+ * the mean pyramid is built in registers (warp shuffles above the thread level), so each thread
+ * knows the coding parameter of every enclosing partition.  The bits of the nine coarse partition
+ * orders are accumulated by parameter VALUE: the cost of the thread's samples is evaluated once per
+ * distinct parameter in the warp's range and credited to every level using it.
  * ---------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constant__ LaunchParams p)
+__device__ __forceinline__ uint32_t zpair_slot(uint32_t j) { return j ^ ((j >> 3) & 1u); }
+
+/* coding parameter of a partition with mean m (srla_coder.c:262-324) */
+__device__ __forceinline__ uint32_t coding_parameter(double m, uint32_t code_type, const double *rice_threshold)
+{
+    if (code_type == kCodeRice) {
+        uint32_t k = 0;
+        #pragma unroll 1
+        for (int j = 1; j < 32; ++j) { if (m >= __ldg(rice_threshold + j)) { k = (uint32_t)j; } }   /* host-libm thresholds */
+        return k;
+    }
+    const double g = 0.66794162356 * (1.0 + m);
+    const uint32_t golomb = (uint32_t)((1.0 > g) ? 1.0 : g);
+    return 31u - (uint32_t)__clz((int)golomb);
+}
+
+/* variable part of the code length of u with parameter k: recursive Rice max((u >> k) - 2, 0), Rice u >> k
+ * (srla_coder.c:165-190, 333-347); the constant part (k + 2, k + 1) is added per partition */
+template <bool kRice>
+__device__ __forceinline__ uint32_t var_len(uint32_t u, uint32_t k)
+{
+    const uint32_t t = u >> k;
+    return kRice ? t : (uint32_t)__viaddmax_s32_relu((int)t, -2, 0);
+}
+
+struct RiceResult { uint32_t code_type, porder, bits; };
+
+/* fast path: n = 1024 * NQ samples, 256 threads, thread t owns samples [4 NQ t, 4 NQ (t + 1)) */
+template <int NQ>
+__device__ __forceinline__ RiceResult rice_search_fast(const int32_t *res_s, unsigned char *scratch, uint32_t *red32,
+                                                       CandOut *out, const double *rice_threshold)
+{
+    constexpr int S = 4 * NQ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *warp_mean = reinterpret_cast<double *>(scratch);                              /* [8]   */
+    unsigned long long *kshare = reinterpret_cast<unsigned long long *>(scratch + 64);    /* [256] */
+    RiceResult rr; rr.porder = 0;
+
+    uint32_t v[S];
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(res_s + (size_t)tid * S);
+        #pragma unroll
+        for (int c = 0; c < NQ; ++c) {
+            const int4 t = src[c];
+            v[4 * c] = zigzag32(t.x); v[4 * c + 1] = zigzag32(t.y); v[4 * c + 2] = zigzag32(t.z); v[4 * c + 3] = zigzag32(t.w);
+        }
+    }
+    /* finest partition means: exact integer sums / NQ (srla_coder.c:371-383) */
+    double m10[4];
+    uint32_t any = 0;
+    #pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        unsigned long long s = 0;
+        #pragma unroll
+        for (int i = 0; i < NQ; ++i) { s += v[f * NQ + i]; any |= v[f * NQ + i]; }
+        m10[f] = (double)s / (double)NQ;
+    }
+    any = (uint32_t)__syncthreads_or((int)(any != 0u));
+    if (!any) { rr.code_type = kCodeAllZero; rr.bits = 2u; return rr; }
+
+    /* mean pyramid (srla_coder.c:385-389): levels 9, 8 in the thread, 7..3 across the warp, 2..0 across warps */
+    double mean[11];
+    const double m9a = (m10[0] + m10[1]) / 2.0, m9b = (m10[2] + m10[3]) / 2.0;
+    mean[8] = (m9a + m9b) / 2.0;
+    #pragma unroll
+    for (int l = 7; l >= 3; --l) {
+        const double mine = mean[l + 1], other = __shfl_xor_sync(0xffffffffu, mine, 1 << (7 - l));
+        mean[l] = (mine + other) / 2.0;
+    }
+    if (lane == 0) { warp_mean[warp] = mean[3]; }
+    __syncthreads();
+    {
+        const int w2 = warp & ~1, w4 = warp & ~3;
+        mean[2] = (warp_mean[w2] + warp_mean[w2 + 1]) / 2.0;
+        const double q0 = (warp_mean[w4] + warp_mean[w4 + 1]) / 2.0, q1 = (warp_mean[w4 + 2] + warp_mean[w4 + 3]) / 2.0;
+        mean[1] = (q0 + q1) / 2.0;
+        const double h0 = ((warp_mean[0] + warp_mean[1]) / 2.0 + (warp_mean[2] + warp_mean[3]) / 2.0) / 2.0;
+        const double h1 = ((warp_mean[4] + warp_mean[5]) / 2.0 + (warp_mean[6] + warp_mean[7]) / 2.0) / 2.0;
+        mean[0] = (h0 + h1) / 2.0;
+    }
+    const uint32_t code_type = (mean[0] < 2.0) ? kCodeRice : kCodeRecursiveRice;
+    rr.code_type = code_type;
+
+    /* coding parameters of every partition this thread lies in (levels 0..8) or owns (9, 10) */
+    uint32_t k[9], k9[2], k10[4];
+    #pragma unroll
+    for (int l = 0; l <= 8; ++l) { k[l] = coding_parameter(mean[l], code_type, rice_threshold); }
+    k9[0] = coding_parameter(m9a, code_type, rice_threshold); k9[1] = coding_parameter(m9b, code_type, rice_threshold);
+    #pragma unroll
+    for (int f = 0; f < 4; ++f) { k10[f] = coding_parameter(m10[f], code_type, rice_threshold); }
+    {
+        unsigned long long pk = 0;
+        #pragma unroll
+        for (int l = 0; l <= 8; ++l) { pk |= (unsigned long long)k[l] << (5 * l); }
+        pk |= (unsigned long long)k9[1] << 45; pk |= (unsigned long long)k10[3] << 50;
+        kshare[tid] = pk;
+    }
+    __syncthreads();
+    const unsigned long long prev = kshare[(tid > 0) ? tid - 1 : 0];
+
+    uint32_t acc[11];
+    /* parameter fields (srla_coder.c:419-428, 445-456): 5 bits for the first partition, zig-zag delta + 1 otherwise;
+     * a partition is accounted by its first thread */
+    #pragma unroll
+    for (int l = 0; l <= 8; ++l) {
+        uint32_t bits = 0;
+        if ((tid & ((1 << (8 - l)) - 1)) == 0) {
+            const uint32_t kp = (uint32_t)(prev >> (5 * l)) & 31u;
+            bits = (tid == 0) ? 5u : (zigzag32((int32_t)k[l] - (int32_t)kp) + 1u);
+        }
+        acc[l] = bits;
+    }
+    {
+        const uint32_t kp9 = (uint32_t)(prev >> 45) & 31u, kp10 = (uint32_t)(prev >> 50) & 31u;
+        acc[9] = ((tid == 0) ? 5u : (zigzag32((int32_t)k9[0] - (int32_t)kp9) + 1u)) + zigzag32((int32_t)k9[1] - (int32_t)k9[0]) + 1u;
+        acc[10] = ((tid == 0) ? 5u : (zigzag32((int32_t)k10[0] - (int32_t)kp10) + 1u))
+                + zigzag32((int32_t)k10[1] - (int32_t)k10[0]) + zigzag32((int32_t)k10[2] - (int32_t)k10[1])
+                + zigzag32((int32_t)k10[3] - (int32_t)k10[2]) + 3u;
+    }
+    /* code bits */
+    const uint32_t fixed = (code_type == kCodeRice) ? 1u : 2u;
+    #pragma unroll
+    for (int l = 0; l <= 8; ++l) { acc[l] += (uint32_t)S * (k[l] + fixed); }
+    acc[9] += (uint32_t)(2 * NQ) * (k9[0] + k9[1] + 2u * fixed);
+    acc[10] += (uint32_t)NQ * (k10[0] + k10[1] + k10[2] + k10[3] + 4u * fixed);
+    uint32_t kmin = k[0], kmax = k[0];
+    #pragma unroll
+    for (int l = 1; l <= 8; ++l) { kmin = min(kmin, k[l]); kmax = max(kmax, k[l]); }
+    const uint32_t wmin = __reduce_min_sync(0xffffffffu, kmin), wmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (code_type == kCodeRice) {
+        for (uint32_t kk = wmin; kk <= wmax; ++kk) {
+            uint32_t s = 0;
+            #pragma unroll
+            for (int i = 0; i < S; ++i) { s += var_len<true>(v[i], kk); }
+            #pragma unroll
+            for (int l = 0; l <= 8; ++l) { acc[l] += (k[l] == kk) ? s : 0u; }
+        }
+        #pragma unroll
+        for (int i = 0; i < S; ++i) { acc[9] += var_len<true>(v[i], k9[i / (2 * NQ)]); acc[10] += var_len<true>(v[i], k10[i / NQ]); }
+    } else {
+        for (uint32_t kk = wmin; kk <= wmax; ++kk) {
+            uint32_t s = 0;
+            #pragma unroll
+            for (int i = 0; i < S; ++i) { s += var_len<false>(v[i], kk); }
+            #pragma unroll
+            for (int l = 0; l <= 8; ++l) { acc[l] += (k[l] == kk) ? s : 0u; }
+        }
+        #pragma unroll
+        for (int i = 0; i < S; ++i) { acc[9] += var_len<false>(v[i], k9[i / (2 * NQ)]); acc[10] += var_len<false>(v[i], k10[i / NQ]); }
+    }
+    #pragma unroll
+    for (int l = 0; l <= 10; ++l) { acc[l] = warp_sum_u32(acc[l]); }
+    if (lane == 0) {
+        #pragma unroll
+        for (int l = 0; l <= 10; ++l) { red32[warp * 12 + l] = acc[l]; }
+    }
+    __syncthreads();
+    uint32_t best_bits = 0xffffffffu, best = 0;
+    #pragma unroll
+    for (int l = 0; l <= 10; ++l) {
+        uint32_t bits = (uint32_t)kLog2MaxParts;
+        #pragma unroll
+        for (int w = 0; w < kWarps; ++w) { bits += red32[w * 12 + l]; }
+        if (bits < best_bits) { best_bits = bits; best = (uint32_t)l; }      /* strict: the lowest order wins ties */
+    }
+    rr.porder = best; rr.bits = best_bits + 2u;
+    if (best <= 8u) {
+        if ((tid & ((1 << (8 - best)) - 1)) == 0) {
+            uint32_t kb = k[0];
+            #pragma unroll
+            for (int l = 1; l <= 8; ++l) { if (best == (uint32_t)l) { kb = k[l]; } }
+            out->kparam[tid >> (8 - best)] = (uint8_t)kb;
+        }
+    } else if (best == 9u) {
+        out->kparam[2 * tid] = (uint8_t)k9[0]; out->kparam[2 * tid + 1] = (uint8_t)k9[1];
+    } else {
+        *reinterpret_cast<uchar4 *>(out->kparam + 4 * tid) = make_uchar4((unsigned char)k10[0], (unsigned char)k10[1], (unsigned char)k10[2], (unsigned char)k10[3]);
+    }
+    return rr;
+}
+
+/* general path: any block length (srla_coder.c:349-483) */
+__device__ RiceResult rice_search_general(const int32_t *res_s, const uint32_t n, unsigned char *scratch, uint32_t *red32,
+                                          CandOut *out, const double *rice_threshold)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    RiceResult rr; rr.porder = 0;
+    uint32_t max_porder = (uint32_t)(__ffs((int)n) - 1);
+    if (max_porder > (uint32_t)kLog2MaxParts) { max_porder = (uint32_t)kLog2MaxParts; }
+    const uint32_t nparts = 1u << max_porder, per = n >> max_porder;
+    /* heap layout: level l occupies [(1<<l)-1, (2<<l)-1).  Each slot first holds the partition's mean
+     * (double), then is overwritten by its packed parameters: bits [5j, 5j+5) = parameter of the
+     * enclosing partition at level j, for every j <= l. */
+    double *mean = reinterpret_cast<double *>(scratch);
+    unsigned long long *pack = reinterpret_cast<unsigned long long *>(mean);
+    /* finest partition means: exact integer sums / per (srla_coder.c:371-383) */
+    uint32_t any = 0;
+    if (per <= 32u) {
+        for (uint32_t q = tid; q < nparts; q += kThreads) {
+            unsigned long long s = 0;
+            const int32_t *rp = res_s + q * per;
+            for (uint32_t i = 0; i < per; ++i) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
+            mean[(nparts - 1u) + q] = (double)s / (double)per;
+        }
+    } else {
+        for (uint32_t q = warp; q < nparts; q += kWarps) {
+            unsigned long long s = 0;
+            const int32_t *rp = res_s + q * per;
+            for (uint32_t i = lane; i < per; i += 32) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
+            s = (unsigned long long)warp_sum_ll((long long)s);
+            if (lane == 0) { mean[(nparts - 1u) + q] = (double)s / (double)per; }
+        }
+    }
+    any = (uint32_t)__syncthreads_or((int)(any != 0u));
+    if (!any) { rr.code_type = kCodeAllZero; rr.bits = 2u; return rr; }
+    for (int lvl = (int)max_porder - 1; lvl >= 0; --lvl) {
+        const uint32_t cnt = 1u << lvl, base = cnt - 1u, child = 2u * cnt - 1u;
+        for (uint32_t q = tid; q < cnt; q += kThreads) { mean[base + q] = (mean[child + 2u * q] + mean[child + 2u * q + 1u]) / 2.0; }
+        __syncthreads();
+    }
+    const uint32_t code_type = (mean[0] < 2.0) ? kCodeRice : kCodeRecursiveRice;
+    rr.code_type = code_type;
+    __syncthreads();
+    /* coding parameter of every partition, top level first, packed with its ancestors' */
+    for (uint32_t lvl = 0; lvl <= max_porder; ++lvl) {
+        const uint32_t cnt = 1u << lvl, base = cnt - 1u;
+        for (uint32_t q = tid; q < cnt; q += kThreads) {
+            const uint32_t k = coding_parameter(mean[base + q], code_type, rice_threshold);
+            const unsigned long long parent = lvl ? pack[(cnt >> 1) - 1u + (q >> 1)] : 0ull;
+            pack[base + q] = parent | ((unsigned long long)(k & 31u) << (5u * lvl));
+        }
+        __syncthreads();
+    }
+    /* bits of every partition order */
+    uint32_t acc[kLog2MaxParts + 1];
+    #pragma unroll
+    for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = 0; }
+    const unsigned long long *finest = pack + (nparts - 1u);
+    if (per <= 32u) {
+        for (uint32_t q = tid; q < nparts; q += kThreads) {
+            const unsigned long long pk = finest[q];
+            const int32_t *rp = res_s + q * per;
+            for (uint32_t i = 0; i < per; ++i) {
+                const uint32_t v = zigzag32(rp[i]);
+                #pragma unroll
+                for (int l = 0; l <= kLog2MaxParts; ++l) {
+                    const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
+                    acc[l] += (code_type == kCodeRice) ? (1u + k + var_len<true>(v, k)) : (2u + k + var_len<false>(v, k));
+                }
+            }
+        }
+    } else {
+        for (uint32_t i = tid; i < n; i += kThreads) {
+            const uint32_t v = zigzag32(res_s[i]);
+            const unsigned long long pk = finest[i / per];
+            #pragma unroll
+            for (int l = 0; l <= kLog2MaxParts; ++l) {
+                const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
+                acc[l] += (code_type == kCodeRice) ? (1u + k + var_len<true>(v, k)) : (2u + k + var_len<false>(v, k));
+            }
+        }
+    }
+    /* levels above max_porder accumulated garbage (their packed fields are 0): ignored below.
+     * parameter fields: 5 bits for the first partition, zig-zag delta + 1 for the others */
+    #pragma unroll
+    for (int l = 0; l <= kLog2MaxParts; ++l) {
+        if ((uint32_t)l <= max_porder) {
+            const uint32_t cnt = 1u << l, base = cnt - 1u;
+            for (uint32_t q = tid; q < cnt; q += kThreads) {
+                const uint32_t k = (uint32_t)(pack[base + q] >> (5 * l)) & 31u;
+                const uint32_t kprev = q ? ((uint32_t)(pack[base + q - 1u] >> (5 * l)) & 31u) : 0u;
+                acc[l] += (q == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)kprev) + 1u);
+            }
+        }
+    }
+    #pragma unroll
+    for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = warp_sum_u32(acc[l]); }
+    if (lane == 0) {
+        #pragma unroll
+        for (int l = 0; l <= kLog2MaxParts; ++l) { red32[warp * 12 + l] = acc[l]; }
+    }
+    __syncthreads();
+    uint32_t best_bits = 0xffffffffu, best = 0;
+    for (uint32_t l = 0; l <= max_porder; ++l) {
+        uint32_t bits = (uint32_t)kLog2MaxParts;
+        #pragma unroll
+        for (int w = 0; w < kWarps; ++w) { bits += red32[w * 12 + l]; }
+        if (bits < best_bits) { best_bits = bits; best = l; }
+    }
+    rr.porder = best; rr.bits = best_bits + 2u;
+    for (uint32_t q = tid; q < (1u << best); q += kThreads) {
+        out->kparam[q] = (uint8_t)((pack[((1u << best) - 1u) + q] >> (5u * best)) & 31u);
+    }
+    return rr;
+}
+
+__global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const ResidLayout L = make_resid_layout(p.nmax, p.max_order);
     int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
     int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;
     int32_t  *coef_s   = reinterpret_cast<int32_t *>(smem + L.coef_off);
+    int32_t  *coef_b   = reinterpret_cast<int32_t *>(smem + L.coefb_off);
     uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
     const Job job = p.jobs[job_id];
     const StreamDev st = p.streams[job.stream];
@@ -808,44 +1120,76 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
     const uint32_t p4 = round_up_u32(order, 4);
     for (uint32_t i = tid; i < p4; i += kThreads) { coef_s[i] = (i < p4 - order) ? 0 : (int32_t)out->coef[i - (p4 - order)]; }
     __syncthreads();
+    for (uint32_t m = tid; m < (p4 >> 2); m += kThreads) {
+        coef_b[m] = (int32_t)(((uint32_t)coef_s[4u * m] & 0xffu) | (((uint32_t)coef_s[4u * m + 1u] & 0xffu) << 8)
+                            | (((uint32_t)coef_s[4u * m + 2u] & 0xffu) << 16) | (((uint32_t)coef_s[4u * m + 3u] & 0xffu) << 24));
+    }
     apply_preemphasis(region_i, sig, n, pre_coef);
     __syncthreads();
     if (ltp_period > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, ltp_period, out->ltp_coef[0], out->ltp_coef[1], out->ltp_coef[2]); }
 
     /* ---- FIR residual, int32 wrapping ---- */
     int32_t *res_s = region_i;
+    unsigned char *scratch = smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16);
     int32_t *res_g = p.residual ? p.residual + ((size_t)job_id * p.ncand + cand) * p.res_stride : nullptr;
     if (order > 0u) {
         const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
-        const uint32_t groups = (n + 3u) >> 2;
-        const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
-        for (uint32_t g = tid; g < groups; g += kThreads) {
-            const uint32_t n0 = g << 2;
-            int32_t r[4];
-            if (n0 >= p4) {
-                uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
-                const int4 *xp = reinterpret_cast<const int4 *>(sig + n0 - p4);
-                int4 w0 = xp[0];
-                for (uint32_t m = 0; m < (p4 >> 2); ++m) {
-                    const int4 w1 = xp[m + 1u];
-                    const int4 cf = coef4[m];
-                    a0 += (uint32_t)cf.x * (uint32_t)w0.x + (uint32_t)cf.y * (uint32_t)w0.y + (uint32_t)cf.z * (uint32_t)w0.z + (uint32_t)cf.w * (uint32_t)w0.w;
-                    a1 += (uint32_t)cf.x * (uint32_t)w0.y + (uint32_t)cf.y * (uint32_t)w0.z + (uint32_t)cf.z * (uint32_t)w0.w + (uint32_t)cf.w * (uint32_t)w1.x;
-                    a2 += (uint32_t)cf.x * (uint32_t)w0.z + (uint32_t)cf.y * (uint32_t)w0.w + (uint32_t)cf.z * (uint32_t)w1.x + (uint32_t)cf.w * (uint32_t)w1.y;
-                    a3 += (uint32_t)cf.x * (uint32_t)w0.w + (uint32_t)cf.y * (uint32_t)w1.x + (uint32_t)cf.z * (uint32_t)w1.y + (uint32_t)cf.w * (uint32_t)w1.z;
-                    w0 = w1;
-                }
-                r[0] = (int32_t)((uint32_t)w0.x + (uint32_t)asr32((int32_t)a0, rshift));
-                r[1] = (int32_t)((uint32_t)w0.y + (uint32_t)asr32((int32_t)a1, rshift));
-                r[2] = (int32_t)((uint32_t)w0.z + (uint32_t)asr32((int32_t)a2, rshift));
-                r[3] = (int32_t)((uint32_t)w0.w + (uint32_t)asr32((int32_t)a3, rshift));
-            } else {
-                const int32_t *cf = coef_s + (p4 - order);
-                #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint32_t i = n0 + t;
-                    int32_t v = 0;
-                    if (i < n) {
+        /* 16-bit pair entries (see the header comment) */
+        int4 *Z = reinterpret_cast<int4 *>(scratch);
+        const uint32_t zcount = round_up_u32(n, 8) >> 2;
+        int fits = 1;
+        for (uint32_t j = tid; j < zcount; j += kThreads) {
+            int32_t x[5];
+            #pragma unroll
+            for (int t = 0; t < 5; ++t) { const uint32_t i = 4u * j + (uint32_t)t; x[t] = (i < n) ? sig[i] : 0; }
+            #pragma unroll
+            for (int t = 0; t < 4; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
+            int4 z;
+            z.x = (int32_t)(((uint32_t)x[0] & 0xffffu) | ((uint32_t)x[1] << 16));
+            z.y = (int32_t)(((uint32_t)x[2] & 0xffffu) | ((uint32_t)x[3] << 16));
+            z.z = (int32_t)(((uint32_t)x[1] & 0xffffu) | ((uint32_t)x[2] << 16));
+            z.w = (int32_t)(((uint32_t)x[3] & 0xffffu) | ((uint32_t)x[4] << 16));
+            Z[zpair_slot(j)] = z;
+        }
+        fits = __syncthreads_and(fits);
+        if (fits) {
+            const uint32_t groups = (n + 7u) >> 3, nm = p4 >> 2;
+            for (uint32_t g = tid; g < groups; g += kThreads) {
+                const uint32_t n0 = g << 3;
+                if (n0 >= p4) {
+                    int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+                    const uint32_t j0 = (n0 - p4) >> 2;
+                    int4 za = Z[zpair_slot(j0)], zb = Z[zpair_slot(j0 + 1u)];
+                    for (uint32_t m = 0; m < nm; ++m) {
+                        const int4 zc = Z[zpair_slot(j0 + m + 2u)];
+                        const int32_t cf = coef_b[m];
+                        a0 = __dp2a_lo(za.x, cf, a0); a0 = __dp2a_hi(za.y, cf, a0);
+                        a1 = __dp2a_lo(za.z, cf, a1); a1 = __dp2a_hi(za.w, cf, a1);
+                        a2 = __dp2a_lo(za.y, cf, a2); a2 = __dp2a_hi(zb.x, cf, a2);
+                        a3 = __dp2a_lo(za.w, cf, a3); a3 = __dp2a_hi(zb.z, cf, a3);
+                        a4 = __dp2a_lo(zb.x, cf, a4); a4 = __dp2a_hi(zb.y, cf, a4);
+                        a5 = __dp2a_lo(zb.z, cf, a5); a5 = __dp2a_hi(zb.w, cf, a5);
+                        a6 = __dp2a_lo(zb.y, cf, a6); a6 = __dp2a_hi(zc.x, cf, a6);
+                        a7 = __dp2a_lo(zb.w, cf, a7); a7 = __dp2a_hi(zc.z, cf, a7);
+                        za = zb; zb = zc;
+                    }
+                    const int4 s0 = *reinterpret_cast<const int4 *>(sig + n0), s1 = *reinterpret_cast<const int4 *>(sig + n0 + 4u);
+                    const int4 r0 = make_int4((int32_t)((uint32_t)s0.x + (uint32_t)asr32(a0, rshift)), (int32_t)((uint32_t)s0.y + (uint32_t)asr32(a1, rshift)),
+                                              (int32_t)((uint32_t)s0.z + (uint32_t)asr32(a2, rshift)), (int32_t)((uint32_t)s0.w + (uint32_t)asr32(a3, rshift)));
+                    const int4 r1 = make_int4((int32_t)((uint32_t)s1.x + (uint32_t)asr32(a4, rshift)), (int32_t)((uint32_t)s1.y + (uint32_t)asr32(a5, rshift)),
+                                              (int32_t)((uint32_t)s1.z + (uint32_t)asr32(a6, rshift)), (int32_t)((uint32_t)s1.w + (uint32_t)asr32(a7, rshift)));
+                    *reinterpret_cast<int4 *>(res_s + n0) = r0;
+                    if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = r0; }
+                    if (n0 + 4u < n) {
+                        *reinterpret_cast<int4 *>(res_s + n0 + 4u) = r1;
+                        if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = r1; }
+                    }
+                } else {
+                    /* warm-up outputs (srla_lpc_predict.c:251-254) and the first outputs of the padded taps */
+                    const int32_t *cf = coef_s + (p4 - order);
+                    #pragma unroll 1
+                    for (uint32_t i = n0; i < n0 + 8u && i < n; ++i) {
+                        int32_t v;
                         if (i == 0u) { v = sig[0]; }
                         else if (i < order) { v = (int32_t)((uint32_t)sig[i] - (uint32_t)sig[i - 1u]); }
                         else {
@@ -853,12 +1197,55 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
                             for (uint32_t j = 0; j < order; ++j) { acc += (uint32_t)cf[j] * (uint32_t)sig[i - order + j]; }
                             v = (int32_t)((uint32_t)sig[i] + (uint32_t)asr32((int32_t)acc, rshift));
                         }
+                        res_s[i] = v;
+                        if (res_g) { res_g[i] = v; }
                     }
-                    r[t] = v;
                 }
             }
-            *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
-            if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
+        } else {
+            const uint32_t groups = (n + 3u) >> 2;
+            const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
+            for (uint32_t g = tid; g < groups; g += kThreads) {
+                const uint32_t n0 = g << 2;
+                int32_t r[4];
+                if (n0 >= p4) {
+                    uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
+                    const int4 *xp = reinterpret_cast<const int4 *>(sig + n0 - p4);
+                    int4 w0 = xp[0];
+                    for (uint32_t m = 0; m < (p4 >> 2); ++m) {
+                        const int4 w1 = xp[m + 1u];
+                        const int4 cf = coef4[m];
+                        a0 += (uint32_t)cf.x * (uint32_t)w0.x + (uint32_t)cf.y * (uint32_t)w0.y + (uint32_t)cf.z * (uint32_t)w0.z + (uint32_t)cf.w * (uint32_t)w0.w;
+                        a1 += (uint32_t)cf.x * (uint32_t)w0.y + (uint32_t)cf.y * (uint32_t)w0.z + (uint32_t)cf.z * (uint32_t)w0.w + (uint32_t)cf.w * (uint32_t)w1.x;
+                        a2 += (uint32_t)cf.x * (uint32_t)w0.z + (uint32_t)cf.y * (uint32_t)w0.w + (uint32_t)cf.z * (uint32_t)w1.x + (uint32_t)cf.w * (uint32_t)w1.y;
+                        a3 += (uint32_t)cf.x * (uint32_t)w0.w + (uint32_t)cf.y * (uint32_t)w1.x + (uint32_t)cf.z * (uint32_t)w1.y + (uint32_t)cf.w * (uint32_t)w1.z;
+                        w0 = w1;
+                    }
+                    r[0] = (int32_t)((uint32_t)w0.x + (uint32_t)asr32((int32_t)a0, rshift));
+                    r[1] = (int32_t)((uint32_t)w0.y + (uint32_t)asr32((int32_t)a1, rshift));
+                    r[2] = (int32_t)((uint32_t)w0.z + (uint32_t)asr32((int32_t)a2, rshift));
+                    r[3] = (int32_t)((uint32_t)w0.w + (uint32_t)asr32((int32_t)a3, rshift));
+                } else {
+                    const int32_t *cf = coef_s + (p4 - order);
+                    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint32_t i = n0 + t;
+                        int32_t v = 0;
+                        if (i < n) {
+                            if (i == 0u) { v = sig[0]; }
+                            else if (i < order) { v = (int32_t)((uint32_t)sig[i] - (uint32_t)sig[i - 1u]); }
+                            else {
+                                uint32_t acc = half;
+                                for (uint32_t j = 0; j < order; ++j) { acc += (uint32_t)cf[j] * (uint32_t)sig[i - order + j]; }
+                                v = (int32_t)((uint32_t)sig[i] + (uint32_t)asr32((int32_t)acc, rshift));
+                            }
+                        }
+                        r[t] = v;
+                    }
+                }
+                *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+                if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
+            }
         }
     } else {
         for (uint32_t i = tid; i < n; i += kThreads) { const int32_t v = sig[i]; res_s[i] = v; if (res_g) { res_g[i] = v; } }
@@ -866,157 +1253,19 @@ __global__ void __launch_bounds__(kThreads) residual_kernel(const __grid_constan
     __syncthreads();
 
     /* ---- residual coder search (srla_coder.c:349-483) ---- */
-    uint32_t max_porder = 0;
-    while (max_porder < (uint32_t)kLog2MaxParts && (n % (2u << max_porder)) == 0u) { max_porder++; }
-    const uint32_t nparts = 1u << max_porder, per = n >> max_porder;
-    /* heap layout: level l occupies [(1<<l)-1, (2<<l)-1).  Each slot first holds the partition's mean
-     * (double), then is overwritten by its packed parameters: bits [5j, 5j+5) = parameter of the
-     * enclosing partition at level j, for every j <= l. */
-    double *mean = reinterpret_cast<double *>(smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16));
-    unsigned long long *pack = reinterpret_cast<unsigned long long *>(mean);
-    /* finest partition means: exact integer sums / per (srla_coder.c:371-383) */
-    uint32_t any = 0;
-    if (per <= 32u) {
-        for (uint32_t q = tid; q < nparts; q += kThreads) {
-            unsigned long long s = 0;
-            const int32_t *rp = res_s + q * per;
-            if ((per & 3u) == 0u) {
-                for (uint32_t i = 0; i < per; i += 4u) {
-                    const int4 v = *reinterpret_cast<const int4 *>(rp + i);
-                    const uint32_t u0 = zigzag32(v.x), u1 = zigzag32(v.y), u2 = zigzag32(v.z), u3 = zigzag32(v.w);
-                    s += (unsigned long long)u0 + u1 + u2 + u3; any |= u0 | u1 | u2 | u3;
-                }
-            } else {
-                for (uint32_t i = 0; i < per; ++i) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
-            }
-            mean[(nparts - 1u) + q] = (double)s / (double)per;
-        }
-    } else {
-        for (uint32_t q = warp; q < nparts; q += kWarps) {
-            unsigned long long s = 0;
-            const int32_t *rp = res_s + q * per;
-            for (uint32_t i = lane; i < per; i += 32) { const uint32_t v = zigzag32(rp[i]); s += v; any |= v; }
-            s = (unsigned long long)warp_sum_ll((long long)s);
-            if (lane == 0) { mean[(nparts - 1u) + q] = (double)s / (double)per; }
-        }
+    RiceResult rr;
+    switch (n) {
+        case 1024u: rr = rice_search_fast<1>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 2048u: rr = rice_search_fast<2>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 3072u: rr = rice_search_fast<3>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 4096u: rr = rice_search_fast<4>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 8192u: rr = rice_search_fast<8>(res_s, scratch, red32, out, p.rice_threshold); break;
+        default:    rr = rice_search_general(res_s, n, scratch, red32, out, p.rice_threshold); break;
     }
-    any = (uint32_t)__syncthreads_or((int)(any != 0u));
-    uint32_t code_type, best_porder = 0, residual_bits;
-    if (!any) {
-        code_type = kCodeAllZero; residual_bits = 2u;
-    } else {
-        for (int lvl = (int)max_porder - 1; lvl >= 0; --lvl) {
-            const uint32_t cnt = 1u << lvl, base = cnt - 1u, child = 2u * cnt - 1u;
-            for (uint32_t q = tid; q < cnt; q += kThreads) { mean[base + q] = (mean[child + 2u * q] + mean[child + 2u * q + 1u]) / 2.0; }
-            __syncthreads();
-        }
-        code_type = (mean[0] < 2.0) ? kCodeRice : kCodeRecursiveRice;
-        __syncthreads();
-        /* coding parameter of every partition, top level first, packed with its ancestors' */
-        for (uint32_t lvl = 0; lvl <= max_porder; ++lvl) {
-            const uint32_t cnt = 1u << lvl, base = cnt - 1u;
-            for (uint32_t q = tid; q < cnt; q += kThreads) {
-                const double m = mean[base + q];
-                uint32_t k;
-                if (code_type == kCodeRice) {
-                    k = 0;
-                    #pragma unroll 1
-                    for (int j = 1; j < 32; ++j) { if (m >= __ldg(p.rice_threshold + j)) { k = (uint32_t)j; } }   /* srla_coder.c:262-287 via host-libm thresholds */
-                } else {
-                    const double g = 0.66794162356 * (1.0 + m);                                                 /* srla_coder.c:298-324 */
-                    const uint32_t golomb = (uint32_t)((1.0 > g) ? 1.0 : g);
-                    k = 31u - (uint32_t)__clz((int)golomb);
-                }
-                const unsigned long long parent = lvl ? pack[(cnt >> 1) - 1u + (q >> 1)] : 0ull;
-                pack[base + q] = parent | ((unsigned long long)(k & 31u) << (5u * lvl));
-            }
-            __syncthreads();
-        }
-        /* bits of every partition order: each thread walks whole finest partitions */
-        uint32_t acc[kLog2MaxParts + 1];
-        #pragma unroll
-        for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = 0; }
-        const unsigned long long *finest = pack + (nparts - 1u);
-        if (per <= 32u) {
-            for (uint32_t q = tid; q < nparts; q += kThreads) {
-                const unsigned long long pk = finest[q];
-                const int32_t *rp = res_s + q * per;
-                if ((per & 3u) == 0u) {
-                    for (uint32_t i0 = 0; i0 < per; i0 += 4u) {
-                        const int4 t = *reinterpret_cast<const int4 *>(rp + i0);
-                        const uint32_t v0 = zigzag32(t.x), v1 = zigzag32(t.y), v2 = zigzag32(t.z), v3 = zigzag32(t.w);
-                        #pragma unroll
-                        for (int l = 0; l <= kLog2MaxParts; ++l) {
-                            const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
-                            if (code_type == kCodeRice) {
-                                acc[l] += 4u * (1u + k) + (v0 >> k) + (v1 >> k) + (v2 >> k) + (v3 >> k);
-                            } else {
-                                const int32_t pivot = (int32_t)(2u << k);
-                                acc[l] += 4u * (k + 2u)
-                                        + ((uint32_t)max((int32_t)v0 - pivot, 0) >> k) + ((uint32_t)max((int32_t)v1 - pivot, 0) >> k)
-                                        + ((uint32_t)max((int32_t)v2 - pivot, 0) >> k) + ((uint32_t)max((int32_t)v3 - pivot, 0) >> k);
-                            }
-                        }
-                    }
-                } else {
-                    for (uint32_t i = 0; i < per; ++i) {
-                        const uint32_t v = zigzag32(rp[i]);
-                        #pragma unroll
-                        for (int l = 0; l <= kLog2MaxParts; ++l) {
-                            const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
-                            if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
-                            else { acc[l] += (k + 2u) + ((uint32_t)max((int32_t)v - (int32_t)(2u << k), 0) >> k); }
-                        }
-                    }
-                }
-            }
-        } else {
-            for (uint32_t i = tid; i < n; i += kThreads) {
-                const uint32_t v = zigzag32(res_s[i]);
-                const unsigned long long pk = finest[i / per];
-                #pragma unroll
-                for (int l = 0; l <= kLog2MaxParts; ++l) {
-                    const uint32_t k = (uint32_t)(pk >> (5 * l)) & 31u;
-                    if (code_type == kCodeRice) { acc[l] += 1u + k + (v >> k); }
-                    else { acc[l] += (k + 2u) + ((uint32_t)max((int32_t)v - (int32_t)(2u << k), 0) >> k); }
-                }
-            }
-        }
-        /* levels above max_porder accumulated garbage (their packed fields are 0): ignored below.
-         * parameter fields: 5 bits for the first partition, zig-zag delta + 1 for the others */
-        #pragma unroll
-        for (int l = 0; l <= kLog2MaxParts; ++l) {
-            if ((uint32_t)l <= max_porder) {
-                const uint32_t cnt = 1u << l, base = cnt - 1u;
-                for (uint32_t q = tid; q < cnt; q += kThreads) {
-                    const uint32_t k = (uint32_t)(pack[base + q] >> (5 * l)) & 31u;
-                    const uint32_t kprev = q ? ((uint32_t)(pack[base + q - 1u] >> (5 * l)) & 31u) : 0u;
-                    acc[l] += (q == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)kprev) + 1u);
-                }
-            }
-        }
-        #pragma unroll
-        for (int l = 0; l <= kLog2MaxParts; ++l) { acc[l] = warp_sum_u32(acc[l]); }
-        if (lane == 0) {
-            #pragma unroll
-            for (int l = 0; l <= kLog2MaxParts; ++l) { red32[warp * 12 + l] = acc[l]; }
-        }
-        __syncthreads();
-        uint32_t best_bits = 0xffffffffu;
-        for (uint32_t l = 0; l <= max_porder; ++l) {
-            uint32_t bits = (uint32_t)kLog2MaxParts;
-            #pragma unroll
-            for (int w = 0; w < kWarps; ++w) { bits += red32[w * 12 + l]; }
-            if (bits < best_bits) { best_bits = bits; best_porder = l; }
-        }
-        residual_bits = best_bits + 2u;
-        for (uint32_t q = tid; q < (1u << best_porder); q += kThreads) {
-            out->kparam[q] = (uint8_t)((pack[((1u << best_porder) - 1u) + q] >> (5u * best_porder)) & 31u);
-        }
-    }
+    const uint32_t code_type = rr.code_type, best_porder = rr.porder, residual_bits = rr.bits;
 
     /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */
-    if (warp == 0) {
+    if (tid < 32) {
         uint32_t plain_bits = 0, sum_bits = 0, bad = 0;
         const int32_t *cf = coef_s + (p4 - order);
         for (uint32_t i = lane; i < order; i += 32) {

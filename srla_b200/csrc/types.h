@@ -162,11 +162,12 @@ SRLA_HD inline LpcLayout make_lpc_layout(uint32_t P)
     return L;
 }
 
-/* residual_kernel: signal, residual + mean pyramid, coefficients, parameter table */
+/* residual_kernel: signal, residual + (packed 16-bit sample pairs of the FIR | mean pyramid), coefficients */
 struct ResidLayout {
-    uint32_t region_off, region_bytes; /* int32 residual[n4] then the mean pyramid (doubles)   */
+    uint32_t region_off, region_bytes; /* int32 residual[n4], then the FIR's packed pairs, later the mean pyramid (doubles) */
     uint32_t sig_off;
     uint32_t coef_off;                 /* int32 x (roundup4(P) + 4)                            */
+    uint32_t coefb_off;                /* the same coefficients as int8 x 4 words              */
     uint32_t red_off;                  /* 1024 bytes of reduction scratch                      */
     uint32_t total;
 };
@@ -175,12 +176,16 @@ SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
     ResidLayout L;
     const uint32_t n4 = round_up_u32(nmax, 4);
     const uint32_t parts = (nmax < (uint32_t)kMaxParts) ? nmax : (uint32_t)kMaxParts;
+    const uint32_t pyramid = 16u * round_up_u32(parts, 2) + 16u;
+    const uint32_t pairs = 4u * round_up_u32(nmax, 8) + 32u;      /* one 16-byte entry per 4 samples */
+    const uint32_t scratch = (pyramid > pairs) ? pyramid : pairs;
     uint32_t off = 0;
     L.region_off = off;
-    L.region_bytes = round_up_u32(4u * n4 + 16u * round_up_u32(parts, 2) + 16u, 16);
+    L.region_bytes = round_up_u32(4u * n4 + (scratch > 4096u ? scratch : 4096u), 16);
     off += L.region_bytes;
     L.sig_off = off; off += 4u * (n4 + 8u);
     L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
+    L.coefb_off = off; off += 4u * (round_up_u32(P, 4) / 4u + 4u);
     L.red_off = off; off += 1024u;
     L.total = off;
     return L;
