@@ -30,23 +30,26 @@ constexpr double kPi = 3.14159265358979323846;   /* fft.c:17 */
 struct Cx { double re, im; };
 static inline Cx cmul(Cx a, Cx b) { Cx r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
 
-/* forward (flag = -1) twiddles {w1,w2,w3} for every stage size 4..max_n (powers of two).
- * off[lg] = offset (in Cx units) of the table for stage size 2^lg; each has 3 * 2^lg / 4 entries. */
+/* forward (flag = -1) twiddles for every stage size 4..max_n (powers of two), one structure-of-arrays
+ * table per stage size 2^lg at off[lg] (in Cx units): w1[0..n/4), w2[0..n/4), w3[0..n/4) -- consecutive
+ * butterflies of a warp read consecutive 16-byte entries. */
 static inline void build_complex_twiddles(int max_lg, std::vector<Cx> &tab, std::vector<uint32_t> &off)
 {
     off.assign(32, 0);
     tab.clear();
     for (int lg = 2; lg <= max_lg; lg++) {
-        const int n = 1 << lg;
+        const int n = 1 << lg, quarter = n / 4;
         const double theta = 2.0 * kPi / n;
         const int flag = -1;
         Cx step; step.re = std::cos(theta); step.im = flag * std::sin(theta);
         Cx w; w.re = 1.0; w.im = 0.0;
         off[lg] = (uint32_t)tab.size();
-        for (int p = 0; p < n / 4; p++) {
+        tab.resize(tab.size() + 3 * (size_t)quarter);
+        Cx *t = tab.data() + off[lg];
+        for (int p = 0; p < quarter; p++) {
             const Cx w2 = cmul(w, w);
             const Cx w3 = cmul(w, w2);
-            tab.push_back(w); tab.push_back(w2); tab.push_back(w3);
+            t[p] = w; t[quarter + p] = w2; t[2 * quarter + p] = w3;
             w = cmul(w, step);
         }
     }

@@ -142,10 +142,11 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ uint32_t fft_slot(uint32_t i) { return i ^ ((i >> 4) & 7u); }
 
 struct Twiddle3 { double2 w1, w2, w3; };
-__device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t p, bool inverse)
+/* table of one stage size ns: w1[ns/4], w2[ns/4], w3[ns/4] (host_tables.h) */
+__device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t quarter, uint32_t p, bool inverse)
 {
     Twiddle3 t;
-    t.w1 = __ldg(table + 3u * p); t.w2 = __ldg(table + 3u * p + 1u); t.w3 = __ldg(table + 3u * p + 2u);
+    t.w1 = __ldg(table + p); t.w2 = __ldg(table + quarter + p); t.w3 = __ldg(table + 2u * quarter + p);
     if (inverse) { t.w1.y = -t.w1.y; t.w2.y = -t.w2.y; t.w3.y = -t.w3.y; }      /* the recurrence is sign-symmetric */
     return t;
 }
@@ -164,8 +165,11 @@ __device__ __forceinline__ void butterfly4(const double2 a, const double2 b, con
     y3 = cmul(w.w3, cadd(amc, jbmd));
 }
 
-/* complex FFT of M points (M a power of two, M/16 <= blockDim.x, M/8 <= blockDim.x when M = 8 * 4^k) */
-__device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inverse, const LaunchParams &p)
+/* complex FFT of M points (M a power of two, M/16 <= blockDim.x, M/8 <= blockDim.x when M = 8 * 4^k).
+ * `need`: only outputs 0..need-1 are required (M = all).  The autocorrelation reads just the first lags
+ * of the inverse transform, so its last two passes skip every butterfly none of whose outputs can reach
+ * them -- the surviving outputs are the reference's expression trees unchanged. */
+__device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inverse, const LaunchParams &p, const uint32_t need)
 {
     const uint32_t tid = threadIdx.x;
     uint32_t nn = M, lgs = 0;
@@ -173,6 +177,7 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
     while (nn >= 16u) {
         const uint32_t units = M >> 4;
         const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
+        const bool last_pair = (nn < 256u);          /* outputs feed the tail pass (or are final) */
         double2 v[4][4];
         if (tid < units) {
             #pragma unroll
@@ -189,19 +194,39 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
             double2 y[4][4];
             #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {
-                const Twiddle3 w = load_twiddle(tw_a, p0 + (uint32_t)jp * (nn >> 4), inverse);
+                const Twiddle3 w = load_twiddle(tw_a, nn >> 2, p0 + (uint32_t)jp * (nn >> 4), inverse);
                 butterfly4(v[jp][0], v[jp][1], v[jp][2], v[jp][3], w, inverse, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
             }
-            const Twiddle3 w = load_twiddle(tw_b, p0, inverse);
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double2 z0, z1, z2, z3;
-                butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], w, inverse, z0, z1, z2, z3);
-                const uint32_t o = q + ((uint32_t)j << lgs) + ((16u * p0) << lgs);
-                x[fft_slot(o)]                = z0;
-                x[fft_slot(o + (4u << lgs))]  = z1;
-                x[fft_slot(o + (8u << lgs))]  = z2;
-                x[fft_slot(o + (12u << lgs))] = z3;
+            if (!last_pair || need >= M) {
+                const Twiddle3 w = load_twiddle(tw_b, nn >> 4, p0, inverse);
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double2 z0, z1, z2, z3;
+                    butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], w, inverse, z0, z1, z2, z3);
+                    const uint32_t o = q + ((uint32_t)j << lgs) + ((16u * p0) << lgs);
+                    x[fft_slot(o)]                = z0;
+                    x[fft_slot(o + (4u << lgs))]  = z1;
+                    x[fft_slot(o + (8u << lgs))]  = z2;
+                    x[fft_slot(o + (12u << lgs))] = z3;
+                }
+            } else {
+                /* an output at position o is read later only when (o mod (16 << lgs)) < need */
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t low = q + ((uint32_t)j << lgs);
+                    const uint32_t o = low + ((16u * p0) << lgs);
+                    if (low + (4u << lgs) < need) {
+                        const Twiddle3 w = load_twiddle(tw_b, nn >> 4, p0, inverse);
+                        double2 z0, z1, z2, z3;
+                        butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], w, inverse, z0, z1, z2, z3);
+                        x[fft_slot(o)]                = z0;
+                        x[fft_slot(o + (4u << lgs))]  = z1;
+                        x[fft_slot(o + (8u << lgs))]  = z2;
+                        x[fft_slot(o + (12u << lgs))] = z3;
+                    } else if (low < need) {
+                        x[fft_slot(o)] = cadd(cadd(y[0][j], y[2][j]), cadd(y[1][j], y[3][j]));     /* y0 of butterfly4 */
+                    }
+                }
             }
         }
         __syncthreads();
@@ -212,11 +237,12 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
     if (nn == 8u) {
         /* radix-4 stage of size 8 (s = M/8) fused with the final radix-2 stage (fft.c:114-123) */
         const uint32_t s = M >> 3;
+        const uint32_t live = (need < s) ? need : s;
         double2 v[2][2][4];
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
-            if (u < s) {
+            if (u < live) {
                 #pragma unroll
                 for (int pp = 0; pp < 2; ++pp) {
                     #pragma unroll
@@ -229,11 +255,11 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
-            if (u < s) {
+            if (u < live) {
                 double2 y[2][4];
-                { const Twiddle3 w0 = load_twiddle(tw, 0u, inverse);
+                { const Twiddle3 w0 = load_twiddle(tw, 2u, 0u, inverse);
                   butterfly4(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, inverse, y[0][0], y[0][1], y[0][2], y[0][3]); }
-                { const Twiddle3 w1 = load_twiddle(tw, 1u, inverse);
+                { const Twiddle3 w1 = load_twiddle(tw, 2u, 1u, inverse);
                   butterfly4(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, inverse, y[1][0], y[1][1], y[1][2], y[1][3]); }
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -246,21 +272,22 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
     } else if (nn == 4u) {
         /* single radix-4 stage of size 4 (s = M/4): twiddle index 0 only */
         const uint32_t s = M >> 2;
+        const uint32_t live = (need < s) ? need : s;
         double2 v[2][4];
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
-            if (u < s) {
+            if (u < live) {
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) { v[r][j] = x[fft_slot(u + (uint32_t)j * s)]; }
             }
         }
         __syncthreads();
-        const Twiddle3 w = load_twiddle(p.tw_complex + p.tw_complex_off[2], 0u, inverse);
+        const Twiddle3 w = load_twiddle(p.tw_complex + p.tw_complex_off[2], 1u, 0u, inverse);
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
-            if (u < s) {
+            if (u < live) {
                 double2 y0, y1, y2, y3;
                 butterfly4(v[r][0], v[r][1], v[r][2], v[r][3], w, inverse, y0, y1, y2, y3);
                 x[fft_slot(u)] = y0; x[fft_slot(u + s)] = y1; x[fft_slot(u + 2u * s)] = y2; x[fft_slot(u + 3u * s)] = y3;
@@ -269,35 +296,48 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
         __syncthreads();
     } else if (nn == 2u) {
         const uint32_t s = M >> 1;
+        const uint32_t live = (need < s) ? need : s;
         double2 v[2][2];
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
-            if (u < s) { v[r][0] = x[fft_slot(u)]; v[r][1] = x[fft_slot(u + s)]; }
+            if (u < live) { v[r][0] = x[fft_slot(u)]; v[r][1] = x[fft_slot(u + s)]; }
         }
         __syncthreads();
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
-            if (u < s) { x[fft_slot(u)] = cadd(v[r][0], v[r][1]); x[fft_slot(u + s)] = csub(v[r][0], v[r][1]); }
+            if (u < live) { x[fft_slot(u)] = cadd(v[r][0], v[r][1]); x[fft_slot(u + s)] = csub(v[r][0], v[r][1]); }
         }
         __syncthreads();
     }
 }
 
+/* exact int32 -> double without the quarter-rate I2F.F64: 2^52 + 2^31 + x is representable */
+__device__ __forceinline__ double int_to_double(int32_t x)
+{
+    return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
+}
+
 /* Welch window (lpc.c:252-266) + autocorrelation through the FFT (lpc.c:330-376).
- * sig[n] int32 in shared memory -> lags[0..nlags) (lags >= N read as 0.0).  buf: N doubles. */
-__device__ void welch_autocorr(const int32_t *sig, const uint32_t n, double *buf, double *lags, const uint32_t nlags,
+ * sig[n] int32 in shared memory -> lags[0..nlags) (lags >= N read as 0.0).  buf: N doubles.
+ * kPre: sig holds the UNFILTERED candidate and the pre-emphasis (srla_utility.c:342-358) is applied
+ * on the fly with coefficient pre_coef. */
+template <bool kPre>
+__device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const uint32_t n, double *buf, double *lags, const uint32_t nlags,
                                const Job &job, const LaunchParams &p)
 {
     const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t N = ceil_pow2_u32(n);
     const double unit = p.unit, div = job.welch_div;
     double2 *cx = reinterpret_cast<double2 *>(buf);
+    const uint32_t pc = (uint32_t)pre_coef;
     if (N < 2u) {
         if (tid == 0) {
             const double w = div * 0.0 * (double)(n - 1u);
-            buf[0] = ((double)sig[0] * unit) * w;
+            int32_t x = sig[0];
+            if (kPre) { x = (int32_t)((uint32_t)x - (uint32_t)((int32_t)((uint32_t)x * pc) >> 4)); }    /* filter memory = first sample */
+            buf[0] = ((double)x * unit) * w;
         }
         __syncthreads();
         for (uint32_t i = tid; i < nlags; i += nthreads) { lags[i] = (i < N) ? buf[i] * job.ac_scale : 0.0; }
@@ -305,23 +345,71 @@ __device__ void welch_autocorr(const int32_t *sig, const uint32_t n, double *buf
         return;
     }
     const uint32_t M = N >> 1;
-    for (uint32_t c = tid; c < M; c += nthreads) {
-        double v[2];
-        #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const uint32_t i = 2u * c + (uint32_t)t;
-            double r = 0.0;
-            if (i < n) {
-                const uint32_t s = (i < (n >> 1)) ? i : (n - 1u - i);
-                const double w = div * (double)s * (double)(n - 1u - s);
-                r = ((double)sig[i] * unit) * w;
+    if (N < 4u) {
+        for (uint32_t c = tid; c < M; c += nthreads) {
+            double v[2];
+            #pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t i = 2u * c + (uint32_t)t;
+                double r = 0.0;
+                if (i < n) {
+                    const uint32_t s = (i < (n >> 1)) ? i : (n - 1u - i);
+                    const double w = div * (double)s * (double)(n - 1u - s);
+                    int32_t x = sig[i];
+                    if (kPre) { x = (int32_t)((uint32_t)x - (uint32_t)((int32_t)((uint32_t)sig[i ? i - 1u : 0u] * pc) >> 4)); }
+                    r = ((double)x * unit) * w;
+                }
+                v[t] = r;
             }
-            v[t] = r;
+            cx[fft_slot(c)] = make_double2(v[0], v[1]);
         }
-        cx[fft_slot(c)] = make_double2(v[0], v[1]);
+    } else {
+        const uint32_t half_n = n >> 1;
+        const double dn1 = (double)(int32_t)(n - 1u);
+        for (uint32_t g = tid; g < (N >> 2); g += nthreads) {
+            const uint32_t i0 = 4u * g;
+            double v[4];
+            if (i0 + 4u <= n && (i0 + 4u <= half_n || i0 >= half_n)) {
+                /* four samples of one window half: weights from exact double increments instead of conversions */
+                const int4 q = *reinterpret_cast<const int4 *>(sig + i0);
+                int32_t x[4] = { q.x, q.y, q.z, q.w };
+                if (kPre) {
+                    const int32_t prv = sig[i0 ? i0 - 1u : 0u];
+                    x[3] = (int32_t)((uint32_t)q.w - (uint32_t)((int32_t)((uint32_t)q.z * pc) >> 4));
+                    x[2] = (int32_t)((uint32_t)q.z - (uint32_t)((int32_t)((uint32_t)q.y * pc) >> 4));
+                    x[1] = (int32_t)((uint32_t)q.y - (uint32_t)((int32_t)((uint32_t)q.x * pc) >> 4));
+                    x[0] = (int32_t)((uint32_t)q.x - (uint32_t)((int32_t)((uint32_t)prv * pc) >> 4));
+                }
+                const bool first = (i0 < half_n);
+                const double s0 = first ? (double)(int32_t)i0 : (double)(int32_t)(n - 1u - i0);
+                const double inc = first ? 1.0 : -1.0;
+                #pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double ds = s0 + inc * (double)t;                 /* exact: small integers */
+                    const double w = div * ds * (dn1 - ds);
+                    v[t] = (int_to_double(x[t]) * unit) * w;
+                }
+            } else {
+                #pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t i = i0 + (uint32_t)t;
+                    double r = 0.0;
+                    if (i < n) {
+                        const uint32_t s = (i < half_n) ? i : (n - 1u - i);
+                        const double w = div * (double)s * (double)(n - 1u - s);
+                        int32_t x = sig[i];
+                        if (kPre) { x = (int32_t)((uint32_t)x - (uint32_t)((int32_t)((uint32_t)sig[i ? i - 1u : 0u] * pc) >> 4)); }
+                        r = ((double)x * unit) * w;
+                    }
+                    v[t] = r;
+                }
+            }
+            cx[fft_slot(2u * g)] = make_double2(v[0], v[1]);
+            cx[fft_slot(2u * g + 1u)] = make_double2(v[2], v[3]);
+        }
     }
     __syncthreads();
-    complex_fft_inplace(cx, M, false, p);
+    complex_fft_inplace(cx, M, false, p, M);
     /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three
      * only touch the element pair (i, N/2 - i) */
     {
@@ -374,7 +462,10 @@ __device__ void welch_autocorr(const int32_t *sig, const uint32_t n, double *buf
         }
         __syncthreads();
     }
-    complex_fft_inplace(cx, M, true, p);
+    {
+        const uint32_t want = (nlags < N) ? nlags : N;
+        complex_fft_inplace(cx, M, true, p, (want + 1u) >> 1);
+    }
     const double scale = job.ac_scale;
     for (uint32_t i = tid; i < nlags; i += nthreads) {
         double v = 0.0;
@@ -523,12 +614,23 @@ __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &jo
  * plus the zero padding the FIR's vector loads may touch */
 __device__ __forceinline__ void apply_preemphasis(const int32_t *raw, int32_t *sig, uint32_t n, int32_t pre_coef)
 {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t c = (uint32_t)pre_coef, nquad = n >> 2;
+    for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
+        const int4 q = *reinterpret_cast<const int4 *>(raw + 4u * g);
+        const int32_t prv = raw[g ? 4u * g - 1u : 0u];
+        int4 o;
+        o.x = (int32_t)((uint32_t)q.x - (uint32_t)((int32_t)((uint32_t)prv * c) >> 4));
+        o.y = (int32_t)((uint32_t)q.y - (uint32_t)((int32_t)((uint32_t)q.x * c) >> 4));
+        o.z = (int32_t)((uint32_t)q.z - (uint32_t)((int32_t)((uint32_t)q.y * c) >> 4));
+        o.w = (int32_t)((uint32_t)q.w - (uint32_t)((int32_t)((uint32_t)q.z * c) >> 4));
+        *reinterpret_cast<int4 *>(sig + 4u * g) = o;
+    }
+    for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += blockDim.x) {
         const int32_t cur = raw[i], prv = raw[(i == 0u) ? 0u : i - 1u];
-        sig[i] = (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)pre_coef) >> 4));
+        sig[i] = (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * c) >> 4));
     }
     if (threadIdx.x < 4) { sig[-1 - (int)threadIdx.x] = 0; }
-    for (uint32_t i = n + threadIdx.x; i < round_up_u32(n, 4) + 4u; i += blockDim.x) { sig[i] = 0; }
+    for (uint32_t i = n + threadIdx.x; i < round_up_u32(n, 4) + 12u; i += blockDim.x) { sig[i] = 0; }
 }
 
 /* long-term prediction residual replaces the signal (srla_lpc_predict.c:267-294); tmp: n int32 */
@@ -556,8 +658,61 @@ __device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n
  * front_kernel: one CTA per (job, candidate).  Pre-emphasis decision, optional LTP analysis, and
  * the Welch-windowed FFT autocorrelation of the signal the LPC stage sees; lags 0..P go to HBM.
  * ---------------------------------------------------------------------------------------------- */
+/* pre-emphasis coefficient (srla_utility.c:214-257) from the candidate samples raw[0..n): r0, r1 as exact
+ * integers.  Every thread returns the coefficient; thread 0 also records it. */
 template <int kT>
-__global__ void __launch_bounds__(kT, (kT <= 128) ? 4 : 2) front_kernel(const __grid_constant__ LaunchParams p)
+__device__ __forceinline__ int32_t preemphasis_coefficient(const int32_t *raw, const uint32_t n, CandOut *out,
+                                                           unsigned long long *red64, int32_t *sh_coef)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long r0 = 0, r1 = 0;
+    const uint32_t nquad = n >> 2;
+    for (uint32_t g = tid; g < nquad; g += kT) {
+        const int4 q = *reinterpret_cast<const int4 *>(raw + 4u * g);
+        const long long a = q.x, b = q.y, c = q.z, d = q.w;
+        r0 += a * a + b * b + c * c + d * d;
+        r1 += a * b + b * c + c * d;
+        if (4u * g + 4u < n) { r1 += d * (long long)raw[4u * g + 4u]; }
+    }
+    for (uint32_t i = 4u * nquad + tid; i < n; i += kT) {
+        const long long a = raw[i];
+        r0 += a * a;
+        if (i + 1u < n) { r1 += a * (long long)raw[i + 1u]; }
+    }
+    r0 = warp_sum_ll(r0); r1 = warp_sum_ll(r1);
+    if (lane == 0) { red64[2 * warp] = (unsigned long long)r0; red64[2 * warp + 1] = (unsigned long long)r1; }
+    __syncthreads();
+    if (tid == 0) {
+        long long s0 = 0, s1 = 0;
+        for (int w = 0; w < kT / 32; ++w) { s0 += (long long)red64[2 * w]; s1 += (long long)red64[2 * w + 1]; }
+        int32_t c = 0;
+        if (s0 != 0) {
+            double v = ((double)s1 / (double)s0) * 16.0;
+            if (s0 >= (1ll << 53)) {
+                /* the reference's sequential double sums round above 2^53 (relative error
+                 * <= n * 2^-53 each); only a value this close to a rounding boundary can differ */
+                const double frac = fabs(v) - floor(fabs(v));
+                if (fabs(frac - 0.5) < 1e-7) {
+                    double q0 = 0.0, q1 = 0.0;
+                    for (uint32_t i = 0; i + 1u < n; ++i) { const double a = raw[i], b = raw[i + 1u]; q0 += a * a; q1 += a * b; }
+                    { const double a = raw[n - 1u]; q0 += a * a; }
+                    v = (q1 / q0) * 16.0;
+                }
+            }
+            c = (int32_t)round_half_away(v);
+            if (c < -16) { c = -16; }
+            if (c > 15) { c = 15; }
+        }
+        *sh_coef = c;
+        out->pre_coef = c; out->pre_prev = raw[0];
+    }
+    __syncthreads();
+    return *sh_coef;
+}
+
+/* kOcc: resident CTAs per SM the register allocation is sized for */
+template <int kT, int kOcc>
+__global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FrontLayout L = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
@@ -569,7 +724,7 @@ __global__ void __launch_bounds__(kT, (kT <= 128) ? 4 : 2) front_kernel(const __
     __shared__ int32_t  sh_i[8];
     __shared__ uint32_t sh_u[8];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
     const Job &job = p.jobs[job_id];
     const StreamDev &st = p.streams[job.stream];
@@ -577,7 +732,10 @@ __global__ void __launch_bounds__(kT, (kT <= 128) ? 4 : 2) front_kernel(const __
     const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
     CandOut *out = p.cand + (size_t)job_id * p.ncand + cand;
 
-    int nz = load_candidate(st, job, p, cand, lshift, region_i);
+    /* without LTP the candidate goes straight into the signal buffer and the pre-emphasis is folded into
+     * the window pass; with LTP the filtered signal itself is needed in shared memory */
+    int32_t *raw = (p.ltp_order > 0u) ? region_i : sig;
+    int nz = load_candidate(st, job, p, cand, lshift, raw);
     nz = __syncthreads_or(nz);
     if (tid == 0) {
         out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
@@ -586,69 +744,31 @@ __global__ void __launch_bounds__(kT, (kT <= 128) ? 4 : 2) front_kernel(const __
     }
     if (n <= P) { return; }                          /* RAW block (srla_encoder.c:777-779): nothing to analyse */
 
-    /* ---- pre-emphasis coefficient (srla_utility.c:214-257): r0, r1 as exact integers ---- */
-    {
-        long long r0 = 0, r1 = 0;
-        for (uint32_t i = tid; i < n; i += blockDim.x) {
-            const long long a = region_i[i];
-            r0 += a * a;
-            if (i + 1u < n) { r1 += a * (long long)region_i[i + 1u]; }
-        }
-        r0 = warp_sum_ll(r0); r1 = warp_sum_ll(r1);
-        if (lane == 0) { red64[2 * warp] = (unsigned long long)r0; red64[2 * warp + 1] = (unsigned long long)r1; }
-        __syncthreads();
-        if (tid == 0) {
-            long long s0 = 0, s1 = 0;
-            for (int w = 0; w < kT / 32; ++w) { s0 += (long long)red64[2 * w]; s1 += (long long)red64[2 * w + 1]; }
-            int32_t c = 0;
-            if (s0 != 0) {
-                double v = ((double)s1 / (double)s0) * 16.0;
-                if (s0 >= (1ll << 53)) {
-                    /* the reference's sequential double sums round above 2^53 (relative error
-                     * <= n * 2^-53 each); only a value this close to a rounding boundary can differ */
-                    const double frac = fabs(v) - floor(fabs(v));
-                    if (fabs(frac - 0.5) < 1e-7) {
-                        double q0 = 0.0, q1 = 0.0;
-                        for (uint32_t i = 0; i + 1u < n; ++i) { const double a = region_i[i], b = region_i[i + 1u]; q0 += a * a; q1 += a * b; }
-                        { const double a = region_i[n - 1u]; q0 += a * a; }
-                        v = (q1 / q0) * 16.0;
-                    }
-                }
-                c = (int32_t)round_half_away(v);
-                if (c < -16) { c = -16; }
-                if (c > 15) { c = 15; }
-            }
-            sh_i[0] = c;
-            out->pre_coef = c; out->pre_prev = region_i[0];
-        }
-        __syncthreads();
+    const int32_t pre_coef = preemphasis_coefficient<kT>(raw, n, out, red64, &sh_i[0]);
+    double *g = p.lags + ((size_t)job_id * p.ncand + cand) * p.lag_stride;
+    if (p.ltp_order == 0u) {
+        /* ---- autocorrelation of the signal the LPC stage sees (lpc.c:444-483) ---- */
+        if (P > 0u) { welch_autocorr<true>(raw, pre_coef, n, region_d, g, P + 1u, job, p); }
+        return;
     }
-    const int32_t pre_coef = sh_i[0];
     apply_preemphasis(region_i, sig, n, pre_coef);
     __syncthreads();
 
     /* ---- long-term prediction (srla_encoder.c:1008-1058) ---- */
-    if (p.ltp_order > 0u) {
-        welch_autocorr(sig, n, region_d, lags, kLtpLags, job, p);
-        if (tid == 0) {
-            /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
-            for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
-            uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
-            const int rc = ltp_solve(lags, p.ltp_order, &period, q);
-            sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
-            out->status = (uint32_t)rc;
-            if (!rc && period > 0u) { out->ltp_period = period; out->ltp_coef[0] = q[0]; out->ltp_coef[1] = q[1]; out->ltp_coef[2] = q[2]; }
-        }
-        __syncthreads();
-        if (sh_u[1]) { return; }
-        if (sh_u[0] > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
+    welch_autocorr<false>(sig, 0, n, region_d, lags, kLtpLags, job, p);
+    if (tid == 0) {
+        /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
+        for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
+        uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
+        const int rc = ltp_solve(lags, p.ltp_order, &period, q);
+        sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
+        out->status = (uint32_t)rc;
+        if (!rc && period > 0u) { out->ltp_period = period; out->ltp_coef[0] = q[0]; out->ltp_coef[1] = q[1]; out->ltp_coef[2] = q[2]; }
     }
-
-    /* ---- autocorrelation of the signal the LPC stage sees (lpc.c:444-483) ---- */
-    if (P > 0u) {
-        double *g = p.lags + ((size_t)job_id * p.ncand + cand) * p.lag_stride;
-        welch_autocorr(sig, n, region_d, g, P + 1u, job, p);
-    }
+    __syncthreads();
+    if (sh_u[1]) { return; }
+    if (sh_u[0] > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
+    if (P > 0u) { welch_autocorr<false>(sig, 0, n, region_d, g, P + 1u, job, p); }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -949,20 +1069,26 @@ __device__ __forceinline__ RiceResult rice_search_fast(const int32_t *res_s, uns
         for (int i = 0; i < S; ++i) { acc[9] += var_len<false>(v[i], k9[i / (2 * NQ)]); acc[10] += var_len<false>(v[i], k10[i / NQ]); }
     }
     #pragma unroll
-    for (int l = 0; l <= 10; ++l) { acc[l] = warp_sum_u32(acc[l]); }
+    for (int l = 0; l <= 10; ++l) { acc[l] = __reduce_add_sync(0xffffffffu, acc[l]); }
     if (lane == 0) {
         #pragma unroll
         for (int l = 0; l <= 10; ++l) { red32[warp * 12 + l] = acc[l]; }
     }
     __syncthreads();
-    uint32_t best_bits = 0xffffffffu, best = 0;
-    #pragma unroll
-    for (int l = 0; l <= 10; ++l) {
-        uint32_t bits = (uint32_t)kLog2MaxParts;
-        #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { bits += red32[w * 12 + l]; }
-        if (bits < best_bits) { best_bits = bits; best = (uint32_t)l; }      /* strict: the lowest order wins ties */
+    if (warp == 0) {
+        /* lane l totals partition order l; first minimum (srla_coder.c:434, 463: strict <, lowest order wins ties) */
+        uint32_t bits = 0xffffffffu;
+        if (lane <= 10) {
+            bits = (uint32_t)kLog2MaxParts;
+            #pragma unroll
+            for (int w = 0; w < kWarps; ++w) { bits += red32[w * 12 + lane]; }
+        }
+        const uint32_t lowest = __reduce_min_sync(0xffffffffu, bits);
+        const uint32_t arg = (uint32_t)__ffs((int)__ballot_sync(0xffffffffu, bits == lowest)) - 1u;
+        if (lane == 0) { red32[96] = lowest; red32[97] = arg; }
     }
+    __syncthreads();
+    const uint32_t best_bits = red32[96], best = red32[97];
     rr.porder = best; rr.bits = best_bits + 2u;
     if (best <= 8u) {
         if ((tid & ((1 << (8 - best)) - 1)) == 0) {
@@ -1139,9 +1265,9 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
         const uint32_t zcount = round_up_u32(n, 8) >> 2;
         int fits = 1;
         for (uint32_t j = tid; j < zcount; j += kThreads) {
-            int32_t x[5];
-            #pragma unroll
-            for (int t = 0; t < 5; ++t) { const uint32_t i = 4u * j + (uint32_t)t; x[t] = (i < n) ? sig[i] : 0; }
+            /* sig is zero beyond n (apply_preemphasis pads 12 samples past the rounded end) */
+            const int4 q = *reinterpret_cast<const int4 *>(sig + 4u * j);
+            const int32_t x[5] = { q.x, q.y, q.z, q.w, sig[4u * j + 4u] };
             #pragma unroll
             for (int t = 0; t < 4; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
             int4 z;

@@ -134,7 +134,7 @@ SRLA_HD inline uint32_t round_up_u32(uint32_t v, uint32_t a) { return (v + a - 1
 /* front_kernel: FFT buffer, the pre-emphasised signal, LTP lags */
 struct FrontLayout {
     uint32_t region_off, region_bytes; /* FFT buffer (doubles) / int32 scratch                 */
-    uint32_t sig_off;                  /* int32: 4 pad + nmax rounded up to 4 + 4              */
+    uint32_t sig_off;                  /* int32: 4 pad + nmax rounded up to 4 + 12             */
     uint32_t lags_off, nlags;          /* doubles (LTP pitch search only)                      */
     uint32_t total;
 };
@@ -146,7 +146,7 @@ SRLA_HD inline FrontLayout make_front_layout(uint32_t nmax, uint32_t fft_max, ui
     L.region_off = off;
     L.region_bytes = round_up_u32((8u * fft_max > 4u * n4) ? 8u * fft_max : 4u * n4, 16);
     off += L.region_bytes;
-    L.sig_off = off; off += 4u * (n4 + 8u);
+    L.sig_off = off; off += 4u * (n4 + 16u);
     L.nlags = ltp ? round_up_u32((uint32_t)kLtpLags, 2) : 0u;
     L.lags_off = off; off += 8u * L.nlags;
     L.total = off;
@@ -183,7 +183,7 @@ SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
     L.region_off = off;
     L.region_bytes = round_up_u32(4u * n4 + (scratch > 4096u ? scratch : 4096u), 16);
     off += L.region_bytes;
-    L.sig_off = off; off += 4u * (n4 + 8u);
+    L.sig_off = off; off += 4u * (n4 + 16u);
     L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
     L.coefb_off = off; off += 4u * (round_up_u32(P, 4) / 4u + 4u);
     L.red_off = off; off += 1024u;
