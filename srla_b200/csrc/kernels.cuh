@@ -39,14 +39,27 @@ __device__ __forceinline__ int32_t load_sample(const StreamDev &st, uint32_t ch,
                                    : __ldg(reinterpret_cast<const int32_t *>(st.pcm) + at);
 }
 
+/* PCM is streamed once per candidate: keep it out of L1 so the FFT twiddle tables stay resident there */
+__device__ __forceinline__ int2 ldg_stream_v2(const void *ptr)
+{
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ int4 ldg_stream_v4(const void *ptr)
+{
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    return v;
+}
 __device__ __forceinline__ int4 load_quad(const StreamDev &st, uint32_t ch, uint32_t idx)
 {
     const unsigned long long at = (unsigned long long)ch * st.stride + idx;
     if (st.sample_bytes == 2u) {
-        const int2 v = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const short *>(st.pcm) + at));
+        const int2 v = ldg_stream_v2(reinterpret_cast<const short *>(st.pcm) + at);
         return make_int4((int32_t)(short)(v.x & 0xffff), v.x >> 16, (int32_t)(short)(v.y & 0xffff), v.y >> 16);
     }
-    return __ldg(reinterpret_cast<const int4 *>(reinterpret_cast<const int32_t *>(st.pcm) + at));
+    return ldg_stream_v4(reinterpret_cast<const int32_t *>(st.pcm) + at);
 }
 __device__ __forceinline__ bool quad_aligned(const StreamDev &st, uint32_t ch, uint32_t idx)
 {
@@ -143,8 +156,10 @@ __device__ __forceinline__ uint32_t fft_slot(uint32_t i) { return i ^ ((i >> 4) 
 
 struct Twiddle3 { double2 w1, w2, w3; };
 /* table of one stage size ns: w1[ns/4], w2[ns/4], w3[ns/4] (host_tables.h) */
-__device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t quarter, uint32_t p, bool inverse)
+template <bool kInv>
+__device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t quarter, uint32_t p)
 {
+    const bool inverse = kInv;
     Twiddle3 t;
     t.w1 = __ldg(table + p); t.w2 = __ldg(table + quarter + p); t.w3 = __ldg(table + 2u * quarter + p);
     if (inverse) { t.w1.y = -t.w1.y; t.w2.y = -t.w2.y; t.w3.y = -t.w3.y; }      /* the recurrence is sign-symmetric */
@@ -152,9 +167,11 @@ __device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t 
 }
 
 /* one radix-4 butterfly, fft.c:93-105 */
+template <bool kInv>
 __device__ __forceinline__ void butterfly4(const double2 a, const double2 b, const double2 c, const double2 d, const Twiddle3 &w,
-                                           const bool inverse, double2 &y0, double2 &y1, double2 &y2, double2 &y3)
+                                           double2 &y0, double2 &y1, double2 &y2, double2 &y3)
 {
+    const bool inverse = kInv;
     const double2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
     /* j * (b - d), j = (0, -flag): forward (0,+1) -> (-im, re); inverse (0,-1) -> (im, -re).
      * (the reference's 0.0 * x terms only affect the sign of zeros) */
@@ -165,71 +182,128 @@ __device__ __forceinline__ void butterfly4(const double2 a, const double2 b, con
     y3 = cmul(w.w3, cadd(amc, jbmd));
 }
 
+/* exact int32 -> double without the quarter-rate I2F.F64: 2^52 + 2^31 + x is representable */
+__device__ __forceinline__ double int_to_double(int32_t x)
+{
+    return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+/* Welch-windowed input of the autocorrelation (lpc.c:252-266, srla_encoder.c:1061-1064): complex element e of
+ * the packed real transform = samples (2e, 2e+1), zero beyond n.  kPre: sig holds the UNFILTERED candidate
+ * and the pre-emphasis (srla_utility.c:342-358, filter memory = first sample) is applied on the fly. */
+template <bool kPre>
+struct WindowSource {
+    const int32_t *sig; uint32_t n, half_n, pc; double unit, div, dn1;
+    __device__ __forceinline__ double one(uint32_t i, int32_t cur, int32_t prv) const
+    {
+        if (i >= n) { return 0.0; }
+        const int32_t x = kPre ? (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * pc) >> 4)) : cur;
+        const uint32_t s = (i < half_n) ? i : (n - 1u - i);
+        const double ds = int_to_double((int32_t)s);
+        const double w = div * ds * (dn1 - ds);              /* (n - 1 - s) as an exact double difference */
+        return (int_to_double(x) * unit) * w;
+    }
+    __device__ __forceinline__ double2 element(uint32_t e) const
+    {
+        const uint32_t i = 2u * e;
+        if (i >= n) { return make_double2(0.0, 0.0); }
+        /* sig is zero-padded past n and has 4 readable samples in front of index 0 */
+        const int2 c = *reinterpret_cast<const int2 *>(sig + i);
+        const int32_t prv = kPre ? sig[i ? i - 1u : 0u] : 0;
+        return make_double2(one(i, c.x, prv), one(i + 1u, c.y, c.x));
+    }
+};
+
 /* complex FFT of M points (M a power of two, M/16 <= blockDim.x, M/8 <= blockDim.x when M = 8 * 4^k).
  * `need`: only outputs 0..need-1 are required (M = all).  The autocorrelation reads just the first lags
  * of the inverse transform, so its last two passes skip every butterfly none of whose outputs can reach
- * them -- the surviving outputs are the reference's expression trees unchanged. */
-__device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inverse, const LaunchParams &p, const uint32_t need)
+ * them -- the surviving outputs are the reference's expression trees unchanged.
+ * `src` (forward transform, M >= 16 only): the first pass takes its inputs from the windowed samples
+ * instead of x, which saves one full write + read of the buffer. */
+/* one fused pair of radix-4 stages (sizes nn and nn/4, output stride 1 << lgs) */
+template <bool kInv, bool kPre, bool kFromSamples>
+__device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs, const LaunchParams &p,
+                                              const uint32_t need, const WindowSource<kPre> *src)
 {
     const uint32_t tid = threadIdx.x;
-    uint32_t nn = M, lgs = 0;
-    /* fused pairs of radix-4 stages */
-    while (nn >= 16u) {
-        const uint32_t units = M >> 4;
-        const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
-        const bool last_pair = (nn < 256u);          /* outputs feed the tail pass (or are final) */
-        double2 v[4][4];
-        if (tid < units) {
+    const uint32_t units = M >> 4;
+    const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
+    const bool last_pair = (nn < 256u);          /* outputs feed the tail pass (or are final) */
+    const bool active = tid < units;
+    const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
+    double2 v[4][4];
+    if (active) {
+        #pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
             #pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) { v[jp][j] = x[fft_slot(tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2))]; }
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
+                v[jp][j] = kFromSamples ? src->element(e) : x[fft_slot(e)];
             }
         }
-        __syncthreads();
-        if (tid < units) {
-            const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
-            const double2 *tw_a = p.tw_complex + p.tw_complex_off[lgn];
-            const double2 *tw_b = p.tw_complex + p.tw_complex_off[lgn - 2u];
-            double2 y[4][4];
+    }
+    if (!kFromSamples) { __syncthreads(); }      /* in place: every input is in registers before any output is stored */
+    if (active) {
+        const double2 *tw_a = p.tw_complex + p.tw_complex_off[lgn];
+        const double2 *tw_b = p.tw_complex + p.tw_complex_off[lgn - 2u];
+        double2 y[4][4];
+        #pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+            const Twiddle3 wa = load_twiddle<kInv>(tw_a, nn >> 2, p0 + (uint32_t)jp * (nn >> 4));
+            butterfly4<kInv>(v[jp][0], v[jp][1], v[jp][2], v[jp][3], wa, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
+        }
+        const Twiddle3 wb = load_twiddle<kInv>(tw_b, nn >> 4, p0);
+        if (!last_pair || need >= M) {
             #pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {
-                const Twiddle3 w = load_twiddle(tw_a, nn >> 2, p0 + (uint32_t)jp * (nn >> 4), inverse);
-                butterfly4(v[jp][0], v[jp][1], v[jp][2], v[jp][3], w, inverse, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
+            for (int j = 0; j < 4; ++j) {
+                double2 z0, z1, z2, z3;
+                butterfly4<kInv>(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
+                const uint32_t o = q + ((uint32_t)j << lgs) + ((16u * p0) << lgs);
+                x[fft_slot(o)]                = z0;
+                x[fft_slot(o + (4u << lgs))]  = z1;
+                x[fft_slot(o + (8u << lgs))]  = z2;
+                x[fft_slot(o + (12u << lgs))] = z3;
             }
-            if (!last_pair || need >= M) {
-                const Twiddle3 w = load_twiddle(tw_b, nn >> 4, p0, inverse);
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+        } else {
+            /* an output at position o is read later only when (o mod (16 << lgs)) < need */
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t low = q + ((uint32_t)j << lgs);
+                const uint32_t o = low + ((16u * p0) << lgs);
+                if (low + (4u << lgs) < need) {
                     double2 z0, z1, z2, z3;
-                    butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], w, inverse, z0, z1, z2, z3);
-                    const uint32_t o = q + ((uint32_t)j << lgs) + ((16u * p0) << lgs);
+                    butterfly4<kInv>(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
                     x[fft_slot(o)]                = z0;
                     x[fft_slot(o + (4u << lgs))]  = z1;
                     x[fft_slot(o + (8u << lgs))]  = z2;
                     x[fft_slot(o + (12u << lgs))] = z3;
-                }
-            } else {
-                /* an output at position o is read later only when (o mod (16 << lgs)) < need */
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t low = q + ((uint32_t)j << lgs);
-                    const uint32_t o = low + ((16u * p0) << lgs);
-                    if (low + (4u << lgs) < need) {
-                        const Twiddle3 w = load_twiddle(tw_b, nn >> 4, p0, inverse);
-                        double2 z0, z1, z2, z3;
-                        butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], w, inverse, z0, z1, z2, z3);
-                        x[fft_slot(o)]                = z0;
-                        x[fft_slot(o + (4u << lgs))]  = z1;
-                        x[fft_slot(o + (8u << lgs))]  = z2;
-                        x[fft_slot(o + (12u << lgs))] = z3;
-                    } else if (low < need) {
-                        x[fft_slot(o)] = cadd(cadd(y[0][j], y[2][j]), cadd(y[1][j], y[3][j]));     /* y0 of butterfly4 */
-                    }
+                } else if (low < need) {
+                    x[fft_slot(o)] = cadd(cadd(y[0][j], y[2][j]), cadd(y[1][j], y[3][j]));     /* y0 of butterfly4 */
                 }
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+}
+
+/* complex FFT of M points (M a power of two, M/16 <= blockDim.x, M/8 <= blockDim.x when M = 8 * 4^k).
+ * `need`: only outputs 0..need-1 are required (M = all).  The autocorrelation reads just the first lags
+ * of the inverse transform, so its last two passes skip every butterfly none of whose outputs can reach
+ * them -- the surviving outputs are the reference's expression trees unchanged.
+ * `src` (forward transform, M >= 16 only): the first pass takes its inputs from the windowed samples
+ * instead of x, which saves one full write + read of the buffer. */
+template <bool kInv, bool kPre>
+__device__ __forceinline__ void complex_fft_inplace(double2 *x, const uint32_t M, const LaunchParams &p, const uint32_t need,
+                                                    const WindowSource<kPre> *src)
+{
+    const uint32_t tid = threadIdx.x;
+    uint32_t nn = M, lgs = 0;
+    if (src != nullptr && nn >= 16u) {
+        fft_pair_pass<kInv, kPre, true>(x, M, nn, lgs, p, need, src);
+        nn >>= 4; lgs += 4;
+    }
+    while (nn >= 16u) {
+        fft_pair_pass<kInv, kPre, false>(x, M, nn, lgs, p, need, src);
         nn >>= 4; lgs += 4;
     }
     /* tail passes: up to two work units per thread (all loads precede all stores: in place is safe) */
@@ -257,10 +331,10 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
             const uint32_t u = tid + (uint32_t)r * T;
             if (u < live) {
                 double2 y[2][4];
-                { const Twiddle3 w0 = load_twiddle(tw, 2u, 0u, inverse);
-                  butterfly4(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, inverse, y[0][0], y[0][1], y[0][2], y[0][3]); }
-                { const Twiddle3 w1 = load_twiddle(tw, 2u, 1u, inverse);
-                  butterfly4(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, inverse, y[1][0], y[1][1], y[1][2], y[1][3]); }
+                { const Twiddle3 w0 = load_twiddle<kInv>(tw, 2u, 0u);
+                  butterfly4<kInv>(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, y[0][0], y[0][1], y[0][2], y[0][3]); }
+                { const Twiddle3 w1 = load_twiddle<kInv>(tw, 2u, 1u);
+                  butterfly4<kInv>(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, y[1][0], y[1][1], y[1][2], y[1][3]); }
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     x[fft_slot(u + (uint32_t)j * s)]            = cadd(y[0][j], y[1][j]);
@@ -283,13 +357,13 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
             }
         }
         __syncthreads();
-        const Twiddle3 w = load_twiddle(p.tw_complex + p.tw_complex_off[2], 1u, 0u, inverse);
+        const Twiddle3 w = load_twiddle<kInv>(p.tw_complex + p.tw_complex_off[2], 1u, 0u);
         #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t u = tid + (uint32_t)r * T;
             if (u < live) {
                 double2 y0, y1, y2, y3;
-                butterfly4(v[r][0], v[r][1], v[r][2], v[r][3], w, inverse, y0, y1, y2, y3);
+                butterfly4<kInv>(v[r][0], v[r][1], v[r][2], v[r][3], w, y0, y1, y2, y3);
                 x[fft_slot(u)] = y0; x[fft_slot(u + s)] = y1; x[fft_slot(u + 2u * s)] = y2; x[fft_slot(u + 3u * s)] = y3;
             }
         }
@@ -311,12 +385,6 @@ __device__ void complex_fft_inplace(double2 *x, const uint32_t M, const bool inv
         }
         __syncthreads();
     }
-}
-
-/* exact int32 -> double without the quarter-rate I2F.F64: 2^52 + 2^31 + x is representable */
-__device__ __forceinline__ double int_to_double(int32_t x)
-{
-    return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) - 4503601774854144.0;
 }
 
 /* Welch window (lpc.c:252-266) + autocorrelation through the FFT (lpc.c:330-376).
@@ -345,71 +413,15 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
         return;
     }
     const uint32_t M = N >> 1;
-    if (N < 4u) {
-        for (uint32_t c = tid; c < M; c += nthreads) {
-            double v[2];
-            #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const uint32_t i = 2u * c + (uint32_t)t;
-                double r = 0.0;
-                if (i < n) {
-                    const uint32_t s = (i < (n >> 1)) ? i : (n - 1u - i);
-                    const double w = div * (double)s * (double)(n - 1u - s);
-                    int32_t x = sig[i];
-                    if (kPre) { x = (int32_t)((uint32_t)x - (uint32_t)((int32_t)((uint32_t)sig[i ? i - 1u : 0u] * pc) >> 4)); }
-                    r = ((double)x * unit) * w;
-                }
-                v[t] = r;
-            }
-            cx[fft_slot(c)] = make_double2(v[0], v[1]);
-        }
+    WindowSource<kPre> ws;
+    ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = unit; ws.div = div; ws.dn1 = (double)(int32_t)(n - 1u);
+    if (M >= 16u) {
+        complex_fft_inplace<false, kPre>(cx, M, p, M, &ws);      /* the first pass windows the samples itself */
     } else {
-        const uint32_t half_n = n >> 1;
-        const double dn1 = (double)(int32_t)(n - 1u);
-        for (uint32_t g = tid; g < (N >> 2); g += nthreads) {
-            const uint32_t i0 = 4u * g;
-            double v[4];
-            if (i0 + 4u <= n && (i0 + 4u <= half_n || i0 >= half_n)) {
-                /* four samples of one window half: weights from exact double increments instead of conversions */
-                const int4 q = *reinterpret_cast<const int4 *>(sig + i0);
-                int32_t x[4] = { q.x, q.y, q.z, q.w };
-                if (kPre) {
-                    const int32_t prv = sig[i0 ? i0 - 1u : 0u];
-                    x[3] = (int32_t)((uint32_t)q.w - (uint32_t)((int32_t)((uint32_t)q.z * pc) >> 4));
-                    x[2] = (int32_t)((uint32_t)q.z - (uint32_t)((int32_t)((uint32_t)q.y * pc) >> 4));
-                    x[1] = (int32_t)((uint32_t)q.y - (uint32_t)((int32_t)((uint32_t)q.x * pc) >> 4));
-                    x[0] = (int32_t)((uint32_t)q.x - (uint32_t)((int32_t)((uint32_t)prv * pc) >> 4));
-                }
-                const bool first = (i0 < half_n);
-                const double s0 = first ? (double)(int32_t)i0 : (double)(int32_t)(n - 1u - i0);
-                const double inc = first ? 1.0 : -1.0;
-                #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const double ds = s0 + inc * (double)t;                 /* exact: small integers */
-                    const double w = div * ds * (dn1 - ds);
-                    v[t] = (int_to_double(x[t]) * unit) * w;
-                }
-            } else {
-                #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const uint32_t i = i0 + (uint32_t)t;
-                    double r = 0.0;
-                    if (i < n) {
-                        const uint32_t s = (i < half_n) ? i : (n - 1u - i);
-                        const double w = div * (double)s * (double)(n - 1u - s);
-                        int32_t x = sig[i];
-                        if (kPre) { x = (int32_t)((uint32_t)x - (uint32_t)((int32_t)((uint32_t)sig[i ? i - 1u : 0u] * pc) >> 4)); }
-                        r = ((double)x * unit) * w;
-                    }
-                    v[t] = r;
-                }
-            }
-            cx[fft_slot(2u * g)] = make_double2(v[0], v[1]);
-            cx[fft_slot(2u * g + 1u)] = make_double2(v[2], v[3]);
-        }
+        for (uint32_t c = tid; c < M; c += nthreads) { cx[fft_slot(c)] = ws.element(c); }
+        __syncthreads();
+        complex_fft_inplace<false, kPre>(cx, M, p, M, nullptr);
     }
-    __syncthreads();
-    complex_fft_inplace(cx, M, false, p, M);
     /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three
      * only touch the element pair (i, N/2 - i) */
     {
@@ -464,7 +476,7 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
     }
     {
         const uint32_t want = (nlags < N) ? nlags : N;
-        complex_fft_inplace(cx, M, true, p, (want + 1u) >> 1);
+        complex_fft_inplace<true, kPre>(cx, M, p, (want + 1u) >> 1, nullptr);
     }
     const double scale = job.ac_scale;
     for (uint32_t i = tid; i < nlags; i += nthreads) {
@@ -711,7 +723,7 @@ __device__ __forceinline__ int32_t preemphasis_coefficient(const int32_t *raw, c
 }
 
 /* kOcc: resident CTAs per SM the register allocation is sized for */
-template <int kT, int kOcc>
+template <int kT, int kOcc, bool kLtp>
 __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -734,7 +746,7 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
 
     /* without LTP the candidate goes straight into the signal buffer and the pre-emphasis is folded into
      * the window pass; with LTP the filtered signal itself is needed in shared memory */
-    int32_t *raw = (p.ltp_order > 0u) ? region_i : sig;
+    int32_t *raw = kLtp ? region_i : sig;
     int nz = load_candidate(st, job, p, cand, lshift, raw);
     nz = __syncthreads_or(nz);
     if (tid == 0) {
@@ -746,7 +758,7 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
 
     const int32_t pre_coef = preemphasis_coefficient<kT>(raw, n, out, red64, &sh_i[0]);
     double *g = p.lags + ((size_t)job_id * p.ncand + cand) * p.lag_stride;
-    if (p.ltp_order == 0u) {
+    if (!kLtp) {
         /* ---- autocorrelation of the signal the LPC stage sees (lpc.c:444-483) ---- */
         if (P > 0u) { welch_autocorr<true>(raw, pre_coef, n, region_d, g, P + 1u, job, p); }
         return;

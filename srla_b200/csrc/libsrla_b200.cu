@@ -91,7 +91,7 @@ struct DeviceCtx {
     uint32_t smem_set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     int max_smem_optin = 0;
     int num_sms = 0;
-    int front_occ = 4;             /* CTAs per SM front_kernel<128> is register-sized for (SRLA_B200_FRONT_OCC=3|4, tuning) */
+    int front_occ = 3;             /* CTAs per SM front_kernel<128> is register-sized for (SRLA_B200_FRONT_OCC=3|4, tuning) */
 };
 
 } // namespace
@@ -127,7 +127,7 @@ bool ctx_init(DeviceCtx *c)
         return false;
     }
     c->num_sms = prop.multiProcessorCount;
-    if (const char *e = std::getenv("SRLA_B200_FRONT_OCC")) { if (e[0] == '3') { c->front_occ = 3; } }
+    if (const char *e = std::getenv("SRLA_B200_FRONT_OCC")) { if (e[0] == '3') { c->front_occ = 3; } else if (e[0] == '4') { c->front_occ = 4; } }
     CU_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
@@ -309,18 +309,27 @@ struct Runner {
         }
         const uint32_t ncands = p.num_jobs * p.ncand;
         const dim3 grid(ncands), block(kThreads);
+        const bool ltp = p.ltp_order > 0u;
         if (p.fft_max <= 4096u) {
             /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
-            if (c->front_occ == 3) {
-                if (!prep_kernel(front_kernel<128, 3>, FL.total, 5)) { return false; }
-                front_kernel<128, 3><<<grid, 128, FL.total, c->stream>>>(p);
+            if (ltp) {
+                if (!prep_kernel(front_kernel<128, 3, true>, FL.total, 5)) { return false; }
+                front_kernel<128, 3, true><<<grid, 128, FL.total, c->stream>>>(p);
+            } else if (c->front_occ == 4) {
+                if (!prep_kernel(front_kernel<128, 4, false>, FL.total, 6)) { return false; }
+                front_kernel<128, 4, false><<<grid, 128, FL.total, c->stream>>>(p);
             } else {
-                if (!prep_kernel(front_kernel<128, 4>, FL.total, 0)) { return false; }
-                front_kernel<128, 4><<<grid, 128, FL.total, c->stream>>>(p);
+                if (!prep_kernel(front_kernel<128, 3, false>, FL.total, 0)) { return false; }
+                front_kernel<128, 3, false><<<grid, 128, FL.total, c->stream>>>(p);
             }
         } else if (p.fft_max <= 8192u) {
-            if (!prep_kernel(front_kernel<256, 2>, FL.total, 1)) { return false; }
-            front_kernel<256, 2><<<grid, 256, FL.total, c->stream>>>(p);
+            if (ltp) {
+                if (!prep_kernel(front_kernel<256, 2, true>, FL.total, 1)) { return false; }
+                front_kernel<256, 2, true><<<grid, 256, FL.total, c->stream>>>(p);
+            } else {
+                if (!prep_kernel(front_kernel<256, 2, false>, FL.total, 7)) { return false; }
+                front_kernel<256, 2, false><<<grid, 256, FL.total, c->stream>>>(p);
+            }
         } else {
             std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
             return false;
