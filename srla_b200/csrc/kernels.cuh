@@ -221,7 +221,7 @@ struct WindowSource {
  * `src` (forward transform, M >= 16 only): the first pass takes its inputs from the windowed samples
  * instead of x, which saves one full write + read of the buffer. */
 /* one fused pair of radix-4 stages (sizes nn and nn/4, output stride 1 << lgs) */
-template <bool kInv, bool kPre, bool kFromSamples>
+template <bool kInv, bool kPre, bool kFromSamples, bool kPrune>
 __device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs, const LaunchParams &p,
                                               const uint32_t need, const WindowSource<kPre> *src)
 {
@@ -253,7 +253,7 @@ __device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, cons
             butterfly4<kInv>(v[jp][0], v[jp][1], v[jp][2], v[jp][3], wa, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
         }
         const Twiddle3 wb = load_twiddle<kInv>(tw_b, nn >> 4, p0);
-        if (!last_pair || need >= M) {
+        if (!kPrune || !last_pair || need >= M) {
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 double2 z0, z1, z2, z3;
@@ -299,11 +299,11 @@ __device__ __forceinline__ void complex_fft_inplace(double2 *x, const uint32_t M
     const uint32_t tid = threadIdx.x;
     uint32_t nn = M, lgs = 0;
     if (src != nullptr && nn >= 16u) {
-        fft_pair_pass<kInv, kPre, true>(x, M, nn, lgs, p, need, src);
+        fft_pair_pass<kInv, kPre, true, kInv>(x, M, nn, lgs, p, need, src);
         nn >>= 4; lgs += 4;
     }
     while (nn >= 16u) {
-        fft_pair_pass<kInv, kPre, false>(x, M, nn, lgs, p, need, src);
+        fft_pair_pass<kInv, kPre, false, kInv>(x, M, nn, lgs, p, need, src);
         nn >>= 4; lgs += 4;
     }
     /* tail passes: up to two work units per thread (all loads precede all stores: in place is safe) */
@@ -392,7 +392,7 @@ __device__ __forceinline__ void complex_fft_inplace(double2 *x, const uint32_t M
  * kPre: sig holds the UNFILTERED candidate and the pre-emphasis (srla_utility.c:342-358) is applied
  * on the fly with coefficient pre_coef. */
 template <bool kPre>
-__device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const uint32_t n, double *buf, double *lags, const uint32_t nlags,
+__device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const uint32_t n, double *buf, double *lags, const uint32_t lag_step, const uint32_t nlags,
                                const Job &job, const LaunchParams &p)
 {
     const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
@@ -408,7 +408,7 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
             buf[0] = ((double)x * unit) * w;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < nlags; i += nthreads) { lags[i] = (i < N) ? buf[i] * job.ac_scale : 0.0; }
+        for (uint32_t i = tid; i < nlags; i += nthreads) { lags[(size_t)i * lag_step] = (i < N) ? buf[i] * job.ac_scale : 0.0; }
         __syncthreads();
         return;
     }
@@ -482,7 +482,7 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
     for (uint32_t i = tid; i < nlags; i += nthreads) {
         double v = 0.0;
         if (i < N) { const double2 e = cx[fft_slot(i >> 1)]; v = ((i & 1u) ? e.y : e.x) * scale; }
-        lags[i] = v;
+        lags[(size_t)i * lag_step] = v;
     }
     __syncthreads();
 }
@@ -757,17 +757,18 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
     if (n <= P) { return; }                          /* RAW block (srla_encoder.c:777-779): nothing to analyse */
 
     const int32_t pre_coef = preemphasis_coefficient<kT>(raw, n, out, red64, &sh_i[0]);
-    double *g = p.lags + ((size_t)job_id * p.ncand + cand) * p.lag_stride;
+    /* lags of 32 consecutive candidates are interleaved for the lpc kernel: [lag][candidate % 32] */
+    double *g = p.lags + (size_t)(blockIdx.x >> 5) * p.lag_stride * 32u + (blockIdx.x & 31u);
     if (!kLtp) {
         /* ---- autocorrelation of the signal the LPC stage sees (lpc.c:444-483) ---- */
-        if (P > 0u) { welch_autocorr<true>(raw, pre_coef, n, region_d, g, P + 1u, job, p); }
+        if (P > 0u) { welch_autocorr<true>(raw, pre_coef, n, region_d, g, 32u, P + 1u, job, p); }
         return;
     }
     apply_preemphasis(region_i, sig, n, pre_coef);
     __syncthreads();
 
     /* ---- long-term prediction (srla_encoder.c:1008-1058) ---- */
-    welch_autocorr<false>(sig, 0, n, region_d, lags, kLtpLags, job, p);
+    welch_autocorr<false>(sig, 0, n, region_d, lags, 1u, kLtpLags, job, p);
     if (tid == 0) {
         /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
         for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
@@ -780,7 +781,7 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
     __syncthreads();
     if (sh_u[1]) { return; }
     if (sh_u[0] > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
-    if (P > 0u) { welch_autocorr<false>(sig, 0, n, region_d, g, P + 1u, job, p); }
+    if (P > 0u) { welch_autocorr<false>(sig, 0, n, region_d, g, 32u, P + 1u, job, p); }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -830,12 +831,22 @@ __device__ __forceinline__ void levinson_lane(const double *R, double *A, const 
         const double refl = acc / (-e);
         e = e * (1.0 - refl * refl);
         LPC_A(k + 1u) = 0.0;
-        for (uint32_t lo = 0, hi = k + 1u; lo <= hi; ++lo, --hi) {
-            const double t1 = LPC_A(lo), t2 = LPC_A(hi);
-            LPC_A(lo) = t1 + refl * t2;
-            if (hi != lo) { LPC_A(hi) = t2 + refl * t1; }
-            if (hi == 0u) { break; }
+        /* new[i] = prev[i] + refl * prev[k+1-i] (lpc.c:432-435) in symmetric pairs; four pairs are loaded before
+         * any is stored so the shared-memory latencies overlap */
+        const uint32_t npairs = (k + 2u) >> 1;
+        uint32_t j = 0;
+        for (; j + 4u <= npairs; j += 4u) {
+            const double a0 = LPC_A(j), a1 = LPC_A(j + 1u), a2 = LPC_A(j + 2u), a3 = LPC_A(j + 3u);
+            const double b0 = LPC_A(k + 1u - j), b1 = LPC_A(k - j), b2 = LPC_A(k - 1u - j), b3 = LPC_A(k - 2u - j);
+            LPC_A(j) = a0 + refl * b0; LPC_A(j + 1u) = a1 + refl * b1; LPC_A(j + 2u) = a2 + refl * b2; LPC_A(j + 3u) = a3 + refl * b3;
+            LPC_A(k + 1u - j) = b0 + refl * a0; LPC_A(k - j) = b1 + refl * a1; LPC_A(k - 1u - j) = b2 + refl * a2; LPC_A(k - 2u - j) = b3 + refl * a3;
         }
+        for (; j < npairs; ++j) {
+            const double t1 = LPC_A(j), t2 = LPC_A(k + 1u - j);
+            LPC_A(j) = t1 + refl * t2;
+            LPC_A(k + 1u - j) = t2 + refl * t1;
+        }
+        if (((k + 1u) & 1u) == 0u) { const uint32_t mid = (k + 1u) >> 1; const double t = LPC_A(mid); LPC_A(mid) = t + refl * t; }
         if (diag_err) { diag_err[k + 1u] = e * gain; }
         if (pk) { consider_order(*pk, e, k + 1u, gain, n, bps); }
     }
@@ -850,10 +861,11 @@ __global__ void __launch_bounds__(32) lpc_kernel(const __grid_constant__ LaunchP
     const uint32_t first = blockIdx.x * 32u;
     double *R = reinterpret_cast<double *>(smem);            /* [P + 2][32] */
     double *A = R + (size_t)(P + 2u) * 32u;                  /* [P + 3][32] */
-    /* coalesced transpose-load of the 32 candidates' lags */
-    for (uint32_t c = 0; c < 32u && first + c < total; ++c) {
-        const double *g = p.lags + (size_t)(first + c) * p.lag_stride;
-        for (uint32_t i = lane; i <= P; i += 32u) { R[(size_t)i * 32u + c] = g[i]; }
+    /* the front kernel stores the lags of 32 consecutive candidates interleaved ([lag][candidate % 32]):
+     * coalesced loads, conflict-free stores */
+    {
+        const double *g = p.lags + (size_t)blockIdx.x * p.lag_stride * 32u;
+        for (uint32_t i = 0; i <= P; ++i) { R[(size_t)i * 32u + lane] = g[(size_t)i * 32u + lane]; }
     }
     __syncwarp();
     const uint32_t idx = first + lane;
@@ -1565,6 +1577,32 @@ struct BitCursor {
     }
 };
 
+/* sequential MSB-first writer of one thread's contiguous bit range (bit_stream.h:245-307 semantics): a 64-bit
+ * shift register whose completed upper word is stored as soon as it fills.  Only the first and the last word
+ * of the range can be shared with the neighbouring threads: those are OR-ed atomically, every other word is
+ * owned exclusively and stored plainly (the staging buffer starts zeroed). */
+struct BitSink {
+    uint32_t *words;
+    unsigned long long acc;
+    uint32_t w, first_w, fill;
+    __device__ __forceinline__ void init(uint32_t *base, uint32_t start_bit) { words = base; w = start_bit >> 5; first_w = w; fill = start_bit & 31u; acc = 0ull; }
+    __device__ __forceinline__ void flush_word()
+    {
+        const uint32_t out = (uint32_t)(acc >> 32);
+        if (w == first_w) { if (out) { atomicOr(words + w, out); } } else { words[w] = out; }
+        acc <<= 32; fill -= 32u; w++;
+    }
+    __device__ __forceinline__ void zeros(uint32_t q) { fill += q; while (fill >= 32u) { flush_word(); } }
+    /* the low len bits of value, 1 <= len <= 32, value < 2^len */
+    __device__ __forceinline__ void put(uint32_t value, uint32_t len)
+    {
+        acc |= (unsigned long long)value << (64u - fill - len);
+        fill += len;
+        if (fill >= 32u) { flush_word(); }
+    }
+    __device__ __forceinline__ void finish() { const uint32_t out = (uint32_t)(acc >> 32); if (out) { atomicOr(words + w, out); } }
+};
+
 /* length in bits of the code of u with parameter k (srla_coder.c:165-190) */
 __device__ __forceinline__ uint32_t code_len(uint32_t u, uint32_t k, uint32_t code_type)
 {
@@ -1693,7 +1731,10 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ 
         }
         for (uint32_t ch = 0; ch < nch; ++ch) { const CandOut &c = cands[jo.cand_of_channel[ch]]; pos += 1u + (c.ltp_period ? (1u + 8u + 6u * p.ltp_order) : 0u); }
         __syncthreads();
-        /* section 4: residual codes (srla_coder.c:486-595) */
+        /* section 4: residual codes (srla_coder.c:486-595).  Every thread codes one contiguous run of samples,
+         * four at a time (one 16-byte load): pass 1 sizes the run, a block scan places it, pass 2 writes it.
+         * The loops over the quads are deliberately not unrolled: the body is large and the kernel is otherwise
+         * bound by instruction fetch. */
         const uint32_t chunk = (n + kThreads - 1u) / kThreads;
         for (uint32_t ch = 0; ch < nch; ++ch) {
             const uint32_t cidx = jo.cand_of_channel[ch];
@@ -1709,43 +1750,91 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ 
             const int32_t *res = p.residual + ((size_t)j * p.ncand + cidx) * p.res_stride;
             const uint32_t plen = n >> c.porder;
             const uint32_t i0 = (uint32_t)tid * chunk, i1 = (i0 + chunk < n) ? i0 + chunk : n;
-            /* pass 1: bits of this thread's samples (+ parameter fields of partitions starting here) */
+            const uint32_t cnt = (i0 < n) ? i1 - i0 : 0u;
+            const bool vec = (chunk & 3u) == 0u;                 /* runs start 16-byte aligned; res_stride pads the last quad */
+            /* partitions: `part0` holds sample i0; a partition's parameter field precedes its first sample */
+            const uint32_t part0 = (cnt > 0u) ? i0 / plen : 0u;
+            const uint32_t first_boundary = (part0 * plen == i0) ? i0 : (part0 + 1u) * plen;
+            const bool rice = (code_type == kCodeRice);
+            /* pass 1 */
             uint32_t mybits = 0;
-            if (i0 < n) {
-                uint32_t part = i0 / plen, next_start = part * plen;
-                if (next_start < i0) { part++; next_start += plen; }
-                uint32_t cur_part = i0 / plen;
-                uint32_t k = c.kparam[cur_part];
-                for (uint32_t i = i0; i < i1; ++i) {
-                    if (i == next_start) {
-                        cur_part = part; k = c.kparam[cur_part];
-                        mybits += (cur_part == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)c.kparam[cur_part - 1u]) + 1u);
-                        part++; next_start += plen;
+            {
+                uint32_t part = part0, k = (cnt > 0u) ? (uint32_t)c.kparam[part0] : 0u, next = first_boundary;
+                #pragma unroll 1
+                for (uint32_t t0 = 0; t0 < cnt; t0 += 4u) {
+                    int4 q4 = make_int4(0, 0, 0, 0);
+                    if (vec) { q4 = __ldg(reinterpret_cast<const int4 *>(res + i0 + t0)); }
+                    else {
+                        q4.x = __ldg(res + i0 + t0);
+                        if (t0 + 1u < cnt) { q4.y = __ldg(res + i0 + t0 + 1u); }
+                        if (t0 + 2u < cnt) { q4.z = __ldg(res + i0 + t0 + 2u); }
+                        if (t0 + 3u < cnt) { q4.w = __ldg(res + i0 + t0 + 3u); }
                     }
-                    mybits += code_len(zigzag32(__ldg(res + i)), k, code_type);
+                    const uint32_t uu[4] = { zigzag32(q4.x), zigzag32(q4.y), zigzag32(q4.z), zigzag32(q4.w) };
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t i = i0 + t0 + (uint32_t)e;
+                        if (t0 + (uint32_t)e < cnt) {
+                            if (i == next) {
+                                part = (i == i0) ? part0 : part + 1u;
+                                k = c.kparam[part];
+                                mybits += (part == 0u) ? 5u : (zigzag32((int32_t)k - (int32_t)c.kparam[part - 1u]) + 1u);
+                                next += plen;
+                            }
+                            mybits += code_len(uu[e], k, code_type);
+                        }
+                    }
                 }
             }
             uint32_t total;
             const uint32_t incl = block_scan_inclusive(mybits, scan_scratch, &total);
-            /* pass 2: emit */
-            if (i0 < n && mybits) {
-                const uint32_t start = pos + 12u + incl - mybits;
-                BitCursor bc; bc.init(words, start, start + mybits);
-                uint32_t at = start;
-                uint32_t part = i0 / plen, next_start = part * plen;
-                if (next_start < i0) { part++; next_start += plen; }
-                uint32_t cur_part = i0 / plen;
-                uint32_t k = c.kparam[cur_part];
-                for (uint32_t i = i0; i < i1; ++i) {
-                    if (i == next_start) {
-                        cur_part = part; k = c.kparam[cur_part];
-                        if (cur_part == 0u) { bc.put(at, k, 5u); at += 5u; }
-                        else { const uint32_t run = zigzag32((int32_t)k - (int32_t)c.kparam[cur_part - 1u]); bc.put(at + run, 1u, 1u); at += run + 1u; }
-                        part++; next_start += plen;
+            /* pass 2 */
+            if (mybits) {
+                BitSink bs; bs.init(words, pos + 12u + incl - mybits);
+                uint32_t part = part0, k = c.kparam[part0], next = first_boundary;
+                #pragma unroll 1
+                for (uint32_t t0 = 0; t0 < cnt; t0 += 4u) {
+                    int4 q4 = make_int4(0, 0, 0, 0);
+                    if (vec) { q4 = __ldg(reinterpret_cast<const int4 *>(res + i0 + t0)); }
+                    else {
+                        q4.x = __ldg(res + i0 + t0);
+                        if (t0 + 1u < cnt) { q4.y = __ldg(res + i0 + t0 + 1u); }
+                        if (t0 + 2u < cnt) { q4.z = __ldg(res + i0 + t0 + 2u); }
+                        if (t0 + 3u < cnt) { q4.w = __ldg(res + i0 + t0 + 3u); }
                     }
-                    at += emit_code(bc, at, zigzag32(__ldg(res + i)), k, code_type);
+                    const uint32_t uu[4] = { zigzag32(q4.x), zigzag32(q4.y), zigzag32(q4.z), zigzag32(q4.w) };
+                    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t i = i0 + t0 + (uint32_t)e;
+                        if (t0 + (uint32_t)e < cnt) {
+                            if (i == next) {
+                                part = (i == i0) ? part0 : part + 1u;
+                                k = c.kparam[part];
+                                if (part == 0u) { bs.put(k, 5u); }
+                                else { bs.zeros(zigzag32((int32_t)k - (int32_t)c.kparam[part - 1u])); bs.put(1u, 1u); }
+                                next += plen;
+                            }
+                            /* q zeros, a one, nb low bits (srla_coder.c:165-190) */
+                            const uint32_t v = uu[e];
+                            uint32_t q, nb, low;
+                            if (rice) { q = v >> k; nb = k; low = v & ((1u << k) - 1u); }
+                            else {
+                                const uint32_t k1 = k + 1u, pivot = 1u << k1;
+                                const bool small = v < pivot;
+                                const uint32_t z = v - pivot;
+                                q = small ? 0u : 1u + (z >> k);
+                                nb = small ? k1 : k;
+                                low = small ? v : (z & ((1u << k) - 1u));
+                            }
+                            if (q + nb < 32u) { bs.put((1u << nb) | low, q + nb + 1u); }      /* leading zeros ride along */
+                            else {
+                                bs.zeros(q);
+                                if (nb < 32u) { bs.put((1u << nb) | low, nb + 1u); } else { bs.put(1u, 1u); bs.put(low, 32u); }
+                            }
+                        }
+                    }
                 }
-                bc.flush();
+                bs.finish();
             }
             pos += 12u + total;
             __syncthreads();
@@ -1761,17 +1850,24 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ 
         words[2] |= (jo.type << 24) | ((n & 0xffffu) << 8);
     }
     __syncthreads();
-    /* Fletcher-16 over bytes [8, nbytes) (srla_utility.c:36-60): lo = sum d, hi = sum (L - i) d, mod 255 */
+    /* Fletcher-16 over bytes [8, nbytes) (srla_utility.c:36-60): lo = sum d, hi = sum (L - i) d, mod 255.
+     * Bytes 8.. start on a word boundary of the staging buffer; partial sums stay below 2^32 for 64 words
+     * (4 * 64 * 255 * 2^16), so the modulo is taken once per 32 words. */
     {
         const uint32_t Lb = nbytes - 8u;
-        uint32_t lo = 0, hi = 0;
-        for (uint32_t i = tid; i < Lb; i += kThreads) {
-            const uint32_t at = 8u + i;
-            const uint32_t d = (words[at >> 2] >> (24u - 8u * (at & 3u))) & 0xffu;
-            lo += d;
-            hi = (hi + ((Lb - i) % 255u) * d) % 255u;
+        const uint32_t nw = (Lb + 3u) >> 2;
+        uint32_t lo = 0, hi = 0, since = 0;
+        for (uint32_t wi = tid; wi < nw; wi += kThreads) {
+            const uint32_t wd = words[2u + wi];               /* bytes beyond nbytes are zero */
+            const uint32_t i = wi << 2;                        /* index of the word's first byte inside [8, nbytes) */
+            const uint32_t d0 = wd >> 24, d1 = (wd >> 16) & 0xffu, d2 = (wd >> 8) & 0xffu, d3 = wd & 0xffu;
+            lo += d0 + d1 + d2 + d3;
+            /* weights (Lb - i - t); a zero padding byte may get a "negative" weight, times zero */
+            const uint32_t wgt = Lb - i;
+            hi += wgt * d0 + (wgt - 1u) * d1 + (wgt - 2u) * d2 + (wgt - 3u) * d3;
+            if (++since == 32u) { hi %= 255u; since = 0; }
         }
-        lo %= 255u;
+        lo %= 255u; hi %= 255u;
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
         if (lane == 0) { fl_lo[warp] = lo % 255u; fl_hi[warp] = hi % 255u; }

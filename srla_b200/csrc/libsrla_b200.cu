@@ -71,6 +71,8 @@ struct PinBuf {
     void release() { if (p) { cudaFreeHost(p); } p = nullptr; cap = 0; }
 };
 
+constexpr int kMaxLanes = 4;
+
 struct DeviceCtx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -82,7 +84,17 @@ struct DeviceCtx {
     DevBuf tw_complex, tw_real, rice_thr, huff_code, huff_len;
     uint32_t tw_c_off[20], tw_r_off[20];
     /* work */
-    DevBuf streams, jobs, cand, diag, jobout, residual, lags, misc, stream_begin, pcm, out;
+    DevBuf streams, jobs, misc, stream_begin, pcm, out;
+    /* a lane = one compute stream + its own per-group scratch; alternate groups of a call run on different
+     * lanes so the latency-bound kernels of one group (lpc, scan) overlap the throughput-bound ones of the next */
+    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags; };
+    Lane lane[kMaxLanes];
+    int lanes = 3;                 /* SRLA_B200_LANES */
+    int groups = 8;                /* SRLA_B200_GROUPS: groups a large call is split into */
+    int sized_carveout = 1;        /* SRLA_B200_CARVE=max: every kernel asks for the maximum shared-memory carve-out */
+    int split_device = 0;          /* SRLA_B200_SPLIT_DEVICE=1: also split device-resident calls across the lanes */
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_scan;
     PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox;
     DevBuf snapshot;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
@@ -131,6 +143,14 @@ bool ctx_init(DeviceCtx *c)
     CU_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    c->lane[0].stream = c->own_stream;
+    for (int l = 1; l < kMaxLanes; l++) { CU_TRY(cudaStreamCreateWithFlags(&c->lane[l].own, cudaStreamNonBlocking)); c->lane[l].stream = c->lane[l].own; }
+    for (int l = 0; l < kMaxLanes; l++) { CU_TRY(cudaEventCreateWithFlags(&c->lane[l].done, cudaEventDisableTiming)); }
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    if (const char *e = std::getenv("SRLA_B200_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= kMaxLanes) { c->lanes = v; } }
+    if (const char *e = std::getenv("SRLA_B200_CARVE")) { if (e[0] == 'm') { c->sized_carveout = 0; } }
+    if (const char *e = std::getenv("SRLA_B200_SPLIT_DEVICE")) { c->split_device = std::atoi(e); }
+    if (const char *e = std::getenv("SRLA_B200_GROUPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) { c->groups = v; } }
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev_begin));
@@ -174,14 +194,22 @@ void ctx_destroy(DeviceCtx *c)
     for (cudaEvent_t e : c->ev_pool) { cudaEventDestroy(e); }
     for (cudaEvent_t e : c->ev_h2d) { cudaEventDestroy(e); }
     for (cudaEvent_t e : c->ev_grp) { cudaEventDestroy(e); }
+    for (cudaEvent_t e : c->ev_scan) { cudaEventDestroy(e); }
+    for (int l = 0; l < kMaxLanes; l++) {
+        if (c->lane[l].own) { cudaStreamSynchronize(c->lane[l].own); cudaStreamDestroy(c->lane[l].own); }
+        if (c->lane[l].done) { cudaEventDestroy(c->lane[l].done); }
+        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags };
+        for (DevBuf *b : lb) { b->release(); }
+    }
+    if (c->ev_fork) { cudaEventDestroy(c->ev_fork); }
     if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); }
     if (c->d2h_stream) { cudaStreamDestroy(c->d2h_stream); }
     c->snapshot.release(); c->h_mailbox.release();
     if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
     if (c->ev_upload) { cudaEventDestroy(c->ev_upload); }
-    DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs, &c->cand,
-                       &c->diag, &c->jobout, &c->residual, &c->lags, &c->misc, &c->stream_begin, &c->pcm, &c->out };
+    DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
+                       &c->misc, &c->stream_begin, &c->pcm, &c->out };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release();
     if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
@@ -278,27 +306,34 @@ struct Runner {
         return p;
     }
 
-    bool mark(size_t batch, int slot)
+    bool mark(size_t batch, int slot, cudaStream_t on)
     {
         const size_t idx = batch * 5 + (size_t)slot;
         while (c->ev_pool.size() <= idx) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->ev_pool.push_back(e); }
-        CU_TRY(cudaEventRecord(c->ev_pool[idx], c->stream));
+        CU_TRY(cudaEventRecord(c->ev_pool[idx], on));
         return true;
     }
 
-    /* dynamic shared memory opt-in + maximum carve-out, once per (kernel, size) */
+    /* dynamic shared memory opt-in + carve-out, once per (kernel, size).  `ctas` = CTAs per SM the kernel is
+     * meant to run with: the carve-out is sized for exactly that many (plus the 1 KB the driver reserves per
+     * CTA) so that the rest of the 228 KB stays L1 -- the FFT twiddle tables live there.  0 = maximum carve-out. */
     template <typename K>
-    bool prep_kernel(K kernel, uint32_t smem_bytes, int slot)
+    bool prep_kernel(K kernel, uint32_t smem_bytes, int slot, int ctas = 0)
     {
         if (c->smem_set[slot] == smem_bytes) { return true; }
         CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int carve = cudaSharedmemCarveoutMaxShared;
+        if (ctas > 0 && c->sized_carveout) {
+            const double want = (double)ctas * (smem_bytes + 1024.0 + 256.0) / (228.0 * 1024.0) * 100.0;
+            carve = (int)std::min(100.0, std::ceil(want));
+        }
+        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         c->smem_set[slot] = smem_bytes;
         return true;
     }
 
     /* the three analysis kernels: front (autocorrelation) -> lpc (Levinson-Durbin) -> residual (FIR + Rice search) */
-    bool launch_analyse(const LaunchParams &p, size_t batch)
+    bool launch_analyse(const LaunchParams &p, size_t batch, cudaStream_t on)
     {
         const FrontLayout FL = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
         const LpcLayout LL = make_lpc_layout(p.max_order);
@@ -313,37 +348,37 @@ struct Runner {
         if (p.fft_max <= 4096u) {
             /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
             if (ltp) {
-                if (!prep_kernel(front_kernel<128, 3, true>, FL.total, 5)) { return false; }
-                front_kernel<128, 3, true><<<grid, 128, FL.total, c->stream>>>(p);
+                if (!prep_kernel(front_kernel<128, 3, true>, FL.total, 5, 3)) { return false; }
+                front_kernel<128, 3, true><<<grid, 128, FL.total, on>>>(p);
             } else if (c->front_occ == 4) {
-                if (!prep_kernel(front_kernel<128, 4, false>, FL.total, 6)) { return false; }
-                front_kernel<128, 4, false><<<grid, 128, FL.total, c->stream>>>(p);
+                if (!prep_kernel(front_kernel<128, 4, false>, FL.total, 6, 4)) { return false; }
+                front_kernel<128, 4, false><<<grid, 128, FL.total, on>>>(p);
             } else {
-                if (!prep_kernel(front_kernel<128, 3, false>, FL.total, 0)) { return false; }
-                front_kernel<128, 3, false><<<grid, 128, FL.total, c->stream>>>(p);
+                if (!prep_kernel(front_kernel<128, 3, false>, FL.total, 0, 3)) { return false; }
+                front_kernel<128, 3, false><<<grid, 128, FL.total, on>>>(p);
             }
         } else if (p.fft_max <= 8192u) {
             if (ltp) {
-                if (!prep_kernel(front_kernel<256, 2, true>, FL.total, 1)) { return false; }
-                front_kernel<256, 2, true><<<grid, 256, FL.total, c->stream>>>(p);
+                if (!prep_kernel(front_kernel<256, 2, true>, FL.total, 1, 2)) { return false; }
+                front_kernel<256, 2, true><<<grid, 256, FL.total, on>>>(p);
             } else {
-                if (!prep_kernel(front_kernel<256, 2, false>, FL.total, 7)) { return false; }
-                front_kernel<256, 2, false><<<grid, 256, FL.total, c->stream>>>(p);
+                if (!prep_kernel(front_kernel<256, 2, false>, FL.total, 7, 2)) { return false; }
+                front_kernel<256, 2, false><<<grid, 256, FL.total, on>>>(p);
             }
         } else {
             std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
             return false;
         }
         launches++;
-        if (!mark(batch, 1)) { return false; }
+        if (!mark(batch, 1, on)) { return false; }
         if (p.max_order > 0) {
             if (!prep_kernel(lpc_kernel, LL.total, 2)) { return false; }
-            lpc_kernel<<<(ncands + 31u) / 32u, 32, LL.total, c->stream>>>(p);
+            lpc_kernel<<<(ncands + 31u) / 32u, 32, LL.total, on>>>(p);
             launches++;
         }
-        if (!mark(batch, 2)) { return false; }
+        if (!mark(batch, 2, on)) { return false; }
         if (!prep_kernel(residual_kernel, RL.total, 3)) { return false; }
-        residual_kernel<<<grid, block, RL.total, c->stream>>>(p);
+        residual_kernel<<<grid, block, RL.total, on>>>(p);
         launches++;
         CU_TRY(cudaGetLastError());
         return true;
@@ -365,50 +400,57 @@ struct Runner {
     }
 
     /* OR-reduce the samples of `count` jobs into their streams and refresh every stream's shift */
-    bool launch_lshift(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t *d_snapshot)
+    bool launch_lshift(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t *d_snapshot, cudaStream_t on)
     {
-        lshift_jobs_kernel<<<count, 256, 0, c->stream>>>((StreamDev *)c->streams.p, d_jobs, pl.nch);
-        lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.num_streams, d_snapshot);
+        lshift_jobs_kernel<<<count, 256, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch);
+        lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, on>>>((StreamDev *)c->streams.p, pl.num_streams, d_snapshot);
         CU_TRY(cudaGetLastError());
         launches += 2;
         return true;
     }
 
-    /* analyse + decide a list of jobs (already on the device at d_jobs), optionally scan + emit */
+    /* analyse + decide a list of jobs (already on the device at d_jobs), optionally scan + emit, on lane `ln`.
+     * scan_after: event the output-offset scan has to wait for (the previous group's scan, on another lane);
+     * scan_done: recorded once this group's scan has run. */
     bool run_batch(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t nmax, bool emit, uint8_t *d_out, uint64_t cap,
-                   bool store_residual, size_t ev_idx, unsigned long long *h_mailbox)
+                   bool store_residual, size_t ev_idx, unsigned long long *h_mailbox, int ln = 0,
+                   cudaEvent_t scan_after = nullptr, cudaEvent_t scan_done = nullptr)
     {
+        DeviceCtx::Lane &L = c->lane[ln];
+        const cudaStream_t on = L.stream;
         LaunchParams p = base_params(pl, nmax);
         p.jobs = d_jobs; p.num_jobs = count;
         const size_t ncand = p.ncand;
-        if (!c->cand.reserve(sizeof(CandOut) * ncand * count) || !c->jobout.reserve(sizeof(JobOut) * count)) { return false; }
-        if (store_residual && !c->residual.reserve(sizeof(int32_t) * ncand * count * (size_t)p.res_stride)) { return false; }
-        if (pl.want_diag && !c->diag.reserve(sizeof(CandDiag) * ncand * count)) { return false; }
+        if (!L.cand.reserve(sizeof(CandOut) * ncand * count) || !L.jobout.reserve(sizeof(JobOut) * count)) { return false; }
+        if (store_residual && !L.residual.reserve(sizeof(int32_t) * ncand * count * (size_t)p.res_stride)) { return false; }
+        if (pl.want_diag && !L.diag.reserve(sizeof(CandDiag) * ncand * count)) { return false; }
         p.lag_stride = round_up_u32(p.max_order + 2u, 2);
-        if (!c->lags.reserve(sizeof(double) * ncand * count * (size_t)p.lag_stride)) { return false; }
-        p.lags = (double *)c->lags.p;
-        p.cand = (CandOut *)c->cand.p; p.jobout = (JobOut *)c->jobout.p;
-        p.residual = store_residual ? (int32_t *)c->residual.p : nullptr;
-        p.diag = pl.want_diag ? (CandDiag *)c->diag.p : nullptr;
+        if (!L.lags.reserve(sizeof(double) * round_up_u32((uint32_t)(ncand * count), 32) * (size_t)p.lag_stride)) { return false; }
+        p.lags = (double *)L.lags.p;
+        p.cand = (CandOut *)L.cand.p; p.jobout = (JobOut *)L.jobout.p;
+        p.residual = store_residual ? (int32_t *)L.residual.p : nullptr;
+        p.diag = pl.want_diag ? (CandDiag *)L.diag.p : nullptr;
         p.out = d_out; p.out_capacity = cap;
         const uint32_t raw_max = 11u + (uint32_t)(((uint64_t)p.bps * nmax * p.nch) / 8u);
         p.emit_smem_bytes = raw_max;
-        if (!mark(ev_idx, 0)) { return false; }
-        if (!launch_analyse(p, ev_idx)) { return false; }
-        if (!mark(ev_idx, 3)) { return false; }
-        decide_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(p);
+        if (!mark(ev_idx, 0, on)) { return false; }
+        if (!launch_analyse(p, ev_idx, on)) { return false; }
+        if (!mark(ev_idx, 3, on)) { return false; }
+        decide_kernel<<<(count + 127) / 128, 128, 0, on>>>(p);
         launches++;
         if (emit) {
-            scan_kernel<<<1, 1024, 0, c->stream>>>(p);
-            if (h_mailbox) { CU_TRY(cudaMemcpyAsync(h_mailbox, p.running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream)); }
+            if (scan_after) { CU_TRY(cudaStreamWaitEvent(on, scan_after, 0)); }
+            scan_kernel<<<1, 1024, 0, on>>>(p);
+            if (h_mailbox) { CU_TRY(cudaMemcpyAsync(h_mailbox, p.running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, on)); }
+            if (scan_done) { CU_TRY(cudaEventRecord(scan_done, on)); }      /* after the mailbox copy: the next scan overwrites running[0] */
             const uint32_t smem = round_up_u32(raw_max, 4) + 16u;
             if ((int)smem > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] block too large for the emit stage (%u bytes)\n", smem); return false; }
             if (c->smem_set[4] != smem) { CU_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); c->smem_set[4] = smem; }
-            emit_kernel<<<count, kThreads, smem, c->stream>>>(p);
+            emit_kernel<<<count, kThreads, smem, on>>>(p);
             launches += 2;
         }
         CU_TRY(cudaGetLastError());
-        if (!mark(ev_idx, 4)) { return false; }
+        if (!mark(ev_idx, 4, on)) { return false; }
         return true;
     }
 
@@ -505,11 +547,16 @@ struct Runner {
                 jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
             }
         }
-        const bool pipelined = io && !pl.variable && !pl.size_only && pl.allow_pipeline && !pl.use_fixed_lshift && jobs.size() >= 2048;
-        const uint32_t per_batch = jobs_per_batch(pl, max_block);
+        /* large fixed-block calls are split into groups that alternate between the lanes (compute streams);
+         * with host I/O every group additionally has its own H2D / D2H copies on the copy streams */
+        const bool split = !pl.variable && !pl.size_only && pl.allow_pipeline && jobs.size() >= 2048 && (io || (c->split_device && c->lanes > 1));
+        const bool pipelined = split && io && !pl.use_fixed_lshift;
+        const int lanes = split ? c->lanes : 1;
+        const uint32_t per_batch = jobs_per_batch(pl, max_block) / (uint32_t)lanes;
         uint32_t group = per_batch;
-        if (pipelined) { group = std::min<uint32_t>(per_batch, std::max<uint32_t>(1024u, (uint32_t)((jobs.size() + 7) / 8))); }
+        if (split) { group = std::min<uint32_t>(per_batch, std::max<uint32_t>(512u, (uint32_t)((jobs.size() + c->groups - 1) / c->groups))); }
         const size_t num_groups = (jobs.size() + group - 1) / group;
+        c->lane[0].stream = c->stream;                     /* lane 0 is the caller's stream */
 
         if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
@@ -542,7 +589,7 @@ struct Runner {
         uint32_t nmax = 1;
         if (!pipelined && !pl.use_fixed_lshift) {
             /* exact offset_lshift of every stream before any analysis */
-            if (!launch_lshift(pl, (const Job *)c->jobs.p, (uint32_t)jobs.size(), nullptr)) { return SRLA_APIRESULT_NG; }
+            if (!launch_lshift(pl, (const Job *)c->jobs.p, (uint32_t)jobs.size(), nullptr, c->stream)) { return SRLA_APIRESULT_NG; }
         }
 
         if (pl.variable) {
@@ -573,7 +620,7 @@ struct Runner {
                 const uint32_t cnt = (uint32_t)std::min<size_t>(per_batch, cand_jobs.size() - b);
                 if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, max_block, false, nullptr, 0, false, ev_idx++, nullptr)) { return SRLA_APIRESULT_NG; }
                 if (!c->h_jobout.reserve(sizeof(JobOut) * cnt)) { return SRLA_APIRESULT_NG; }
-                if (cudaMemcpyAsync(c->h_jobout.p, c->jobout.p, sizeof(JobOut) * cnt, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
+                if (cudaMemcpyAsync(c->h_jobout.p, c->lane[0].jobout.p, sizeof(JobOut) * cnt, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
                     || cudaStreamSynchronize(c->stream) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] size pass failed: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
                 const JobOut *jo = (const JobOut *)c->h_jobout.p;
                 for (uint32_t k = 0; k < cnt; k++) { if (jo[k].status) { return SRLA_APIRESULT_NG; } est[b + k] = jo[k].estimate_bytes; }
@@ -612,19 +659,39 @@ struct Runner {
             while (grp_done.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } grp_done.push_back(e); }
             if (!c->h_mailbox.reserve(sizeof(unsigned long long) * (groups_now + 1))) { return SRLA_APIRESULT_NG; }
             mailbox = (unsigned long long *)c->h_mailbox.p;
-            if (!c->snapshot.reserve(sizeof(uint32_t) * groups_now * pl.num_streams)) { return SRLA_APIRESULT_NG; }
+            if (!c->snapshot.reserve(sizeof(uint32_t) * (groups_now + 1) * pl.num_streams)) { return SRLA_APIRESULT_NG; }
             d_snap = (uint32_t *)c->snapshot.p;
+        }
+        const int lanes_now = pl.variable ? 1 : lanes;
+        if (lanes_now > 1) {
+            /* fork: the other lanes start after everything queued on the caller's stream so far (uploads, shift) */
+            if (cudaEventRecord(c->ev_fork, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+            for (int l = 1; l < lanes_now; l++) { if (cudaStreamWaitEvent(c->lane[l].stream, c->ev_fork, 0) != cudaSuccess) { return SRLA_APIRESULT_NG; } }
+            while (c->ev_scan.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } c->ev_scan.push_back(e); }
         }
         for (size_t g = 0; g < groups_now; g++) {
             const size_t j0 = g * group_now;
             const uint32_t cnt = (uint32_t)std::min<size_t>(group_now, jobs.size() - j0);
+            const int ln = (int)(g % (size_t)lanes_now);
+            const cudaStream_t on = c->lane[ln].stream;
             if (pipelined) {
-                if (cudaStreamWaitEvent(c->stream, h2d_done[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-                if (!launch_lshift(pl, (const Job *)c->jobs.p + j0, cnt, d_snap + g * pl.num_streams)) { return SRLA_APIRESULT_NG; }
+                if (cudaStreamWaitEvent(on, h2d_done[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                if (!launch_lshift(pl, (const Job *)c->jobs.p + j0, cnt, d_snap + g * pl.num_streams, on)) { return SRLA_APIRESULT_NG; }
             }
+            const bool chain = lanes_now > 1;
             if (!run_batch(pl, (const Job *)c->jobs.p + j0, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++,
-                           pipelined ? mailbox + g : nullptr)) { return SRLA_APIRESULT_NG; }
-            if (pipelined && cudaEventRecord(grp_done[g], c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                           pipelined ? mailbox + g : nullptr, ln,
+                           (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr)) { return SRLA_APIRESULT_NG; }
+            if (pipelined && cudaEventRecord(grp_done[g], on) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        }
+        /* join: the caller's stream continues after every lane */
+        for (int l = 1; l < lanes_now; l++) {
+            if (cudaEventRecord(c->lane[l].done, c->lane[l].stream) != cudaSuccess || cudaStreamWaitEvent(c->stream, c->lane[l].done, 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        }
+        if (pipelined) {
+            /* the shift every stream really has, once all groups have been OR-ed in (slot groups_now) */
+            lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, c->stream>>>((StreamDev *)c->streams.p, pl.num_streams, d_snap + groups_now * pl.num_streams);
+            launches++;
         }
         if (cudaEventRecord(c->ev_end, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
 
@@ -644,12 +711,12 @@ struct Runner {
         /* ---- results ---- */
         const size_t small_bytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t);
         const size_t sb_bytes = sizeof(unsigned long long) * (pl.num_streams + 1);
-        const size_t snap_bytes = pipelined ? sizeof(uint32_t) * groups_now * pl.num_streams : 0;
+        const size_t snap_bytes = pipelined ? sizeof(uint32_t) * (groups_now + 1) * pl.num_streams : 0;
         if (!c->h_result.reserve(small_bytes + sb_bytes + sizeof(JobOut) + snap_bytes + 64)) { return SRLA_APIRESULT_NG; }
         unsigned char *hs = (unsigned char *)c->h_result.p;
         cudaMemcpyAsync(hs, c->misc.p, small_bytes, cudaMemcpyDeviceToHost, c->stream);
         cudaMemcpyAsync(hs + small_bytes, c->stream_begin.p, sb_bytes, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(hs + small_bytes + sb_bytes, c->jobout.p, sizeof(JobOut), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hs + small_bytes + sb_bytes, c->lane[0].jobout.p, sizeof(JobOut), cudaMemcpyDeviceToHost, c->stream);
         if (pipelined) { cudaMemcpyAsync(hs + small_bytes + sb_bytes + sizeof(JobOut), c->snapshot.p, snap_bytes, cudaMemcpyDeviceToHost, c->stream); }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || (pipelined && (cudaStreamSynchronize(c->d2h_stream) != cudaSuccess || cudaStreamSynchronize(c->copy_stream) != cudaSuccess))) {
             std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -662,9 +729,9 @@ struct Runner {
         if (pipelined) {
             /* did every group run with the final shift of the streams it touched? */
             const uint32_t *snap = (const uint32_t *)(hs + small_bytes + sb_bytes + sizeof(JobOut));
-            const uint32_t *fin = snap + (groups_now - 1) * pl.num_streams;
+            const uint32_t *fin = snap + groups_now * pl.num_streams;
             bool redo = false;
-            for (size_t g = 0; g + 1 < groups_now && !redo; g++) {
+            for (size_t g = 0; g < groups_now && !redo; g++) {
                 const size_t j0 = g * group_now, j1 = std::min(jobs.size(), j0 + group_now);
                 for (size_t j = j0; j < j1; j++) { const uint32_t s = jobs[j].stream; if (snap[g * pl.num_streams + s] != fin[s]) { redo = true; break; } }
             }
@@ -1032,6 +1099,7 @@ SRLAApiResult SRLAB200_SetStream(struct SRLAEncoder *encoder, void *cuda_stream)
 {
     if (encoder == NULL || encoder->magic != kEncoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
     encoder->ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : encoder->ctx->own_stream;
+    encoder->ctx->lane[0].stream = encoder->ctx->stream;
     return SRLA_APIRESULT_OK;
 }
 
@@ -1061,9 +1129,9 @@ SRLAApiResult SRLAB200_TestAnalyseChannel(
     if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0, nullptr)) { return SRLA_APIRESULT_NG; }
     CandOut co; CandDiag dg;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess
-        || cudaMemcpy(&co, c->cand.p, sizeof(co), cudaMemcpyDeviceToHost) != cudaSuccess
-        || cudaMemcpy(&dg, c->diag.p, sizeof(dg), cudaMemcpyDeviceToHost) != cudaSuccess
-        || cudaMemcpy(residual, c->residual.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        || cudaMemcpy(&co, c->lane[0].cand.p, sizeof(co), cudaMemcpyDeviceToHost) != cudaSuccess
+        || cudaMemcpy(&dg, c->lane[0].diag.p, sizeof(dg), cudaMemcpyDeviceToHost) != cudaSuccess
+        || cudaMemcpy(residual, c->lane[0].residual.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
         std::fprintf(stderr, "[srla_b200] TestAnalyseChannel failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         return SRLA_APIRESULT_NG;
     }
