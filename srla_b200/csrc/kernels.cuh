@@ -156,26 +156,24 @@ __device__ __forceinline__ uint32_t fft_slot(uint32_t i) { return i ^ ((i >> 4) 
 
 struct Twiddle3 { double2 w1, w2, w3; };
 /* table of one stage size ns: w1[ns/4], w2[ns/4], w3[ns/4] (host_tables.h) */
-template <bool kInv>
 __device__ __forceinline__ Twiddle3 load_twiddle(const double2 *table, uint32_t quarter, uint32_t p)
 {
-    const bool inverse = kInv;
     Twiddle3 t;
     t.w1 = __ldg(table + p); t.w2 = __ldg(table + quarter + p); t.w3 = __ldg(table + 2u * quarter + p);
-    if (inverse) { t.w1.y = -t.w1.y; t.w2.y = -t.w2.y; t.w3.y = -t.w3.y; }      /* the recurrence is sign-symmetric */
     return t;
 }
 
-/* one radix-4 butterfly, fft.c:93-105 */
-template <bool kInv>
+/* one radix-4 butterfly of the FORWARD transform, fft.c:93-105.
+ * The inverse transform (flag = +1: conjugate twiddles, opposite rotation) is evaluated as
+ * conj(forward(conj(x))): IEEE round-to-nearest is sign-symmetric, so every intermediate of that
+ * evaluation is the exact conjugate of the reference's and the results are bit-identical -- and the
+ * kernel carries one copy of the transform code instead of two (it is bound by instruction fetch). */
 __device__ __forceinline__ void butterfly4(const double2 a, const double2 b, const double2 c, const double2 d, const Twiddle3 &w,
                                            double2 &y0, double2 &y1, double2 &y2, double2 &y3)
 {
-    const bool inverse = kInv;
     const double2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
-    /* j * (b - d), j = (0, -flag): forward (0,+1) -> (-im, re); inverse (0,-1) -> (im, -re).
-     * (the reference's 0.0 * x terms only affect the sign of zeros) */
-    const double2 jbmd = inverse ? make_double2(bmd.y, -bmd.x) : make_double2(-bmd.y, bmd.x);
+    /* j * (b - d), j = (0, +1) -> (-im, re)   (the reference's 0.0 * x terms only affect the sign of zeros) */
+    const double2 jbmd = make_double2(-bmd.y, bmd.x);
     y0 = cadd(apc, bpd);
     y1 = cmul(w.w1, csub(amc, jbmd));
     y2 = cmul(w.w2, csub(apc, bpd));
@@ -220,14 +218,17 @@ struct WindowSource {
  * them -- the surviving outputs are the reference's expression trees unchanged.
  * `src` (forward transform, M >= 16 only): the first pass takes its inputs from the windowed samples
  * instead of x, which saves one full write + read of the buffer. */
-/* one fused pair of radix-4 stages (sizes nn and nn/4, output stride 1 << lgs) */
-template <bool kInv, bool kPre, bool kFromSamples, bool kPrune>
-__device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs, const LaunchParams &p,
-                                              const uint32_t need, const WindowSource<kPre> *src)
+/* one fused pair of radix-4 stages (sizes nn and nn/4, output stride 1 << lgs).
+ * `need`: only outputs 0..need-1 of the whole transform are required (M = all); in the last pair pass an
+ * output at position o is read later only when (o mod (16 << lgs)) < need, so butterflies that cannot
+ * reach a required output are skipped -- the surviving outputs are the reference's expression trees. */
+template <bool kPre, bool kFromSamples>
+__device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs,
+                                           const double2 *tw_a, const double2 *tw_b, const uint32_t need, const WindowSource<kPre> src)
 {
+    /* a real call, not inlined: each pass gets its own register allocation and the kernel one copy of it */
     const uint32_t tid = threadIdx.x;
     const uint32_t units = M >> 4;
-    const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
     const bool last_pair = (nn < 256u);          /* outputs feed the tail pass (or are final) */
     const bool active = tid < units;
     const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
@@ -238,26 +239,24 @@ __device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, cons
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
-                v[jp][j] = kFromSamples ? src->element(e) : x[fft_slot(e)];
+                v[jp][j] = kFromSamples ? src.element(e) : x[fft_slot(e)];
             }
         }
     }
     if (!kFromSamples) { __syncthreads(); }      /* in place: every input is in registers before any output is stored */
     if (active) {
-        const double2 *tw_a = p.tw_complex + p.tw_complex_off[lgn];
-        const double2 *tw_b = p.tw_complex + p.tw_complex_off[lgn - 2u];
         double2 y[4][4];
         #pragma unroll
         for (int jp = 0; jp < 4; ++jp) {
-            const Twiddle3 wa = load_twiddle<kInv>(tw_a, nn >> 2, p0 + (uint32_t)jp * (nn >> 4));
-            butterfly4<kInv>(v[jp][0], v[jp][1], v[jp][2], v[jp][3], wa, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
+            const Twiddle3 wa = load_twiddle(tw_a, nn >> 2, p0 + (uint32_t)jp * (nn >> 4));
+            butterfly4(v[jp][0], v[jp][1], v[jp][2], v[jp][3], wa, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
         }
-        const Twiddle3 wb = load_twiddle<kInv>(tw_b, nn >> 4, p0);
-        if (!kPrune || !last_pair || need >= M) {
+        const Twiddle3 wb = load_twiddle(tw_b, nn >> 4, p0);
+        if (!last_pair || need >= M) {
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 double2 z0, z1, z2, z3;
-                butterfly4<kInv>(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
+                butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
                 const uint32_t o = q + ((uint32_t)j << lgs) + ((16u * p0) << lgs);
                 x[fft_slot(o)]                = z0;
                 x[fft_slot(o + (4u << lgs))]  = z1;
@@ -265,14 +264,13 @@ __device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, cons
                 x[fft_slot(o + (12u << lgs))] = z3;
             }
         } else {
-            /* an output at position o is read later only when (o mod (16 << lgs)) < need */
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t low = q + ((uint32_t)j << lgs);
                 const uint32_t o = low + ((16u * p0) << lgs);
                 if (low + (4u << lgs) < need) {
                     double2 z0, z1, z2, z3;
-                    butterfly4<kInv>(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
+                    butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
                     x[fft_slot(o)]                = z0;
                     x[fft_slot(o + (4u << lgs))]  = z1;
                     x[fft_slot(o + (8u << lgs))]  = z2;
@@ -286,105 +284,54 @@ __device__ __forceinline__ void fft_pair_pass(double2 *x, const uint32_t M, cons
     __syncthreads();
 }
 
-/* complex FFT of M points (M a power of two, M/16 <= blockDim.x, M/8 <= blockDim.x when M = 8 * 4^k).
- * `need`: only outputs 0..need-1 are required (M = all).  The autocorrelation reads just the first lags
- * of the inverse transform, so its last two passes skip every butterfly none of whose outputs can reach
- * them -- the surviving outputs are the reference's expression trees unchanged.
- * `src` (forward transform, M >= 16 only): the first pass takes its inputs from the windowed samples
- * instead of x, which saves one full write + read of the buffer. */
-template <bool kInv, bool kPre>
-__device__ __forceinline__ void complex_fft_inplace(double2 *x, const uint32_t M, const LaunchParams &p, const uint32_t need,
-                                                    const WindowSource<kPre> *src)
+/* the stages left after the fused pairs: nn = 8 (radix-4 + radix-2), 4 (radix-4) or 2 (radix-2).  A tail unit
+ * reads and writes exactly the same positions (u + k * s), so units are independent of each other: no barrier
+ * between loads and stores, and a thread walks its units one at a time.  Units beyond `need` are skipped. */
+__device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const uint32_t nn, const double2 *tw8, const double2 *tw4, const uint32_t need)
 {
-    const uint32_t tid = threadIdx.x;
-    uint32_t nn = M, lgs = 0;
-    if (src != nullptr && nn >= 16u) {
-        fft_pair_pass<kInv, kPre, true, kInv>(x, M, nn, lgs, p, need, src);
-        nn >>= 4; lgs += 4;
-    }
-    while (nn >= 16u) {
-        fft_pair_pass<kInv, kPre, false, kInv>(x, M, nn, lgs, p, need, src);
-        nn >>= 4; lgs += 4;
-    }
-    /* tail passes: up to two work units per thread (all loads precede all stores: in place is safe) */
-    const uint32_t T = blockDim.x;
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
     if (nn == 8u) {
         /* radix-4 stage of size 8 (s = M/8) fused with the final radix-2 stage (fft.c:114-123) */
         const uint32_t s = M >> 3;
         const uint32_t live = (need < s) ? need : s;
-        double2 v[2][2][4];
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t u = tid + (uint32_t)r * T;
-            if (u < live) {
+        const Twiddle3 w0 = load_twiddle(tw8, 2u, 0u), w1 = load_twiddle(tw8, 2u, 1u);
+        #pragma unroll 1
+        for (uint32_t u = tid; u < live; u += T) {
+            double2 v[2][4], y[2][4];
+            #pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
                 #pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) { v[r][pp][j] = x[fft_slot((uint32_t)pp * s + u + (uint32_t)j * (M >> 2))]; }
-                }
+                for (int j = 0; j < 4; ++j) { v[pp][j] = x[fft_slot((uint32_t)pp * s + u + (uint32_t)j * (M >> 2))]; }
+            }
+            butterfly4(v[0][0], v[0][1], v[0][2], v[0][3], w0, y[0][0], y[0][1], y[0][2], y[0][3]);
+            butterfly4(v[1][0], v[1][1], v[1][2], v[1][3], w1, y[1][0], y[1][1], y[1][2], y[1][3]);
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                x[fft_slot(u + (uint32_t)j * s)]            = cadd(y[0][j], y[1][j]);
+                x[fft_slot(u + (uint32_t)j * s + (M >> 1))] = csub(y[0][j], y[1][j]);
             }
         }
-        __syncthreads();
-        const double2 *tw = p.tw_complex + p.tw_complex_off[3];
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t u = tid + (uint32_t)r * T;
-            if (u < live) {
-                double2 y[2][4];
-                { const Twiddle3 w0 = load_twiddle<kInv>(tw, 2u, 0u);
-                  butterfly4<kInv>(v[r][0][0], v[r][0][1], v[r][0][2], v[r][0][3], w0, y[0][0], y[0][1], y[0][2], y[0][3]); }
-                { const Twiddle3 w1 = load_twiddle<kInv>(tw, 2u, 1u);
-                  butterfly4<kInv>(v[r][1][0], v[r][1][1], v[r][1][2], v[r][1][3], w1, y[1][0], y[1][1], y[1][2], y[1][3]); }
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    x[fft_slot(u + (uint32_t)j * s)]            = cadd(y[0][j], y[1][j]);
-                    x[fft_slot(u + (uint32_t)j * s + (M >> 1))] = csub(y[0][j], y[1][j]);
-                }
-            }
-        }
-        __syncthreads();
     } else if (nn == 4u) {
         /* single radix-4 stage of size 4 (s = M/4): twiddle index 0 only */
         const uint32_t s = M >> 2;
         const uint32_t live = (need < s) ? need : s;
-        double2 v[2][4];
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t u = tid + (uint32_t)r * T;
-            if (u < live) {
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) { v[r][j] = x[fft_slot(u + (uint32_t)j * s)]; }
-            }
+        const Twiddle3 w = load_twiddle(tw4, 1u, 0u);
+        #pragma unroll 1
+        for (uint32_t u = tid; u < live; u += T) {
+            double2 y0, y1, y2, y3;
+            butterfly4(x[fft_slot(u)], x[fft_slot(u + s)], x[fft_slot(u + 2u * s)], x[fft_slot(u + 3u * s)], w, y0, y1, y2, y3);
+            x[fft_slot(u)] = y0; x[fft_slot(u + s)] = y1; x[fft_slot(u + 2u * s)] = y2; x[fft_slot(u + 3u * s)] = y3;
         }
-        __syncthreads();
-        const Twiddle3 w = load_twiddle<kInv>(p.tw_complex + p.tw_complex_off[2], 1u, 0u);
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t u = tid + (uint32_t)r * T;
-            if (u < live) {
-                double2 y0, y1, y2, y3;
-                butterfly4<kInv>(v[r][0], v[r][1], v[r][2], v[r][3], w, y0, y1, y2, y3);
-                x[fft_slot(u)] = y0; x[fft_slot(u + s)] = y1; x[fft_slot(u + 2u * s)] = y2; x[fft_slot(u + 3u * s)] = y3;
-            }
-        }
-        __syncthreads();
     } else if (nn == 2u) {
         const uint32_t s = M >> 1;
         const uint32_t live = (need < s) ? need : s;
-        double2 v[2][2];
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t u = tid + (uint32_t)r * T;
-            if (u < live) { v[r][0] = x[fft_slot(u)]; v[r][1] = x[fft_slot(u + s)]; }
+        #pragma unroll 1
+        for (uint32_t u = tid; u < live; u += T) {
+            const double2 a = x[fft_slot(u)], b = x[fft_slot(u + s)];
+            x[fft_slot(u)] = cadd(a, b); x[fft_slot(u + s)] = csub(a, b);
         }
-        __syncthreads();
-        #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const uint32_t u = tid + (uint32_t)r * T;
-            if (u < live) { x[fft_slot(u)] = cadd(v[r][0], v[r][1]); x[fft_slot(u + s)] = csub(v[r][0], v[r][1]); }
-        }
-        __syncthreads();
     }
+    __syncthreads();
 }
 
 /* Welch window (lpc.c:252-266) + autocorrelation through the FFT (lpc.c:330-376).
@@ -415,73 +362,88 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
     const uint32_t M = N >> 1;
     WindowSource<kPre> ws;
     ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = unit; ws.div = div; ws.dn1 = (double)(int32_t)(n - 1u);
-    if (M >= 16u) {
-        complex_fft_inplace<false, kPre>(cx, M, p, M, &ws);      /* the first pass windows the samples itself */
-    } else {
-        for (uint32_t c = tid; c < M; c += nthreads) { cx[fft_slot(c)] = ws.element(c); }
-        __syncthreads();
-        complex_fft_inplace<false, kPre>(cx, M, p, M, nullptr);
-    }
-    /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three
-     * only touch the element pair (i, N/2 - i) */
-    {
-        const uint32_t lgN = 31u - (uint32_t)__clz((int)N);
-        const double2 *tw = p.tw_real + p.tw_real_off[lgN];
-        const uint32_t quarter = N >> 2;
-        for (uint32_t i = 1u + tid; i <= quarter; i += nthreads) {
-            const double2 w = __ldg(tw + (i - 1u));
-            const double wr = w.x, wi_f = w.y, wi_b = -w.y;
-            const uint32_t lo = i, hi = M - i;
-            const double2 xl = cx[fft_slot(lo)], xh = cx[fft_slot(hi)];
-            /* forward, flag = -1: c2 = -0.5 */
-            double f1, f2, f3, f4;
-            {
-                const double c2 = -0.5;
-                const double h1r = 0.5 * (xl.x + xh.x);
-                const double h1i = 0.5 * (xl.y - xh.y);
-                const double h2r = -c2 * (xl.y + xh.y);
-                const double h2i = c2 * (xl.x - xh.x);
-                f1 = h1r + (wr * h2r) - (wi_f * h2i);
-                f2 = h1i + (wr * h2i) + (wi_f * h2r);
-                f3 = h1r - (wr * h2r) + (wi_f * h2i);
-                f4 = -h1i + (wr * h2i) + (wi_f * h2r);
+    const uint32_t want = (nlags < N) ? nlags : N;
+    /* dir 0: forward transform of the windowed samples; dir 1: the inverse transform, evaluated as the
+     * conjugate of a forward transform of conjugated data (see butterfly4) so both directions share one
+     * copy of the pass code */
+    #pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+        uint32_t nn = M, lgs = 0;
+        const uint32_t need = dir ? ((want + 1u) >> 1) : M;
+        if (dir == 0) {
+            if (M >= 16u) {
+                const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
+                fft_pair_pass<kPre, true>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, ws);   /* windows the samples itself */
+                nn >>= 4; lgs += 4;
+            } else {
+                for (uint32_t c = tid; c < M; c += nthreads) { cx[fft_slot(c)] = ws.element(c); }
+                __syncthreads();
             }
-            /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
-            double p_lo, p_hi;
-            if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
-            else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
-            /* inverse, flag = +1: c2 = +0.5, imaginary parts are 0.0 */
-            {
-                const double c2 = 0.5;
-                const double zl = 0.0, zh = 0.0;
-                const double h1r = 0.5 * (p_lo + p_hi);
-                const double h1i = 0.5 * (zl - zh);
-                const double h2r = -c2 * (zl + zh);
-                const double h2i = c2 * (p_lo - p_hi);
-                const double g1 = h1r + (wr * h2r) - (wi_b * h2i);
-                const double g2 = h1i + (wr * h2i) + (wi_b * h2r);
-                const double g3 = h1r - (wr * h2r) + (wi_b * h2i);
-                const double g4 = -h1i + (wr * h2i) + (wi_b * h2r);
-                if (lo != hi) { cx[fft_slot(lo)] = make_double2(g1, g2); }
-                cx[fft_slot(hi)] = make_double2(g3, g4);
+        } else {
+            /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three only touch
+             * the element pair (i, N/2 - i).  The inverse split's outputs are stored CONJUGATED. */
+            const uint32_t lgN = 31u - (uint32_t)__clz((int)N);
+            const double2 *tw = p.tw_real + p.tw_real_off[lgN];
+            const uint32_t quarter = N >> 2;
+            for (uint32_t i = 1u + tid; i <= quarter; i += nthreads) {
+                const double2 w = __ldg(tw + (i - 1u));
+                const double wr = w.x, wi_f = w.y, wi_b = -w.y;
+                const uint32_t lo = i, hi = M - i;
+                const double2 xl = cx[fft_slot(lo)], xh = cx[fft_slot(hi)];
+                /* forward, flag = -1: c2 = -0.5 */
+                double f1, f2, f3, f4;
+                {
+                    const double c2 = -0.5;
+                    const double h1r = 0.5 * (xl.x + xh.x);
+                    const double h1i = 0.5 * (xl.y - xh.y);
+                    const double h2r = -c2 * (xl.y + xh.y);
+                    const double h2i = c2 * (xl.x - xh.x);
+                    f1 = h1r + (wr * h2r) - (wi_f * h2i);
+                    f2 = h1i + (wr * h2i) + (wi_f * h2r);
+                    f3 = h1r - (wr * h2r) + (wi_f * h2i);
+                    f4 = -h1i + (wr * h2i) + (wi_f * h2r);
+                }
+                /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
+                double p_lo, p_hi;
+                if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
+                else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
+                /* inverse, flag = +1: c2 = +0.5, imaginary parts are 0.0 */
+                {
+                    const double c2 = 0.5;
+                    const double zl = 0.0, zh = 0.0;
+                    const double h1r = 0.5 * (p_lo + p_hi);
+                    const double h1i = 0.5 * (zl - zh);
+                    const double h2r = -c2 * (zl + zh);
+                    const double h2i = c2 * (p_lo - p_hi);
+                    const double g1 = h1r + (wr * h2r) - (wi_b * h2i);
+                    const double g2 = h1i + (wr * h2i) + (wi_b * h2r);
+                    const double g3 = h1r - (wr * h2r) + (wi_b * h2i);
+                    const double g4 = -h1i + (wr * h2i) + (wi_b * h2r);
+                    if (lo != hi) { cx[fft_slot(lo)] = make_double2(g1, -g2); }
+                    cx[fft_slot(hi)] = make_double2(g3, -g4);
+                }
             }
+            if (tid == 0) {
+                const double2 dc = cx[0];
+                const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
+                const double q0 = f0 * f0, q1 = f1 * f1;
+                cx[0] = make_double2(0.5 * (q0 + q1), -(0.5 * (q0 - q1)));
+            }
+            __syncthreads();
         }
-        if (tid == 0) {
-            const double2 dc = cx[0];
-            const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
-            const double q0 = f0 * f0, q1 = f1 * f1;
-            cx[0] = make_double2(0.5 * (q0 + q1), 0.5 * (q0 - q1));
+        #pragma unroll 1
+        while (nn >= 16u) {
+            const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
+            fft_pair_pass<kPre, false>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, ws);
+            nn >>= 4; lgs += 4;
         }
-        __syncthreads();
+        fft_tail_pass(cx, M, nn, p.tw_complex + p.tw_complex_off[3], p.tw_complex + p.tw_complex_off[2], need);
     }
-    {
-        const uint32_t want = (nlags < N) ? nlags : N;
-        complex_fft_inplace<true, kPre>(cx, M, p, (want + 1u) >> 1, nullptr);
-    }
+    /* the buffer holds the conjugate of the reference's inverse transform: odd lags are -imag */
     const double scale = job.ac_scale;
     for (uint32_t i = tid; i < nlags; i += nthreads) {
         double v = 0.0;
-        if (i < N) { const double2 e = cx[fft_slot(i >> 1)]; v = ((i & 1u) ? e.y : e.x) * scale; }
+        if (i < N) { const double2 e = cx[fft_slot(i >> 1)]; v = ((i & 1u) ? -e.y : e.x) * scale; }
         lags[(size_t)i * lag_step] = v;
     }
     __syncthreads();
