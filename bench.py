@@ -214,8 +214,9 @@ class ClockSampler:
 
 
 def load_traffic():
-    """dram bytes per analyse-kernel launch from the committed ncu --set full summary, if present."""
-    path = os.path.join(ROOT, "profiles", "analyse_kernel_full.json")
+    """Per-kernel figures of the committed `ncu --set full` capture (profiles/ncu_kernels.json, written by
+    tools/ncu_summary.py --traffic from the same bench command): dram bytes per launch, pipe utilisation."""
+    path = os.path.join(ROOT, "profiles", "ncu_kernels.json")
     try:
         with open(path) as f:
             return json.load(f)
@@ -341,6 +342,32 @@ def main() -> None:
     h2d = CHANNELS * stride * 2
     d2h = int(offs[1])
 
+    # ---- the reference's own entry point: SRLAEncoder_EncodeWhole(int32_t *const *input, ...), pageable host arrays ----
+    ref_api = None
+    if rank == 0 and world == 1:
+        pcm32 = np.ascontiguousarray(pcm_np.astype(np.int32))
+        rows = (C.POINTER(C.c_int32) * CHANNELS)()
+        for ch in range(CHANNELS):
+            rows[ch] = C.cast(pcm32[ch].ctypes.data, C.POINTER(C.c_int32))
+        out_np = np.empty(cap, dtype=np.uint8)
+        size = C.c_uint32(0)
+        lib.SRLAEncoder_EncodeWhole.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32)), C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+        best = None
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rc = lib.SRLAEncoder_EncodeWhole(enc.handle, rows, nsamp, out_np.ctypes.data, min(cap, 0xffffffff), C.byref(size), None)
+            dt = time.perf_counter() - t0
+            assert rc == E.OK, rc
+            if it > 0:
+                best = dt if best is None else min(best, dt)
+        ref_api = {"value": samples_per_step / best / 1e6, "unit": "Msamples/s", "ms_per_step": best * 1e3,
+                   "h2d_bytes_per_step": int(pcm32.nbytes), "d2h_bytes_per_step": int(size.value),
+                   "api": "SRLAEncoder_EncodeWhole (include/srla_encoder.h:74-80 signature: planar int32 PCM in pageable host memory, "
+                          "host output buffer; wall clock, best of 2 after one warm-up)",
+                   "identical_to_streams_api": bool(bytes(out_np[:size.value]) == bytes(h_out[:int(offs[1])].numpy().tobytes()))}
+        del pcm32
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -357,14 +384,16 @@ def main() -> None:
     an = kernel_ms[dominant]
     achieved = alg_bytes / (an * 1e-3) / 1e9
     traffic = load_traffic()
+    ncu_dom = (traffic or {}).get(dominant) or {}
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": ((traffic or {}).get(dominant) or {}).get("dram_bytes_per_launch"),
+                "traffic": ncu_dom.get("dram_bytes_per_launch"),
+                "ncu": {k: v for k, v in ncu_dom.items() if k != "dram_bytes_per_launch"} or None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": an,
                 "share_of_step": an / (ms_total / args.steps), "all_kernels_ms": kernel_ms,
                 "whole_step_achieved_gbs": alg_bytes / (ms_total / args.steps * 1e-3) / 1e9,
-                "note": "compute-bound stage (FP64 FFT + int32 FIR + Rice search at ~100 ops/byte): the HBM fraction is "
-                        "expected to be low; see DESIGN.md for the issue-rate ceilings"}
+                "note": "compute-bound path (bit-exact non-FMA FP64 FFT + int32 FIR + Rice search, ~100 ops per algorithmic byte): "
+                        "the HBM fraction is low by construction; DESIGN.md section 3 gives the issue-rate ceilings that bind"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
@@ -387,7 +416,9 @@ def main() -> None:
             "dtype": "int32+f64", "data": "synthetic", "config": workload_config(args.blocks),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / e2e_steps, "api": "SRLAB200_EncodeStreamsHost (pinned int16 host PCM in, pinned host bytes out)"},
+                    "ms_per_step": ms_e2e / e2e_steps, "api": "SRLAB200_EncodeStreamsHost (pinned int16 host PCM in, pinned host bytes out; "
+                    "groups of blocks pipelined over copy streams and compute lanes)"},
+            "e2e_reference_api": ref_api,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -11,6 +11,9 @@
  * There is deliberately no CPU encode path in this file: without a CUDA device Create() fails.
  */
 #include <algorithm>
+#include <atomic>
+#include <memory>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -92,10 +95,13 @@ struct DeviceCtx {
     int lanes = 3;                 /* SRLA_B200_LANES */
     int groups = 8;                /* SRLA_B200_GROUPS: groups a large call is split into */
     int sized_carveout = 1;        /* SRLA_B200_CARVE=max: every kernel asks for the maximum shared-memory carve-out */
+    int ramp = 1;                  /* SRLA_B200_RAMP=0: uniform groups on the host path */
+    int trace = 0;                 /* SRLA_B200_TRACE=1: print the per-group timeline of every pipelined call */
     int split_device = 0;          /* SRLA_B200_SPLIT_DEVICE=1: also split device-resident calls across the lanes */
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_scan;
-    PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox;
+    PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox, h_stage;
+    int feed_threads = 8;          /* SRLA_B200_FEED_THREADS */
     DevBuf snapshot;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_grp;
@@ -149,6 +155,10 @@ bool ctx_init(DeviceCtx *c)
     CU_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     if (const char *e = std::getenv("SRLA_B200_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= kMaxLanes) { c->lanes = v; } }
     if (const char *e = std::getenv("SRLA_B200_CARVE")) { if (e[0] == 'm') { c->sized_carveout = 0; } }
+    if (const char *e = std::getenv("SRLA_B200_RAMP")) { c->ramp = std::atoi(e); }
+    { const unsigned hc = std::thread::hardware_concurrency(); c->feed_threads = (int)std::max(2u, std::min(16u, hc ? hc : 8u)); }
+    if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->feed_threads = v; } }
+    if (const char *e = std::getenv("SRLA_B200_TRACE")) { c->trace = std::atoi(e); }
     if (const char *e = std::getenv("SRLA_B200_SPLIT_DEVICE")) { c->split_device = std::atoi(e); }
     if (const char *e = std::getenv("SRLA_B200_GROUPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) { c->groups = v; } }
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -211,7 +221,7 @@ void ctx_destroy(DeviceCtx *c)
     DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
                        &c->misc, &c->stream_begin, &c->pcm, &c->out };
     for (DevBuf *b : bufs) { b->release(); }
-    c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release();
+    c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release();
     if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
 }
 
@@ -259,6 +269,47 @@ struct HostIO {
     const HostStream *streams = nullptr;   /* per-channel host pointers of every stream */
     uint8_t *out = nullptr;                /* host output buffer */
     uint64_t out_capacity = 0;
+    bool narrow = false;                   /* host samples are int32_t but the device layout is int16_t: they are
+                                              narrowed by the feeder threads into pinned staging on their way in */
+};
+
+/* Host feeder: the reference API hands over planar int32_t PCM in pageable memory.  For sources of
+ * at most 16 bits a team of host threads narrows it to int16_t into a pinned staging buffer, group by group, while
+ * the copy engine and the kernels work on the groups already staged: half the PCIe bytes, true asynchronous
+ * copies, 2-byte kernel loads.  A sample outside the int16 range (a caller breaking the bits_per_sample
+ * contract) is detected and the call falls back to the int32 layout. */
+struct Feeder {
+    struct Chunk { const int32_t *src; int16_t *dst; uint32_t count; uint32_t group; };
+    std::vector<Chunk> chunks;
+    std::unique_ptr<std::atomic<int>[]> left;      /* chunks of each group still to convert */
+    std::atomic<size_t> next{0};
+    std::atomic<int> overflow{0};
+    std::vector<std::thread> team;
+    void start(size_t num_groups, int threads)
+    {
+        left.reset(new std::atomic<int>[num_groups]);
+        for (size_t g = 0; g < num_groups; g++) { left[g].store(0); }
+        for (const Chunk &ck : chunks) { left[ck.group].fetch_add(1); }
+        for (int t = 0; t < threads; t++) { team.emplace_back([this] { work(); }); }
+    }
+    void work()
+    {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= chunks.size()) { return; }
+            const Chunk &ck = chunks[i];
+            uint32_t bad = 0;
+            for (uint32_t k = 0; k < ck.count; k++) {
+                const int32_t v = ck.src[k];
+                bad |= (uint32_t)(v + 32768) >> 16;
+                ck.dst[k] = (int16_t)v;
+            }
+            if (bad) { overflow.store(1); }
+            left[ck.group].fetch_sub(1, std::memory_order_release);
+        }
+    }
+    void wait_group(size_t g) { while (left[g].load(std::memory_order_acquire) > 0) { std::this_thread::yield(); } }
+    ~Feeder() { for (std::thread &t : team) { if (t.joinable()) { t.join(); } } }
 };
 
 /* what one call encodes */
@@ -279,6 +330,7 @@ struct Runner {
     SRLAEncoder *enc; DeviceCtx *c;
     LenCache len_cache;
     uint64_t launches = 0;
+    bool narrow_overflow = false;      /* the feeder met a sample outside int16: the caller redoes the call with the int32 layout */
 
     LaunchParams base_params(const Plan &pl, uint32_t nmax) const
     {
@@ -511,7 +563,9 @@ struct Runner {
         const size_t sb = d.sample_bytes;
         for (uint32_t ch = 0; ch < pl.nch; ch++) {
             unsigned char *dst = (unsigned char *)d.pcm + ((size_t)d.channel_stride * ch + begin) * sb;
-            const unsigned char *src = (const unsigned char *)io.streams[s].ch[ch] + (size_t)begin * sb;
+            /* narrowed input: the staging buffer mirrors the device layout byte for byte */
+            const unsigned char *src = io.narrow ? (const unsigned char *)c->h_stage.p + (dst - (unsigned char *)c->pcm.p)
+                                                 : (const unsigned char *)io.streams[s].ch[ch] + (size_t)begin * sb;
             CU_TRY(cudaMemcpyAsync(dst, src, (size_t)(end - begin) * sb, cudaMemcpyHostToDevice, on));
         }
         return true;
@@ -553,10 +607,30 @@ struct Runner {
         const bool pipelined = split && io && !pl.use_fixed_lshift;
         const int lanes = split ? c->lanes : 1;
         const uint32_t per_batch = jobs_per_batch(pl, max_block) / (uint32_t)lanes;
-        uint32_t group = per_batch;
-        if (split) { group = std::min<uint32_t>(per_batch, std::max<uint32_t>(512u, (uint32_t)((jobs.size() + c->groups - 1) / c->groups))); }
-        const size_t num_groups = (jobs.size() + group - 1) / group;
+        /* group boundaries (job indices).  With host I/O the first groups are small so the kernels start as soon
+         * as a little PCM has arrived, and the last ones are small so little output is left to copy back when the
+         * kernels finish; in between the groups are large enough to fill the machine. */
+        std::vector<size_t> gstart;
+        gstart.push_back(0);
+        if (!split) {
+            for (size_t at = per_batch; at < jobs.size(); at += per_batch) { gstart.push_back(at); }
+        } else if (pipelined && c->ramp && jobs.size() >= 4096) {
+            static const double kRamp[] = { 0.03, 0.06, 0.11, 0.15, 0.15, 0.15, 0.14, 0.11, 0.06, 0.04 };
+            double acc = 0.0;
+            for (double f : kRamp) {
+                acc += f;
+                size_t at = std::min(jobs.size(), (size_t)(acc * (double)jobs.size() + 0.5));
+                while (at - gstart.back() > per_batch) { gstart.push_back(gstart.back() + per_batch); }
+                if (at > gstart.back() && at < jobs.size()) { gstart.push_back(at); }
+            }
+        } else {
+            const size_t group = std::min<size_t>(per_batch, std::max<size_t>(512u, (jobs.size() + c->groups - 1) / c->groups));
+            for (size_t at = group; at < jobs.size(); at += group) { gstart.push_back(at); }
+        }
+        gstart.push_back(jobs.size());
+        const size_t num_groups = gstart.size() - 1;
         c->lane[0].stream = c->stream;                     /* lane 0 is the caller's stream */
+        if (io && io->narrow && !pipelined) { std::fprintf(stderr, "[srla_b200] internal: narrowed input outside the pipelined path\n"); return SRLA_APIRESULT_NG; }
 
         if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
@@ -565,21 +639,51 @@ struct Runner {
 
         /* ---- host input ---- */
         std::vector<cudaEvent_t> &h2d_done = c->ev_h2d;
+        Feeder feeder;
+        /* copies group g's samples to the device (copy stream) and records h2d_done[g] */
+        auto issue_h2d = [&](size_t g) -> bool {
+            if (io->narrow) { feeder.wait_group(g); }
+            const size_t j0 = gstart[g], j1 = gstart[g + 1];
+            size_t j = j0;
+            while (j < j1) {                                   /* one contiguous sample range per stream touched */
+                const uint32_t s = jobs[j].stream, begin = jobs[j].offset;
+                size_t k = j;
+                while (k + 1 < j1 && jobs[k + 1].stream == s) { k++; }
+                if (!h2d_range(pl, *io, s, begin, jobs[k].offset + jobs[k].nsmpl, c->copy_stream)) { return false; }
+                j = k + 1;
+            }
+            return cudaEventRecord(h2d_done[g], c->copy_stream) == cudaSuccess;
+        };
+        bool copies_async = true;      /* pinned source: the H2D of the next group is queued before this group's kernels */
         if (io) {
             if (pipelined) {
-                while (h2d_done.size() < num_groups) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } h2d_done.push_back(e); }
-                for (size_t g = 0; g < num_groups; g++) {
-                    const size_t j0 = g * group, j1 = std::min(jobs.size(), j0 + group);
-                    size_t j = j0;
-                    while (j < j1) {                                   /* one contiguous sample range per stream touched */
-                        const uint32_t s = jobs[j].stream, begin = jobs[j].offset;
-                        size_t k = j;
-                        while (k + 1 < j1 && jobs[k + 1].stream == s) { k++; }
-                        if (!h2d_range(pl, *io, s, begin, jobs[k].offset + jobs[k].nsmpl, c->copy_stream)) { return SRLA_APIRESULT_NG; }
-                        j = k + 1;
+                while (h2d_done.size() < num_groups) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, c->trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } h2d_done.push_back(e); }
+                if (io->narrow) {
+                    for (size_t g = 0; g < num_groups; g++) {
+                        size_t j = gstart[g];
+                        while (j < gstart[g + 1]) {
+                            const uint32_t s = jobs[j].stream, begin = jobs[j].offset;
+                            size_t k = j;
+                            while (k + 1 < gstart[g + 1] && jobs[k + 1].stream == s) { k++; }
+                            const uint32_t end = jobs[k].offset + jobs[k].nsmpl;
+                            const struct SRLAB200Stream &d = pl.streams[s];
+                            for (uint32_t ch = 0; ch < pl.nch; ch++) {
+                                int16_t *dst = (int16_t *)((unsigned char *)c->h_stage.p + ((unsigned char *)d.pcm - (unsigned char *)c->pcm.p)) + (size_t)d.channel_stride * ch;
+                                const int32_t *src = (const int32_t *)io->streams[s].ch[ch];
+                                for (uint32_t at = begin; at < end; at += 65536u) {
+                                    Feeder::Chunk ck; ck.src = src + at; ck.dst = dst + at; ck.count = std::min(65536u, end - at); ck.group = (uint32_t)g;
+                                    feeder.chunks.push_back(ck);
+                                }
+                            }
+                            j = k + 1;
+                        }
                     }
-                    if (cudaEventRecord(h2d_done[g], c->copy_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                    feeder.start(num_groups, c->feed_threads);
+                } else {
+                    cudaPointerAttributes attr;
+                    if (cudaPointerGetAttributes(&attr, io->streams[0].ch[0]) != cudaSuccess || attr.type != cudaMemoryTypeHost) { copies_async = false; (void)cudaGetLastError(); }
                 }
+                if (!issue_h2d(0)) { return SRLA_APIRESULT_NG; }
             } else {
                 for (uint32_t s = 0; s < pl.num_streams; s++) { if (!h2d_range(pl, *io, s, 0, pl.streams[s].num_samples, c->stream)) { return SRLA_APIRESULT_NG; } }
             }
@@ -651,8 +755,12 @@ struct Runner {
         for (const Job &j : jobs) { nmax = std::max(nmax, j.nsmpl); }
 
         /* ---- groups: [lshift so far] -> analyse -> decide -> scan -> emit ---- */
-        const size_t groups_now = pl.variable ? (jobs.size() + per_batch - 1) / per_batch : num_groups;
-        const uint32_t group_now = pl.variable ? per_batch : group;
+        if (pl.variable) {                      /* the final block list replaces the fixed tiling */
+            gstart.clear();
+            for (size_t at = 0; at < jobs.size(); at += per_batch) { gstart.push_back(at); }
+            gstart.push_back(jobs.size());
+        }
+        const size_t groups_now = gstart.size() - 1;
         std::vector<cudaEvent_t> &grp_done = c->ev_grp;
         unsigned long long *mailbox = nullptr; uint32_t *d_snap = nullptr;
         if (pipelined) {
@@ -670,11 +778,13 @@ struct Runner {
             while (c->ev_scan.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } c->ev_scan.push_back(e); }
         }
         for (size_t g = 0; g < groups_now; g++) {
-            const size_t j0 = g * group_now;
-            const uint32_t cnt = (uint32_t)std::min<size_t>(group_now, jobs.size() - j0);
+            const size_t j0 = gstart[g];
+            const uint32_t cnt = (uint32_t)(gstart[g + 1] - j0);
             const int ln = (int)(g % (size_t)lanes_now);
             const cudaStream_t on = c->lane[ln].stream;
             if (pipelined) {
+                /* pinned source: queue the next group's copy first so the copy engine never waits for the host */
+                if (copies_async && !io->narrow && g + 1 < groups_now && !issue_h2d(g + 1)) { return SRLA_APIRESULT_NG; }
                 if (cudaStreamWaitEvent(on, h2d_done[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
                 if (!launch_lshift(pl, (const Job *)c->jobs.p + j0, cnt, d_snap + g * pl.num_streams, on)) { return SRLA_APIRESULT_NG; }
             }
@@ -683,6 +793,9 @@ struct Runner {
                            pipelined ? mailbox + g : nullptr, ln,
                            (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr)) { return SRLA_APIRESULT_NG; }
             if (pipelined && cudaEventRecord(grp_done[g], on) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+            /* pageable source (the copy blocks the host) or feeder staging: the next group's copy follows this
+             * group's launches, so the device works on group g while the host moves group g + 1 */
+            if (pipelined && (!copies_async || io->narrow) && g + 1 < groups_now && !issue_h2d(g + 1)) { return SRLA_APIRESULT_NG; }
         }
         /* join: the caller's stream continues after every lane */
         for (int l = 1; l < lanes_now; l++) {
@@ -722,6 +835,7 @@ struct Runner {
             std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
             return SRLA_APIRESULT_NG;
         }
+        if (io && io->narrow && feeder.overflow.load()) { narrow_overflow = true; return SRLA_APIRESULT_NG; }
         const unsigned long long *running = (const unsigned long long *)hs;
         const uint32_t *dstats = (const uint32_t *)(hs + 2 * sizeof(unsigned long long));
         const unsigned long long *sbeg = (const unsigned long long *)(hs + small_bytes);
@@ -732,7 +846,7 @@ struct Runner {
             const uint32_t *fin = snap + groups_now * pl.num_streams;
             bool redo = false;
             for (size_t g = 0; g < groups_now && !redo; g++) {
-                const size_t j0 = g * group_now, j1 = std::min(jobs.size(), j0 + group_now);
+                const size_t j0 = gstart[g], j1 = gstart[g + 1];
                 for (size_t j = j0; j < j1; j++) { const uint32_t s = jobs[j].stream; if (snap[g * pl.num_streams + s] != fin[s]) { redo = true; break; } }
             }
             if (redo) {
@@ -752,6 +866,16 @@ struct Runner {
         for (int i = 0; i < 4; i++) { stt.method_histogram[i] = dstats[256 + i]; }
         for (int i = 0; i < 3; i++) { stt.type_histogram[i] = dstats[260 + i]; }
         cudaEventElapsedTime(&stt.ms_total_device, c->ev_begin, c->ev_end);
+        if (c->trace && pipelined) {
+            std::fprintf(stderr, "[srla_b200 trace] %zu groups, %d lanes, total %.3f ms (device clock, origin = call start)\n", groups_now, lanes_now, stt.ms_total_device);
+            for (size_t g = 0; g < groups_now; g++) {
+                float h = 0, t[5] = { 0, 0, 0, 0, 0 };
+                cudaEventElapsedTime(&h, c->ev_begin, h2d_done[g]);
+                for (int k = 0; k < 5; k++) { cudaEventElapsedTime(&t[k], c->ev_begin, c->ev_pool[g * 5 + k]); }
+                std::fprintf(stderr, "  group %2zu jobs %5zu lane %d: h2d done %.3f | front %.3f lpc %.3f residual %.3f decide %.3f end %.3f\n",
+                             g, gstart[g + 1] - gstart[g], (int)(g % (size_t)lanes_now), h, t[0], t[1], t[2], t[3], t[4]);
+            }
+        }
         for (size_t i = 0; i < ev_idx; i++) {
             float t[4] = { 0, 0, 0, 0 };
             for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&t[k], c->ev_pool[i * 5 + k], c->ev_pool[i * 5 + k + 1]); }
@@ -988,17 +1112,27 @@ SRLAApiResult SRLAEncoder_EncodeWhole(
     const uint64_t stride = round_up_u32(num_samples, 16);
     const uint64_t cap = max_encoded_size(encoder, num_samples);
     if (!c->pcm.reserve(sizeof(int32_t) * stride * nch) || !c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
-    struct SRLAB200Stream desc;
-    desc.pcm = c->pcm.p; desc.channel_stride = stride; desc.num_samples = num_samples; desc.sample_bytes = 4;
     HostStream hs;
     for (uint32_t ch = 0; ch < nch; ch++) { if (input[ch] == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; } hs.ch[ch] = input[ch]; }
-    HostIO io; io.streams = &hs; io.out = data; io.out_capacity = data_size;
     Plan pl;
-    pl.streams = &desc; pl.num_streams = 1; pl.nch = nch;
+    pl.num_streams = 1; pl.nch = nch;
     pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
-    Runner r{ encoder, c };
+    /* long fixed-block inputs of <= 16-bit sources are narrowed to int16 by the host feeder on their way in */
+    const uint64_t num_blocks = ((uint64_t)num_samples + encoder->param.max_num_samples_per_block - 1) / encoder->param.max_num_samples_per_block;
+    bool narrow = c->feed_threads > 0 && encoder->param.bits_per_sample <= 16 && !pl.variable && num_blocks >= 2048
+                  && c->h_stage.reserve(sizeof(int16_t) * stride * nch);
     uint64_t offs[2] = { 0, 0 };
-    const SRLAApiResult rc = r.run(pl, (uint8_t *)c->out.p, cap, offs, nullptr, &io);
+    SRLAApiResult rc = SRLA_APIRESULT_NG;
+    for (;;) {
+        struct SRLAB200Stream desc;
+        desc.pcm = c->pcm.p; desc.channel_stride = stride; desc.num_samples = num_samples; desc.sample_bytes = narrow ? 2u : 4u;
+        HostIO io; io.streams = &hs; io.out = data; io.out_capacity = data_size; io.narrow = narrow;
+        pl.streams = &desc;
+        Runner r{ encoder, c };
+        rc = r.run(pl, (uint8_t *)c->out.p, cap, offs, nullptr, &io);
+        if (narrow && r.narrow_overflow) { narrow = false; continue; }       /* samples beyond 16 bits: int32 layout */
+        break;
+    }
     if (rc != SRLA_APIRESULT_OK) { return rc; }
     *output_size = (uint32_t)offs[1];
     encoder->offset_lshift = data[24];                        /* the reference keeps it in its header (srla_encoder.c:1732) */

@@ -6,6 +6,9 @@ Integer / byte results must be bit-exact; the FP64 LPC stage is compared at 1e-1
 (BASELINE.json north_star) and exactly on the integers derived from it.
 """
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -16,6 +19,7 @@ from srla_b200 import encoder as E
 from srla_b200.synth import synth_stereo
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _first_diff(a: bytes, b: bytes) -> str:
@@ -258,3 +262,30 @@ def test_pipelined_host_path_and_late_shift_change():
             want = oracle_encode(st.astype(np.int32), **kw)
             got = out[offs[i]:offs[i + 1]].tobytes()
             assert got == want, (i, _first_diff(got, want))
+
+
+def test_reference_api_feeder_and_its_fallbacks():
+    """SRLAEncoder_EncodeWhole on long inputs: (a) <= 16-bit sources are narrowed to int16 by the host feeder threads
+    (covered with the ordinary signal above); (b) a sample outside the int16 range although bits_per_sample says 16
+    (a caller breaking the contract) must be noticed and the call redone with the int32 layout -- the reference codes
+    such values as they are; (c) 24-bit sources keep the int32 layout and the copy/launch interleaving for pageable
+    memory; (d) one feeder thread and no feeder at all give the same bytes."""
+    n = 256 * 2300
+    base = synth_stereo(n, seed=17)
+    kw = dict(preset=2, max_block=256)
+    want = oracle_encode(base, **kw)
+    assert E.encode(base, **kw) == want
+    loud = base.astype(np.int32).copy()
+    loud[1, n - 1000] = 40000
+    got, ref = E.encode(loud, **kw), oracle_encode(loud, **kw)
+    assert got == ref, _first_diff(got, ref)
+    wide = synth_stereo(n, seed=18, bits=24)
+    got, ref = E.encode(wide, bps=24, **kw), oracle_encode(wide, bps=24, **kw)
+    assert got == ref, _first_diff(got, ref)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from srla_b200 import encoder as E; from srla_b200.synth import synth_stereo\n"
+            "sys.stdout.buffer.write(E.encode(synth_stereo(%d, seed=17), preset=2, max_block=256))\n") % (ROOT, os.path.join(ROOT, "tests"), n)
+    for threads in ("1", "0"):
+        env = dict(os.environ, SRLA_B200_FEED_THREADS=threads)
+        out = subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True).stdout
+        assert out == want, threads

@@ -64,7 +64,33 @@ def stalls(rep, top):
     return outd
 
 
+def traffic(rep):
+    """{short kernel name: {...}} for bench.py (profiles/ncu_kernels.json); averages over the captured launches."""
+    acc = {}
+    for d in raw(rep):
+        name = d["kernel"].split("(")[0].split("<")[0].replace("void ", "").replace("srla::", "").strip()
+        def val(k):
+            v, u = d.get(k, ("0", ""))
+            f = float(v.replace(",", ""))
+            return f * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}.get(u, 1.0)
+        e = acc.setdefault(name, {"n": 0, "dram": 0.0, "t": 0.0, "fp64": 0.0, "issue": 0.0, "lsu_smem": 0.0, "alu": 0.0, "fma": 0.0, "warps": 0.0})
+        e["n"] += 1; e["dram"] += val("dram__bytes_read.sum") + val("dram__bytes_write.sum"); e["t"] += val("gpu__time_duration.sum")
+        e["fp64"] += val("sm__inst_executed_pipe_fp64.sum.pct_of_peak_sustained_active"); e["issue"] += val("smsp__issue_active.avg.pct_of_peak_sustained_active")
+        e["lsu_smem"] += val("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed")
+        e["alu"] += val("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"); e["fma"] += val("sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active")
+        e["warps"] += val("sm__warps_active.avg.pct_of_peak_sustained_active")
+    out = {}
+    for k, e in acc.items():
+        n = e["n"]
+        out[k] = {"dram_bytes_per_launch": int(e["dram"] / n), "ncu_duration_ms": round(e["t"] / n * 1e3, 4), "launches_captured": n,
+                  "issue_slots_active_pct": round(e["issue"] / n, 1), "fp64_pipe_pct": round(e["fp64"] / n, 1), "alu_pipe_pct": round(e["alu"] / n, 1),
+                  "fma_pipe_pct": round(e["fma"] / n, 1), "shared_mem_wavefronts_pct": round(e["lsu_smem"] / n, 1), "warps_active_pct": round(e["warps"] / n, 1)}
+    return out
+
+
 if __name__ == "__main__":
     rep = sys.argv[1]
+    if "--traffic" in sys.argv:
+        print(json.dumps(traffic(rep), indent=1)); sys.exit(0)
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 25
     print(json.dumps({"kernels": raw(rep), "stalls": stalls(rep, top)}, indent=1))
