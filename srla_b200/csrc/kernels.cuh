@@ -1211,7 +1211,7 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     extern __shared__ __align__(16) unsigned char smem[];
     const ResidLayout L = make_resid_layout(p.nmax, p.max_order);
     int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
-    int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;
+    int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + resid_front_pad(p.max_order);
     int32_t  *coef_s   = reinterpret_cast<int32_t *>(smem + L.coef_off);
     int32_t  *coef_b   = reinterpret_cast<int32_t *>(smem + L.coefb_off);
     uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
@@ -1246,14 +1246,22 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     int32_t *res_g = p.residual ? p.residual + ((size_t)job_id * p.ncand + cand) * p.res_stride : nullptr;
     if (order > 0u) {
         const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
-        /* 16-bit pair entries (see the header comment) */
+        /* Every group of outputs that reaches past the warm-up (first output >= order, or straddling it) runs the
+         * full padded filter: for an output i >= order the taps that fall in front of the block carry zero
+         * coefficients (order is padded to p4 in FRONT), so they may read anything addressable.  Warm-up outputs
+         * (i < order: first differences, srla_lpc_predict.c:251-254) are patched in afterwards.  No output is ever
+         * computed by a serial loop: one slow thread would hold the whole CTA at the next barrier. */
+        /* 16-bit pair entries (see the header comment); entry of sample quad j at Z[zpair_slot(j + zf)] */
         int4 *Z = reinterpret_cast<int4 *>(scratch);
+        const uint32_t zf = resid_pair_front(p.max_order);
         const uint32_t zcount = round_up_u32(n, 8) >> 2;
         int fits = 1;
-        for (uint32_t j = tid; j < zcount; j += kThreads) {
-            /* sig is zero beyond n (apply_preemphasis pads 12 samples past the rounded end) */
-            const int4 q = *reinterpret_cast<const int4 *>(sig + 4u * j);
-            const int32_t x[5] = { q.x, q.y, q.z, q.w, sig[4u * j + 4u] };
+        for (uint32_t jj = tid; jj < zcount + 1u; jj += kThreads) {
+            /* sig is zero beyond n (apply_preemphasis pads 12 samples past the rounded end) and in the four samples in
+             * front of the block; entry -1 is written too because its last pair (x[-1], x[0]) carries a real sample */
+            const int32_t j = (int32_t)jj - 1;
+            const int4 q = *reinterpret_cast<const int4 *>(sig + 4 * j);
+            const int32_t x[5] = { q.x, q.y, q.z, q.w, sig[4 * j + 4] };
             #pragma unroll
             for (int t = 0; t < 4; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
             int4 z;
@@ -1261,16 +1269,16 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
             z.y = (int32_t)(((uint32_t)x[2] & 0xffffu) | ((uint32_t)x[3] << 16));
             z.z = (int32_t)(((uint32_t)x[1] & 0xffffu) | ((uint32_t)x[2] << 16));
             z.w = (int32_t)(((uint32_t)x[3] & 0xffffu) | ((uint32_t)x[4] << 16));
-            Z[zpair_slot(j)] = z;
+            Z[zpair_slot((uint32_t)(j + (int32_t)zf))] = z;
         }
         fits = __syncthreads_and(fits);
         if (fits) {
             const uint32_t groups = (n + 7u) >> 3, nm = p4 >> 2;
             for (uint32_t g = tid; g < groups; g += kThreads) {
                 const uint32_t n0 = g << 3;
-                if (n0 >= p4) {
-                    int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
-                    const uint32_t j0 = (n0 - p4) >> 2;
+                int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+                if (n0 + 8u > order) {
+                    const uint32_t j0 = zf + (n0 >> 2) - nm;                       /* >= 0: zf covers p4 / 4 entries */
                     int4 za = Z[zpair_slot(j0)], zb = Z[zpair_slot(j0 + 1u)];
                     for (uint32_t m = 0; m < nm; ++m) {
                         const int4 zc = Z[zpair_slot(j0 + m + 2u)];
@@ -1285,33 +1293,27 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
                         a7 = __dp2a_lo(zb.w, cf, a7); a7 = __dp2a_hi(zc.z, cf, a7);
                         za = zb; zb = zc;
                     }
-                    const int4 s0 = *reinterpret_cast<const int4 *>(sig + n0), s1 = *reinterpret_cast<const int4 *>(sig + n0 + 4u);
-                    const int4 r0 = make_int4((int32_t)((uint32_t)s0.x + (uint32_t)asr32(a0, rshift)), (int32_t)((uint32_t)s0.y + (uint32_t)asr32(a1, rshift)),
-                                              (int32_t)((uint32_t)s0.z + (uint32_t)asr32(a2, rshift)), (int32_t)((uint32_t)s0.w + (uint32_t)asr32(a3, rshift)));
-                    const int4 r1 = make_int4((int32_t)((uint32_t)s1.x + (uint32_t)asr32(a4, rshift)), (int32_t)((uint32_t)s1.y + (uint32_t)asr32(a5, rshift)),
-                                              (int32_t)((uint32_t)s1.z + (uint32_t)asr32(a6, rshift)), (int32_t)((uint32_t)s1.w + (uint32_t)asr32(a7, rshift)));
-                    *reinterpret_cast<int4 *>(res_s + n0) = r0;
-                    if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = r0; }
-                    if (n0 + 4u < n) {
-                        *reinterpret_cast<int4 *>(res_s + n0 + 4u) = r1;
-                        if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = r1; }
+                }
+                const int4 s0 = *reinterpret_cast<const int4 *>(sig + n0), s1 = *reinterpret_cast<const int4 *>(sig + n0 + 4u);
+                int32_t r[8] = { (int32_t)((uint32_t)s0.x + (uint32_t)asr32(a0, rshift)), (int32_t)((uint32_t)s0.y + (uint32_t)asr32(a1, rshift)),
+                                 (int32_t)((uint32_t)s0.z + (uint32_t)asr32(a2, rshift)), (int32_t)((uint32_t)s0.w + (uint32_t)asr32(a3, rshift)),
+                                 (int32_t)((uint32_t)s1.x + (uint32_t)asr32(a4, rshift)), (int32_t)((uint32_t)s1.y + (uint32_t)asr32(a5, rshift)),
+                                 (int32_t)((uint32_t)s1.z + (uint32_t)asr32(a6, rshift)), (int32_t)((uint32_t)s1.w + (uint32_t)asr32(a7, rshift)) };
+                if (n0 < order) {
+                    /* warm-up outputs of this group */
+                    const int32_t x[8] = { s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w };
+                    const int32_t before = sig[n0 ? n0 - 1u : 0u];
+                    #pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const uint32_t i = n0 + (uint32_t)t;
+                        if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
                     }
-                } else {
-                    /* warm-up outputs (srla_lpc_predict.c:251-254) and the first outputs of the padded taps */
-                    const int32_t *cf = coef_s + (p4 - order);
-                    #pragma unroll 1
-                    for (uint32_t i = n0; i < n0 + 8u && i < n; ++i) {
-                        int32_t v;
-                        if (i == 0u) { v = sig[0]; }
-                        else if (i < order) { v = (int32_t)((uint32_t)sig[i] - (uint32_t)sig[i - 1u]); }
-                        else {
-                            uint32_t acc = half;
-                            for (uint32_t j = 0; j < order; ++j) { acc += (uint32_t)cf[j] * (uint32_t)sig[i - order + j]; }
-                            v = (int32_t)((uint32_t)sig[i] + (uint32_t)asr32((int32_t)acc, rshift));
-                        }
-                        res_s[i] = v;
-                        if (res_g) { res_g[i] = v; }
-                    }
+                }
+                *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+                if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
+                if (n0 + 4u < n) {
+                    *reinterpret_cast<int4 *>(res_s + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]);
+                    if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]); }
                 }
             }
         } else {
@@ -1319,10 +1321,10 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
             const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
             for (uint32_t g = tid; g < groups; g += kThreads) {
                 const uint32_t n0 = g << 2;
-                int32_t r[4];
-                if (n0 >= p4) {
-                    uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
-                    const int4 *xp = reinterpret_cast<const int4 *>(sig + n0 - p4);
+                uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
+                const int4 w_self = *reinterpret_cast<const int4 *>(sig + n0);
+                if (n0 + 4u > order) {
+                    const int4 *xp = reinterpret_cast<const int4 *>(sig + n0) - (p4 >> 2);      /* may start in the front padding */
                     int4 w0 = xp[0];
                     for (uint32_t m = 0; m < (p4 >> 2); ++m) {
                         const int4 w1 = xp[m + 1u];
@@ -1333,26 +1335,16 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
                         a3 += (uint32_t)cf.x * (uint32_t)w0.w + (uint32_t)cf.y * (uint32_t)w1.x + (uint32_t)cf.z * (uint32_t)w1.y + (uint32_t)cf.w * (uint32_t)w1.z;
                         w0 = w1;
                     }
-                    r[0] = (int32_t)((uint32_t)w0.x + (uint32_t)asr32((int32_t)a0, rshift));
-                    r[1] = (int32_t)((uint32_t)w0.y + (uint32_t)asr32((int32_t)a1, rshift));
-                    r[2] = (int32_t)((uint32_t)w0.z + (uint32_t)asr32((int32_t)a2, rshift));
-                    r[3] = (int32_t)((uint32_t)w0.w + (uint32_t)asr32((int32_t)a3, rshift));
-                } else {
-                    const int32_t *cf = coef_s + (p4 - order);
+                }
+                int32_t r[4] = { (int32_t)((uint32_t)w_self.x + (uint32_t)asr32((int32_t)a0, rshift)), (int32_t)((uint32_t)w_self.y + (uint32_t)asr32((int32_t)a1, rshift)),
+                                 (int32_t)((uint32_t)w_self.z + (uint32_t)asr32((int32_t)a2, rshift)), (int32_t)((uint32_t)w_self.w + (uint32_t)asr32((int32_t)a3, rshift)) };
+                if (n0 < order) {
+                    const int32_t x[4] = { w_self.x, w_self.y, w_self.z, w_self.w };
+                    const int32_t before = sig[n0 ? n0 - 1u : 0u];
                     #pragma unroll
                     for (int t = 0; t < 4; ++t) {
-                        const uint32_t i = n0 + t;
-                        int32_t v = 0;
-                        if (i < n) {
-                            if (i == 0u) { v = sig[0]; }
-                            else if (i < order) { v = (int32_t)((uint32_t)sig[i] - (uint32_t)sig[i - 1u]); }
-                            else {
-                                uint32_t acc = half;
-                                for (uint32_t j = 0; j < order; ++j) { acc += (uint32_t)cf[j] * (uint32_t)sig[i - order + j]; }
-                                v = (int32_t)((uint32_t)sig[i] + (uint32_t)asr32((int32_t)acc, rshift));
-                            }
-                        }
-                        r[t] = v;
+                        const uint32_t i = n0 + (uint32_t)t;
+                        if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
                     }
                 }
                 *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);

@@ -171,19 +171,24 @@ struct ResidLayout {
     uint32_t red_off;                  /* 1024 bytes of reduction scratch                      */
     uint32_t total;
 };
+/* front padding of the FIR's inputs: the taps of the first outputs after the warm-up reach up to roundup4(P)
+ * samples in front of the block; those taps carry zero coefficients, so the padding only has to be addressable */
+SRLA_HD inline uint32_t resid_front_pad(uint32_t P) { return round_up_u32(P, 4) + 4u; }             /* samples, multiple of 4 */
+SRLA_HD inline uint32_t resid_pair_front(uint32_t P) { return round_up_u32(round_up_u32(P, 4) / 4u + 2u, 16); }   /* pair entries */
+
 SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
 {
     ResidLayout L;
     const uint32_t n4 = round_up_u32(nmax, 4);
     const uint32_t parts = (nmax < (uint32_t)kMaxParts) ? nmax : (uint32_t)kMaxParts;
     const uint32_t pyramid = 16u * round_up_u32(parts, 2) + 16u;
-    const uint32_t pairs = 4u * round_up_u32(nmax, 8) + 32u;      /* one 16-byte entry per 4 samples */
+    const uint32_t pairs = 4u * round_up_u32(nmax, 8) + 32u + 16u * resid_pair_front(P);      /* one 16-byte entry per 4 samples */
     const uint32_t scratch = (pyramid > pairs) ? pyramid : pairs;
     uint32_t off = 0;
     L.region_off = off;
     L.region_bytes = round_up_u32(4u * n4 + (scratch > 4096u ? scratch : 4096u), 16);
     off += L.region_bytes;
-    L.sig_off = off; off += 4u * (n4 + 16u);
+    L.sig_off = off; off += 4u * (n4 + 12u + resid_front_pad(P));
     L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
     L.coefb_off = off; off += 4u * (round_up_u32(P, 4) / 4u + 4u);
     L.red_off = off; off += 1024u;
