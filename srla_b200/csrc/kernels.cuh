@@ -538,8 +538,23 @@ __device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, 
 /* ------------------------------------------------------------------------------------------------
  * Candidate signal preparation shared by front_kernel and residual_kernel
  * ---------------------------------------------------------------------------------------------- */
+/* raw 16-byte (int32 PCM) or 8-byte (int16 PCM) global load of one sample quad, unpacked later: the loads of a
+ * whole batch of quads are issued back to back so a thread waits for the memory latency once per batch */
+__device__ __forceinline__ int4 load_quad_raw(const StreamDev &st, uint32_t ch, uint32_t idx)
+{
+    const unsigned long long at = (unsigned long long)ch * st.stride + idx;
+    if (st.sample_bytes == 2u) { const int2 v = ldg_stream_v2(reinterpret_cast<const short *>(st.pcm) + at); return make_int4(v.x, v.y, 0, 0); }
+    return ldg_stream_v4(reinterpret_cast<const int32_t *>(st.pcm) + at);
+}
+__device__ __forceinline__ int4 unpack_quad(const StreamDev &st, int4 v)
+{
+    if (st.sample_bytes == 2u) { return make_int4((int32_t)(short)(v.x & 0xffff), v.x >> 16, (int32_t)(short)(v.y & 0xffff), v.y >> 16); }
+    return v;
+}
+
 /* load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) -> raw[0..n).
  * returns OR of the unshifted samples of a plain channel candidate (0 for M/S). */
+template <int kBatch>                         /* quads in flight per thread */
 __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
                                               uint32_t lshift, int32_t *raw)
 {
@@ -549,33 +564,58 @@ __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &jo
     const uint32_t ch = ms ? 0u : cand - first_ch;
     const bool vec = quad_aligned(st, ch, job.offset) && (!ms || quad_aligned(st, 1u, job.offset));
     const uint32_t nquad = vec ? (n >> 2) : 0u;
+    const uint32_t T = blockDim.x;
     int nz = 0;
     if (ms) {
-        for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
-            const int4 lq = load_quad(st, 0, job.offset + 4u * g), rq = load_quad(st, 1, job.offset + 4u * g);
-            const int32_t l[4] = { asr32(lq.x, lshift), asr32(lq.y, lshift), asr32(lq.z, lshift), asr32(lq.w, lshift) };
-            const int32_t r[4] = { asr32(rq.x, lshift), asr32(rq.y, lshift), asr32(rq.z, lshift), asr32(rq.w, lshift) };
-            int32_t o[4];
+        for (uint32_t g0 = threadIdx.x; g0 < nquad; g0 += kBatch * T) {
+            int4 lraw[kBatch], rraw[kBatch];
             #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int32_t side = (int32_t)((uint32_t)r[t] - (uint32_t)l[t]);
-                o[t] = (cand == 1u) ? side : (int32_t)((uint32_t)l[t] + (uint32_t)(side >> 1));
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t g = g0 + (uint32_t)b * T;
+                if (g < nquad) { lraw[b] = load_quad_raw(st, 0, job.offset + 4u * g); rraw[b] = load_quad_raw(st, 1, job.offset + 4u * g); }
             }
-            *reinterpret_cast<int4 *>(raw + 4u * g) = make_int4(o[0], o[1], o[2], o[3]);
+            #pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t g = g0 + (uint32_t)b * T;
+                if (g < nquad) {
+                    const int4 lq = unpack_quad(st, lraw[b]), rq = unpack_quad(st, rraw[b]);
+                    const int32_t l[4] = { asr32(lq.x, lshift), asr32(lq.y, lshift), asr32(lq.z, lshift), asr32(lq.w, lshift) };
+                    const int32_t r[4] = { asr32(rq.x, lshift), asr32(rq.y, lshift), asr32(rq.z, lshift), asr32(rq.w, lshift) };
+                    int32_t o[4];
+                    #pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int32_t side = (int32_t)((uint32_t)r[t] - (uint32_t)l[t]);
+                        o[t] = (cand == 1u) ? side : (int32_t)((uint32_t)l[t] + (uint32_t)(side >> 1));
+                    }
+                    *reinterpret_cast<int4 *>(raw + 4u * g) = make_int4(o[0], o[1], o[2], o[3]);
+                }
+            }
         }
-        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += blockDim.x) {
+        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += T) {
             const int32_t l = asr32(load_sample(st, 0, job.offset + i), lshift);
             const int32_t r = asr32(load_sample(st, 1, job.offset + i), lshift);
             const int32_t side = (int32_t)((uint32_t)r - (uint32_t)l);
             raw[i] = (cand == 1u) ? side : (int32_t)((uint32_t)l + (uint32_t)(side >> 1));
         }
     } else {
-        for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
-            const int4 q = load_quad(st, ch, job.offset + 4u * g);
-            nz |= q.x | q.y | q.z | q.w;
-            *reinterpret_cast<int4 *>(raw + 4u * g) = make_int4(asr32(q.x, lshift), asr32(q.y, lshift), asr32(q.z, lshift), asr32(q.w, lshift));
+        for (uint32_t g0 = threadIdx.x; g0 < nquad; g0 += kBatch * T) {
+            int4 qraw[kBatch];
+            #pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t g = g0 + (uint32_t)b * T;
+                if (g < nquad) { qraw[b] = load_quad_raw(st, ch, job.offset + 4u * g); }
+            }
+            #pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t g = g0 + (uint32_t)b * T;
+                if (g < nquad) {
+                    const int4 q = unpack_quad(st, qraw[b]);
+                    nz |= q.x | q.y | q.z | q.w;
+                    *reinterpret_cast<int4 *>(raw + 4u * g) = make_int4(asr32(q.x, lshift), asr32(q.y, lshift), asr32(q.z, lshift), asr32(q.w, lshift));
+                }
+            }
         }
-        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += blockDim.x) {
+        for (uint32_t i = 4u * nquad + threadIdx.x; i < n; i += T) {
             const int32_t v = load_sample(st, ch, job.offset + i);
             nz |= v;
             raw[i] = asr32(v, lshift);
@@ -709,7 +749,7 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
     /* without LTP the candidate goes straight into the signal buffer and the pre-emphasis is folded into
      * the window pass; with LTP the filtered signal itself is needed in shared memory */
     int32_t *raw = kLtp ? region_i : sig;
-    int nz = load_candidate(st, job, p, cand, lshift, raw);
+    int nz = load_candidate<8>(st, job, p, cand, lshift, raw);          /* 4096 samples / 128 threads = 8 quads each */
     nz = __syncthreads_or(nz);
     if (tid == 0) {
         out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
@@ -1228,7 +1268,7 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     const int32_t pre_coef = out->pre_coef;
 
     /* ---- rebuild the signal the FIR runs on ---- */
-    (void)load_candidate(st, job, p, cand, lshift, region_i);
+    (void)load_candidate<2>(st, job, p, cand, lshift, region_i);        /* 64 registers per thread: two quads (x 2 channels) in flight */
     const uint32_t p4 = round_up_u32(order, 4);
     for (uint32_t i = tid; i < p4; i += kThreads) { coef_s[i] = (i < p4 - order) ? 0 : (int32_t)out->coef[i - (p4 - order)]; }
     __syncthreads();
