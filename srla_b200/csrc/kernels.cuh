@@ -192,6 +192,22 @@ __device__ __forceinline__ double int_to_double(int32_t x)
 template <bool kPre>
 struct WindowSource {
     const int32_t *sig; uint32_t n, half_n, pc; double unit, div, dn1;
+    bool full;                    /* n is the transform size: no zero padding, the window halves meet at n / 2 */
+    /* element whose two samples are 2e, 2e+1 with window arguments ds0, ds0 + step (exact doubles supplied by the caller) */
+    __device__ __forceinline__ double2 element_at(uint32_t e, double ds0, double step) const
+    {
+        const uint32_t i = 2u * e;
+        const int2 c = *reinterpret_cast<const int2 *>(sig + i);
+        int32_t x0 = c.x, x1 = c.y;
+        if (kPre) {
+            const int32_t prv = sig[i ? i - 1u : 0u];
+            x1 = (int32_t)((uint32_t)c.y - (uint32_t)((int32_t)((uint32_t)c.x * pc) >> 4));
+            x0 = (int32_t)((uint32_t)c.x - (uint32_t)((int32_t)((uint32_t)prv * pc) >> 4));
+        }
+        const double ds1 = ds0 + step;
+        const double w0 = div * ds0 * (dn1 - ds0), w1 = div * ds1 * (dn1 - ds1);
+        return make_double2((int_to_double(x0) * unit) * w0, (int_to_double(x1) * unit) * w1);
+    }
     __device__ __forceinline__ double one(uint32_t i, int32_t cur, int32_t prv) const
     {
         if (i >= n) { return 0.0; }
@@ -234,12 +250,28 @@ __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const u
     const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
     double2 v[4][4];
     if (active) {
-        #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {
+        if (kFromSamples && src.full) {
+            /* no padding: elements with j < 2 lie in the rising window half (argument s = i), the others in the falling
+             * half (s = n - 1 - i); all arguments are exact doubles derived from two conversions per thread */
+            const double lo0 = int_to_double((int32_t)(2u * tid)), hi0 = int_to_double((int32_t)(src.n - 1u - 2u * tid));
+            const double dq = int_to_double((int32_t)(M >> 3));            /* samples between consecutive jp */
             #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
-                v[jp][j] = kFromSamples ? src.element(e) : x[fft_slot(e)];
+            for (int jp = 0; jp < 4; ++jp) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
+                    const double off = dq * (double)(jp + 4 * j);          /* 2 * (e - tid), exact */
+                    v[jp][j] = (j < 2) ? src.element_at(e, lo0 + off, 1.0) : src.element_at(e, hi0 - off, -1.0);
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
+                    v[jp][j] = kFromSamples ? src.element(e) : x[fft_slot(e)];
+                }
             }
         }
     }
@@ -362,6 +394,7 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
     const uint32_t M = N >> 1;
     WindowSource<kPre> ws;
     ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = unit; ws.div = div; ws.dn1 = (double)(int32_t)(n - 1u);
+    ws.full = (n == N) && (N >= 32u);
     const uint32_t want = (nlags < N) ? nlags : N;
     /* dir 0: forward transform of the windowed samples; dir 1: the inverse transform, evaluated as the
      * conjugate of a forward transform of conjugated data (see butterfly4) so both directions share one
