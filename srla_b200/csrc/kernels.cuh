@@ -248,6 +248,7 @@ __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const u
     const bool last_pair = (nn < 256u);          /* outputs feed the tail pass (or are final) */
     const bool active = tid < units;
     const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
+    const bool fast_load = ((M >> 4) & 127u) == 0u;
     double2 v[4][4];
     if (active) {
         if (kFromSamples && src.full) {
@@ -264,6 +265,14 @@ __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const u
                     v[jp][j] = (j < 2) ? src.element_at(e, lo0 + off, 1.0) : src.element_at(e, hi0 - off, -1.0);
                 }
             }
+        } else if (!kFromSamples && fast_load) {
+            /* M / 16 is a multiple of 128: the swizzle term (e >> 4) & 7 is the same for all 16 inputs of the unit */
+            const double2 *b = x + (tid ^ ((tid >> 4) & 7u));
+            #pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) { v[jp][j] = b[(uint32_t)(jp + 4 * j) * (M >> 4)]; }
+            }
         } else {
             #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {
@@ -275,6 +284,7 @@ __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const u
             }
         }
     }
+    (void)fast_load;
     if (!kFromSamples) { __syncthreads(); }      /* in place: every input is in registers before any output is stored */
     if (active) {
         double2 y[4][4];
@@ -284,7 +294,29 @@ __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const u
             butterfly4(v[jp][0], v[jp][1], v[jp][2], v[jp][3], wa, y[jp][0], y[jp][1], y[jp][2], y[jp][3]);
         }
         const Twiddle3 wb = load_twiddle(tw_b, nn >> 4, p0);
-        if (!last_pair || need >= M) {
+        if (lgs == 0u && (!last_pair || need >= M)) {
+            /* outputs 16 tid + (j + 4 i): the swizzle term is tid & 7 */
+            double2 *b = x + 16u * tid;
+            const uint32_t t = tid & 7u;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 z0, z1, z2, z3;
+                butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
+                b[(uint32_t)j ^ t] = z0; b[(uint32_t)(j + 4) ^ t] = z1; b[(uint32_t)(j + 8) ^ t] = z2; b[(uint32_t)(j + 12) ^ t] = z3;
+            }
+        } else if (lgs == 4u && (!last_pair || need >= M)) {
+            /* outputs q + 16 j + 64 i + 256 p0: the swizzle term is (j + 4 i) & 7, a constant per output */
+            double2 *b = x + 256u * p0;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 z0, z1, z2, z3;
+                butterfly4(y[0][j], y[1][j], y[2][j], y[3][j], wb, z0, z1, z2, z3);
+                b[(q ^ (uint32_t)(j & 7)) + 16u * j]              = z0;
+                b[(q ^ (uint32_t)((j + 4) & 7)) + 16u * j + 64u]  = z1;
+                b[(q ^ (uint32_t)(j & 7)) + 16u * j + 128u]       = z2;
+                b[(q ^ (uint32_t)((j + 4) & 7)) + 16u * j + 192u] = z3;
+            }
+        } else if (!last_pair || need >= M) {
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 double2 z0, z1, z2, z3;
