@@ -145,7 +145,7 @@ bool ctx_init(DeviceCtx *c)
         return false;
     }
     c->num_sms = prop.multiProcessorCount;
-    if (const char *e = std::getenv("SRLA_B200_FRONT_OCC")) { if (e[0] == '3') { c->front_occ = 3; } else if (e[0] == '4') { c->front_occ = 4; } }
+    if (const char *e = std::getenv("SRLA_B200_FRONT_OCC")) { if (e[0] >= '2' && e[0] <= '4') { c->front_occ = e[0] - '0'; } }
     CU_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
@@ -402,6 +402,9 @@ struct Runner {
             if (ltp) {
                 if (!prep_kernel(front_kernel<128, 3, true>, FL.total, 5, 3)) { return false; }
                 front_kernel<128, 3, true><<<grid, 128, FL.total, on>>>(p);
+            } else if (c->front_occ == 2) {
+                if (!prep_kernel(front_kernel<128, 2, false>, FL.total, 6, 2)) { return false; }
+                front_kernel<128, 2, false><<<grid, 128, FL.total, on>>>(p);
             } else if (c->front_occ == 4) {
                 if (!prep_kernel(front_kernel<128, 4, false>, FL.total, 6, 4)) { return false; }
                 front_kernel<128, 4, false><<<grid, 128, FL.total, on>>>(p);
