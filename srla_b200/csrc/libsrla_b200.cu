@@ -106,6 +106,8 @@ struct DeviceCtx {
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_grp;
     std::vector<Job> jobs_scratch;
+    std::vector<uint32_t> jobs_key;   /* stream lengths + block size of the fixed tiling that jobs_scratch and the device copy hold */
+    bool jobs_cached = false;
     uint32_t smem_set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
     int max_smem_optin = 0;
     int num_sms = 0;
@@ -551,6 +553,7 @@ struct Runner {
     {
         const size_t bytes = sizeof(Job) * jobs.size();
         if (c->upload_pending) { CU_TRY(cudaEventSynchronize(c->ev_upload)); c->upload_pending = false; }   /* the staging buffer is reused */
+        c->jobs_cached = false;                              /* the device copy is being replaced */
         if (!c->jobs.reserve(bytes) || !c->h_jobs.reserve(bytes)) { return false; }
         std::memcpy(c->h_jobs.p, jobs.data(), bytes);
         CU_TRY(cudaMemcpyAsync(c->jobs.p, c->h_jobs.p, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -596,12 +599,22 @@ struct Runner {
         }
 
         /* ---- job list ---- */
+        /* repeated calls on equally shaped input (a service encoding batch after batch) reuse the tiling and its
+         * device copy: building and uploading 10^4 jobs would leave the device idle between calls */
         std::vector<Job> &jobs = c->jobs_scratch;
-        jobs.clear();
-        for (uint32_t s = 0; s < pl.num_streams; s++) {          /* fixed tiling: the block list, or the cover used for the shift */
-            const uint32_t total = pl.streams[s].num_samples;
-            for (uint32_t at = 0; at < total; at += max_block) {
-                jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
+        std::vector<uint32_t> key;
+        key.reserve(pl.num_streams + 2);
+        key.push_back(max_block); key.push_back(pl.num_streams);
+        for (uint32_t s = 0; s < pl.num_streams; s++) { key.push_back(pl.streams[s].num_samples); }
+        const bool reuse_jobs = c->jobs_cached && !pl.variable && key == c->jobs_key;
+        if (!reuse_jobs) {
+            c->jobs_cached = false;
+            jobs.clear();
+            for (uint32_t s = 0; s < pl.num_streams; s++) {          /* fixed tiling: the block list, or the cover used for the shift */
+                const uint32_t total = pl.streams[s].num_samples;
+                for (uint32_t at = 0; at < total; at += max_block) {
+                    jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
+                }
             }
         }
         /* large fixed-block calls are split into groups that alternate between the lanes (compute streams);
@@ -638,7 +651,10 @@ struct Runner {
         if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
         if (cudaMemsetAsync(c->misc.p, 0, 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t), c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-        if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
+        if (!reuse_jobs) {
+            if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
+            if (!pl.variable) { c->jobs_key = key; c->jobs_cached = true; }
+        }
 
         /* ---- host input ---- */
         std::vector<cudaEvent_t> &h2d_done = c->ev_h2d;
@@ -1261,6 +1277,7 @@ SRLAApiResult SRLAB200_TestAnalyseChannel(
     std::memset(&encoder->stats, 0, sizeof(encoder->stats));
     if (!r.prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
     Job job = make_job(0, 0, n, 0, r.len_cache);
+    c->jobs_cached = false;
     if (!c->jobs.reserve(sizeof(Job))) { return SRLA_APIRESULT_NG; }
     if (cudaMemcpyAsync(c->jobs.p, &job, sizeof(Job), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
     if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0, nullptr)) { return SRLA_APIRESULT_NG; }
