@@ -75,6 +75,7 @@ struct PinBuf {
 };
 
 constexpr int kMaxLanes = 4;
+constexpr size_t kMiscBytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t) + 4;   /* running[2], stats[263], pad to 8 */
 
 struct DeviceCtx {
     int device = 0;
@@ -100,11 +101,11 @@ struct DeviceCtx {
     int split_device = 0;          /* SRLA_B200_SPLIT_DEVICE=1: also split device-resident calls across the lanes */
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_scan;
-    PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox, h_stage;
+    PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox, h_stage, h_stage_out;
     int feed_threads = 8;          /* SRLA_B200_FEED_THREADS */
     DevBuf snapshot;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
-    std::vector<cudaEvent_t> ev_h2d, ev_grp;
+    std::vector<cudaEvent_t> ev_h2d, ev_grp, ev_d2h;
     std::vector<Job> jobs_scratch;
     std::vector<uint32_t> jobs_key;   /* stream lengths + block size of the fixed tiling that jobs_scratch and the device copy hold */
     bool jobs_cached = false;
@@ -206,6 +207,7 @@ void ctx_destroy(DeviceCtx *c)
     for (cudaEvent_t e : c->ev_pool) { cudaEventDestroy(e); }
     for (cudaEvent_t e : c->ev_h2d) { cudaEventDestroy(e); }
     for (cudaEvent_t e : c->ev_grp) { cudaEventDestroy(e); }
+    for (cudaEvent_t e : c->ev_d2h) { cudaEventDestroy(e); }
     for (cudaEvent_t e : c->ev_scan) { cudaEventDestroy(e); }
     for (int l = 0; l < kMaxLanes; l++) {
         if (c->lane[l].own) { cudaStreamSynchronize(c->lane[l].own); cudaStreamDestroy(c->lane[l].own); }
@@ -223,7 +225,7 @@ void ctx_destroy(DeviceCtx *c)
     DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
                        &c->misc, &c->stream_begin, &c->pcm, &c->out };
     for (DevBuf *b : bufs) { b->release(); }
-    c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release();
+    c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release(); c->h_stage_out.release();
     if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
 }
 
@@ -286,6 +288,13 @@ struct Feeder {
     std::unique_ptr<std::atomic<int>[]> left;      /* chunks of each group still to convert */
     std::atomic<size_t> next{0};
     std::atomic<int> overflow{0};
+    /* output phase: once the input is staged the same threads copy the encoded bytes from the pinned staging
+     * buffer (the target of the asynchronous D2H copies) into the caller's pageable buffer, 1 MB at a time, as soon
+     * as the bytes are there */
+    static constexpr unsigned long long kOutChunk = 1ull << 20, kUnknown = ~0ull;
+    const uint8_t *out_stage = nullptr; uint8_t *out_user = nullptr;
+    std::atomic<unsigned long long> out_ready{0}, out_total{kUnknown}, out_next{0};
+    std::atomic<int> abort{0};
     std::vector<std::thread> team;
     void start(size_t num_groups, int threads)
     {
@@ -298,7 +307,7 @@ struct Feeder {
     {
         for (;;) {
             const size_t i = next.fetch_add(1);
-            if (i >= chunks.size()) { return; }
+            if (i >= chunks.size()) { break; }
             const Chunk &ck = chunks[i];
             uint32_t bad = 0;
             for (uint32_t k = 0; k < ck.count; k++) {
@@ -309,9 +318,22 @@ struct Feeder {
             if (bad) { overflow.store(1); }
             left[ck.group].fetch_sub(1, std::memory_order_release);
         }
+        if (out_stage == nullptr) { return; }
+        for (;;) {
+            const unsigned long long begin = out_next.fetch_add(1) * kOutChunk;
+            for (;;) {
+                if (abort.load(std::memory_order_acquire)) { return; }
+                const unsigned long long total = out_total.load(std::memory_order_acquire);
+                if (total != kUnknown && begin >= total) { return; }
+                const unsigned long long want = std::min(begin + kOutChunk, total);          /* total == kUnknown: the full chunk */
+                if (out_ready.load(std::memory_order_acquire) >= want) { std::memcpy(out_user + begin, out_stage + begin, (size_t)(want - begin)); break; }
+                std::this_thread::yield();
+            }
+        }
     }
     void wait_group(size_t g) { while (left[g].load(std::memory_order_acquire) > 0) { std::this_thread::yield(); } }
-    ~Feeder() { for (std::thread &t : team) { if (t.joinable()) { t.join(); } } }
+    void join() { for (std::thread &t : team) { if (t.joinable()) { t.join(); } } }
+    ~Feeder() { abort.store(1, std::memory_order_release); join(); }
 };
 
 /* what one call encodes */
@@ -356,7 +378,7 @@ struct Runner {
         p.huff_code = (const uint32_t *)c->huff_code.p; p.huff_len = (const uint8_t *)c->huff_len.p;
         p.running = (unsigned long long *)c->misc.p;
         p.stats = (uint32_t *)((unsigned char *)c->misc.p + 2 * sizeof(unsigned long long));
-        p.stream_begin = (unsigned long long *)c->stream_begin.p;
+        p.stream_begin = (unsigned long long *)((unsigned char *)c->misc.p + kMiscBytes);       /* behind the counters: one result copy */
         return p;
     }
 
@@ -445,7 +467,7 @@ struct Runner {
     bool prepare_streams(const Plan &pl)
     {
         const size_t bytes = sizeof(StreamDev) * pl.num_streams;
-        if (!c->streams.reserve(bytes) || !c->h_small.reserve(bytes + 64) || !c->stream_begin.reserve(sizeof(unsigned long long) * (pl.num_streams + 1))) { return false; }
+        if (!c->streams.reserve(bytes) || !c->h_small.reserve(bytes + 64)) { return false; }
         StreamDev *h = (StreamDev *)c->h_small.p;
         for (uint32_t s = 0; s < pl.num_streams; s++) {
             h[s].pcm = pl.streams[s].pcm; h[s].stride = pl.streams[s].channel_stride;
@@ -650,7 +672,8 @@ struct Runner {
 
         if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
-        if (cudaMemsetAsync(c->misc.p, 0, 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t), c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        if (!c->misc.reserve(kMiscBytes + sizeof(unsigned long long) * (pl.num_streams + 1) + 64)) { return SRLA_APIRESULT_NG; }
+        if (cudaMemsetAsync(c->misc.p, 0, kMiscBytes, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!reuse_jobs) {
             if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
             if (!pl.variable) { c->jobs_key = key; c->jobs_cached = true; }
@@ -697,6 +720,7 @@ struct Runner {
                             j = k + 1;
                         }
                     }
+                    if (c->h_stage_out.reserve(std::min<uint64_t>(cap, io->out_capacity))) { feeder.out_stage = (const uint8_t *)c->h_stage_out.p; feeder.out_user = io->out; }
                     feeder.start(num_groups, c->feed_threads);
                 } else {
                     cudaPointerAttributes attr;
@@ -830,25 +854,47 @@ struct Runner {
         /* ---- pipelined device -> host copies of finished groups ---- */
         bool host_overflow = false;
         if (pipelined) {
+            /* with the feeder the copies land in pinned staging and its threads move the bytes on to the caller's
+             * (pageable) buffer as they arrive; otherwise they go straight to the caller's buffer */
+            const bool staged = io->narrow && feeder.out_stage != nullptr;
+            uint8_t *h_dst = staged ? (uint8_t *)c->h_stage_out.p : io->out;
+            if (staged) { while (c->ev_d2h.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } c->ev_d2h.push_back(e); } }
+            std::vector<unsigned long long> gend(groups_now, 0);
+            size_t published = 0;
             unsigned long long prev = 0;
             for (size_t g = 0; g < groups_now; g++) {
                 if (cudaEventSynchronize(grp_done[g]) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
                 const unsigned long long end = mailbox[g];
                 if (end > io->out_capacity || end > cap) { host_overflow = true; break; }
-                if (end > prev && cudaMemcpyAsync(io->out + prev, d_out + prev, end - prev, cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-                prev = end;
+                if (end > prev && cudaMemcpyAsync(h_dst + prev, d_out + prev, end - prev, cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                prev = end; gend[g] = end;
+                if (staged) {
+                    if (cudaEventRecord(c->ev_d2h[g], c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                    while (published <= g && cudaEventQuery(c->ev_d2h[published]) == cudaSuccess) { feeder.out_ready.store(gend[published], std::memory_order_release); published++; }
+                }
+            }
+            if (staged) {
+                (void)cudaGetLastError();                      /* cudaEventQuery's cudaErrorNotReady is not an error */
+                if (host_overflow) { feeder.abort.store(1, std::memory_order_release); }
+                else {
+                    for (; published < groups_now; published++) {
+                        if (cudaEventSynchronize(c->ev_d2h[published]) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+                        feeder.out_ready.store(gend[published], std::memory_order_release);
+                    }
+                    feeder.out_total.store(prev, std::memory_order_release);
+                }
+                feeder.join();
             }
         }
 
         /* ---- results ---- */
-        const size_t small_bytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t);
+        const size_t small_bytes = kMiscBytes;
         const size_t sb_bytes = sizeof(unsigned long long) * (pl.num_streams + 1);
         const size_t snap_bytes = pipelined ? sizeof(uint32_t) * (groups_now + 1) * pl.num_streams : 0;
         if (!c->h_result.reserve(small_bytes + sb_bytes + sizeof(JobOut) + snap_bytes + 64)) { return SRLA_APIRESULT_NG; }
         unsigned char *hs = (unsigned char *)c->h_result.p;
-        cudaMemcpyAsync(hs, c->misc.p, small_bytes, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(hs + small_bytes, c->stream_begin.p, sb_bytes, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(hs + small_bytes + sb_bytes, c->lane[0].jobout.p, sizeof(JobOut), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(hs, c->misc.p, small_bytes + sb_bytes, cudaMemcpyDeviceToHost, c->stream);      /* counters, statistics, stream offsets */
+        if (single_estimate) { cudaMemcpyAsync(hs + small_bytes + sb_bytes, c->lane[0].jobout.p, sizeof(JobOut), cudaMemcpyDeviceToHost, c->stream); }
         if (pipelined) { cudaMemcpyAsync(hs + small_bytes + sb_bytes + sizeof(JobOut), c->snapshot.p, snap_bytes, cudaMemcpyDeviceToHost, c->stream); }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || (pipelined && (cudaStreamSynchronize(c->d2h_stream) != cudaSuccess || cudaStreamSynchronize(c->copy_stream) != cudaSuccess))) {
             std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
