@@ -1723,8 +1723,6 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ 
     if (jo.type == kBlockRaw) {
         /* interleaved big-endian zig-zag samples of the UNSHIFTED input (srla_encoder.c:799-858) */
         const uint32_t bytes_per = bps >> 3;
-        uint8_t *bytes = smem;      /* staged as plain bytes, converted below */
-        (void)bytes;
         for (uint32_t e = tid; e < n * nch; e += kThreads) {
             const uint32_t i = e / nch, ch = e % nch;
             const uint32_t v = zigzag32(load_sample(st, ch, job.offset + i));
