@@ -289,3 +289,31 @@ def test_reference_api_feeder_and_its_fallbacks():
         env = dict(os.environ, SRLA_B200_FEED_THREADS=threads)
         out = subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True).stdout
         assert out == want, threads
+
+
+def test_one_handle_many_shapes_reuses_and_replaces_the_cached_tiling():
+    """The fixed tiling (job list) and its device copy are kept between equally shaped calls on one handle and must be
+    rebuilt when the shape, the block size or the mode (fixed / variable blocks) changes in between."""
+    a = [synth_stereo(4096 * 5 + 100, seed=41).astype(np.int16), synth_stereo(4096 * 2, seed=42).astype(np.int16)]
+    b = [synth_stereo(4096 * 3, seed=43).astype(np.int16)]
+    a2 = [synth_stereo(4096 * 5 + 100, seed=44).astype(np.int16), synth_stereo(4096 * 2, seed=45).astype(np.int16)]   # same shape as a, other samples
+
+    def check(enc, streams, **kw):
+        out, offs = enc.encode_streams_host(streams)
+        for i, s in enumerate(streams):
+            want = oracle_encode(s.astype(np.int32), **kw)
+            got = out[offs[i]:offs[i + 1]].tobytes()
+            assert got == want, (i, _first_diff(got, want))
+
+    with E.Encoder(max_block=4096, min_block=1024, lookahead=8192) as enc:
+        assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+        check(enc, a, preset=4, max_block=4096)
+        check(enc, a2, preset=4, max_block=4096)            # cached tiling, new samples
+        check(enc, b, preset=4, max_block=4096)             # other shape
+        check(enc, a, preset=4, max_block=4096)
+        assert enc.set_parameter(2, 16, 48000, 2048, 2048, 2048, 0, 2) == E.OK
+        check(enc, a, preset=2, max_block=2048)             # same streams, other block size
+        assert enc.set_parameter(2, 16, 48000, 1024, 4096, 8192, 0, 4) == E.OK
+        check(enc, a, preset=4, max_block=4096, min_block=1024, lookahead=8192)     # variable blocks rewrite the device job list
+        assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+        check(enc, a2, preset=4, max_block=4096)
