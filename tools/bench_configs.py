@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Throughput of the other BASELINE.json configs (they are parity-test cases, not bench.py lines; this table is
+extra evidence that the widened paths run at scale).  Every configuration is encoded through the batch C ABI with
+pinned host buffers (H2D + kernels + D2H timed, best of 3 after a warm-up), a slice of it is encoded by the
+compiled reference (oracle/_ref) on one host thread and compared byte for byte, and the single-thread reference
+rate is reported beside it.
+
+  config 3: 48 kHz / 24-bit stereo, block 8192, mode 4, LTP order 3
+  config 4: 16-bit stereo, variable blocks -V 2 -L 4 (min 1024, max 4096, look-ahead 16384), mode 4
+  config 5: one GPU's shard of the 1024-file batch: 128 stereo 16-bit files of 30 s (1 440 000 frames = 351 blocks
+            of 4096 + a 2304-frame tail each), mode 4, one SRLAB200_EncodeStreamsHost call
+Usage: python tools/bench_configs.py [--files 128] [--seconds 60]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--files", type=int, default=128)
+    ap.add_argument("--seconds", type=int, default=60, help="length of the config 3 / 4 streams")
+    args = ap.parse_args()
+    import torch
+    from helpers import have_ref, ref_encode
+    from srla_b200 import encoder as E
+    from srla_b200.workload import make_blocks_workload
+
+    def pinned(a: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+
+    def run(name, streams, bits, min_block, max_block, lookahead, ltp, ref_frames):
+        with E.Encoder(max_channels=2, max_block=max_block, min_block=min_block, lookahead=lookahead) as enc:
+            assert enc.set_parameter(2, bits, 48000, min_block, max_block, lookahead, ltp, 4) == E.OK
+            cap = sum(enc.max_encoded_size(s.shape[1]) for s in streams)
+            out = pinned(np.empty(cap, dtype=np.uint8))
+            best = None
+            for it in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out, offs = enc.encode_streams_host(streams, out)
+                dt = time.perf_counter() - t0
+                if it:
+                    best = dt if best is None else min(best, dt)
+            st = enc.stats()
+            samples = sum(s.size for s in streams)
+            line = {"config": name, "streams": len(streams), "Msamples": samples / 1e6, "ms": best * 1e3,
+                    "e2e_Msamples_per_s": samples / best / 1e6, "blocks": int(st.num_blocks), "analysed_blocks": int(st.num_analysed),
+                    "compression": offs[-1] / float(st.bytes_in)}
+            if have_ref():
+                sl = np.ascontiguousarray(streams[0][:, :ref_frames].astype(np.int32))
+                t0 = time.perf_counter()
+                want = ref_encode(sl, bps=bits, max_block=max_block, min_block=min_block, lookahead=lookahead, ltp=ltp, preset=4)
+                dt = time.perf_counter() - t0
+                got = E.encode(sl, bps=bits, max_block=max_block, min_block=min_block, lookahead=lookahead, ltp=ltp, preset=4)
+                line["reference_1thread_Msamples_per_s"] = sl.size / dt / 1e6
+                line["identical_to_reference_on_slice"] = bool(got == want)
+            print(json.dumps(line), flush=True)
+
+    n = 48000 * args.seconds
+    wide = make_blocks_workload((n + 8191) // 8192, 8192, 2, 24, seed=77, num_templates=2, template_blocks=24)[:, :n]
+    run("3: 24-bit stereo, block 8192, mode 4, LTP 3", [pinned(wide.astype(np.int32))], 24, 8192, 8192, 8192, 3, 8192 * 12)
+    narrow = make_blocks_workload((n + 4095) // 4096, 4096, 2, 16, seed=78, num_templates=2, template_blocks=48)[:, :n]
+    run("4: 16-bit stereo, -V 2 -L 4 (1024..4096, look-ahead 16384), mode 4", [pinned(narrow.astype(np.int16))], 16, 1024, 4096, 16384, 0, 16384 * 6)
+    frames = 1_440_000
+    base = make_blocks_workload((frames + 4095) // 4096 + 1, 4096, 2, 16, seed=79, num_templates=2, template_blocks=88)
+    files = [pinned(np.roll(base, 4099 * k, axis=1)[:, :frames].astype(np.int16)) for k in range(args.files)]
+    run(f"5 (one GPU's shard): {args.files} stereo 16-bit files x 30 s, block 4096, mode 4", files, 16, 4096, 4096, 4096, 0, 4096 * 40)
+
+
+if __name__ == "__main__":
+    main()
