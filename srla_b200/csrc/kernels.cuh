@@ -180,6 +180,19 @@ __device__ __forceinline__ void butterfly4(const double2 a, const double2 b, con
     y3 = cmul(w.w3, cadd(amc, jbmd));
 }
 
+/* butterfly whose twiddles are the first entries of a stage table, exactly (1, 0): multiplying by them returns the
+ * operand (up to the sign of a zero), so the three complex products are skipped */
+__device__ __forceinline__ void butterfly4_unit(const double2 a, const double2 b, const double2 c, const double2 d,
+                                                double2 &y0, double2 &y1, double2 &y2, double2 &y3)
+{
+    const double2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
+    const double2 jbmd = make_double2(-bmd.y, bmd.x);
+    y0 = cadd(apc, bpd);
+    y1 = csub(amc, jbmd);
+    y2 = csub(apc, bpd);
+    y3 = cadd(amc, jbmd);
+}
+
 /* exact int32 -> double without the quarter-rate I2F.F64: 2^52 + 2^31 + x is representable */
 __device__ __forceinline__ double int_to_double(int32_t x)
 {
@@ -206,7 +219,7 @@ struct WindowSource {
         }
         const double ds1 = ds0 + step;
         const double w0 = div * ds0 * (dn1 - ds0), w1 = div * ds1 * (dn1 - ds1);
-        return make_double2((int_to_double(x0) * unit) * w0, (int_to_double(x1) * unit) * w1);
+        return make_double2(int_to_double(x0) * w0, int_to_double(x1) * w1);
     }
     __device__ __forceinline__ double one(uint32_t i, int32_t cur, int32_t prv) const
     {
@@ -215,7 +228,7 @@ struct WindowSource {
         const uint32_t s = (i < half_n) ? i : (n - 1u - i);
         const double ds = int_to_double((int32_t)s);
         const double w = div * ds * (dn1 - ds);              /* (n - 1 - s) as an exact double difference */
-        return (int_to_double(x) * unit) * w;
+        return int_to_double(x) * w;
     }
     __device__ __forceinline__ double2 element(uint32_t e) const
     {
@@ -358,7 +371,7 @@ __device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const u
         /* radix-4 stage of size 8 (s = M/8) fused with the final radix-2 stage (fft.c:114-123) */
         const uint32_t s = M >> 3;
         const uint32_t live = (need < s) ? need : s;
-        const Twiddle3 w0 = load_twiddle(tw8, 2u, 0u), w1 = load_twiddle(tw8, 2u, 1u);
+        const Twiddle3 w1 = load_twiddle(tw8, 2u, 1u);             /* entry 0 is (1, 0): butterfly4_unit */
         #pragma unroll 1
         for (uint32_t u = tid; u < live; u += T) {
             double2 v[2][4], y[2][4];
@@ -367,7 +380,7 @@ __device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const u
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) { v[pp][j] = x[fft_slot((uint32_t)pp * s + u + (uint32_t)j * (M >> 2))]; }
             }
-            butterfly4(v[0][0], v[0][1], v[0][2], v[0][3], w0, y[0][0], y[0][1], y[0][2], y[0][3]);
+            butterfly4_unit(v[0][0], v[0][1], v[0][2], v[0][3], y[0][0], y[0][1], y[0][2], y[0][3]);
             butterfly4(v[1][0], v[1][1], v[1][2], v[1][3], w1, y[1][0], y[1][1], y[1][2], y[1][3]);
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -379,11 +392,11 @@ __device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const u
         /* single radix-4 stage of size 4 (s = M/4): twiddle index 0 only */
         const uint32_t s = M >> 2;
         const uint32_t live = (need < s) ? need : s;
-        const Twiddle3 w = load_twiddle(tw4, 1u, 0u);
+        (void)tw4;                                                  /* the only twiddle of this stage is (1, 0) */
         #pragma unroll 1
         for (uint32_t u = tid; u < live; u += T) {
             double2 y0, y1, y2, y3;
-            butterfly4(x[fft_slot(u)], x[fft_slot(u + s)], x[fft_slot(u + 2u * s)], x[fft_slot(u + 3u * s)], w, y0, y1, y2, y3);
+            butterfly4_unit(x[fft_slot(u)], x[fft_slot(u + s)], x[fft_slot(u + 2u * s)], x[fft_slot(u + 3u * s)], y0, y1, y2, y3);
             x[fft_slot(u)] = y0; x[fft_slot(u + s)] = y1; x[fft_slot(u + 2u * s)] = y2; x[fft_slot(u + 3u * s)] = y3;
         }
     } else if (nn == 2u) {
@@ -425,7 +438,9 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
     }
     const uint32_t M = N >> 1;
     WindowSource<kPre> ws;
-    ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = unit; ws.div = div; ws.dn1 = (double)(int32_t)(n - 1u);
+    /* unit = 2^-(bps-1) is a power of two: (x * unit) * w == x * (w * unit) exactly and w * unit == ((div * unit) * s) * (n-1-s)
+     * exactly (no subnormals: |w| >= 4 / n^2 * 2^-23), so the scale rides on the divisor and costs no multiply per sample */
+    ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = 1.0; ws.div = div * unit; ws.dn1 = (double)(int32_t)(n - 1u);
     ws.full = (n == N) && (N >= 32u);
     const uint32_t want = (nlags < N) ? nlags : N;
     /* dir 0: forward transform of the windowed samples; dir 1: the inverse transform, evaluated as the
@@ -472,20 +487,15 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
                 double p_lo, p_hi;
                 if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
                 else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
-                /* inverse, flag = +1: c2 = +0.5, imaginary parts are 0.0 */
+                /* inverse, flag = +1: c2 = +0.5.  The power spectrum is real, so h1i and h2r of fft.c:171-184 are
+                 * exact zeros and every term they enter only adds +-0.0: g1 = h1r - wi*h2i, g2 = g4 = wr*h2i,
+                 * g3 = h1r + wi*h2i are the same values (up to the sign of a zero, which cannot reach a decision) */
                 {
-                    const double c2 = 0.5;
-                    const double zl = 0.0, zh = 0.0;
                     const double h1r = 0.5 * (p_lo + p_hi);
-                    const double h1i = 0.5 * (zl - zh);
-                    const double h2r = -c2 * (zl + zh);
-                    const double h2i = c2 * (p_lo - p_hi);
-                    const double g1 = h1r + (wr * h2r) - (wi_b * h2i);
-                    const double g2 = h1i + (wr * h2i) + (wi_b * h2r);
-                    const double g3 = h1r - (wr * h2r) + (wi_b * h2i);
-                    const double g4 = -h1i + (wr * h2i) + (wi_b * h2r);
-                    if (lo != hi) { cx[fft_slot(lo)] = make_double2(g1, -g2); }
-                    cx[fft_slot(hi)] = make_double2(g3, -g4);
+                    const double h2i = 0.5 * (p_lo - p_hi);
+                    const double t = wi_b * h2i, g2 = wr * h2i;
+                    if (lo != hi) { cx[fft_slot(lo)] = make_double2(h1r - t, -g2); }
+                    cx[fft_slot(hi)] = make_double2(h1r + t, -g2);
                 }
             }
             if (tid == 0) {
