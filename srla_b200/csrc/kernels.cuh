@@ -4,7 +4,8 @@
  *   lshift_jobs_kernel / lshift_finish_kernel whole-stream OR reduce -> trailing-zero shift   (A0)
  *   front_kernel<BPT>       one CTA per (block, candidate channel): mid/side, pre-emphasis, optional LTP,
  *                           Welch window + FFT autocorrelation, block resident in shared memory (A2-A5, A11)
- *   lpc_kernel              one thread per candidate: Levinson-Durbin, order choice, quantisation   (A5, A6)
+ *   lpc_levinson_kernel     one thread per candidate: Levinson-Durbin, reflection coefficients + error variances (A5)
+ *   lpc_select_kernel       order choice (parallel over orders), coefficient rebuild, quantisation          (A6)
  *   residual_kernel         one CTA per candidate: int32 FIR residual, Rice search, side-info bits   (A3, A7, A8)
  *   decide_kernel           block type, stereo method, exact block size                       (A1, A2)
  *   scan_kernel             output offsets of the blocks / streams
@@ -871,73 +872,61 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
  * ([index][lane]) so every access is conflict free.  The coefficient vector is updated in place in
  * symmetric pairs (new[i], new[k+1-i] depend only on prev[i], prev[k+1-i]).
  * ---------------------------------------------------------------------------------------------- */
-struct OrderPick { double best; uint32_t arg; };
-__device__ __forceinline__ void consider_order(OrderPick &pk, double err_k, uint32_t k, double gain, uint32_t n, uint32_t bps)
+/* estimated size of a block coded with the error variance of one order (srla_encoder.c:938-950, with the
+ * window-compensated variance of lpc.c:493) */
+__device__ __forceinline__ double order_bits(double err_k, uint32_t k, double gain, uint32_t n, uint32_t bps)
 {
-    /* srla_encoder.c:938-950 with the window-compensated variance of lpc.c:493 */
     const double ev = err_k * gain;
     const double mean_abs = 2.0 * sqrt(ev / 2.0);
     double bits = geometric_entropy(mean_abs, bps) * (double)n;
     bits += (double)(8u * k);
-    if (pk.best > bits) { pk.best = bits; pk.arg = k; }
+    return bits;
 }
 
-/* Levinson-Durbin up to order `stop` for this lane's candidate; when pk != NULL every order's
- * estimated size is considered on the way.  Returns nothing: the vector a[0..stop] is in A. */
 #define LPC_R(i) R[(size_t)(i) * 32u + lane]
 #define LPC_A(i) A[(size_t)(i) * 32u + lane]
-__device__ __forceinline__ void levinson_lane(const double *R, double *A, const uint32_t lane, const uint32_t stop,
-                                              OrderPick *pk, double gain, uint32_t n, uint32_t bps, double *diag_err)
+/* step k of the recursion's coefficient update: new[i] = prev[i] + refl * prev[k+1-i] (lpc.c:432-435) in symmetric
+ * pairs; four pairs are loaded before any is stored so the shared-memory latencies overlap */
+__device__ __forceinline__ void levinson_update(double *A, const uint32_t lane, const uint32_t k, const double refl)
 {
-    const double r0 = LPC_R(0), r1 = LPC_R(1);
-    double e = r0;
-    const double a1 = -r1 / r0;
-    LPC_A(0) = 1.0; LPC_A(1) = a1;
-    e = e + r1 * a1;
-    if (diag_err) { diag_err[0] = r0 * gain; diag_err[1] = e * gain; }
-    if (pk) { consider_order(*pk, e, 1u, gain, n, bps); }
-    for (uint32_t k = 1; k < stop; ++k) {
-        double acc = 0.0;
-        uint32_t i = 0;
-        for (; i + 4u <= k + 1u; i += 4u) {
-            const double m0 = LPC_A(i) * LPC_R(k + 1u - i), m1 = LPC_A(i + 1u) * LPC_R(k - i);
-            const double m2 = LPC_A(i + 2u) * LPC_R(k - 1u - i), m3 = LPC_A(i + 3u) * LPC_R(k - 2u - i);
-            acc += m0; acc += m1; acc += m2; acc += m3;
-        }
-        for (; i <= k; ++i) { acc += LPC_A(i) * LPC_R(k + 1u - i); }
-        const double refl = acc / (-e);
-        e = e * (1.0 - refl * refl);
-        LPC_A(k + 1u) = 0.0;
-        /* new[i] = prev[i] + refl * prev[k+1-i] (lpc.c:432-435) in symmetric pairs; four pairs are loaded before
-         * any is stored so the shared-memory latencies overlap */
-        const uint32_t npairs = (k + 2u) >> 1;
-        uint32_t j = 0;
-        for (; j + 4u <= npairs; j += 4u) {
-            const double a0 = LPC_A(j), a1 = LPC_A(j + 1u), a2 = LPC_A(j + 2u), a3 = LPC_A(j + 3u);
-            const double b0 = LPC_A(k + 1u - j), b1 = LPC_A(k - j), b2 = LPC_A(k - 1u - j), b3 = LPC_A(k - 2u - j);
-            LPC_A(j) = a0 + refl * b0; LPC_A(j + 1u) = a1 + refl * b1; LPC_A(j + 2u) = a2 + refl * b2; LPC_A(j + 3u) = a3 + refl * b3;
-            LPC_A(k + 1u - j) = b0 + refl * a0; LPC_A(k - j) = b1 + refl * a1; LPC_A(k - 1u - j) = b2 + refl * a2; LPC_A(k - 2u - j) = b3 + refl * a3;
-        }
-        for (; j < npairs; ++j) {
-            const double t1 = LPC_A(j), t2 = LPC_A(k + 1u - j);
-            LPC_A(j) = t1 + refl * t2;
-            LPC_A(k + 1u - j) = t2 + refl * t1;
-        }
-        if (((k + 1u) & 1u) == 0u) { const uint32_t mid = (k + 1u) >> 1; const double t = LPC_A(mid); LPC_A(mid) = t + refl * t; }
-        if (diag_err) { diag_err[k + 1u] = e * gain; }
-        if (pk) { consider_order(*pk, e, k + 1u, gain, n, bps); }
+    LPC_A(k + 1u) = 0.0;
+    const uint32_t npairs = (k + 2u) >> 1;
+    uint32_t j = 0;
+    for (; j + 4u <= npairs; j += 4u) {
+        const double a0 = LPC_A(j), a1 = LPC_A(j + 1u), a2 = LPC_A(j + 2u), a3 = LPC_A(j + 3u);
+        const double b0 = LPC_A(k + 1u - j), b1 = LPC_A(k - j), b2 = LPC_A(k - 1u - j), b3 = LPC_A(k - 2u - j);
+        LPC_A(j) = a0 + refl * b0; LPC_A(j + 1u) = a1 + refl * b1; LPC_A(j + 2u) = a2 + refl * b2; LPC_A(j + 3u) = a3 + refl * b3;
+        LPC_A(k + 1u - j) = b0 + refl * a0; LPC_A(k - j) = b1 + refl * a1; LPC_A(k - 1u - j) = b2 + refl * a2; LPC_A(k - 2u - j) = b3 + refl * a3;
     }
+    for (; j < npairs; ++j) {
+        const double t1 = LPC_A(j), t2 = LPC_A(k + 1u - j);
+        LPC_A(j) = t1 + refl * t2;
+        LPC_A(k + 1u - j) = t2 + refl * t1;
+    }
+    if (((k + 1u) & 1u) == 0u) { const uint32_t mid = (k + 1u) >> 1; const double t = LPC_A(mid); LPC_A(mid) = t + refl * t; }
 }
 
-__global__ void __launch_bounds__(32) lpc_kernel(const __grid_constant__ LaunchParams p)
+/* ------------------------------------------------------------------------------------------------
+ * lpc_levinson_kernel: one THREAD per candidate (32 candidates per CTA).  Ridge and the Levinson-Durbin
+ * recursion for all orders (lpc.c:379-441, 483-493).  The recursion is sequential in the order and its
+ * reflection numerators are sequential sums in the reference's order, so the work of one candidate is a
+ * dependent chain: it gets one lane, and the lags / coefficient vectors of the 32 candidates of a warp are
+ * interleaved in shared memory ([index][lane]) so every access is conflict free.  The kernel keeps ONLY what the
+ * chain needs: it records every order's reflection coefficient and error variance ([group][2][P+2][32] doubles)
+ * and leaves the order choice (64 independent entropy estimates per candidate -- `log`, `sqrt`, divisions) and
+ * the rebuild of the chosen order's coefficients to lpc_select_kernel, which has the parallelism for them.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(32) lpc_levinson_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t P = p.max_order, bps = p.bps;
+    const uint32_t P = p.max_order;
     const uint32_t lane = threadIdx.x;
     const uint32_t total = p.num_jobs * p.ncand;
     const uint32_t first = blockIdx.x * 32u;
     double *R = reinterpret_cast<double *>(smem);            /* [P + 2][32] */
     double *A = R + (size_t)(P + 2u) * 32u;                  /* [P + 3][32] */
+    double *g_refl = p.lpc_state + (size_t)blockIdx.x * 2u * (P + 2u) * 32u;     /* [P + 2][32]: a1, then the reflection of every step */
+    double *g_err = g_refl + (size_t)(P + 2u) * 32u;                            /* [P + 2][32]: error variance of every order */
     /* the front kernel stores the lags of 32 consecutive candidates interleaved ([lag][candidate % 32]):
      * coalesced loads, conflict-free stores */
     {
@@ -949,28 +938,112 @@ __global__ void __launch_bounds__(32) lpc_kernel(const __grid_constant__ LaunchP
     if (idx >= total) { return; }
     const uint32_t job_id = idx / p.ncand;
     const uint32_t n = p.jobs[job_id].nsmpl;
-    CandOut *out = p.cand + idx;
+    const CandOut *out = p.cand + idx;
     if (n <= P || out->status != 0u) { return; }
     const double gain = p.jobs[job_id].welch_gain;
     CandDiag *dg = p.diag ? p.diag + idx : nullptr;
     LPC_R(0) = LPC_R(0) * (1.0 + 1e-5);                      /* ridge, lpc.c:483 */
     if (dg) { for (uint32_t i = 0; i <= P; ++i) { dg->autocorr[i] = LPC_R(i); } }
-
-    OrderPick pk; pk.best = (double)FLT_MAX; pk.arg = 0u;
-    const bool degenerate = fabs(LPC_R(0)) < (double)FLT_EPSILON;      /* lpc.c:399-407: all vectors zero, variances r[0] */
-    if (degenerate) {
-        const double r0 = LPC_R(0);
-        for (uint32_t k = 1; k <= P; ++k) { consider_order(pk, r0, k, gain, n, bps); }
+    const double r0 = LPC_R(0), r1 = LPC_R(1);
+    if (fabs(r0) < (double)FLT_EPSILON) {
+        /* lpc.c:399-407: all coefficient vectors zero, every variance r[0] */
+        for (uint32_t k = 0; k <= P; ++k) { g_refl[(size_t)k * 32u + lane] = 0.0; g_err[(size_t)k * 32u + lane] = r0; }
         if (dg) { for (uint32_t i = 0; i <= P; ++i) { dg->error_vars[i] = r0 * gain; } }
-    } else {
-        levinson_lane(R, A, lane, P, &pk, gain, n, bps, dg ? dg->error_vars : nullptr);
+        return;
     }
-    const uint32_t order = pk.arg;
+    double e = r0;
+    const double a1 = -r1 / r0;
+    LPC_A(0) = 1.0; LPC_A(1) = a1;
+    e = e + r1 * a1;
+    g_refl[lane] = a1; g_err[lane] = r0; g_err[32u + lane] = e;
+    if (dg) { dg->error_vars[0] = r0 * gain; dg->error_vars[1] = e * gain; }
+    for (uint32_t k = 1; k < P; ++k) {
+        double acc = 0.0;
+        uint32_t i = 0;
+        for (; i + 4u <= k + 1u; i += 4u) {
+            const double m0 = LPC_A(i) * LPC_R(k + 1u - i), m1 = LPC_A(i + 1u) * LPC_R(k - i);
+            const double m2 = LPC_A(i + 2u) * LPC_R(k - 1u - i), m3 = LPC_A(i + 3u) * LPC_R(k - 2u - i);
+            acc += m0; acc += m1; acc += m2; acc += m3;
+        }
+        for (; i <= k; ++i) { acc += LPC_A(i) * LPC_R(k + 1u - i); }
+        const double refl = acc / (-e);
+        e = e * (1.0 - refl * refl);
+        levinson_update(A, lane, k, refl);
+        g_refl[(size_t)k * 32u + lane] = refl; g_err[(size_t)(k + 1u) * 32u + lane] = e;
+        if (dg) { dg->error_vars[k + 1u] = e * gain; }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * lpc_select_kernel: one CTA (128 threads) per 32 candidates.  Phase 1, all four warps: the estimated size of
+ * every order (thread = candidate x order mod 4), first minimum (srla_encoder.c:934-957).  Phase 2, warp 0, one
+ * lane per candidate: the chosen order's coefficient vector is rebuilt from the recorded reflection coefficients
+ * (the recursion's update steps replayed: the same operations on the same values as the reference's second run),
+ * then quantised with error feedback from the tail (lpc.c:1341-1405) and reversed for the FIR
+ * (srla_encoder.c:1104-1108).
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(128) lpc_select_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t P = p.max_order, bps = p.bps;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, part = tid >> 5;
+    const uint32_t total = p.num_jobs * p.ncand;
+    double *A = reinterpret_cast<double *>(smem);                               /* [P + 3][32] */
+    double *best_bits = A + (size_t)(P + 3u) * 32u;                             /* [4][32] */
+    uint32_t *best_arg = reinterpret_cast<uint32_t *>(best_bits + 4u * 32u);    /* [4][32] */
+    const double *g_refl = p.lpc_state + (size_t)blockIdx.x * 2u * (P + 2u) * 32u;
+    const double *g_err = g_refl + (size_t)(P + 2u) * 32u;
+    const uint32_t idx = blockIdx.x * 32u + lane;
+    bool live = idx < total;
+    uint32_t n = 0; double gain = 0.0;
+    CandOut *out = p.cand + (live ? idx : 0u);
+    if (live) {
+        const uint32_t job_id = idx / p.ncand;
+        n = p.jobs[job_id].nsmpl; gain = p.jobs[job_id].welch_gain;
+        live = (n > P) && (out->status == 0u);
+    }
+    /* phase 1: orders part + 1, part + 5, ... ; strict comparison in ascending order = the reference's first minimum.
+     * The variances of eight orders are fetched before any is evaluated: one memory latency per eight estimates. */
+    {
+        double best = (double)FLT_MAX; uint32_t arg = 0u;
+        if (live) {
+            for (uint32_t k0 = 1u + part; k0 <= P; k0 += 32u) {
+                double ev[8];
+                #pragma unroll
+                for (int t = 0; t < 8; ++t) { const uint32_t k = k0 + 4u * (uint32_t)t; ev[t] = (k <= P) ? g_err[(size_t)k * 32u + lane] : 0.0; }
+                #pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t k = k0 + 4u * (uint32_t)t;
+                    if (k <= P) {
+                        const double bits = order_bits(ev[t], k, gain, n, bps);
+                        if (best > bits) { best = bits; arg = k; }
+                    }
+                }
+            }
+        }
+        best_bits[part * 32u + lane] = best; best_arg[part * 32u + lane] = arg;
+    }
+    __syncthreads();
+    if (part != 0u || !live) { return; }
+    uint32_t order = 0u;
+    {
+        double best = (double)FLT_MAX;
+        for (uint32_t q = 0; q < 4u; ++q) {
+            const double b = best_bits[q * 32u + lane]; const uint32_t a = best_arg[q * 32u + lane];
+            if (a != 0u && (best > b || (best == b && a < order))) { best = b; order = a; }
+        }
+    }
+    CandDiag *dg = p.diag ? p.diag + idx : nullptr;
     uint32_t rshift = 0;
     if (order > 0u) {
-        if (degenerate) { for (uint32_t i = 0; i <= order; ++i) { LPC_A(i) = 0.0; } }
-        else if (order != P) { levinson_lane(R, A, lane, order, nullptr, gain, n, bps, nullptr); }
-        /* quantisation with error feedback from the tail (lpc.c:1341-1405), reversed for the FIR */
+        /* phase 2: replay the update steps 1 .. order-1 (reflection coefficients fetched one step ahead) */
+        LPC_A(0) = 1.0; LPC_A(1) = g_refl[lane];
+        double next = (order > 1u) ? g_refl[32u + lane] : 0.0;
+        for (uint32_t k = 1; k < order; ++k) {
+            const double refl = next;
+            if (k + 1u < order) { next = g_refl[(size_t)(k + 1u) * 32u + lane]; }
+            levinson_update(A, lane, k, refl);
+        }
         double peak = 0.0;
         for (uint32_t i = 1; i <= order; ++i) { const double v = fabs(LPC_A(i)); if (peak < v) { peak = v; } }
         if (peak <= 0.0078125) {
@@ -1030,9 +1103,11 @@ __device__ __forceinline__ uint32_t coding_parameter(double m, uint32_t code_typ
         for (int j = 1; j < 32; ++j) { if (m >= __ldg(rice_threshold + j)) { k = (uint32_t)j; } }   /* host-libm thresholds */
         return k;
     }
+    /* floor(log2((uint32_t)max(1.0, g))) (srla_coder.c:305-309) is the binary exponent of g when g >= 1 and 0 below:
+     * read it from the exponent field instead of converting (F2I.F64 issues at a quarter of the rate) */
     const double g = 0.66794162356 * (1.0 + m);
-    const uint32_t golomb = (uint32_t)((1.0 > g) ? 1.0 : g);
-    return 31u - (uint32_t)__clz((int)golomb);
+    const int e = ((__double2hiint(g) >> 20) & 0x7ff) - 1023;
+    return (uint32_t)max(e, 0);
 }
 
 /* variable part of the code length of u with parameter k: recursive Rice max((u >> k) - 2, 0), Rice u >> k

@@ -91,7 +91,7 @@ struct DeviceCtx {
     DevBuf streams, jobs, misc, stream_begin, pcm, out;
     /* a lane = one compute stream + its own per-group scratch; alternate groups of a call run on different
      * lanes so the latency-bound kernels of one group (lpc, scan) overlap the throughput-bound ones of the next */
-    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags; };
+    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags, lpc_state; };
     Lane lane[kMaxLanes];
     int lanes = 3;                 /* SRLA_B200_LANES */
     int groups = 8;                /* SRLA_B200_GROUPS: groups a large call is split into */
@@ -109,7 +109,7 @@ struct DeviceCtx {
     std::vector<Job> jobs_scratch;
     std::vector<uint32_t> jobs_key;   /* stream lengths + block size of the fixed tiling that jobs_scratch and the device copy hold */
     bool jobs_cached = false;
-    uint32_t smem_set[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    uint32_t smem_set[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     int max_smem_optin = 0;
     int num_sms = 0;
     int front_occ = 3;             /* CTAs per SM front_kernel<128> is register-sized for (SRLA_B200_FRONT_OCC=3|4, tuning) */
@@ -212,7 +212,7 @@ void ctx_destroy(DeviceCtx *c)
     for (int l = 0; l < kMaxLanes; l++) {
         if (c->lane[l].own) { cudaStreamSynchronize(c->lane[l].own); cudaStreamDestroy(c->lane[l].own); }
         if (c->lane[l].done) { cudaEventDestroy(c->lane[l].done); }
-        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags };
+        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags, &c->lane[l].lpc_state };
         for (DevBuf *b : lb) { b->release(); }
     }
     if (c->ev_fork) { cudaEventDestroy(c->ev_fork); }
@@ -451,9 +451,10 @@ struct Runner {
         launches++;
         if (!mark(batch, 1, on)) { return false; }
         if (p.max_order > 0) {
-            if (!prep_kernel(lpc_kernel, LL.total, 2)) { return false; }
-            lpc_kernel<<<(ncands + 31u) / 32u, 32, LL.total, on>>>(p);
-            launches++;
+            if (!prep_kernel(lpc_levinson_kernel, LL.total, 2) || !prep_kernel(lpc_select_kernel, LL.select_total, 8)) { return false; }
+            lpc_levinson_kernel<<<(ncands + 31u) / 32u, 32, LL.total, on>>>(p);
+            lpc_select_kernel<<<(ncands + 31u) / 32u, 128, LL.select_total, on>>>(p);
+            launches += 2;
         }
         if (!mark(batch, 2, on)) { return false; }
         if (!prep_kernel(residual_kernel, RL.total, 3)) { return false; }
@@ -505,7 +506,8 @@ struct Runner {
         if (pl.want_diag && !L.diag.reserve(sizeof(CandDiag) * ncand * count)) { return false; }
         p.lag_stride = round_up_u32(p.max_order + 2u, 2);
         if (!L.lags.reserve(sizeof(double) * round_up_u32((uint32_t)(ncand * count), 32) * (size_t)p.lag_stride)) { return false; }
-        p.lags = (double *)L.lags.p;
+        if (!L.lpc_state.reserve(sizeof(double) * (size_t)(round_up_u32((uint32_t)(ncand * count), 32) / 32u) * 2u * (p.max_order + 2u) * 32u)) { return false; }
+        p.lags = (double *)L.lags.p; p.lpc_state = (double *)L.lpc_state.p;
         p.cand = (CandOut *)L.cand.p; p.jobout = (JobOut *)L.jobout.p;
         p.residual = store_residual ? (int32_t *)L.residual.p : nullptr;
         p.diag = pl.want_diag ? (CandDiag *)L.diag.p : nullptr;

@@ -93,6 +93,7 @@ struct LaunchParams {
     int32_t         *residual;       /* [job][cand][res_stride] or NULL (size-only pass)   */
     double          *lags;           /* [job][cand][lag_stride]: autocorrelation lags 0..P  */
     uint32_t lag_stride;
+    double          *lpc_state;      /* [candidate group of 32][2][P+2][32]: reflection coefficients, error variances */
     uint32_t num_jobs, num_streams;
     uint32_t nch, ncand, bps;
     uint32_t max_order;              /* preset's maximum LPC order                         */
@@ -153,12 +154,13 @@ SRLA_HD inline FrontLayout make_front_layout(uint32_t nmax, uint32_t fft_max, ui
     return L;
 }
 
-/* lpc_kernel: lags and one coefficient vector of 32 candidates, interleaved [index][lane] */
-struct LpcLayout { uint32_t total; };
+/* lpc kernels: lags and one coefficient vector of 32 candidates, interleaved [index][lane] */
+struct LpcLayout { uint32_t total; uint32_t select_total; };
 SRLA_HD inline LpcLayout make_lpc_layout(uint32_t P)
 {
     LpcLayout L;
     L.total = 8u * 32u * ((P + 2u) + (P + 3u));
+    L.select_total = 8u * 32u * (P + 3u) + (8u + 4u) * 4u * 32u;      /* coefficient vectors + per-warp best (bits, order) */
     return L;
 }
 
