@@ -310,7 +310,7 @@ def main() -> None:
     sampler = ClockSampler(local_rank)
     sampler.start()
     an_ms, em_ms, launches = [], [], 0
-    k_ms = {"front_kernel": [], "lpc_kernel": [], "residual_kernel": [], "emit_kernel(+decide+scan)": []}
+    k_ms = {"front_kernel": [], "lpc_kernels(levinson+select)": [], "residual_kernel": [], "emit_kernel(+decide+scan)": []}
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -318,7 +318,7 @@ def main() -> None:
         step_device()
         st = enc.stats()
         an_ms.append(st.ms_analyse); em_ms.append(st.ms_emit); launches += int(st.kernel_launches)
-        k_ms["front_kernel"].append(st.ms_front); k_ms["lpc_kernel"].append(st.ms_lpc)
+        k_ms["front_kernel"].append(st.ms_front); k_ms["lpc_kernels(levinson+select)"].append(st.ms_lpc)
         k_ms["residual_kernel"].append(st.ms_residual); k_ms["emit_kernel(+decide+scan)"].append(st.ms_emit)
     e1.record(stream)
     barrier()
@@ -380,7 +380,7 @@ def main() -> None:
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
     alg_bytes = int(st.bytes_in) + bytes_out              # PCM in (2 B/sample) + encoded bytes out
     kernel_ms = {k: float(np.mean(v)) for k, v in k_ms.items()}
-    dominant = max(("front_kernel", "lpc_kernel", "residual_kernel"), key=lambda k: kernel_ms[k])
+    dominant = max(("front_kernel", "lpc_kernels(levinson+select)", "residual_kernel"), key=lambda k: kernel_ms[k])
     an = kernel_ms[dominant]
     achieved = alg_bytes / (an * 1e-3) / 1e9
     traffic = load_traffic()
