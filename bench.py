@@ -250,6 +250,11 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the SRLA B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # Everything libraries print on the way (NCCL's version banner goes to stdout) is sent to stderr: stdout carries
+    # exactly ONE line, the JSON below.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -427,8 +432,11 @@ def main() -> None:
                       "order_histogram_by_16": [int(hist[i:i + 16].sum()) for i in range(0, 80, 16)],
                       "stereo_methods_LR_MS_LS_SR": list(st.method_histogram[:]),
                       "block_types_compress_silent_raw": list(st.type_histogram[:])}}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
