@@ -748,6 +748,17 @@ __device__ __forceinline__ void apply_ltp(int32_t *sig, int32_t *tmp, uint32_t n
  * front_kernel: one CTA per (job, candidate).  Pre-emphasis decision, optional LTP analysis, and
  * the Welch-windowed FFT autocorrelation of the signal the LPC stage sees; lags 0..P go to HBM.
  * ---------------------------------------------------------------------------------------------- */
+/* 16-bit pair entry of the filtered samples x[0..4] = signal[4j .. 4j+4] (see residual_kernel) */
+__device__ __forceinline__ int4 pack_pair_entry(const int32_t x[5])
+{
+    int4 z;
+    z.x = (int32_t)(((uint32_t)x[0] & 0xffffu) | ((uint32_t)x[1] << 16));
+    z.y = (int32_t)(((uint32_t)x[2] & 0xffffu) | ((uint32_t)x[3] << 16));
+    z.z = (int32_t)(((uint32_t)x[1] & 0xffffu) | ((uint32_t)x[2] << 16));
+    z.w = (int32_t)(((uint32_t)x[3] & 0xffffu) | ((uint32_t)x[4] << 16));
+    return z;
+}
+
 /* pre-emphasis coefficient (srla_utility.c:214-257) from the candidate samples raw[0..n): r0, r1 as exact
  * integers.  Every thread returns the coefficient; thread 0 also records it. */
 template <int kT>
@@ -1417,96 +1428,133 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     const uint32_t order = out->order, rshift = out->rshift, ltp_period = out->ltp_period;
     const int32_t pre_coef = out->pre_coef;
 
-    /* ---- rebuild the signal the FIR runs on ---- */
-    (void)load_candidate<2>(st, job, p, cand, lshift, region_i);        /* 64 registers per thread: two quads (x 2 channels) in flight */
     const uint32_t p4 = round_up_u32(order, 4);
     for (uint32_t i = tid; i < p4; i += kThreads) { coef_s[i] = (i < p4 - order) ? 0 : (int32_t)out->coef[i - (p4 - order)]; }
-    __syncthreads();
-    for (uint32_t m = tid; m < (p4 >> 2); m += kThreads) {
-        coef_b[m] = (int32_t)(((uint32_t)coef_s[4u * m] & 0xffu) | (((uint32_t)coef_s[4u * m + 1u] & 0xffu) << 8)
-                            | (((uint32_t)coef_s[4u * m + 2u] & 0xffu) << 16) | (((uint32_t)coef_s[4u * m + 3u] & 0xffu) << 24));
-    }
-    apply_preemphasis(region_i, sig, n, pre_coef);
-    __syncthreads();
-    if (ltp_period > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, ltp_period, out->ltp_coef[0], out->ltp_coef[1], out->ltp_coef[2]); }
-
-    /* ---- FIR residual, int32 wrapping ---- */
     int32_t *res_s = region_i;
     unsigned char *scratch = smem + L.region_off + round_up_u32(4u * round_up_u32(n, 4), 16);
     int32_t *res_g = p.residual ? p.residual + ((size_t)job_id * p.ncand + cand) * p.res_stride : nullptr;
-    if (order > 0u) {
-        const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
-        /* Every group of outputs that reaches past the warm-up (first output >= order, or straddling it) runs the
-         * full padded filter: for an output i >= order the taps that fall in front of the block carry zero
-         * coefficients (order is padded to p4 in FRONT), so they may read anything addressable.  Warm-up outputs
-         * (i < order: first differences, srla_lpc_predict.c:251-254) are patched in afterwards.  No output is ever
-         * computed by a serial loop: one slow thread would hold the whole CTA at the next barrier. */
-        /* 16-bit pair entries (see the header comment); entry of sample quad j at Z[zpair_slot(j + zf)] */
-        int4 *Z = reinterpret_cast<int4 *>(scratch);
-        const uint32_t zf = resid_pair_front(p.max_order);
-        const uint32_t zcount = round_up_u32(n, 8) >> 2;
-        int fits = 1;
+    const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
+    /* ---- the signal the FIR runs on, as 16-bit pair entries (entry j = samples 4j .. 4j+4 at Z[zpair_slot(j + zf)]) ---- */
+    int4 *Z = reinterpret_cast<int4 *>(scratch);
+    const uint32_t zf = resid_pair_front(p.max_order);
+    const uint32_t zcount = round_up_u32(n, 8) >> 2;
+    (void)load_candidate<2>(st, job, p, cand, lshift, region_i);        /* two quads (x 2 channels) in flight; four measured slower */
+    __syncthreads();
+    int fits = 1;
+    if (ltp_period == 0u) {
+        /* pre-emphasis (srla_utility.c:342-358, filter memory = first sample) folded into the packing: raw -> entries */
+        const int32_t *raw = region_i;
+        const uint32_t pc = (uint32_t)pre_coef;
         for (uint32_t jj = tid; jj < zcount + 1u; jj += kThreads) {
-            /* sig is zero beyond n (apply_preemphasis pads 12 samples past the rounded end) and in the four samples in
-             * front of the block; entry -1 is written too because its last pair (x[-1], x[0]) carries a real sample */
+            const int32_t j = (int32_t)jj - 1;
+            int32_t x[5];
+            if (j >= 0 && 4u * (uint32_t)j + 4u < n) {
+                const int4 q = *reinterpret_cast<const int4 *>(raw + 4 * j);
+                const int32_t nxt = raw[4 * j + 4], prv = raw[j ? 4 * j - 1 : 0];
+                x[0] = (int32_t)((uint32_t)q.x - (uint32_t)((int32_t)((uint32_t)prv * pc) >> 4));
+                x[1] = (int32_t)((uint32_t)q.y - (uint32_t)((int32_t)((uint32_t)q.x * pc) >> 4));
+                x[2] = (int32_t)((uint32_t)q.z - (uint32_t)((int32_t)((uint32_t)q.y * pc) >> 4));
+                x[3] = (int32_t)((uint32_t)q.w - (uint32_t)((int32_t)((uint32_t)q.z * pc) >> 4));
+                x[4] = (int32_t)((uint32_t)nxt - (uint32_t)((int32_t)((uint32_t)q.w * pc) >> 4));
+            } else {
+                #pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const int32_t i = 4 * j + t;
+                    int32_t v = 0;
+                    if (i >= 0 && (uint32_t)i < n) { v = (int32_t)((uint32_t)raw[i] - (uint32_t)((int32_t)((uint32_t)raw[i ? i - 1 : 0] * pc) >> 4)); }
+                    x[t] = v;
+                }
+            }
+            #pragma unroll
+            for (int t = 0; t < 4; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
+            Z[zpair_slot(jj + zf - 1u)] = pack_pair_entry(x);
+        }
+    } else {
+        apply_preemphasis(region_i, sig, n, pre_coef);
+        __syncthreads();
+        apply_ltp(sig, region_i, n, p.ltp_order, ltp_period, out->ltp_coef[0], out->ltp_coef[1], out->ltp_coef[2]);
+        for (uint32_t jj = tid; jj < zcount + 1u; jj += kThreads) {
+            /* sig is zero beyond n (apply_preemphasis pads 12 samples past the rounded end) and in the four samples in front */
             const int32_t j = (int32_t)jj - 1;
             const int4 q = *reinterpret_cast<const int4 *>(sig + 4 * j);
             const int32_t x[5] = { q.x, q.y, q.z, q.w, sig[4 * j + 4] };
             #pragma unroll
             for (int t = 0; t < 4; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
-            int4 z;
-            z.x = (int32_t)(((uint32_t)x[0] & 0xffffu) | ((uint32_t)x[1] << 16));
-            z.y = (int32_t)(((uint32_t)x[2] & 0xffffu) | ((uint32_t)x[3] << 16));
-            z.z = (int32_t)(((uint32_t)x[1] & 0xffffu) | ((uint32_t)x[2] << 16));
-            z.w = (int32_t)(((uint32_t)x[3] & 0xffffu) | ((uint32_t)x[4] << 16));
-            Z[zpair_slot((uint32_t)(j + (int32_t)zf))] = z;
+            Z[zpair_slot(jj + zf - 1u)] = pack_pair_entry(x);
         }
-        fits = __syncthreads_and(fits);
-        if (fits) {
-            const uint32_t groups = (n + 7u) >> 3, nm = p4 >> 2;
-            for (uint32_t g = tid; g < groups; g += kThreads) {
-                const uint32_t n0 = g << 3;
-                int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
-                if (n0 + 8u > order) {
-                    const uint32_t j0 = zf + (n0 >> 2) - nm;                       /* >= 0: zf covers p4 / 4 entries */
-                    int4 za = Z[zpair_slot(j0)], zb = Z[zpair_slot(j0 + 1u)];
-                    for (uint32_t m = 0; m < nm; ++m) {
-                        const int4 zc = Z[zpair_slot(j0 + m + 2u)];
-                        const int32_t cf = coef_b[m];
-                        a0 = __dp2a_lo(za.x, cf, a0); a0 = __dp2a_hi(za.y, cf, a0);
-                        a1 = __dp2a_lo(za.z, cf, a1); a1 = __dp2a_hi(za.w, cf, a1);
-                        a2 = __dp2a_lo(za.y, cf, a2); a2 = __dp2a_hi(zb.x, cf, a2);
-                        a3 = __dp2a_lo(za.w, cf, a3); a3 = __dp2a_hi(zb.z, cf, a3);
-                        a4 = __dp2a_lo(zb.x, cf, a4); a4 = __dp2a_hi(zb.y, cf, a4);
-                        a5 = __dp2a_lo(zb.z, cf, a5); a5 = __dp2a_hi(zb.w, cf, a5);
-                        a6 = __dp2a_lo(zb.y, cf, a6); a6 = __dp2a_hi(zc.x, cf, a6);
-                        a7 = __dp2a_lo(zb.w, cf, a7); a7 = __dp2a_hi(zc.z, cf, a7);
-                        za = zb; zb = zc;
-                    }
+    }
+    const bool zmode = __syncthreads_and(fits) != 0;
+    if (zmode) {
+        for (uint32_t m = tid; m < (p4 >> 2); m += kThreads) {
+            coef_b[m] = (int32_t)(((uint32_t)coef_s[4u * m] & 0xffu) | (((uint32_t)coef_s[4u * m + 1u] & 0xffu) << 8)
+                                | (((uint32_t)coef_s[4u * m + 2u] & 0xffu) << 16) | (((uint32_t)coef_s[4u * m + 3u] & 0xffu) << 24));
+        }
+        __syncthreads();
+        /* ---- FIR residual with IDP.2A, int32 wrapping.  Every group of 8 outputs that reaches past the warm-up (first
+         * output >= order, or straddling it) runs the full padded filter: for an output i >= order the taps that fall in
+         * front of the block carry zero coefficients (order is padded to p4 in FRONT), so they may read anything
+         * addressable.  Warm-up outputs (i < order: first differences, srla_lpc_predict.c:251-254) are patched in
+         * afterwards.  No output is ever computed by a serial loop: one slow thread would hold the whole CTA at the
+         * next barrier. ---- */
+        const uint32_t groups = (n + 7u) >> 3, nm = p4 >> 2;
+        for (uint32_t g = tid; g < groups; g += kThreads) {
+            const uint32_t n0 = g << 3;
+            int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+            int4 za, zb;
+            if (order > 0u && n0 + 8u > order) {
+                const uint32_t j0 = zf + (n0 >> 2) - nm;                       /* >= 0: zf covers p4 / 4 entries */
+                za = Z[zpair_slot(j0)]; zb = Z[zpair_slot(j0 + 1u)];
+                for (uint32_t m = 0; m < nm; ++m) {
+                    const int4 zc = Z[zpair_slot(j0 + m + 2u)];
+                    const int32_t cf = coef_b[m];
+                    a0 = __dp2a_lo(za.x, cf, a0); a0 = __dp2a_hi(za.y, cf, a0);
+                    a1 = __dp2a_lo(za.z, cf, a1); a1 = __dp2a_hi(za.w, cf, a1);
+                    a2 = __dp2a_lo(za.y, cf, a2); a2 = __dp2a_hi(zb.x, cf, a2);
+                    a3 = __dp2a_lo(za.w, cf, a3); a3 = __dp2a_hi(zb.z, cf, a3);
+                    a4 = __dp2a_lo(zb.x, cf, a4); a4 = __dp2a_hi(zb.y, cf, a4);
+                    a5 = __dp2a_lo(zb.z, cf, a5); a5 = __dp2a_hi(zb.w, cf, a5);
+                    a6 = __dp2a_lo(zb.y, cf, a6); a6 = __dp2a_hi(zc.x, cf, a6);
+                    a7 = __dp2a_lo(zb.w, cf, a7); a7 = __dp2a_hi(zc.z, cf, a7);
+                    za = zb; zb = zc;
                 }
-                const int4 s0 = *reinterpret_cast<const int4 *>(sig + n0), s1 = *reinterpret_cast<const int4 *>(sig + n0 + 4u);
-                int32_t r[8] = { (int32_t)((uint32_t)s0.x + (uint32_t)asr32(a0, rshift)), (int32_t)((uint32_t)s0.y + (uint32_t)asr32(a1, rshift)),
-                                 (int32_t)((uint32_t)s0.z + (uint32_t)asr32(a2, rshift)), (int32_t)((uint32_t)s0.w + (uint32_t)asr32(a3, rshift)),
-                                 (int32_t)((uint32_t)s1.x + (uint32_t)asr32(a4, rshift)), (int32_t)((uint32_t)s1.y + (uint32_t)asr32(a5, rshift)),
-                                 (int32_t)((uint32_t)s1.z + (uint32_t)asr32(a6, rshift)), (int32_t)((uint32_t)s1.w + (uint32_t)asr32(a7, rshift)) };
+            } else {
+                za = Z[zpair_slot(zf + (n0 >> 2))]; zb = Z[zpair_slot(zf + (n0 >> 2) + 1u)];
+            }
+            /* za, zb now hold the entries of samples n0 .. n0+4 and n0+4 .. n0+8: the outputs' own samples */
+            const int32_t x[8] = { (int32_t)(short)(za.x & 0xffff), za.x >> 16, (int32_t)(short)(za.y & 0xffff), za.y >> 16,
+                                   (int32_t)(short)(zb.x & 0xffff), zb.x >> 16, (int32_t)(short)(zb.y & 0xffff), zb.y >> 16 };
+            int32_t r[8];
+            if (order > 0u) {
+                r[0] = (int32_t)((uint32_t)x[0] + (uint32_t)asr32(a0, rshift)); r[1] = (int32_t)((uint32_t)x[1] + (uint32_t)asr32(a1, rshift));
+                r[2] = (int32_t)((uint32_t)x[2] + (uint32_t)asr32(a2, rshift)); r[3] = (int32_t)((uint32_t)x[3] + (uint32_t)asr32(a3, rshift));
+                r[4] = (int32_t)((uint32_t)x[4] + (uint32_t)asr32(a4, rshift)); r[5] = (int32_t)((uint32_t)x[5] + (uint32_t)asr32(a5, rshift));
+                r[6] = (int32_t)((uint32_t)x[6] + (uint32_t)asr32(a6, rshift)); r[7] = (int32_t)((uint32_t)x[7] + (uint32_t)asr32(a7, rshift));
                 if (n0 < order) {
-                    /* warm-up outputs of this group */
-                    const int32_t x[8] = { s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w };
-                    const int32_t before = sig[n0 ? n0 - 1u : 0u];
+                    /* warm-up outputs of this group; x[n0 - 1] is the first half of the previous entry's last pair */
+                    const int32_t before = (int32_t)(short)(Z[zpair_slot(zf + (n0 >> 2) - 1u)].w & 0xffff);
                     #pragma unroll
                     for (int t = 0; t < 8; ++t) {
                         const uint32_t i = n0 + (uint32_t)t;
                         if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
                     }
                 }
-                *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
-                if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
-                if (n0 + 4u < n) {
-                    *reinterpret_cast<int4 *>(res_s + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]);
-                    if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]); }
-                }
+            } else {
+                #pragma unroll
+                for (int t = 0; t < 8; ++t) { r[t] = x[t]; }
             }
-        } else {
+            *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+            if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
+            if (n0 + 4u < n) {
+                *reinterpret_cast<int4 *>(res_s + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]);
+                if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]); }
+            }
+        }
+    } else {
+        /* ---- the signal does not fit 16 bits (24-bit sources, loud side channels): int32 signal, IMAD filter ---- */
+        if (ltp_period == 0u) { apply_preemphasis(region_i, sig, n, pre_coef); }
+        __syncthreads();
+        if (order > 0u) {
+            /* same scheme as above: padded filter for every group reaching past the warm-up, warm-up outputs patched in */
             const uint32_t groups = (n + 3u) >> 2;
             const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
             for (uint32_t g = tid; g < groups; g += kThreads) {
@@ -1540,9 +1588,9 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
                 *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
                 if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
             }
+        } else {
+            for (uint32_t i = tid; i < n; i += kThreads) { const int32_t v = sig[i]; res_s[i] = v; if (res_g) { res_g[i] = v; } }
         }
-    } else {
-        for (uint32_t i = tid; i < n; i += kThreads) { const int32_t v = sig[i]; res_s[i] = v; if (res_g) { res_g[i] = v; } }
     }
     __syncthreads();
 
