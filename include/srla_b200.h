@@ -160,6 +160,27 @@ SRLAApiResult SRLAB200_EncodeStreamsHost(
     struct SRLAEncoder *encoder, const struct SRLAB200Stream *streams, uint32_t num_streams,
     uint8_t *out, uint64_t out_capacity, uint64_t *stream_offsets);
 
+/* WAV ingest.  One stream whose PCM is still in the shape of a WAV `data` chunk: frames of
+ * num_channels little-endian samples of bits_per_sample / 8 bytes each (8-bit: unsigned with offset 128; 16- and
+ * 24-bit: two's complement), exactly what the reference's reader consumes one sample at a time before it calls
+ * SRLAEncoder_EncodeWhole (libs/wav/src/wav.c:543-553, :841-866; tools/srla_codec/srla_codec.c:103-134). */
+struct SRLAB200Frames {
+    const void *frames;       /* HOST memory (ideally pinned, see SRLAB200_AllocPinned): the data chunk's payload */
+    uint32_t num_samples;     /* frames, i.e. samples per channel                                                 */
+};
+
+/* Encode `num_streams` such streams under the handle's current parameters: the payloads are copied to the
+ * device as they are, de-interleaved and widened by a CUDA kernel, and encoded like SRLAB200_EncodeStreamsHost
+ * does; the outputs are byte-identical to what the reference CLI writes for the same WAV files. */
+SRLAApiResult SRLAB200_EncodeInterleavedHost(
+    struct SRLAEncoder *encoder, const struct SRLAB200Frames *items, uint32_t num_streams,
+    uint8_t *out, uint64_t out_capacity, uint64_t *stream_offsets);
+
+/* Page-locked host memory for the buffers of the *Host entry points (asynchronous copies at full PCIe rate);
+ * NULL when the allocation fails. */
+void *SRLAB200_AllocPinned(size_t bytes);
+void SRLAB200_FreePinned(void *p);
+
 /* Upper bound of the encoded size of a stream of num_samples samples per channel under the
  * handle's current parameters (header + every block stored raw). */
 uint64_t SRLAB200_MaxEncodedSize(const struct SRLAEncoder *encoder, uint32_t num_samples);

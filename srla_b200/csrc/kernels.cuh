@@ -126,6 +126,60 @@ __global__ void __launch_bounds__(256) lshift_jobs_kernel(StreamDev *streams, co
     if ((threadIdx.x & 31) == 0 && acc) { atomicOr(&st.or_mask, acc); }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * WAV ingest.  The reference CLI reads a WAV data chunk one sample at a time through a bit buffer
+ * and converts it to planar sign-extended int32 (libs/wav/src/wav.c:543-553, conversions :841-866: 8-bit is
+ * unsigned with offset 128, 16- and 24-bit are little-endian two's complement).  Here the data chunk is copied
+ * to HBM as it lies in the file and one CTA per job writes the planar layout the analysis kernels read
+ * (int16 for sources of at most 16 bits, else int32).  The samples are OR-ed into the stream's or_mask on the
+ * way (srla_utility.c:177-203), so no lshift_jobs_kernel pass is needed over data that came in this way.
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) deinterleave_jobs_kernel(StreamDev *streams, const Job *jobs, uint32_t nch)
+{
+    const Job &job = jobs[blockIdx.x];
+    StreamDev &st = streams[job.stream];
+    const uint32_t n = job.nsmpl, cb = st.container_bytes;
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(st.raw) + (size_t)job.offset * nch * cb;
+    uint32_t acc = 0;
+    uint32_t done = 0;                                   /* frames handled by the vector path */
+    if (cb == 2u && nch == 2u && st.sample_bytes == 2u && (reinterpret_cast<uintptr_t>(src) & 15u) == 0u
+        && quad_aligned(st, 0, job.offset) && quad_aligned(st, 1, job.offset)) {
+        /* 16-bit stereo: four frames per 16-byte load, one 8-byte store per channel */
+        short *left = reinterpret_cast<short *>(const_cast<void *>(st.pcm)) + job.offset;
+        short *right = left + st.stride;
+        const uint32_t nquad = n >> 2;
+        for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
+            const int4 v = ldg_stream_v4(src + 16u * (size_t)g);
+            int2 l, r;
+            l.x = (int32_t)__byte_perm((uint32_t)v.x, (uint32_t)v.y, 0x5410); r.x = (int32_t)__byte_perm((uint32_t)v.x, (uint32_t)v.y, 0x7632);
+            l.y = (int32_t)__byte_perm((uint32_t)v.z, (uint32_t)v.w, 0x5410); r.y = (int32_t)__byte_perm((uint32_t)v.z, (uint32_t)v.w, 0x7632);
+            /* only the lowest set bit of the mask matters (trailing-zero count) and it lies in the 16 raw bits */
+            const uint32_t any = (uint32_t)(v.x | v.y | v.z | v.w);
+            acc |= (any & 0xffffu) | (any >> 16);
+            *reinterpret_cast<int2 *>(left + 4u * g) = l;
+            *reinterpret_cast<int2 *>(right + 4u * g) = r;
+        }
+        done = nquad << 2;
+    }
+    const uint32_t total = (n - done) * nch;
+    const unsigned char *tail = src + (size_t)done * nch * cb;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        const uint32_t frame = i / nch, ch = i - frame * nch;
+        const unsigned char *q = tail + (size_t)i * cb;
+        int32_t v;
+        if (cb == 1u) { v = (int32_t)q[0] - 128; }
+        else if (cb == 2u) { v = (int32_t)(short)((uint32_t)q[0] | ((uint32_t)q[1] << 8)); }
+        else { v = (int32_t)(((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16)) << 8) >> 8; }
+        acc |= (uint32_t)v;
+        const size_t at = (size_t)ch * st.stride + job.offset + done + frame;
+        if (st.sample_bytes == 2u) { reinterpret_cast<short *>(const_cast<void *>(st.pcm))[at] = (short)v; }
+        else { reinterpret_cast<int32_t *>(const_cast<void *>(st.pcm))[at] = v; }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { acc |= __shfl_xor_sync(0xffffffffu, acc, o); }
+    if ((threadIdx.x & 31) == 0 && acc) { atomicOr(&st.or_mask, acc); }
+}
+
 __global__ void lshift_finish_kernel(StreamDev *streams, uint32_t num_streams, uint32_t *snapshot)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;

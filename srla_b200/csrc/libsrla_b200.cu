@@ -88,7 +88,7 @@ struct DeviceCtx {
     DevBuf tw_complex, tw_real, rice_thr, huff_code, huff_len;
     uint32_t tw_c_off[20], tw_r_off[20];
     /* work */
-    DevBuf streams, jobs, misc, stream_begin, pcm, out;
+    DevBuf streams, jobs, misc, stream_begin, pcm, out, raw;
     /* a lane = one compute stream + its own per-group scratch; alternate groups of a call run on different
      * lanes so the latency-bound kernels of one group (lpc, scan) overlap the throughput-bound ones of the next */
     struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags, lpc_state; };
@@ -223,7 +223,7 @@ void ctx_destroy(DeviceCtx *c)
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
     if (c->ev_upload) { cudaEventDestroy(c->ev_upload); }
     DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
-                       &c->misc, &c->stream_begin, &c->pcm, &c->out };
+                       &c->misc, &c->stream_begin, &c->pcm, &c->out, &c->raw };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release(); c->h_stage_out.release();
     if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
@@ -275,6 +275,9 @@ struct HostIO {
     uint64_t out_capacity = 0;
     bool narrow = false;                   /* host samples are int32_t but the device layout is int16_t: they are
                                               narrowed by the feeder threads into pinned staging on their way in */
+    const void *const *raw = nullptr;      /* WAV ingest: per stream, the interleaved frames of its data chunk (then
+                                              `streams` is unused); they are copied as they are and de-interleaved on
+                                              the device (Plan::raw_dev says where) */
 };
 
 /* Host feeder: the reference API hands over planar int32_t PCM in pageable memory.  For sources of
@@ -348,6 +351,8 @@ struct Plan {
     bool size_only = false;           /* ComputeBlockSize */
     bool want_diag = false;
     bool allow_pipeline = true;
+    const void *const *raw_dev = nullptr;   /* WAV ingest: per stream, device address of its interleaved frames */
+    uint32_t container_bytes = 0;           /* bytes per sample there */
 };
 
 struct Runner {
@@ -474,15 +479,19 @@ struct Runner {
             h[s].pcm = pl.streams[s].pcm; h[s].stride = pl.streams[s].channel_stride;
             h[s].num_samples = pl.streams[s].num_samples; h[s].sample_bytes = pl.streams[s].sample_bytes;
             h[s].lshift = 0; h[s].or_mask = 0;
+            h[s].raw = pl.raw_dev ? pl.raw_dev[s] : nullptr; h[s].container_bytes = pl.container_bytes; h[s].pad_ = 0;
         }
         CU_TRY(cudaMemcpyAsync(c->streams.p, h, bytes, cudaMemcpyHostToDevice, c->stream));
         return true;
     }
 
     /* OR-reduce the samples of `count` jobs into their streams and refresh every stream's shift */
-    bool launch_lshift(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t *d_snapshot, cudaStream_t on)
+    /* with `ingest` the jobs' frames have just arrived as interleaved WAV data: they are de-interleaved first, and
+     * that kernel ORs the samples on its way */
+    bool launch_lshift(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t *d_snapshot, cudaStream_t on, bool ingest = false)
     {
-        lshift_jobs_kernel<<<count, 256, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch);
+        if (ingest) { deinterleave_jobs_kernel<<<count, 256, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch); }
+        else { lshift_jobs_kernel<<<count, 256, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch); }
         lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, on>>>((StreamDev *)c->streams.p, pl.num_streams, d_snapshot);
         CU_TRY(cudaGetLastError());
         launches += 2;
@@ -591,6 +600,12 @@ struct Runner {
     {
         const struct SRLAB200Stream &d = pl.streams[s];
         const size_t sb = d.sample_bytes;
+        if (io.raw) {
+            const size_t frame = (size_t)pl.nch * pl.container_bytes;
+            CU_TRY(cudaMemcpyAsync((unsigned char *)pl.raw_dev[s] + begin * frame, (const unsigned char *)io.raw[s] + begin * frame,
+                                   (size_t)(end - begin) * frame, cudaMemcpyHostToDevice, on));
+            return true;
+        }
         for (uint32_t ch = 0; ch < pl.nch; ch++) {
             unsigned char *dst = (unsigned char *)d.pcm + ((size_t)d.channel_stride * ch + begin) * sb;
             /* narrowed input: the staging buffer mirrors the device layout byte for byte */
@@ -726,7 +741,7 @@ struct Runner {
                     feeder.start(num_groups, c->feed_threads);
                 } else {
                     cudaPointerAttributes attr;
-                    if (cudaPointerGetAttributes(&attr, io->streams[0].ch[0]) != cudaSuccess || attr.type != cudaMemoryTypeHost) { copies_async = false; (void)cudaGetLastError(); }
+                    if (cudaPointerGetAttributes(&attr, io->raw ? io->raw[0] : io->streams[0].ch[0]) != cudaSuccess || attr.type != cudaMemoryTypeHost) { copies_async = false; (void)cudaGetLastError(); }
                 }
                 if (!issue_h2d(0)) { return SRLA_APIRESULT_NG; }
             } else {
@@ -736,9 +751,11 @@ struct Runner {
 
         size_t ev_idx = 0;
         uint32_t nmax = 1;
+        const bool ingest = io && io->raw;
+        if (ingest && pl.use_fixed_lshift) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
         if (!pipelined && !pl.use_fixed_lshift) {
             /* exact offset_lshift of every stream before any analysis */
-            if (!launch_lshift(pl, (const Job *)c->jobs.p, (uint32_t)jobs.size(), nullptr, c->stream)) { return SRLA_APIRESULT_NG; }
+            if (!launch_lshift(pl, (const Job *)c->jobs.p, (uint32_t)jobs.size(), nullptr, c->stream, ingest)) { return SRLA_APIRESULT_NG; }
         }
 
         if (pl.variable) {
@@ -831,7 +848,7 @@ struct Runner {
                 /* pinned source: queue the next group's copy first so the copy engine never waits for the host */
                 if (copies_async && !io->narrow && g + 1 < groups_now && !issue_h2d(g + 1)) { return SRLA_APIRESULT_NG; }
                 if (cudaStreamWaitEvent(on, h2d_done[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-                if (!launch_lshift(pl, (const Job *)c->jobs.p + j0, cnt, d_snap + g * pl.num_streams, on)) { return SRLA_APIRESULT_NG; }
+                if (!launch_lshift(pl, (const Job *)c->jobs.p + j0, cnt, d_snap + g * pl.num_streams, on, ingest)) { return SRLA_APIRESULT_NG; }
             }
             const bool chain = lanes_now > 1;
             if (!run_batch(pl, (const Job *)c->jobs.p + j0, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++,
@@ -1274,6 +1291,55 @@ SRLAApiResult SRLAB200_EncodeStreamsHost(
     Runner r{ encoder, c };
     return r.run(pl, (uint8_t *)c->out.p, cap, stream_offsets, nullptr, &io);
 }
+
+SRLAApiResult SRLAB200_EncodeInterleavedHost(
+    struct SRLAEncoder *encoder, const struct SRLAB200Frames *items, uint32_t num_streams,
+    uint8_t *out, uint64_t out_capacity, uint64_t *stream_offsets)
+{
+    if (encoder == NULL || items == NULL || num_streams == 0 || out == NULL || stream_offsets == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    const SRLAApiResult ready = check_ready(encoder);
+    if (ready != SRLA_APIRESULT_OK) { return ready; }
+    DeviceCtx *c = encoder->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    const uint32_t nch = encoder->param.num_channels;
+    const uint32_t cb = encoder->param.bits_per_sample / 8u;              /* 1, 2 or 3: SetEncodeParameter admits 8/16/24 bits */
+    const uint32_t sb = (encoder->param.bits_per_sample <= 16) ? 2u : 4u; /* planar device layout */
+    std::vector<struct SRLAB200Stream> dev(num_streams);
+    std::vector<const void *> raw_host(num_streams), raw_dev(num_streams);
+    uint64_t planar_bytes = 0, raw_bytes = 0, cap = 0;
+    for (uint32_t s = 0; s < num_streams; s++) {
+        if (items[s].frames == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+        planar_bytes += (uint64_t)round_up_u32(items[s].num_samples, 16) * nch * sb;
+        raw_bytes += ((uint64_t)items[s].num_samples * nch * cb + 255u) / 256u * 256u;
+        cap += max_encoded_size(encoder, items[s].num_samples);
+    }
+    if (!c->pcm.reserve(planar_bytes) || !c->raw.reserve(raw_bytes) || !c->out.reserve(cap)) { return SRLA_APIRESULT_NG; }
+    uint64_t at = 0, raw_at = 0;
+    for (uint32_t s = 0; s < num_streams; s++) {
+        const uint64_t stride = round_up_u32(items[s].num_samples, 16);
+        dev[s].pcm = (unsigned char *)c->pcm.p + at; dev[s].channel_stride = stride;
+        dev[s].num_samples = items[s].num_samples; dev[s].sample_bytes = sb;
+        raw_host[s] = items[s].frames; raw_dev[s] = (unsigned char *)c->raw.p + raw_at;
+        at += stride * nch * sb;
+        raw_at += ((uint64_t)items[s].num_samples * nch * cb + 255u) / 256u * 256u;
+    }
+    HostIO io; io.raw = raw_host.data(); io.out = out; io.out_capacity = out_capacity;
+    Plan pl;
+    pl.streams = dev.data(); pl.num_streams = num_streams; pl.nch = nch;
+    pl.raw_dev = raw_dev.data(); pl.container_bytes = cb;
+    pl.variable = encoder->param.min_num_samples_per_block != encoder->param.max_num_samples_per_block;
+    Runner r{ encoder, c };
+    return r.run(pl, (uint8_t *)c->out.p, cap, stream_offsets, nullptr, &io);
+}
+
+void *SRLAB200_AllocPinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void SRLAB200_FreePinned(void *p) { if (p) { cudaFreeHost(p); } }
 
 uint64_t SRLAB200_MaxEncodedSize(const struct SRLAEncoder *encoder, uint32_t num_samples)
 {

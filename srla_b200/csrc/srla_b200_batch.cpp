@@ -1,0 +1,301 @@
+/*
+ * srla_b200_batch -- many-file front end of the B200 SRLA encode path.
+ *
+ * The reference has one production caller of the encoder, `srla -e in.wav out.srl`
+ * (tools/srla_codec/srla_codec.c:75-158): it parses the WAV one sample at a time through a bit buffer
+ * (libs/wav/src/wav.c:543-553), encodes that one file, writes it.  This tool takes the same encode
+ * options (same letters, defaults and range checks, srla_codec.c:38-63, :311-403) and any number of WAV
+ * files: headers are parsed on the host with the reference reader's rules, the data chunks are read by a
+ * thread team straight into page-locked memory, files of equal format are submitted together through
+ * SRLAB200_EncodeInterleavedHost (de-interleaving, widening and the whole encode run on the GPU) and the
+ * .srl files -- byte-identical to the reference CLI's -- are written by the same team.
+ *
+ * Host-only C++: it binds nothing but the C ABI of include/srla_b200.h.
+ */
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/srla_b200.h"
+
+namespace {
+
+struct WavInfo {
+    std::string path, out_path;
+    uint32_t channels = 0, rate = 0, bits = 0, frames = 0;
+    uint64_t data_at = 0, data_bytes = 0, file_bytes = 0;
+    bool ok = false;
+    uint64_t encoded = 0;
+};
+
+uint32_t le(const unsigned char *p, int n) { uint32_t v = 0; for (int i = 0; i < n; i++) { v |= (uint32_t)p[i] << (8 * i); } return v; }
+
+/* Header walk with the rules of the reference reader (wav.c:136-281): "RIFF" <size> "WAVE", then the "fmt "
+ * chunk FIRST, of size 16 (format tag 1) or 40 (tag 0xFFFE, extension size 22), then chunks are skipped by their
+ * stated size (no padding byte, like the reference's seek) until "data"; frames = data bytes / frame bytes. */
+bool parse_wav(WavInfo &w, std::string &why)
+{
+    FILE *fp = std::fopen(w.path.c_str(), "rb");
+    if (!fp) { why = "cannot open"; return false; }
+    struct stat sb;
+    if (fstat(fileno(fp), &sb) != 0) { std::fclose(fp); why = "cannot stat"; return false; }
+    w.file_bytes = (uint64_t)sb.st_size;
+    unsigned char h[64];
+    auto need = [&](size_t n) { return std::fread(h, 1, n, fp) == n; };
+    bool good = false;
+    do {
+        if (!need(12) || std::memcmp(h, "RIFF", 4) != 0 || std::memcmp(h + 8, "WAVE", 4) != 0) { why = "not a RIFF/WAVE file"; break; }
+        if (!need(8) || std::memcmp(h, "fmt ", 4) != 0) { why = "fmt chunk does not follow the WAVE signature"; break; }
+        const uint32_t fmt_size = le(h + 4, 4);
+        if (fmt_size != 16 && fmt_size != 40) { why = "unsupported fmt chunk size"; break; }
+        if (!need(fmt_size)) { why = "truncated fmt chunk"; break; }
+        const uint32_t tag = le(h, 2);
+        if ((fmt_size == 16 && tag != 1) || (fmt_size == 40 && tag != 0xFFFE)) { why = "not linear PCM"; break; }
+        w.channels = le(h + 2, 2); w.rate = le(h + 4, 4); w.bits = le(h + 14, 2);
+        if (fmt_size == 40 && le(h + 16, 2) != 22) { why = "bad WAVEFORMATEXTENSIBLE extension size"; break; }
+        for (;;) {
+            if (!need(8)) { why = "no data chunk"; break; }
+            const uint32_t size = le(h + 4, 4);
+            if (std::memcmp(h, "data", 4) == 0) { w.data_at = (uint64_t)std::ftell(fp); w.data_bytes = size; good = true; break; }
+            std::fprintf(stderr, "WARNING: skiping chunk:%.4s size:%d \n", (const char *)h, (int32_t)size);
+            if (std::fseek(fp, (long)(int32_t)size, SEEK_CUR) != 0) { why = "seek failed"; break; }
+        }
+    } while (0);
+    std::fclose(fp);
+    if (!good) { return false; }
+    if (w.bits != 8 && w.bits != 16 && w.bits != 24) { why = "unsupported bits per sample"; return false; }   /* the format's raw blocks carry 8/16/24 */
+    if (w.channels == 0 || w.channels > SRLA_MAX_NUM_CHANNELS) { why = "unsupported channel count"; return false; }
+    const uint32_t frame = (w.bits / 8) * w.channels;
+    w.frames = (uint32_t)(w.data_bytes / frame);
+    if (w.frames == 0) { why = "empty data chunk"; return false; }
+    if (w.data_at + (uint64_t)w.frames * frame > w.file_bytes) { why = "data chunk is longer than the file"; return false; }
+    return true;
+}
+
+/* run fn(i) for i in [0, count) on `threads` host threads */
+template <class F> void parallel_for(size_t count, int threads, F fn)
+{
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> team;
+    const int t = (int)std::min<size_t>((size_t)std::max(1, threads), std::max<size_t>(count, 1));
+    for (int k = 0; k < t; k++) { team.emplace_back([&] { for (;;) { const size_t i = next.fetch_add(1); if (i >= count) { break; } fn(i); } }); }
+    for (std::thread &th : team) { th.join(); }
+}
+
+bool read_range(const std::string &path, uint64_t at, unsigned char *dst, uint64_t bytes)
+{
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { return false; }
+    uint64_t done = 0;
+    while (done < bytes) {
+        const ssize_t got = pread(fd, dst + done, (size_t)std::min<uint64_t>(bytes - done, 1u << 30), (off_t)(at + done));
+        if (got <= 0) { break; }
+        done += (uint64_t)got;
+    }
+    close(fd);
+    return done == bytes;
+}
+
+bool write_file(const std::string &path, const uint8_t *src, uint64_t bytes)
+{
+    FILE *fp = std::fopen(path.c_str(), "wb");
+    if (!fp) { return false; }
+    const bool ok = std::fwrite(src, 1, (size_t)bytes, fp) == bytes;
+    return (std::fclose(fp) == 0) && ok;
+}
+
+bool parse_u32(const char *prog, const char *what, const char *str, uint32_t *out)
+{
+    char *e = nullptr;
+    const long v = std::strtol(str, &e, 10);
+    if (*e != '\0') { std::fprintf(stderr, "%s: invalid %s. (irregular character found in %s at %s)\n", prog, what, str, e); return false; }
+    *out = (uint32_t)v;
+    return true;
+}
+
+void usage(const char *prog)
+{
+    std::fprintf(stderr,
+        "Usage: %s [options] -o OUTPUT_DIR INPUT.wav [INPUT.wav ...]\n"
+        "  -m, --mode N                       compress mode 0(fast) .. 6(high compression) (default:4)\n"
+        "  -B, --max-block-size N             max number of block samples (default:4096, at most 8192 here)\n"
+        "  -V, --variable-block-divisions N   number of variable block-size divisions (default:1)\n"
+        "  -L, --lookahead-sample-factor N    multiply factor for lookahead samples (default:4)\n"
+        "  -P, --long-term-prediction N       long term prediction order, odd (default:0, disabled)\n"
+        "  -o, --output-dir DIR               INPUT.wav is written to DIR/INPUT.srl\n"
+        "  -j, --threads N                    host threads reading / writing files (default:8)\n"
+        "  -g, --device N                     CUDA device ordinal (default: current)\n"
+        "      --batch-megabytes N            PCM submitted per GPU call (default:2048)\n"
+        "Every file is encoded exactly as `srla -e` with the same options would encode it.\n", prog);
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+    const char *prog = argv[0];
+    uint32_t mode = 4, max_block = 4096, divisions = 1, factor = 4, ltp = 0, threads = 8, batch_mb = 2048;
+    int device = -1;
+    std::string out_dir;
+    std::vector<std::string> inputs;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto value = [&](const char *name) -> const char * { if (i + 1 >= argc) { std::fprintf(stderr, "%s: option %s needs an argument. \n", prog, name); std::exit(1); } return argv[++i]; };
+        if (a == "-h" || a == "--help") { usage(prog); return 0; }
+        else if (a == "-v" || a == "--version") { std::printf("%s\n", SRLAB200_Version()); return 0; }
+        else if (a == "-e" || a == "--encode") { /* the only mode */ }
+        else if (a == "-m" || a == "--mode") {
+            if (!parse_u32(prog, "encode preset number", value("mode"), &mode)) { return 1; }
+            if (mode >= SRLA_NUM_PARAMETER_PRESETS) { std::fprintf(stderr, "%s: encode preset number is out of range. \n", prog); return 1; }
+        } else if (a == "-L" || a == "--lookahead-sample-factor") {
+            if (!parse_u32(prog, "number of lookahead samples", value("lookahead-sample-factor"), &factor)) { return 1; }
+            if (factor == 0 || factor >= (1u << 16)) { std::fprintf(stderr, "%s: lookahead factor is out of range. \n", prog); return 1; }
+        } else if (a == "-B" || a == "--max-block-size") {
+            if (!parse_u32(prog, "number of block samples", value("max-block-size"), &max_block)) { return 1; }
+            if (max_block == 0 || max_block >= (1u << 16)) { std::fprintf(stderr, "%s: number of block samples is out of range. \n", prog); return 1; }
+        } else if (a == "-V" || a == "--variable-block-divisions") {
+            if (!parse_u32(prog, "number of variable block divisions", value("variable-block-divisions"), &divisions)) { return 1; }
+        } else if (a == "-P" || a == "--long-term-prediction") {
+            if (!parse_u32(prog, "number of long term prediction order", value("long-term-prediction"), &ltp)) { return 1; }
+            if (ltp > 0 && (ltp % 2) == 0) { std::fprintf(stderr, "%s: long term prediction order is must be odd. \n", prog); return 1; }
+            if (ltp > SRLA_MAX_LTP_ORDER) { std::fprintf(stderr, "%s: long term prediction order is too large. \n", prog); return 1; }
+        } else if (a == "-o" || a == "--output-dir") { out_dir = value("output-dir"); }
+        else if (a == "-j" || a == "--threads") { if (!parse_u32(prog, "thread count", value("threads"), &threads)) { return 1; } }
+        else if (a == "-g" || a == "--device") { uint32_t d = 0; if (!parse_u32(prog, "device ordinal", value("device"), &d)) { return 1; } device = (int)d; }
+        else if (a == "--batch-megabytes") { if (!parse_u32(prog, "batch size", value("batch-megabytes"), &batch_mb)) { return 1; } }
+        else if (!a.empty() && a[0] == '-') { std::fprintf(stderr, "%s: unknown option %s\n", prog, a.c_str()); usage(prog); return 1; }
+        else { inputs.push_back(a); }
+    }
+    if (divisions >= 32 || (max_block >> divisions) == 0) { std::fprintf(stderr, "%s: number of variable block divisions is too large. \n", prog); return 1; }
+    if (inputs.empty()) { std::fprintf(stderr, "%s: input file must be specified. \n", prog); return 1; }
+    if (out_dir.empty()) { std::fprintf(stderr, "%s: output directory must be specified. \n", prog); return 1; }
+    threads = std::max(1u, std::min(64u, threads));
+    batch_mb = std::max(1u, batch_mb);
+    if (device >= 0 && SRLAB200_SetDevice(device) != SRLA_APIRESULT_OK) { std::fprintf(stderr, "%s: no CUDA device %d. \n", prog, device); return 1; }
+    mkdir(out_dir.c_str(), 0777);
+
+    /* ---- headers ---- */
+    std::vector<WavInfo> files(inputs.size());
+    int failures = 0;
+    for (size_t i = 0; i < inputs.size(); i++) {
+        WavInfo &w = files[i];
+        w.path = inputs[i];
+        std::string base = w.path.substr(w.path.find_last_of('/') == std::string::npos ? 0 : w.path.find_last_of('/') + 1);
+        const size_t dot = base.find_last_of('.');
+        if (dot != std::string::npos && dot > 0) { base.resize(dot); }
+        w.out_path = out_dir + "/" + base + ".srl";
+        std::string why;
+        w.ok = parse_wav(w, why);
+        if (!w.ok) { std::fprintf(stderr, "Failed to open %s. (%s)\n", w.path.c_str(), why.c_str()); failures++; }
+    }
+
+    /* ---- one handle; files of equal (channels, bits, rate) are submitted together ---- */
+    struct SRLAEncoderConfig config;
+    config.max_num_channels = SRLA_MAX_NUM_CHANNELS;
+    config.min_num_samples_per_block = max_block >> divisions;
+    config.max_num_samples_per_block = max_block;
+    config.max_num_lookahead_samples = factor * max_block;
+    config.max_num_parameters = SRLA_MAX_COEFFICIENT_ORDER;
+    struct SRLAEncoder *encoder = SRLAEncoder_Create(&config, NULL, 0);
+    if (encoder == NULL) { std::fprintf(stderr, "Failed to create encoder handle. \n"); return 1; }
+
+    std::vector<size_t> order;
+    for (size_t i = 0; i < files.size(); i++) { if (files[i].ok) { order.push_back(i); } }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        const WavInfo &x = files[a], &y = files[b];
+        if (x.channels != y.channels) { return x.channels < y.channels; }
+        if (x.bits != y.bits) { return x.bits < y.bits; }
+        return x.rate < y.rate;
+    });
+    const auto t_begin = std::chrono::steady_clock::now();
+    uint64_t total_in = 0, total_out = 0, total_samples = 0;
+    size_t succeeded = 0;
+    double gpu_seconds = 0.0;
+    const uint64_t batch_bytes = (uint64_t)batch_mb << 20;
+    size_t at = 0;
+    while (at < order.size()) {
+        const WavInfo &first = files[order[at]];
+        size_t end = at; uint64_t bytes = 0, cap = 0;
+        struct SRLAEncodeParameter parameter;
+        parameter.num_channels = (uint16_t)first.channels;
+        parameter.bits_per_sample = (uint16_t)first.bits;
+        parameter.sampling_rate = first.rate;
+        parameter.min_num_samples_per_block = max_block >> divisions;
+        parameter.max_num_samples_per_block = max_block;
+        parameter.num_lookahead_samples = factor * max_block;
+        parameter.num_svr_filter_learning_iteration = 0;
+        parameter.ltp_order = ltp;
+        parameter.preset = (uint8_t)mode;
+        const SRLAApiResult set = SRLAEncoder_SetEncodeParameter(encoder, &parameter);
+        while (end < order.size()) {
+            const WavInfo &w = files[order[end]];
+            if (w.channels != first.channels || w.bits != first.bits || w.rate != first.rate) { break; }
+            const uint64_t payload = (uint64_t)w.frames * w.channels * (w.bits / 8);
+            if (end > at && bytes + payload > batch_bytes) { break; }
+            bytes += (payload + 255u) / 256u * 256u;
+            if (set == SRLA_APIRESULT_OK) { cap += SRLAB200_MaxEncodedSize(encoder, w.frames); }
+            end++;
+        }
+        const size_t count = end - at;
+        if (set != SRLA_APIRESULT_OK) {
+            std::fprintf(stderr, "Failed to set encode parameter: %d \n", (int)set);
+            for (size_t k = at; k < end; k++) { files[order[k]].ok = false; failures++; }
+            at = end; continue;
+        }
+        unsigned char *pcm = (unsigned char *)SRLAB200_AllocPinned(bytes);
+        uint8_t *out = (uint8_t *)SRLAB200_AllocPinned(cap);
+        if (!pcm || !out) { std::fprintf(stderr, "%s: cannot allocate %llu MB of page-locked memory. \n", prog, (unsigned long long)((bytes + cap) >> 20)); return 1; }
+        std::vector<struct SRLAB200Frames> items(count);
+        std::vector<uint64_t> offsets(count + 1, 0);
+        std::vector<int> read_ok(count, 0);
+        { uint64_t o = 0; for (size_t k = 0; k < count; k++) { const WavInfo &w = files[order[at + k]]; items[k].frames = pcm + o; items[k].num_samples = w.frames; o += ((uint64_t)w.frames * w.channels * (w.bits / 8) + 255u) / 256u * 256u; } }
+        parallel_for(count, (int)threads, [&](size_t k) {
+            const WavInfo &w = files[order[at + k]];
+            read_ok[k] = read_range(w.path, w.data_at, (unsigned char *)items[k].frames, (uint64_t)w.frames * w.channels * (w.bits / 8)) ? 1 : 0;
+        });
+        bool all_read = true;
+        for (size_t k = 0; k < count; k++) { if (!read_ok[k]) { std::fprintf(stderr, "Failed to open %s. (read error)\n", files[order[at + k]].path.c_str()); all_read = false; } }
+        if (!all_read) { return 1; }
+        const auto t0 = std::chrono::steady_clock::now();
+        const SRLAApiResult rc = SRLAB200_EncodeInterleavedHost(encoder, items.data(), (uint32_t)count, out, cap, offsets.data());
+        gpu_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (rc != SRLA_APIRESULT_OK) {
+            std::fprintf(stderr, "Failed to encode data: %d \n", (int)rc);
+            for (size_t k = at; k < end; k++) { files[order[k]].ok = false; failures++; }
+        } else {
+            std::vector<int> wrote(count, 0);
+            parallel_for(count, (int)threads, [&](size_t k) {
+                WavInfo &w = files[order[at + k]];
+                w.encoded = offsets[k + 1] - offsets[k];
+                wrote[k] = write_file(w.out_path, out + offsets[k], w.encoded) ? 1 : 0;
+            });
+            for (size_t k = 0; k < count; k++) {
+                WavInfo &w = files[order[at + k]];
+                if (!wrote[k]) { std::fprintf(stderr, "File output error! %s \n", w.out_path.c_str()); w.ok = false; failures++; continue; }
+                std::printf("finished: %s %llu -> %llu (%6.2f %%) \n", w.path.c_str(), (unsigned long long)w.file_bytes, (unsigned long long)w.encoded,
+                            100.0 * (double)w.encoded / (double)w.file_bytes);
+                total_in += w.file_bytes; total_out += w.encoded; total_samples += (uint64_t)w.frames * w.channels; succeeded++;
+            }
+        }
+        SRLAB200_FreePinned(pcm); SRLAB200_FreePinned(out);
+        at = end;
+    }
+    SRLAEncoder_Destroy(encoder);
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    std::printf("total: %zu files, %llu -> %llu bytes (%6.2f %%), %.1f Msamples/s in the encode calls (host buffers in, bytes out), %.1f Msamples/s with file I/O\n",
+                succeeded, (unsigned long long)total_in, (unsigned long long)total_out,
+                total_in ? 100.0 * (double)total_out / (double)total_in : 0.0,
+                gpu_seconds > 0 ? (double)total_samples / gpu_seconds / 1e6 : 0.0, wall > 0 ? (double)total_samples / wall / 1e6 : 0.0);
+    return failures ? 1 : 0;
+}

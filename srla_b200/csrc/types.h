@@ -36,6 +36,10 @@ struct StreamDev {
     uint32_t sample_bytes;     /* 2: int16_t, 4: int32_t                                  */
     uint32_t lshift;           /* common trailing-zero shift (srla_utility.c:177-203)      */
     uint32_t or_mask;          /* scratch of the OR-reduction                              */
+    const void *raw;           /* WAV ingest: the stream's frames as they lie in a WAV data chunk (interleaved,
+                                  little endian), or NULL; deinterleave_jobs_kernel turns them into `pcm`   */
+    uint32_t container_bytes;  /* bytes per sample in `raw`: 1 (unsigned, offset 128), 2, 3 (signed)        */
+    uint32_t pad_;
 };
 
 /* one block to analyse / emit */

@@ -55,6 +55,10 @@ class SRLAB200Stream(C.Structure):
                 ("sample_bytes", C.c_uint32)]
 
 
+class SRLAB200Frames(C.Structure):
+    _fields_ = [("frames", C.c_void_p), ("num_samples", C.c_uint32)]
+
+
 class SRLAB200Stats(C.Structure):
     _fields_ = [("num_blocks", C.c_uint64), ("num_analysed", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64),
@@ -78,7 +82,8 @@ EXPORTED_SYMBOLS = [
     "SRLAEncoder_EncodeHeader", "SRLAEncoder_CalculateWorkSize", "SRLAEncoder_Create", "SRLAEncoder_Destroy",
     "SRLAEncoder_SetEncodeParameter", "SRLAEncoder_ComputeBlockSize", "SRLAEncoder_EncodeBlock",
     "SRLAEncoder_EncodeOptimalPartitionedBlock", "SRLAEncoder_EncodeWhole",
-    "SRLAB200_EncodeStreamsDevice", "SRLAB200_EncodeStreamsHost", "SRLAB200_MaxEncodedSize", "SRLAB200_GetStats",
+    "SRLAB200_EncodeStreamsDevice", "SRLAB200_EncodeStreamsHost", "SRLAB200_EncodeInterleavedHost",
+    "SRLAB200_AllocPinned", "SRLAB200_FreePinned", "SRLAB200_MaxEncodedSize", "SRLAB200_GetStats",
     "SRLAB200_SetDevice", "SRLAB200_SetStream", "SRLAB200_Version", "SRLAB200_TestAnalyseChannel",
 ]
 
@@ -119,6 +124,12 @@ def load_library() -> C.CDLL:
         f = getattr(lib, name)
         f.argtypes = [C.c_void_p, C.POINTER(SRLAB200Stream), C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         f.restype = C.c_int
+    lib.SRLAB200_EncodeInterleavedHost.argtypes = [C.c_void_p, C.POINTER(SRLAB200Frames), C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.SRLAB200_EncodeInterleavedHost.restype = C.c_int
+    lib.SRLAB200_AllocPinned.argtypes = [C.c_size_t]
+    lib.SRLAB200_AllocPinned.restype = C.c_void_p
+    lib.SRLAB200_FreePinned.argtypes = [C.c_void_p]
+    lib.SRLAB200_FreePinned.restype = None
     lib.SRLAB200_MaxEncodedSize.argtypes = [C.c_void_p, C.c_uint32]
     lib.SRLAB200_MaxEncodedSize.restype = C.c_uint64
     lib.SRLAB200_GetStats.argtypes = [C.c_void_p, C.POINTER(SRLAB200Stats)]
@@ -253,6 +264,25 @@ class Encoder:
         rc = self.lib.SRLAB200_EncodeStreamsHost(self.handle, descs, len(streams), out.ctypes.data, out.size, offsets)
         if rc != OK:
             raise SRLAError("SRLAB200_EncodeStreamsHost", rc)
+        return out, list(offsets)
+
+    def encode_interleaved_host(self, payloads: Sequence[np.ndarray], out: Optional[np.ndarray] = None):
+        """payloads: one uint8 array per stream holding the payload of a WAV `data` chunk (interleaved little-endian
+        frames of the handle's channel count and bits_per_sample / 8 bytes per sample).
+        Returns (out_buffer, offsets[num_streams + 1])."""
+        frame = self.param.num_channels * (self.param.bits_per_sample // 8)
+        items = (SRLAB200Frames * len(payloads))()
+        cap = 0
+        for i, b in enumerate(payloads):
+            assert b.ndim == 1 and b.dtype == np.uint8 and b.flags.c_contiguous and b.size % frame == 0
+            items[i] = SRLAB200Frames(b.ctypes.data, b.size // frame)
+            cap += self.max_encoded_size(b.size // frame)
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        offsets = (C.c_uint64 * (len(payloads) + 1))()
+        rc = self.lib.SRLAB200_EncodeInterleavedHost(self.handle, items, len(payloads), out.ctypes.data, out.size, offsets)
+        if rc != OK:
+            raise SRLAError("SRLAB200_EncodeInterleavedHost", rc)
         return out, list(offsets)
 
     def encode_streams_device(self, descs, num_streams: int, d_out_ptr: int, capacity: int):

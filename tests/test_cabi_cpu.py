@@ -103,11 +103,44 @@ def test_no_cpu_fallback_without_a_device(lib):
     lib.SRLAEncoder_Destroy(None)
 
 
+def test_batch_cli_options_follow_the_reference_cli(tmp_path):
+    """srla_b200_batch takes the reference CLI's encode options with its range checks (srla_codec.c:311-403); on a
+    box without a GPU it fails loudly instead of falling back"""
+    import struct
+    tool = os.path.join(ROOT, "srla_b200", "srla_b200_batch")
+    if not os.path.exists(tool):
+        import __graft_entry__ as g
+        g.build()
+    run = lambda *a: subprocess.run([tool, *a], capture_output=True, text=True)
+    assert run("--help").returncode == 0
+    assert "sm_100a" in run("-v").stdout
+    r = run("-o", str(tmp_path)); assert r.returncode == 1 and "input file must be specified" in r.stderr
+    r = run("x.wav"); assert r.returncode == 1 and "output directory must be specified" in r.stderr
+    for args, msg in ((("-m", "7"), "encode preset number is out of range"), (("-m", "4x"), "irregular character found in 4x at x"),
+                      (("-B", "65536"), "number of block samples is out of range"), (("-L", "0"), "lookahead factor is out of range"),
+                      (("-V", "13"), "number of variable block divisions is too large"), (("-P", "2"), "must be odd"),
+                      (("-P", "5"), "long term prediction order is too large")):
+        r = run(*args, "-o", str(tmp_path), "x.wav")
+        assert r.returncode == 1 and msg in r.stderr, (args, r.stderr)
+    # header rules of the reference reader (wav.c:136-281): fmt first, size 16 or 40, linear PCM
+    bad = tmp_path / "float.wav"
+    fmt = struct.pack("<HHIIHH", 3, 1, 48000, 192000, 4, 32)
+    bad.write_bytes(b"RIFF" + struct.pack("<I", 36) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"data" + struct.pack("<I", 0))
+    import torch
+    if not torch.cuda.is_available():
+        good = tmp_path / "ok.wav"
+        fmt = struct.pack("<HHIIHH", 1, 1, 48000, 96000, 2, 16)
+        good.write_bytes(b"RIFF" + struct.pack("<I", 36 + 64) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"data" + struct.pack("<I", 64) + bytes(64))
+        r = run("-o", str(tmp_path / "out"), str(good), str(bad))
+        assert r.returncode == 1 and "Failed to create encoder handle" in r.stderr and "float.wav" in r.stderr, r.stderr
+        assert not (tmp_path / "out" / "ok.srl").exists()
+
+
 def test_product_code_never_touches_the_oracle():
     """the oracle is test infrastructure: nothing under srla_b200/ or include/ may reference it"""
     for base, _dirs, files in os.walk(os.path.join(ROOT, "srla_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "liboracle" not in text and "srla_oracle" not in text and "libsrla_ref" not in text, f
 
