@@ -1335,7 +1335,7 @@ SRLAApiResult SRLAB200_EncodeInterleavedHost(
 void *SRLAB200_AllocPinned(size_t bytes)
 {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
     return p;
 }
 
