@@ -15,6 +15,7 @@
 #include <memory>
 #include <thread>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -670,9 +671,15 @@ struct Runner {
         if (!split) {
             for (size_t at = per_batch; at < jobs.size(); at += per_batch) { gstart.push_back(at); }
         } else if (pipelined && c->ramp && jobs.size() >= 4096) {
-            static const double kRamp[] = { 0.03, 0.06, 0.11, 0.15, 0.15, 0.15, 0.14, 0.11, 0.06, 0.04 };
+            static const double kRampDefault[] = { 0.03, 0.06, 0.11, 0.15, 0.15, 0.15, 0.14, 0.11, 0.06, 0.04 };
+            std::vector<double> ramp_spec(kRampDefault, kRampDefault + sizeof(kRampDefault) / sizeof(kRampDefault[0]));
+            if (const char *e = std::getenv("SRLA_B200_RAMP_SPEC")) {             /* tuning: comma-separated group fractions */
+                std::vector<double> v; const char *q = e;
+                while (*q) { char *end = nullptr; const double f = std::strtod(q, &end); if (end == q) { break; } v.push_back(f); q = (*end == ',') ? end + 1 : end; }
+                if (!v.empty()) { ramp_spec = v; }
+            }
             double acc = 0.0;
-            for (double f : kRamp) {
+            for (double f : ramp_spec) {
                 acc += f;
                 size_t at = std::min(jobs.size(), (size_t)(acc * (double)jobs.size() + 0.5));
                 while (at - gstart.back() > per_batch) { gstart.push_back(gstart.back() + per_batch); }
@@ -688,6 +695,9 @@ struct Runner {
         if (io && io->narrow && !pipelined) { std::fprintf(stderr, "[srla_b200] internal: narrowed input outside the pipelined path\n"); return SRLA_APIRESULT_NG; }
 
         if (cudaEventRecord(c->ev_begin, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        const auto host_t0 = std::chrono::steady_clock::now();
+        auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+        std::vector<double> host_h2d, host_launch, host_d2h;
         if (!prepare_streams(pl)) { return SRLA_APIRESULT_NG; }
         if (!c->misc.reserve(kMiscBytes + sizeof(unsigned long long) * (pl.num_streams + 1) + 64)) { return SRLA_APIRESULT_NG; }
         if (cudaMemsetAsync(c->misc.p, 0, kMiscBytes, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
@@ -711,7 +721,9 @@ struct Runner {
                 if (!h2d_range(pl, *io, s, begin, jobs[k].offset + jobs[k].nsmpl, c->copy_stream)) { return false; }
                 j = k + 1;
             }
-            return cudaEventRecord(h2d_done[g], c->copy_stream) == cudaSuccess;
+            const bool ok = cudaEventRecord(h2d_done[g], c->copy_stream) == cudaSuccess;
+            if (c->trace) { if (host_h2d.size() <= g) { host_h2d.resize(g + 1, 0.0); } host_h2d[g] = host_ms(); }
+            return ok;
         };
         bool copies_async = true;      /* pinned source: the H2D of the next group is queued before this group's kernels */
         if (io) {
@@ -855,6 +867,7 @@ struct Runner {
                            pipelined ? mailbox + g : nullptr, ln,
                            (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr)) { return SRLA_APIRESULT_NG; }
             if (pipelined && cudaEventRecord(grp_done[g], on) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+            if (c->trace) { host_launch.push_back(host_ms()); }
             /* pageable source (the copy blocks the host) or feeder staging: the next group's copy follows this
              * group's launches, so the device works on group g while the host moves group g + 1 */
             if (pipelined && (!copies_async || io->narrow) && g + 1 < groups_now && !issue_h2d(g + 1)) { return SRLA_APIRESULT_NG; }
@@ -887,6 +900,7 @@ struct Runner {
                 if (end > io->out_capacity || end > cap) { host_overflow = true; break; }
                 if (end > prev && cudaMemcpyAsync(h_dst + prev, d_out + prev, end - prev, cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
                 prev = end; gend[g] = end;
+                if (c->trace) { host_d2h.push_back(host_ms()); }
                 if (staged) {
                     if (cudaEventRecord(c->ev_d2h[g], c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
                     while (published <= g && cudaEventQuery(c->ev_d2h[published]) == cudaSuccess) { feeder.out_ready.store(gend[published], std::memory_order_release); published++; }
@@ -951,13 +965,14 @@ struct Runner {
         for (int i = 0; i < 3; i++) { stt.type_histogram[i] = dstats[260 + i]; }
         cudaEventElapsedTime(&stt.ms_total_device, c->ev_begin, c->ev_end);
         if (c->trace && pipelined) {
-            std::fprintf(stderr, "[srla_b200 trace] %zu groups, %d lanes, total %.3f ms (device clock, origin = call start)\n", groups_now, lanes_now, stt.ms_total_device);
+            std::fprintf(stderr, "[srla_b200 trace] %zu groups, %d lanes, total %.3f ms (device clock, origin = call start); host clock at return %.3f ms\n", groups_now, lanes_now, stt.ms_total_device, host_ms());
             for (size_t g = 0; g < groups_now; g++) {
                 float h = 0, t[5] = { 0, 0, 0, 0, 0 };
                 cudaEventElapsedTime(&h, c->ev_begin, h2d_done[g]);
                 for (int k = 0; k < 5; k++) { cudaEventElapsedTime(&t[k], c->ev_begin, c->ev_pool[g * 5 + k]); }
-                std::fprintf(stderr, "  group %2zu jobs %5zu lane %d: h2d done %.3f | front %.3f lpc %.3f residual %.3f decide %.3f end %.3f\n",
-                             g, gstart[g + 1] - gstart[g], (int)(g % (size_t)lanes_now), h, t[0], t[1], t[2], t[3], t[4]);
+                std::fprintf(stderr, "  group %2zu jobs %5zu lane %d: h2d done %.3f | front %.3f lpc %.3f residual %.3f decide %.3f end %.3f | host: h2d issued %.3f, kernels issued %.3f, d2h issued %.3f\n",
+                             g, gstart[g + 1] - gstart[g], (int)(g % (size_t)lanes_now), h, t[0], t[1], t[2], t[3], t[4],
+                             g < host_h2d.size() ? host_h2d[g] : -1.0, g < host_launch.size() ? host_launch[g] : -1.0, g < host_d2h.size() ? host_d2h[g] : -1.0);
             }
         }
         for (size_t i = 0; i < ev_idx; i++) {
