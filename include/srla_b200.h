@@ -69,7 +69,7 @@ struct SRLAEncodeParameter {
     uint32_t max_num_samples_per_block;
     uint32_t num_lookahead_samples;
     uint32_t ltp_order;                              /* 0 (off), 1 or 3 */
-    uint32_t num_svr_filter_learning_iteration;      /* must be 0: SVR refinement is out of scope */
+    uint32_t num_svr_filter_learning_iteration;      /* iterations of the SVR coefficient refinement (0: off) */
     uint8_t  preset;                                 /* 0..6 -> max LPC order 0,8,16,32,64,128,255 */
 };
 
@@ -108,8 +108,8 @@ struct SRLAEncoder *SRLAEncoder_Create(const struct SRLAEncoderConfig *config, v
 void SRLAEncoder_Destroy(struct SRLAEncoder *encoder);
 
 /* include/srla_encoder.h:56-57 (srla_encoder.c:710-763): same validation and result codes;
- * additionally INVALID_FORMAT when num_svr_filter_learning_iteration != 0 or bits_per_sample is
- * not one of 8/16/24 (the widths the format's raw blocks can carry, srla_encoder.c:825-852). */
+ * additionally INVALID_FORMAT when bits_per_sample is not one of 8/16/24 (the widths the format's raw
+ * blocks can carry, srla_encoder.c:825-852). */
 SRLAApiResult SRLAEncoder_SetEncodeParameter(struct SRLAEncoder *encoder, const struct SRLAEncodeParameter *parameter);
 
 /* include/srla_encoder.h:60-62 (srla_encoder.c:1477-1546): exact encoded size of one block. */

@@ -1039,6 +1039,34 @@ __global__ void __launch_bounds__(32) lpc_levinson_kernel(const __grid_constant_
     }
 }
 
+/* 8-bit quantisation of the coefficient vector a(0) .. a(order-1) with error feedback from the tail
+ * (lpc.c:1341-1405), stored reversed for the FIR (srla_encoder.c:1104-1108); returns the right shift */
+template <typename Get>
+__device__ __forceinline__ uint32_t quantise_coefficients(Get a, uint32_t order, int16_t *coef)
+{
+    double peak = 0.0;
+    for (uint32_t i = 0; i < order; ++i) { const double v = fabs(a(i)); if (peak < v) { peak = v; } }
+    if (peak <= 0.0078125) {
+        for (uint32_t i = 0; i < order; ++i) { coef[i] = 0; }
+        return 8u;
+    }
+    int exponent;
+    (void)frexp(peak, &exponent);
+    uint32_t rshift = (uint32_t)(7 - exponent);
+    if (rshift >= 16u) { rshift = 15u; }
+    const double scale = (double)(1u << rshift);
+    double carry = 0.0;
+    for (int i = (int)order - 1; i >= 0; --i) {
+        carry += a((uint32_t)i) * scale;
+        int32_t v = (int32_t)round_half_away(carry);
+        if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
+        carry -= (double)v;
+        /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
+        coef[order - 1u - (uint32_t)i] = (int16_t)v;
+    }
+    return rshift;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * lpc_select_kernel: one CTA (128 threads) per 32 candidates.  Phase 1, all four warps: the estimated size of
  * every order (thread = candidate x order mod 4), first minimum (srla_encoder.c:934-957).  Phase 2, warp 0, one
@@ -1109,33 +1137,201 @@ __global__ void __launch_bounds__(128) lpc_select_kernel(const __grid_constant__
             if (k + 1u < order) { next = g_refl[(size_t)(k + 1u) * 32u + lane]; }
             levinson_update(A, lane, k, refl);
         }
-        double peak = 0.0;
-        for (uint32_t i = 1; i <= order; ++i) { const double v = fabs(LPC_A(i)); if (peak < v) { peak = v; } }
-        if (peak <= 0.0078125) {
-            for (uint32_t i = 0; i < order; ++i) { out->coef[i] = 0; }
-            rshift = 8u;
-        } else {
-            int exponent;
-            (void)frexp(peak, &exponent);
-            rshift = (uint32_t)(7 - exponent);
-            if (rshift >= 16u) { rshift = 15u; }
-            const double scale = (double)(1u << rshift);
-            double carry = 0.0;
-            for (int i = (int)order - 1; i >= 0; --i) {
-                carry += LPC_A(1 + i) * scale;
-                int32_t v = (int32_t)round_half_away(carry);
-                if (v >= 128) { v = 127; } else if (v < -128) { v = -128; }
-                carry -= (double)v;
-                /* FIR order: coef[j] multiplies x[n - order + j]  =>  quantised a[order-1-j] */
-                out->coef[order - 1u - (uint32_t)i] = (int16_t)v;
-            }
-        }
+        rshift = quantise_coefficients([&](uint32_t i) { return LPC_A(1u + i); }, order, out->coef);
+        if (p.svr_iterations) { double *keep = p.svr_coef + (size_t)idx * P; for (uint32_t i = 0; i < order; ++i) { keep[i] = LPC_A(1u + i); } }
         if (dg) { for (uint32_t i = 0; i < order; ++i) { dg->lpc_double[i] = LPC_A(1u + i); } }
     }
     out->order = order; out->rshift = rshift;
 }
 #undef LPC_R
 #undef LPC_A
+
+/* ------------------------------------------------------------------------------------------------
+ * svr_kernel (only with num_svr_filter_learning_iteration > 0): the reference refines the chosen
+ * order's coefficients by iteratively re-weighted least squares with a soft-thresholded ("support vector")
+ * residual before quantising them (LPC_CalculateCoefSVR, lpc.c:1036-1136; call site srla_encoder.c:1087-1101).
+ * Persistent CTAs, one candidate at a time per CTA.  Every floating-point sum is taken in the reference's order;
+ * the parallelism is across sums:
+ *   covariance   cov[i][j] = sum_s x[s+i] x[s+j]  (lpc.c:988-1017): a thread owns eight neighbouring j of one i
+ *   Cholesky     (lpc.c:573-602): column by column, the entries of a column in parallel; L(j,i) overwrites cov[i][j]
+ *   iteration    residual per sample in parallel (taps in order), then |residual| summed by ONE thread in sample
+ *                order while other threads accumulate the right-hand side r[i] (one i each, samples in order),
+ *                then the two triangular solves (lpc.c:605-631) and the bookkeeping by one thread.
+ * The objective (lpc.c:1020-1030) uses log() and pow(); it only ever enters comparisons.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ double svr_objective(double mean_abs)
+{
+    const double intmean = mean_abs * 65536.0;                       /* BITS_PER_SAMPLE is fixed to 16 there */
+    const double rho = 1.0 / (1.0 + intmean);
+    const double l2 = log(log(0.5127629514) / log(1.0 - rho)) * 1.4426950408889634;
+    const uint32_t k2 = (uint32_t)((0.0 > l2) ? 0.0 : l2);
+    const uint32_t k1 = k2 + 1u;
+    const double k1factor = pow(1.0 - rho, (double)(1u << k1));
+    const double k2factor = pow(1.0 - rho, (double)(1u << k2));
+    return (1.0 + k1) * (1.0 - k1factor) + (1.0 + k2 + (1.0 / (1.0 - k2factor))) * k1factor;
+}
+
+__global__ void __launch_bounds__(kThreads) svr_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SvrLayout L = make_svr_layout(p.nmax, p.max_order);
+    const uint32_t P = p.max_order, tid = threadIdx.x;
+    double *data = reinterpret_cast<double *>(smem + L.data_off) + 8;          /* 8 zeros in front, 24 behind */
+    double *resid = reinterpret_cast<double *>(smem + L.resid_off);
+    double *vec = reinterpret_cast<double *>(smem + L.vec_off);
+    double *coef = vec, *best = vec + (P + 1u), *init = vec + 2u * (P + 1u), *delta = vec + 3u * (P + 1u),
+           *rvec = vec + 4u * (P + 1u), *inv_diag = vec + 5u * (P + 1u), *scal = vec + 6u * (P + 1u);
+    /* scal[0] mean-abs sum, scal[1] stop flag, scal[2] singular flag */
+    double *M = p.svr_matrix + (size_t)blockIdx.x * P * P;
+    const uint32_t total = p.num_jobs * p.ncand;
+
+    for (uint32_t idx = blockIdx.x; idx < total; idx += gridDim.x) {
+        const uint32_t job_id = idx / p.ncand, cand = idx % p.ncand;
+        const Job job = p.jobs[job_id];
+        const StreamDev st = p.streams[job.stream];
+        const uint32_t n = job.nsmpl;
+        CandOut *out = p.cand + idx;
+        __syncthreads();                                             /* the previous candidate is done with shared memory */
+        if (n <= P || out->status != 0u || out->order == 0u) { continue; }
+        const uint32_t dim = out->order, ltp_period = out->ltp_period;
+        const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+
+        /* ---- the signal the LPC stage saw, normalised to [-1, 1) (srla_encoder.c:1060-1064) ---- */
+        {
+            int32_t *raw = reinterpret_cast<int32_t *>(resid);
+            int32_t *sig = raw + round_up_u32(n, 4) + 4;
+            (void)load_candidate<2>(st, job, p, cand, lshift, raw);
+            __syncthreads();
+            apply_preemphasis(raw, sig, n, out->pre_coef);
+            __syncthreads();
+            if (ltp_period > 0u) { apply_ltp(sig, raw, n, p.ltp_order, ltp_period, out->ltp_coef[0], out->ltp_coef[1], out->ltp_coef[2]); }
+            for (uint32_t i = tid; i < n; i += kThreads) { data[i] = (double)sig[i] * p.unit; }
+            if (tid < 8u) { data[-1 - (int)tid] = 0.0; }
+            if (tid < 24u) { data[n + tid] = 0.0; }
+            const double *start = p.svr_coef + (size_t)idx * P;
+            for (uint32_t i = tid; i < dim; i += kThreads) { const double c0 = start[i]; coef[i] = c0; init[i] = c0; best[i] = c0; }
+        }
+        __syncthreads();
+
+        /* ---- covariance: task = (row i, eight columns j0 .. j0+7), samples in order ---- */
+        {
+            const uint32_t chunks = (dim + 7u) >> 3, terms = n - dim;
+            for (uint32_t t = tid; t < dim * chunks; t += kThreads) {
+                const uint32_t i = t / chunks, j0 = (t - i * chunks) << 3;
+                if (j0 + 7u < i) { continue; }
+                double acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+                double w[8];
+                #pragma unroll
+                for (int k = 0; k < 7; ++k) { w[k] = data[j0 + (uint32_t)k]; }
+                w[7] = 0.0;
+                for (uint32_t s0 = 0; s0 < terms; s0 += 8u) {
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t sm = s0 + (uint32_t)u;
+                        /* window w[(u+k) & 7] = data[sm + j0 + k]: one new element per sample */
+                        w[(u + 7) & 7] = data[sm + j0 + 7u];
+                        if (sm < terms) {
+                            const double sv = data[sm + i];
+                            #pragma unroll
+                            for (int k = 0; k < 8; ++k) { acc[k] += sv * w[(u + k) & 7]; }
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) { const uint32_t j = j0 + (uint32_t)k; if (j >= i && j < dim) { M[(size_t)i * P + j] = acc[k]; } }
+            }
+        }
+        __syncthreads();
+        /* ---- ridge (lpc.c:1066-1068) and Cholesky; L(j,i), j > i, takes the place of cov[i][j] ---- */
+        if (tid == 0u) { scal[2] = 0.0; }
+        for (uint32_t i = tid; i < dim; i += kThreads) { M[(size_t)i * P + i] *= (1.0 + 1e-5); }
+        __syncthreads();
+        for (uint32_t i = 0; i < dim; ++i) {
+            if (tid == 0u) {
+                double sum = M[(size_t)i * P + i];
+                for (int k = (int)i - 1; k >= 0; --k) { const double l = M[(size_t)k * P + i]; sum -= l * l; }
+                if (sum <= 0.0) { scal[2] = 1.0; inv_diag[i] = 0.0; } else { inv_diag[i] = inv_sqrt_cr(sum); }
+            }
+            __syncthreads();
+            if (scal[2] != 0.0) { break; }
+            const double inv = inv_diag[i];
+            for (uint32_t j = i + 1u + tid; j < dim; j += kThreads) {
+                double sum = M[(size_t)i * P + j];
+                for (int k = (int)i - 1; k >= 0; --k) { sum -= M[(size_t)k * P + i] * M[(size_t)k * P + j]; }
+                M[(size_t)i * P + j] = sum * inv;
+            }
+            __syncthreads();
+        }
+        if (scal[2] != 0.0) {
+            /* singular: all-zero input in theory; the reference clears the coefficients (lpc.c:1071-1076) */
+            if (tid == 0u) { out->rshift = quantise_coefficients([&](uint32_t) { return 0.0; }, dim, out->coef); }
+            continue;
+        }
+
+        /* ---- margins x iterations ---- */
+        double min_obj = (double)FLT_MAX;                            /* thread 0's copy is the one that counts */
+        for (int mi = 0; mi < 6; ++mi) {
+            const double margin = (mi == 0) ? 0.0 : 1.0 / (double)(4096u >> (2 * (mi - 1)));   /* 0, 1/4096, 1/1024, 1/256, 1/64, 1/16 (srla_internal.c:27) */
+            double prev_obj = (double)FLT_MAX;
+            __syncthreads();
+            for (uint32_t i = tid; i < dim; i += kThreads) { coef[i] = init[i]; }
+            __syncthreads();
+            for (uint32_t itr = 0; itr < p.svr_iterations; ++itr) {
+                /* residual of the current iterate, taps in order (lpc.c:1097-1100) */
+                for (uint32_t sm = dim + tid; sm < n; sm += kThreads) {
+                    double r = data[sm];
+                    for (uint32_t i = 0; i < dim; ++i) { r += coef[i] * data[sm - i - 1u]; }
+                    resid[sm] = r;
+                }
+                __syncthreads();
+                if (tid == 0u) {
+                    double mabse = 0.0;
+                    #pragma unroll 8
+                    for (uint32_t sm = dim; sm < n; ++sm) { const double r = resid[sm]; mabse += (r > 0) ? r : -r; }
+                    scal[0] = mabse;
+                } else if (tid >= 32u) {
+                    for (uint32_t i = tid - 32u; i < dim; i += kThreads - 32u) {
+                        double acc = 0.0;
+                        #pragma unroll 4
+                        for (uint32_t sm = dim; sm < n; ++sm) {
+                            const double r = resid[sm];
+                            const double mag = ((r > 0) ? r : -r) - margin;
+                            const double soft = (double)((r > 0) - (r < 0)) * ((mag > 0.0) ? mag : 0.0);      /* LPC_SOFT_THRESHOLD */
+                            acc += soft * data[sm - i - 1u];
+                        }
+                        rvec[i] = acc;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0u) {
+                    const double obj = svr_objective(scal[0] / n);
+                    /* cov * delta = r by the Cholesky factor (lpc.c:605-631) */
+                    for (uint32_t i = 0; i < dim; ++i) {
+                        double sum = rvec[i];
+                        for (int j = (int)i - 1; j >= 0; --j) { sum -= M[(size_t)j * P + i] * delta[j]; }
+                        delta[i] = sum * inv_diag[i];
+                    }
+                    for (int i = (int)dim - 1; i >= 0; --i) {
+                        double sum = delta[i];
+                        for (uint32_t j = (uint32_t)i + 1u; j < dim; ++j) { sum -= M[(size_t)i * P + j] * delta[j]; }
+                        delta[i] = sum * inv_diag[i];
+                    }
+                    if (obj < min_obj) { for (uint32_t i = 0; i < dim; ++i) { best[i] = coef[i]; } min_obj = obj; }
+                    const bool stop = (prev_obj < obj) || (fabs(prev_obj - obj) < 1e-8);
+                    if (!stop) { for (uint32_t i = 0; i < dim; ++i) { coef[i] += delta[i]; } prev_obj = obj; }
+                    scal[1] = stop ? 1.0 : 0.0;
+                }
+                __syncthreads();
+                if (scal[1] != 0.0) { break; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0u) {
+            out->rshift = quantise_coefficients([&](uint32_t i) { return best[i]; }, dim, out->coef);
+            if (p.diag) { CandDiag *dg = p.diag + idx; for (uint32_t i = 0; i < dim; ++i) { dg->lpc_double[i] = best[i]; } }
+        }
+    }
+}
 
 /* ------------------------------------------------------------------------------------------------
  * residual_kernel: one CTA per (job, candidate).  Rebuilds the candidate signal, runs the int32

@@ -92,7 +92,7 @@ struct DeviceCtx {
     DevBuf streams, jobs, misc, stream_begin, pcm, out, raw;
     /* a lane = one compute stream + its own per-group scratch; alternate groups of a call run on different
      * lanes so the latency-bound kernels of one group (lpc, scan) overlap the throughput-bound ones of the next */
-    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags, lpc_state; };
+    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags, lpc_state, svr_coef, svr_matrix; };
     Lane lane[kMaxLanes];
     int lanes = 3;                 /* SRLA_B200_LANES */
     int groups = 8;                /* SRLA_B200_GROUPS: groups a large call is split into */
@@ -213,7 +213,7 @@ void ctx_destroy(DeviceCtx *c)
     for (int l = 0; l < kMaxLanes; l++) {
         if (c->lane[l].own) { cudaStreamSynchronize(c->lane[l].own); cudaStreamDestroy(c->lane[l].own); }
         if (c->lane[l].done) { cudaEventDestroy(c->lane[l].done); }
-        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags, &c->lane[l].lpc_state };
+        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags, &c->lane[l].lpc_state, &c->lane[l].svr_coef, &c->lane[l].svr_matrix };
         for (DevBuf *b : lb) { b->release(); }
     }
     if (c->ev_fork) { cudaEventDestroy(c->ev_fork); }
@@ -414,6 +414,13 @@ struct Runner {
         return true;
     }
 
+    uint32_t svr_grid(const LaunchParams &p) const
+    {
+        const SvrLayout SL = make_svr_layout(p.nmax, p.max_order);
+        const uint32_t per_sm = std::max(1u, std::min(8u, (uint32_t)(227u * 1024u) / (SL.total + 1024u)));
+        return std::min(p.num_jobs * p.ncand, (uint32_t)c->num_sms * per_sm);
+    }
+
     /* the three analysis kernels: front (autocorrelation) -> lpc (Levinson-Durbin) -> residual (FIR + Rice search) */
     bool launch_analyse(const LaunchParams &p, size_t batch, cudaStream_t on)
     {
@@ -461,6 +468,13 @@ struct Runner {
             lpc_levinson_kernel<<<(ncands + 31u) / 32u, 32, LL.total, on>>>(p);
             lpc_select_kernel<<<(ncands + 31u) / 32u, 128, LL.select_total, on>>>(p);
             launches += 2;
+            if (p.svr_iterations > 0u) {
+                /* persistent CTAs: one covariance / Cholesky matrix of P x P doubles each in global memory */
+                const SvrLayout SL = make_svr_layout(p.nmax, p.max_order);
+                if (!prep_kernel(svr_kernel, SL.total, 9)) { return false; }
+                svr_kernel<<<svr_grid(p), kThreads, SL.total, on>>>(p);
+                launches++;
+            }
         }
         if (!mark(batch, 2, on)) { return false; }
         if (!prep_kernel(residual_kernel, RL.total, 3)) { return false; }
@@ -518,6 +532,12 @@ struct Runner {
         if (!L.lags.reserve(sizeof(double) * round_up_u32((uint32_t)(ncand * count), 32) * (size_t)p.lag_stride)) { return false; }
         if (!L.lpc_state.reserve(sizeof(double) * (size_t)(round_up_u32((uint32_t)(ncand * count), 32) / 32u) * 2u * (p.max_order + 2u) * 32u)) { return false; }
         p.lags = (double *)L.lags.p; p.lpc_state = (double *)L.lpc_state.p;
+        p.svr_iterations = enc->param.num_svr_filter_learning_iteration;
+        if (p.svr_iterations > 0u && p.max_order > 0u) {
+            if (!L.svr_coef.reserve(sizeof(double) * (size_t)ncand * count * p.max_order)
+                || !L.svr_matrix.reserve(sizeof(double) * (size_t)svr_grid(p) * p.max_order * p.max_order)) { return false; }
+            p.svr_coef = (double *)L.svr_coef.p; p.svr_matrix = (double *)L.svr_matrix.p;
+        }
         p.cand = (CandOut *)L.cand.p; p.jobout = (JobOut *)L.jobout.p;
         p.residual = store_residual ? (int32_t *)L.residual.p : nullptr;
         p.diag = pl.want_diag ? (CandDiag *)L.diag.p : nullptr;
@@ -1117,8 +1137,7 @@ SRLAApiResult SRLAEncoder_SetEncodeParameter(struct SRLAEncoder *encoder, const 
         || (parameter->ltp_order > 0 && (parameter->ltp_order % 2) == 0) || parameter->ltp_order > SRLA_MAX_LTP_ORDER) {
         return SRLA_APIRESULT_INVALID_FORMAT;
     }
-    /* this implementation: SVR refinement out of scope; raw blocks exist for 8/16/24 bit only */
-    if (parameter->num_svr_filter_learning_iteration != 0) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    /* this implementation: raw blocks exist for 8/16/24 bit only */
     if (parameter->bits_per_sample != 8 && parameter->bits_per_sample != 16 && parameter->bits_per_sample != 24) { return SRLA_APIRESULT_INVALID_FORMAT; }
     /* srla_encoder.c:737-742 */
     if (encoder->config.max_num_samples_per_block < parameter->max_num_samples_per_block

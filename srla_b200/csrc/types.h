@@ -98,6 +98,10 @@ struct LaunchParams {
     double          *lags;           /* [job][cand][lag_stride]: autocorrelation lags 0..P  */
     uint32_t lag_stride;
     double          *lpc_state;      /* [candidate group of 32][2][P+2][32]: reflection coefficients, error variances */
+    double          *svr_coef;       /* SVR refinement only: [job][cand][P] un-quantised coefficients of the chosen order */
+    double          *svr_matrix;     /* SVR refinement only: [CTA of svr_kernel][P][P] covariance / Cholesky factor      */
+    uint32_t svr_iterations;         /* num_svr_filter_learning_iteration (0: off)                                       */
+    uint32_t pad_svr;
     uint32_t num_jobs, num_streams;
     uint32_t nch, ncand, bps;
     uint32_t max_order;              /* preset's maximum LPC order                         */
@@ -181,6 +185,21 @@ struct ResidLayout {
  * samples in front of the block; those taps carry zero coefficients, so the padding only has to be addressable */
 SRLA_HD inline uint32_t resid_front_pad(uint32_t P) { return round_up_u32(P, 4) + 4u; }             /* samples, multiple of 4 */
 SRLA_HD inline uint32_t resid_pair_front(uint32_t P) { return round_up_u32(round_up_u32(P, 4) / 4u + 2u, 16); }   /* pair entries */
+
+/* svr_kernel: the normalised signal, the residual of the current iterate (first used as int32 scratch of the
+ * signal rebuild), seven vectors of P+1 doubles, scalars */
+struct SvrLayout { uint32_t data_off, resid_off, vec_off, total; };
+SRLA_HD inline SvrLayout make_svr_layout(uint32_t nmax, uint32_t P)
+{
+    SvrLayout L;
+    const uint32_t n4 = round_up_u32(nmax, 4);
+    uint32_t off = 0;
+    L.data_off = off; off += 8u * (n4 + 32u);
+    L.resid_off = off; off += 8u * n4 + 128u;
+    L.vec_off = off; off += 8u * 7u * (P + 1u) + 64u;
+    L.total = off;
+    return L;
+}
 
 SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
 {

@@ -120,7 +120,7 @@ def make_param(nch, bps, rate, min_block, max_block, lookahead, ltp, preset, svr
 
 
 def api_encode_whole(lib: C.CDLL, pcm: np.ndarray, bps=16, rate=48000, max_block=4096, min_block=None,
-                     lookahead=None, ltp=0, preset=4, max_params=255, max_channels=8) -> bytes:
+                     lookahead=None, ltp=0, preset=4, max_params=255, max_channels=8, svr=0) -> bytes:
     """Drive Create / SetEncodeParameter / EncodeWhole / Destroy the way tools/srla_codec does
     (srla_codec.c:91-134) on any library exporting the SRLAEncoder_* API."""
     pcm = np.ascontiguousarray(pcm, dtype=np.int32)
@@ -138,7 +138,7 @@ def api_encode_whole(lib: C.CDLL, pcm: np.ndarray, bps=16, rate=48000, max_block
     enc = lib.SRLAEncoder_Create(C.byref(cfg), work.ctypes.data, work_size)
     assert enc, "SRLAEncoder_Create failed"
     try:
-        prm = make_param(nch, bps, rate, min_block, max_block, lookahead, ltp, preset)
+        prm = make_param(nch, bps, rate, min_block, max_block, lookahead, ltp, preset, svr)
         rc = lib.SRLAEncoder_SetEncodeParameter(enc, C.byref(prm))
         assert rc == 0, f"SetEncodeParameter -> {rc}"
         cap = 2 * (nch * n * 4) + 4096
