@@ -137,6 +137,7 @@ void usage(const char *prog)
         "  -V, --variable-block-divisions N   number of variable block-size divisions (default:1)\n"
         "  -L, --lookahead-sample-factor N    multiply factor for lookahead samples (default:4)\n"
         "  -P, --long-term-prediction N       long term prediction order, odd (default:0, disabled)\n"
+        "      --svr-filter-learning-iteration N   iterations of the SVR filter refinement (default:0)\n"
         "  -o, --output-dir DIR               INPUT.wav is written to DIR/INPUT.srl\n"
         "  -j, --threads N                    host threads reading / writing files (default:8)\n"
         "  -g, --device N                     CUDA device ordinal (default: current)\n"
@@ -150,7 +151,7 @@ void usage(const char *prog)
 int main(int argc, char **argv)
 {
     const char *prog = argv[0];
-    uint32_t mode = 4, max_block = 4096, divisions = 1, factor = 4, ltp = 0, threads = 8, batch_mb = 32;
+    uint32_t mode = 4, max_block = 4096, divisions = 1, factor = 4, ltp = 0, svr = 0, threads = 8, batch_mb = 32;
     bool timing = false;
     int device = -1;
     std::string out_dir;
@@ -176,6 +177,8 @@ int main(int argc, char **argv)
             if (!parse_u32(prog, "number of long term prediction order", value("long-term-prediction"), &ltp)) { return 1; }
             if (ltp > 0 && (ltp % 2) == 0) { std::fprintf(stderr, "%s: long term prediction order is must be odd. \n", prog); return 1; }
             if (ltp > SRLA_MAX_LTP_ORDER) { std::fprintf(stderr, "%s: long term prediction order is too large. \n", prog); return 1; }
+        } else if (a == "--svr-filter-learning-iteration") {
+            if (!parse_u32(prog, "number of lookahead samples", value("svr-filter-learning-iteration"), &svr)) { return 1; }     /* (sic: the reference's message, srla_codec.c:392) */
         } else if (a == "-o" || a == "--output-dir") { out_dir = value("output-dir"); }
         else if (a == "-j" || a == "--threads") { if (!parse_u32(prog, "thread count", value("threads"), &threads)) { return 1; } }
         else if (a == "-g" || a == "--device") { uint32_t d = 0; if (!parse_u32(prog, "device ordinal", value("device"), &d)) { return 1; } device = (int)d; }
@@ -343,7 +346,7 @@ int main(int argc, char **argv)
         struct SRLAEncodeParameter parameter;
         parameter.num_channels = (uint16_t)first.channels; parameter.bits_per_sample = (uint16_t)first.bits; parameter.sampling_rate = first.rate;
         parameter.min_num_samples_per_block = max_block >> divisions; parameter.max_num_samples_per_block = max_block;
-        parameter.num_lookahead_samples = factor * max_block; parameter.num_svr_filter_learning_iteration = 0;
+        parameter.num_lookahead_samples = factor * max_block; parameter.num_svr_filter_learning_iteration = svr;
         parameter.ltp_order = ltp; parameter.preset = (uint8_t)mode;
         if (SRLAEncoder_SetEncodeParameter(encoder, &parameter) == SRLA_APIRESULT_OK) {
             const auto tw = std::chrono::steady_clock::now();
@@ -370,7 +373,7 @@ int main(int argc, char **argv)
             parameter.min_num_samples_per_block = max_block >> divisions;
             parameter.max_num_samples_per_block = max_block;
             parameter.num_lookahead_samples = factor * max_block;
-            parameter.num_svr_filter_learning_iteration = 0;
+            parameter.num_svr_filter_learning_iteration = svr;
             parameter.ltp_order = ltp;
             parameter.preset = (uint8_t)mode;
             const SRLAApiResult set = SRLAEncoder_SetEncodeParameter(encoder, &parameter);

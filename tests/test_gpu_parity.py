@@ -223,7 +223,8 @@ def test_reference_cli_relinked_against_libsrla_b200(tmp_path):
     with wave.open(str(wav), "wb") as w:
         w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000)
         w.writeframes(pcm.T.astype("<i2").tobytes())
-    for extra, tag in ((["-m", "4", "-B", "4096", "-V", "0"], "fixed"), (["-m", "4"], "cli_defaults_v1"), (["-m", "2", "-B", "2048", "-V", "0", "-P", "3"], "ltp")):
+    for extra, tag in ((["-m", "4", "-B", "4096", "-V", "0"], "fixed"), (["-m", "4"], "cli_defaults_v1"), (["-m", "2", "-B", "2048", "-V", "0", "-P", "3"], "ltp"),
+                       (["-m", "3", "-B", "4096", "-V", "0", "--svr-filter-learning-iteration", "2"], "svr")):
         a, b = tmp_path / f"ref_{tag}.srl", tmp_path / f"b200_{tag}.srl"
         subprocess.run([ref_cli, "-e"] + extra + [str(wav), str(a)], check=True, stdout=subprocess.DEVNULL)
         subprocess.run([our_cli, "-e"] + extra + [str(wav), str(b)], check=True, stdout=subprocess.DEVNULL)
@@ -415,7 +416,8 @@ def test_batch_cli_writes_what_the_reference_cli_writes(tmp_path):
     for name, (pcm, bits, kw) in files.items():
         _write_wav(tmp_path / f"{name}.wav", pcm, bits, **kw)
     (tmp_path / "broken.wav").write_bytes(b"RIFF\x00\x00\x00\x00WAVEjunk")
-    for extra, tag in ((["-m", "4", "-B", "4096", "-V", "0"], "fixed"), (["-m", "3"], "defaults_v1"), (["-m", "2", "-B", "2048", "-V", "0", "-P", "3"], "ltp")):
+    for extra, tag in ((["-m", "4", "-B", "4096", "-V", "0"], "fixed"), (["-m", "3"], "defaults_v1"), (["-m", "2", "-B", "2048", "-V", "0", "-P", "3"], "ltp"),
+                       (["-m", "3", "-B", "4096", "-V", "0", "--svr-filter-learning-iteration", "2"], "svr")):
         out_dir = tmp_path / f"out_{tag}"
         r = subprocess.run([batch] + extra + ["-o", str(out_dir)] + [str(tmp_path / f"{n}.wav") for n in files] + [str(tmp_path / "broken.wav")],
                            stdout=subprocess.PIPE, stderr=subprocess.PIPE)

@@ -7,6 +7,7 @@ rate is reported beside it.
 
   config 3: 48 kHz / 24-bit stereo, block 8192, mode 4, LTP order 3
   config 4: 16-bit stereo, variable blocks -V 2 -L 4 (min 1024, max 4096, look-ahead 16384), mode 4
+  config 2 + SVR: the config-2 signal with the SVR coefficient refinement switched on (3 iterations)
   config 5: one GPU's shard of the 1024-file batch: 128 stereo 16-bit files of 30 s (1 440 000 frames = 351 blocks
             of 4096 + a 2304-frame tail each), mode 4, one SRLAB200_EncodeStreamsHost call
 Usage: python tools/bench_configs.py [--files 128] [--seconds 60]
@@ -48,9 +49,9 @@ def main() -> None:
             return pinned(inter.astype("<i2").view(np.uint8).reshape(-1))
         return pinned(np.ascontiguousarray(inter.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1))
 
-    def run(name, streams, bits, min_block, max_block, lookahead, ltp, ref_frames):
+    def run(name, streams, bits, min_block, max_block, lookahead, ltp, ref_frames, svr=0):
         with E.Encoder(max_channels=2, max_block=max_block, min_block=min_block, lookahead=lookahead) as enc:
-            assert enc.set_parameter(2, bits, 48000, min_block, max_block, lookahead, ltp, 4) == E.OK
+            assert enc.set_parameter(2, bits, 48000, min_block, max_block, lookahead, ltp, 4, svr) == E.OK
             cap = sum(enc.max_encoded_size(s.shape[1]) for s in streams)
             out = pinned(np.empty(cap, dtype=np.uint8))
             best = None
@@ -81,9 +82,11 @@ def main() -> None:
             if have_ref():
                 sl = np.ascontiguousarray(streams[0][:, :ref_frames].astype(np.int32))
                 t0 = time.perf_counter()
-                want = ref_encode(sl, bps=bits, max_block=max_block, min_block=min_block, lookahead=lookahead, ltp=ltp, preset=4)
+                want = ref_encode(sl, bps=bits, max_block=max_block, min_block=min_block, lookahead=lookahead, ltp=ltp, preset=4, svr=svr)
                 dt = time.perf_counter() - t0
-                got = E.encode(sl, bps=bits, max_block=max_block, min_block=min_block, lookahead=lookahead, ltp=ltp, preset=4)
+                with E.Encoder(max_channels=2, max_block=max_block, min_block=min_block, lookahead=lookahead) as e2:
+                    assert e2.set_parameter(2, bits, 48000, min_block, max_block, lookahead, ltp, 4, svr) == E.OK
+                    got = e2.encode_whole(sl) if min_block == max_block else E.encode(sl, bps=bits, max_block=max_block, min_block=min_block, lookahead=lookahead, ltp=ltp, preset=4)
                 line["reference_1thread_Msamples_per_s"] = sl.size / dt / 1e6
                 line["identical_to_reference_on_slice"] = bool(got == want)
             print(json.dumps(line), flush=True)
@@ -93,6 +96,7 @@ def main() -> None:
     run("3: 24-bit stereo, block 8192, mode 4, LTP 3", [pinned(wide.astype(np.int32))], 24, 8192, 8192, 8192, 3, 8192 * 12)
     narrow = make_blocks_workload((n + 4095) // 4096, 4096, 2, 16, seed=78, num_templates=2, template_blocks=48)[:, :n]
     run("4: 16-bit stereo, -V 2 -L 4 (1024..4096, look-ahead 16384), mode 4", [pinned(narrow.astype(np.int16))], 16, 1024, 4096, 16384, 0, 16384 * 6)
+    run("2 + SVR: 16-bit stereo, block 4096, mode 4, --svr-filter-learning-iteration 3", [pinned(narrow.astype(np.int16))], 16, 4096, 4096, 4096, 0, 4096 * 4, svr=3)
     frames = 1_440_000
     base = make_blocks_workload((frames + 4095) // 4096 + 1, 4096, 2, 16, seed=79, num_templates=2, template_blocks=88)
     files = [pinned(np.roll(base, 4099 * k, axis=1)[:, :frames].astype(np.int16)) for k in range(args.files)]
