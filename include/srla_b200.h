@@ -132,6 +132,47 @@ SRLAApiResult SRLAEncoder_EncodeWhole(
     struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples,
     uint8_t *data, uint32_t data_size, uint32_t *output_size, SRLAEncoder_EncodeBlockCallback encode_callback);
 
+/* ---- decoder: include/srla_decoder.h:8-56, same names, layouts and result codes ---- */
+
+/* include/srla_decoder.h:8-12 */
+struct SRLADecoderConfig {
+    uint32_t max_num_channels;
+    uint32_t max_num_parameters;
+    uint8_t  check_checksum;              /* 1: verify every block's Fletcher-16, anything else: do not */
+};
+
+struct SRLADecoder;   /* opaque */
+
+/* include/srla_decoder.h:22-23 (srla_decoder.c:63-134): 30-byte header -> struct. Host only. */
+SRLAApiResult SRLADecoder_DecodeHeader(const uint8_t *data, uint32_t data_size, struct SRLAHeader *header);
+
+/* include/srla_decoder.h:26 (srla_decoder.c:185-218): host bytes Create needs; -1 for an invalid config. */
+int32_t SRLADecoder_CalculateWorkSize(const struct SRLADecoderConfig *config);
+
+/* include/srla_decoder.h:29 (srla_decoder.c:221-312); NULL also when no CUDA device is usable. */
+struct SRLADecoder *SRLADecoder_Create(const struct SRLADecoderConfig *config, void *work, int32_t work_size);
+
+/* include/srla_decoder.h:32 (srla_decoder.c:315-322) */
+void SRLADecoder_Destroy(struct SRLADecoder *decoder);
+
+/* include/srla_decoder.h:35-36 (srla_decoder.c:325-360); additionally INVALID_FORMAT for bit depths other than 8/16/24. */
+SRLAApiResult SRLADecoder_SetHeader(struct SRLADecoder *decoder, const struct SRLAHeader *header);
+
+/* include/srla_decoder.h:39-43 (srla_decoder.c:633-737): one block, host bytes in, planar host int32 out. */
+SRLAApiResult SRLADecoder_DecodeBlock(
+    struct SRLADecoder *decoder, const uint8_t *data, uint32_t data_size,
+    int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples,
+    uint32_t *decode_size, uint32_t *num_decode_samples);
+
+/* include/srla_decoder.h:46-49 (srla_decoder.c:740-799): header + every block; all blocks of the stream are
+ * decoded by one kernel launch (one CTA per block). */
+SRLAApiResult SRLADecoder_DecodeWhole(
+    struct SRLADecoder *decoder, const uint8_t *data, uint32_t data_size,
+    int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples);
+
+/* device time (CUDA events) of the decode kernel of the handle's most recent call, in ms */
+float SRLAB200_DecoderKernelMs(const struct SRLADecoder *decoder);
+
 /* ------------------------------------------------------------------------------------------------
  * Part 2 -- batch / device-resident extension (not in the reference)
  * ---------------------------------------------------------------------------------------------- */

@@ -1,0 +1,622 @@
+/*
+ * decoder.cuh -- the decode path: SRLADecoder_* with the reference's signatures
+ * (include/srla_decoder.h:8-56) on the GPU.  Included by libsrla_b200.cu (one translation unit).
+ *
+ * A stream decodes block by block and nothing crosses a block boundary (srla_decoder.c:633-799), so
+ * a whole stream is one launch: one CTA per block, one warp per channel.
+ *   parse     the bitstream of a block is serial (the second channel starts where the first one's
+ *             codes end), so lane 0 of warp 0 walks it: side information into shared memory, residual
+ *             codes (srla_coder.c:596-690) straight into the output buffer.  Meanwhile the other lanes
+ *             of warp 0 have summed the block's Fletcher-16 checksum (srla_utility.c:36-60).
+ *   synthesis (srla_lpc_synthesize.c:238-262) is a recurrence over samples; warp w runs channel w as a
+ *             systolic filter: lane L owns the outputs m = L (mod 32) and keeps their partial sums, every
+ *             finished sample is broadcast with one shuffle and each lane adds its tap's product -- one
+ *             shuffle and one multiply-add on the dependent chain per sample instead of `order` of them.
+ *             Long-term synthesis (:264-327) advances in chunks shorter than the pitch lag, de-emphasis
+ *             (srla_utility.c:361-378) is a first-order recurrence left to one lane.
+ *   finish    mid/side -> left/right (srla_utility.c:106-174) and the offset shift, all threads.
+ * All integer arithmetic wraps like the reference's int32 code does on x86.
+ */
+#ifndef SRLA_B200_DECODER_CUH
+#define SRLA_B200_DECODER_CUH
+
+namespace srla {
+
+struct DecBlock {
+    unsigned long long offset;     /* byte offset of the block (its sync code) inside the data buffer */
+    uint32_t bytes;                /* 6 + size field                                                   */
+    uint32_t sample_offset;        /* where its samples go inside every channel                        */
+    uint32_t nsmpl;                /* samples per channel (block header, read by the host walk)        */
+    uint32_t pad;
+};
+
+struct DecParams {
+    const uint8_t *data;
+    const DecBlock *blocks;
+    uint32_t *status;              /* per block: SRLAApiResult                                         */
+    int32_t *out;                  /* planar: channel c at out + c * stride                            */
+    unsigned long long stride;
+    uint32_t nch, bps, lshift, check;
+    const uint16_t *tree;          /* [2 trees][2 bits][256] children, then the two roots               */
+};
+
+/* ---- big-endian bit reader over global memory: 64-bit window, aligned 32-bit refills, one word prefetched ---- */
+struct DecBits {
+    const uint32_t *word;          /* next aligned word to fetch                                       */
+    const uint32_t *limit;         /* first word past the block                                        */
+    uint32_t ahead;                /* prefetched word (already byte-swapped)                           */
+    unsigned long long win;        /* valid bits at the top                                            */
+    int avail;
+    unsigned long long consumed;   /* bits taken so far                                                */
+    __device__ __forceinline__ uint32_t fetch()
+    {
+        const uint32_t v = (word < limit) ? __ldg(word) : 0u;
+        ++word;
+        return __byte_perm(v, 0u, 0x0123);
+    }
+    __device__ __forceinline__ void open(const uint8_t *p, const uint8_t *end)
+    {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        word = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        limit = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(end) + 3) & ~(uintptr_t)3);
+        const int skip = (int)(a & 3) * 8;
+        win = (unsigned long long)fetch() << 32;
+        win <<= skip;
+        avail = 32 - skip;
+        ahead = fetch();
+        consumed = 0;
+        refill();
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (avail <= 32) { win |= (unsigned long long)ahead << (32 - avail); avail += 32; ahead = fetch(); }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n)               /* n <= 32; 0 gives 0 (bit_stream.h: GetBits) */
+    {
+        if (n == 0u) { return 0u; }
+        const uint32_t v = (uint32_t)(win >> (64 - n));
+        win <<= n; avail -= (int)n; consumed += n;
+        refill();
+        return v;
+    }
+    __device__ __forceinline__ uint32_t zero_run(unsigned long long max_bits)      /* zeros up to and including the closing 1 */
+    {
+        uint32_t run = 0;
+        for (;;) {
+            const int z = win ? __clzll((long long)win) : 64;
+            if (z < avail) { win <<= (z + 1); avail -= z + 1; consumed += (unsigned)(z + 1); refill(); return run + (uint32_t)z; }
+            run += (uint32_t)avail; consumed += (unsigned)avail;
+            win = 0; avail = 0;
+            refill();
+            if (consumed > max_bits) { return run; }                                /* ran off the block: corrupt data */
+        }
+    }
+};
+
+__device__ __forceinline__ int32_t dec_zigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+
+constexpr int kDecMaxTaps = 8;                 /* accumulators per lane: 8 x 32 >= order 255 */
+
+struct DecChannel {
+    int32_t head, pre_coef;
+    uint32_t order, rshift;
+    uint32_t ltp_order, ltp_period;
+    int32_t ltp_coef[4];
+    int32_t cp[32 * kDecMaxTaps + 4];          /* cp[d] multiplies x[m - d], d = 1 .. order; 0 elsewhere */
+};
+
+/* LPC synthesis of one channel by one warp, T accumulators per lane (order <= 32 T) */
+template <int T>
+__device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const DecChannel &chn, uint32_t lane)
+{
+    const uint32_t order = chn.order, rshift = chn.rshift;
+    const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;     /* 1 << -1 on x86 */
+    uint32_t acc[T];
+    #pragma unroll
+    for (int t = 0; t < T; ++t) { acc[t] = 0u; }
+    uint32_t xprev = 0u, mine = 0u;
+    for (uint32_t base = 0; base < n; base += 32u) {
+        const uint32_t own = base + lane;
+        const uint32_t res = (own < n) ? (uint32_t)x[own] : 0u;                     /* this lane's output of the round */
+        const uint32_t steps = (n - base < 32u) ? n - base : 32u;
+        for (uint32_t s = 0; s < steps; ++s) {
+            const uint32_t q = base + s;
+            /* every lane evaluates "its" candidate; only the owner's is taken */
+            uint32_t cand;
+            if (q == 0u) { cand = res; }
+            else if (q < order) { cand = res + xprev; }
+            else { cand = res - (uint32_t)((int32_t)(acc[0] + half) >> rshift); }
+            const uint32_t xq = __shfl_sync(0xffffffffu, cand, (int)s);
+            if (lane == s) {
+                mine = xq;
+                #pragma unroll
+                for (int t = 0; t + 1 < T; ++t) { acc[t] = acc[t + 1]; }
+                acc[T - 1] = 0u;
+            }
+            xprev = xq;
+            const uint32_t d0 = ((lane - s - 1u) & 31u) + 1u;                       /* distance to this lane's next output */
+            #pragma unroll
+            for (int t = 0; t < T; ++t) { acc[t] += (uint32_t)chn.cp[d0 + 32u * (uint32_t)t] * xq; }
+        }
+        if (own < n) { x[own] = (int32_t)mine; }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
+{
+    __shared__ DecChannel chan[kMaxChannels];
+    __shared__ uint32_t sh_type, sh_n, sh_status, sh_method;
+    __shared__ uint32_t sh_sum[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const DecBlock blk = p.blocks[blockIdx.x];
+    const uint8_t *b = p.data + blk.offset;
+    const uint32_t nch = p.nch;
+    if (tid == 0u) { sh_status = 0u; sh_type = 3u; sh_n = 0u; sh_method = 0u; }
+    __syncthreads();
+
+    /* ---- block header (srla_decoder.c:661-700): sync, size, checksum, type, sample count ---- */
+    if (warp == 0u) {
+        const uint32_t size = ((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5];
+        const bool size_ok = size >= 5u && size + 6u <= blk.bytes;
+        if (lane == 0u) { sh_sum[0] = 0u; sh_sum[1] = 0u; }
+        __syncwarp();
+        if (p.check && size_ok) {
+            /* Fletcher-16 over the size - 2 bytes after the checksum field: lanes take contiguous chunks,
+             * sum2 of the whole = sum over chunks of (sum2_chunk + bytes_after_chunk_start ... ) folded below */
+            const uint32_t len = size - 2u;
+            const uint8_t *q = b + 8;
+            const uint32_t per = (len + 31u) / 32u;
+            const uint32_t lo = min(len, lane * per), hi = min(len, lo + per);
+            uint32_t s1 = 0, s2 = 0;
+            for (uint32_t i = lo; i < hi; ++i) {
+                s1 += q[i]; s2 += s1;
+                if (((i - lo) & 4095u) == 4095u) { s1 %= 255u; s2 %= 255u; }
+            }
+            s1 %= 255u; s2 %= 255u;
+            /* combine in lane order: after a chunk of length L, sum2 += L * sum1_before */
+            uint32_t t1 = 0, t2 = 0;
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t c1 = __shfl_sync(0xffffffffu, s1, l), c2 = __shfl_sync(0xffffffffu, s2, l);
+                const uint32_t cl = min(len, min(len, (uint32_t)l * per) + per) - min(len, (uint32_t)l * per);
+                t2 = (t2 + c2 + (cl % 255u) * t1) % 255u;
+                t1 = (t1 + c1) % 255u;
+            }
+            if (lane == 0u) { sh_sum[0] = t1; sh_sum[1] = t2; }
+        }
+        __syncwarp();
+        if (lane == 0u) {
+            uint32_t status = 0u;
+            if (b[0] != 0xFFu || b[1] != 0xFFu) { status = SRLA_APIRESULT_INVALID_FORMAT; }
+            else if (size + 6u > blk.bytes) { status = SRLA_APIRESULT_INSUFFICIENT_DATA; }
+            else if (size < 5u) { status = SRLA_APIRESULT_INVALID_FORMAT; }
+            else if (p.check && ((sh_sum[1] << 8) | sh_sum[0]) != (((uint32_t)b[6] << 8) | b[7])) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+            else if (b[8] > 2u) { status = SRLA_APIRESULT_INVALID_FORMAT; }
+            sh_type = b[8];
+            sh_n = ((uint32_t)b[9] << 8) | b[10];
+            if (!status && sh_n != blk.nsmpl) { status = SRLA_APIRESULT_INVALID_FORMAT; }
+            sh_status = status;
+        }
+    }
+    __syncthreads();
+    const uint32_t n = sh_n, type = sh_type;
+    int32_t *out = p.out + blk.sample_offset;
+    if (sh_status != 0u) { if (tid == 0u) { p.status[blockIdx.x] = sh_status; } return; }
+    const uint8_t *payload = b + 11;
+    const uint32_t payload_bytes = blk.bytes - 11u;
+
+    if (type == (uint32_t)kBlockSilent) {
+        for (uint32_t i = tid; i < n * nch; i += blockDim.x) { out[(size_t)(i / n) * p.stride + (i % n)] = 0; }
+        if (tid == 0u) { p.status[blockIdx.x] = 0u; }
+        return;
+    }
+    if (type == (uint32_t)kBlockRaw) {
+        /* srla_decoder.c:363-433: frames of big-endian zig-zag samples */
+        const uint32_t sb = p.bps >> 3;
+        if ((uint64_t)payload_bytes < ((uint64_t)p.bps * n * nch) / 8u) { if (tid == 0u) { p.status[blockIdx.x] = SRLA_APIRESULT_INSUFFICIENT_DATA; } return; }
+        for (uint32_t i = tid; i < n * nch; i += blockDim.x) {
+            const uint8_t *q = payload + (size_t)i * sb;
+            uint32_t u = 0;
+            for (uint32_t k = 0; k < sb; ++k) { u = (u << 8) | q[k]; }
+            const uint32_t smpl = i / nch, ch = i - smpl * nch;
+            out[(size_t)ch * p.stride + smpl] = dec_zigzag(u);
+        }
+        if (tid == 0u) { p.status[blockIdx.x] = 0u; }
+        return;
+    }
+
+    /* ---- compressed block: the serial walk (srla_decoder.c:436-540) ---- */
+    if (tid == 0u) {
+        DecBits br;
+        br.open(payload, payload + payload_bytes);
+        const unsigned long long max_bits = 8ull * payload_bytes;
+        const uint16_t *tree0 = p.tree, *tree1 = p.tree + 512;
+        const uint32_t root0 = p.tree[1024], root1 = p.tree[1025];
+        uint32_t status = 0u;
+        sh_method = br.get(2);
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            chan[ch].head = dec_zigzag(br.get(p.bps + 1u));
+            chan[ch].pre_coef = dec_zigzag(br.get(5));
+        }
+        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
+            DecChannel &c = chan[ch];
+            c.order = br.get(8); c.rshift = br.get(4);
+            const uint32_t use_sum = br.get(1);
+            for (uint32_t d = 0; d < 32u * kDecMaxTaps + 4u; ++d) { c.cp[d] = 0; }
+            int32_t prev = 0;
+            for (uint32_t i = 0; i < c.order; ++i) {
+                const uint16_t *tree = (use_sum && i > 0u) ? tree1 : tree0;
+                uint32_t node = (use_sum && i > 0u) ? root1 : root0;
+                do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u && br.consumed <= max_bits);
+                int32_t v = dec_zigzag(node & 255u);
+                if (use_sum && i > 0u) { v -= prev; }                                /* summed-neighbour table: coef[i] = code - coef[i-1] */
+                prev = v;
+                c.cp[c.order - i] = v;                                               /* coef[i] multiplies x[m - order + i] */
+            }
+            if (br.consumed > max_bits) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+        }
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            DecChannel &c = chan[ch];
+            c.ltp_period = 0; c.ltp_order = 0;
+            if (br.get(1)) {
+                c.ltp_order = 2u * br.get(1) + 1u;
+                c.ltp_period = br.get(8) + (uint32_t)kLtpMinPeriod;
+                for (uint32_t i = 0; i < c.ltp_order; ++i) { c.ltp_coef[i] = dec_zigzag(br.get(6)); }
+            }
+        }
+        /* residual codes (srla_coder.c:648-690) */
+        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
+            int32_t *x = out + (size_t)ch * p.stride;
+            const uint32_t code = br.get(2);
+            if (code == (uint32_t)kCodeAllZero) { for (uint32_t i = 0; i < n; ++i) { x[i] = 0; } continue; }
+            if (code > (uint32_t)kCodeAllZero) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+            const uint32_t porder = br.get(10);
+            if (porder > (uint32_t)kLog2MaxParts) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+            const uint32_t per = n >> porder;
+            uint32_t k = 0;
+            for (uint32_t part = 0; part < (1u << porder); ++part) {
+                if (part == 0u) { k = br.get(5); }
+                else { k = (uint32_t)((int32_t)k + dec_zigzag(br.zero_run(max_bits))); }
+                if (k > 31u) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+                int32_t *dst = x + (size_t)part * per;
+                if (code == (uint32_t)kCodeRice) {
+                    for (uint32_t i = 0; i < per; ++i) { const uint32_t quot = br.zero_run(max_bits); dst[i] = dec_zigzag((quot << k) + br.get(k)); }
+                } else {
+                    for (uint32_t i = 0; i < per; ++i) {
+                        const uint32_t quot = br.zero_run(max_bits);
+                        const uint32_t low = br.get(k + (quot ? 0u : 1u));
+                        dst[i] = dec_zigzag(low | ((quot + (quot ? 1u : 0u)) << k));
+                    }
+                }
+                if (br.consumed > max_bits) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+            }
+            for (uint32_t i = per << porder; i < n; ++i) { x[i] = 0; }              /* never happens for streams the encoder writes */
+        }
+        sh_status = status;
+        __threadfence_block();
+    }
+    __syncthreads();
+    if (sh_status != 0u) { if (tid == 0u) { p.status[blockIdx.x] = sh_status; } return; }
+
+    /* ---- synthesis: warp w = channel w ---- */
+    if (warp < nch && n > 0u) {
+        int32_t *x = out + (size_t)warp * p.stride;
+        const DecChannel &c = chan[warp];
+        if (c.order > 0u && n > c.order) {
+            if (c.order <= 32u) { dec_lpc_synthesize<1>(x, n, c, lane); }
+            else if (c.order <= 64u) { dec_lpc_synthesize<2>(x, n, c, lane); }
+            else if (c.order <= 128u) { dec_lpc_synthesize<4>(x, n, c, lane); }
+            else { dec_lpc_synthesize<8>(x, n, c, lane); }
+        } else if (c.order > 0u) {
+            /* a block no longer than the order is all warm-up (srla_lpc_synthesize.c:253-255): running sum */
+            if (lane == 0u) { for (uint32_t i = 1; i < n && i < c.order; ++i) { x[i] = (int32_t)((uint32_t)x[i] + (uint32_t)x[i - 1]); } }
+            __syncwarp();
+        }
+        if (c.ltp_period > 0u && c.ltp_order > 0u) {
+            /* srla_lpc_synthesize.c:264-327: x[s] += (16 + sum_j c[j] x[s - T - h + j]) >> 5 for s > T + h; a chunk shorter
+             * than the shortest lag T - h never reads what it writes */
+            const uint32_t h = c.ltp_order >> 1, T0 = c.ltp_period;
+            const uint32_t chunk = min(32u, T0 - h);
+            for (uint32_t s0 = T0 + h + 1u; s0 < n; s0 += chunk) {
+                const uint32_t s = s0 + lane;
+                if (lane < chunk && s < n) {
+                    uint32_t predict = 16u;
+                    for (uint32_t j = 0; j < c.ltp_order; ++j) { predict += (uint32_t)c.ltp_coef[j] * (uint32_t)x[s - T0 - h + j]; }
+                    x[s] = (int32_t)((uint32_t)x[s] + (uint32_t)((int32_t)predict >> 5));
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0u) {
+            /* de-emphasis (srla_utility.c:361-378): x[0] += (head c) >> 4, x[i] += (x[i-1] c) >> 4 */
+            const uint32_t pc = (uint32_t)c.pre_coef;
+            uint32_t prev = (uint32_t)x[0] + (uint32_t)((int32_t)((uint32_t)c.head * pc) >> 4);
+            x[0] = (int32_t)prev;
+            #pragma unroll 8
+            for (uint32_t i = 1; i < n; ++i) {
+                prev = (uint32_t)x[i] + (uint32_t)((int32_t)(prev * pc) >> 4);
+                x[i] = (int32_t)prev;
+            }
+        }
+    }
+    __syncthreads();
+    /* ---- channel reconstruction (srla_utility.c:106-174) and the offset shift (srla_decoder.c:582-590) ---- */
+    const uint32_t method = sh_method, sh = p.lshift;
+    if (nch >= 2u && method != 0u) {
+        int32_t *c0 = out, *c1 = out + p.stride;
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            uint32_t a = (uint32_t)c0[i], s = (uint32_t)c1[i];
+            if (method == 1u) { a -= (uint32_t)((int32_t)s >> 1); s += a; }          /* MS */
+            else if (method == 2u) { s += a; }                                       /* LS */
+            else { a = s - a; }                                                      /* SR */
+            c0[i] = (int32_t)(a << sh); c1[i] = (int32_t)(s << sh);
+        }
+        if (sh > 0u) { for (uint32_t i = tid; i < n * (nch - 2u); i += blockDim.x) { int32_t *v = out + (size_t)(2u + i / n) * p.stride + (i % n); *v = (int32_t)((uint32_t)*v << sh); } }
+    } else if (sh > 0u) {
+        for (uint32_t i = tid; i < n * nch; i += blockDim.x) { int32_t *v = out + (size_t)(i / n) * p.stride + (i % n); *v = (int32_t)((uint32_t)*v << sh); }
+    }
+    if (tid == 0u) { p.status[blockIdx.x] = 0u; }
+}
+
+} // namespace srla
+
+/* ================================================================================================
+ * host side: the reference's decoder API
+ * ============================================================================================== */
+namespace {
+
+const uint32_t kDecoderMagic = 0x53424C44u;
+
+struct DecoderCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf data, out, blocks, status, tree;
+    PinBuf h_blocks, h_status;
+    float last_ms = 0.f;
+};
+
+} // namespace
+
+struct SRLADecoder {
+    uint32_t magic;
+    struct SRLADecoderConfig config;
+    struct SRLAHeader header;
+    int set_header;
+    uint8_t alloced_by_own;
+    void *work;
+    DecoderCtx *ctx;
+};
+
+namespace {
+
+bool decoder_ctx_init(DecoderCtx *c)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        std::fprintf(stderr, "[srla_b200] no CUDA device: the SRLA B200 decode path has no CPU fallback\n");
+        return false;
+    }
+    if (g_device >= 0) { CU_TRY(cudaSetDevice(g_device)); }
+    CU_TRY(cudaGetDevice(&c->device));
+    CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreate(&c->ev0));
+    CU_TRY(cudaEventCreate(&c->ev1));
+    host::HuffTable plain, summed; host::HuffTree t0, t1;
+    host::build_format_huffman(plain, summed, &t0, &t1);
+    uint16_t tab[1026];
+    for (int b = 0; b < 2; b++) { for (int i = 0; i < 256; i++) { tab[b * 256 + i] = t0.child[b][i]; tab[512 + b * 256 + i] = t1.child[b][i]; } }
+    tab[1024] = t0.root; tab[1025] = t1.root;
+    if (!c->tree.reserve(sizeof(tab))) { return false; }
+    CU_TRY(cudaMemcpy(c->tree.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    return true;
+}
+
+void decoder_ctx_destroy(DecoderCtx *c)
+{
+    if (!c) { return; }
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->ev0) { cudaEventDestroy(c->ev0); }
+    if (c->ev1) { cudaEventDestroy(c->ev1); }
+    DevBuf *bufs[] = { &c->data, &c->out, &c->blocks, &c->status, &c->tree };
+    for (DevBuf *b : bufs) { b->release(); }
+    c->h_blocks.release(); c->h_status.release();
+}
+
+SRLAApiResult decoder_header_valid(const struct SRLAHeader *h)            /* srla_decoder.c:137-182 */
+{
+    if (h->format_version != SRLA_FORMAT_VERSION || h->codec_version != SRLA_CODEC_VERSION) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (h->num_channels == 0 || h->num_samples == 0 || h->sampling_rate == 0 || h->bits_per_sample == 0) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (h->offset_lshift >= 32 || h->max_num_samples_per_block == 0 || h->preset >= SRLA_NUM_PARAMETER_PRESETS) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    return SRLA_APIRESULT_OK;
+}
+
+/* decode `blocks` (already walked) of the stream at `data` into the caller's channel pointers */
+SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t data_bytes, const std::vector<DecBlock> &blocks,
+                          int32_t **buffer, uint32_t total_samples)
+{
+    DecoderCtx *c = d->ctx;
+    if (cudaSetDevice(c->device) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    const uint32_t nch = d->header.num_channels;
+    const uint64_t stride = round_up_u32(total_samples, 16);
+    const size_t nb = blocks.size();
+    if (nb == 0) { return SRLA_APIRESULT_OK; }
+    if (!c->data.reserve(data_bytes + 16) || !c->out.reserve(sizeof(int32_t) * stride * nch) || !c->blocks.reserve(sizeof(DecBlock) * nb)
+        || !c->status.reserve(sizeof(uint32_t) * nb) || !c->h_blocks.reserve(sizeof(DecBlock) * nb) || !c->h_status.reserve(sizeof(uint32_t) * nb)) { return SRLA_APIRESULT_NG; }
+    std::memcpy(c->h_blocks.p, blocks.data(), sizeof(DecBlock) * nb);
+    if (cudaMemcpyAsync(c->blocks.p, c->h_blocks.p, sizeof(DecBlock) * nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
+        || cudaMemcpyAsync(c->data.p, data, data_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
+        || cudaMemsetAsync((uint8_t *)c->data.p + data_bytes, 0, 16, c->stream) != cudaSuccess
+        || cudaMemsetAsync(c->status.p, 0xff, sizeof(uint32_t) * nb, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    DecParams p;
+    p.data = (const uint8_t *)c->data.p; p.blocks = (const DecBlock *)c->blocks.p; p.status = (uint32_t *)c->status.p;
+    p.out = (int32_t *)c->out.p; p.stride = stride;
+    p.nch = nch; p.bps = d->header.bits_per_sample; p.lshift = d->header.offset_lshift; p.check = (d->config.check_checksum == 1) ? 1u : 0u;
+    p.tree = (const uint16_t *)c->tree.p;
+    cudaEventRecord(c->ev0, c->stream);
+    decode_blocks_kernel<<<(unsigned)nb, 32u * std::max(1u, nch), 0, c->stream>>>(p);
+    cudaEventRecord(c->ev1, c->stream);
+    if (cudaGetLastError() != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    if (cudaMemcpyAsync(c->h_status.p, c->status.p, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
+        || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        std::fprintf(stderr, "[srla_b200] decode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return SRLA_APIRESULT_NG;
+    }
+    cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    /* the reference stops at the first bad block and leaves the earlier ones decoded (srla_decoder.c:780-786) */
+    const uint32_t *st = (const uint32_t *)c->h_status.p;
+    uint32_t good_samples = total_samples; SRLAApiResult rc = SRLA_APIRESULT_OK;
+    for (size_t i = 0; i < nb; i++) { if (st[i] != 0u) { rc = (st[i] <= (uint32_t)SRLA_APIRESULT_NG) ? (SRLAApiResult)st[i] : SRLA_APIRESULT_NG; good_samples = blocks[i].sample_offset; break; } }
+    for (uint32_t ch = 0; ch < nch && good_samples > 0; ch++) {
+        if (cudaMemcpy(buffer[ch], (const int32_t *)c->out.p + stride * ch, sizeof(int32_t) * good_samples, cudaMemcpyDeviceToHost) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    }
+    return rc;
+}
+
+} // namespace
+
+extern "C" {
+
+SRLAApiResult SRLADecoder_DecodeHeader(const uint8_t *data, uint32_t data_size, struct SRLAHeader *header)
+{
+    if (data == NULL || header == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (data_size < SRLA_HEADER_SIZE) { return SRLA_APIRESULT_INSUFFICIENT_DATA; }
+    if (data[0] != '1' || data[1] != '2' || data[2] != '4' || data[3] != '9') { return SRLA_APIRESULT_INVALID_FORMAT; }
+    auto be32 = [&](int at) { return ((uint32_t)data[at] << 24) | ((uint32_t)data[at + 1] << 16) | ((uint32_t)data[at + 2] << 8) | data[at + 3]; };
+    auto be16 = [&](int at) { return (uint16_t)(((uint32_t)data[at] << 8) | data[at + 1]); };
+    struct SRLAHeader h;
+    h.format_version = be32(4); h.codec_version = be32(8); h.num_channels = be16(12); h.num_samples = be32(14);
+    h.sampling_rate = be32(18); h.bits_per_sample = be16(22); h.offset_lshift = data[24];
+    h.max_num_samples_per_block = be32(25); h.preset = data[29];
+    *header = h;
+    return SRLA_APIRESULT_OK;
+}
+
+int32_t SRLADecoder_CalculateWorkSize(const struct SRLADecoderConfig *config)
+{
+    if (config == NULL || config->max_num_channels == 0) { return -1; }
+    return (int32_t)(sizeof(struct SRLADecoder) + 64);
+}
+
+struct SRLADecoder *SRLADecoder_Create(const struct SRLADecoderConfig *config, void *work, int32_t work_size)
+{
+    uint8_t own = 0;
+    if (work == NULL && work_size == 0) {
+        if ((work_size = SRLADecoder_CalculateWorkSize(config)) < 0) { return NULL; }
+        work = std::malloc((size_t)work_size);
+        own = 1;
+    }
+    if (config == NULL || work == NULL || work_size < SRLADecoder_CalculateWorkSize(config) || config->max_num_channels == 0
+        || config->max_num_channels > SRLA_MAX_NUM_CHANNELS) {
+        if (own) { std::free(work); }
+        return NULL;
+    }
+    struct SRLADecoder *d = (struct SRLADecoder *)(((uintptr_t)work + 15u) & ~(uintptr_t)15u);
+    std::memset(d, 0, sizeof(*d));
+    d->magic = kDecoderMagic; d->config = *config; d->alloced_by_own = own; d->work = work;
+    d->ctx = new (std::nothrow) DecoderCtx();
+    if (d->ctx == nullptr || !decoder_ctx_init(d->ctx)) {
+        if (d->ctx) { decoder_ctx_destroy(d->ctx); delete d->ctx; }
+        d->magic = 0;
+        if (own) { std::free(work); }
+        return NULL;
+    }
+    return d;
+}
+
+void SRLADecoder_Destroy(struct SRLADecoder *decoder)
+{
+    if (decoder == NULL || decoder->magic != kDecoderMagic) { return; }
+    decoder_ctx_destroy(decoder->ctx);
+    delete decoder->ctx;
+    decoder->magic = 0;
+    if (decoder->alloced_by_own) { std::free(decoder->work); }
+}
+
+SRLAApiResult SRLADecoder_SetHeader(struct SRLADecoder *decoder, const struct SRLAHeader *header)
+{
+    if (decoder == NULL || header == NULL || decoder->magic != kDecoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (decoder_header_valid(header) != SRLA_APIRESULT_OK) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (decoder->config.max_num_channels < header->num_channels) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (decoder->config.max_num_parameters < kPresetMaxOrder[header->preset]) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (header->bits_per_sample != 8 && header->bits_per_sample != 16 && header->bits_per_sample != 24) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    decoder->header = *header;
+    decoder->set_header = 1;
+    return SRLA_APIRESULT_OK;
+}
+
+SRLAApiResult SRLADecoder_DecodeBlock(
+    struct SRLADecoder *decoder, const uint8_t *data, uint32_t data_size,
+    int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples, uint32_t *decode_size, uint32_t *num_decode_samples)
+{
+    if (decoder == NULL || data == NULL || buffer == NULL || decode_size == NULL || num_decode_samples == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (decoder->magic != kDecoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (!decoder->set_header) { return SRLA_APIRESULT_PARAMETER_NOT_SET; }
+    if (buffer_num_channels < decoder->header.num_channels) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    if (data_size < 11u) { return SRLA_APIRESULT_INSUFFICIENT_DATA; }
+    if (data[0] != 0xFF || data[1] != 0xFF) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    const uint32_t size = ((uint32_t)data[2] << 24) | ((uint32_t)data[3] << 16) | ((uint32_t)data[4] << 8) | data[5];
+    if ((uint64_t)size + 6u > data_size) { return SRLA_APIRESULT_INSUFFICIENT_DATA; }
+    const uint32_t n = ((uint32_t)data[9] << 8) | data[10];
+    std::vector<DecBlock> one(1);
+    one[0].offset = 0; one[0].bytes = size + 6u; one[0].sample_offset = 0; one[0].nsmpl = n; one[0].pad = 0;
+    if (size < 5u) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (n > buffer_num_samples) {
+        /* a bad checksum outranks the capacity error (srla_decoder.c:683-700) */
+        if (decoder->config.check_checksum == 1 && host::fletcher16(data + 8, size - 2u) != (uint16_t)(((uint32_t)data[6] << 8) | data[7])) { return SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+        return SRLA_APIRESULT_INSUFFICIENT_BUFFER;
+    }
+    const SRLAApiResult rc = decoder_run(decoder, data, size + 6u, one, buffer, n);
+    if (rc != SRLA_APIRESULT_OK) { return rc; }
+    *decode_size = size + 6u;
+    *num_decode_samples = n;
+    return SRLA_APIRESULT_OK;
+}
+
+SRLAApiResult SRLADecoder_DecodeWhole(
+    struct SRLADecoder *decoder, const uint8_t *data, uint32_t data_size,
+    int32_t **buffer, uint32_t buffer_num_channels, uint32_t buffer_num_samples)
+{
+    if (decoder == NULL || data == NULL || buffer == NULL) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (decoder->magic != kDecoderMagic) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    struct SRLAHeader h;
+    SRLAApiResult rc = SRLADecoder_DecodeHeader(data, data_size, &h);
+    if (rc != SRLA_APIRESULT_OK) { return rc; }
+    if ((rc = SRLADecoder_SetHeader(decoder, &h)) != SRLA_APIRESULT_OK) { return rc; }
+    if (buffer_num_channels < h.num_channels || buffer_num_samples < h.num_samples) { return SRLA_APIRESULT_INSUFFICIENT_BUFFER; }
+    /* host walk over the block headers (srla_decoder.c:768-795): the size fields chain the blocks */
+    std::vector<DecBlock> blocks;
+    uint32_t progress = 0; uint64_t at = SRLA_HEADER_SIZE;
+    SRLAApiResult walk = SRLA_APIRESULT_OK;
+    while (progress < h.num_samples && at < data_size) {
+        const uint64_t left = data_size - at;
+        if (left < 11u) { walk = SRLA_APIRESULT_INSUFFICIENT_DATA; break; }
+        const uint8_t *b = data + at;
+        if (b[0] != 0xFF || b[1] != 0xFF) { walk = SRLA_APIRESULT_INVALID_FORMAT; break; }
+        const uint32_t size = ((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5];
+        if ((uint64_t)size + 6u > left) { walk = SRLA_APIRESULT_INSUFFICIENT_DATA; break; }
+        if (size < 5u) { walk = SRLA_APIRESULT_INVALID_FORMAT; break; }
+        const uint32_t n = ((uint32_t)b[9] << 8) | b[10];
+        if (n > buffer_num_samples - progress) {
+            /* a bad checksum outranks the capacity error (srla_decoder.c:683-700) */
+            const bool corrupt = decoder->config.check_checksum == 1 && host::fletcher16(b + 8, size - 2u) != (uint16_t)(((uint32_t)b[6] << 8) | b[7]);
+            walk = corrupt ? SRLA_APIRESULT_DETECT_DATA_CORRUPTION : SRLA_APIRESULT_INSUFFICIENT_BUFFER;
+            break;
+        }
+        DecBlock blk; blk.offset = at; blk.bytes = size + 6u; blk.sample_offset = progress; blk.nsmpl = n; blk.pad = 0;
+        blocks.push_back(blk);
+        at += (uint64_t)size + 6u; progress += n;
+    }
+    rc = decoder_run(decoder, data, at, blocks, buffer, std::max(progress, 1u));
+    return (rc != SRLA_APIRESULT_OK) ? rc : walk;
+}
+
+float SRLAB200_DecoderKernelMs(const struct SRLADecoder *decoder)
+{
+    return (decoder && decoder->magic == kDecoderMagic) ? decoder->ctx->last_ms : -1.0f;
+}
+
+} /* extern "C" */
+
+#endif

@@ -120,8 +120,11 @@ static inline void build_rice_thresholds(double thr[32])
 /* static Huffman table: merge the two smallest live nodes under (count, index) order, smaller one
  * on the 0 branch, zero counts bumped to one; codes read root -> leaf. */
 struct HuffTable { uint32_t code[256]; uint8_t len[256]; };
+/* the same tree for decoding (static_huffman.c:145-162 walks it bit by bit): node >= 256 is internal,
+ * child[bit][node - 256] is where `bit` leads; leaves are the symbols */
+struct HuffTree { uint16_t child[2][256]; uint16_t root; };
 
-static inline void build_huffman(const uint32_t *counts, uint32_t nsym, HuffTable &t)
+static inline void build_huffman(const uint32_t *counts, uint32_t nsym, HuffTable &t, HuffTree *tree = nullptr)
 {
     std::vector<uint32_t> weight(2 * nsym + 1);
     std::vector<uint8_t> live(2 * nsym + 1, 0);
@@ -143,6 +146,11 @@ static inline void build_huffman(const uint32_t *counts, uint32_t nsym, HuffTabl
         child0[total] = (uint32_t)a; child1[total] = (uint32_t)b;
         total++;
     }
+    if (tree) {
+        std::memset(tree, 0, sizeof(*tree));
+        tree->root = (uint16_t)root;
+        for (uint32_t i = nsym; i < total; i++) { tree->child[0][i - nsym] = (uint16_t)child0[i]; tree->child[1][i - nsym] = (uint16_t)child1[i]; }
+    }
     /* iterative root -> leaf walk */
     struct Item { uint32_t node, code; uint8_t len; };
     std::vector<Item> stack;
@@ -155,12 +163,12 @@ static inline void build_huffman(const uint32_t *counts, uint32_t nsym, HuffTabl
     }
 }
 
-static inline void build_format_huffman(HuffTable &plain, HuffTable &summed)
+static inline void build_format_huffman(HuffTable &plain, HuffTable &summed, HuffTree *plain_tree = nullptr, HuffTree *summed_tree = nullptr)
 {
     static const uint32_t f_plain[256] = SRLA_FMT_COEF_SYMBOL_FREQ_INIT;
     static const uint32_t f_summed[256] = SRLA_FMT_SUMMED_COEF_SYMBOL_FREQ_INIT;
-    build_huffman(f_plain, 256, plain);
-    build_huffman(f_summed, 256, summed);
+    build_huffman(f_plain, 256, plain, plain_tree);
+    build_huffman(f_summed, 256, summed, summed_tree);
 }
 
 /* Fletcher-16 (srla_utility.c:36-60) */

@@ -1451,3 +1451,5 @@ SRLAApiResult SRLAB200_TestAnalyseChannel(
 }
 
 } /* extern "C" */
+
+#include "decoder.cuh"

@@ -85,6 +85,8 @@ EXPORTED_SYMBOLS = [
     "SRLAB200_EncodeStreamsDevice", "SRLAB200_EncodeStreamsHost", "SRLAB200_EncodeInterleavedHost",
     "SRLAB200_AllocPinned", "SRLAB200_FreePinned", "SRLAB200_MaxEncodedSize", "SRLAB200_GetStats",
     "SRLAB200_SetDevice", "SRLAB200_SetStream", "SRLAB200_Version", "SRLAB200_TestAnalyseChannel",
+    "SRLADecoder_DecodeHeader", "SRLADecoder_CalculateWorkSize", "SRLADecoder_Create", "SRLADecoder_Destroy",
+    "SRLADecoder_SetHeader", "SRLADecoder_DecodeBlock", "SRLADecoder_DecodeWhole", "SRLAB200_DecoderKernelMs",
 ]
 
 _lib: Optional[C.CDLL] = None

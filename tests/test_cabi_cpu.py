@@ -30,7 +30,7 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     header = open(os.path.join(ROOT, "include", "srla_b200.h")).read()
-    declared = set(re.findall(r"\b(SRLAEncoder_[A-Za-z]+|SRLAB200_[A-Za-z]+)\s*\(", header))
+    declared = set(re.findall(r"\b(SRLAEncoder_[A-Za-z]+|SRLADecoder_[A-Za-z]+|SRLAB200_[A-Za-z]+)\s*\(", header))
     declared.discard("SRLAEncoder_EncodeBlockCallback")
     assert declared == set(E.EXPORTED_SYMBOLS)
     for name in declared:
