@@ -40,14 +40,15 @@ struct DecParams {
     const uint16_t *tree;          /* [2 trees][2 bits][256] children, then the two roots               */
 };
 
-/* ---- big-endian bit reader over global memory: 64-bit window, aligned 32-bit refills, one word prefetched ---- */
+/* ---- big-endian bit reader over global memory: 64-bit window, aligned 32-bit refills, one word prefetched.
+ * After every operation more than 32 bits are valid, so any field of up to 32 bits and any code whose zero run,
+ * stop bit and remainder fit 33 bits is taken from the window without touching memory. ---- */
 struct DecBits {
     const uint32_t *word;          /* next aligned word to fetch                                       */
     const uint32_t *limit;         /* first word past the block                                        */
     uint32_t ahead;                /* prefetched word (already byte-swapped)                           */
     unsigned long long win;        /* valid bits at the top                                            */
     int avail;
-    unsigned long long consumed;   /* bits taken so far                                                */
     __device__ __forceinline__ uint32_t fetch()
     {
         const uint32_t v = (word < limit) ? __ldg(word) : 0u;
@@ -64,9 +65,10 @@ struct DecBits {
         win <<= skip;
         avail = 32 - skip;
         ahead = fetch();
-        consumed = 0;
         refill();
     }
+    /* the reader ran past the end of the block (two words are always in flight): corrupt data */
+    __device__ __forceinline__ bool overrun() const { return word > limit + 3; }
     __device__ __forceinline__ void refill()
     {
         if (avail <= 32) { win |= (unsigned long long)ahead << (32 - avail); avail += 32; ahead = fetch(); }
@@ -75,26 +77,45 @@ struct DecBits {
     {
         if (n == 0u) { return 0u; }
         const uint32_t v = (uint32_t)(win >> (64 - n));
-        win <<= n; avail -= (int)n; consumed += n;
+        win <<= n; avail -= (int)n;
         refill();
         return v;
     }
-    __device__ __forceinline__ uint32_t zero_run(unsigned long long max_bits)      /* zeros up to and including the closing 1 */
+    __device__ __forceinline__ uint32_t zero_run()                    /* zeros up to and including the closing 1 */
     {
         uint32_t run = 0;
         for (;;) {
-            const int z = win ? __clzll((long long)win) : 64;
-            if (z < avail) { win <<= (z + 1); avail -= z + 1; consumed += (unsigned)(z + 1); refill(); return run + (uint32_t)z; }
-            run += (uint32_t)avail; consumed += (unsigned)avail;
+            const int z = __clzll((long long)win);                    /* 64 for an empty window */
+            if (z < avail) { win <<= (z + 1); avail -= z + 1; refill(); return run + (uint32_t)z; }
+            run += (uint32_t)avail;
             win = 0; avail = 0;
             refill();
-            if (consumed > max_bits) { return run; }                                /* ran off the block: corrupt data */
+            if (overrun()) { return run; }
         }
+    }
+    /* zero run followed by a remainder of `low_bits(run)` bits, in one go when both lie in the window */
+    template <typename Low>
+    __device__ __forceinline__ void run_and_bits(Low low_bits, uint32_t *run_out, uint32_t *bits_out)
+    {
+        const int z = __clzll((long long)win);
+        const uint32_t nb = low_bits((uint32_t)z);
+        if (z + 1 + (int)nb <= avail && nb > 0u) {
+            const unsigned long long rest = win << (z + 1);
+            *run_out = (uint32_t)z;
+            *bits_out = (uint32_t)(rest >> (64 - nb));
+            win = rest << nb; avail -= z + 1 + (int)nb;
+            refill();
+            return;
+        }
+        const uint32_t run = zero_run();
+        *run_out = run;
+        *bits_out = get(low_bits(run));
     }
 };
 
 __device__ __forceinline__ int32_t dec_zigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
 
+constexpr int kDecStage = 128;               /* samples a warp stages in shared memory for the de-emphasis chain */
 constexpr int kDecMaxTaps = 8;                 /* accumulators per lane: 8 x 32 >= order 255 */
 
 struct DecChannel {
@@ -115,9 +136,11 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
     #pragma unroll
     for (int t = 0; t < T; ++t) { acc[t] = 0u; }
     uint32_t xprev = 0u, mine = 0u;
+    uint32_t next_res = (lane < n) ? (uint32_t)x[lane] : 0u;
     for (uint32_t base = 0; base < n; base += 32u) {
         const uint32_t own = base + lane;
-        const uint32_t res = (own < n) ? (uint32_t)x[own] : 0u;                     /* this lane's output of the round */
+        const uint32_t res = next_res;                                              /* this lane's output of the round */
+        next_res = (own + 32u < n) ? (uint32_t)x[own + 32u] : 0u;                   /* fetched a round ahead */
         const uint32_t steps = (n - base < 32u) ? n - base : 32u;
         for (uint32_t s = 0; s < steps; ++s) {
             const uint32_t q = base + s;
@@ -145,7 +168,9 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
 
 __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
 {
-    __shared__ DecChannel chan[kMaxChannels];
+    extern __shared__ __align__(16) unsigned char dec_smem[];
+    DecChannel *chan = reinterpret_cast<DecChannel *>(dec_smem);                       /* [channels] */
+    int32_t *stage = reinterpret_cast<int32_t *>(chan + p.nch);                        /* [channels][kDecStage] */
     __shared__ uint32_t sh_type, sh_n, sh_status, sh_method;
     __shared__ uint32_t sh_sum[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -229,7 +254,6 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
     if (tid == 0u) {
         DecBits br;
         br.open(payload, payload + payload_bytes);
-        const unsigned long long max_bits = 8ull * payload_bytes;
         const uint16_t *tree0 = p.tree, *tree1 = p.tree + 512;
         const uint32_t root0 = p.tree[1024], root1 = p.tree[1025];
         uint32_t status = 0u;
@@ -247,13 +271,13 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
             for (uint32_t i = 0; i < c.order; ++i) {
                 const uint16_t *tree = (use_sum && i > 0u) ? tree1 : tree0;
                 uint32_t node = (use_sum && i > 0u) ? root1 : root0;
-                do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u && br.consumed <= max_bits);
+                do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u);
                 int32_t v = dec_zigzag(node & 255u);
                 if (use_sum && i > 0u) { v -= prev; }                                /* summed-neighbour table: coef[i] = code - coef[i-1] */
                 prev = v;
                 c.cp[c.order - i] = v;                                               /* coef[i] multiplies x[m - order + i] */
             }
-            if (br.consumed > max_bits) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+            if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
         }
         for (uint32_t ch = 0; ch < nch; ++ch) {
             DecChannel &c = chan[ch];
@@ -276,19 +300,23 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
             uint32_t k = 0;
             for (uint32_t part = 0; part < (1u << porder); ++part) {
                 if (part == 0u) { k = br.get(5); }
-                else { k = (uint32_t)((int32_t)k + dec_zigzag(br.zero_run(max_bits))); }
+                else { k = (uint32_t)((int32_t)k + dec_zigzag(br.zero_run())); }
                 if (k > 31u) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
                 int32_t *dst = x + (size_t)part * per;
                 if (code == (uint32_t)kCodeRice) {
-                    for (uint32_t i = 0; i < per; ++i) { const uint32_t quot = br.zero_run(max_bits); dst[i] = dec_zigzag((quot << k) + br.get(k)); }
+                    for (uint32_t i = 0; i < per; ++i) {
+                        uint32_t quot, low;
+                        br.run_and_bits([k](uint32_t) { return k; }, &quot, &low);
+                        dst[i] = dec_zigzag((quot << k) + low);
+                    }
                 } else {
                     for (uint32_t i = 0; i < per; ++i) {
-                        const uint32_t quot = br.zero_run(max_bits);
-                        const uint32_t low = br.get(k + (quot ? 0u : 1u));
+                        uint32_t quot, low;
+                        br.run_and_bits([k](uint32_t run) { return k + (run ? 0u : 1u); }, &quot, &low);
                         dst[i] = dec_zigzag(low | ((quot + (quot ? 1u : 0u)) << k));
                     }
                 }
-                if (br.consumed > max_bits) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+                if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
             }
             for (uint32_t i = per << porder; i < n; ++i) { x[i] = 0; }              /* never happens for streams the encoder writes */
         }
@@ -327,15 +355,23 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
                 __syncwarp();
             }
         }
-        if (lane == 0u) {
-            /* de-emphasis (srla_utility.c:361-378): x[0] += (head c) >> 4, x[i] += (x[i-1] c) >> 4 */
+        {
+            /* de-emphasis (srla_utility.c:361-378): x[0] += (head c) >> 4, x[i] += (x[i-1] c) >> 4 -- a serial chain.  The
+             * warp moves 128 samples at a time through shared memory (coalesced both ways); lane 0 runs the chain there. */
             const uint32_t pc = (uint32_t)c.pre_coef;
-            uint32_t prev = (uint32_t)x[0] + (uint32_t)((int32_t)((uint32_t)c.head * pc) >> 4);
-            x[0] = (int32_t)prev;
-            #pragma unroll 8
-            for (uint32_t i = 1; i < n; ++i) {
-                prev = (uint32_t)x[i] + (uint32_t)((int32_t)(prev * pc) >> 4);
-                x[i] = (int32_t)prev;
+            int32_t *st = stage + warp * kDecStage;
+            uint32_t prev = (uint32_t)c.head;
+            for (uint32_t i0 = 0; i0 < n; i0 += (uint32_t)kDecStage) {
+                const uint32_t len = min((uint32_t)kDecStage, n - i0);
+                for (uint32_t k = lane; k < len; k += 32u) { st[k] = x[i0 + k]; }
+                __syncwarp();
+                if (lane == 0u) {
+                    #pragma unroll 8
+                    for (uint32_t k = 0; k < len; ++k) { prev = (uint32_t)st[k] + (uint32_t)((int32_t)(prev * pc) >> 4); st[k] = (int32_t)prev; }
+                }
+                __syncwarp();
+                for (uint32_t k = lane; k < len; k += 32u) { x[i0 + k] = st[k]; }
+                __syncwarp();
             }
         }
     }
@@ -455,7 +491,7 @@ SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t d
     p.nch = nch; p.bps = d->header.bits_per_sample; p.lshift = d->header.offset_lshift; p.check = (d->config.check_checksum == 1) ? 1u : 0u;
     p.tree = (const uint16_t *)c->tree.p;
     cudaEventRecord(c->ev0, c->stream);
-    decode_blocks_kernel<<<(unsigned)nb, 32u * std::max(1u, nch), 0, c->stream>>>(p);
+    decode_blocks_kernel<<<(unsigned)nb, 32u * std::max(1u, nch), nch * (sizeof(DecChannel) + sizeof(int32_t) * kDecStage), c->stream>>>(p);
     cudaEventRecord(c->ev1, c->stream);
     if (cudaGetLastError() != cudaSuccess) { return SRLA_APIRESULT_NG; }
     if (cudaMemcpyAsync(c->h_status.p, c->status.p, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess

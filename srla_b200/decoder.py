@@ -79,10 +79,12 @@ class Decoder:
             raise SRLAError("SRLADecoder_DecodeHeader", rc)
         return h
 
-    def decode_whole(self, stream: bytes) -> np.ndarray:
-        """-> int32 [channels, samples]"""
+    def decode_whole(self, stream: bytes, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """-> int32 [channels, samples] (into `out` when given: a C-contiguous int32 array of that shape)"""
         h = self.decode_header(stream)
-        out = np.zeros((h.num_channels, h.num_samples), dtype=np.int32)
+        if out is None:
+            out = np.zeros((h.num_channels, h.num_samples), dtype=np.int32)
+        assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape == (h.num_channels, h.num_samples)
         rc = self.lib.SRLADecoder_DecodeWhole(self.handle, stream, len(stream), _rows(out), h.num_channels, h.num_samples)
         if rc != OK:
             raise SRLAError("SRLADecoder_DecodeWhole", rc)
