@@ -103,6 +103,44 @@ def test_no_cpu_fallback_without_a_device(lib):
     lib.SRLAEncoder_Destroy(None)
 
 
+def test_decoder_host_entry_points_match_the_reference(lib):
+    """SRLADecoder_DecodeHeader / CalculateWorkSize / Create argument handling (host only, no GPU needed)"""
+    from srla_b200 import decoder as D
+    D._bind(lib)
+    hdr = E.SRLAHeader(10, 18, 2, 123456, 44100, 24, 3, 8192, 5)
+    raw = (C.c_uint8 * 30)()
+    assert lib.SRLAEncoder_EncodeHeader(C.byref(hdr), raw, 30) == E.OK
+    data = bytes(raw)
+    back = E.SRLAHeader()
+    assert lib.SRLADecoder_DecodeHeader(data, 30, C.byref(back)) == E.OK
+    assert bytes(back)[:0] == b"" and [getattr(back, f) for f, _ in E.SRLAHeader._fields_] == [getattr(hdr, f) for f, _ in E.SRLAHeader._fields_]
+    assert lib.SRLADecoder_DecodeHeader(data, 29, C.byref(back)) == E.INSUFFICIENT_DATA
+    assert lib.SRLADecoder_DecodeHeader(b"X" + data[1:], 30, C.byref(back)) == E.INVALID_FORMAT
+    assert lib.SRLADecoder_DecodeHeader(None, 30, C.byref(back)) == E.INVALID_ARGUMENT
+    assert lib.SRLADecoder_CalculateWorkSize(None) == -1
+    assert lib.SRLADecoder_CalculateWorkSize(C.byref(D.SRLADecoderConfig(0, 255, 1))) == -1
+    assert lib.SRLADecoder_CalculateWorkSize(C.byref(D.SRLADecoderConfig(8, 255, 1))) > 0
+    if have_ref():
+        from helpers import SRLADecoderConfig as RefCfg, SRLAHeader as RefHdr
+        ref = ref_lib()
+        rb = RefHdr()
+        buf = np.frombuffer(data, dtype=np.uint8).copy()
+        assert ref.SRLADecoder_DecodeHeader(buf.ctypes.data, 30, C.byref(rb)) == E.OK
+        assert [getattr(rb, f) for f, _ in RefHdr._fields_] == [getattr(back, f) for f, _ in E.SRLAHeader._fields_]
+        assert ref.SRLADecoder_DecodeHeader(buf.ctypes.data, 29, C.byref(rb)) == E.INSUFFICIENT_DATA
+        assert ref.SRLADecoder_CalculateWorkSize(C.byref(RefCfg(0, 255, 1))) == -1
+    assert lib.SRLADecoder_SetHeader(None, C.byref(hdr)) == E.INVALID_ARGUMENT
+    size, n = C.c_uint32(0), C.c_uint32(0)
+    assert lib.SRLADecoder_DecodeBlock(None, data, 30, None, 2, 0, C.byref(size), C.byref(n)) == E.INVALID_ARGUMENT
+    assert lib.SRLADecoder_DecodeWhole(None, data, 30, None, 2, 0) == E.INVALID_ARGUMENT
+    lib.SRLADecoder_Destroy(None)
+    import torch
+    if not torch.cuda.is_available():
+        assert not lib.SRLADecoder_Create(C.byref(D.SRLADecoderConfig(8, 255, 1)), None, 0)       # no CPU fallback
+        with pytest.raises(RuntimeError):
+            D.Decoder()
+
+
 def test_batch_cli_options_follow_the_reference_cli(tmp_path):
     """srla_b200_batch takes the reference CLI's encode options with its range checks (srla_codec.c:311-403); on a
     box without a GPU it fails loudly instead of falling back"""
