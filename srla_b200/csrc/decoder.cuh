@@ -3,12 +3,14 @@
  * (include/srla_decoder.h:8-56) on the GPU.  Included by libsrla_b200.cu (one translation unit).
  *
  * A stream decodes block by block and nothing crosses a block boundary (srla_decoder.c:633-799), so
- * a whole stream is one launch: one CTA per block, one warp per channel.
- *   parse     the bitstream of a block is serial (the second channel starts where the first one's
- *             codes end), so lane 0 of warp 0 walks it: side information into shared memory, residual
- *             codes (srla_coder.c:596-690) straight into the output buffer.  Meanwhile the other lanes
- *             of warp 0 have summed the block's Fletcher-16 checksum (srla_utility.c:36-60).
- *   synthesis (srla_lpc_synthesize.c:238-262) is a recurrence over samples; warp w runs channel w as a
+ * a whole stream is two launches over all of its blocks.
+ *   parse     (decode_parse_kernel) the bitstream of a block is serial (the second channel starts where
+ *             the first one's codes end): one thread per block, a few blocks per warp, walks it -- side
+ *             information to a per-channel record, residual codes (srla_coder.c:596-690) straight into
+ *             the output buffer.
+ *   synthesis (decode_blocks_kernel) one CTA per block, one warp per channel.  Warp 0 sums the Fletcher-16
+ *             checksum (srla_utility.c:36-60) in parallel and judges the header.  LPC synthesis
+ *             (srla_lpc_synthesize.c:238-262) is a recurrence over samples; warp w runs channel w as a
  *             systolic filter: lane L owns the outputs m = L (mod 32) and keeps their partial sums, every
  *             finished sample is broadcast with one shuffle and each lane adds its tap's product -- one
  *             shuffle and one multiply-add on the dependent chain per sample instead of `order` of them.
@@ -38,7 +40,20 @@ struct DecParams {
     unsigned long long stride;
     uint32_t nch, bps, lshift, check;
     const uint16_t *tree;          /* [2 trees][2 bits][256] children, then the two roots               */
+    struct DecSide *side;          /* per block: what decode_parse_kernel found                        */
+    struct DecSideChannel *side_ch;/* per (block, channel)                                             */
+    uint32_t num_blocks, pad;
 };
+
+/* side information of one channel of one compressed block, as the bitstream carries it */
+struct DecSideChannel {
+    int32_t head, pre_coef;
+    uint32_t order, rshift;
+    uint32_t ltp_order, ltp_period;
+    int32_t ltp_coef[4];
+    int16_t coef[256];             /* coef[i] multiplies x[m - order + i] */
+};
+struct DecSide { uint32_t status, method; };
 
 /* ---- big-endian bit reader over global memory: 64-bit window, aligned 32-bit refills, one word prefetched.
  * After every operation more than 32 bits are valid, so any field of up to 32 bits and any code whose zero run,
@@ -166,6 +181,102 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
     __syncwarp();
 }
 
+/* The serial walk over a compressed block (srla_decoder.c:436-540, srla_coder.c:596-690): ONE THREAD per block, a
+ * few blocks per warp (the launch picks how many lanes of a warp work: more lanes share the instruction issue, fewer
+ * lanes mean more warps to hide latency with).  Side information goes to p.side / p.side_ch, residuals straight into
+ * the output buffer.  Header problems (sync, size, checksum, type) are judged by decode_blocks_kernel; blocks that
+ * are not well-formed compressed blocks are skipped here. */
+__global__ void __launch_bounds__(32) decode_parse_kernel(const DecParams p)
+{
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= p.num_blocks) { return; }
+    const DecBlock blk = p.blocks[bi];
+    const uint8_t *b = p.data + blk.offset;
+    const uint32_t nch = p.nch, n = blk.nsmpl;
+    DecSide sd; sd.status = 0u; sd.method = 0u;
+    const uint32_t size = ((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5];
+    const bool walk = b[0] == 0xFFu && b[1] == 0xFFu && size >= 5u && size + 6u <= blk.bytes && b[8] == (uint8_t)kBlockCompress
+                      && ((((uint32_t)b[9] << 8) | b[10]) == n) && n > 0u;
+    if (!walk) { p.side[bi] = sd; return; }
+    const uint8_t *payload = b + 11;
+    const uint32_t payload_bytes = blk.bytes - 11u;
+    int32_t *out = p.out + blk.sample_offset;
+    DecSideChannel *chan = p.side_ch + (size_t)bi * nch;
+    {
+        DecBits br;
+        br.open(payload, payload + payload_bytes);
+        const uint16_t *tree0 = p.tree, *tree1 = p.tree + 512;
+        const uint32_t root0 = p.tree[1024], root1 = p.tree[1025];
+        uint32_t status = 0u;
+        sd.method = br.get(2);
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            chan[ch].head = dec_zigzag(br.get(p.bps + 1u));
+            chan[ch].pre_coef = dec_zigzag(br.get(5));
+        }
+        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
+            DecSideChannel &c = chan[ch];
+            const uint32_t order = br.get(8);
+            c.order = order; c.rshift = br.get(4);
+            const uint32_t use_sum = br.get(1);
+            int32_t prev = 0;
+            for (uint32_t i = 0; i < order; ++i) {
+                const uint16_t *tree = (use_sum && i > 0u) ? tree1 : tree0;
+                uint32_t node = (use_sum && i > 0u) ? root1 : root0;
+                do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u);
+                int32_t v = dec_zigzag(node & 255u);
+                if (use_sum && i > 0u) { v -= prev; }                                /* summed-neighbour table: coef[i] = code - coef[i-1] */
+                prev = v;
+                c.coef[i] = (int16_t)v;
+            }
+            if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+        }
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            DecSideChannel &c = chan[ch];
+            uint32_t ltp_order = 0u, ltp_period = 0u;
+            if (br.get(1)) {
+                ltp_order = 2u * br.get(1) + 1u;
+                ltp_period = br.get(8) + (uint32_t)kLtpMinPeriod;
+                for (uint32_t i = 0; i < ltp_order; ++i) { c.ltp_coef[i] = dec_zigzag(br.get(6)); }
+            }
+            c.ltp_order = ltp_order; c.ltp_period = ltp_period;
+        }
+        /* residual codes (srla_coder.c:648-690) */
+        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
+            int32_t *x = out + (size_t)ch * p.stride;
+            const uint32_t code = br.get(2);
+            if (code == (uint32_t)kCodeAllZero) { for (uint32_t i = 0; i < n; ++i) { x[i] = 0; } continue; }
+            if (code > (uint32_t)kCodeAllZero) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+            const uint32_t porder = br.get(10);
+            if (porder > (uint32_t)kLog2MaxParts) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+            const uint32_t per = n >> porder;
+            uint32_t k = 0;
+            for (uint32_t part = 0; part < (1u << porder); ++part) {
+                if (part == 0u) { k = br.get(5); }
+                else { k = (uint32_t)((int32_t)k + dec_zigzag(br.zero_run())); }
+                if (k > 31u) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+                int32_t *dst = x + (size_t)part * per;
+                if (code == (uint32_t)kCodeRice) {
+                    for (uint32_t i = 0; i < per; ++i) {
+                        uint32_t quot, low;
+                        br.run_and_bits([k](uint32_t) { return k; }, &quot, &low);
+                        dst[i] = dec_zigzag((quot << k) + low);
+                    }
+                } else {
+                    for (uint32_t i = 0; i < per; ++i) {
+                        uint32_t quot, low;
+                        br.run_and_bits([k](uint32_t run) { return k + (run ? 0u : 1u); }, &quot, &low);
+                        dst[i] = dec_zigzag(low | ((quot + (quot ? 1u : 0u)) << k));
+                    }
+                }
+                if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
+            }
+            for (uint32_t i = per << porder; i < n; ++i) { x[i] = 0; }              /* never happens for streams the encoder writes */
+        }
+        sd.status = status;
+    }
+    p.side[bi] = sd;
+}
+
 __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
 {
     extern __shared__ __align__(16) unsigned char dec_smem[];
@@ -250,81 +361,26 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
         return;
     }
 
-    /* ---- compressed block: the serial walk (srla_decoder.c:436-540) ---- */
-    if (tid == 0u) {
-        DecBits br;
-        br.open(payload, payload + payload_bytes);
-        const uint16_t *tree0 = p.tree, *tree1 = p.tree + 512;
-        const uint32_t root0 = p.tree[1024], root1 = p.tree[1025];
-        uint32_t status = 0u;
-        sh_method = br.get(2);
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            chan[ch].head = dec_zigzag(br.get(p.bps + 1u));
-            chan[ch].pre_coef = dec_zigzag(br.get(5));
-        }
-        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
-            DecChannel &c = chan[ch];
-            c.order = br.get(8); c.rshift = br.get(4);
-            const uint32_t use_sum = br.get(1);
-            for (uint32_t d = 0; d < 32u * kDecMaxTaps + 4u; ++d) { c.cp[d] = 0; }
-            int32_t prev = 0;
-            for (uint32_t i = 0; i < c.order; ++i) {
-                const uint16_t *tree = (use_sum && i > 0u) ? tree1 : tree0;
-                uint32_t node = (use_sum && i > 0u) ? root1 : root0;
-                do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u);
-                int32_t v = dec_zigzag(node & 255u);
-                if (use_sum && i > 0u) { v -= prev; }                                /* summed-neighbour table: coef[i] = code - coef[i-1] */
-                prev = v;
-                c.cp[c.order - i] = v;                                               /* coef[i] multiplies x[m - order + i] */
-            }
-            if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
-        }
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            DecChannel &c = chan[ch];
-            c.ltp_period = 0; c.ltp_order = 0;
-            if (br.get(1)) {
-                c.ltp_order = 2u * br.get(1) + 1u;
-                c.ltp_period = br.get(8) + (uint32_t)kLtpMinPeriod;
-                for (uint32_t i = 0; i < c.ltp_order; ++i) { c.ltp_coef[i] = dec_zigzag(br.get(6)); }
+    /* ---- compressed block: decode_parse_kernel has walked the bitstream ---- */
+    {
+        const DecSide sd = p.side[blockIdx.x];
+        if (sd.status != 0u) { if (tid == 0u) { p.status[blockIdx.x] = sd.status; } return; }
+        if (tid == 0u) { sh_method = sd.method; }
+        if (warp < nch) {
+            const DecSideChannel &g = p.side_ch[(size_t)blockIdx.x * nch + warp];
+            DecChannel &c = chan[warp];
+            for (uint32_t d = lane; d < 32u * kDecMaxTaps + 4u; d += 32u) { c.cp[d] = 0; }
+            __syncwarp();
+            const uint32_t order = g.order;
+            for (uint32_t i = lane; i < order; i += 32u) { c.cp[order - i] = g.coef[i]; }
+            if (lane == 0u) {
+                c.head = g.head; c.pre_coef = g.pre_coef; c.order = order; c.rshift = g.rshift;
+                c.ltp_order = g.ltp_order; c.ltp_period = g.ltp_period;
+                for (int i = 0; i < 4; ++i) { c.ltp_coef[i] = g.ltp_coef[i]; }
             }
         }
-        /* residual codes (srla_coder.c:648-690) */
-        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
-            int32_t *x = out + (size_t)ch * p.stride;
-            const uint32_t code = br.get(2);
-            if (code == (uint32_t)kCodeAllZero) { for (uint32_t i = 0; i < n; ++i) { x[i] = 0; } continue; }
-            if (code > (uint32_t)kCodeAllZero) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-            const uint32_t porder = br.get(10);
-            if (porder > (uint32_t)kLog2MaxParts) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-            const uint32_t per = n >> porder;
-            uint32_t k = 0;
-            for (uint32_t part = 0; part < (1u << porder); ++part) {
-                if (part == 0u) { k = br.get(5); }
-                else { k = (uint32_t)((int32_t)k + dec_zigzag(br.zero_run())); }
-                if (k > 31u) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-                int32_t *dst = x + (size_t)part * per;
-                if (code == (uint32_t)kCodeRice) {
-                    for (uint32_t i = 0; i < per; ++i) {
-                        uint32_t quot, low;
-                        br.run_and_bits([k](uint32_t) { return k; }, &quot, &low);
-                        dst[i] = dec_zigzag((quot << k) + low);
-                    }
-                } else {
-                    for (uint32_t i = 0; i < per; ++i) {
-                        uint32_t quot, low;
-                        br.run_and_bits([k](uint32_t run) { return k + (run ? 0u : 1u); }, &quot, &low);
-                        dst[i] = dec_zigzag(low | ((quot + (quot ? 1u : 0u)) << k));
-                    }
-                }
-                if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-            }
-            for (uint32_t i = per << porder; i < n; ++i) { x[i] = 0; }              /* never happens for streams the encoder writes */
-        }
-        sh_status = status;
-        __threadfence_block();
     }
     __syncthreads();
-    if (sh_status != 0u) { if (tid == 0u) { p.status[blockIdx.x] = sh_status; } return; }
 
     /* ---- synthesis: warp w = channel w ---- */
     if (warp < nch && n > 0u) {
@@ -407,7 +463,8 @@ struct DecoderCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf data, out, blocks, status, tree;
+    DevBuf data, out, blocks, status, tree, side, side_ch;
+    int parse_lanes = 4;           /* SRLA_B200_DECODE_LANES: blocks walked per warp of decode_parse_kernel */
     PinBuf h_blocks, h_status;
     float last_ms = 0.f;
 };
@@ -438,6 +495,7 @@ bool decoder_ctx_init(DecoderCtx *c)
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev0));
     CU_TRY(cudaEventCreate(&c->ev1));
+    if (const char *e = std::getenv("SRLA_B200_DECODE_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) { c->parse_lanes = v; } }
     host::HuffTable plain, summed; host::HuffTree t0, t1;
     host::build_format_huffman(plain, summed, &t0, &t1);
     uint16_t tab[1026];
@@ -455,7 +513,7 @@ void decoder_ctx_destroy(DecoderCtx *c)
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->ev0) { cudaEventDestroy(c->ev0); }
     if (c->ev1) { cudaEventDestroy(c->ev1); }
-    DevBuf *bufs[] = { &c->data, &c->out, &c->blocks, &c->status, &c->tree };
+    DevBuf *bufs[] = { &c->data, &c->out, &c->blocks, &c->status, &c->tree, &c->side, &c->side_ch };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_blocks.release(); c->h_status.release();
 }
@@ -479,7 +537,7 @@ SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t d
     const size_t nb = blocks.size();
     if (nb == 0) { return SRLA_APIRESULT_OK; }
     if (!c->data.reserve(data_bytes + 16) || !c->out.reserve(sizeof(int32_t) * stride * nch) || !c->blocks.reserve(sizeof(DecBlock) * nb)
-        || !c->status.reserve(sizeof(uint32_t) * nb) || !c->h_blocks.reserve(sizeof(DecBlock) * nb) || !c->h_status.reserve(sizeof(uint32_t) * nb)) { return SRLA_APIRESULT_NG; }
+        || !c->status.reserve(sizeof(uint32_t) * nb) || !c->side.reserve(sizeof(DecSide) * nb) || !c->side_ch.reserve(sizeof(DecSideChannel) * nb * nch) || !c->h_blocks.reserve(sizeof(DecBlock) * nb) || !c->h_status.reserve(sizeof(uint32_t) * nb)) { return SRLA_APIRESULT_NG; }
     std::memcpy(c->h_blocks.p, blocks.data(), sizeof(DecBlock) * nb);
     if (cudaMemcpyAsync(c->blocks.p, c->h_blocks.p, sizeof(DecBlock) * nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
         || cudaMemcpyAsync(c->data.p, data, data_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
@@ -490,7 +548,9 @@ SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t d
     p.out = (int32_t *)c->out.p; p.stride = stride;
     p.nch = nch; p.bps = d->header.bits_per_sample; p.lshift = d->header.offset_lshift; p.check = (d->config.check_checksum == 1) ? 1u : 0u;
     p.tree = (const uint16_t *)c->tree.p;
+    p.side = (DecSide *)c->side.p; p.side_ch = (DecSideChannel *)c->side_ch.p; p.num_blocks = (uint32_t)nb; p.pad = 0;
     cudaEventRecord(c->ev0, c->stream);
+    decode_parse_kernel<<<(unsigned)((nb + c->parse_lanes - 1) / c->parse_lanes), c->parse_lanes, 0, c->stream>>>(p);
     decode_blocks_kernel<<<(unsigned)nb, 32u * std::max(1u, nch), nch * (sizeof(DecChannel) + sizeof(int32_t) * kDecStage), c->stream>>>(p);
     cudaEventRecord(c->ev1, c->stream);
     if (cudaGetLastError() != cudaSuccess) { return SRLA_APIRESULT_NG; }
