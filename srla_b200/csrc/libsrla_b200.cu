@@ -19,6 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <map>
 #include <new>
 #include <vector>
@@ -75,6 +78,49 @@ struct PinBuf {
     void release() { if (p) { cudaFreeHost(p); } p = nullptr; cap = 0; }
 };
 
+/* Host threads of a handle, created once and parked between calls: spawning sixteen threads per EncodeWhole call
+ * cost ~2 ms on the measured box, a quarter of the call. */
+struct WorkerPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable wake, idle;
+    std::function<void()> job;
+    unsigned long long epoch = 0;
+    int running = 0;
+    bool quit = false;
+    void ensure(int n)
+    {
+        while ((int)threads.size() < n) { threads.emplace_back([this] { loop(); }); }
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(m);
+                wake.wait(l, [&] { return quit || epoch != seen; });
+                if (quit) { return; }
+                seen = epoch; f = job;
+            }
+            f();
+            { std::lock_guard<std::mutex> l(m); if (--running == 0) { idle.notify_all(); } }
+        }
+    }
+    void start(std::function<void()> f)                       /* every thread runs f once */
+    {
+        { std::lock_guard<std::mutex> l(m); job = std::move(f); running = (int)threads.size(); ++epoch; }
+        wake.notify_all();
+    }
+    void wait() { std::unique_lock<std::mutex> l(m); idle.wait(l, [&] { return running == 0; }); }
+    ~WorkerPool()
+    {
+        { std::lock_guard<std::mutex> l(m); quit = true; }
+        wake.notify_all();
+        for (std::thread &t : threads) { if (t.joinable()) { t.join(); } }
+    }
+};
+
 constexpr int kMaxLanes = 4;
 constexpr size_t kMiscBytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t) + 4;   /* running[2], stats[263], pad to 8 */
 
@@ -104,6 +150,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> ev_scan;
     PinBuf h_jobs, h_small, h_jobout, h_result, h_mailbox, h_stage, h_stage_out;
     int feed_threads = 8;          /* SRLA_B200_FEED_THREADS */
+    std::unique_ptr<WorkerPool> pool;
     DevBuf snapshot;
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_grp, ev_d2h;
@@ -299,13 +346,15 @@ struct Feeder {
     const uint8_t *out_stage = nullptr; uint8_t *out_user = nullptr;
     std::atomic<unsigned long long> out_ready{0}, out_total{kUnknown}, out_next{0};
     std::atomic<int> abort{0};
-    std::vector<std::thread> team;
-    void start(size_t num_groups, int threads)
+    WorkerPool *pool = nullptr;
+    void start(size_t num_groups, int threads, WorkerPool *workers)
     {
         left.reset(new std::atomic<int>[num_groups]);
         for (size_t g = 0; g < num_groups; g++) { left[g].store(0); }
         for (const Chunk &ck : chunks) { left[ck.group].fetch_add(1); }
-        for (int t = 0; t < threads; t++) { team.emplace_back([this] { work(); }); }
+        pool = workers;
+        pool->ensure(threads);
+        pool->start([this] { work(); });
     }
     void work()
     {
@@ -336,7 +385,7 @@ struct Feeder {
         }
     }
     void wait_group(size_t g) { while (left[g].load(std::memory_order_acquire) > 0) { std::this_thread::yield(); } }
-    void join() { for (std::thread &t : team) { if (t.joinable()) { t.join(); } } }
+    void join() { if (pool) { pool->wait(); pool = nullptr; } }
     ~Feeder() { abort.store(1, std::memory_order_release); join(); }
 };
 
@@ -770,7 +819,8 @@ struct Runner {
                         }
                     }
                     if (c->h_stage_out.reserve(std::min<uint64_t>(cap, io->out_capacity))) { feeder.out_stage = (const uint8_t *)c->h_stage_out.p; feeder.out_user = io->out; }
-                    feeder.start(num_groups, c->feed_threads);
+                    if (!c->pool) { c->pool.reset(new WorkerPool()); }
+                    feeder.start(num_groups, c->feed_threads, c->pool.get());
                 } else {
                     cudaPointerAttributes attr;
                     if (cudaPointerGetAttributes(&attr, io->raw ? io->raw[0] : io->streams[0].ch[0]) != cudaSuccess || attr.type != cudaMemoryTypeHost) { copies_async = false; (void)cudaGetLastError(); }
