@@ -26,6 +26,10 @@
 #include <new>
 #include <vector>
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
+
 #include <cuda_runtime.h>
 
 #include "../../include/srla_b200.h"
@@ -333,6 +337,43 @@ struct HostIO {
  * the copy engine and the kernels work on the groups already staged: half the PCIe bytes, true asynchronous
  * copies, 2-byte kernel loads.  A sample outside the int16 range (a caller breaking the bits_per_sample
  * contract) is detected and the call falls back to the int32 layout. */
+/* int32 -> int16 with a range check; nonzero when a sample does not fit.  The AVX2 version writes with streaming
+ * stores (the staging buffer is only ever read by the copy engine) and packs with saturation: a chunk that saturates
+ * is reported and the whole call falls back to the int32 layout, so its staging bytes are never used. */
+static uint32_t narrow_scalar(const int32_t *src, int16_t *dst, uint32_t n)
+{
+    uint32_t bad = 0;
+    for (uint32_t k = 0; k < n; k++) { const int32_t v = src[k]; bad |= (uint32_t)(v + 32768) >> 16; dst[k] = (int16_t)v; }
+    return bad;
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static uint32_t narrow_avx2(const int32_t *src, int16_t *dst, uint32_t n)
+{
+    uint32_t i = 0, bad = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31u)) { const int32_t v = src[i]; bad |= (uint32_t)(v + 32768) >> 16; dst[i] = (int16_t)v; i++; }
+    __m256i acc = _mm256_setzero_si256();
+    const __m256i bias = _mm256_set1_epi32(32768);
+    for (; i + 16u <= n; i += 16u) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 8));
+        acc = _mm256_or_si256(acc, _mm256_or_si256(_mm256_srli_epi32(_mm256_add_epi32(a, bias), 16), _mm256_srli_epi32(_mm256_add_epi32(b, bias), 16)));
+        const __m256i packed = _mm256_permute4x64_epi64(_mm256_packs_epi32(a, b), 0xD8);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), packed);
+    }
+    _mm_sfence();
+    if (!_mm256_testz_si256(acc, acc)) { bad |= 1u; }
+    for (; i < n; i++) { const int32_t v = src[i]; bad |= (uint32_t)(v + 32768) >> 16; dst[i] = (int16_t)v; }
+    return bad;
+}
+static uint32_t narrow_chunk(const int32_t *src, int16_t *dst, uint32_t n)
+{
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    return have_avx2 ? narrow_avx2(src, dst, n) : narrow_scalar(src, dst, n);
+}
+#else
+static uint32_t narrow_chunk(const int32_t *src, int16_t *dst, uint32_t n) { return narrow_scalar(src, dst, n); }
+#endif
+
 struct Feeder {
     struct Chunk { const int32_t *src; int16_t *dst; uint32_t count; uint32_t group; };
     std::vector<Chunk> chunks;
@@ -362,13 +403,7 @@ struct Feeder {
             const size_t i = next.fetch_add(1);
             if (i >= chunks.size()) { break; }
             const Chunk &ck = chunks[i];
-            uint32_t bad = 0;
-            for (uint32_t k = 0; k < ck.count; k++) {
-                const int32_t v = ck.src[k];
-                bad |= (uint32_t)(v + 32768) >> 16;
-                ck.dst[k] = (int16_t)v;
-            }
-            if (bad) { overflow.store(1); }
+            if (narrow_chunk(ck.src, ck.dst, ck.count)) { overflow.store(1); }
             left[ck.group].fetch_sub(1, std::memory_order_release);
         }
         if (out_stage == nullptr) { return; }
@@ -384,7 +419,8 @@ struct Feeder {
             }
         }
     }
-    void wait_group(size_t g) { while (left[g].load(std::memory_order_acquire) > 0) { std::this_thread::yield(); } }
+    template <typename Poll>
+    void wait_group(size_t g, Poll poll) { while (left[g].load(std::memory_order_acquire) > 0) { poll(); std::this_thread::yield(); } }
     void join() { if (pool) { pool->wait(); pool = nullptr; } }
     ~Feeder() { abort.store(1, std::memory_order_release); join(); }
 };
@@ -779,8 +815,9 @@ struct Runner {
         std::vector<cudaEvent_t> &h2d_done = c->ev_h2d;
         Feeder feeder;
         /* copies group g's samples to the device (copy stream) and records h2d_done[g] */
+        std::function<void()> poll_d2h;                     /* set once the groups run: copies finished groups back while the host waits */
         auto issue_h2d = [&](size_t g) -> bool {
-            if (io->narrow) { feeder.wait_group(g); }
+            if (io->narrow) { feeder.wait_group(g, [&] { if (poll_d2h) { poll_d2h(); } }); }
             const size_t j0 = gstart[g], j1 = gstart[g + 1];
             size_t j = j0;
             while (j < j1) {                                   /* one contiguous sample range per stream touched */
@@ -914,6 +951,40 @@ struct Runner {
             if (!c->snapshot.reserve(sizeof(uint32_t) * (groups_now + 1) * pl.num_streams)) { return SRLA_APIRESULT_NG; }
             d_snap = (uint32_t *)c->snapshot.p;
         }
+        /* device -> host copies of finished groups, in order.  With the feeder the copies land in pinned staging and
+         * its threads move the bytes on to the caller's (pageable) buffer as they arrive; otherwise they go straight to
+         * the caller's buffer.  drain(false) is polled while the host queues groups or waits for the feeder, so a
+         * finished group's bytes leave as soon as they exist. */
+        bool host_overflow = false, drain_failed = false;
+        const bool staged = pipelined && io->narrow && feeder.out_stage != nullptr;
+        uint8_t *h_dst = pipelined ? (staged ? (uint8_t *)c->h_stage_out.p : io->out) : nullptr;
+        if (staged) { while (c->ev_d2h.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } c->ev_d2h.push_back(e); } }
+        std::vector<unsigned long long> gend(groups_now, 0);
+        size_t published = 0, drained = 0, recorded = 0;
+        unsigned long long prev = 0;
+        auto drain = [&](bool block) {
+            while (drained < recorded && !host_overflow && !drain_failed) {
+                if (block) {
+                    if (cudaEventSynchronize(grp_done[drained]) != cudaSuccess) { drain_failed = true; break; }
+                } else {
+                    const cudaError_t q = cudaEventQuery(grp_done[drained]);
+                    if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
+                    if (q != cudaSuccess) { drain_failed = true; break; }
+                }
+                const unsigned long long end = mailbox[drained];
+                if (end > io->out_capacity || end > cap) { host_overflow = true; break; }
+                if (end > prev && cudaMemcpyAsync(h_dst + prev, d_out + prev, end - prev, cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { drain_failed = true; break; }
+                prev = end; gend[drained] = end;
+                if (c->trace) { host_d2h.push_back(host_ms()); }
+                if (staged && cudaEventRecord(c->ev_d2h[drained], c->d2h_stream) != cudaSuccess) { drain_failed = true; break; }
+                drained++;
+            }
+            if (staged) {
+                while (published < drained && cudaEventQuery(c->ev_d2h[published]) == cudaSuccess) { feeder.out_ready.store(gend[published], std::memory_order_release); published++; }
+                (void)cudaGetLastError();                      /* cudaEventQuery's cudaErrorNotReady is not an error */
+            }
+        };
+        if (pipelined) { poll_d2h = [&] { drain(false); }; }
         const int lanes_now = pl.variable ? 1 : lanes;
         if (lanes_now > 1) {
             /* fork: the other lanes start after everything queued on the caller's stream so far (uploads, shift) */
@@ -938,6 +1009,7 @@ struct Runner {
                            (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr)) { return SRLA_APIRESULT_NG; }
             if (pipelined && cudaEventRecord(grp_done[g], on) != cudaSuccess) { return SRLA_APIRESULT_NG; }
             if (c->trace) { host_launch.push_back(host_ms()); }
+            if (pipelined) { recorded = g + 1; drain(false); }
             /* pageable source (the copy blocks the host) or feeder staging: the next group's copy follows this
              * group's launches, so the device works on group g while the host moves group g + 1 */
             if (pipelined && (!copies_async || io->narrow) && g + 1 < groups_now && !issue_h2d(g + 1)) { return SRLA_APIRESULT_NG; }
@@ -953,31 +1025,12 @@ struct Runner {
         }
         if (cudaEventRecord(c->ev_end, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
 
-        /* ---- pipelined device -> host copies of finished groups ---- */
-        bool host_overflow = false;
+        /* ---- the remaining device -> host copies ---- */
+        poll_d2h = nullptr;
         if (pipelined) {
-            /* with the feeder the copies land in pinned staging and its threads move the bytes on to the caller's
-             * (pageable) buffer as they arrive; otherwise they go straight to the caller's buffer */
-            const bool staged = io->narrow && feeder.out_stage != nullptr;
-            uint8_t *h_dst = staged ? (uint8_t *)c->h_stage_out.p : io->out;
-            if (staged) { while (c->ev_d2h.size() < groups_now) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } c->ev_d2h.push_back(e); } }
-            std::vector<unsigned long long> gend(groups_now, 0);
-            size_t published = 0;
-            unsigned long long prev = 0;
-            for (size_t g = 0; g < groups_now; g++) {
-                if (cudaEventSynchronize(grp_done[g]) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
-                const unsigned long long end = mailbox[g];
-                if (end > io->out_capacity || end > cap) { host_overflow = true; break; }
-                if (end > prev && cudaMemcpyAsync(h_dst + prev, d_out + prev, end - prev, cudaMemcpyDeviceToHost, c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-                prev = end; gend[g] = end;
-                if (c->trace) { host_d2h.push_back(host_ms()); }
-                if (staged) {
-                    if (cudaEventRecord(c->ev_d2h[g], c->d2h_stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-                    while (published <= g && cudaEventQuery(c->ev_d2h[published]) == cudaSuccess) { feeder.out_ready.store(gend[published], std::memory_order_release); published++; }
-                }
-            }
+            drain(true);
+            if (drain_failed) { std::fprintf(stderr, "[srla_b200] encode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
             if (staged) {
-                (void)cudaGetLastError();                      /* cudaEventQuery's cudaErrorNotReady is not an error */
                 if (host_overflow) { feeder.abort.store(1, std::memory_order_release); }
                 else {
                     for (; published < groups_now; published++) {
