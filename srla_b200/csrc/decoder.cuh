@@ -463,6 +463,16 @@ struct DecoderCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t lanes[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   /* a block's walk is ~2.5 ms of serial latency whatever the
+                                                       launch size: the groups of a pipelined call must run side by side */
+    cudaEvent_t ev_table = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k0, ev_k1, ev_out;      /* per group of a pipelined call */
+    PinBuf h_in, h_out;
+    std::unique_ptr<WorkerPool> pool;
+    int host_threads = 8;
+    int pipeline = -1;             /* SRLA_B200_DECODE_PIPELINE: 1 always, 0 never, default: from a handle's second long stream on */
+    int long_calls = 0;
     DevBuf data, out, blocks, status, tree, side, side_ch;
     int parse_lanes = 4;           /* SRLA_B200_DECODE_LANES: blocks walked per warp of decode_parse_kernel */
     PinBuf h_blocks, h_status;
@@ -495,6 +505,13 @@ bool decoder_ctx_init(DecoderCtx *c)
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev0));
     CU_TRY(cudaEventCreate(&c->ev1));
+    CU_TRY(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    for (cudaStream_t &l : c->lanes) { CU_TRY(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking)); }
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming));
+    { const unsigned hc = std::thread::hardware_concurrency(); c->host_threads = (int)std::max(2u, std::min(16u, hc ? hc : 8u)); }
+    if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->host_threads = v; } }
+    if (const char *e = std::getenv("SRLA_B200_DECODE_PIPELINE")) { c->pipeline = std::atoi(e) ? 1 : 0; }
     if (const char *e = std::getenv("SRLA_B200_DECODE_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) { c->parse_lanes = v; } }
     host::HuffTable plain, summed; host::HuffTree t0, t1;
     host::build_format_huffman(plain, summed, &t0, &t1);
@@ -513,6 +530,13 @@ void decoder_ctx_destroy(DecoderCtx *c)
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     if (c->ev0) { cudaEventDestroy(c->ev0); }
     if (c->ev1) { cudaEventDestroy(c->ev1); }
+    c->pool.reset();
+    if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
+    if (c->copy_out) { cudaStreamSynchronize(c->copy_out); cudaStreamDestroy(c->copy_out); }
+    for (cudaStream_t &l : c->lanes) { if (l) { cudaStreamSynchronize(l); cudaStreamDestroy(l); } }
+    if (c->ev_table) { cudaEventDestroy(c->ev_table); }
+    for (std::vector<cudaEvent_t> *v : { &c->ev_in, &c->ev_k0, &c->ev_k1, &c->ev_out }) { for (cudaEvent_t e : *v) { cudaEventDestroy(e); } }
+    c->h_in.release(); c->h_out.release();
     DevBuf *bufs[] = { &c->data, &c->out, &c->blocks, &c->status, &c->tree, &c->side, &c->side_ch };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_blocks.release(); c->h_status.release();
@@ -526,6 +550,148 @@ SRLAApiResult decoder_header_valid(const struct SRLAHeader *h)            /* srl
     return SRLA_APIRESULT_OK;
 }
 
+/* Long streams: the blocks are cut into groups whose stages overlap -- host threads stage the group's bytes in
+ * page-locked memory, the copy engine moves them in, the two kernels decode the group, the copy engine moves its
+ * samples out to page-locked memory and the host threads pass them on to the caller's (pageable) channel buffers.
+ * A group is only passed on once every block in it has decoded cleanly, so that -- like the reference, which stops
+ * at the first bad block (srla_decoder.c:780-786) -- nothing behind a bad block is delivered. */
+SRLAApiResult decoder_run_pipelined(struct SRLADecoder *d, const uint8_t *data, uint64_t data_bytes, const std::vector<DecBlock> &blocks,
+                                    int32_t **buffer, uint32_t total_samples)
+{
+    DecoderCtx *c = d->ctx;
+    const uint32_t nch = d->header.num_channels;
+    const uint64_t stride = round_up_u32(total_samples, 16);
+    const size_t nb = blocks.size();
+    const size_t G = std::min<size_t>(12, std::max<size_t>(2, nb / 128));
+    if (!c->data.reserve(data_bytes + 16) || !c->out.reserve(sizeof(int32_t) * stride * nch) || !c->blocks.reserve(sizeof(DecBlock) * nb)
+        || !c->status.reserve(sizeof(uint32_t) * nb) || !c->side.reserve(sizeof(DecSide) * nb) || !c->side_ch.reserve(sizeof(DecSideChannel) * nb * nch)
+        || !c->h_blocks.reserve(sizeof(DecBlock) * nb) || !c->h_status.reserve(sizeof(uint32_t) * nb)
+        || !c->h_in.reserve(data_bytes + 16) || !c->h_out.reserve(sizeof(int32_t) * stride * nch)) { return SRLA_APIRESULT_NG; }
+    for (std::vector<cudaEvent_t> *v : { &c->ev_in, &c->ev_out }) {
+        while (v->size() < G) { cudaEvent_t e; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { return SRLA_APIRESULT_NG; } v->push_back(e); }
+    }
+    for (std::vector<cudaEvent_t> *v : { &c->ev_k0, &c->ev_k1 }) {
+        while (v->size() < G) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) { return SRLA_APIRESULT_NG; } v->push_back(e); }
+    }
+    if (!c->pool) { c->pool.reset(new WorkerPool()); }
+    c->pool->ensure(c->host_threads);
+
+    /* group boundaries (blocks), their byte and sample ranges */
+    std::vector<size_t> gb(G + 1);
+    for (size_t g = 0; g <= G; g++) { gb[g] = nb * g / G; }
+    auto byte_begin = [&](size_t g) { return (uint64_t)blocks[gb[g]].offset; };
+    auto byte_end = [&](size_t g) { return (uint64_t)blocks[gb[g + 1] - 1].offset + blocks[gb[g + 1] - 1].bytes; };
+    auto smp_begin = [&](size_t g) { return blocks[gb[g]].sample_offset; };
+    auto smp_end = [&](size_t g) { return blocks[gb[g + 1] - 1].sample_offset + blocks[gb[g + 1] - 1].nsmpl; };
+
+    struct Item { void *dst; const void *src; size_t bytes; uint32_t group; };
+    std::vector<Item> in_items, out_items;
+    std::unique_ptr<std::atomic<int>[]> in_left(new std::atomic<int>[G]);
+    constexpr size_t kChunk = 1u << 20;
+    for (size_t g = 0; g < G; g++) {
+        in_left[g].store(0);
+        for (uint64_t at = byte_begin(g); at < byte_end(g); at += kChunk) {
+            in_items.push_back({ (uint8_t *)c->h_in.p + at, data + at, (size_t)std::min<uint64_t>(kChunk, byte_end(g) - at), (uint32_t)g });
+            in_left[g].fetch_add(1);
+        }
+        for (uint32_t ch = 0; ch < nch; ch++) {
+            for (uint64_t at = smp_begin(g); at < smp_end(g); at += kChunk / 4) {
+                const size_t cnt = (size_t)std::min<uint64_t>(kChunk / 4, smp_end(g) - at);
+                out_items.push_back({ buffer[ch] + at, (const int32_t *)c->h_out.p + stride * ch + at, cnt * sizeof(int32_t), (uint32_t)g });
+            }
+        }
+    }
+    std::atomic<size_t> in_next{0}, out_next{0}, out_ready{0}, out_limit{G};
+    c->pool->start([&] {
+        for (;;) {
+            const size_t i = in_next.fetch_add(1);
+            if (i >= in_items.size()) { break; }
+            std::memcpy(in_items[i].dst, in_items[i].src, in_items[i].bytes);
+            in_left[in_items[i].group].fetch_sub(1, std::memory_order_release);
+        }
+        for (;;) {
+            const size_t i = out_next.fetch_add(1);
+            if (i >= out_items.size()) { break; }
+            const Item &it = out_items[i];
+            for (;;) {
+                if (out_ready.load(std::memory_order_acquire) > it.group) { std::memcpy(it.dst, it.src, it.bytes); break; }
+                if (out_limit.load(std::memory_order_acquire) <= it.group) { break; }        /* behind a bad block: never delivered */
+                std::this_thread::yield();
+            }
+        }
+    });
+    struct Finish { WorkerPool *pool; std::atomic<size_t> *limit, *ready; ~Finish() { limit->store(ready->load()); pool->wait(); } } finish{ c->pool.get(), &out_limit, &out_ready };
+
+    std::memcpy(c->h_blocks.p, blocks.data(), sizeof(DecBlock) * nb);
+    if (cudaMemcpyAsync(c->blocks.p, c->h_blocks.p, sizeof(DecBlock) * nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
+        || cudaMemsetAsync((uint8_t *)c->data.p + data_bytes, 0, 16, c->stream) != cudaSuccess
+        || cudaMemsetAsync(c->status.p, 0xff, sizeof(uint32_t) * nb, c->stream) != cudaSuccess
+        || cudaEventRecord(c->ev_table, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    for (cudaStream_t l : c->lanes) { if (cudaStreamWaitEvent(l, c->ev_table, 0) != cudaSuccess) { return SRLA_APIRESULT_NG; } }
+    DecParams base;
+    base.data = (const uint8_t *)c->data.p; base.out = (int32_t *)c->out.p; base.stride = stride;
+    base.nch = nch; base.bps = d->header.bits_per_sample; base.lshift = d->header.offset_lshift; base.check = (d->config.check_checksum == 1) ? 1u : 0u;
+    base.tree = (const uint16_t *)c->tree.p; base.pad = 0;
+
+    /* passes finished groups on, in order; stops for good at the first group with a bad block */
+    size_t published = 0, issued = 0; bool failed = false; long bad_block = -1;
+    const uint32_t *st = (const uint32_t *)c->h_status.p;
+    auto publish = [&](bool block) {
+        while (published < issued && bad_block < 0 && !failed) {
+            if (block) { if (cudaEventSynchronize(c->ev_out[published]) != cudaSuccess) { failed = true; break; } }
+            else {
+                const cudaError_t q = cudaEventQuery(c->ev_out[published]);
+                if (q == cudaErrorNotReady) { (void)cudaGetLastError(); break; }
+                if (q != cudaSuccess) { failed = true; break; }
+            }
+            for (size_t i = gb[published]; i < gb[published + 1]; i++) { if (st[i] != 0u) { bad_block = (long)i; break; } }
+            if (bad_block >= 0) { out_limit.store(published, std::memory_order_release); break; }
+            published++;
+            out_ready.store(published, std::memory_order_release);
+        }
+    };
+    for (size_t g = 0; g < G; g++) {
+        while (in_left[g].load(std::memory_order_acquire) > 0) { publish(false); std::this_thread::yield(); }
+        const size_t b0 = gb[g], cnt = gb[g + 1] - gb[g];
+        if (cudaMemcpyAsync((uint8_t *)c->data.p + byte_begin(g), (const uint8_t *)c->h_in.p + byte_begin(g), byte_end(g) - byte_begin(g), cudaMemcpyHostToDevice, c->copy_in) != cudaSuccess
+            || cudaEventRecord(c->ev_in[g], c->copy_in) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        const cudaStream_t on = c->lanes[g % 6];
+        if (cudaStreamWaitEvent(on, c->ev_in[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        DecParams p = base;
+        p.blocks = (const DecBlock *)c->blocks.p + b0; p.status = (uint32_t *)c->status.p + b0;
+        p.side = (DecSide *)c->side.p + b0; p.side_ch = (DecSideChannel *)c->side_ch.p + b0 * nch; p.num_blocks = (uint32_t)cnt;
+        cudaEventRecord(c->ev_k0[g], on);
+        decode_parse_kernel<<<(unsigned)((cnt + c->parse_lanes - 1) / c->parse_lanes), c->parse_lanes, 0, on>>>(p);
+        decode_blocks_kernel<<<(unsigned)cnt, 32u * std::max(1u, nch), nch * (sizeof(DecChannel) + sizeof(int32_t) * kDecStage), on>>>(p);
+        cudaEventRecord(c->ev_k1[g], on);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamWaitEvent(c->copy_out, c->ev_k1[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        if (cudaMemcpyAsync((uint32_t *)c->h_status.p + b0, (const uint32_t *)c->status.p + b0, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, c->copy_out) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        for (uint32_t ch = 0; ch < nch; ch++) {
+            const size_t off = stride * ch + smp_begin(g);
+            if (cudaMemcpyAsync((int32_t *)c->h_out.p + off, (const int32_t *)c->out.p + off, sizeof(int32_t) * (smp_end(g) - smp_begin(g)), cudaMemcpyDeviceToHost, c->copy_out) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        }
+        if (cudaEventRecord(c->ev_out[g], c->copy_out) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        issued = g + 1;
+        publish(false);
+    }
+    publish(true);
+    bool lanes_ok = true;
+    for (cudaStream_t l : c->lanes) { lanes_ok = lanes_ok && cudaStreamSynchronize(l) == cudaSuccess; }
+    if (cudaStreamSynchronize(c->copy_out) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess || !lanes_ok || failed) {
+        std::fprintf(stderr, "[srla_b200] decode failed on the device: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return SRLA_APIRESULT_NG;
+    }
+    /* device time from the first group's kernels to the last group's (they overlap each other and the copies) */
+    c->last_ms = 0.f;
+    for (size_t g = 0; g < G; g++) { float t = 0.f; cudaEventElapsedTime(&t, c->ev_k0[0], c->ev_k1[g]); c->last_ms = std::max(c->last_ms, t); }
+    if (bad_block < 0) { return SRLA_APIRESULT_OK; }
+    /* the blocks of the bad block's group that precede it were decoded and are delivered like the reference does */
+    const uint32_t from = smp_begin(published), to = blocks[(size_t)bad_block].sample_offset;
+    for (uint32_t ch = 0; ch < nch && to > from; ch++) { std::memcpy(buffer[ch] + from, (const int32_t *)c->h_out.p + stride * ch + from, sizeof(int32_t) * (to - from)); }
+    const uint32_t code = st[bad_block];
+    return (code <= (uint32_t)SRLA_APIRESULT_NG) ? (SRLAApiResult)code : SRLA_APIRESULT_NG;
+}
+
 /* decode `blocks` (already walked) of the stream at `data` into the caller's channel pointers */
 SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t data_bytes, const std::vector<DecBlock> &blocks,
                           int32_t **buffer, uint32_t total_samples)
@@ -536,6 +702,12 @@ SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t d
     const uint64_t stride = round_up_u32(total_samples, 16);
     const size_t nb = blocks.size();
     if (nb == 0) { return SRLA_APIRESULT_OK; }
+    if (nb >= 256 && c->host_threads > 0) {
+        /* the pipelined path page-locks staging memory as large as the stream and its PCM (~0.7 ms per MB, once per
+         * handle): worth it for a handle that keeps decoding, not for a one-shot tool */
+        c->long_calls++;
+        if (c->pipeline == 1 || (c->pipeline < 0 && c->long_calls >= 2)) { return decoder_run_pipelined(d, data, data_bytes, blocks, buffer, total_samples); }
+    }
     if (!c->data.reserve(data_bytes + 16) || !c->out.reserve(sizeof(int32_t) * stride * nch) || !c->blocks.reserve(sizeof(DecBlock) * nb)
         || !c->status.reserve(sizeof(uint32_t) * nb) || !c->side.reserve(sizeof(DecSide) * nb) || !c->side_ch.reserve(sizeof(DecSideChannel) * nb * nch) || !c->h_blocks.reserve(sizeof(DecBlock) * nb) || !c->h_status.reserve(sizeof(uint32_t) * nb)) { return SRLA_APIRESULT_NG; }
     std::memcpy(c->h_blocks.p, blocks.data(), sizeof(DecBlock) * nb);

@@ -76,12 +76,28 @@ def test_decodes_reference_test_signals_shifted_and_variable_blocks():
             assert np.array_equal(dec.decode_whole(enc.encode_whole(pcm)), pcm)
 
 
-def test_many_blocks_one_launch_and_round_trip_with_our_encoder():
+def test_many_blocks_simple_and_pipelined_paths():
+    """640 blocks: the first long stream of a handle takes the simple path (one copy in, two launches, one copy out),
+    later ones the pipelined path (groups of blocks staged through page-locked memory by host threads); a bad block in
+    the middle stops the delivery where the reference stops it, on both paths"""
     pcm = np.concatenate([np.roll(synth_stereo(4096 * 40, seed=6), 31 * k, axis=1) for k in range(16)], axis=1)
     stream = E.encode(pcm, preset=4, max_block=4096)
+    n = pcm.shape[1]
+    at, starts = 30, []
+    while at < len(stream):
+        starts.append(at)
+        at += 6 + int.from_bytes(stream[at + 2:at + 6], "big")
+    bad = bytearray(stream); bad[starts[333] + 50] ^= 0x40; bad = bytes(bad)
     with D.Decoder() as dec:
-        got = dec.decode_whole(stream)
-    assert np.array_equal(got, pcm)
+        for round_ in range(3):                                   # round 0: simple path, then pipelined
+            assert np.array_equal(dec.decode_whole(stream), pcm), round_
+            rc, out = dec.decode_whole_rc(bad, 2, n)
+            assert rc == E.DATA_CORRUPTION, (round_, rc)
+            assert np.array_equal(out[:, :333 * 4096], pcm[:, :333 * 4096]), round_
+            assert not out[:, 334 * 4096:].any(), round_           # nothing behind the bad block is delivered
+    if have_ref():
+        rc, out = _ref_rc(bad, 2, n)
+        assert rc == E.DATA_CORRUPTION and np.array_equal(out[:, :333 * 4096], pcm[:, :333 * 4096]) and not out[:, 334 * 4096:].any()
 
 
 def test_malformed_streams_get_the_reference_result_codes():
