@@ -183,3 +183,14 @@ def test_reference_cli_with_encoder_and_decoder_from_libsrla_b200(tmp_path):
         with wave.open(str(back), "rb") as w:
             got = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").reshape(-1, 2).T
         assert np.array_equal(got, pcm)
+
+
+@pytest.mark.parametrize("name", __import__("helpers").golden_names())
+def test_decodes_the_committed_reference_streams(name):
+    """tests/golden/*.npz hold streams written by the REFERENCE encoder here (make_golden.py) next to their PCM: the GPU
+    decoder must return that PCM (no oracle/_ref needed on the GPU box)"""
+    from helpers import load_golden
+    pcm, _kw, srl = load_golden(name)
+    with D.Decoder() as dec:
+        got = dec.decode_whole(srl)
+    assert got.shape == pcm.shape and np.array_equal(got, pcm)
