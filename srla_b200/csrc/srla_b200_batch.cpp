@@ -210,6 +210,8 @@ int main(int argc, char **argv)
         if (!w.ok) { std::fprintf(stderr, "Failed to open %s. (%s)\n", w.path.c_str(), why.c_str()); failures++; }
     }
 
+    if (failures == (int)files.size()) { return 1; }          /* nothing to encode: do not even start the device */
+
     /* ---- one handle; files of equal (channels, bits, rate) are submitted together ---- */
     const auto t_begin = std::chrono::steady_clock::now();
     auto seconds_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };

@@ -164,6 +164,24 @@ def test_batch_cli_options_follow_the_reference_cli(tmp_path):
     bad = tmp_path / "float.wav"
     fmt = struct.pack("<HHIIHH", 3, 1, 48000, 192000, 4, 32)
     bad.write_bytes(b"RIFF" + struct.pack("<I", 36) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"data" + struct.pack("<I", 0))
+    # more header shapes the reference reader refuses (wav.c:150-166, 242-245): each is reported by name
+    def riff(chunks):
+        return b"RIFF" + struct.pack("<I", 4 + len(chunks)) + b"WAVE" + chunks
+    pcm16 = struct.pack("<HHIIHH", 1, 2, 44100, 176400, 4, 16)
+    shapes = {
+        "fmt18.wav": riff(b"fmt " + struct.pack("<I", 18) + pcm16 + b"\0\0" + b"data" + struct.pack("<I", 8) + bytes(8)),
+        "listfirst.wav": riff(b"LIST" + struct.pack("<I", 4) + b"INFO" + b"fmt " + struct.pack("<I", 16) + pcm16 + b"data" + struct.pack("<I", 8) + bytes(8)),
+        "bits32.wav": riff(b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 1, 2, 44100, 352800, 8, 32) + b"data" + struct.pack("<I", 16) + bytes(16)),
+        "nodata.wav": riff(b"fmt " + struct.pack("<I", 16) + pcm16),
+        "short.wav": riff(b"fmt " + struct.pack("<I", 16) + pcm16 + b"data" + struct.pack("<I", 4000) + bytes(8)),
+        "ch9.wav": riff(b"fmt " + struct.pack("<I", 16) + struct.pack("<HHIIHH", 1, 9, 44100, 793800, 18, 16) + b"data" + struct.pack("<I", 18) + bytes(18)),
+    }
+    for name, blob in shapes.items():
+        (tmp_path / name).write_bytes(blob)
+    r = run("-o", str(tmp_path / "none"), *[str(tmp_path / n) for n in shapes])
+    assert r.returncode == 1
+    for name in shapes:
+        assert f"Failed to open {tmp_path / name}" in r.stderr, (name, r.stderr)
     import torch
     if not torch.cuda.is_available():
         good = tmp_path / "ok.wav"
