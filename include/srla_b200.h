@@ -255,6 +255,10 @@ SRLAApiResult SRLAB200_SetStream(struct SRLAEncoder *encoder, void *cuda_stream)
 /* Library identification string ("srla_b200 <ver> sm_100a ..."). */
 const char *SRLAB200_Version(void);
 
+/* Host-only test hook: the int32 -> int16 narrowing the EncodeWhole feeder uses for <= 16-bit sources.
+ * Returns nonzero when a sample lies outside int16 (dst is then unspecified). */
+uint32_t SRLAB200_TestNarrow(const int32_t *src, int16_t *dst, uint32_t count);
+
 /* ---- stage-level entry point used by the parity tests (host buffers in/out, runs on the GPU) ---- */
 
 /* Analysis of one candidate channel (srla_encoder.c:966-1205) under the handle's current bit depth,

@@ -1507,6 +1507,14 @@ SRLAApiResult SRLAB200_SetStream(struct SRLAEncoder *encoder, void *cuda_stream)
     return SRLA_APIRESULT_OK;
 }
 
+/* host-only: the feeder's int32 -> int16 narrowing (AVX2 with streaming stores where available); nonzero when a
+ * sample does not fit.  Exported so the CPU test suite can check it without a device. */
+uint32_t SRLAB200_TestNarrow(const int32_t *src, int16_t *dst, uint32_t count)
+{
+    if (src == NULL || dst == NULL) { return 1u; }
+    return narrow_chunk(src, dst, count);
+}
+
 const char *SRLAB200_Version(void) { return "srla_b200 0.1 sm_100a (format 10 / codec 18)"; }
 
 SRLAApiResult SRLAB200_TestAnalyseChannel(

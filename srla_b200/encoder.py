@@ -87,6 +87,7 @@ EXPORTED_SYMBOLS = [
     "SRLAB200_SetDevice", "SRLAB200_SetStream", "SRLAB200_Version", "SRLAB200_TestAnalyseChannel",
     "SRLADecoder_DecodeHeader", "SRLADecoder_CalculateWorkSize", "SRLADecoder_Create", "SRLADecoder_Destroy",
     "SRLADecoder_SetHeader", "SRLADecoder_DecodeBlock", "SRLADecoder_DecodeWhole", "SRLAB200_DecoderKernelMs",
+    "SRLAB200_TestNarrow",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -132,6 +133,8 @@ def load_library() -> C.CDLL:
     lib.SRLAB200_AllocPinned.restype = C.c_void_p
     lib.SRLAB200_FreePinned.argtypes = [C.c_void_p]
     lib.SRLAB200_FreePinned.restype = None
+    lib.SRLAB200_TestNarrow.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.SRLAB200_TestNarrow.restype = C.c_uint32
     lib.SRLAB200_MaxEncodedSize.argtypes = [C.c_void_p, C.c_uint32]
     lib.SRLAB200_MaxEncodedSize.restype = C.c_uint64
     lib.SRLAB200_GetStats.argtypes = [C.c_void_p, C.POINTER(SRLAB200Stats)]

@@ -141,6 +141,26 @@ def test_decoder_host_entry_points_match_the_reference(lib):
             D.Decoder()
 
 
+def test_feeder_narrowing_on_the_host(lib):
+    """the int32 -> int16 narrowing of the EncodeWhole feeder (AVX2 + streaming stores on this CPU, scalar otherwise):
+    exact for every alignment and length, and every out-of-range sample is reported"""
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 15, 16, 17, 31, 33, 1000, 65536, 65537):
+        src = rng.integers(-32768, 32768, size=n + 1, dtype=np.int32)
+        for off in (0, 1, 3, 8, 15):
+            dst = np.full(n + off + 40, 77, dtype=np.int16)
+            assert lib.SRLAB200_TestNarrow(src.ctypes.data, dst[off:].ctypes.data, n) == 0
+            assert np.array_equal(dst[off:off + n], src[:n].astype(np.int16)) and dst[off + n] == 77 and (off == 0 or dst[off - 1] == 77)
+    src = rng.integers(-32768, 32768, size=4099, dtype=np.int32)
+    dst = np.zeros(4099, dtype=np.int16)
+    for pos in (0, 5, 16, 2048, 4095, 4098):
+        for bad in (32768, -32769, 1 << 20, -(1 << 31)):
+            keep = src[pos]; src[pos] = bad
+            assert lib.SRLAB200_TestNarrow(src.ctypes.data, dst.ctypes.data, 4099) != 0, (pos, bad)
+            src[pos] = keep
+    assert lib.SRLAB200_TestNarrow(src.ctypes.data, dst.ctypes.data, 4099) == 0
+
+
 def test_batch_cli_options_follow_the_reference_cli(tmp_path):
     """srla_b200_batch takes the reference CLI's encode options with its range checks (srla_codec.c:311-403); on a
     box without a GPU it fails loudly instead of falling back"""
