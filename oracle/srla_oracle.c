@@ -947,3 +947,185 @@ int so_encode_whole_flat(const so_params *p, const int32_t *pcm, uint32_t num_sa
     for (c = 0; c < p->num_channels; c++) { rows[c] = pcm + (size_t)c * num_samples; }
     return so_encode_whole(p, rows, num_samples, out, cap, size);
 }
+
+/* ================================================================================================
+ * Decoder restatement (srla_decoder.c:63-799, srla_coder.c:596-690, srla_lpc_synthesize.c:238-327,
+ * srla_utility.c:106-174, 361-378): checks the GPU decoder when oracle/_ref is not at hand.
+ * Decoding by code matching instead of a tree walk: the static Huffman codes are prefix free, so the
+ * first (code, length) that matches the next bits is the symbol the reference's tree walk ends at.
+ * ============================================================================================== */
+typedef struct { const uint8_t *mem; uint64_t bit, limit; int over; } bitsrc;
+
+static uint32_t get_bits(bitsrc *s, uint32_t nbits)
+{
+    uint32_t v = 0, i;
+    for (i = 0; i < nbits; i++) {
+        uint32_t b = 0;
+        if (s->bit < s->limit) { b = (s->mem[s->bit >> 3] >> (7u - (uint32_t)(s->bit & 7u))) & 1u; } else { s->over = 1; }
+        s->bit++;
+        v = (v << 1) | b;
+    }
+    return v;
+}
+static uint32_t get_zero_run(bitsrc *s) { uint32_t run = 0; while (!s->over && get_bits(s, 1) == 0u) { run++; } return run; }
+static int32_t unzigzag(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }            /* srla_utility.h:33 */
+
+static uint32_t huff_get(bitsrc *s, const huff_table *t)
+{
+    uint32_t code = 0, len, sym;
+    for (len = 1; len <= 32 && !s->over; len++) {
+        code = (code << 1) | get_bits(s, 1);
+        for (sym = 0; sym < 256; sym++) { if (t->len[sym] == len && t->code[sym] == code) { return sym; } }
+    }
+    s->over = 1;
+    return 0;
+}
+
+static void residual_decode(bitsrc *s, int32_t *x, uint32_t n)                                   /* srla_coder.c:648-690 */
+{
+    const uint32_t type = get_bits(s, 2);
+    uint32_t porder, per, part, k = 0, i;
+    if (type == 2u) { memset(x, 0, sizeof(int32_t) * n); return; }
+    if (type > 2u) { s->over = 1; return; }
+    porder = get_bits(s, 10);
+    if (porder > 10u) { s->over = 1; return; }
+    per = n >> porder;
+    for (part = 0; part < (1u << porder) && !s->over; part++) {
+        if (part == 0) { k = get_bits(s, 5); } else { k = (uint32_t)((int32_t)k + unzigzag(get_zero_run(s))); }
+        if (k > 31u) { s->over = 1; return; }
+        for (i = 0; i < per && !s->over; i++) {
+            const uint32_t quot = get_zero_run(s);
+            uint32_t u;
+            if (type == 0u) { u = (quot << k) + get_bits(s, k); }
+            else { u = get_bits(s, k + (quot ? 0u : 1u)); u |= (quot + (quot ? 1u : 0u)) << k; }
+            x[part * per + i] = unzigzag(u);
+        }
+    }
+}
+
+/* one block at data (size bytes available) -> pcm[ch][0..n); returns an SO_* code; *used, *n_out like the reference */
+static int decode_block(const so_params *p, int check, const uint8_t *data, uint64_t size, int32_t *const *pcm, uint32_t cap_samples,
+                        uint32_t *used, uint32_t *n_out)
+{
+    uint32_t bsize, n, type, ch, i;
+    const uint32_t nch = p->num_channels, bps = p->bits_per_sample;
+    if (size < 11u) { return SO_INSUFFICIENT_DATA; }
+    if (data[0] != 0xFF || data[1] != 0xFF) { return SO_INVALID_FORMAT; }
+    bsize = ((uint32_t)data[2] << 24) | ((uint32_t)data[3] << 16) | ((uint32_t)data[4] << 8) | data[5];
+    if ((uint64_t)bsize + 6u > size) { return SO_INSUFFICIENT_DATA; }
+    if (bsize < 5u) { return SO_INVALID_FORMAT; }
+    if (check && so_fletcher16(data + 8, bsize - 2u) != (uint16_t)(((uint32_t)data[6] << 8) | data[7])) { return SO_DATA_CORRUPTION; }
+    type = data[8];
+    n = ((uint32_t)data[9] << 8) | data[10];
+    if (n > cap_samples) { return SO_INSUFFICIENT_BUFFER; }
+    if (type == 2u) {                                                                             /* raw: srla_decoder.c:363-433 */
+        const uint32_t sb = bps / 8u;
+        const uint8_t *q = data + 11;
+        if ((uint64_t)bsize - 5u < ((uint64_t)bps * n * nch) / 8u) { return SO_INSUFFICIENT_DATA; }
+        for (i = 0; i < n; i++) { for (ch = 0; ch < nch; ch++) { uint32_t u = 0, b; for (b = 0; b < sb; b++) { u = (u << 8) | *q++; } pcm[ch][i] = unzigzag(u); } }
+    } else if (type == 1u) {
+        for (ch = 0; ch < nch; ch++) { memset(pcm[ch], 0, sizeof(int32_t) * n); }
+    } else if (type == 0u) {
+        bitsrc s; uint32_t method;
+        int32_t head[SO_MAX_CHANNELS], pre[SO_MAX_CHANNELS], coef[SO_MAX_CHANNELS][SO_MAX_ORDER + 1], ltp_coef[SO_MAX_CHANNELS][4];
+        uint32_t order[SO_MAX_CHANNELS], rshift[SO_MAX_CHANNELS], ltp_order[SO_MAX_CHANNELS], ltp_period[SO_MAX_CHANNELS];
+        s.mem = data + 11; s.bit = 0; s.limit = 8ull * (bsize - 5u); s.over = 0;
+        method = get_bits(&s, 2);
+        for (ch = 0; ch < nch; ch++) { head[ch] = unzigzag(get_bits(&s, bps + 1u)); pre[ch] = unzigzag(get_bits(&s, 5)); }
+        for (ch = 0; ch < nch; ch++) {
+            uint32_t use_sum;
+            order[ch] = get_bits(&s, 8); rshift[ch] = get_bits(&s, 4); use_sum = get_bits(&s, 1);
+            for (i = 0; i < order[ch]; i++) {
+                coef[ch][i] = unzigzag(huff_get(&s, format_huffman(use_sum && i > 0)));
+                if (use_sum && i > 0) { coef[ch][i] -= coef[ch][i - 1]; }
+            }
+        }
+        for (ch = 0; ch < nch; ch++) {
+            ltp_order[ch] = 0; ltp_period[ch] = 0;
+            if (get_bits(&s, 1)) {
+                ltp_order[ch] = 2u * get_bits(&s, 1) + 1u; ltp_period[ch] = get_bits(&s, 8) + 8u;
+                for (i = 0; i < ltp_order[ch]; i++) { ltp_coef[ch][i] = unzigzag(get_bits(&s, 6)); }
+            }
+        }
+        for (ch = 0; ch < nch && !s.over; ch++) { residual_decode(&s, pcm[ch], n); }
+        if (s.over) { return SO_DATA_CORRUPTION; }                      /* the reference has no such check: only reachable with the checksum test off */
+        for (ch = 0; ch < nch; ch++) {
+            int32_t *x = pcm[ch];
+            const uint32_t P = order[ch];
+            if (P > 0u) {                                                                         /* srla_lpc_synthesize.c:238-262 */
+                const int32_t half = (rshift[ch] > 0u) ? (int32_t)(1u << (rshift[ch] - 1u)) : (int32_t)0x80000000u;
+                for (i = 1; i < P && i < n; i++) { x[i] = wrap_add(x[i], x[i - 1]); }
+                for (i = 0; n > P && i < n - P; i++) {
+                    int32_t predict = half; uint32_t o;
+                    for (o = 0; o < P; o++) { predict = wrap_add(predict, wrap_mul(coef[ch][o], x[i + o])); }
+                    x[i + P] = wrap_sub(x[i + P], asr(predict, rshift[ch]));
+                }
+            }
+            if (ltp_order[ch] > 0u && ltp_period[ch] > 0u) {                                      /* srla_lpc_synthesize.c:264-327 */
+                const uint32_t h = ltp_order[ch] >> 1, T = ltp_period[ch];
+                for (i = T + h + 1u; i < n; i++) {
+                    int32_t predict = 16; uint32_t o;
+                    for (o = 0; o < ltp_order[ch]; o++) { predict = wrap_add(predict, wrap_mul(ltp_coef[ch][o], x[i - T - h + o])); }
+                    x[i] = wrap_add(x[i], asr(predict, 5));
+                }
+            }
+            x[0] = wrap_add(x[0], asr(wrap_mul(head[ch], pre[ch]), 4));                           /* srla_utility.c:361-378 */
+            for (i = 1; i < n; i++) { x[i] = wrap_add(x[i], asr(wrap_mul(x[i - 1], pre[ch]), 4)); }
+        }
+        if (nch >= 2u && method != 0u) {                                                          /* srla_utility.c:106-174 */
+            for (i = 0; i < n; i++) {
+                int32_t a = pcm[0][i], b = pcm[1][i];
+                if (method == 1u) { a = wrap_sub(a, asr(b, 1)); b = wrap_add(b, a); }
+                else if (method == 2u) { b = wrap_add(b, a); }
+                else { a = wrap_sub(b, a); }
+                pcm[0][i] = a; pcm[1][i] = b;
+            }
+        }
+        if (p->offset_lshift > 0u) { for (ch = 0; ch < nch; ch++) { for (i = 0; i < n; i++) { pcm[ch][i] = (int32_t)((uint32_t)pcm[ch][i] << p->offset_lshift); } } }
+    } else {
+        return SO_INVALID_FORMAT;
+    }
+    *used = bsize + 6u; *n_out = n;
+    return SO_OK;
+}
+
+int so_decode_header(const uint8_t *data, uint32_t size, so_params *p, uint32_t *num_samples)
+{
+    uint32_t fmt, codec;
+    if (!data || !p || !num_samples) { return SO_INVALID_ARGUMENT; }
+    if (size < 30u) { return SO_INSUFFICIENT_DATA; }
+    if (data[0] != '1' || data[1] != '2' || data[2] != '4' || data[3] != '9') { return SO_INVALID_FORMAT; }
+    fmt = ((uint32_t)data[4] << 24) | ((uint32_t)data[5] << 16) | ((uint32_t)data[6] << 8) | data[7];
+    codec = ((uint32_t)data[8] << 24) | ((uint32_t)data[9] << 16) | ((uint32_t)data[10] << 8) | data[11];
+    memset(p, 0, sizeof(*p));
+    p->num_channels = ((uint32_t)data[12] << 8) | data[13];
+    *num_samples = ((uint32_t)data[14] << 24) | ((uint32_t)data[15] << 16) | ((uint32_t)data[16] << 8) | data[17];
+    p->sampling_rate = ((uint32_t)data[18] << 24) | ((uint32_t)data[19] << 16) | ((uint32_t)data[20] << 8) | data[21];
+    p->bits_per_sample = ((uint32_t)data[22] << 8) | data[23];
+    p->offset_lshift = data[24];
+    p->max_block = ((uint32_t)data[25] << 24) | ((uint32_t)data[26] << 16) | ((uint32_t)data[27] << 8) | data[28];
+    p->min_block = p->max_block; p->lookahead = p->max_block;
+    p->preset = data[29];
+    /* srla_decoder.c:137-182 (checked by SetHeader there) */
+    if (fmt != 10u || codec != 18u || p->num_channels == 0 || *num_samples == 0 || p->sampling_rate == 0 || p->bits_per_sample == 0
+        || p->offset_lshift >= 32u || p->max_block == 0 || p->preset >= 7u || p->num_channels > SO_MAX_CHANNELS) { return SO_INVALID_FORMAT; }
+    return SO_OK;
+}
+
+/* header + every block (srla_decoder.c:740-799); pcm is [channels][capacity_samples] contiguous */
+int so_decode_whole_flat(const uint8_t *data, uint32_t size, int check_checksum, int32_t *pcm, uint32_t channels, uint32_t capacity_samples)
+{
+    so_params p; uint32_t total = 0, progress = 0, ch; uint64_t at = 30;
+    int32_t *rows[SO_MAX_CHANNELS];
+    int rc = so_decode_header(data, size, &p, &total);
+    if (rc != SO_OK) { return rc; }
+    if (channels < p.num_channels || capacity_samples < total) { return SO_INSUFFICIENT_BUFFER; }
+    while (progress < total && at < size) {
+        uint32_t used = 0, n = 0;
+        for (ch = 0; ch < p.num_channels; ch++) { rows[ch] = pcm + (size_t)ch * capacity_samples + progress; }
+        rc = decode_block(&p, check_checksum, data + at, size - at, rows, capacity_samples - progress, &used, &n);
+        if (rc != SO_OK) { return rc; }
+        at += used; progress += n;
+    }
+    return SO_OK;
+}

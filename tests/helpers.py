@@ -218,6 +218,8 @@ def oracle_lib() -> C.CDLL:
         lib.so_analyse_channel.argtypes = [C.POINTER(SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SoChannel)]
         lib.so_encode_whole_flat.argtypes = [C.POINTER(SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                              C.POINTER(C.c_uint32)]
+        lib.so_decode_header.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SoParams), C.POINTER(C.c_uint32)]
+        lib.so_decode_whole_flat.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
         _oracle = lib
     return _oracle
 
@@ -239,6 +241,26 @@ def oracle_encode(pcm, bps=16, rate=48000, max_block=4096, min_block=None, looka
     rc = lib.so_encode_whole_flat(C.byref(prm), pcm.ctypes.data, n, out.ctypes.data, cap, C.byref(size))
     assert rc == 0, f"so_encode_whole -> {rc}"
     return out[:size.value].tobytes()
+
+
+def oracle_decode_rc(stream: bytes, channels: int, samples: int, check: int = 1):
+    """the restatement's DecodeWhole: (result code, int32 [channels, samples])"""
+    lib = oracle_lib()
+    buf = np.frombuffer(stream, dtype=np.uint8).copy() if len(stream) else np.zeros(1, dtype=np.uint8)
+    out = np.zeros((max(channels, 1), max(samples, 1)), dtype=np.int32)
+    rc = lib.so_decode_whole_flat(buf.ctypes.data, len(stream), check, out.ctypes.data, channels, max(samples, 1) if samples else 0)
+    return rc, out
+
+
+def oracle_decode(stream: bytes) -> np.ndarray:
+    lib = oracle_lib()
+    buf = np.frombuffer(stream, dtype=np.uint8).copy()
+    prm, n = SoParams(), C.c_uint32(0)
+    rc = lib.so_decode_header(buf.ctypes.data, len(buf), C.byref(prm), C.byref(n))
+    assert rc == 0, f"so_decode_header -> {rc}"
+    rc, out = oracle_decode_rc(stream, prm.num_channels, n.value)
+    assert rc == 0, f"so_decode_whole -> {rc}"
+    return out
 
 
 def oracle_analyse(x: np.ndarray, bps=16, preset=4, ltp=0):
