@@ -1,11 +1,12 @@
 /*
- * srla_oracle.c -- CPU restatement of the SRLA encode path (format 10 / codec 18).
+ * srla_oracle.c -- CPU restatement of the SRLA encode path (format 10 / codec 18) and, at the end of the
+ * file, of the decoder (pinned by tests/test_oracle.py against the reference decoder and the committed streams).
  *
  * TEST INFRASTRUCTURE ONLY: the checker the CUDA path is compared with.  It is never the thing
  * shipped or measured (except as bench.py's "port" CPU baseline).  See srla_oracle.h.
  *
  * Written from the behaviour of the reference (paths relative to /root/reference); every stage
- * cites the file:line it follows.  Parity status: PINNED -- tests/test_oracle_vs_ref.py compares
+ * cites the file:line it follows.  Parity status: PINNED -- tests/test_oracle.py compares
  * whole .srl streams byte for byte with the compiled reference (oracle/_ref/libsrla_ref.so) and
  * with the committed reference-generated fixtures in tests/golden/.
  *
