@@ -615,6 +615,95 @@ static void rice_emit(bitsink *s, const int32_t *res, uint32_t n)
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * SVR coefficient refinement (lpc.c:988-1136; call site srla_encoder.c:1087-1101), used when
+ * so_set_svr_iterations() > 0: covariance of the un-windowed signal, ridge, Cholesky (lpc.c:573-631, with
+ * libm pow(s, -0.5) like the reference), then for six margins up to `iterations` re-weighted least-squares steps
+ * on the soft-thresholded residual; the coefficients of the smallest recursive-Rice length estimate win.
+ * ---------------------------------------------------------------------------------------------- */
+static uint32_t g_svr_iterations = 0;
+void so_set_svr_iterations(uint32_t iterations) { g_svr_iterations = iterations; }
+
+static double svr_objective(double mean_abs)                                       /* lpc.c:1020-1030, BITS_PER_SAMPLE 16 */
+{
+    const double intmean = mean_abs * (1 << 16);
+    const double rho = 1.0 / (1.0 + intmean);
+    const double l2 = log2_via_ln(log(0.5127629514) / log(1.0 - rho));
+    const uint32_t k2 = (uint32_t)((0 > l2) ? 0 : l2);
+    const uint32_t k1 = k2 + 1;
+    const double k1factor = pow(1.0 - rho, (double)(1 << k1));
+    const double k2factor = pow(1.0 - rho, (double)(1 << k2));
+    return (1.0 + k1) * (1.0 - k1factor) + (1.0 + k2 + (1.0 / (1.0 - k2factor))) * k1factor;
+}
+
+static void svr_refine(const double *data, uint32_t n, double *coef, uint32_t dim, uint32_t iterations)
+{
+    static const double margins[6] = { 0.0, 1.0 / 4096, 1.0 / 1024, 1.0 / 256, 1.0 / 64, 1.0 / 16 };   /* srla_internal.c:27 */
+    double *cov = (double *)calloc((size_t)dim * dim, sizeof(double));
+    double *resid = (double *)malloc(sizeof(double) * n);
+    double inv_diag[SO_MAX_ORDER], rvec[SO_MAX_ORDER], delta[SO_MAX_ORDER], init[SO_MAX_ORDER], best[SO_MAX_ORDER];
+    double min_obj = FLT_MAX;
+    uint32_t i, j, smpl, m, itr;
+    int k, singular = 0;
+#define COV(a, b) cov[(size_t)(a) * dim + (b)]
+    for (smpl = 0; smpl < n - dim; smpl++) {
+        const double *pd = &data[smpl];
+        for (i = 0; i < dim; i++) { const double sv = pd[i]; for (j = i; j < dim; j++) { COV(i, j) += sv * pd[j]; } }
+    }
+    for (i = 0; i < dim; i++) { for (j = i + 1; j < dim; j++) { COV(j, i) = COV(i, j); } }
+    for (i = 0; i < dim; i++) { COV(i, i) *= (1.0 + RIDGE); }
+    for (i = 0; i < dim && !singular; i++) {                                        /* lpc.c:573-602 */
+        double sum = COV(i, i);
+        for (k = (int)i - 1; k >= 0; k--) { sum -= COV(i, k) * COV(i, k); }
+        if (sum <= 0.0) { singular = 1; break; }
+        inv_diag[i] = pow(sum, -0.5);
+        for (j = i + 1; j < dim; j++) {
+            sum = COV(i, j);
+            for (k = (int)i - 1; k >= 0; k--) { sum -= COV(i, k) * COV(j, k); }
+            COV(j, i) = sum * inv_diag[i];
+        }
+    }
+    if (singular) { for (i = 0; i < dim; i++) { coef[i] = 0.0; } free(cov); free(resid); return; }
+    memcpy(init, coef, sizeof(double) * dim);
+    memcpy(best, coef, sizeof(double) * dim);
+    for (m = 0; m < 6; m++) {
+        const double margin = margins[m];
+        double prev_obj = FLT_MAX;
+        memcpy(coef, init, sizeof(double) * dim);
+        for (itr = 0; itr < iterations; itr++) {
+            double mabse = 0.0, obj;
+            memcpy(resid, data, sizeof(double) * n);
+            for (i = 0; i < dim; i++) { rvec[i] = 0.0; }
+            for (smpl = dim; smpl < n; smpl++) {
+                double r;
+                for (i = 0; i < dim; i++) { resid[smpl] += coef[i] * data[smpl - i - 1]; }
+                r = resid[smpl];
+                mabse += (r > 0) ? r : -r;
+                { const double mag = ((r > 0) ? r : -r) - margin; resid[smpl] = ((r > 0) - (r < 0)) * ((mag > 0.0) ? mag : 0.0); }
+                for (i = 0; i < dim; i++) { rvec[i] += resid[smpl] * data[smpl - i - 1]; }
+            }
+            obj = svr_objective(mabse / n);
+            for (i = 0; i < dim; i++) {                                             /* lpc.c:605-631 */
+                double sum = rvec[i];
+                for (k = (int)i - 1; k >= 0; k--) { sum -= COV(i, k) * delta[k]; }
+                delta[i] = sum * inv_diag[i];
+            }
+            for (k = (int)dim - 1; k >= 0; k--) {
+                double sum = delta[k];
+                for (j = (uint32_t)k + 1; j < dim; j++) { sum -= COV(j, k) * delta[j]; }
+                delta[k] = sum * inv_diag[k];
+            }
+            if (obj < min_obj) { memcpy(best, coef, sizeof(double) * dim); min_obj = obj; }
+            if ((prev_obj < obj) || (fabs(prev_obj - obj) < 1e-8)) { break; }
+            for (i = 0; i < dim; i++) { coef[i] += delta[i]; }
+            prev_obj = obj;
+        }
+    }
+    memcpy(coef, best, sizeof(double) * dim);
+#undef COV
+    free(cov); free(resid);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * one candidate channel (srla_encoder.c:966-1205)
  * ---------------------------------------------------------------------------------------------- */
 int so_analyse_channel(const so_params *p, int32_t *sig, uint32_t n, int32_t *residual, so_channel *out)
@@ -653,6 +742,7 @@ int so_analyse_channel(const so_params *p, int32_t *sig, uint32_t n, int32_t *re
     if (order > 0) {
         int32_t q[SO_MAX_ORDER];
         memcpy(out->lpc_double, &rows[order - 1][1], sizeof(double) * order);
+        if (g_svr_iterations > 0) { svr_refine(xd, n, out->lpc_double, order, g_svr_iterations); }
         quantise_lpc(out->lpc_double, order, q, &rshift);
         for (i = 0; i < order; i++) { out->coef[i] = q[order - 1 - i]; }   /* FIR order (srla_encoder.c:1104-1108) */
         fir_residual(sig, n, out->coef, order, rshift, residual);

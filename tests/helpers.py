@@ -218,6 +218,8 @@ def oracle_lib() -> C.CDLL:
         lib.so_analyse_channel.argtypes = [C.POINTER(SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SoChannel)]
         lib.so_encode_whole_flat.argtypes = [C.POINTER(SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                              C.POINTER(C.c_uint32)]
+        lib.so_set_svr_iterations.argtypes = [C.c_uint32]
+        lib.so_set_svr_iterations.restype = None
         lib.so_decode_header.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SoParams), C.POINTER(C.c_uint32)]
         lib.so_decode_whole_flat.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
         _oracle = lib
@@ -230,15 +232,19 @@ def so_params(nch, bps=16, rate=48000, max_block=4096, min_block=None, lookahead
     return SoParams(nch, bps, rate, min_block, max_block, lookahead, ltp, preset, lshift)
 
 
-def oracle_encode(pcm, bps=16, rate=48000, max_block=4096, min_block=None, lookahead=None, ltp=0, preset=4) -> bytes:
+def oracle_encode(pcm, bps=16, rate=48000, max_block=4096, min_block=None, lookahead=None, ltp=0, preset=4, svr=0) -> bytes:
     lib = oracle_lib()
+    lib.so_set_svr_iterations(svr)
     pcm = np.ascontiguousarray(pcm, dtype=np.int32)
     nch, n = pcm.shape
     prm = so_params(nch, bps, rate, max_block, min_block, lookahead, ltp, preset)
     cap = 2 * (nch * n * 4) + 4096
     out = np.zeros(cap, dtype=np.uint8)
     size = C.c_uint32(0)
-    rc = lib.so_encode_whole_flat(C.byref(prm), pcm.ctypes.data, n, out.ctypes.data, cap, C.byref(size))
+    try:
+        rc = lib.so_encode_whole_flat(C.byref(prm), pcm.ctypes.data, n, out.ctypes.data, cap, C.byref(size))
+    finally:
+        lib.so_set_svr_iterations(0)
     assert rc == 0, f"so_encode_whole -> {rc}"
     return out[:size.value].tobytes()
 

@@ -436,33 +436,32 @@ def test_batch_cli_writes_what_the_reference_cli_writes(tmp_path):
 def test_svr_refinement_is_byte_identical_to_the_reference(preset, bits, ltp, svr):
     """LPC_CalculateCoefSVR (lpc.c:1036-1136) between order selection and quantisation: covariance, Cholesky,
     six margins x `svr` iterations -- the stream must equal the reference's for the same parameter"""
-    if not have_ref():
-        pytest.skip("oracle/_ref not present (the C restatement does not cover SVR)")
     pcm = synth_stereo(4096 * 3 + 1500, seed=40 + preset)
     if bits == 24:
         pcm = np.clip(pcm.astype(np.int64) * 180 + 3, -(1 << 23), (1 << 23) - 1).astype(np.int32)
     if bits == 8:
         pcm = (pcm >> 8).astype(np.int32)
     kw = dict(bps=bits, preset=preset, max_block=4096, ltp=ltp)
-    want = ref_encode(pcm, svr=svr, **kw)
+    reference = ref_encode if have_ref() else oracle_encode        # the restatement's SVR is pinned on these cases (tests/test_oracle.py)
+    want = reference(pcm, svr=svr, **kw)
     with E.Encoder(max_channels=2, max_block=4096) as enc:
         assert enc.set_parameter(2, bits, 48000, 4096, 4096, 4096, ltp, preset, svr) == E.OK
         got = enc.encode_whole(pcm)
     assert got == want, _first_diff(got, want)
-    assert np.array_equal(ref_decode(got), pcm)
+    if have_ref():
+        assert np.array_equal(ref_decode(got), pcm)
     if svr >= 3 and preset >= 3:
-        assert want != ref_encode(pcm, svr=0, **kw)          # the refinement did change the stream
+        assert want != reference(pcm, svr=0, **kw)           # the refinement did change the stream
 
 
 def test_svr_on_the_reference_test_signals():
     """silence (singular covariance -> zero coefficients), constants, impulses, noise, Nyquist"""
-    if not have_ref():
-        pytest.skip("oracle/_ref not present")
+    reference = ref_encode if have_ref() else oracle_encode
     sigs = reference_test_signals(n=4096 + 700, bps=16, nch=2, seed=5)
     with E.Encoder(max_channels=2, max_block=4096) as enc:
         assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 3, 3) == E.OK
         for name, pcm in sorted(sigs.items()):
             pcm = np.ascontiguousarray(pcm, dtype=np.int32)
-            want = ref_encode(pcm, preset=3, max_block=4096, svr=3)
+            want = reference(pcm, preset=3, max_block=4096, svr=3)
             got = enc.encode_whole(pcm)
             assert got == want, (name, _first_diff(got, want))

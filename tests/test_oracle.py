@@ -205,3 +205,29 @@ def test_oracle_round_trip(kw):
     pcm = np.stack([base, np.roll(base, 5) * 0.9]) * (1 << (bits - 1)) * 0.9
     pcm = pcm.astype(np.int32)
     assert np.array_equal(oracle_decode(oracle_encode(pcm, **kw)), pcm)
+
+
+@pytest.mark.parametrize("preset,bits,ltp,svr", [(4, 16, 0, 1), (4, 16, 0, 3), (3, 16, 0, 8), (2, 24, 3, 2), (5, 16, 0, 2), (1, 8, 0, 4)])
+def test_oracle_svr_matches_reference(preset, bits, ltp, svr):
+    """the SVR coefficient refinement of the restatement (lpc.c:1036-1136) against the compiled reference"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not present")
+    pcm = synth_stereo(4096 * 2 + 1500, seed=40 + preset)
+    if bits == 24:
+        pcm = np.clip(pcm.astype(np.int64) * 180 + 3, -(1 << 23), (1 << 23) - 1).astype(np.int32)
+    if bits == 8:
+        pcm = (pcm >> 8).astype(np.int32)
+    kw = dict(bps=bits, preset=preset, max_block=4096, ltp=ltp, svr=svr)
+    got, want = oracle_encode(pcm, **kw), ref_encode(pcm, **kw)
+    assert got == want
+
+
+def test_oracle_svr_on_the_reference_test_signals():
+    """silence (singular covariance), constants, impulses, noise, Nyquist -- the cases the GPU test uses"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not present")
+    from helpers import reference_test_signals
+    for name, pcm in sorted(reference_test_signals(n=4096 + 700, bps=16, nch=2, seed=5).items()):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int32)
+        kw = dict(preset=3, max_block=4096, svr=3)
+        assert oracle_encode(pcm, **kw) == ref_encode(pcm, **kw), name
