@@ -10,17 +10,18 @@
  * whole .srl streams byte for byte with the compiled reference (oracle/_ref/libsrla_ref.so) and
  * with the committed reference-generated fixtures in tests/golden/.
  *
- * Known, documented deviations from the reference (all are "uninitialised / stale memory" corners
- * where the reference's own output depends on what earlier calls left in its scratch buffers):
- *  - odd block length: the reference's Welch window leaves the middle sample of its scratch buffer
- *    stale (lpc.c:260-264); here the middle sample is windowed like every other one.
- *  - LTP pitch search may read autocorrelation lags 263/264 that the reference never writes
- *    (lpc.c:1497-1513 with lag buffer from lpc.c:330-376); here they read as 0.0, which is what a
- *    handle created on zeroed memory (a fresh `srla` CLI process) sees.
- *  - LTP enabled and block length n with FFT size N = 2^ceil(log2 n) < 263: the reference copies
- *    lags N..262 from beyond the transformed region of its FFT buffer (lpc.c:371-373), i.e. stale
- *    data of the previous call; here those lags are 0.0.  Byte parity is only claimed for LTP
- *    blocks of at least 263 samples; shorter ones are covered by decoder round trips.
+ * Stale scratch memory.  Three corners of the reference read what EARLIER calls left in the LPC calculator's
+ * scratch (lpc.c:211-216 `buffer`, lpc.c:188 `auto_corr`), so its output there depends on the handle's history:
+ *  - odd block length: the Welch window never writes the middle sample of `buffer` (lpc.c:260-264); it keeps the
+ *    previous call's inverse-transform output at that index;
+ *  - LTP with an FFT size N < 263: lags N..262 are copied from beyond the transformed region (lpc.c:371-373);
+ *  - the LTP pitch search may read lags 263/264, which nothing ever writes (lpc.c:1497-1513).
+ * This restatement keeps the same persistent scratch (lpc_scratch below) and walks the calls in the reference's
+ * order, so it reproduces all three for a handle that starts from zeroed memory -- which is what a fresh `srla`
+ * CLI process has (its work area is one large malloc, i.e. fresh zero pages) and what so_encode_whole() models by
+ * resetting the scratch first.  so_reset_state() does the same for the single-block entry points.
+ * Not modelled: an SVR run (num_svr_filter_learning_iteration > 0) also parks its residual in `buffer`
+ * (lpc.c:1049), and a max block size below 263 with LTP lets the reference read past `buffer`.
  *
  * Floating point: compile with -ffp-contract=off (oracle/Makefile does); the reference is built as
  * ISO C90, i.e. without FMA contraction, and byte-identical output needs the same roundings.
@@ -269,20 +270,37 @@ void so_real_fft(int n, int flag, double *x)
  *   r[k] = (2/n) * IFFT(|FFT(xw, zero padded to N)|^2)[k],  N = next power of two >= n
  * which is (N/n) x the circular autocorrelation over N (no padding when n is a power of two).
  * ---------------------------------------------------------------------------------------------- */
+/* the reference calculator's persistent scratch: `buffer` (lpc.c:211-213) survives from call to call */
+static struct { double *buffer; uint32_t cap; } lpc_scratch;
+static double *lpc_scratch_reserve(uint32_t want)
+{
+    if (want > lpc_scratch.cap) {
+        uint32_t cap = lpc_scratch.cap ? lpc_scratch.cap : 1024u;
+        double *grown;
+        while (cap < want) { cap <<= 1; }
+        grown = (double *)calloc((size_t)cap, sizeof(double));       /* memory the reference never touched reads as zero */
+        if (lpc_scratch.buffer) { memcpy(grown, lpc_scratch.buffer, sizeof(double) * lpc_scratch.cap); free(lpc_scratch.buffer); }
+        lpc_scratch.buffer = grown; lpc_scratch.cap = cap;
+    }
+    return lpc_scratch.buffer;
+}
+void so_reset_state(void) { if (lpc_scratch.buffer) { memset(lpc_scratch.buffer, 0, sizeof(double) * lpc_scratch.cap); } }
+
 static void welch_autocorr(const double *x, uint32_t n, double *r, uint32_t nlags)
 {
     const uint32_t N = ceil_pow2(n);
-    double *buf = (double *)calloc((size_t)N + 2, sizeof(double));
+    double *buf = lpc_scratch_reserve(((N > nlags) ? N : nlags) + 2u);
     double *work = (double *)calloc((size_t)N + 2, sizeof(double));
     const double divisor = 4.0 * pow((double)(n - 1), -2.0);
     const double scale = 2.0 / n;
     uint32_t i;
+    /* lpc.c:260-264: both window halves, i < n / 2 -- for odd n the middle sample keeps what the previous call left */
     for (i = 0; i < (n >> 1); i++) {
         const double w = divisor * i * (n - 1 - i);
         buf[i] = x[i] * w;
         buf[n - 1 - i] = x[n - 1 - i] * w;
     }
-    if (n & 1u) { const uint32_t m = n >> 1; buf[m] = x[m] * (divisor * m * (n - 1 - m)); } /* documented deviation */
+    for (i = n; i < N; i++) { buf[i] = 0.0; }                                   /* lpc.c:349-351 */
     if (N >= 2) {
         real_fft_work((int)N, -1, buf, work);
         buf[0] *= buf[0];
@@ -290,8 +308,8 @@ static void welch_autocorr(const double *x, uint32_t n, double *r, uint32_t nlag
         for (i = 2; i < N; i += 2) { const double a = buf[i], b = buf[i + 1]; buf[i] = a * a + b * b; buf[i + 1] = 0.0; }
         real_fft_work((int)N, 1, buf, work);
     }
-    for (i = 0; i < nlags; i++) { r[i] = (i < N) ? buf[i] * scale : 0.0; }
-    free(buf); free(work);
+    for (i = 0; i < nlags; i++) { r[i] = buf[i] * scale; }                      /* lpc.c:371-373: also beyond N */
+    free(work);
 }
 
 void so_autocorr(const double *x, uint32_t n, double *r, uint32_t max_lag) { welch_autocorr(x, n, r, max_lag + 1); }
@@ -469,7 +487,8 @@ static int ltp_analyse(const double *xd, uint32_t n, uint32_t order, uint32_t *p
     uint32_t period = 0; int32_t i, j, k; const int32_t dim = (int32_t)order; const double *rhs;
     *period_out = 0;
     memset(r, 0, sizeof(r));
-    welch_autocorr(xd, n, r, LTP_MAX_PERIOD + 1);           /* lags 0..262; 263,264 read as 0 (see header) */
+    welch_autocorr(xd, n, r, LTP_MAX_PERIOD + 1);           /* lags 0..262 (beyond the FFT size: stale scratch); 263, 264 are
+                                                               never written by any call and read as 0 on a fresh handle */
     if (fabs(r[0]) <= FLT_MIN) { return SO_OK; }
     if (!detect_pitch(r, &period)) { return SO_OK; }
     if (period < order / 2 + 1) { return SO_OK; }
@@ -1001,6 +1020,7 @@ int so_encode_whole(const so_params *p_in, const int32_t *const *pcm, uint32_t n
     so_params p; uint32_t done = 0, at = FILE_HEADER_BYTES, c; int rc;
     if (!p_in || !pcm || !out || !size) { return SO_INVALID_ARGUMENT; }
     p = *p_in;
+    so_reset_state();                                           /* a fresh handle (the CLI creates one per file) */
     p.offset_lshift = so_offset_lshift(pcm, p.num_channels, num_samples);
     if ((rc = so_encode_header(&p, num_samples, out, cap)) != SO_OK) { return rc; }
     while (done < num_samples) {

@@ -20,6 +20,8 @@ from srla_b200.synth import synth_stereo  # noqa: E402
 
 
 def save(name, pcm, **kw):
+    if os.path.exists(os.path.join(HERE, name + ".npz")) and "--force" not in sys.argv:
+        return                                     # fixtures are deterministic; --force regenerates all of them
     pcm = np.ascontiguousarray(pcm, dtype=np.int32)
     srl = ref_encode(pcm, **kw)
     assert np.array_equal(ref_decode(srl), pcm), name
@@ -50,6 +52,19 @@ def main():
             save(f"refgen_{name}_ltp{ltp}", sig, preset=0, min_block=512, max_block=1024, lookahead=2048, ltp=ltp, rate=44100)
     for name, sig in reference_test_signals(n=4000, bps=24, nch=1, seed=3).items():
         save(f"refgen24_{name}", sig, bps=24, preset=4, max_block=1024, ltp=3, rate=44100)
+    # stale-scratch corners of the reference (lpc.c:260-264, 371-373): odd stream / tail lengths, where the Welch
+    # window's middle sample is what the previous call left behind, and LTP on a tail shorter than 263 samples
+    for n in (1, 3, 4095, 8969, 9001, 9193):
+        for ltp in (0, 3):
+            save(f"odd{n}_m4_b4096_ltp{ltp}", synth_stereo(n, seed=n), preset=4, max_block=4096, ltp=ltp)
+    save("odd7001_mono_m3_b2048", synth_stereo(7001, seed=71)[:1], preset=3, max_block=2048)
+    save("odd5001_three_ch_m2_b2048_ltp3", synth_stereo(5001, seed=72, channels=3), preset=2, max_block=2048, ltp=3)
+    save("odd16999_24bit_m4_b8192_ltp3", synth_stereo(16999, seed=73, bits=24), bps=24, preset=4, max_block=8192, ltp=3)
+    save("ltp_short_tail_4196_m4_b4096", synth_stereo(4196, seed=74), preset=4, max_block=4096, ltp=3)
+    save("ltp_short_tail_odd_8391_m4_b4096", synth_stereo(8391, seed=75), preset=4, max_block=4096, ltp=3)
+    save("odd9001_m4_v2_l4", synth_stereo(9001, seed=76), preset=4, max_block=4096, min_block=1024, lookahead=16384)
+    save("odd_after_silence_m4_b4096", np.concatenate([synth_stereo(4096, seed=77), np.zeros((2, 4096), dtype=np.int32),
+                                                       synth_stereo(1001, seed=78)], axis=1), preset=4, max_block=4096)
 
 
 if __name__ == "__main__":

@@ -111,6 +111,19 @@ def test_oracle_matches_reference_16bit(seed, kw):
 
 
 @needs_ref
+@pytest.mark.parametrize("kw", [dict(preset=4, max_block=4096), dict(preset=2, max_block=1024), dict(preset=4, max_block=4096, min_block=1024),
+                                dict(preset=4, max_block=4095), dict(preset=3, max_block=1001), dict(preset=4, max_block=3000, min_block=750)])
+@pytest.mark.parametrize("ltp", [0, 3])
+def test_oracle_reproduces_the_stale_scratch_corners(kw, ltp):
+    """odd block lengths keep the previous call's inverse transform in the Welch window's middle sample (lpc.c:260-264)
+    and LTP on blocks shorter than 263 samples copies lags from beyond the transform (lpc.c:371-373): the restatement
+    keeps the calculator's scratch from call to call like the reference does (a handle on zeroed memory = the CLI)"""
+    for n in (1, 3, 65, 67, 100, 263, 265, 511, 4095, 4097, 8969, 9001, 9193):
+        pcm = synth_stereo(n, seed=n)
+        assert oracle_encode(pcm, ltp=ltp, **kw) == ref_encode(pcm, ltp=ltp, **kw), n
+
+
+@needs_ref
 @pytest.mark.parametrize("bits,nch", [(8, 2), (24, 2), (24, 1), (16, 5)])
 def test_oracle_matches_reference_widths_and_channels(bits, nch):
     pcm = synth_stereo(20000, seed=40 + bits + nch, bits=bits, channels=nch)
