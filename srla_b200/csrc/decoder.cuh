@@ -64,6 +64,8 @@ struct DecBits {
     uint32_t ahead;                /* prefetched word (already byte-swapped)                           */
     unsigned long long win;        /* valid bits at the top                                            */
     int avail;
+    const uint32_t *base;          /* aligned word the block's first byte lies in                      */
+    int skip;                      /* bits of that word in front of the block                          */
     __device__ __forceinline__ uint32_t fetch()
     {
         const uint32_t v = (word < limit) ? __ldg(word) : 0u;
@@ -75,7 +77,8 @@ struct DecBits {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
         word = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         limit = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(end) + 3) & ~(uintptr_t)3);
-        const int skip = (int)(a & 3) * 8;
+        base = word;
+        skip = (int)(a & 3) * 8;
         win = (unsigned long long)fetch() << 32;
         win <<= skip;
         avail = 32 - skip;
@@ -84,6 +87,8 @@ struct DecBits {
     }
     /* the reader ran past the end of the block (two words are always in flight): corrupt data */
     __device__ __forceinline__ bool overrun() const { return word > limit + 3; }
+    /* bits taken from the block so far: everything fetched minus what still waits in the window and the prefetched word */
+    __device__ __forceinline__ long long consumed_bits() const { return (long long)(word - base) * 32 - 32 - avail - skip; }
     __device__ __forceinline__ void refill()
     {
         if (avail <= 32) { win |= (unsigned long long)ahead << (32 - avail); avail += 32; ahead = fetch(); }
@@ -272,6 +277,8 @@ __global__ void __launch_bounds__(32) decode_parse_kernel(const DecParams p)
             }
             for (uint32_t i = per << porder; i < n; ++i) { x[i] = 0; }              /* never happens for streams the encoder writes */
         }
+        /* exact bound: a walk that took more bits than the block holds read its neighbour's bytes (corrupt data) */
+        if (!status && br.consumed_bits() > (long long)payload_bytes * 8) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
         sd.status = status;
     }
     p.side[bi] = sd;
@@ -362,6 +369,12 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
     }
 
     /* ---- compressed block: decode_parse_kernel has walked the bitstream ---- */
+    if (n == 0u) {
+        /* a block that announces no samples (only a hostile or broken stream has one): decode_parse_kernel skips it and
+         * leaves its side records unwritten, so they must not be read; there is nothing to synthesise */
+        if (tid == 0u) { p.status[blockIdx.x] = SRLA_APIRESULT_INVALID_FORMAT; }
+        return;
+    }
     {
         const DecSide sd = p.side[blockIdx.x];
         if (sd.status != 0u) { if (tid == 0u) { p.status[blockIdx.x] = sd.status; } return; }
@@ -371,7 +384,7 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
             DecChannel &c = chan[warp];
             for (uint32_t d = lane; d < 32u * kDecMaxTaps + 4u; d += 32u) { c.cp[d] = 0; }
             __syncwarp();
-            const uint32_t order = g.order;
+            const uint32_t order = min(g.order, (uint32_t)kMaxOrder);      /* the order field is 8 bits; never index past cp[] */
             for (uint32_t i = lane; i < order; i += 32u) { c.cp[order - i] = g.coef[i]; }
             if (lane == 0u) {
                 c.head = g.head; c.pre_coef = g.pre_coef; c.order = order; c.rshift = g.rshift;
@@ -502,6 +515,7 @@ bool decoder_ctx_init(DecoderCtx *c)
     }
     if (g_device >= 0) { CU_TRY(cudaSetDevice(g_device)); }
     CU_TRY(cudaGetDevice(&c->device));
+    if (!device_is_sm100(c->device)) { return false; }
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev0));
     CU_TRY(cudaEventCreate(&c->ev1));
@@ -626,6 +640,8 @@ SRLAApiResult decoder_run_pipelined(struct SRLADecoder *d, const uint8_t *data, 
     if (cudaMemcpyAsync(c->blocks.p, c->h_blocks.p, sizeof(DecBlock) * nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
         || cudaMemsetAsync((uint8_t *)c->data.p + data_bytes, 0, 16, c->stream) != cudaSuccess
         || cudaMemsetAsync(c->status.p, 0xff, sizeof(uint32_t) * nb, c->stream) != cudaSuccess
+        || cudaMemsetAsync(c->side.p, 0, sizeof(DecSide) * nb, c->stream) != cudaSuccess
+        || cudaMemsetAsync(c->side_ch.p, 0, sizeof(DecSideChannel) * nb * nch, c->stream) != cudaSuccess
         || cudaEventRecord(c->ev_table, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
     for (cudaStream_t l : c->lanes) { if (cudaStreamWaitEvent(l, c->ev_table, 0) != cudaSuccess) { return SRLA_APIRESULT_NG; } }
     DecParams base;
@@ -714,7 +730,9 @@ SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t d
     if (cudaMemcpyAsync(c->blocks.p, c->h_blocks.p, sizeof(DecBlock) * nb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
         || cudaMemcpyAsync(c->data.p, data, data_bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
         || cudaMemsetAsync((uint8_t *)c->data.p + data_bytes, 0, 16, c->stream) != cudaSuccess
-        || cudaMemsetAsync(c->status.p, 0xff, sizeof(uint32_t) * nb, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+        || cudaMemsetAsync(c->status.p, 0xff, sizeof(uint32_t) * nb, c->stream) != cudaSuccess
+        || cudaMemsetAsync(c->side.p, 0, sizeof(DecSide) * nb, c->stream) != cudaSuccess
+        || cudaMemsetAsync(c->side_ch.p, 0, sizeof(DecSideChannel) * nb * nch, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
     DecParams p;
     p.data = (const uint8_t *)c->data.p; p.blocks = (const DecBlock *)c->blocks.p; p.status = (uint32_t *)c->status.p;
     p.out = (int32_t *)c->out.p; p.stride = stride;
@@ -829,7 +847,7 @@ SRLAApiResult SRLADecoder_DecodeBlock(
     const uint32_t n = ((uint32_t)data[9] << 8) | data[10];
     std::vector<DecBlock> one(1);
     one[0].offset = 0; one[0].bytes = size + 6u; one[0].sample_offset = 0; one[0].nsmpl = n; one[0].pad = 0;
-    if (size < 5u) { return SRLA_APIRESULT_INVALID_FORMAT; }
+    if (size < 5u || n == 0u) { return SRLA_APIRESULT_INVALID_FORMAT; }
     if (n > buffer_num_samples) {
         /* a bad checksum outranks the capacity error (srla_decoder.c:683-700) */
         if (decoder->config.check_checksum == 1 && host::fletcher16(data + 8, size - 2u) != (uint16_t)(((uint32_t)data[6] << 8) | data[7])) { return SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
@@ -866,6 +884,7 @@ SRLAApiResult SRLADecoder_DecodeWhole(
         if ((uint64_t)size + 6u > left) { walk = SRLA_APIRESULT_INSUFFICIENT_DATA; break; }
         if (size < 5u) { walk = SRLA_APIRESULT_INVALID_FORMAT; break; }
         const uint32_t n = ((uint32_t)b[9] << 8) | b[10];
+        if (n == 0u) { walk = SRLA_APIRESULT_INVALID_FORMAT; break; }       /* the reference's encoder never writes one; the loop would not advance */
         if (n > buffer_num_samples - progress) {
             /* a bad checksum outranks the capacity error (srla_decoder.c:683-700) */
             const bool corrupt = decoder->config.check_checksum == 1 && host::fletcher16(b + 8, size - 2u) != (uint16_t)(((uint32_t)b[6] << 8) | b[7]);
@@ -876,7 +895,8 @@ SRLAApiResult SRLADecoder_DecodeWhole(
         blocks.push_back(blk);
         at += (uint64_t)size + 6u; progress += n;
     }
-    rc = decoder_run(decoder, data, at, blocks, buffer, std::max(progress, 1u));
+    if (progress == 0u) { return walk; }                                   /* no block to decode: nothing is copied back */
+    rc = decoder_run(decoder, data, at, blocks, buffer, progress);
     return (rc != SRLA_APIRESULT_OK) ? rc : walk;
 }
 

@@ -257,9 +257,13 @@ __device__ __forceinline__ double int_to_double(int32_t x)
 /* Welch-windowed input of the autocorrelation (lpc.c:252-266, srla_encoder.c:1061-1064): complex element e of
  * the packed real transform = samples (2e, 2e+1), zero beyond n.  kPre: sig holds the UNFILTERED candidate
  * and the pre-emphasis (srla_utility.c:342-358, filter memory = first sample) is applied on the fly. */
-template <bool kPre>
+/* kChain (front_tail_kernel only): for an odd n the reference's window loop never writes the middle sample of its
+ * scratch buffer (lpc.c:260-264), which therefore still holds what the previous call's inverse transform left at that
+ * index: `stale` */
+template <bool kPre, bool kChain = false>
 struct WindowSource {
     const int32_t *sig; uint32_t n, half_n, pc; double unit, div, dn1;
+    double stale;
     bool full;                    /* n is the transform size: no zero padding, the window halves meet at n / 2 */
     /* element whose two samples are 2e, 2e+1 with window arguments ds0, ds0 + step (exact doubles supplied by the caller) */
     __device__ __forceinline__ double2 element_at(uint32_t e, double ds0, double step) const
@@ -279,6 +283,7 @@ struct WindowSource {
     __device__ __forceinline__ double one(uint32_t i, int32_t cur, int32_t prv) const
     {
         if (i >= n) { return 0.0; }
+        if (kChain && (n & 1u) && i == half_n) { return stale; }
         const int32_t x = kPre ? (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * pc) >> 4)) : cur;
         const uint32_t s = (i < half_n) ? i : (n - 1u - i);
         const double ds = int_to_double((int32_t)s);
@@ -306,9 +311,9 @@ struct WindowSource {
  * `need`: only outputs 0..need-1 of the whole transform are required (M = all); in the last pair pass an
  * output at position o is read later only when (o mod (16 << lgs)) < need, so butterflies that cannot
  * reach a required output are skipped -- the surviving outputs are the reference's expression trees. */
-template <bool kPre, bool kFromSamples>
+template <bool kPre, bool kFromSamples, bool kChain = false>
 __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs,
-                                           const double2 *tw_a, const double2 *tw_b, const uint32_t need, const WindowSource<kPre> src)
+                                           const double2 *tw_a, const double2 *tw_b, const uint32_t need, const WindowSource<kPre, kChain> src)
 {
     /* a real call, not inlined: each pass gets its own register allocation and the kernel one copy of it */
     const uint32_t tid = threadIdx.x;
@@ -470,9 +475,13 @@ __device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const u
  * sig[n] int32 in shared memory -> lags[0..nlags) (lags >= N read as 0.0).  buf: N doubles.
  * kPre: sig holds the UNFILTERED candidate and the pre-emphasis (srla_utility.c:342-358) is applied
  * on the fly with coefficient pre_coef. */
-template <bool kPre>
+/* kChain (front_tail_kernel): `pbuf` mirrors the reference calculator's persistent scratch buffer in natural order
+ * (lpc.c:211-213).  It supplies the stale middle sample of an odd-length window, receives the WHOLE inverse transform
+ * of this call (no pruning), and the lags are read from it -- also those beyond the transform size, which the
+ * reference copies from whatever earlier calls left there (lpc.c:371-373). */
+template <bool kPre, bool kChain = false>
 __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const uint32_t n, double *buf, double *lags, const uint32_t lag_step, const uint32_t nlags,
-                               const Job &job, const LaunchParams &p)
+                               const Job &job, const LaunchParams &p, double *pbuf = nullptr)
 {
     const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t N = ceil_pow2_u32(n);
@@ -492,12 +501,13 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
         return;
     }
     const uint32_t M = N >> 1;
-    WindowSource<kPre> ws;
+    WindowSource<kPre, kChain> ws;
+    ws.stale = kChain ? pbuf[n >> 1] : 0.0;
     /* unit = 2^-(bps-1) is a power of two: (x * unit) * w == x * (w * unit) exactly and w * unit == ((div * unit) * s) * (n-1-s)
      * exactly (no subnormals: |w| >= 4 / n^2 * 2^-23), so the scale rides on the divisor and costs no multiply per sample */
     ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = 1.0; ws.div = div * unit; ws.dn1 = (double)(int32_t)(n - 1u);
     ws.full = (n == N) && (N >= 32u);
-    const uint32_t want = (nlags < N) ? nlags : N;
+    const uint32_t want = kChain ? N : ((nlags < N) ? nlags : N);
     /* dir 0: forward transform of the windowed samples; dir 1: the inverse transform, evaluated as the
      * conjugate of a forward transform of conjugated data (see butterfly4) so both directions share one
      * copy of the pass code */
@@ -508,7 +518,7 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
         if (dir == 0) {
             if (M >= 16u) {
                 const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
-                fft_pair_pass<kPre, true>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, ws);   /* windows the samples itself */
+                fft_pair_pass<kPre, true, kChain>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, ws);   /* windows the samples itself */
                 nn >>= 4; lgs += 4;
             } else {
                 for (uint32_t c = tid; c < M; c += nthreads) { cx[fft_slot(c)] = ws.element(c); }
@@ -564,17 +574,23 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
         #pragma unroll 1
         while (nn >= 16u) {
             const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
-            fft_pair_pass<kPre, false>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, ws);
+            fft_pair_pass<kPre, false, kChain>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, ws);
             nn >>= 4; lgs += 4;
         }
         fft_tail_pass(cx, M, nn, p.tw_complex + p.tw_complex_off[3], p.tw_complex + p.tw_complex_off[2], need);
     }
     /* the buffer holds the conjugate of the reference's inverse transform: odd lags are -imag */
     const double scale = job.ac_scale;
-    for (uint32_t i = tid; i < nlags; i += nthreads) {
-        double v = 0.0;
-        if (i < N) { const double2 e = cx[fft_slot(i >> 1)]; v = ((i & 1u) ? -e.y : e.x) * scale; }
-        lags[(size_t)i * lag_step] = v;
+    if constexpr (kChain) {
+        for (uint32_t e = tid; e < M; e += nthreads) { const double2 v = cx[fft_slot(e)]; pbuf[2u * e] = v.x; pbuf[2u * e + 1u] = -v.y; }
+        __syncthreads();
+        for (uint32_t i = tid; i < nlags; i += nthreads) { lags[(size_t)i * lag_step] = pbuf[i] * scale; }
+    } else {
+        for (uint32_t i = tid; i < nlags; i += nthreads) {
+            double v = 0.0;
+            if (i < N) { const double2 e = cx[fft_slot(i >> 1)]; v = ((i & 1u) ? -e.y : e.x) * scale; }
+            lags[(size_t)i * lag_step] = v;
+        }
     }
     __syncthreads();
 }
@@ -925,6 +941,108 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
     if (sh_u[1]) { return; }
     if (sh_u[0] > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
     if (P > 0u) { welch_autocorr<false>(sig, 0, n, region_d, g, 32u, P + 1u, job, p); }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * front_tail_kernel: the reference's stale-scratch corners (lpc.c:260-264, 371-373), fixed blocks only.
+ * The reference's LPC calculator keeps ONE scratch buffer for all its calls.  For an odd block length the Welch window
+ * leaves the middle sample of that buffer as the previous call's inverse transform left it, and with LTP on a block whose
+ * transform is shorter than 263 points the lags beyond the transform are copied from it as well.  With fixed blocks only
+ * the last block of a stream can be that short or odd (the block size itself must be even and, with LTP, at least 263),
+ * so the chain of calls that matters is short: the last call of the latest analysed block in front of it (silent blocks
+ * make no call), then the calls of the tail block's own candidates in the reference's order M, S, channel 0, 1, ...
+ * (srla_encoder.c:1254-1273; two calls per candidate with LTP).  One CTA replays that chain for one tail job with `pbuf`
+ * standing in for the scratch buffer (zeroed first: a handle on fresh memory, like the `srla` CLI's) and overwrites what
+ * front_kernel wrote for the job's candidates.
+ * ---------------------------------------------------------------------------------------------- */
+struct TailJob { uint32_t job; uint32_t first_of_stream; };     /* indices into LaunchParams.jobs_all */
+
+template <int kT, bool kLtp>
+__device__ void front_chain_step(const LaunchParams &p, const Job &job, const StreamDev &st, const uint32_t cand, const uint32_t lshift,
+                                 const FrontLayout &L, unsigned char *smem, double *pbuf, CandOut *out, double *g, const uint32_t gstep,
+                                 unsigned long long *red64, int32_t *sh_i, uint32_t *sh_u)
+{
+    double   *region_d = reinterpret_cast<double *>(smem + L.region_off);
+    int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
+    int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + 4;
+    double   *lags     = reinterpret_cast<double *>(smem + L.lags_off);
+    const int tid = threadIdx.x;
+    const uint32_t n = job.nsmpl, P = p.max_order;
+    __syncthreads();
+    /* zero padding of the signal buffer the window pass may touch (a longer block was here before) */
+    for (uint32_t i = n + tid; i < round_up_u32(p.nmax, 4) + 12u; i += kT) { sig[i] = 0; }
+    int32_t *raw = kLtp ? region_i : sig;
+    int nz = load_candidate<8>(st, job, p, cand, lshift, raw);
+    nz = __syncthreads_or(nz);
+    if (tid == 0) {
+        out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
+        out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
+        out->total_bits = 0; out->residual_bits = 0; out->pre_coef = 0; out->pre_prev = 0;
+    }
+    const int32_t pre_coef = preemphasis_coefficient<kT>(raw, n, out, red64, &sh_i[0]);
+    if (!kLtp) {
+        if (P > 0u) { welch_autocorr<true, true>(raw, pre_coef, n, region_d, g, gstep, P + 1u, job, p, pbuf); }
+        return;
+    }
+    apply_preemphasis(region_i, sig, n, pre_coef);
+    __syncthreads();
+    welch_autocorr<false, true>(sig, 0, n, region_d, lags, 1u, kLtpMaxPeriod + 1u, job, p, pbuf);
+    if (tid == 0) {
+        for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }      /* never written by any call */
+        uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
+        const int rc = ltp_solve(lags, p.ltp_order, &period, q);
+        sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
+        out->status = (uint32_t)rc;
+        if (!rc && period > 0u) { out->ltp_period = period; out->ltp_coef[0] = q[0]; out->ltp_coef[1] = q[1]; out->ltp_coef[2] = q[2]; }
+    }
+    __syncthreads();
+    if (sh_u[1]) { return; }
+    if (sh_u[0] > 0u) { apply_ltp(sig, region_i, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
+    if (P > 0u) { welch_autocorr<false, true>(sig, 0, n, region_d, g, gstep, P + 1u, job, p, pbuf); }
+}
+
+template <int kT, bool kLtp>
+__global__ void __launch_bounds__(kT) front_tail_kernel(const __grid_constant__ LaunchParams p, const TailJob *tails, const Job *jobs_all,
+                                                        const uint32_t group_first, const uint32_t pbuf_len)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const FrontLayout L = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
+    double *pbuf = reinterpret_cast<double *>(smem + L.total);
+    __shared__ unsigned long long red64[2 * (kT / 32)];
+    __shared__ int32_t  sh_i[8];
+    __shared__ uint32_t sh_u[8];
+    __shared__ CandOut scratch_out;
+    const int tid = threadIdx.x;
+    const TailJob tj = tails[blockIdx.x];
+    const Job job = jobs_all[tj.job];
+    const StreamDev st = p.streams[job.stream];
+    const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+    const uint32_t P = p.max_order;
+    if (job.nsmpl <= P) { return; }
+    for (uint32_t i = tid; i < pbuf_len; i += kT) { pbuf[i] = 0.0; }
+    /* the latest block in front of the tail that made calls: more samples than the order, not silent (srla_encoder.c:766-796) */
+    uint32_t pred = tj.job;
+    bool found = false;
+    while (!found && pred > tj.first_of_stream) {
+        pred--;
+        const Job pj = jobs_all[pred];
+        int nz = 0;
+        if (pj.nsmpl > P) {
+            for (uint32_t ch = 0; ch < p.nch; ++ch) { for (uint32_t i = tid; i < pj.nsmpl; i += kT) { nz |= load_sample(st, ch, pj.offset + i); } }
+        }
+        found = __syncthreads_or(nz) != 0;
+    }
+    if (found) {
+        /* its last call: the last candidate (the reference analyses M, S first, then the channels in order) */
+        const Job pj = jobs_all[pred];
+        front_chain_step<kT, kLtp>(p, pj, st, p.ncand - 1u, lshift, L, smem, pbuf, &scratch_out, pbuf + pbuf_len, 1u, red64, sh_i, sh_u);   /* lags to a dump area */
+    }
+    const uint32_t rel = tj.job - group_first;
+    for (uint32_t cand = 0; cand < p.ncand; ++cand) {
+        const uint32_t idx = rel * p.ncand + cand;
+        double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);
+        front_chain_step<kT, kLtp>(p, job, st, cand, lshift, L, smem, pbuf, p.cand + idx, g, 32u, red64, sh_i, sh_u);
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------

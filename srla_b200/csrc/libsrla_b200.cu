@@ -125,6 +125,11 @@ struct WorkerPool {
     }
 };
 
+/* cudaFuncSetAttribute state per (device, kernel), process-wide (see Runner::prep_kernel) */
+struct FuncAttr { uint32_t max_dynamic = 0; int carveout = -2; };
+struct FuncAttrCache { std::mutex m; std::map<std::pair<int, const void *>, FuncAttr> set; };
+FuncAttrCache g_func_attr;
+
 constexpr int kMaxLanes = 4;
 constexpr size_t kMiscBytes = 2 * sizeof(unsigned long long) + 263 * sizeof(uint32_t) + 4;   /* running[2], stats[263], pad to 8 */
 
@@ -159,9 +164,10 @@ struct DeviceCtx {
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_grp, ev_d2h;
     std::vector<Job> jobs_scratch;
+    std::vector<TailJob> tails_scratch;   /* tail blocks of the fixed tiling that need front_tail_kernel (odd, or short with LTP) */
+    DevBuf tails;
     std::vector<uint32_t> jobs_key;   /* stream lengths + block size of the fixed tiling that jobs_scratch and the device copy hold */
     bool jobs_cached = false;
-    uint32_t smem_set[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     int max_smem_optin = 0;
     int num_sms = 0;
     int front_occ = 3;             /* CTAs per SM front_kernel<128> is register-sized for (SRLA_B200_FRONT_OCC=3|4, tuning) */
@@ -184,6 +190,19 @@ struct SRLAEncoder {
 
 namespace {
 
+/* the library carries sm_100a code only (arch-specific: it does not run on any other compute capability) */
+bool device_is_sm100(int device)
+{
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess
+        || cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess) { return false; }
+    if (major != 10 || minor != 0) {
+        std::fprintf(stderr, "[srla_b200] device %d is sm_%d%d; this library is built for sm_100a only\n", device, major, minor);
+        return false;
+    }
+    return true;
+}
+
 bool ctx_init(DeviceCtx *c)
 {
     int count = 0;
@@ -193,13 +212,8 @@ bool ctx_init(DeviceCtx *c)
     }
     if (g_device >= 0) { CU_TRY(cudaSetDevice(g_device)); }
     CU_TRY(cudaGetDevice(&c->device));
-    cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, c->device));
-    if (prop.major < 10) {
-        std::fprintf(stderr, "[srla_b200] device %d is sm_%d%d; this library is built for sm_100a only\n", c->device, prop.major, prop.minor);
-        return false;
-    }
-    c->num_sms = prop.multiProcessorCount;
+    if (!device_is_sm100(c->device)) { return false; }
+    CU_TRY(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
     if (const char *e = std::getenv("SRLA_B200_FRONT_OCC")) { if (e[0] >= '2' && e[0] <= '4') { c->front_occ = e[0] - '0'; } }
     CU_TRY(cudaDeviceGetAttribute(&c->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -274,7 +288,7 @@ void ctx_destroy(DeviceCtx *c)
     if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
     if (c->ev_upload) { cudaEventDestroy(c->ev_upload); }
-    DevBuf *bufs[] = { &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
+    DevBuf *bufs[] = { &c->tails, &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
                        &c->misc, &c->stream_begin, &c->pcm, &c->out, &c->raw };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release(); c->h_stage_out.release();
@@ -485,17 +499,25 @@ struct Runner {
      * meant to run with: the carve-out is sized for exactly that many (plus the 1 KB the driver reserves per
      * CTA) so that the rest of the 228 KB stays L1 -- the FFT twiddle tables live there.  0 = maximum carve-out. */
     template <typename K>
-    bool prep_kernel(K kernel, uint32_t smem_bytes, int slot, int ctas = 0)
+    bool prep_kernel(K kernel, uint32_t smem_bytes, int ctas = 0)
     {
-        if (c->smem_set[slot] == smem_bytes) { return true; }
-        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        /* the attributes are state of the FUNCTION on a device, shared by every handle of the process: the cache is
+         * process-wide, and the dynamic shared-memory limit is only ever raised */
+        std::lock_guard<std::mutex> lock(g_func_attr.m);
+        FuncAttr &fa = g_func_attr.set[std::make_pair(c->device, reinterpret_cast<const void *>(kernel))];
+        if (smem_bytes > fa.max_dynamic) {
+            CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            fa.max_dynamic = smem_bytes;
+        }
         int carve = cudaSharedmemCarveoutMaxShared;
         if (ctas > 0 && c->sized_carveout) {
             const double want = (double)ctas * (smem_bytes + 1024.0 + 256.0) / (228.0 * 1024.0) * 100.0;
             carve = (int)std::min(100.0, std::ceil(want));
         }
-        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        c->smem_set[slot] = smem_bytes;
+        if (carve != fa.carveout) {
+            CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            fa.carveout = carve;
+        }
         return true;
     }
 
@@ -507,7 +529,8 @@ struct Runner {
     }
 
     /* the three analysis kernels: front (autocorrelation) -> lpc (Levinson-Durbin) -> residual (FIR + Rice search) */
-    bool launch_analyse(const LaunchParams &p, size_t batch, cudaStream_t on)
+    /* tails [tail_lo, tail_hi) of c->tails_scratch lie in this launch's jobs, which start at index group_first of c->jobs */
+    bool launch_analyse(const LaunchParams &p, size_t batch, cudaStream_t on, size_t tail_lo = 0, size_t tail_hi = 0, uint32_t group_first = 0)
     {
         const FrontLayout FL = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
         const LpcLayout LL = make_lpc_layout(p.max_order);
@@ -522,24 +545,24 @@ struct Runner {
         if (p.fft_max <= 4096u) {
             /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
             if (ltp) {
-                if (!prep_kernel(front_kernel<128, 3, true>, FL.total, 5, 3)) { return false; }
+                if (!prep_kernel(front_kernel<128, 3, true>, FL.total, 3)) { return false; }
                 front_kernel<128, 3, true><<<grid, 128, FL.total, on>>>(p);
             } else if (c->front_occ == 2) {
-                if (!prep_kernel(front_kernel<128, 2, false>, FL.total, 6, 2)) { return false; }
+                if (!prep_kernel(front_kernel<128, 2, false>, FL.total, 2)) { return false; }
                 front_kernel<128, 2, false><<<grid, 128, FL.total, on>>>(p);
             } else if (c->front_occ == 4) {
-                if (!prep_kernel(front_kernel<128, 4, false>, FL.total, 6, 4)) { return false; }
+                if (!prep_kernel(front_kernel<128, 4, false>, FL.total, 4)) { return false; }
                 front_kernel<128, 4, false><<<grid, 128, FL.total, on>>>(p);
             } else {
-                if (!prep_kernel(front_kernel<128, 3, false>, FL.total, 0, 3)) { return false; }
+                if (!prep_kernel(front_kernel<128, 3, false>, FL.total, 3)) { return false; }
                 front_kernel<128, 3, false><<<grid, 128, FL.total, on>>>(p);
             }
         } else if (p.fft_max <= 8192u) {
             if (ltp) {
-                if (!prep_kernel(front_kernel<256, 2, true>, FL.total, 1, 2)) { return false; }
+                if (!prep_kernel(front_kernel<256, 2, true>, FL.total, 2)) { return false; }
                 front_kernel<256, 2, true><<<grid, 256, FL.total, on>>>(p);
             } else {
-                if (!prep_kernel(front_kernel<256, 2, false>, FL.total, 7, 2)) { return false; }
+                if (!prep_kernel(front_kernel<256, 2, false>, FL.total, 2)) { return false; }
                 front_kernel<256, 2, false><<<grid, 256, FL.total, on>>>(p);
             }
         } else {
@@ -547,22 +570,38 @@ struct Runner {
             return false;
         }
         launches++;
+        if (tail_hi > tail_lo) {
+            /* the reference's stale-scratch corners on the last block of a stream (see front_tail_kernel) */
+            const uint32_t pbuf_len = std::max(p.fft_max, 512u);
+            const uint32_t smem_tail = FL.total + 8u * (pbuf_len + 272u);
+            if ((int)smem_tail + 1024 > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] tail block replay needs %u bytes of shared memory\n", smem_tail); return false; }
+            const TailJob *d_tails = (const TailJob *)c->tails.p + tail_lo;
+            const uint32_t nt = (uint32_t)(tail_hi - tail_lo);
+            if (p.fft_max <= 4096u) {
+                if (ltp) { if (!prep_kernel(front_tail_kernel<128, true>, smem_tail)) { return false; } front_tail_kernel<128, true><<<nt, 128, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
+                else { if (!prep_kernel(front_tail_kernel<128, false>, smem_tail)) { return false; } front_tail_kernel<128, false><<<nt, 128, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
+            } else {
+                if (ltp) { if (!prep_kernel(front_tail_kernel<256, true>, smem_tail)) { return false; } front_tail_kernel<256, true><<<nt, 256, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
+                else { if (!prep_kernel(front_tail_kernel<256, false>, smem_tail)) { return false; } front_tail_kernel<256, false><<<nt, 256, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
+            }
+            launches++;
+        }
         if (!mark(batch, 1, on)) { return false; }
         if (p.max_order > 0) {
-            if (!prep_kernel(lpc_levinson_kernel, LL.total, 2) || !prep_kernel(lpc_select_kernel, LL.select_total, 8)) { return false; }
+            if (!prep_kernel(lpc_levinson_kernel, LL.total) || !prep_kernel(lpc_select_kernel, LL.select_total)) { return false; }
             lpc_levinson_kernel<<<(ncands + 31u) / 32u, 32, LL.total, on>>>(p);
             lpc_select_kernel<<<(ncands + 31u) / 32u, 128, LL.select_total, on>>>(p);
             launches += 2;
             if (p.svr_iterations > 0u) {
                 /* persistent CTAs: one covariance / Cholesky matrix of P x P doubles each in global memory */
                 const SvrLayout SL = make_svr_layout(p.nmax, p.max_order);
-                if (!prep_kernel(svr_kernel, SL.total, 9)) { return false; }
+                if (!prep_kernel(svr_kernel, SL.total)) { return false; }
                 svr_kernel<<<svr_grid(p), kThreads, SL.total, on>>>(p);
                 launches++;
             }
         }
         if (!mark(batch, 2, on)) { return false; }
-        if (!prep_kernel(residual_kernel, RL.total, 3)) { return false; }
+        if (!prep_kernel(residual_kernel, RL.total)) { return false; }
         residual_kernel<<<grid, block, RL.total, on>>>(p);
         launches++;
         CU_TRY(cudaGetLastError());
@@ -603,7 +642,7 @@ struct Runner {
      * scan_done: recorded once this group's scan has run. */
     bool run_batch(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t nmax, bool emit, uint8_t *d_out, uint64_t cap,
                    bool store_residual, size_t ev_idx, unsigned long long *h_mailbox, int ln = 0,
-                   cudaEvent_t scan_after = nullptr, cudaEvent_t scan_done = nullptr)
+                   cudaEvent_t scan_after = nullptr, cudaEvent_t scan_done = nullptr, bool with_tails = false)
     {
         DeviceCtx::Lane &L = c->lane[ln];
         const cudaStream_t on = L.stream;
@@ -630,7 +669,15 @@ struct Runner {
         const uint32_t raw_max = 11u + (uint32_t)(((uint64_t)p.bps * nmax * p.nch) / 8u);
         p.emit_smem_bytes = raw_max;
         if (!mark(ev_idx, 0, on)) { return false; }
-        if (!launch_analyse(p, ev_idx, on)) { return false; }
+        size_t tail_lo = 0, tail_hi = 0; uint32_t group_first = 0;
+        if (with_tails) {
+            /* d_jobs points into the call's fixed tiling (c->jobs): the tails whose job lies in [group_first, group_first + count) */
+            group_first = (uint32_t)(d_jobs - (const Job *)c->jobs.p);
+            const std::vector<TailJob> &tv = c->tails_scratch;
+            tail_lo = std::lower_bound(tv.begin(), tv.end(), group_first, [](const TailJob &t, uint32_t v) { return t.job < v; }) - tv.begin();
+            tail_hi = std::lower_bound(tv.begin(), tv.end(), group_first + count, [](const TailJob &t, uint32_t v) { return t.job < v; }) - tv.begin();
+        }
+        if (!launch_analyse(p, ev_idx, on, tail_lo, tail_hi, group_first)) { return false; }
         if (!mark(ev_idx, 3, on)) { return false; }
         decide_kernel<<<(count + 127) / 128, 128, 0, on>>>(p);
         launches++;
@@ -641,7 +688,7 @@ struct Runner {
             if (scan_done) { CU_TRY(cudaEventRecord(scan_done, on)); }      /* after the mailbox copy: the next scan overwrites running[0] */
             const uint32_t smem = round_up_u32(raw_max, 4) + 16u;
             if ((int)smem > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] block too large for the emit stage (%u bytes)\n", smem); return false; }
-            if (c->smem_set[4] != smem) { CU_TRY(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); c->smem_set[4] = smem; }
+            if (!prep_kernel(emit_kernel, smem)) { return false; }
             emit_kernel<<<count, kThreads, smem, on>>>(p);
             launches += 2;
         }
@@ -749,16 +796,27 @@ struct Runner {
         std::vector<Job> &jobs = c->jobs_scratch;
         std::vector<uint32_t> key;
         key.reserve(pl.num_streams + 2);
-        key.push_back(max_block); key.push_back(pl.num_streams);
+        key.push_back(max_block); key.push_back(pl.num_streams); key.push_back(enc->param.ltp_order); key.push_back(enc->max_order);
         for (uint32_t s = 0; s < pl.num_streams; s++) { key.push_back(pl.streams[s].num_samples); }
         const bool reuse_jobs = c->jobs_cached && !pl.variable && key == c->jobs_key;
         if (!reuse_jobs) {
             c->jobs_cached = false;
             jobs.clear();
+            c->tails_scratch.clear();
+            /* stale-scratch corners of the reference (front_tail_kernel): only the last block of a stream can be odd or, with
+             * LTP, shorter than the 263 lags the pitch search reads -- as long as the block size itself is neither */
+            const uint32_t ltp = enc->param.ltp_order;
+            const bool replay_tails = !pl.variable && (max_block & 1u) == 0u && (ltp == 0u || max_block >= 263u);
             for (uint32_t s = 0; s < pl.num_streams; s++) {          /* fixed tiling: the block list, or the cover used for the shift */
                 const uint32_t total = pl.streams[s].num_samples;
+                const uint32_t first = (uint32_t)jobs.size();
                 for (uint32_t at = 0; at < total; at += max_block) {
                     jobs.push_back(make_job(s, at, std::min(max_block, total - at), at == 0 ? kJobFirstOfStream : 0u, len_cache));
+                }
+                const uint32_t last_n = jobs.back().nsmpl;
+                if (replay_tails && last_n > enc->max_order && ((last_n & 1u) || (ltp > 0u && ceil_pow2_host(last_n) < 263u))) {
+                    TailJob tj; tj.job = (uint32_t)jobs.size() - 1u; tj.first_of_stream = first;
+                    c->tails_scratch.push_back(tj);
                 }
             }
         }
@@ -808,8 +866,15 @@ struct Runner {
         if (cudaMemsetAsync(c->misc.p, 0, kMiscBytes, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
         if (!reuse_jobs) {
             if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
+            if (!pl.variable && !c->tails_scratch.empty()) {
+                const size_t bytes = sizeof(TailJob) * c->tails_scratch.size();
+                if (!c->tails.reserve(bytes)) { return SRLA_APIRESULT_NG; }
+                /* pageable source: the copy is staged by the driver before the call returns */
+                if (cudaMemcpyAsync(c->tails.p, c->tails_scratch.data(), bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+            }
             if (!pl.variable) { c->jobs_key = key; c->jobs_cached = true; }
         }
+        const bool use_tails = !pl.variable && !c->tails_scratch.empty();
 
         /* ---- host input ---- */
         std::vector<cudaEvent_t> &h2d_done = c->ev_h2d;
@@ -1006,7 +1071,7 @@ struct Runner {
             const bool chain = lanes_now > 1;
             if (!run_batch(pl, (const Job *)c->jobs.p + j0, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++,
                            pipelined ? mailbox + g : nullptr, ln,
-                           (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr)) { return SRLA_APIRESULT_NG; }
+                           (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr, use_tails)) { return SRLA_APIRESULT_NG; }
             if (pipelined && cudaEventRecord(grp_done[g], on) != cudaSuccess) { return SRLA_APIRESULT_NG; }
             if (c->trace) { host_launch.push_back(host_ms()); }
             if (pipelined) { recorded = g + 1; drain(false); }
@@ -1539,7 +1604,16 @@ SRLAApiResult SRLAB200_TestAnalyseChannel(
     c->jobs_cached = false;
     if (!c->jobs.reserve(sizeof(Job))) { return SRLA_APIRESULT_NG; }
     if (cudaMemcpyAsync(c->jobs.p, &job, sizeof(Job), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
-    if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0, nullptr)) { return SRLA_APIRESULT_NG; }
+    /* an odd length (or, with LTP, fewer than 263 samples) is analysed the way a freshly created reference handle would */
+    c->tails_scratch.clear();
+    const uint32_t ltp = encoder->param.ltp_order;
+    const bool tail = (n & 1u) || (ltp > 0u && ceil_pow2_host(n) < 263u);
+    if (tail) {
+        TailJob tj; tj.job = 0; tj.first_of_stream = 0;
+        c->tails_scratch.push_back(tj);
+        if (!c->tails.reserve(sizeof(TailJob)) || cudaMemcpyAsync(c->tails.p, c->tails_scratch.data(), sizeof(TailJob), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
+    }
+    if (!r.run_batch(pl, (const Job *)c->jobs.p, 1, n, false, nullptr, 0, true, 0, nullptr, 0, nullptr, nullptr, tail)) { return SRLA_APIRESULT_NG; }
     CandOut co; CandDiag dg;
     if (cudaStreamSynchronize(c->stream) != cudaSuccess
         || cudaMemcpy(&co, c->lane[0].cand.p, sizeof(co), cudaMemcpyDeviceToHost) != cudaSuccess

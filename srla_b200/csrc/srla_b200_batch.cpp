@@ -123,7 +123,8 @@ bool parse_u32(const char *prog, const char *what, const char *str, uint32_t *ou
 {
     char *e = nullptr;
     const long v = std::strtol(str, &e, 10);
-    if (*e != '\0') { std::fprintf(stderr, "%s: invalid %s. (irregular character found in %s at %s)\n", prog, what, str, e); return false; }
+    if (*e != '\0' || e == str) { std::fprintf(stderr, "%s: invalid %s. (irregular character found in %s at %s)\n", prog, what, str, e); return false; }
+    if (v < 0 || v > 0x7fffffffL) { std::fprintf(stderr, "%s: invalid %s. (%s is out of range)\n", prog, what, str); return false; }
     *out = (uint32_t)v;
     return true;
 }
@@ -208,6 +209,20 @@ int main(int argc, char **argv)
         std::string why;
         w.ok = parse_wav(w, why);
         if (!w.ok) { std::fprintf(stderr, "Failed to open %s. (%s)\n", w.path.c_str(), why.c_str()); failures++; }
+    }
+    /* two inputs that map to the same DIR/NAME.srl (a/x.wav and b/x.wav, x.wav and x.wave) would overwrite each other,
+     * possibly from two writer threads at once: the later ones are refused */
+    {
+        std::vector<size_t> by_out(files.size());
+        for (size_t i = 0; i < files.size(); i++) { by_out[i] = i; }
+        std::stable_sort(by_out.begin(), by_out.end(), [&](size_t a, size_t b) { return files[a].out_path < files[b].out_path; });
+        for (size_t k = 1; k < by_out.size(); k++) {
+            WavInfo &w = files[by_out[k]];
+            if (w.out_path == files[by_out[k - 1]].out_path && w.ok) {
+                std::fprintf(stderr, "%s: %s and %s would both be written to %s; the latter is skipped. \n", prog, files[by_out[k - 1]].path.c_str(), w.path.c_str(), w.out_path.c_str());
+                w.ok = false; failures++;
+            }
+        }
     }
 
     if (failures == (int)files.size()) { return 1; }          /* nothing to encode: do not even start the device */

@@ -216,6 +216,8 @@ def oracle_lib() -> C.CDLL:
         lib.so_rice_search.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         lib.so_rice_search.restype = C.c_uint32
         lib.so_analyse_channel.argtypes = [C.POINTER(SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(SoChannel)]
+        lib.so_reset_state.argtypes = []
+        lib.so_reset_state.restype = None
         lib.so_encode_whole_flat.argtypes = [C.POINTER(SoParams), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                              C.POINTER(C.c_uint32)]
         lib.so_set_svr_iterations.argtypes = [C.c_uint32]
@@ -276,6 +278,7 @@ def oracle_analyse(x: np.ndarray, bps=16, preset=4, ltp=0):
     res = np.zeros_like(sig)
     ch = SoChannel()
     prm = so_params(1, bps, preset=preset, ltp=ltp)
+    lib.so_reset_state()                                 # a freshly created handle (odd lengths read the calculator's scratch)
     rc = lib.so_analyse_channel(C.byref(prm), sig.ctypes.data, len(sig), res.ctypes.data, C.byref(ch))
     assert rc == 0
     return ch, sig, res

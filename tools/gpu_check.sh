@@ -6,7 +6,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo pytes
 summ() { python - "$1" <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))
-print(sys.argv[1],'value',round(d['value']),'e2e',round(d['e2e']['value']),'ms/step',round(d['ms_per_step'],3),'kernels',{k:round(v,3) for k,v in d['roofline']['all_kernels_ms'].items()},'clk',d['clocks']['sm_mhz'],d['clocks']['reasons'])
+print(sys.argv[1],"value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"batch",round(d["e2e_batch_api"]["value"]),'ms/step',round(d['ms_per_step'],3),'kernels',{k:round(v,3) for k,v in d['roofline']['all_kernels_ms'].items()},'clk',d['clocks']['sm_mhz'],d['clocks']['reasons'])
 PY
 }
 if [ "$FULL" = "1" ]; then python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; else python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; fi
