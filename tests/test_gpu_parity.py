@@ -247,9 +247,78 @@ def test_full_size_roundtrip_property():
     if not have_ref():
         pytest.skip("oracle/_ref not present")
     tile = synth_stereo(4096 * 50, seed=31)
-    pcm = np.concatenate([np.roll(tile, 37 * k, axis=1) for k in range(8)], axis=1)[:, :4096 * 400]
+    pcm = np.ascontiguousarray(np.concatenate([np.roll(tile, 37 * k, axis=1) for k in range(40)], axis=1)[:, :4096 * 2000])
     got = E.encode(pcm, preset=4, max_block=4096)
     assert np.array_equal(ref_decode(got), pcm)
+    # ... and byte for byte: the reference encodes the same 2 000 blocks as 16 independent pieces of 125 blocks; every
+    # block of a fixed-block stream depends only on its own samples and the stream's offset shift (0 here)
+    pieces = _reference_many([np.ascontiguousarray(pcm[:, 4096 * 125 * k:4096 * 125 * (k + 1)]) for k in range(16)], preset=4, max_block=4096)
+    assert got[24] == 0 and got[30:] == b"".join(p[30:] for p in pieces)
+
+
+def _reference_many(streams, **kw):
+    """the compiled reference (or the restatement without oracle/_ref) over many streams, one host thread each
+    (ctypes releases the GIL; one handle per call)"""
+    from concurrent.futures import ThreadPoolExecutor
+    fn = ref_encode if have_ref() else oracle_encode
+    if not have_ref():
+        return [fn(s, **kw) for s in streams]            # the restatement keeps process-wide scratch: one at a time
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as pool:
+        return list(pool.map(lambda s: fn(s, **kw), streams))
+
+
+def _variants(base, count, length):
+    """`count` different streams of `length` frames cut from one synthetic signal (rotations and integer gains)"""
+    out = []
+    for k in range(count):
+        seg = np.roll(base, 7919 * k, axis=1)[:, :length].astype(np.int64) * (16 - (k % 7)) // 16
+        out.append(np.ascontiguousarray(seg.astype(np.int32)))
+    return out
+
+
+def test_config5_shape_at_scale_is_byte_identical_to_the_reference():
+    """BASELINE configs[4] shape: 48 kHz stereo 16-bit files of 30 s (1 440 000 frames = 351 blocks of 4096 + a 2304-frame
+    tail), mode 4, submitted together as WAV payloads -- 16 files, every one compared byte for byte"""
+    frames = 48000 * 30
+    base = synth_stereo(frames + 4096, seed=500)
+    streams = _variants(base, 16, frames)
+    with E.Encoder(max_channels=2, max_block=4096) as enc:
+        assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+        out, offs = enc.encode_interleaved_host([_payload(s, 16) for s in streams])
+    want = _reference_many(streams, preset=4, max_block=4096)
+    for k in range(len(streams)):
+        got = out[offs[k]:offs[k + 1]].tobytes()
+        assert got == want[k], (k, _first_diff(got, want[k]))
+        assert [n for _p, _s, _t, n in walk_blocks(got)][-1] == 2304
+
+
+def test_config3_at_scale_is_byte_identical_to_the_reference():
+    """BASELINE configs[2]: 24-bit stereo, block 8192, mode 4, LTP order 3 -- 2 048 blocks (16 streams of 128)"""
+    base = synth_stereo(8192 * 160, seed=501, bits=24)
+    streams = _variants(base, 16, 8192 * 128)
+    kw = dict(bps=24, preset=4, max_block=8192, ltp=3)
+    with E.Encoder(max_channels=2, max_block=8192) as enc:
+        assert enc.set_parameter(2, 24, 48000, 8192, 8192, 8192, 3, 4) == E.OK
+        out, offs = enc.encode_streams_host(streams)
+    want = _reference_many(streams, **kw)
+    for k in range(len(streams)):
+        got = out[offs[k]:offs[k + 1]].tobytes()
+        assert got == want[k], (k, _first_diff(got, want[k]))
+
+
+def test_config4_at_scale_is_byte_identical_to_the_reference():
+    """BASELINE configs[3]: variable block division -V 2 -L 4 at max block 4096, mode 4 -- 2 048 blocks' worth of
+    frames (16 streams of 32 look-ahead chunks)"""
+    base = synth_stereo(16384 * 40, seed=502)
+    streams = _variants(base, 16, 16384 * 32)
+    kw = dict(preset=4, max_block=4096, min_block=1024, lookahead=16384)
+    with E.Encoder(max_channels=2, max_block=4096, min_block=1024, lookahead=16384) as enc:
+        assert enc.set_parameter(2, 16, 48000, 1024, 4096, 16384, 0, 4) == E.OK
+        out, offs = enc.encode_streams_host([s.astype(np.int16) for s in streams])
+    want = _reference_many(streams, **kw)
+    for k in range(len(streams)):
+        got = out[offs[k]:offs[k + 1]].tobytes()
+        assert got == want[k], (k, _first_diff(got, want[k]))
 
 
 def test_reference_cli_relinked_against_libsrla_b200(tmp_path):
