@@ -226,6 +226,110 @@ def load_traffic():
         return None
 
 
+# ------------------------------------------------------------------------------------------ config 5
+def run_config5(args, rank, world, local_rank, enc, lib, barrier, torch, dist):
+    """BASELINE configs[4]: `--files` synthetic 48 kHz stereo 16-bit WAV payloads of 30 s (1 440 000 frames = 351 blocks of
+    4096 + a 2304-frame tail), mode 4, split over the ranks by srla_b200.sharding.shard_range -- total work is fixed, so
+    the throughput over N is a STRONG-scaling curve.  Per rank and step the shard goes through
+    SRLAB200_EncodeInterleavedHost (page-locked WAV data-chunk bytes in, page-locked .srl bytes out: H2D, de-interleave,
+    encode, D2H inside the timed region); the same shard is also timed device-resident, and a copy-only pass (the shard's
+    bytes host->device, its encoded bytes device->host, all ranks at once) gives the ceiling the host side allows."""
+    from srla_b200 import encoder as E
+    from srla_b200.sharding import shard_range
+    from srla_b200.synth import synth_stereo
+    frames = 30 * RATE
+    lo, hi = shard_range(args.files, rank, world)
+    mine = hi - lo
+    if mine == 0:
+        lo, hi, mine = 0, 1, 1                       # more ranks than files: this rank repeats file 0 (not counted)
+        counted = 0
+    else:
+        counted = mine
+    # file k = rotation + integer gain of one synthetic 30 s signal (seed 1234): deterministic, every file different
+    base = synth_stereo(frames, seed=1234).astype(np.int16)
+    inter = np.ascontiguousarray(base.T)                                   # [frames, 2] = WAV data-chunk order
+    pitch = (frames * CHANNELS * 2 + 255) // 256 * 256                     # bytes per file in the staging buffers
+    h_raw = torch.empty(mine * pitch, dtype=torch.uint8).pin_memory()
+    raw_np = h_raw.numpy()
+    for i in range(mine):
+        k = lo + i
+        seg = np.roll(inter, 7919 * k, axis=0).astype(np.int32) * (16 - (k % 7)) // 16
+        raw_np[i * pitch:i * pitch + frames * 4] = seg.astype("<i2").reshape(-1).view(np.uint8)
+    items = (E.SRLAB200Frames * mine)()
+    for i in range(mine):
+        items[i] = E.SRLAB200Frames(h_raw.data_ptr() + i * pitch, frames)
+    cap = mine * enc.max_encoded_size(frames)
+    h_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    offs = (C.c_uint64 * (mine + 1))()
+
+    def step_e2e():
+        rc = lib.SRLAB200_EncodeInterleavedHost(enc.handle, items, mine, h_out.data_ptr(), cap, offs)
+        assert rc == E.OK, rc
+
+    def wall(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    steps = 3
+    step_e2e(); step_e2e()                                                  # warm-up: buffers grow, tiling cached
+    ms_e2e = wall(step_e2e, steps)
+    out_bytes = int(offs[mine])
+    total_samples = args.files * frames * CHANNELS                           # the whole batch, all ranks
+    # device resident: the same shard as planar int16 in HBM, output left in HBM
+    d_raw = h_raw.cuda()
+    stride = (frames + 15) // 16 * 16
+    d_planar = torch.zeros((mine, CHANNELS, stride), dtype=torch.int16, device="cuda")
+    for i in range(mine):
+        d_planar[i, :, :frames] = d_raw[i * pitch:i * pitch + frames * 4].view(torch.int16).view(frames, CHANNELS).t()
+    descs = (E.SRLAB200Stream * mine)()
+    for i in range(mine):
+        descs[i] = E.SRLAB200Stream(d_planar[i].data_ptr(), stride, frames, 2)
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+
+    def step_dev():
+        rc = lib.SRLAB200_EncodeStreamsDevice(enc.handle, descs, mine, d_out.data_ptr(), cap, offs)
+        assert rc == E.OK, rc
+
+    step_dev()
+    ms_dev = wall(step_dev, steps)
+    same = int(offs[mine]) == out_bytes
+    # copy-only ceiling: what the host side allows when every rank moves its shard at once
+    def step_copy():
+        d_raw.copy_(h_raw, non_blocking=True)
+        h_out[:out_bytes].copy_(d_out[:out_bytes], non_blocking=True)
+
+    step_copy()
+    ms_copy = wall(step_copy, steps)
+    rate = lambda ms: total_samples * steps / (ms * 1e-3) / 1e6
+    res = {"workload": f"configs[4]: {args.files} synthetic 48 kHz stereo 16-bit files of 30 s (351 blocks of 4096 + a 2304-frame tail), "
+                       f"mode 4, sharded {world} ways by contiguous file ranges (strong scaling: total work fixed)",
+           "files": args.files, "files_per_rank": counted, "frames_per_file": frames, "scaling": "strong",
+           "e2e": {"value": rate(ms_e2e), "unit": "Msamples/s", "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step_per_rank": mine * frames * 4, "d2h_bytes_per_step_per_rank": out_bytes,
+                   "api": "SRLAB200_EncodeInterleavedHost per rank on its shard (page-locked WAV payloads in, page-locked .srl bytes out); "
+                          "wall clock, max over ranks"},
+           "device": {"value": rate(ms_dev), "unit": "Msamples/s", "ms_per_step": ms_dev / steps,
+                      "api": "SRLAB200_EncodeStreamsDevice per rank on its shard (planar int16 in HBM)", "same_size_as_e2e": bool(same)},
+           "copy_ceiling": {"value": rate(ms_copy), "unit": "Msamples/s", "ms_per_step": ms_copy / steps,
+                            "h2d_gbs_per_rank": mine * frames * 4 * steps / (ms_copy * 1e-3) / 1e9,
+                            "what": "the shard's WAV bytes host->device and its encoded bytes device->host from the same page-locked buffers, "
+                                    "no kernels, all ranks at once: the end-to-end ceiling the host/PCIe side sets"},
+           "e2e_fraction_of_copy_ceiling": ms_copy / ms_e2e}
+    del d_raw, d_planar, d_out, h_raw, h_out
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -235,6 +339,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--files", type=int, default=1024, help="config 5: number of 30 s stereo files in the sharded batch (0: skip)")
+    ap.add_argument("--no-pin", action="store_true", help="do not restrict the rank to the CPUs next to its GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,6 +358,21 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the SRLA B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # host placement: this rank's page-locked staging memory and feeder threads stay next to its GPU, and the ranks that
+    # share a memory node split its CPUs (srla_b200/sharding.py).  Before any pinned allocation and before the library
+    # starts its thread pool.
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    placement = None
+    if not args.no_pin:
+        from srla_b200.sharding import pin_rank_to_gpu_cpus
+        try:
+            ids = []
+            for i in range(torch.cuda.device_count()):
+                pr = torch.cuda.get_device_properties(i)
+                ids.append("%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+            placement = pin_rank_to_gpu_cpus(ids, local_rank, min(local_world, len(ids)))
+        except Exception as exc:                                     # placement is an optimisation, never a failure
+            placement = {"pinned": False, "error": str(exc)}
     # Everything libraries print on the way (NCCL's version banner goes to stdout) is sent to stderr: stdout carries
     # exactly ONE line, the JSON below.
     sys.stdout.flush()
@@ -385,6 +506,13 @@ def main() -> None:
     same_bytes = bool(bytes(out_np[:size.value]) == bytes(h_out[:int(offs[1])].numpy().tobytes()))
     del pcm32
 
+    # ---- config 5 (BASELINE configs[4]): a batch of 30 s stereo files SHARDED over the ranks (strong scaling) ----
+    config5 = None
+    if args.files > 0:
+        del d_pcm, h_pcm, d_out, h_out
+        torch.cuda.empty_cache()
+        config5 = run_config5(args, rank, world, local_rank, enc, lib, barrier, torch, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -438,6 +566,8 @@ def main() -> None:
                            "output buffer in pageable host memory; wall clock, max over ranks",
                     "identical_to_batch_api_output": same_bytes},
             "e2e_batch_api": batch_api,
+            "config5": config5,
+            "host_placement": placement,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -248,6 +248,12 @@ SRLAApiResult SRLAB200_GetStats(const struct SRLAEncoder *encoder, struct SRLAB2
 /* Device selection for handles created afterwards by this thread (default: current CUDA device). */
 SRLAApiResult SRLAB200_SetDevice(int device_ordinal);
 
+/* Multi-GPU hosts (files shard across devices without any exchange): how many CUDA devices there are, and the
+ * PCI address ("dddd:bb:dd.f") of one of them (-1: the current device) -- what a host front end needs to place each
+ * device's reader / feeder threads and page-locked buffers on the CPUs next to it (/sys/bus/pci/devices/<address>/local_cpulist). */
+int SRLAB200_GetDeviceCount(void);
+SRLAApiResult SRLAB200_GetDevicePciBusId(int device_ordinal, char *buffer, int buffer_size);
+
 /* Run the handle's kernels on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL
  * restores the handle's own stream).  Lets a host framework time the kernels with its own events. */
 SRLAApiResult SRLAB200_SetStream(struct SRLAEncoder *encoder, void *cuda_stream);

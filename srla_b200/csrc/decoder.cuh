@@ -523,7 +523,7 @@ bool decoder_ctx_init(DecoderCtx *c)
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
     for (cudaStream_t &l : c->lanes) { CU_TRY(cudaStreamCreateWithFlags(&l, cudaStreamNonBlocking)); }
     CU_TRY(cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming));
-    { const unsigned hc = std::thread::hardware_concurrency(); c->host_threads = (int)std::max(2u, std::min(16u, hc ? hc : 8u)); }
+    c->host_threads = (int)std::max(2u, std::min(16u, usable_cpus()));
     if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->host_threads = v; } }
     if (const char *e = std::getenv("SRLA_B200_DECODE_PIPELINE")) { c->pipeline = std::atoi(e) ? 1 : 0; }
     if (const char *e = std::getenv("SRLA_B200_DECODE_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) { c->parse_lanes = v; } }

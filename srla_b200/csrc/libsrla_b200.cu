@@ -30,6 +30,10 @@
 #include <immintrin.h>
 #endif
 
+#if defined(__linux__)
+#include <sched.h>
+#endif
+
 #include <cuda_runtime.h>
 
 #include "../../include/srla_b200.h"
@@ -190,6 +194,18 @@ struct SRLAEncoder {
 
 namespace {
 
+/* CPUs this process may run on (its affinity mask, not the machine's CPU count): a rank pinned next to its GPU sizes its
+ * feeder team for its own share of the host */
+unsigned usable_cpus()
+{
+#if defined(__linux__)
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) { return (unsigned)n; } }
+#endif
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? hc : 8u;
+}
+
 /* the library carries sm_100a code only (arch-specific: it does not run on any other compute capability) */
 bool device_is_sm100(int device)
 {
@@ -225,7 +241,7 @@ bool ctx_init(DeviceCtx *c)
     if (const char *e = std::getenv("SRLA_B200_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= kMaxLanes) { c->lanes = v; } }
     if (const char *e = std::getenv("SRLA_B200_CARVE")) { if (e[0] == 'm') { c->sized_carveout = 0; } }
     if (const char *e = std::getenv("SRLA_B200_RAMP")) { c->ramp = std::atoi(e); }
-    { const unsigned hc = std::thread::hardware_concurrency(); c->feed_threads = (int)std::max(2u, std::min(16u, hc ? hc : 8u)); }
+    c->feed_threads = (int)std::max(2u, std::min(16u, usable_cpus()));
     if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->feed_threads = v; } }
     if (const char *e = std::getenv("SRLA_B200_TRACE")) { c->trace = std::atoi(e); }
     if (const char *e = std::getenv("SRLA_B200_SPLIT_DEVICE")) { c->split_device = std::atoi(e); }
@@ -1561,6 +1577,21 @@ SRLAApiResult SRLAB200_SetDevice(int device_ordinal)
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device_ordinal < 0 || device_ordinal >= count) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
     g_device = device_ordinal;
+    return SRLA_APIRESULT_OK;
+}
+
+int SRLAB200_GetDeviceCount(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return count;
+}
+
+SRLAApiResult SRLAB200_GetDevicePciBusId(int device_ordinal, char *buffer, int buffer_size)
+{
+    if (buffer == NULL || buffer_size < 16) { return SRLA_APIRESULT_INVALID_ARGUMENT; }
+    if (device_ordinal < 0) { if (cudaGetDevice(&device_ordinal) != cudaSuccess) { return SRLA_APIRESULT_NG; } }
+    if (cudaDeviceGetPCIBusId(buffer, buffer_size, device_ordinal) != cudaSuccess) { (void)cudaGetLastError(); return SRLA_APIRESULT_INVALID_ARGUMENT; }
     return SRLA_APIRESULT_OK;
 }
 

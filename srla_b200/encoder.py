@@ -87,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "SRLAB200_SetDevice", "SRLAB200_SetStream", "SRLAB200_Version", "SRLAB200_TestAnalyseChannel",
     "SRLADecoder_DecodeHeader", "SRLADecoder_CalculateWorkSize", "SRLADecoder_Create", "SRLADecoder_Destroy",
     "SRLADecoder_SetHeader", "SRLADecoder_DecodeBlock", "SRLADecoder_DecodeWhole", "SRLAB200_DecoderKernelMs",
-    "SRLAB200_TestNarrow",
+    "SRLAB200_TestNarrow", "SRLAB200_GetDeviceCount", "SRLAB200_GetDevicePciBusId",
 ]
 
 _lib: Optional[C.CDLL] = None

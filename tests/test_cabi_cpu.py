@@ -243,3 +243,54 @@ def test_shard_streams_world2_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_host_placement_helpers(tmp_path):
+    """srla_b200/sharding.py: sysfs cpulist parsing, the CPUs next to a GPU, and how ranks sharing a node split them"""
+    from srla_b200.sharding import gpu_locality, parse_cpulist, split_cpus
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    dev = tmp_path / "0000:1b:00.0"
+    dev.mkdir()
+    (dev / "numa_node").write_text("1\n")
+    (dev / "local_cpulist").write_text("32-63\n")
+    assert gpu_locality("0000:1B:00.0", str(tmp_path)) == (1, list(range(32, 64)))
+    assert gpu_locality("0000:ff:00.0", str(tmp_path)) == (None, [])
+    (dev / "numa_node").write_text("-1\n")                       # a host that does not report the node
+    assert gpu_locality("0000:1b:00.0", str(tmp_path))[0] is None
+    cpus = list(range(32))
+    parts = [split_cpus(cpus, 8, i) for i in range(8)]
+    assert sorted(c for p in parts for c in p) == cpus and all(len(p) == 4 for p in parts)
+    assert split_cpus(cpus, 1, 0) == cpus
+    assert all(len(split_cpus([0, 1, 2], 8, i)) == 1 for i in range(8))      # more ranks than CPUs: one each, wrapped
+
+
+def test_pinned_ranks_world2_gloo(tmp_path):
+    """two ranks whose GPUs sit on the same node take disjoint halves of its CPUs (world_size-2, gloo)"""
+    fake = tmp_path / "sys"
+    for bdf in ("0000:1b:00.0", "0000:1c:00.0"):
+        (fake / bdf).mkdir(parents=True)
+        (fake / bdf / "numa_node").write_text("0\n")
+        (fake / bdf / "local_cpulist").write_text(",".join(str(c) for c in sorted(os.sched_getaffinity(0))) + "\n")
+    script = tmp_path / "pin.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import srla_b200.sharding as S\n"
+        f"real = S.gpu_locality; S.gpu_locality = lambda bdf, root=None: real(bdf, {str(fake)!r})\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "before = sorted(os.sched_getaffinity(0))\n"
+        "info = S.pin_rank_to_gpu_cpus(['0000:1b:00.0', '0000:1c:00.0'], r, w)\n"
+        "mine = sorted(os.sched_getaffinity(0))\n"
+        "t = torch.zeros(4096, dtype=torch.int64); t[mine] = 1\n"
+        "dist.all_reduce(t)\n"
+        "assert info['pinned'] and info['ranks_sharing_them'] == 2, info\n"
+        "if len(before) >= 2:\n"
+        "    assert int(t.max()) == 1 and int(t.sum()) == len(before), 'halves overlap or leave CPUs unused'\n"
+        "dist.destroy_process_group()\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29618", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -551,6 +551,19 @@ def test_batch_cli_writes_what_the_reference_cli_writes(tmp_path):
             got = (out_dir / f"{name}.srl").read_bytes()
             assert got == want.read_bytes(), (tag, name, _first_diff(got, want.read_bytes()))
         assert not (out_dir / "broken.srl").exists()
+    # every CUDA device of the host, each with its own pipeline, submissions of ~1 MB so that several devices get work;
+    # two inputs that would land on the same output name: the later one is refused
+    out_dir = tmp_path / "out_all"
+    dup = tmp_path / "dup"
+    dup.mkdir()
+    (dup / "a16.wav").write_bytes((tmp_path / "a16.wav").read_bytes())
+    r = subprocess.run([batch, "-m", "4", "-B", "4096", "-V", "0", "--devices", "all", "--batch-megabytes", "1", "-o", str(out_dir)]
+                       + [str(tmp_path / f"{n}.wav") for n in files] + [str(dup / "a16.wav")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"would both be written" in r.stderr, r.stderr
+    for name in files:
+        assert (out_dir / f"{name}.srl").read_bytes() == (tmp_path / f"ref_fixed_{name}.srl").read_bytes(), name
+    r = subprocess.run([batch, "-m", "-4", "-o", str(out_dir), str(tmp_path / "a16.wav")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"out of range" in r.stderr
 
 
 # ---- SVR coefficient refinement (--svr-filter-learning-iteration) ----------------------------------
