@@ -1775,6 +1775,442 @@ __device__ RiceResult rice_search_general(const int32_t *res_s, const uint32_t n
     return rr;
 }
 
+/* ---- FIR residual with IDP.2A (srla_lpc_predict.c:236-264), shared by residual_kernel and residual16_kernel ---- */
+__device__ __forceinline__ void fir_residual_dp2a(const int4 *Z, const uint32_t zf, const int32_t *coef_b, const uint32_t n, const uint32_t order,
+                                                  const uint32_t p4, const uint32_t rshift, const uint32_t half, int32_t *res_s, int32_t *res_g)
+{
+    const int tid = threadIdx.x;
+    /* ---- FIR residual with IDP.2A, int32 wrapping.  Every group of 8 outputs that reaches past the warm-up (first
+     * output >= order, or straddling it) runs the full padded filter: for an output i >= order the taps that fall in
+     * front of the block carry zero coefficients (order is padded to p4 in FRONT), so they may read anything
+     * addressable.  Warm-up outputs (i < order: first differences, srla_lpc_predict.c:251-254) are patched in
+     * afterwards.  No output is ever computed by a serial loop: one slow thread would hold the whole CTA at the
+     * next barrier. ---- */
+    const uint32_t groups = (n + 7u) >> 3, nm = p4 >> 2;
+    for (uint32_t g = tid; g < groups; g += kThreads) {
+        const uint32_t n0 = g << 3;
+        int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+        int4 za, zb;
+        if (order > 0u && n0 + 8u > order) {
+            const uint32_t j0 = zf + (n0 >> 2) - nm;                       /* >= 0: zf covers p4 / 4 entries */
+            za = Z[zpair_slot(j0)]; zb = Z[zpair_slot(j0 + 1u)];
+            for (uint32_t m = 0; m < nm; ++m) {
+                const int4 zc = Z[zpair_slot(j0 + m + 2u)];
+                const int32_t cf = coef_b[m];
+                a0 = __dp2a_lo(za.x, cf, a0); a0 = __dp2a_hi(za.y, cf, a0);
+                a1 = __dp2a_lo(za.z, cf, a1); a1 = __dp2a_hi(za.w, cf, a1);
+                a2 = __dp2a_lo(za.y, cf, a2); a2 = __dp2a_hi(zb.x, cf, a2);
+                a3 = __dp2a_lo(za.w, cf, a3); a3 = __dp2a_hi(zb.z, cf, a3);
+                a4 = __dp2a_lo(zb.x, cf, a4); a4 = __dp2a_hi(zb.y, cf, a4);
+                a5 = __dp2a_lo(zb.z, cf, a5); a5 = __dp2a_hi(zb.w, cf, a5);
+                a6 = __dp2a_lo(zb.y, cf, a6); a6 = __dp2a_hi(zc.x, cf, a6);
+                a7 = __dp2a_lo(zb.w, cf, a7); a7 = __dp2a_hi(zc.z, cf, a7);
+                za = zb; zb = zc;
+            }
+        } else {
+            za = Z[zpair_slot(zf + (n0 >> 2))]; zb = Z[zpair_slot(zf + (n0 >> 2) + 1u)];
+        }
+        /* za, zb now hold the entries of samples n0 .. n0+4 and n0+4 .. n0+8: the outputs' own samples */
+        const int32_t x[8] = { (int32_t)(short)(za.x & 0xffff), za.x >> 16, (int32_t)(short)(za.y & 0xffff), za.y >> 16,
+                               (int32_t)(short)(zb.x & 0xffff), zb.x >> 16, (int32_t)(short)(zb.y & 0xffff), zb.y >> 16 };
+        int32_t r[8];
+        if (order > 0u) {
+            r[0] = (int32_t)((uint32_t)x[0] + (uint32_t)asr32(a0, rshift)); r[1] = (int32_t)((uint32_t)x[1] + (uint32_t)asr32(a1, rshift));
+            r[2] = (int32_t)((uint32_t)x[2] + (uint32_t)asr32(a2, rshift)); r[3] = (int32_t)((uint32_t)x[3] + (uint32_t)asr32(a3, rshift));
+            r[4] = (int32_t)((uint32_t)x[4] + (uint32_t)asr32(a4, rshift)); r[5] = (int32_t)((uint32_t)x[5] + (uint32_t)asr32(a5, rshift));
+            r[6] = (int32_t)((uint32_t)x[6] + (uint32_t)asr32(a6, rshift)); r[7] = (int32_t)((uint32_t)x[7] + (uint32_t)asr32(a7, rshift));
+            if (n0 < order) {
+                /* warm-up outputs of this group; x[n0 - 1] is the first half of the previous entry's last pair */
+                const int32_t before = (int32_t)(short)(Z[zpair_slot(zf + (n0 >> 2) - 1u)].w & 0xffff);
+                #pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const uint32_t i = n0 + (uint32_t)t;
+                    if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int t = 0; t < 8; ++t) { r[t] = x[t]; }
+        }
+        *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+        if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
+        if (n0 + 4u < n) {
+            *reinterpret_cast<int4 *>(res_s + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]);
+            if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]); }
+        }
+    }
+}
+
+/* ---- the same filter on an int32 signal (24-bit sources, signals that do not fit 16 bits) ---- */
+__device__ __forceinline__ void fir_residual_imad(const int32_t *sig, const int32_t *coef_s, const uint32_t n, const uint32_t order,
+                                                  const uint32_t p4, const uint32_t rshift, const uint32_t half, int32_t *res_s, int32_t *res_g)
+{
+    const int tid = threadIdx.x;
+    if (order > 0u) {
+        /* same scheme as above: padded filter for every group reaching past the warm-up, warm-up outputs patched in */
+        const uint32_t groups = (n + 3u) >> 2;
+        const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
+        for (uint32_t g = tid; g < groups; g += kThreads) {
+            const uint32_t n0 = g << 2;
+            uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
+            const int4 w_self = *reinterpret_cast<const int4 *>(sig + n0);
+            if (n0 + 4u > order) {
+                const int4 *xp = reinterpret_cast<const int4 *>(sig + n0) - (p4 >> 2);      /* may start in the front padding */
+                int4 w0 = xp[0];
+                for (uint32_t m = 0; m < (p4 >> 2); ++m) {
+                    const int4 w1 = xp[m + 1u];
+                    const int4 cf = coef4[m];
+                    a0 += (uint32_t)cf.x * (uint32_t)w0.x + (uint32_t)cf.y * (uint32_t)w0.y + (uint32_t)cf.z * (uint32_t)w0.z + (uint32_t)cf.w * (uint32_t)w0.w;
+                    a1 += (uint32_t)cf.x * (uint32_t)w0.y + (uint32_t)cf.y * (uint32_t)w0.z + (uint32_t)cf.z * (uint32_t)w0.w + (uint32_t)cf.w * (uint32_t)w1.x;
+                    a2 += (uint32_t)cf.x * (uint32_t)w0.z + (uint32_t)cf.y * (uint32_t)w0.w + (uint32_t)cf.z * (uint32_t)w1.x + (uint32_t)cf.w * (uint32_t)w1.y;
+                    a3 += (uint32_t)cf.x * (uint32_t)w0.w + (uint32_t)cf.y * (uint32_t)w1.x + (uint32_t)cf.z * (uint32_t)w1.y + (uint32_t)cf.w * (uint32_t)w1.z;
+                    w0 = w1;
+                }
+            }
+            int32_t r[4] = { (int32_t)((uint32_t)w_self.x + (uint32_t)asr32((int32_t)a0, rshift)), (int32_t)((uint32_t)w_self.y + (uint32_t)asr32((int32_t)a1, rshift)),
+                             (int32_t)((uint32_t)w_self.z + (uint32_t)asr32((int32_t)a2, rshift)), (int32_t)((uint32_t)w_self.w + (uint32_t)asr32((int32_t)a3, rshift)) };
+            if (n0 < order) {
+                const int32_t x[4] = { w_self.x, w_self.y, w_self.z, w_self.w };
+                const int32_t before = sig[n0 ? n0 - 1u : 0u];
+                #pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t i = n0 + (uint32_t)t;
+                    if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
+                }
+            }
+            *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
+            if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
+        }
+    } else {
+        for (uint32_t i = tid; i < n; i += kThreads) { const int32_t v = sig[i]; res_s[i] = v; if (res_g) { res_g[i] = v; } }
+    }
+}
+
+/* ---- residual coder search, side-information bits, result record: the tail of both residual kernels ---- */
+__device__ __forceinline__ void residual_finish(const LaunchParams &p, CandOut *out, const int32_t *res_s, const uint32_t n, unsigned char *scratch,
+                                                uint32_t *red32, const int32_t *coef_s, const uint32_t p4, const uint32_t order, const uint32_t ltp_period)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t bps = p.bps;
+    /* ---- residual coder search (srla_coder.c:349-483) ---- */
+    RiceResult rr;
+    switch (n) {
+        case 1024u: rr = rice_search_fast<1>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 2048u: rr = rice_search_fast<2>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 3072u: rr = rice_search_fast<3>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 4096u: rr = rice_search_fast<4>(res_s, scratch, red32, out, p.rice_threshold); break;
+        case 8192u: rr = rice_search_fast<8>(res_s, scratch, red32, out, p.rice_threshold); break;
+        default:    rr = rice_search_general(res_s, n, scratch, red32, out, p.rice_threshold); break;
+    }
+    const uint32_t code_type = rr.code_type, best_porder = rr.porder, residual_bits = rr.bits;
+
+    /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */
+    if (tid < 32) {
+        uint32_t plain_bits = 0, sum_bits = 0, bad = 0;
+        const int32_t *cf = coef_s + (p4 - order);
+        for (uint32_t i = lane; i < order; i += 32) {
+            const int32_t c = cf[i];
+            const uint32_t len = __ldg(p.huff_len + zigzag32(c));
+            plain_bits += len;
+            if (i == 0u) { sum_bits += len; }
+            else {
+                const uint32_t sym = zigzag32(c + cf[i - 1u]);
+                if (sym >= 256u) { bad = 1; } else { sum_bits += __ldg(p.huff_len + 256 + sym); }
+            }
+        }
+        plain_bits = warp_sum_u32(plain_bits); sum_bits = warp_sum_u32(sum_bits); bad = warp_sum_u32(bad);
+        if (lane == 0) {
+            uint32_t use_sum = 0, coef_bits = 0;
+            if (order > 0u) {
+                /* the reference's early exits are equivalent to: every symbol valid and the summed form strictly shorter */
+                use_sum = (!bad && (order == 1u || sum_bits < plain_bits)) ? 1u : 0u;
+                coef_bits = use_sum ? sum_bits : plain_bits;
+            }
+            uint32_t bits = residual_bits;
+            bits += bps + 1u + 5u;
+            bits += 8u + 4u + 1u;
+            bits += coef_bits;
+            bits += 1u;
+            if (ltp_period > 0u) { bits += 1u + 8u + p.ltp_order * 6u; }
+            out->use_sum = use_sum; out->coef_bits = coef_bits;
+            out->code_type = code_type; out->porder = best_porder;
+            out->residual_bits = residual_bits; out->total_bits = bits;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * residual16_kernel: the residual stage for 16-bit PCM without LTP (configs 2, 4, 5) as PERSISTENT CTAs whose source
+ * samples arrive by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier) one work item ahead.
+ *
+ * While a CTA filters and searches candidate i, the int16 source rows of candidate i + gridDim.x are already on their way
+ * into the other buffer, and the descriptors that copy needs (job, stream, the candidate's analysis record) were fetched by
+ * cp.async during the phases before: nobody waits for a dependent chain of global loads at the start of an item, which cost
+ * the one-CTA-per-candidate kernel a fifth of every CTA's life.  The rows are converted straight into the FIR's 16-bit pair
+ * entries (offset shift, mid/side, pre-emphasis on the way), so the int32 candidate signal is never materialised; the int32
+ * residual of the current item is written over its own source rows once they are packed.
+ * Same arithmetic as residual_kernel (shared device functions); items a bulk copy cannot serve (rows that are not
+ * 16-byte aligned or not a multiple of 8 samples, e.g. a stream's tail block) are loaded with plain loads.
+ * ---------------------------------------------------------------------------------------------- */
+struct Resid16Desc {
+    uint32_t n, skip, bulk, order, rshift, lshift, kind, two_rows;      /* kind 0: mid, 1: side, 2: a channel as it is */
+    int32_t  pre_coef;
+    uint32_t job_id, cand, stream, offset, pad[3];
+};
+static_assert(sizeof(Resid16Desc) == 64, "descriptor slot");
+
+__device__ __forceinline__ uint32_t smem_addr(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+/* global -> shared bulk copy of `bytes` (a multiple of 16, both addresses 16-byte aligned); completes on `bar` */
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_addr(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_addr(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* candidate sample from the (shifted) left / right samples (srla_utility.c:91-103) */
+__device__ __forceinline__ int32_t cand16_value(int32_t l, int32_t r, uint32_t kind, uint32_t lshift)
+{
+    l = asr32(l, lshift);
+    if (kind == 2u) { return l; }
+    r = asr32(r, lshift);
+    const int32_t side = (int32_t)((uint32_t)r - (uint32_t)l);
+    return (kind == 1u) ? side : (int32_t)((uint32_t)l + (uint32_t)(side >> 1));
+}
+
+/* pre-emphasised candidate sample i of an item, 0 outside [0, n) (srla_utility.c:342-358, filter memory = first sample) */
+__device__ __forceinline__ int32_t cand16_filtered(const short *row0, const short *row1, const Resid16Desc &d, int32_t i)
+{
+    if (i < 0 || (uint32_t)i >= d.n) { return 0; }
+    const int32_t ip = i ? i - 1 : 0;
+    const int32_t cur = cand16_value(row0[i], d.two_rows ? row1[i] : 0, d.kind, d.lshift);
+    const int32_t prv = cand16_value(row0[ip], d.two_rows ? row1[ip] : 0, d.kind, d.lshift);
+    return (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)d.pre_coef) >> 4));
+}
+
+__global__ void __launch_bounds__(kThreads, 4) residual16_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Resid16Layout L = make_resid16_layout(p.nmax, p.max_order);
+    unsigned char *scratch = smem + L.scratch_off;
+    int32_t  *coef_s = reinterpret_cast<int32_t *>(smem + L.coef_off);
+    int32_t  *coef_b = reinterpret_cast<int32_t *>(smem + L.coefb_off);
+    uint32_t *red32  = reinterpret_cast<uint32_t *>(smem + L.red_off);
+    unsigned char *stage_base = smem + L.stage_off;            /* two slots of 128 bytes: [0,16) job head, [16,80) candidate record head, [80,128) stream */
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
+    const int tid = threadIdx.x;
+    const uint32_t total = p.num_jobs * p.ncand;
+    const uint32_t first_ch = (p.nch >= 2u) ? 2u : 0u;
+
+    /* every thread: the item whose records are staged in slot b */
+    auto describe = [&](uint32_t idx, uint32_t b) {
+        const unsigned char *stage = stage_base + 128u * b;
+        const uint32_t *jh = reinterpret_cast<const uint32_t *>(stage);                 /* stream, offset, nsmpl, flags */
+        const int32_t *ch = reinterpret_cast<const int32_t *>(stage + 16);              /* CandOut head */
+        const StreamDev *st = reinterpret_cast<const StreamDev *>(stage + 80);
+        Resid16Desc d;
+        d.job_id = idx / p.ncand; d.cand = idx - d.job_id * p.ncand;
+        d.stream = jh[0]; d.offset = jh[1]; d.n = jh[2];
+        d.pre_coef = ch[0]; d.order = (uint32_t)ch[2]; d.rshift = (uint32_t)ch[3];
+        d.skip = (d.n <= p.max_order || ch[15] != 0) ? 1u : 0u;                        /* RAW block / failed analysis */
+        d.lshift = p.use_fixed_lshift ? p.fixed_lshift : st->lshift;
+        const bool ms = (p.nch >= 2u) && (d.cand < 2u);
+        d.kind = ms ? d.cand : 2u; d.two_rows = ms ? 1u : 0u;
+        const uint32_t chan = ms ? 0u : d.cand - first_ch;
+        /* rows a bulk copy can serve: 16-byte aligned, a multiple of 8 samples */
+        const unsigned long long a0 = reinterpret_cast<unsigned long long>(st->pcm) + 2ull * ((unsigned long long)chan * st->stride + d.offset);
+        const unsigned long long a1 = reinterpret_cast<unsigned long long>(st->pcm) + 2ull * (st->stride + d.offset);       /* right channel (mid / side) */
+        d.bulk = (!d.skip && (d.n & 7u) == 0u && (a0 & 15ull) == 0ull && (!ms || (a1 & 15ull) == 0ull)) ? 1u : 0u;
+        d.pad[0] = (uint32_t)a0; d.pad[1] = (uint32_t)(a0 >> 32); d.pad[2] = (uint32_t)(a1 - a0);
+        return d;
+    };
+    /* thread 0: the source rows of the item staged in slot b on their way into buffer b */
+    auto fetch_rows = [&](uint32_t idx, uint32_t b) {
+        const Resid16Desc d = describe(idx, b);
+        if (d.bulk) {
+            unsigned char *buf = smem + L.buf_off[b];
+            const uint32_t bytes = 2u * d.n;
+            const unsigned long long a0 = ((unsigned long long)d.pad[1] << 32) | d.pad[0];
+            /* the buffer was last written through the generic proxy (the previous item's residual): order those accesses
+             * before the asynchronous-proxy writes of the copy */
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&bar[b], d.two_rows ? 2u * bytes : bytes);
+            bulk_copy_g2s(buf, reinterpret_cast<const void *>(a0), bytes, &bar[b]);
+            if (d.two_rows) { bulk_copy_g2s(buf + L.row_bytes, reinterpret_cast<const void *>(a0 + d.pad[2]), bytes, &bar[b]); }
+        }
+    };
+    /* thread 0: start fetching the records of item idx into slot b (job head and candidate record now; the stream once the
+     * job is known) */
+    auto stage_job_and_cand = [&](uint32_t idx, uint32_t b) {
+        unsigned char *stage = stage_base + 128u * b;
+        const uint32_t job_id = idx / p.ncand;
+        const unsigned char *jsrc = reinterpret_cast<const unsigned char *>(p.jobs + job_id);
+        cp_async_8(stage, jsrc); cp_async_8(stage + 8, jsrc + 8);
+        const unsigned char *csrc = reinterpret_cast<const unsigned char *>(p.cand + idx);
+        cp_async_16(stage + 16, csrc); cp_async_16(stage + 32, csrc + 16); cp_async_16(stage + 48, csrc + 32); cp_async_16(stage + 64, csrc + 48);
+        cp_async_commit();
+    };
+    auto stage_stream = [&](uint32_t b) {
+        unsigned char *stage = stage_base + 128u * b;
+        cp_async_wait_all();
+        const uint32_t stream = *reinterpret_cast<const volatile uint32_t *>(stage);
+        const unsigned char *ssrc = reinterpret_cast<const unsigned char *>(p.streams + stream);
+        cp_async_16(stage + 80, ssrc); cp_async_16(stage + 96, ssrc + 16); cp_async_16(stage + 112, ssrc + 32);
+        cp_async_commit();
+    };
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1u); mbar_init(&bar[1], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x < total) { stage_job_and_cand(blockIdx.x, 0u); stage_stream(0u); cp_async_wait_all(); fetch_rows(blockIdx.x, 0u); }
+    }
+    __syncthreads();
+
+    uint32_t parity_bits = 0u;                                 /* bit b: phase parity of mbarrier b (no locally indexed array) */
+    uint32_t it = 0;
+    for (uint32_t idx = blockIdx.x; idx < total; idx += gridDim.x, ++it) {
+        const uint32_t cur = it & 1u, nxt = cur ^ 1u;
+        const uint32_t next_idx = idx + gridDim.x;
+        const bool have_next = next_idx < total;
+        const Resid16Desc d = describe(idx, cur);                                      /* every thread, from the staged records */
+        if (tid == 0 && have_next) { stage_job_and_cand(next_idx, nxt); }            /* phase A of the next item's fetch */
+        const uint32_t n = d.n, order = d.order, rshift = d.rshift;
+        CandOut *out = p.cand + idx;
+        unsigned char *buf = smem + L.buf_off[cur];
+        const short *row0 = reinterpret_cast<const short *>(buf);
+        const short *row1 = reinterpret_cast<const short *>(buf + L.row_bytes);
+        int32_t *res_s = reinterpret_cast<int32_t *>(buf);
+        const uint32_t p4 = round_up_u32(order, 4);
+        int32_t my_coef = 0;                                                          /* loaded now, stored after the packing loop */
+        if (!d.skip && (uint32_t)tid < p4 && (uint32_t)tid >= p4 - order) { my_coef = (int32_t)out->coef[(uint32_t)tid - (p4 - order)]; }
+
+        if (!d.skip) {
+            if (d.bulk) { mbar_wait(&bar[cur], (parity_bits >> cur) & 1u); }
+            else {
+                /* plain loads: a tail block, or rows the bulk copy cannot address */
+                const StreamDev st = p.streams[d.stream];
+                const uint32_t chan = d.two_rows ? 0u : d.cand - first_ch;
+                short *w0 = reinterpret_cast<short *>(buf), *w1 = reinterpret_cast<short *>(buf + L.row_bytes);
+                for (uint32_t i = tid; i < n; i += kThreads) {
+                    w0[i] = (short)load_sample(st, chan, d.offset + i);
+                    if (d.two_rows) { w1[i] = (short)load_sample(st, 1u, d.offset + i); }
+                }
+                __syncthreads();
+            }
+        }
+        if (d.bulk) { parity_bits ^= 1u << cur; }
+
+        int32_t *res_g = p.residual ? p.residual + (size_t)idx * p.res_stride : nullptr;
+        const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;
+        int4 *Z = reinterpret_cast<int4 *>(scratch);
+        const uint32_t zf = resid_pair_front(p.max_order);
+        int fits = 1;
+        if (!d.skip) {
+            /* ---- rows -> 16-bit pair entries, two entries (8 samples) per work item.  With a block that is a multiple of 8
+             * samples every item takes the same straight-line path: the sample in front of the block is the first sample
+             * itself (filter memory, srla_utility.c:342-358) and the sample behind it is zero -- both are selects, so no
+             * warp diverges and no thread runs a longer path than its neighbours (they would all wait for it at the
+             * barrier below). ---- */
+            const uint32_t items = round_up_u32(n, 8) >> 3;
+            const uint32_t pc = (uint32_t)d.pre_coef, kind = d.kind, lshift = d.lshift;
+            if ((n & 7u) == 0u) {
+                for (uint32_t q = tid; q < items; q += kThreads) {
+                    int32_t x[9], c[10];
+                    const int4 a = *reinterpret_cast<const int4 *>(row0 + 8u * q);
+                    int32_t l[10] = { 0, (int32_t)(short)(a.x & 0xffff), a.x >> 16, (int32_t)(short)(a.y & 0xffff), a.y >> 16,
+                                      (int32_t)(short)(a.z & 0xffff), a.z >> 16, (int32_t)(short)(a.w & 0xffff), a.w >> 16, (int32_t)row0[8u * q + 8u] };
+                    l[0] = q ? (int32_t)row0[8u * q - 1u] : l[1];
+                    if (d.two_rows) {
+                        const int4 b = *reinterpret_cast<const int4 *>(row1 + 8u * q);
+                        int32_t r[10] = { 0, (int32_t)(short)(b.x & 0xffff), b.x >> 16, (int32_t)(short)(b.y & 0xffff), b.y >> 16,
+                                          (int32_t)(short)(b.z & 0xffff), b.z >> 16, (int32_t)(short)(b.w & 0xffff), b.w >> 16, (int32_t)row1[8u * q + 8u] };
+                        r[0] = q ? (int32_t)row1[8u * q - 1u] : r[1];
+                        if (lshift != 0u) {
+                            #pragma unroll
+                            for (int t = 0; t < 10; ++t) { l[t] = asr32(l[t], lshift); r[t] = asr32(r[t], lshift); }
+                        }
+                        #pragma unroll
+                        for (int t = 0; t < 10; ++t) {
+                            const int32_t side = (int32_t)((uint32_t)r[t] - (uint32_t)l[t]);
+                            c[t] = (kind == 1u) ? side : (int32_t)((uint32_t)l[t] + (uint32_t)(side >> 1));
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int t = 0; t < 10; ++t) { c[t] = (lshift != 0u) ? asr32(l[t], lshift) : l[t]; }
+                    }
+                    #pragma unroll
+                    for (int t = 0; t < 9; ++t) { x[t] = (int32_t)((uint32_t)c[t + 1] - (uint32_t)((int32_t)((uint32_t)c[t] * pc) >> 4)); }
+                    if (8u * q + 8u >= n) { x[8] = 0; }
+                    #pragma unroll
+                    for (int t = 0; t < 8; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
+                    Z[zpair_slot(zf + 2u * q)] = pack_pair_entry(x);
+                    Z[zpair_slot(zf + 2u * q + 1u)] = pack_pair_entry(x + 4);
+                    if (q == 0u) {
+                        /* the entry in front of the block: zeros, then the first sample (the odd outputs' first pair) */
+                        const int32_t f[5] = { 0, 0, 0, 0, x[0] };
+                        Z[zpair_slot(zf - 1u)] = pack_pair_entry(f);
+                    }
+                }
+            } else {
+                for (uint32_t q = tid; q < items; q += kThreads) {
+                    int32_t x[9];
+                    #pragma unroll
+                    for (int t = 0; t < 9; ++t) { x[t] = cand16_filtered(row0, row1, d, (int32_t)(8u * q) + t); }
+                    #pragma unroll
+                    for (int t = 0; t < 8; ++t) { fits &= ((uint32_t)(x[t] + 32768) < 65536u) ? 1 : 0; }
+                    Z[zpair_slot(zf + 2u * q)] = pack_pair_entry(x);
+                    Z[zpair_slot(zf + 2u * q + 1u)] = pack_pair_entry(x + 4);
+                    if (q == 0u) { const int32_t f[5] = { 0, 0, 0, 0, x[0] }; Z[zpair_slot(zf - 1u)] = pack_pair_entry(f); }
+                }
+            }
+            if ((uint32_t)tid < p4) {
+                coef_s[tid] = my_coef;
+                /* the same coefficients as bytes, four taps per word: p4 is a multiple of 4, so the four lanes of a word are
+                 * active together */
+                const uint32_t lanes = __activemask();
+                uint32_t w = (uint32_t)my_coef & 0xffu;
+                w |= (__shfl_down_sync(lanes, (uint32_t)my_coef & 0xffu, 1) << 8);
+                w |= (__shfl_down_sync(lanes, (uint32_t)my_coef & 0xffu, 2) << 16);
+                w |= (__shfl_down_sync(lanes, (uint32_t)my_coef & 0xffu, 3) << 24);
+                if ((tid & 3) == 0) { coef_b[tid >> 2] = (int32_t)w; }
+            }
+        }
+        if (tid == 0 && have_next) { stage_stream(nxt); }                             /* phase B */
+        const bool zmode = __syncthreads_and(fits) != 0;
+
+        if (!d.skip) {
+            if (zmode) {
+                fir_residual_dp2a(Z, zf, coef_b, n, order, p4, rshift, half, res_s, res_g);
+            } else {
+                /* a sample of the filtered signal does not fit 16 bits (a loud side channel): int32 signal in the scratch area.
+                 * The entries are dead; every thread keeps its samples in registers across the barrier that retires them. */
+                int32_t *sig = reinterpret_cast<int32_t *>(scratch) + resid_front_pad(p.max_order);
+                const uint32_t lo = resid_front_pad(p.max_order), hi = round_up_u32(n, 4) + 12u;
+                __syncthreads();
+                for (int32_t i = -(int32_t)lo + tid; i < (int32_t)hi; i += kThreads) { sig[i] = cand16_filtered(row0, row1, d, i); }
+                __syncthreads();
+                fir_residual_imad(sig, coef_s, n, order, p4, rshift, half, res_s, res_g);
+            }
+        }
+        if (tid == 0 && have_next) { cp_async_wait_all(); fetch_rows(next_idx, nxt); }   /* phase C: buffer nxt held the previous item's residual */
+        __syncthreads();
+        if (!d.skip) { residual_finish(p, out, res_s, n, scratch, red32, coef_s, p4, order, 0u); }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -1785,11 +2221,11 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     int32_t  *coef_b   = reinterpret_cast<int32_t *>(smem + L.coefb_off);
     uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
     const Job job = p.jobs[job_id];
     const StreamDev st = p.streams[job.stream];
-    const uint32_t n = job.nsmpl, bps = p.bps;
+    const uint32_t n = job.nsmpl;
     const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
     CandOut *out = p.cand + (size_t)job_id * p.ncand + cand;
     if (n <= p.max_order || out->status != 0u) { return; }
@@ -1858,155 +2294,16 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
                                 | (((uint32_t)coef_s[4u * m + 2u] & 0xffu) << 16) | (((uint32_t)coef_s[4u * m + 3u] & 0xffu) << 24));
         }
         __syncthreads();
-        /* ---- FIR residual with IDP.2A, int32 wrapping.  Every group of 8 outputs that reaches past the warm-up (first
-         * output >= order, or straddling it) runs the full padded filter: for an output i >= order the taps that fall in
-         * front of the block carry zero coefficients (order is padded to p4 in FRONT), so they may read anything
-         * addressable.  Warm-up outputs (i < order: first differences, srla_lpc_predict.c:251-254) are patched in
-         * afterwards.  No output is ever computed by a serial loop: one slow thread would hold the whole CTA at the
-         * next barrier. ---- */
-        const uint32_t groups = (n + 7u) >> 3, nm = p4 >> 2;
-        for (uint32_t g = tid; g < groups; g += kThreads) {
-            const uint32_t n0 = g << 3;
-            int32_t a0 = (int32_t)half, a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
-            int4 za, zb;
-            if (order > 0u && n0 + 8u > order) {
-                const uint32_t j0 = zf + (n0 >> 2) - nm;                       /* >= 0: zf covers p4 / 4 entries */
-                za = Z[zpair_slot(j0)]; zb = Z[zpair_slot(j0 + 1u)];
-                for (uint32_t m = 0; m < nm; ++m) {
-                    const int4 zc = Z[zpair_slot(j0 + m + 2u)];
-                    const int32_t cf = coef_b[m];
-                    a0 = __dp2a_lo(za.x, cf, a0); a0 = __dp2a_hi(za.y, cf, a0);
-                    a1 = __dp2a_lo(za.z, cf, a1); a1 = __dp2a_hi(za.w, cf, a1);
-                    a2 = __dp2a_lo(za.y, cf, a2); a2 = __dp2a_hi(zb.x, cf, a2);
-                    a3 = __dp2a_lo(za.w, cf, a3); a3 = __dp2a_hi(zb.z, cf, a3);
-                    a4 = __dp2a_lo(zb.x, cf, a4); a4 = __dp2a_hi(zb.y, cf, a4);
-                    a5 = __dp2a_lo(zb.z, cf, a5); a5 = __dp2a_hi(zb.w, cf, a5);
-                    a6 = __dp2a_lo(zb.y, cf, a6); a6 = __dp2a_hi(zc.x, cf, a6);
-                    a7 = __dp2a_lo(zb.w, cf, a7); a7 = __dp2a_hi(zc.z, cf, a7);
-                    za = zb; zb = zc;
-                }
-            } else {
-                za = Z[zpair_slot(zf + (n0 >> 2))]; zb = Z[zpair_slot(zf + (n0 >> 2) + 1u)];
-            }
-            /* za, zb now hold the entries of samples n0 .. n0+4 and n0+4 .. n0+8: the outputs' own samples */
-            const int32_t x[8] = { (int32_t)(short)(za.x & 0xffff), za.x >> 16, (int32_t)(short)(za.y & 0xffff), za.y >> 16,
-                                   (int32_t)(short)(zb.x & 0xffff), zb.x >> 16, (int32_t)(short)(zb.y & 0xffff), zb.y >> 16 };
-            int32_t r[8];
-            if (order > 0u) {
-                r[0] = (int32_t)((uint32_t)x[0] + (uint32_t)asr32(a0, rshift)); r[1] = (int32_t)((uint32_t)x[1] + (uint32_t)asr32(a1, rshift));
-                r[2] = (int32_t)((uint32_t)x[2] + (uint32_t)asr32(a2, rshift)); r[3] = (int32_t)((uint32_t)x[3] + (uint32_t)asr32(a3, rshift));
-                r[4] = (int32_t)((uint32_t)x[4] + (uint32_t)asr32(a4, rshift)); r[5] = (int32_t)((uint32_t)x[5] + (uint32_t)asr32(a5, rshift));
-                r[6] = (int32_t)((uint32_t)x[6] + (uint32_t)asr32(a6, rshift)); r[7] = (int32_t)((uint32_t)x[7] + (uint32_t)asr32(a7, rshift));
-                if (n0 < order) {
-                    /* warm-up outputs of this group; x[n0 - 1] is the first half of the previous entry's last pair */
-                    const int32_t before = (int32_t)(short)(Z[zpair_slot(zf + (n0 >> 2) - 1u)].w & 0xffff);
-                    #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const uint32_t i = n0 + (uint32_t)t;
-                        if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
-                    }
-                }
-            } else {
-                #pragma unroll
-                for (int t = 0; t < 8; ++t) { r[t] = x[t]; }
-            }
-            *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
-            if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
-            if (n0 + 4u < n) {
-                *reinterpret_cast<int4 *>(res_s + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]);
-                if (res_g) { *reinterpret_cast<int4 *>(res_g + n0 + 4u) = make_int4(r[4], r[5], r[6], r[7]); }
-            }
-        }
+        fir_residual_dp2a(Z, zf, coef_b, n, order, p4, rshift, half, res_s, res_g);
     } else {
         /* ---- the signal does not fit 16 bits (24-bit sources, loud side channels): int32 signal, IMAD filter ---- */
         if (ltp_period == 0u) { apply_preemphasis(region_i, sig, n, pre_coef); }
         __syncthreads();
-        if (order > 0u) {
-            /* same scheme as above: padded filter for every group reaching past the warm-up, warm-up outputs patched in */
-            const uint32_t groups = (n + 3u) >> 2;
-            const int4 *coef4 = reinterpret_cast<const int4 *>(coef_s);
-            for (uint32_t g = tid; g < groups; g += kThreads) {
-                const uint32_t n0 = g << 2;
-                uint32_t a0 = half, a1 = half, a2 = half, a3 = half;
-                const int4 w_self = *reinterpret_cast<const int4 *>(sig + n0);
-                if (n0 + 4u > order) {
-                    const int4 *xp = reinterpret_cast<const int4 *>(sig + n0) - (p4 >> 2);      /* may start in the front padding */
-                    int4 w0 = xp[0];
-                    for (uint32_t m = 0; m < (p4 >> 2); ++m) {
-                        const int4 w1 = xp[m + 1u];
-                        const int4 cf = coef4[m];
-                        a0 += (uint32_t)cf.x * (uint32_t)w0.x + (uint32_t)cf.y * (uint32_t)w0.y + (uint32_t)cf.z * (uint32_t)w0.z + (uint32_t)cf.w * (uint32_t)w0.w;
-                        a1 += (uint32_t)cf.x * (uint32_t)w0.y + (uint32_t)cf.y * (uint32_t)w0.z + (uint32_t)cf.z * (uint32_t)w0.w + (uint32_t)cf.w * (uint32_t)w1.x;
-                        a2 += (uint32_t)cf.x * (uint32_t)w0.z + (uint32_t)cf.y * (uint32_t)w0.w + (uint32_t)cf.z * (uint32_t)w1.x + (uint32_t)cf.w * (uint32_t)w1.y;
-                        a3 += (uint32_t)cf.x * (uint32_t)w0.w + (uint32_t)cf.y * (uint32_t)w1.x + (uint32_t)cf.z * (uint32_t)w1.y + (uint32_t)cf.w * (uint32_t)w1.z;
-                        w0 = w1;
-                    }
-                }
-                int32_t r[4] = { (int32_t)((uint32_t)w_self.x + (uint32_t)asr32((int32_t)a0, rshift)), (int32_t)((uint32_t)w_self.y + (uint32_t)asr32((int32_t)a1, rshift)),
-                                 (int32_t)((uint32_t)w_self.z + (uint32_t)asr32((int32_t)a2, rshift)), (int32_t)((uint32_t)w_self.w + (uint32_t)asr32((int32_t)a3, rshift)) };
-                if (n0 < order) {
-                    const int32_t x[4] = { w_self.x, w_self.y, w_self.z, w_self.w };
-                    const int32_t before = sig[n0 ? n0 - 1u : 0u];
-                    #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const uint32_t i = n0 + (uint32_t)t;
-                        if (i < order) { r[t] = (i == 0u) ? x[0] : (int32_t)((uint32_t)x[t] - (uint32_t)(t ? x[t - 1] : before)); }
-                    }
-                }
-                *reinterpret_cast<int4 *>(res_s + n0) = make_int4(r[0], r[1], r[2], r[3]);
-                if (res_g) { *reinterpret_cast<int4 *>(res_g + n0) = make_int4(r[0], r[1], r[2], r[3]); }
-            }
-        } else {
-            for (uint32_t i = tid; i < n; i += kThreads) { const int32_t v = sig[i]; res_s[i] = v; if (res_g) { res_g[i] = v; } }
-        }
+        fir_residual_imad(sig, coef_s, n, order, p4, rshift, half, res_s, res_g);
     }
     __syncthreads();
 
-    /* ---- residual coder search (srla_coder.c:349-483) ---- */
-    RiceResult rr;
-    switch (n) {
-        case 1024u: rr = rice_search_fast<1>(res_s, scratch, red32, out, p.rice_threshold); break;
-        case 2048u: rr = rice_search_fast<2>(res_s, scratch, red32, out, p.rice_threshold); break;
-        case 3072u: rr = rice_search_fast<3>(res_s, scratch, red32, out, p.rice_threshold); break;
-        case 4096u: rr = rice_search_fast<4>(res_s, scratch, red32, out, p.rice_threshold); break;
-        case 8192u: rr = rice_search_fast<8>(res_s, scratch, red32, out, p.rice_threshold); break;
-        default:    rr = rice_search_general(res_s, n, scratch, red32, out, p.rice_threshold); break;
-    }
-    const uint32_t code_type = rr.code_type, best_porder = rr.porder, residual_bits = rr.bits;
-
-    /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */
-    if (tid < 32) {
-        uint32_t plain_bits = 0, sum_bits = 0, bad = 0;
-        const int32_t *cf = coef_s + (p4 - order);
-        for (uint32_t i = lane; i < order; i += 32) {
-            const int32_t c = cf[i];
-            const uint32_t len = __ldg(p.huff_len + zigzag32(c));
-            plain_bits += len;
-            if (i == 0u) { sum_bits += len; }
-            else {
-                const uint32_t sym = zigzag32(c + cf[i - 1u]);
-                if (sym >= 256u) { bad = 1; } else { sum_bits += __ldg(p.huff_len + 256 + sym); }
-            }
-        }
-        plain_bits = warp_sum_u32(plain_bits); sum_bits = warp_sum_u32(sum_bits); bad = warp_sum_u32(bad);
-        if (lane == 0) {
-            uint32_t use_sum = 0, coef_bits = 0;
-            if (order > 0u) {
-                /* the reference's early exits are equivalent to: every symbol valid and the summed form strictly shorter */
-                use_sum = (!bad && (order == 1u || sum_bits < plain_bits)) ? 1u : 0u;
-                coef_bits = use_sum ? sum_bits : plain_bits;
-            }
-            uint32_t bits = residual_bits;
-            bits += bps + 1u + 5u;
-            bits += 8u + 4u + 1u;
-            bits += coef_bits;
-            bits += 1u;
-            if (ltp_period > 0u) { bits += 1u + 8u + p.ltp_order * 6u; }
-            out->use_sum = use_sum; out->coef_bits = coef_bits;
-            out->code_type = code_type; out->porder = best_porder;
-            out->residual_bits = residual_bits; out->total_bits = bits;
-        }
-    }
+    residual_finish(p, out, res_s, n, scratch, red32, coef_s, p4, order, ltp_period);
 }
 
 /* ------------------------------------------------------------------------------------------------

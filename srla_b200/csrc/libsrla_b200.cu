@@ -174,6 +174,7 @@ struct DeviceCtx {
     bool jobs_cached = false;
     int max_smem_optin = 0;
     int num_sms = 0;
+    int resid16 = 1;               /* SRLA_B200_RESID16=0: the one-CTA-per-candidate residual kernel for 16-bit PCM as well (tuning / A-B) */
     int front_occ = 3;             /* CTAs per SM front_kernel<128> is register-sized for (SRLA_B200_FRONT_OCC=3|4, tuning) */
 };
 
@@ -244,6 +245,7 @@ bool ctx_init(DeviceCtx *c)
     c->feed_threads = (int)std::max(2u, std::min(16u, usable_cpus()));
     if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->feed_threads = v; } }
     if (const char *e = std::getenv("SRLA_B200_TRACE")) { c->trace = std::atoi(e); }
+    if (const char *e = std::getenv("SRLA_B200_RESID16")) { c->resid16 = std::atoi(e); }
     if (const char *e = std::getenv("SRLA_B200_SPLIT_DEVICE")) { c->split_device = std::atoi(e); }
     if (const char *e = std::getenv("SRLA_B200_GROUPS")) { const int v = std::atoi(e); if (v >= 1 && v <= 64) { c->groups = v; } }
     CU_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -546,7 +548,8 @@ struct Runner {
 
     /* the three analysis kernels: front (autocorrelation) -> lpc (Levinson-Durbin) -> residual (FIR + Rice search) */
     /* tails [tail_lo, tail_hi) of c->tails_scratch lie in this launch's jobs, which start at index group_first of c->jobs */
-    bool launch_analyse(const LaunchParams &p, size_t batch, cudaStream_t on, size_t tail_lo = 0, size_t tail_hi = 0, uint32_t group_first = 0)
+    bool launch_analyse(const LaunchParams &p, size_t batch, cudaStream_t on, size_t tail_lo = 0, size_t tail_hi = 0, uint32_t group_first = 0,
+                        bool pcm16_only = false)
     {
         const FrontLayout FL = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
         const LpcLayout LL = make_lpc_layout(p.max_order);
@@ -617,8 +620,16 @@ struct Runner {
             }
         }
         if (!mark(batch, 2, on)) { return false; }
-        if (!prep_kernel(residual_kernel, RL.total)) { return false; }
-        residual_kernel<<<grid, block, RL.total, on>>>(p);
+        if (p.ltp_order == 0u && pcm16_only && c->resid16) {
+            /* 16-bit PCM without LTP: persistent CTAs, source rows staged one item ahead by bulk asynchronous copies */
+            const Resid16Layout R16 = make_resid16_layout(p.nmax, p.max_order);
+            if (!prep_kernel(residual16_kernel, R16.total)) { return false; }
+            const uint32_t per_sm = std::max(1u, std::min(4u, (uint32_t)(227u * 1024u) / (R16.total + 1024u)));
+            residual16_kernel<<<std::min(ncands, (uint32_t)c->num_sms * per_sm), block, R16.total, on>>>(p);
+        } else {
+            if (!prep_kernel(residual_kernel, RL.total)) { return false; }
+            residual_kernel<<<grid, block, RL.total, on>>>(p);
+        }
         launches++;
         CU_TRY(cudaGetLastError());
         return true;
@@ -693,7 +704,9 @@ struct Runner {
             tail_lo = std::lower_bound(tv.begin(), tv.end(), group_first, [](const TailJob &t, uint32_t v) { return t.job < v; }) - tv.begin();
             tail_hi = std::lower_bound(tv.begin(), tv.end(), group_first + count, [](const TailJob &t, uint32_t v) { return t.job < v; }) - tv.begin();
         }
-        if (!launch_analyse(p, ev_idx, on, tail_lo, tail_hi, group_first)) { return false; }
+        bool pcm16_only = true;
+        for (uint32_t s = 0; s < pl.num_streams && pcm16_only; s++) { pcm16_only = pl.streams[s].sample_bytes == 2u; }
+        if (!launch_analyse(p, ev_idx, on, tail_lo, tail_hi, group_first, pcm16_only)) { return false; }
         if (!mark(ev_idx, 3, on)) { return false; }
         decide_kernel<<<(count + 127) / 128, 128, 0, on>>>(p);
         launches++;

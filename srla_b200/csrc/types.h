@@ -221,5 +221,39 @@ SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
     return L;
 }
 
+/* residual16_kernel (persistent CTAs, 16-bit PCM staged by bulk asynchronous copies): two buffers that hold the int16 source
+ * rows of the NEXT candidate while the int32 residual of the current one lives where its own rows were, the pair entries /
+ * int32 signal / mean pyramid scratch, coefficients, reduction scratch, the two item descriptors and their mbarriers */
+struct Resid16Layout {
+    uint32_t buf_off[2], buf_bytes, row_bytes;
+    uint32_t scratch_off, coef_off, coefb_off, red_off, desc_off, stage_off, bar_off, total;
+};
+SRLA_HD inline Resid16Layout make_resid16_layout(uint32_t nmax, uint32_t P)
+{
+    Resid16Layout L;
+    const uint32_t n8 = round_up_u32(nmax, 8);
+    const uint32_t parts = (nmax < (uint32_t)kMaxParts) ? nmax : (uint32_t)kMaxParts;
+    const uint32_t pyramid = 16u * round_up_u32(parts, 2) + 16u;
+    const uint32_t pairs = 4u * n8 + 32u + 16u * resid_pair_front(P);
+    const uint32_t sigbytes = 4u * (n8 + 12u + resid_front_pad(P));
+    uint32_t scratch = (pyramid > pairs) ? pyramid : pairs;
+    if (sigbytes > scratch) { scratch = sigbytes; }
+    if (scratch < 4096u) { scratch = 4096u; }
+    L.row_bytes = round_up_u32(2u * n8 + 16u, 16);
+    L.buf_bytes = round_up_u32((4u * n8 > 2u * L.row_bytes) ? 4u * n8 : 2u * L.row_bytes, 128);
+    uint32_t off = 0;
+    L.buf_off[0] = off; off += L.buf_bytes;
+    L.buf_off[1] = off; off += L.buf_bytes;
+    L.scratch_off = off; off += round_up_u32(scratch, 16);
+    L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
+    L.coefb_off = off; off += round_up_u32(4u * (round_up_u32(P, 4) / 4u + 4u), 16);
+    L.red_off = off; off += 1024u;
+    L.desc_off = off;
+    L.stage_off = off; off += 2u * 128u;           /* two slots: job head (16) + candidate record head (64) + stream (48), fetched with cp.async */
+    L.bar_off = off; off += 16u;
+    L.total = off;
+    return L;
+}
+
 } // namespace srla
 #endif
