@@ -1003,11 +1003,13 @@ __device__ void front_chain_step(const LaunchParams &p, const Job &job, const St
 
 template <int kT, bool kLtp>
 __global__ void __launch_bounds__(kT) front_tail_kernel(const __grid_constant__ LaunchParams p, const TailJob *tails, const Job *jobs_all,
-                                                        const uint32_t group_first, const uint32_t pbuf_len)
+                                                        const uint32_t group_first, const uint32_t pbuf_len, double *pbuf_global)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const FrontLayout L = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
-    double *pbuf = reinterpret_cast<double *>(smem + L.total);
+    /* the scratch-buffer replica lives behind the kernel's own shared memory, or -- for block sizes whose transform already
+     * fills it -- in global memory (pbuf_len + 272 doubles per CTA) */
+    double *pbuf = pbuf_global ? pbuf_global + (size_t)blockIdx.x * (pbuf_len + 272u) : reinterpret_cast<double *>(smem + L.total);
     __shared__ unsigned long long red64[2 * (kT / 32)];
     __shared__ int32_t  sh_i[8];
     __shared__ uint32_t sh_u[8];

@@ -169,7 +169,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> ev_h2d, ev_grp, ev_d2h;
     std::vector<Job> jobs_scratch;
     std::vector<TailJob> tails_scratch;   /* tail blocks of the fixed tiling that need front_tail_kernel (odd, or short with LTP) */
-    DevBuf tails;
+    DevBuf tails, tail_scratch;
     std::vector<uint32_t> jobs_key;   /* stream lengths + block size of the fixed tiling that jobs_scratch and the device copy hold */
     bool jobs_cached = false;
     int max_smem_optin = 0;
@@ -306,7 +306,7 @@ void ctx_destroy(DeviceCtx *c)
     if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
     if (c->ev_upload) { cudaEventDestroy(c->ev_upload); }
-    DevBuf *bufs[] = { &c->tails, &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
+    DevBuf *bufs[] = { &c->tails, &c->tail_scratch, &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
                        &c->misc, &c->stream_begin, &c->pcm, &c->out, &c->raw };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release(); c->h_stage_out.release();
@@ -584,6 +584,15 @@ struct Runner {
                 if (!prep_kernel(front_kernel<256, 2, false>, FL.total, 2)) { return false; }
                 front_kernel<256, 2, false><<<grid, 256, FL.total, on>>>(p);
             }
+        } else if (p.fft_max <= 16384u) {
+            /* one CTA of 512 threads per SM: the transform (128 KB) and the signal (64 KB) fill its shared memory */
+            if (ltp) {
+                if (!prep_kernel(front_kernel<512, 1, true>, FL.total, 1)) { return false; }
+                front_kernel<512, 1, true><<<grid, 512, FL.total, on>>>(p);
+            } else {
+                if (!prep_kernel(front_kernel<512, 1, false>, FL.total, 1)) { return false; }
+                front_kernel<512, 1, false><<<grid, 512, FL.total, on>>>(p);
+            }
         } else {
             std::fprintf(stderr, "[srla_b200] block of %u samples exceeds the pipeline capacity (%d)\n", p.nmax, kMaxBlock);
             return false;
@@ -592,16 +601,27 @@ struct Runner {
         if (tail_hi > tail_lo) {
             /* the reference's stale-scratch corners on the last block of a stream (see front_tail_kernel) */
             const uint32_t pbuf_len = std::max(p.fft_max, 512u);
-            const uint32_t smem_tail = FL.total + 8u * (pbuf_len + 272u);
-            if ((int)smem_tail + 1024 > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] tail block replay needs %u bytes of shared memory\n", smem_tail); return false; }
+            const uint32_t pbuf_bytes = 8u * (pbuf_len + 272u);
             const TailJob *d_tails = (const TailJob *)c->tails.p + tail_lo;
             const uint32_t nt = (uint32_t)(tail_hi - tail_lo);
+            /* the replica of the reference's scratch buffer sits behind the kernel's shared memory when it fits, else in global memory */
+            const bool in_smem = (int)(FL.total + pbuf_bytes) + 1024 <= c->max_smem_optin;
+            const uint32_t smem_tail = in_smem ? FL.total + pbuf_bytes : FL.total;
+            double *pbuf_global = nullptr;
+            if (!in_smem) {
+                if (!c->tail_scratch.reserve((size_t)nt * pbuf_bytes)) { return false; }
+                pbuf_global = (double *)c->tail_scratch.p;
+            }
+            const Job *all = (const Job *)c->jobs.p;
             if (p.fft_max <= 4096u) {
-                if (ltp) { if (!prep_kernel(front_tail_kernel<128, true>, smem_tail)) { return false; } front_tail_kernel<128, true><<<nt, 128, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
-                else { if (!prep_kernel(front_tail_kernel<128, false>, smem_tail)) { return false; } front_tail_kernel<128, false><<<nt, 128, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
+                if (ltp) { if (!prep_kernel(front_tail_kernel<128, true>, smem_tail)) { return false; } front_tail_kernel<128, true><<<nt, 128, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
+                else { if (!prep_kernel(front_tail_kernel<128, false>, smem_tail)) { return false; } front_tail_kernel<128, false><<<nt, 128, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
+            } else if (p.fft_max <= 8192u) {
+                if (ltp) { if (!prep_kernel(front_tail_kernel<256, true>, smem_tail)) { return false; } front_tail_kernel<256, true><<<nt, 256, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
+                else { if (!prep_kernel(front_tail_kernel<256, false>, smem_tail)) { return false; } front_tail_kernel<256, false><<<nt, 256, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
             } else {
-                if (ltp) { if (!prep_kernel(front_tail_kernel<256, true>, smem_tail)) { return false; } front_tail_kernel<256, true><<<nt, 256, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
-                else { if (!prep_kernel(front_tail_kernel<256, false>, smem_tail)) { return false; } front_tail_kernel<256, false><<<nt, 256, smem_tail, on>>>(p, d_tails, (const Job *)c->jobs.p, group_first, pbuf_len); }
+                if (ltp) { if (!prep_kernel(front_tail_kernel<512, true>, smem_tail)) { return false; } front_tail_kernel<512, true><<<nt, 512, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
+                else { if (!prep_kernel(front_tail_kernel<512, false>, smem_tail)) { return false; } front_tail_kernel<512, false><<<nt, 512, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
             }
             launches++;
         }

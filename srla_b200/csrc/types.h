@@ -18,7 +18,7 @@ constexpr int kWarps          = kThreads / 32;
 constexpr int kMaxOrder       = 255;   /* SRLA_MAX_COEFFICIENT_ORDER                           */
 constexpr int kMaxChannels    = 8;
 constexpr int kMaxCand        = kMaxChannels + 2;
-constexpr int kMaxBlock       = 8192;  /* capacity of the shared-memory resident pipeline       */
+constexpr int kMaxBlock       = 16384; /* capacity of the shared-memory resident pipeline       */
 constexpr int kLog2MaxParts   = 10;    /* srla_coder.c:18                                       */
 constexpr int kMaxParts       = 1 << kLog2MaxParts;
 constexpr int kLtpMinPeriod   = 8;     /* srla_internal.h:31-35                                 */

@@ -63,6 +63,10 @@ def main():
     save("ltp_short_tail_4196_m4_b4096", synth_stereo(4196, seed=74), preset=4, max_block=4096, ltp=3)
     save("ltp_short_tail_odd_8391_m4_b4096", synth_stereo(8391, seed=75), preset=4, max_block=4096, ltp=3)
     save("odd9001_m4_v2_l4", synth_stereo(9001, seed=76), preset=4, max_block=4096, min_block=1024, lookahead=16384)
+    # blocks beyond 8192 samples (the reference CLI admits -B up to 65535; this implementation up to 16384)
+    save("stereo16_m4_b16384", synth_stereo(16384 * 2 + 5001, seed=79), preset=4, max_block=16384)
+    save("stereo24_m3_b16384_ltp3", synth_stereo(16384 + 9000, seed=80, bits=24), bps=24, preset=3, max_block=16384, ltp=3)
+    save("mono16_m5_b12000", synth_stereo(12000 * 2 + 100, seed=81)[:1], preset=5, max_block=12000)
     save("odd_after_silence_m4_b4096", np.concatenate([synth_stereo(4096, seed=77), np.zeros((2, 4096), dtype=np.int32),
                                                        synth_stereo(1001, seed=78)], axis=1), preset=4, max_block=4096)
 
