@@ -101,7 +101,8 @@ int32_t SRLAEncoder_CalculateWorkSize(const struct SRLAEncoderConfig *config);
 /* include/srla_encoder.h:50 (srla_encoder.c:549-694): (work == NULL && work_size == 0) => the
  * handle allocates for itself and Destroy frees; otherwise the caller owns `work`.
  * NULL on bad arguments, short work area, or when no CUDA device is usable.
- * Capacity limit of this implementation: max_num_samples_per_block <= 16384 (the reference's CLI admits 65535). */
+ * Capacity limit of this implementation: max_num_samples_per_block <= 65535 (the block header's 16-bit sample count; blocks beyond 16384 samples
+ * work in global memory instead of shared memory; SVR refinement is limited to 16384). */
 struct SRLAEncoder *SRLAEncoder_Create(const struct SRLAEncoderConfig *config, void *work, int32_t work_size);
 
 /* include/srla_encoder.h:53 (srla_encoder.c:697-707) */

@@ -1048,6 +1048,231 @@ __global__ void __launch_bounds__(kT) front_tail_kernel(const __grid_constant__ 
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * front_big_kernel: blocks of more than kMaxSharedBlock samples (the format's block header carries up to 65535,
+ * srla_encoder.c:1593; the reference CLI admits -B < 65536, srla_codec.c:354).  Their transform does not fit an SM's
+ * shared memory, so one CTA works on a job in global memory (the working set of the resident CTAs stays in L2): the
+ * reference's own loop structure -- radix-4 Stockham stages ping-ponging between two buffers, one radix-2 stage at the
+ * end (fft.c:71-128), the real-transform split (fft.c:147-198) -- with the butterflies of a stage spread over the threads.
+ * Every butterfly is the expression tree front_kernel evaluates (butterfly4, the host-tabulated twiddle recurrence), the
+ * inverse transform again runs as the conjugate of a forward transform of conjugated data, so the lags are bit-identical.
+ * A CTA takes a whole job and analyses its candidates in the reference's order with `pbuf` standing in for the LPC
+ * calculator's scratch buffer, exactly like front_tail_kernel; the stale middle sample / stale lags are only USED for the
+ * jobs front_tail_kernel would replay (chain == true), so both paths deviate from the reference in the same documented
+ * places and nowhere else.
+ * ---------------------------------------------------------------------------------------------- */
+/* forward complex FFT of M points, natural order, out of place between x and y; returns the buffer holding the result */
+__device__ double2 *fft_stockham_global(double2 *x, double2 *y, const uint32_t M, const LaunchParams &p)
+{
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    uint32_t n = M, lgs = 0;
+    while (n > 2u) {
+        const uint32_t n1 = n >> 2, lgn = 31u - (uint32_t)__clz((int)n);
+        const double2 *tw = p.tw_complex + p.tw_complex_off[lgn];
+        const uint32_t s = 1u << lgs, count = n1 << lgs;
+        for (uint32_t b = tid; b < count; b += T) {
+            const uint32_t pp = b >> lgs, q = b & (s - 1u);
+            const Twiddle3 w = load_twiddle(tw, n1, pp);
+            double2 y0, y1, y2, y3;
+            butterfly4(x[q + ((pp) << lgs)], x[q + ((pp + n1) << lgs)], x[q + ((pp + 2u * n1) << lgs)], x[q + ((pp + 3u * n1) << lgs)], w, y0, y1, y2, y3);
+            double2 *o = y + q + ((4u * pp) << lgs);
+            o[0] = y0; o[s] = y1; o[2u * s] = y2; o[3u * s] = y3;
+        }
+        __syncthreads();
+        n >>= 2; lgs += 2;
+        double2 *t = x; x = y; y = t;
+    }
+    if (n == 2u) {
+        const uint32_t s = 1u << lgs;
+        for (uint32_t q = tid; q < s; q += T) { const double2 a = x[q], b = x[q + s]; y[q] = cadd(a, b); y[q + s] = csub(a, b); }
+        __syncthreads();
+        double2 *t = x; x = y; y = t;
+    }
+    return x;
+}
+
+/* Welch window + FFT autocorrelation of sig[0..n) (global memory), lags[0..nlags) out; kPre as in welch_autocorr.
+ * pbuf: natural-order replica of the reference's scratch buffer (always updated); `chain`: its stale contents are used
+ * (odd middle sample, lags beyond the transform) */
+template <bool kPre>
+__device__ void welch_autocorr_big(const int32_t *sig, const int32_t pre_coef, const uint32_t n, double2 *bufa, double2 *bufb, double *lags, const uint32_t lag_step,
+                                   const uint32_t nlags, const Job &job, const LaunchParams &p, double *pbuf, const bool chain)
+{
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const uint32_t N = ceil_pow2_u32(n), M = N >> 1;
+    WindowSource<kPre, true> ws;
+    ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = (uint32_t)pre_coef; ws.unit = 1.0; ws.div = job.welch_div * p.unit; ws.dn1 = (double)(int32_t)(n - 1u);
+    ws.full = false;
+    /* without the chain an odd block's middle sample is windowed like every other one (front_kernel's behaviour) */
+    {
+        const uint32_t mid = n >> 1;
+        double stale = pbuf[mid];
+        if (!chain && (n & 1u)) {
+            const int32_t cur = sig[mid], prv = sig[mid ? mid - 1u : 0u];
+            const int32_t x = kPre ? (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * ws.pc) >> 4)) : cur;
+            const double ds = int_to_double((int32_t)mid);
+            stale = int_to_double(x) * (ws.div * ds * (ws.dn1 - ds));
+        }
+        ws.stale = stale;
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < M; e += T) { bufa[e] = ws.element(e); }
+    __syncthreads();
+    double2 *cx = fft_stockham_global(bufa, bufb, M, p);
+    double2 *other = (cx == bufa) ? bufb : bufa;
+    /* forward split, power spectrum, inverse split (stored conjugated): see welch_autocorr */
+    {
+        const uint32_t lgN = 31u - (uint32_t)__clz((int)N);
+        const double2 *tw = p.tw_real + p.tw_real_off[lgN];
+        const uint32_t quarter = N >> 2;
+        for (uint32_t i = 1u + tid; i <= quarter; i += T) {
+            const double2 w = __ldg(tw + (i - 1u));
+            const double wr = w.x, wi_f = w.y, wi_b = -w.y;
+            const uint32_t lo = i, hi = M - i;
+            const double2 xl = cx[lo], xh = cx[hi];
+            const double c2 = -0.5;
+            const double h1r = 0.5 * (xl.x + xh.x), h1i = 0.5 * (xl.y - xh.y), h2r = -c2 * (xl.y + xh.y), h2i = c2 * (xl.x - xh.x);
+            const double f1 = h1r + (wr * h2r) - (wi_f * h2i), f2 = h1i + (wr * h2i) + (wi_f * h2r);
+            const double f3 = h1r - (wr * h2r) + (wi_f * h2i), f4 = -h1i + (wr * h2i) + (wi_f * h2r);
+            double p_lo, p_hi;
+            if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; } else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
+            const double g1r = 0.5 * (p_lo + p_hi), g2i = 0.5 * (p_lo - p_hi);
+            const double t = wi_b * g2i, g2 = wr * g2i;
+            if (lo != hi) { cx[lo] = make_double2(g1r - t, -g2); }
+            cx[hi] = make_double2(g1r + t, -g2);
+        }
+        if (tid == 0) {
+            const double2 dc = cx[0];
+            const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;
+            const double q0 = f0 * f0, q1 = f1 * f1;
+            cx[0] = make_double2(0.5 * (q0 + q1), -(0.5 * (q0 - q1)));
+        }
+        __syncthreads();
+    }
+    double2 *res = fft_stockham_global(cx, other, M, p);
+    for (uint32_t e = tid; e < M; e += T) { const double2 v = res[e]; pbuf[2u * e] = v.x; pbuf[2u * e + 1u] = -v.y; }
+    __syncthreads();
+    const double scale = job.ac_scale;
+    for (uint32_t i = tid; i < nlags; i += T) { lags[(size_t)i * lag_step] = (chain || i < N) ? pbuf[i] * scale : 0.0; }
+    __syncthreads();
+}
+
+template <bool kLtp>
+__global__ void __launch_bounds__(1024) front_big_kernel(const __grid_constant__ LaunchParams p)
+{
+    constexpr int kT = 1024;
+    const FrontBigLayout L = make_front_big_layout(p.nmax, p.fft_max);
+    unsigned char *base = p.big_scratch + (size_t)blockIdx.x * p.big_stride;
+    int32_t *raw = reinterpret_cast<int32_t *>(base + L.raw_off) + 8;
+    int32_t *sig = reinterpret_cast<int32_t *>(base + L.sig_off) + 8;
+    double2 *bufa = reinterpret_cast<double2 *>(base + L.a_off), *bufb = reinterpret_cast<double2 *>(base + L.b_off);
+    double *pbuf = reinterpret_cast<double *>(base + L.pbuf_off);
+    double *lags = reinterpret_cast<double *>(base + L.lags_off);
+    __shared__ unsigned long long red64[2 * (kT / 32)];
+    __shared__ int32_t  sh_i[8];
+    __shared__ uint32_t sh_u[8];
+    __shared__ CandOut scratch_out;
+    const int tid = threadIdx.x;
+    const uint32_t P = p.max_order, pbuf_len = p.fft_max + 272u;
+
+    /* one candidate of one job, chain semantics as in front_chain_step */
+    auto step = [&](const Job &job, const StreamDev &st, uint32_t cand, uint32_t lshift, CandOut *out, double *g, uint32_t gstep, bool chain) {
+        const uint32_t n = job.nsmpl;
+        __syncthreads();
+        int nz = load_candidate<4>(st, job, p, cand, lshift, raw);
+        nz = __syncthreads_or(nz);
+        if (tid == 0) {
+            out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
+            out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
+            out->total_bits = 0; out->residual_bits = 0; out->pre_coef = 0; out->pre_prev = 0;
+        }
+        const int32_t pre_coef = preemphasis_coefficient<kT>(raw, n, out, red64, &sh_i[0]);
+        if (!kLtp) {
+            if (P > 0u) { welch_autocorr_big<true>(raw, pre_coef, n, bufa, bufb, g, gstep, P + 1u, job, p, pbuf, chain); }
+            return;
+        }
+        apply_preemphasis(raw, sig, n, pre_coef);
+        __syncthreads();
+        welch_autocorr_big<false>(sig, 0, n, bufa, bufb, lags, 1u, kLtpMaxPeriod + 1u, job, p, pbuf, chain);
+        if (tid == 0) {
+            for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
+            uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
+            const int rc = ltp_solve(lags, p.ltp_order, &period, q);
+            sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
+            out->status = (uint32_t)rc;
+            if (!rc && period > 0u) { out->ltp_period = period; out->ltp_coef[0] = q[0]; out->ltp_coef[1] = q[1]; out->ltp_coef[2] = q[2]; }
+        }
+        __syncthreads();
+        if (sh_u[1]) { return; }
+        if (sh_u[0] > 0u) { apply_ltp(sig, raw, n, p.ltp_order, sh_u[0], sh_i[1], sh_i[2], sh_i[3]); }
+        if (P > 0u) { welch_autocorr_big<false>(sig, 0, n, bufa, bufb, g, gstep, P + 1u, job, p, pbuf, chain); }
+    };
+
+    /* candidates of a block the reference makes no call for (RAW: not more samples than the order; SILENT): only the
+     * non-zero flags decide_kernel reads */
+    auto flags_only = [&](const Job &job, const StreamDev &st, uint32_t lshift, uint32_t j) {
+        for (uint32_t cand = 0; cand < p.ncand; ++cand) {
+            int nz = load_candidate<4>(st, job, p, cand, lshift, raw);
+            nz = __syncthreads_or(nz);
+            if (tid == 0) { CandOut *o = p.cand + (size_t)j * p.ncand + cand; o->nonzero = (nz != 0); o->status = 0; o->order = 0; o->rshift = 0; o->ltp_period = 0; o->total_bits = 0; o->residual_bits = 0; o->pre_coef = 0; o->pre_prev = 0; }
+            __syncthreads();
+        }
+    };
+    auto block_is_silent = [&](const Job &job, const StreamDev &st) {
+        int nz = 0;
+        for (uint32_t ch = 0; ch < p.nch; ++ch) { for (uint32_t i = tid; i < job.nsmpl; i += kT) { nz |= load_sample(st, ch, job.offset + i); } }
+        return __syncthreads_or(nz) == 0;
+    };
+
+    if (p.serial_streams) {
+        /* ODD block size: every block's window keeps a sample of the previous call (lpc.c:260-264), so the calls of a
+         * stream form one chain from its first block to its last.  A CTA walks a stream's blocks in order with `pbuf`
+         * never reset in between -- the reference's calculator, replayed call for call; streams run side by side. */
+        uint32_t owner = 0xffffffffu, seen = 0;
+        for (uint32_t j = 0; j < p.num_jobs; ++j) {
+            const Job job = p.jobs[j];
+            if (job.flags & kJobFirstOfStream) { owner = seen % gridDim.x; seen++; }
+            if (owner != blockIdx.x) { continue; }
+            const StreamDev st = p.streams[job.stream];
+            const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+            __syncthreads();
+            if (job.flags & kJobFirstOfStream) { for (uint32_t i = tid; i < pbuf_len; i += kT) { pbuf[i] = 0.0; } }
+            if (job.nsmpl <= P || block_is_silent(job, st)) { flags_only(job, st, lshift, j); continue; }
+            for (uint32_t cand = 0; cand < p.ncand; ++cand) {
+                const uint32_t idx = j * p.ncand + cand;
+                double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);
+                step(job, st, cand, lshift, p.cand + idx, g, 32u, true);
+            }
+        }
+        return;
+    }
+    for (uint32_t j = blockIdx.x; j < p.num_jobs; j += gridDim.x) {
+        const Job job = p.jobs[j];
+        const StreamDev st = p.streams[job.stream];
+        const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+        const uint32_t n = job.nsmpl;
+        __syncthreads();
+        if (n <= P) { flags_only(job, st, lshift, j); continue; }
+        for (uint32_t i = tid; i < pbuf_len; i += kT) { pbuf[i] = 0.0; }
+        /* with fixed blocks only a stream's last block can be odd or that short (the block size itself is even and >= 263) */
+        const bool chain = p.replay_tails && ((n & 1u) || (kLtp && ceil_pow2_u32(n) < 263u));
+        if (chain) {
+            uint32_t pred = p.group_first + j; bool found = false;
+            while (!found && !(p.jobs_all[pred].flags & kJobFirstOfStream)) {
+                pred--;
+                const Job pj = p.jobs_all[pred];
+                found = (pj.nsmpl > P) && !block_is_silent(pj, st);
+            }
+            if (found) { const Job pj = p.jobs_all[pred]; step(pj, st, p.ncand - 1u, lshift, &scratch_out, pbuf + p.fft_max, 1u, true); }     /* lags into pbuf's tail: a dump area */
+        }
+        for (uint32_t cand = 0; cand < p.ncand; ++cand) {
+            const uint32_t idx = j * p.ncand + cand;
+            double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);
+            step(job, st, cand, lshift, p.cand + idx, g, 32u, chain);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * lpc_kernel: one THREAD per candidate (32 candidates per CTA).  Ridge, Levinson-Durbin for all
  * orders, order choice, coefficient quantisation (lpc.c:379-441, 483-493, 1341-1405;
  * srla_encoder.c:934-957, 1104-1108).
@@ -2213,9 +2438,10 @@ __global__ void __launch_bounds__(kThreads, 4) residual16_kernel(const __grid_co
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_constant__ LaunchParams p)
+/* kBig: blocks beyond the shared-memory capacity -- the same code on a per-CTA scratch area in global memory, persistent CTAs */
+template <bool kBig>
+__device__ __forceinline__ void residual_item(const LaunchParams &p, unsigned char *smem, const uint32_t item)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
     const ResidLayout L = make_resid_layout(p.nmax, p.max_order);
     int32_t  *region_i = reinterpret_cast<int32_t *>(smem + L.region_off);
     int32_t  *sig      = reinterpret_cast<int32_t *>(smem + L.sig_off) + resid_front_pad(p.max_order);
@@ -2224,7 +2450,7 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     uint32_t *red32    = reinterpret_cast<uint32_t *>(smem + L.red_off);
 
     const int tid = threadIdx.x;
-    const uint32_t job_id = blockIdx.x / p.ncand, cand = blockIdx.x % p.ncand;
+    const uint32_t job_id = item / p.ncand, cand = item % p.ncand;
     const Job job = p.jobs[job_id];
     const StreamDev st = p.streams[job.stream];
     const uint32_t n = job.nsmpl;
@@ -2306,6 +2532,22 @@ __global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_cons
     __syncthreads();
 
     residual_finish(p, out, res_s, n, scratch, red32, coef_s, p4, order, ltp_period);
+}
+
+__global__ void __launch_bounds__(kThreads, 4) residual_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    residual_item<false>(p, smem, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kThreads, 4) residual_big_kernel(const __grid_constant__ LaunchParams p)
+{
+    unsigned char *scratch = p.big_scratch + (size_t)blockIdx.x * p.big_stride;
+    const uint32_t total = p.num_jobs * p.ncand;
+    for (uint32_t item = blockIdx.x; item < total; item += gridDim.x) {
+        residual_item<true>(p, scratch, item);
+        __syncthreads();
+    }
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -2483,14 +2725,10 @@ __device__ __forceinline__ uint32_t emit_code(BitCursor &bc, uint32_t pos, uint3
     return q + 1u + k;
 }
 
-__global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ LaunchParams p)
+/* one block; `words`: the staging area (shared memory, or -- blocks beyond its capacity -- a per-CTA area in global memory) */
+__device__ __forceinline__ void emit_block(const LaunchParams &p, uint32_t *words, const uint32_t j, uint32_t *scan_scratch, uint32_t *fl_lo, uint32_t *fl_hi)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *words = reinterpret_cast<uint32_t *>(smem);
-    __shared__ uint32_t scan_scratch[kWarps + 1];
-    __shared__ uint32_t fl_lo[kWarps], fl_hi[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t j = blockIdx.x;
     const Job job = p.jobs[j];
     const JobOut jo = p.jobout[j];
     const StreamDev st = p.streams[job.stream];
@@ -2761,6 +2999,26 @@ __global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ 
             const CandOut *cands = p.cand + (size_t)j * p.ncand;
             for (uint32_t ch = 0; ch < nch; ++ch) { atomicAdd(p.stats + (cands[jo.cand_of_channel[ch]].order & 255u), 1u); }
         }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) emit_kernel(const __grid_constant__ LaunchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t scan_scratch[kWarps + 1];
+    __shared__ uint32_t fl_lo[kWarps], fl_hi[kWarps];
+    emit_block(p, reinterpret_cast<uint32_t *>(smem), blockIdx.x, scan_scratch, fl_lo, fl_hi);
+}
+
+/* blocks whose encoded size exceeds the shared memory of an SM: persistent CTAs, staging area in global memory */
+__global__ void __launch_bounds__(kThreads) emit_big_kernel(const __grid_constant__ LaunchParams p)
+{
+    __shared__ uint32_t scan_scratch[kWarps + 1];
+    __shared__ uint32_t fl_lo[kWarps], fl_hi[kWarps];
+    uint32_t *words = reinterpret_cast<uint32_t *>(p.big_scratch + (size_t)blockIdx.x * p.big_stride);
+    for (uint32_t j = blockIdx.x; j < p.num_jobs; j += gridDim.x) {
+        emit_block(p, words, j, scan_scratch, fl_lo, fl_hi);
+        __syncthreads();
     }
 }
 

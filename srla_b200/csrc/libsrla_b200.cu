@@ -151,7 +151,7 @@ struct DeviceCtx {
     DevBuf streams, jobs, misc, stream_begin, pcm, out, raw;
     /* a lane = one compute stream + its own per-group scratch; alternate groups of a call run on different
      * lanes so the latency-bound kernels of one group (lpc, scan) overlap the throughput-bound ones of the next */
-    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags, lpc_state, svr_coef, svr_matrix; };
+    struct Lane { cudaStream_t own = nullptr, stream = nullptr; cudaEvent_t done = nullptr; DevBuf cand, diag, jobout, residual, lags, lpc_state, svr_coef, svr_matrix, big; };
     Lane lane[kMaxLanes];
     int lanes = 3;                 /* SRLA_B200_LANES */
     int groups = 8;                /* SRLA_B200_GROUPS: groups a large call is split into */
@@ -256,7 +256,7 @@ bool ctx_init(DeviceCtx *c)
 
     /* host-libm tables (host_tables.h) */
     std::vector<host::Cx> tab; std::vector<uint32_t> off;
-    const int max_lg = 14;
+    const int max_lg = 16;                                    /* real transforms up to 65536 points (blocks up to 65535 samples) */
     host::build_complex_twiddles(max_lg, tab, off);
     if (!c->tw_complex.reserve(tab.size() * sizeof(host::Cx))) { return false; }
     CU_TRY(cudaMemcpy(c->tw_complex.p, tab.data(), tab.size() * sizeof(host::Cx), cudaMemcpyHostToDevice));
@@ -296,7 +296,7 @@ void ctx_destroy(DeviceCtx *c)
     for (int l = 0; l < kMaxLanes; l++) {
         if (c->lane[l].own) { cudaStreamSynchronize(c->lane[l].own); cudaStreamDestroy(c->lane[l].own); }
         if (c->lane[l].done) { cudaEventDestroy(c->lane[l].done); }
-        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags, &c->lane[l].lpc_state, &c->lane[l].svr_coef, &c->lane[l].svr_matrix };
+        DevBuf *lb[] = { &c->lane[l].cand, &c->lane[l].diag, &c->lane[l].jobout, &c->lane[l].residual, &c->lane[l].lags, &c->lane[l].lpc_state, &c->lane[l].svr_coef, &c->lane[l].svr_matrix, &c->lane[l].big };
         for (DevBuf *b : lb) { b->release(); }
     }
     if (c->ev_fork) { cudaEventDestroy(c->ev_fork); }
@@ -478,6 +478,7 @@ struct Runner {
     LenCache len_cache;
     uint64_t launches = 0;
     bool narrow_overflow = false;      /* the feeder met a sample outside int16: the caller redoes the call with the int32 layout */
+    bool serial_streams = false;       /* odd block size: the analysis calls of a stream form one chain (front_big_kernel) */
 
     LaunchParams base_params(const Plan &pl, uint32_t nmax) const
     {
@@ -503,6 +504,12 @@ struct Runner {
         p.stats = (uint32_t *)((unsigned char *)c->misc.p + 2 * sizeof(unsigned long long));
         p.stream_begin = (unsigned long long *)((unsigned char *)c->misc.p + kMiscBytes);       /* behind the counters: one result copy */
         return p;
+    }
+
+    DeviceCtx::Lane &lane_of(cudaStream_t on)
+    {
+        for (int l = 1; l < kMaxLanes; l++) { if (c->lane[l].stream == on) { return c->lane[l]; } }
+        return c->lane[0];
     }
 
     bool mark(size_t batch, int slot, cudaStream_t on)
@@ -554,13 +561,37 @@ struct Runner {
         const FrontLayout FL = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
         const LpcLayout LL = make_lpc_layout(p.max_order);
         const ResidLayout RL = make_resid_layout(p.nmax, p.max_order);
-        if ((int)std::max(FL.total, RL.total) + 1024 > c->max_smem_optin) {
-            std::fprintf(stderr, "[srla_b200] block of %u samples needs %u bytes of shared memory (> %d)\n", p.nmax, std::max(FL.total, RL.total), c->max_smem_optin);
-            return false;
-        }
         const uint32_t ncands = p.num_jobs * p.ncand;
         const dim3 grid(ncands), block(kThreads);
         const bool ltp = p.ltp_order > 0u;
+        /* blocks whose transform / signal / residual do not fit an SM's shared memory (more than kMaxSharedBlock samples):
+         * the same stages on per-CTA scratch in global memory, persistent CTAs */
+        const bool big = p.serial_streams || p.nmax > (uint32_t)kMaxSharedBlock || (int)std::max(FL.total, RL.total) + 1024 > c->max_smem_optin;
+        if (big) {
+            if (p.svr_iterations > 0u) { std::fprintf(stderr, "[srla_b200] SVR refinement is limited to blocks of at most %d samples\n", kMaxSharedBlock); return false; }
+            const FrontBigLayout FB = make_front_big_layout(p.nmax, p.fft_max);
+            const uint32_t front_ctas = std::min(p.serial_streams ? std::max(1u, p.num_streams) : p.num_jobs, (uint32_t)c->num_sms * 2u);
+            const uint32_t resid_ctas = std::min(ncands, (uint32_t)c->num_sms * 4u);
+            const size_t need = std::max((size_t)front_ctas * FB.total, (size_t)resid_ctas * round_up_u32(RL.total, 256));
+            if (!lane_of(on).big.reserve(need)) { return false; }
+            LaunchParams pb = p;
+            pb.big_scratch = (unsigned char *)lane_of(on).big.p; pb.big_stride = FB.total;
+            if (ltp) { front_big_kernel<true><<<front_ctas, 1024, 0, on>>>(pb); } else { front_big_kernel<false><<<front_ctas, 1024, 0, on>>>(pb); }
+            launches++;
+            if (!mark(batch, 1, on)) { return false; }
+            if (p.max_order > 0) {
+                if (!prep_kernel(lpc_levinson_kernel, LL.total) || !prep_kernel(lpc_select_kernel, LL.select_total)) { return false; }
+                lpc_levinson_kernel<<<(ncands + 31u) / 32u, 32, LL.total, on>>>(p);
+                lpc_select_kernel<<<(ncands + 31u) / 32u, 128, LL.select_total, on>>>(p);
+                launches += 2;
+            }
+            if (!mark(batch, 2, on)) { return false; }
+            pb.big_stride = round_up_u32(RL.total, 256);
+            residual_big_kernel<<<resid_ctas, block, 0, on>>>(pb);
+            launches++;
+            CU_TRY(cudaGetLastError());
+            return true;
+        }
         if (p.fft_max <= 4096u) {
             /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
             if (ltp) {
@@ -726,6 +757,8 @@ struct Runner {
         }
         bool pcm16_only = true;
         for (uint32_t s = 0; s < pl.num_streams && pcm16_only; s++) { pcm16_only = pl.streams[s].sample_bytes == 2u; }
+        p.replay_tails = with_tails ? 1u : 0u; p.group_first = group_first; p.jobs_all = (const Job *)c->jobs.p;     /* big-block path */
+        p.serial_streams = (serial_streams && !pl.variable) ? 1u : 0u;
         if (!launch_analyse(p, ev_idx, on, tail_lo, tail_hi, group_first, pcm16_only)) { return false; }
         if (!mark(ev_idx, 3, on)) { return false; }
         decide_kernel<<<(count + 127) / 128, 128, 0, on>>>(p);
@@ -736,9 +769,18 @@ struct Runner {
             if (h_mailbox) { CU_TRY(cudaMemcpyAsync(h_mailbox, p.running, sizeof(unsigned long long), cudaMemcpyDeviceToHost, on)); }
             if (scan_done) { CU_TRY(cudaEventRecord(scan_done, on)); }      /* after the mailbox copy: the next scan overwrites running[0] */
             const uint32_t smem = round_up_u32(raw_max, 4) + 16u;
-            if ((int)smem > c->max_smem_optin) { std::fprintf(stderr, "[srla_b200] block too large for the emit stage (%u bytes)\n", smem); return false; }
-            if (!prep_kernel(emit_kernel, smem)) { return false; }
-            emit_kernel<<<count, kThreads, smem, on>>>(p);
+            if ((int)smem + 2048 > c->max_smem_optin) {
+                /* a block larger than an SM's shared memory is staged in global memory by persistent CTAs */
+                const uint32_t ctas = std::min(count, (uint32_t)c->num_sms * 4u);
+                LaunchParams pb = p;
+                pb.big_stride = round_up_u32(smem, 256);
+                if (!L.big.reserve((size_t)ctas * pb.big_stride)) { return false; }
+                pb.big_scratch = (unsigned char *)L.big.p;
+                emit_big_kernel<<<ctas, kThreads, 0, on>>>(pb);
+            } else {
+                if (!prep_kernel(emit_kernel, smem)) { return false; }
+                emit_kernel<<<count, kThreads, smem, on>>>(p);
+            }
             launches += 2;
         }
         CU_TRY(cudaGetLastError());
@@ -869,12 +911,19 @@ struct Runner {
                 }
             }
         }
+        /* An ODD block size makes every block's Welch window keep a sample of the previous analysis call (lpc.c:260-264): the
+         * calls of a stream form one chain, which front_big_kernel walks block by block -- all blocks of a stream in one launch */
+        serial_streams = !pl.variable && (max_block & 1u) != 0u && (enc->param.ltp_order == 0u || max_block >= 263u) && enc->max_order > 0u;
         /* large fixed-block calls are split into groups that alternate between the lanes (compute streams);
          * with host I/O every group additionally has its own H2D / D2H copies on the copy streams */
-        const bool split = !pl.variable && !pl.size_only && pl.allow_pipeline && jobs.size() >= 2048 && (io || (c->split_device && c->lanes > 1));
+        const bool split = !pl.variable && !pl.size_only && pl.allow_pipeline && !serial_streams && jobs.size() >= 2048 && (io || (c->split_device && c->lanes > 1));
         const bool pipelined = split && io && !pl.use_fixed_lshift;
         const int lanes = split ? c->lanes : 1;
-        const uint32_t per_batch = jobs_per_batch(pl, max_block) / (uint32_t)lanes;
+        uint32_t per_batch = jobs_per_batch(pl, max_block) / (uint32_t)lanes;
+        if (serial_streams) {
+            if (jobs.size() > (size_t)per_batch * 8u) { std::fprintf(stderr, "[srla_b200] odd block size %u: %zu blocks exceed what one serial launch holds\n", max_block, jobs.size()); return SRLA_APIRESULT_NG; }
+            per_batch = (uint32_t)std::max<size_t>(per_batch, jobs.size());
+        }
         /* group boundaries (job indices).  With host I/O the first groups are small so the kernels start as soon
          * as a little PCM has arrived, and the last ones are small so little output is left to copy back when the
          * kernels finish; in between the groups are large enough to fill the machine. */
@@ -1308,7 +1357,7 @@ struct SRLAEncoder *SRLAEncoder_Create(const struct SRLAEncoderConfig *config, v
         if (own) { std::free(work); }
         return NULL;
     }
-    if (config->max_num_samples_per_block > (uint32_t)kMaxBlock) {
+    if (config->max_num_samples_per_block > (uint32_t)kMaxBlock) {                 /* the block header's sample count is 16 bits */
         std::fprintf(stderr, "[srla_b200] max_num_samples_per_block %u exceeds this implementation's capacity %d\n", config->max_num_samples_per_block, kMaxBlock);
         if (own) { std::free(work); }
         return NULL;

@@ -192,7 +192,7 @@ void usage(const char *prog)
     std::fprintf(stderr,
         "Usage: %s [options] -o OUTPUT_DIR INPUT.wav [INPUT.wav ...]\n"
         "  -m, --mode N                       compress mode 0(fast) .. 6(high compression) (default:4)\n"
-        "  -B, --max-block-size N             max number of block samples (default:4096, at most 16384 here)\n"
+        "  -B, --max-block-size N             max number of block samples (default:4096)\n"
         "  -V, --variable-block-divisions N   number of variable block-size divisions (default:1)\n"
         "  -L, --lookahead-sample-factor N    multiply factor for lookahead samples (default:4)\n"
         "  -P, --long-term-prediction N       long term prediction order, odd (default:0, disabled)\n"

@@ -18,7 +18,8 @@ constexpr int kWarps          = kThreads / 32;
 constexpr int kMaxOrder       = 255;   /* SRLA_MAX_COEFFICIENT_ORDER                           */
 constexpr int kMaxChannels    = 8;
 constexpr int kMaxCand        = kMaxChannels + 2;
-constexpr int kMaxBlock       = 16384; /* capacity of the shared-memory resident pipeline       */
+constexpr int kMaxBlock       = 65535; /* SRLA block header: u16 sample count (srla_encoder.c:1593)                      */
+constexpr int kMaxSharedBlock = 16384; /* capacity of the shared-memory resident pipeline; longer blocks work in HBM   */
 constexpr int kLog2MaxParts   = 10;    /* srla_coder.c:18                                       */
 constexpr int kMaxParts       = 1 << kLog2MaxParts;
 constexpr int kLtpMinPeriod   = 8;     /* srla_internal.h:31-35                                 */
@@ -101,7 +102,12 @@ struct LaunchParams {
     double          *svr_coef;       /* SVR refinement only: [job][cand][P] un-quantised coefficients of the chosen order */
     double          *svr_matrix;     /* SVR refinement only: [CTA of svr_kernel][P][P] covariance / Cholesky factor      */
     uint32_t svr_iterations;         /* num_svr_filter_learning_iteration (0: off)                                       */
-    uint32_t pad_svr;
+    uint32_t replay_tails;           /* big-block path: the stale-scratch replay applies (fixed blocks, even block size)  */
+    uint32_t group_first;            /* big-block path: index of jobs[0] inside jobs_all                                  */
+    uint32_t serial_streams;         /* big-block path: ODD block size -- the calls of a stream form one chain (front_big_kernel) */
+    const Job *jobs_all;             /* big-block path: the call's whole job list (a tail's predecessor may lie in an earlier launch) */
+    unsigned char *big_scratch;      /* big-block path (blocks beyond the shared-memory capacity): per-CTA scratch in HBM  */
+    unsigned long long big_stride;   /* bytes per CTA there                                                               */
     uint32_t num_jobs, num_streams;
     uint32_t nch, ncand, bps;
     uint32_t max_order;              /* preset's maximum LPC order                         */
@@ -252,6 +258,23 @@ SRLA_HD inline Resid16Layout make_resid16_layout(uint32_t nmax, uint32_t P)
     L.stage_off = off; off += 2u * 128u;           /* two slots: job head (16) + candidate record head (64) + stream (48), fetched with cp.async */
     L.bar_off = off; off += 16u;
     L.total = off;
+    return L;
+}
+
+/* front_big_kernel (blocks beyond kMaxSharedBlock): everything a job needs, in global memory per CTA */
+struct FrontBigLayout { uint32_t raw_off, sig_off, a_off, b_off, pbuf_off, lags_off, total; };
+SRLA_HD inline FrontBigLayout make_front_big_layout(uint32_t nmax, uint32_t fft_max)
+{
+    FrontBigLayout L;
+    const uint32_t n4 = round_up_u32(nmax, 4);
+    uint32_t off = 0;
+    L.raw_off = off; off += 4u * (n4 + 32u);
+    L.sig_off = off; off += 4u * (n4 + 32u);
+    L.a_off = off; off += 8u * fft_max;                 /* fft_max / 2 complex elements */
+    L.b_off = off; off += 8u * fft_max;
+    L.pbuf_off = off; off += 8u * (fft_max + 272u);
+    L.lags_off = off; off += 8u * 272u;
+    L.total = round_up_u32(off, 256);
     return L;
 }
 

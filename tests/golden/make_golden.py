@@ -67,6 +67,14 @@ def main():
     save("stereo16_m4_b16384", synth_stereo(16384 * 2 + 5001, seed=79), preset=4, max_block=16384)
     save("stereo24_m3_b16384_ltp3", synth_stereo(16384 + 9000, seed=80, bits=24), bps=24, preset=3, max_block=16384, ltp=3)
     save("mono16_m5_b12000", synth_stereo(12000 * 2 + 100, seed=81)[:1], preset=5, max_block=12000)
+    # ... and beyond the shared-memory capacity (front_big_kernel: transform in global memory), up to the format's limit;
+    # an ODD block size chains every block's analysis to the one before it (front_big_kernel's serial-stream mode)
+    save("stereo16_m4_b32768", synth_stereo(32768 * 2 + 12345, seed=82), preset=4, max_block=32768)
+    save("stereo16_m4_b65535", synth_stereo(65535 * 2 + 4001, seed=83), preset=4, max_block=65535)
+    save("stereo24_m2_b20000_ltp3", synth_stereo(20000 * 2 + 777, seed=84, bits=24), bps=24, preset=2, max_block=20000, ltp=3)
+    save("stereo16_m4_b4095", synth_stereo(4095 * 4 + 100, seed=85), preset=4, max_block=4095)
+    save("mono16_m3_b1001_silence_inside", np.concatenate([synth_stereo(2002, seed=86)[:1], np.zeros((1, 1001), dtype=np.int32),
+                                                           synth_stereo(1500, seed=87)[:1]], axis=1), preset=3, max_block=1001)
     save("odd_after_silence_m4_b4096", np.concatenate([synth_stereo(4096, seed=77), np.zeros((2, 4096), dtype=np.int32),
                                                        synth_stereo(1001, seed=78)], axis=1), preset=4, max_block=4096)
 

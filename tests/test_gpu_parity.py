@@ -343,6 +343,7 @@ def test_reference_cli_relinked_against_libsrla_b200(tmp_path):
             w.writeframes(frames.T.astype("<i2").tobytes())
     for extra, tag, src in ((["-m", "4", "-B", "4096", "-V", "0"], "fixed", wav), (["-m", "4"], "cli_defaults_v1", wav_even),
                             (["-m", "4", "-B", "16384", "-V", "0"], "b16384", wav), (["-m", "3", "-B", "16384", "-V", "1"], "b16384_v1", wav_even),
+                            (["-m", "4", "-B", "65535", "-V", "0"], "b65535", wav), (["-m", "2", "-B", "40000", "-V", "2"], "b40000_v2", wav_even),
                             (["-m", "2", "-B", "2048", "-V", "0", "-P", "3"], "ltp", wav),
                             (["-m", "3", "-B", "4096", "-V", "0", "--svr-filter-learning-iteration", "2"], "svr", wav_even)):
         a, b = tmp_path / f"ref_{tag}.srl", tmp_path / f"b200_{tag}.srl"
