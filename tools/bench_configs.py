@@ -31,7 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", type=int, default=128)
-    ap.add_argument("--seconds", type=int, default=60, help="length of the config 3 / 4 streams")
+    ap.add_argument("--seconds", type=int, default=900, help="length of the config 3 / 4 streams (900 s = 86.4 M channel-samples)")
     args = ap.parse_args()
     import torch
     from helpers import have_ref, ref_encode
@@ -78,7 +78,10 @@ def main() -> None:
             line = {"config": name, "streams": len(streams), "Msamples": samples / 1e6, "ms": best * 1e3,
                     "e2e_Msamples_per_s": samples / best / 1e6,
                     "wav_payload_e2e_Msamples_per_s": samples / wav_best / 1e6, "blocks": int(st.num_blocks), "analysed_blocks": int(st.num_analysed),
-                    "compression": offs[-1] / float(st.bytes_in)}
+                    "compression": offs[-1] / float(st.bytes_in),
+                    "device_kernel_ms": {"front": round(st.ms_front, 3), "lpc": round(st.ms_lpc, 3), "residual": round(st.ms_residual, 3),
+                                         "decide+scan+emit": round(st.ms_emit, 3), "all_analysis_passes": round(st.ms_analyse, 3)},
+                    "device_Msamples_per_s": samples / max(1e-9, (st.ms_analyse + st.ms_emit) * 1e-3) / 1e6}
             if have_ref():
                 sl = np.ascontiguousarray(streams[0][:, :ref_frames].astype(np.int32))
                 t0 = time.perf_counter()
@@ -96,7 +99,11 @@ def main() -> None:
     run("3: 24-bit stereo, block 8192, mode 4, LTP 3", [pinned(wide.astype(np.int32))], 24, 8192, 8192, 8192, 3, 8192 * 12)
     narrow = make_blocks_workload((n + 4095) // 4096, 4096, 2, 16, seed=78, num_templates=2, template_blocks=48)[:, :n]
     run("4: 16-bit stereo, -V 2 -L 4 (1024..4096, look-ahead 16384), mode 4", [pinned(narrow.astype(np.int16))], 16, 1024, 4096, 16384, 0, 16384 * 6)
-    run("2 + SVR: 16-bit stereo, block 4096, mode 4, --svr-filter-learning-iteration 3", [pinned(narrow.astype(np.int16))], 16, 4096, 4096, 4096, 0, 4096 * 4, svr=3)
+    short = narrow[:, :48000 * min(args.seconds, 60)]                     # the SVR refinement is a slow optional mode: one minute
+    run("2 + SVR: 16-bit stereo, block 4096, mode 4, --svr-filter-learning-iteration 3", [pinned(short.astype(np.int16))], 16, 4096, 4096, 4096, 0, 4096 * 4, svr=3)
+    big = make_blocks_workload((n // 4 + 65534) // 65535, 65535, 2, 16, seed=80, num_templates=2, template_blocks=4)[:, :n // 4]
+    run("blocks of 65535 samples (odd: serial-stream mode), 16-bit stereo, mode 4", [pinned(big.astype(np.int16))], 16, 65535, 65535, 65535, 0, 65535 * 2)
+    run("blocks of 32768 samples, 16-bit stereo, mode 4", [pinned(big.astype(np.int16))], 16, 32768, 32768, 32768, 0, 32768 * 2)
     frames = 1_440_000
     base = make_blocks_workload((frames + 4095) // 4096 + 1, 4096, 2, 16, seed=79, num_templates=2, template_blocks=88)
     files = [pinned(np.roll(base, 4099 * k, axis=1)[:, :frames].astype(np.int16)) for k in range(args.files)]
