@@ -226,6 +226,17 @@ def load_traffic():
         return None
 
 
+def load_floors():
+    """Issue-rate floors per kernel (profiles/r2_kernel_floors.json, written by tools/ncu_floors.py from the committed
+    `ncu --set full` capture: executed warp instructions per SASS opcode x the issue cost measured with tools/pipe_rates.cu)."""
+    path = os.path.join(ROOT, "profiles", "r2_kernel_floors.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("kernels")
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------ config 5
 def run_config5(args, rank, world, local_rank, enc, lib, barrier, torch, dist):
     """BASELINE configs[4]: `--files` synthetic 48 kHz stereo 16-bit WAV payloads of 30 s (1 440 000 frames = 351 blocks of
@@ -569,7 +580,20 @@ def main() -> None:
     achieved = alg_bytes / (an * 1e-3) / 1e9
     traffic = load_traffic()
     ncu_dom = (traffic or {}).get(dominant) or {}
+    floors = load_floors() or {}
+    floor_of = {"front_kernel": ["front_kernel"], "lpc_kernels(levinson+select)": ["lpc_levinson_kernel", "lpc_select_kernel"],
+                "residual_kernel": ["residual16_kernel"], "emit_kernel(+decide+scan)": ["decide_kernel", "scan_kernel", "emit_kernel"]}
+    issue_floor = {k: (round(sum(floors[n]["issue_floor_ms"] for n in names), 4) if all(n in floors for n in names) else None)
+                   for k, names in floor_of.items()}
+    step_floor = sum(v for v in issue_floor.values() if v) if all(issue_floor.values()) else None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "issue_floor_ms": issue_floor.get(dominant),
+                "compute_frac": (issue_floor[dominant] / an) if issue_floor.get(dominant) else None,
+                "all_kernels_issue_floor_ms": issue_floor,
+                "step_issue_floor_ms": step_floor,
+                "step_compute_frac": (step_floor / (ms_total / args.steps)) if step_floor else None,
+                "issue_floor_source": "profiles/r2_kernel_floors.json: executed warp instructions per SASS opcode (ncu) x issue cost per "
+                                      "instruction class measured with tools/pipe_rates.cu; the kernel cannot run faster than its busiest pipe",
                 "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": ncu_dom.get("dram_bytes_per_launch"),
                 "ncu": {k: v for k, v in ncu_dom.items() if k != "dram_bytes_per_launch"} or None,

@@ -106,13 +106,36 @@ __device__ __forceinline__ uint32_t block_scan_inclusive(uint32_t v, uint32_t *s
  * lshift_finish_kernel: or_mask -> trailing zero count; optionally snapshots the value the jobs of
  * this launch group are about to use (pipelined host path, see Runner::run).
  * ---------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) lshift_jobs_kernel(StreamDev *streams, const Job *jobs, uint32_t nch)
+/* 16-byte loads of 16-bit PCM (eight samples each), several per thread in flight: the pass that only ORs samples is bound
+ * by HBM and by how many bytes a CTA keeps in flight */
+__device__ __forceinline__ uint32_t or_row_int16(const short *row, uint32_t n, uint32_t tid, uint32_t nthreads)
 {
-    const Job &job = jobs[blockIdx.x];
+    uint32_t acc = 0;
+    const uint32_t nvec = n >> 3;
+    const int4 *v = reinterpret_cast<const int4 *>(row);
+    uint32_t g = tid;
+    for (; g + 3u * nthreads < nvec; g += 4u * nthreads) {
+        const int4 a = ldg_stream_v4(v + g), b = ldg_stream_v4(v + g + nthreads), c = ldg_stream_v4(v + g + 2u * nthreads), d = ldg_stream_v4(v + g + 3u * nthreads);
+        acc |= (uint32_t)(a.x | a.y | a.z | a.w) | (uint32_t)(b.x | b.y | b.z | b.w) | (uint32_t)(c.x | c.y | c.z | c.w) | (uint32_t)(d.x | d.y | d.z | d.w);
+    }
+    for (; g < nvec; g += nthreads) { const int4 a = ldg_stream_v4(v + g); acc |= (uint32_t)(a.x | a.y | a.z | a.w); }
+    for (uint32_t i = (nvec << 3) + tid; i < n; i += nthreads) { acc |= (uint32_t)(int32_t)__ldg(row + i); }
+    /* only the lowest set bit of the mask matters (trailing-zero count) and it lies in the 16 raw bits of either half */
+    return (acc & 0xffffu) | (acc >> 16);
+}
+
+__global__ void __launch_bounds__(256) lshift_jobs_kernel(StreamDev *streams, const Job *jobs, uint32_t nch, uint32_t num_jobs)
+{
+  for (uint32_t jb = blockIdx.x; jb < num_jobs; jb += gridDim.x) {
+    const Job &job = jobs[jb];
     StreamDev &st = streams[job.stream];
     const uint32_t n = job.nsmpl;
     uint32_t acc = 0;
     for (uint32_t c = 0; c < nch; ++c) {
+        if (st.sample_bytes == 2u) {
+            const short *row = reinterpret_cast<const short *>(st.pcm) + (unsigned long long)c * st.stride + job.offset;
+            if ((reinterpret_cast<unsigned long long>(row) & 15ull) == 0ull) { acc |= or_row_int16(row, n, threadIdx.x, blockDim.x); continue; }
+        }
         const bool vec = quad_aligned(st, c, job.offset);
         const uint32_t nquad = vec ? (n >> 2) : 0u;
         for (uint32_t g = threadIdx.x; g < nquad; g += blockDim.x) {
@@ -123,7 +146,9 @@ __global__ void __launch_bounds__(256) lshift_jobs_kernel(StreamDev *streams, co
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { acc |= __shfl_xor_sync(0xffffffffu, acc, o); }
-    if ((threadIdx.x & 31) == 0 && acc) { atomicOr(&st.or_mask, acc); }
+    /* the mask only ever gains bits: skip the atomic when this warp adds nothing new (almost always after the first blocks) */
+    if ((threadIdx.x & 31) == 0 && (acc & ~*reinterpret_cast<volatile uint32_t *>(&st.or_mask))) { atomicOr(&st.or_mask, acc); }
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -708,7 +708,7 @@ struct Runner {
     bool launch_lshift(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t *d_snapshot, cudaStream_t on, bool ingest = false)
     {
         if (ingest) { deinterleave_jobs_kernel<<<count, 256, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch); }
-        else { lshift_jobs_kernel<<<count, 256, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch); }
+        else { lshift_jobs_kernel<<<std::min(count, (uint32_t)c->num_sms * 16u), 128, 0, on>>>((StreamDev *)c->streams.p, d_jobs, pl.nch, count); }
         lshift_finish_kernel<<<(pl.num_streams + 255) / 256, 256, 0, on>>>((StreamDev *)c->streams.p, pl.num_streams, d_snapshot);
         CU_TRY(cudaGetLastError());
         launches += 2;

@@ -29,7 +29,7 @@ for r in csv.reader(io.StringIO(out)):
     if not r:
         continue
     if r[0] == "Kernel Name":
-        kern = r[1].split("(")[0].replace("void ", "").replace("srla::", "").strip(); launches[kern] += 1; continue
+        kern = r[1].split("(")[0].split("<")[0].replace("void ", "").replace("srla::", "").strip(); launches[kern] += 1; continue
     if r[0] == "Address":
         hdr = r; continue
     if hdr and len(r) == len(hdr) and kern:
