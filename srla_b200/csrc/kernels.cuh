@@ -1750,7 +1750,7 @@ __device__ __forceinline__ uint32_t var_len(uint32_t u, uint32_t k)
     return kRice ? t : (uint32_t)__viaddmax_s32_relu((int)t, -2, 0);
 }
 
-struct RiceResult { uint32_t code_type, porder, bits; };
+struct RiceResult { uint32_t code_type, porder, bits; uint32_t thread_bits, tb_valid; };
 
 /* fast path: n = 1024 * NQ samples, 256 threads, thread t owns samples [4 NQ t, 4 NQ (t + 1)) */
 template <int NQ>
@@ -1761,7 +1761,8 @@ __device__ __forceinline__ RiceResult rice_search_fast(const int32_t *res_s, uns
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *warp_mean = reinterpret_cast<double *>(scratch);                              /* [8]   */
     unsigned long long *kshare = reinterpret_cast<unsigned long long *>(scratch + 64);    /* [256] */
-    RiceResult rr; rr.porder = 0;
+    uint16_t *thread_bits_all = reinterpret_cast<uint16_t *>(scratch + 64 + 8 * kThreads);   /* [11][256], saturated */
+    RiceResult rr; rr.porder = 0; rr.thread_bits = 0; rr.tb_valid = 0;
 
     uint32_t v[S];
     {
@@ -1876,6 +1877,8 @@ __device__ __forceinline__ RiceResult rice_search_fast(const int32_t *res_s, uns
         for (int i = 0; i < S; ++i) { acc[9] += var_len<false>(v[i], k9[i / (2 * NQ)]); acc[10] += var_len<false>(v[i], k10[i / NQ]); }
     }
     #pragma unroll
+    for (int l = 0; l <= 10; ++l) { thread_bits_all[l * kThreads + tid] = (uint16_t)min(acc[l], 0xffffu); }
+    #pragma unroll
     for (int l = 0; l <= 10; ++l) { acc[l] = __reduce_add_sync(0xffffffffu, acc[l]); }
     if (lane == 0) {
         #pragma unroll
@@ -1897,6 +1900,10 @@ __device__ __forceinline__ RiceResult rice_search_fast(const int32_t *res_s, uns
     __syncthreads();
     const uint32_t best_bits = red32[96], best = red32[97];
     rr.porder = best; rr.bits = best_bits + 2u;
+    /* ... and what THIS thread's samples cost at the chosen order (parameter fields of the partitions that start here
+     * included): exactly what emit_kernel's sizing pass would compute for the same samples.  Every thread parked its
+     * eleven per-order counts in shared memory before the reduction. */
+    const uint32_t tb = thread_bits_all[best * kThreads + tid];
     if (best <= 8u) {
         if ((tid & ((1 << (8 - best)) - 1)) == 0) {
             uint32_t kb = k[0];
@@ -1909,6 +1916,7 @@ __device__ __forceinline__ RiceResult rice_search_fast(const int32_t *res_s, uns
     } else {
         *reinterpret_cast<uchar4 *>(out->kparam + 4 * tid) = make_uchar4((unsigned char)k10[0], (unsigned char)k10[1], (unsigned char)k10[2], (unsigned char)k10[3]);
     }
+    rr.thread_bits = tb; rr.tb_valid = 1u;
     return rr;
 }
 
@@ -1917,7 +1925,7 @@ __device__ RiceResult rice_search_general(const int32_t *res_s, const uint32_t n
                                           CandOut *out, const double *rice_threshold)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    RiceResult rr; rr.porder = 0;
+    RiceResult rr; rr.porder = 0; rr.thread_bits = 0; rr.tb_valid = 0;
     uint32_t max_porder = (uint32_t)(__ffs((int)n) - 1);
     if (max_porder > (uint32_t)kLog2MaxParts) { max_porder = (uint32_t)kLog2MaxParts; }
     const uint32_t nparts = 1u << max_porder, per = n >> max_porder;
@@ -2155,6 +2163,7 @@ __device__ __forceinline__ void residual_finish(const LaunchParams &p, CandOut *
         default:    rr = rice_search_general(res_s, n, scratch, red32, out, p.rice_threshold); break;
     }
     const uint32_t code_type = rr.code_type, best_porder = rr.porder, residual_bits = rr.bits;
+    if (rr.tb_valid) { out->thread_bits[tid] = (uint16_t)min(rr.thread_bits, 0xffffu); }
 
     /* ---- side-information bits (srla_encoder.c:1122-1187) and result ---- */
     if (tid < 32) {
@@ -2184,7 +2193,7 @@ __device__ __forceinline__ void residual_finish(const LaunchParams &p, CandOut *
             bits += coef_bits;
             bits += 1u;
             if (ltp_period > 0u) { bits += 1u + 8u + p.ltp_order * 6u; }
-            out->use_sum = use_sum; out->coef_bits = coef_bits;
+            out->use_sum = use_sum; out->coef_bits = coef_bits; out->tb_valid = rr.tb_valid;
             out->code_type = code_type; out->porder = best_porder;
             out->residual_bits = residual_bits; out->total_bits = bits;
         }
@@ -2876,9 +2885,11 @@ __device__ __forceinline__ void emit_block(const LaunchParams &p, uint32_t *word
             const uint32_t part0 = (cnt > 0u) ? i0 / plen : 0u;
             const uint32_t first_boundary = (part0 * plen == i0) ? i0 : (part0 + 1u) * plen;
             const bool rice = (code_type == kCodeRice);
-            /* pass 1 */
+            /* pass 1: the residual stage left this thread's bit count when its sample ranges are the same as here */
             uint32_t mybits = 0;
-            {
+            const uint32_t known = (c.tb_valid && (n & (kThreads - 1u)) == 0u) ? (uint32_t)c.thread_bits[tid] : 0xffffu;
+            if (known != 0xffffu) { mybits = known; }
+            else {
                 uint32_t part = part0, k = (cnt > 0u) ? (uint32_t)c.kparam[part0] : 0u, next = first_boundary;
                 #pragma unroll 1
                 for (uint32_t t0 = 0; t0 < cnt; t0 += 4u) {

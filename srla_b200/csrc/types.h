@@ -66,8 +66,13 @@ struct CandOut {
     uint32_t status;           /* 0 ok, 1: reference would fail the encode (singular LTP system) */
     int16_t  coef[256];        /* FIR order                                                */
     uint8_t  kparam[kMaxParts];/* coding parameter per partition at `porder`               */
-    /* diagnostics for the stage-level parity tests (written only when LaunchParams.diag) */
+    /* code bits (parameter fields included) of the samples [t * n / 256, (t + 1) * n / 256) at the chosen partition order,
+     * t = 0..255, saturated at 0xffff: the residual stage knows them, so emit_kernel's sizing pass only reads them.
+     * Valid when tb_valid (blocks of 1024 * {1,2,3,4,8} samples, i.e. the register-resident Rice search ran). */
+    uint16_t thread_bits[kThreads];
+    uint32_t tb_valid, pad_tb[3];
 };
+static_assert(sizeof(CandOut) % 16 == 0, "candidate records are fetched in 16-byte pieces");
 
 /* optional diagnostics of one candidate (stage-level parity tests) */
 struct CandDiag {
@@ -217,7 +222,7 @@ SRLA_HD inline ResidLayout make_resid_layout(uint32_t nmax, uint32_t P)
     const uint32_t scratch = (pyramid > pairs) ? pyramid : pairs;
     uint32_t off = 0;
     L.region_off = off;
-    L.region_bytes = round_up_u32(4u * n4 + (scratch > 4096u ? scratch : 4096u), 16);
+    L.region_bytes = round_up_u32(4u * n4 + (scratch > 8192u ? scratch : 8192u), 16);     /* the Rice search parks 64 + 2048 + 5632 bytes there */
     off += L.region_bytes;
     L.sig_off = off; off += 4u * (n4 + 12u + resid_front_pad(P));
     L.coef_off = off; off += 4u * (round_up_u32(P, 4) + 4u);
@@ -244,7 +249,7 @@ SRLA_HD inline Resid16Layout make_resid16_layout(uint32_t nmax, uint32_t P)
     const uint32_t sigbytes = 4u * (n8 + 12u + resid_front_pad(P));
     uint32_t scratch = (pyramid > pairs) ? pyramid : pairs;
     if (sigbytes > scratch) { scratch = sigbytes; }
-    if (scratch < 4096u) { scratch = 4096u; }
+    if (scratch < 8192u) { scratch = 8192u; }
     L.row_bytes = round_up_u32(2u * n8 + 16u, 16);
     L.buf_bytes = round_up_u32((4u * n8 > 2u * L.row_bytes) ? 4u * n8 : 2u * L.row_bytes, 128);
     uint32_t off = 0;
