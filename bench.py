@@ -523,7 +523,7 @@ def main() -> None:
     lib.SRLAB200_TestNarrow.restype = C.c_uint32
     feed_threads = max(2, min(16, len(os.sched_getaffinity(0))))
     h_narrow = torch.empty((CHANNELS, nsamp), dtype=torch.int16).pin_memory()
-    chunk = 1 << 16
+    chunk = max(1 << 16, -(-nsamp // (2 * feed_threads)))       # a few large pieces per thread: the Python dispatch must not count
     pieces = [(ch, at) for ch in range(CHANNELS) for at in range(0, nsamp, chunk)]
 
     def narrow_worker(t):
