@@ -725,10 +725,11 @@ __device__ __forceinline__ int4 unpack_quad(const StreamDev &st, int4 v)
 
 /* load, >> offset_lshift, mid/side (srla_encoder.c:1229-1253, srla_utility.c:91-103) -> raw[0..n).
  * returns OR of the unshifted samples of a plain channel candidate (0 for M/S). */
-template <int kBatch>                         /* quads in flight per thread */
-__device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
-                                              uint32_t lshift, int32_t *raw)
+template <int kBatch, bool kShift>            /* quads in flight per thread; kShift: the stream has a non-zero offset shift */
+__device__ __forceinline__ int load_candidate_impl(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
+                                                   uint32_t lshift_in, int32_t *raw)
 {
+    const uint32_t lshift = kShift ? lshift_in : 0u;          /* a compile-time zero removes every shift below */
     const uint32_t n = job.nsmpl;
     const uint32_t first_ch = (p.nch >= 2u) ? 2u : 0u;
     const bool ms = (p.nch >= 2u) && (cand < 2u);
@@ -793,6 +794,14 @@ __device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &jo
         }
     }
     return nz;
+}
+
+/* almost every stream has offset shift 0 (its first odd sample comes early): that case runs without the variable shifts */
+template <int kBatch>
+__device__ __forceinline__ int load_candidate(const StreamDev &st, const Job &job, const LaunchParams &p, uint32_t cand,
+                                              uint32_t lshift, int32_t *raw)
+{
+    return (lshift == 0u) ? load_candidate_impl<kBatch, false>(st, job, p, cand, 0u, raw) : load_candidate_impl<kBatch, true>(st, job, p, cand, lshift, raw);
 }
 
 /* pre-emphasis (srla_utility.c:342-358), filter memory seeded with the first sample; raw -> sig,
