@@ -28,3 +28,24 @@ with D.Decoder() as dec:
     print("corrupt ->", dec.decode_whole_rc(bytes(bad), 2, pcm24.shape[1])[0])
 with D.Decoder(check_checksum=False) as dec:
     print("corrupt, unchecked ->", dec.decode_whole_rc(bytes(bad), 2, pcm24.shape[1])[0])
+# ---- round-2 additions: odd tails (front_tail_kernel), residual16_kernel's bulk copies incl. the plain-load fallback for a tail that
+# is not a multiple of 8, blocks beyond the shared-memory capacity and an odd block size (front_big / residual_big / emit_big),
+# a block of 16384 samples (front_kernel<512>), a hostile stream with a zero-sample compressed block ----
+odd = synth_stereo(4096 * 2 + 1235, seed=21)
+print("odd tail", E.encode(odd, preset=4, max_block=4096) == oracle_encode(odd, preset=4, max_block=4096))
+print("odd tail ltp", E.encode(odd[:, :4096 + 101], preset=3, max_block=4096, ltp=3) == oracle_encode(odd[:, :4096 + 101], preset=3, max_block=4096, ltp=3))
+with E.Encoder(max_channels=2, max_block=4096) as enc:
+    assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+    many = [synth_stereo(n, seed=30 + i).astype(np.int16) for i, n in enumerate((4096 * 3, 4096 + 7, 9001, 100))]
+    o, offs = enc.encode_streams_host(many)
+    print("batch with ragged tails", all(o[offs[i]:offs[i + 1]].tobytes() == oracle_encode(m.astype(np.int32), preset=4, max_block=4096) for i, m in enumerate(many)))
+big = synth_stereo(20000 * 2 + 333, seed=22)
+print("block 20000", E.encode(big, preset=3, max_block=20000) == oracle_encode(big, preset=3, max_block=20000))
+print("block 16384", E.encode(big, preset=3, max_block=16384) == oracle_encode(big, preset=3, max_block=16384))
+print("odd block size 4095", E.encode(big[:, :13000], preset=2, max_block=4095) == oracle_encode(big[:, :13000], preset=2, max_block=4095))
+w24 = synth_stereo(17000 * 2 + 55, seed=23, bits=24)
+print("block 17000 24-bit ltp", E.encode(w24, bps=24, preset=2, max_block=17000, ltp=3) == oracle_encode(w24, bps=24, preset=2, max_block=17000, ltp=3))
+with D.Decoder() as dec:
+    s = bytearray(E.encode(odd, preset=4, max_block=4096))
+    s[30 + 9] = 0; s[30 + 10] = 0                      # first block announces zero samples
+    print("zero-sample block ->", dec.decode_whole_rc(bytes(s), 2, odd.shape[1])[0])
