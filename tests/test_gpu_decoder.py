@@ -196,3 +196,45 @@ def test_decodes_the_committed_reference_streams(name):
     with D.Decoder() as dec:
         got = dec.decode_whole(srl)
     assert got.shape == pcm.shape and np.array_equal(got, pcm)
+
+
+def test_hostile_blocks_are_refused_without_touching_unwritten_records():
+    """a compressed block that announces ZERO samples (valid checksum, so only a hostile or broken writer produces it) used
+    to make the synthesis kernel read side records nobody had written; a walk that runs past the end of its block is
+    corruption even when the next block's bytes happen to parse"""
+    pcm = synth_stereo(4096 * 3 + 100, seed=3)
+    good = E.encode(pcm, preset=4, max_block=4096)
+    starts, at = [], 30
+    while at < len(good):
+        starts.append(at)
+        at += 6 + int.from_bytes(good[at + 2:at + 6], "big")
+
+    def fletcher(b):
+        lo = hi = 0
+        for v in b:
+            lo = (lo + v) % 255
+            hi = (hi + lo) % 255
+        return (hi << 8) | lo
+
+    for which in (0, 1, len(starts) - 1):
+        s = bytearray(good)
+        p0 = starts[which]
+        size = int.from_bytes(s[p0 + 2:p0 + 6], "big")
+        s[p0 + 9] = 0; s[p0 + 10] = 0
+        s[p0 + 6:p0 + 8] = fletcher(s[p0 + 8:p0 + 6 + size]).to_bytes(2, "big")        # keep the checksum valid
+        with D.Decoder() as dec:
+            for _ in range(2):                                                         # the handle stays usable afterwards
+                rc, _out = dec.decode_whole_rc(bytes(s), 2, pcm.shape[1])
+                assert rc == E.INVALID_FORMAT, (which, rc)
+            assert np.array_equal(dec.decode_whole(good), pcm)
+        with D.Decoder(check_checksum=False) as dec:
+            rc, _out = dec.decode_whole_rc(bytes(s), 2, pcm.shape[1])
+            assert rc == E.INVALID_FORMAT
+    # a block whose size field is cut short by 12 bytes (checksum test off): its walk needs bits beyond its end
+    s = bytearray(good)
+    p0 = starts[1]
+    size = int.from_bytes(s[p0 + 2:p0 + 6], "big")
+    cut = bytes(s[:p0 + 2]) + (size - 12).to_bytes(4, "big") + bytes(s[p0 + 6:p0 + 6 + size - 12]) + bytes(s[p0 + 6 + size:])
+    with D.Decoder(check_checksum=False) as dec:
+        rc, _out = dec.decode_whole_rc(cut, 2, pcm.shape[1])
+        assert rc == E.DATA_CORRUPTION, rc

@@ -603,3 +603,18 @@ def test_svr_on_the_reference_test_signals():
             want = reference(pcm, preset=3, max_block=4096, svr=3)
             got = enc.encode_whole(pcm)
             assert got == want, (name, _first_diff(got, want))
+
+
+def test_two_handles_with_different_block_sizes_share_the_kernels():
+    """the dynamic shared-memory limit is state of the KERNEL on a device, not of a handle: a handle that needs more than
+    another one configured last must still launch (the limit is kept process-wide and only ever raised)"""
+    a_pcm = synth_stereo(8192 * 2 + 500, seed=71, bits=24)
+    b_pcm = synth_stereo(1024 * 5 + 100, seed=72)
+    with E.Encoder(max_channels=2, max_block=8192) as a, E.Encoder(max_channels=2, max_block=1024) as b:
+        assert a.set_parameter(2, 24, 48000, 8192, 8192, 8192, 3, 4) == E.OK
+        assert b.set_parameter(2, 16, 48000, 1024, 1024, 1024, 0, 2) == E.OK
+        want_a = oracle_encode(a_pcm, bps=24, preset=4, max_block=8192, ltp=3)
+        want_b = oracle_encode(b_pcm, preset=2, max_block=1024)
+        for _ in range(3):
+            assert a.encode_whole(a_pcm) == want_a
+            assert b.encode_whole(b_pcm) == want_b
