@@ -633,7 +633,12 @@ def main() -> None:
                                           "what": "only the int32 -> int16 narrowing of the input into page-locked staging (4 B read + 2 B written "
                                                   "of host DRAM per sample), all ranks at once, no GPU work: the ceiling the reference's "
                                                   "pageable-int32 signature sets on this host"},
-                    "fraction_of_host_feed_ceiling": e2e_value / feed_ceiling},
+                    "fraction_of_host_feed_ceiling": e2e_value / feed_ceiling,
+                    # everything the call moves through host DRAM per sample: 4 B read + 2 B written by the narrowing, 2 B read by the
+                    # H2D copy engine, and the encoded bytes three times (written by the D2H copy engine into page-locked staging,
+                    # read and written again on their way into the caller's pageable buffer)
+                    "host_dram_traffic_gbs": e2e_value * 1e6 * (8.0 + 3.0 * d2h / float(samples_per_step)) / 1e9,
+                    "fraction_of_host_dram_ceiling": (e2e_value * (8.0 + 3.0 * d2h / float(samples_per_step))) / (feed_ceiling * 6.0)},
             "e2e_batch_api": batch_api,
             "config5": config5,
             "host_placement": placement,
