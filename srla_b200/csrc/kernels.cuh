@@ -2529,46 +2529,28 @@ __global__ void __launch_bounds__(kThreads, 4) residual16_kernel(const __grid_co
 }
 
 /* ------------------------------------------------------------------------------------------------
- * front16_kernel: front_kernel for 16-bit PCM without LTP and transforms of at most 4096 points (configs 2, 4, 5), as
- * persistent CTAs that take a whole JOB at a time.  What front_kernel does per candidate with its own loads happens once
- * per job here:
- *   - the int16 rows of the job's channels arrive in shared memory by cp.async.bulk (completion on an mbarrier), fetched
- *     while the previous job's last candidate is being transformed (the records the copy needs come by cp.async in the
- *     candidates before), instead of every candidate CTA loading and unpacking its channel(s) again: 2 rows per stereo
- *     block instead of 6, and no int32 copy of the candidate in shared memory;
+ * front16_kernel: front_kernel for 16-bit PCM without LTP and transforms of at most 4096 points (configs 2, 4, 5), with
+ * one CTA per JOB instead of one per candidate.  What front_kernel does per candidate with its own loads happens once per
+ * job here:
+ *   - the int16 rows of the job's channels arrive in shared memory by cp.async.bulk (completion on an mbarrier) instead of
+ *     every candidate CTA loading and unpacking its channel(s) again: 2 rows per stereo block instead of 6, and no int32
+ *     copy of the candidate in shared memory;
  *   - ONE pass over the rows gives the exact integer sums r0, r1 (srla_utility.c:214-257) of all candidates;
- *   - the mid/side samples are formed on the fly from the rows where the window pass reads them (srla_utility.c:91-103),
- *     and the Welch weights of a full block (lpc.c:252-266) come from a table that window_table_kernel fills with the very
- *     expression the other kernels evaluate per sample.
- * Same transform code and therefore the same lags, bit for bit, as front_kernel.
+ *   - the mid/side samples are formed on the fly from the rows where the window pass reads them (srla_utility.c:91-103).
+ * Same transform code and therefore the same lags, bit for bit, as front_kernel.  Measured on config 2: 1.25 -> 1.01 ms.
+ * What did NOT pay here (all measured): persistent CTAs that prefetch the next job's rows (1.29 ms: the loop state costs
+ * registers in the pass functions, whose spills then compete with the twiddle tables for L1 -- 12 % instead of 4 % of the
+ * twiddle sectors missed); a table of the Welch weights instead of evaluating them (1.06 ms: 7 % fewer FP64 instructions,
+ * but 16 KB more in L1).
  * ---------------------------------------------------------------------------------------------- */
-__global__ void window_table_kernel(double *w, const uint32_t n, const double div_unit)
-{
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < (n >> 1)) {
-        const double ds = int_to_double((int32_t)s), dn1 = (double)(int32_t)(n - 1u);
-        w[s] = div_unit * ds * (dn1 - ds);                   /* WindowSource::element_at, argument s */
-    }
-}
-
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ int32_t lds_s16(uint32_t addr) { int32_t v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ double2 ldg_stream_d2(const double2 *ptr)
-{
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
-    return v;
-}
 
-#ifndef SRLA_F16_INLINE
-#define SRLA_F16_INLINE 0
-#endif
 struct RowSource {
-    static constexpr bool kInlinePasses = SRLA_F16_INLINE != 0;
+    static constexpr bool kInlinePasses = false;
     uint32_t row0, row1;          /* SHARED-space addresses of the staged rows (offset shift applied, row[-1] == row[0]); row1 only for mid / side */
-    const double2 *wtab;          /* window weights of a block of n samples in pairs (or NULL: they are evaluated) */
     uint32_t kind;                /* 0: mid, 1: side, 2: the channel in row0 as it is */
-    uint32_t n, half_n, pc, tune;
+    uint32_t n, half_n, pc;
     double div, dn1;
     bool full;                    /* n is the transform size and at least 32 */
     /* candidate samples i - 1, i, i + 1 (i even) */
@@ -2603,39 +2585,22 @@ struct RowSource {
         return make_double2(one(i, c0, cm), one(i + 1u, c1, c0));
     }
     __device__ __forceinline__ void first_pass(double2 *x, uint32_t M, uint32_t nn, uint32_t lgs, const double2 *tw_a, const double2 *tw_b, uint32_t need) const;
+    /* the weights evaluated per sample from exact double arguments, as WindowSource::load_full does */
     __device__ __forceinline__ void load_full(double2 (&v)[4][4], const uint32_t tid, const uint32_t M) const
     {
-        if (wtab != nullptr) {
+        const double lo0 = int_to_double((int32_t)(2u * tid)), hi0 = int_to_double((int32_t)(n - 1u - 2u * tid));
+        const double dq = int_to_double((int32_t)(M >> 3));
+        #pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
             #pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
-                    int32_t cm, c0, c1;
-                    cand3(2u * e, cm, c0, c1);
-                    const double x0 = int_to_double(emphasised(c0, cm)), x1 = int_to_double(emphasised(c1, c0));
-                    /* rising half: samples 2e, 2e+1 take w[2e], w[2e+1]; falling half: w[n-1-2e], w[n-2-2e] = the pair M-1-e reversed */
-                    const double2 *wp = wtab + ((j < 2) ? e : (M - 1u - e));
-                    const double2 w = (tune & 2u) ? ldg_stream_d2(wp) : __ldg(wp);
-                    v[jp][j] = (j < 2) ? make_double2(x0 * w.x, x1 * w.y) : make_double2(x0 * w.y, x1 * w.x);
-                }
-            }
-        } else {
-            /* the weights evaluated per sample from exact double arguments, as WindowSource::load_full does */
-            const double lo0 = int_to_double((int32_t)(2u * tid)), hi0 = int_to_double((int32_t)(n - 1u - 2u * tid));
-            const double dq = int_to_double((int32_t)(M >> 3));
-            #pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
-                    int32_t cm, c0, c1;
-                    cand3(2u * e, cm, c0, c1);
-                    const double off = dq * (double)(jp + 4 * j);
-                    const double ds0 = (j < 2) ? lo0 + off : hi0 - off, ds1 = (j < 2) ? ds0 + 1.0 : ds0 + -1.0;
-                    const double w0 = div * ds0 * (dn1 - ds0), w1 = div * ds1 * (dn1 - ds1);
-                    v[jp][j] = make_double2(int_to_double(emphasised(c0, cm)) * w0, int_to_double(emphasised(c1, c0)) * w1);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t e = tid + (uint32_t)jp * (M >> 4) + (uint32_t)j * (M >> 2);
+                int32_t cm, c0, c1;
+                cand3(2u * e, cm, c0, c1);
+                const double off = dq * (double)(jp + 4 * j);
+                const double ds0 = (j < 2) ? lo0 + off : hi0 - off, ds1 = (j < 2) ? ds0 + 1.0 : ds0 + -1.0;
+                const double w0 = div * ds0 * (dn1 - ds0), w1 = div * ds1 * (dn1 - ds1);
+                v[jp][j] = make_double2(int_to_double(emphasised(c0, cm)) * w0, int_to_double(emphasised(c1, c0)) * w1);
             }
         }
     }
@@ -2644,20 +2609,18 @@ struct RowSource {
 /* RowSource's first pass as a real call whose arguments travel in registers (a struct by value would go through the stack) */
 __device__ __noinline__ void fft_first_pass_rows(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs, const double2 *tw_a, const double2 *tw_b,
                                                  const uint32_t need, const uint32_t row0, const uint32_t row1, const uint32_t flags, const uint32_t n,
-                                                 const uint32_t pc, const double div, const double2 *wtab)
+                                                 const uint32_t pc, const double div)
 {
     RowSource ws;
-    ws.row0 = row0; ws.row1 = row1; ws.wtab = wtab; ws.kind = flags & 3u; ws.tune = (flags >> 2) & 3u; ws.full = (flags >> 4) & 1u;
+    ws.row0 = row0; ws.row1 = row1; ws.kind = flags & 3u; ws.full = (flags >> 4) & 1u;
     ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.div = div; ws.dn1 = (double)(int32_t)(n - 1u);
     fft_pair_pass_impl<RowSource, true>(x, M, nn, lgs, tw_a, tw_b, need, ws);
 }
 __device__ __forceinline__ void RowSource::first_pass(double2 *x, uint32_t M, uint32_t nn, uint32_t lgs, const double2 *tw_a, const double2 *tw_b, uint32_t need) const
 {
-    if constexpr (kInlinePasses) { fft_pair_pass_impl<RowSource, true>(x, M, nn, lgs, tw_a, tw_b, need, *this); }
-    else { fft_first_pass_rows(x, M, nn, lgs, tw_a, tw_b, need, row0, row1, kind | ((tune & 3u) << 2) | (full ? 16u : 0u), n, pc, div, wtab); }
+    fft_first_pass_rows(x, M, nn, lgs, tw_a, tw_b, need, row0, row1, kind | (full ? 16u : 0u), n, pc, div);
 }
 
-__device__ __forceinline__ uint32_t warp_sum_u32_redux(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 /* exact warp sum of one int64 per lane whose magnitude stays below 2^50: low 24 bits and the (signed) rest separately */
 __device__ __forceinline__ long long warp_sum_ll_redux(long long v)
 {
@@ -2666,217 +2629,155 @@ __device__ __forceinline__ long long warp_sum_ll_redux(long long v)
     return (long long)hi * (1ll << 24) + (long long)lo;
 }
 
-template <int kT, bool kPersistent>
+template <int kT>
 __global__ void __launch_bounds__(kT, 3) front16_kernel(const __grid_constant__ LaunchParams p)
 {
     static_assert(kT == 128, "four warps: the reduction scratch and the work split assume it");
     extern __shared__ __align__(16) unsigned char smem[];
-    const Front16Layout &L = p.f16;
+    const Front16Layout &L = p.f16;                                                    /* computed by the host: the offsets cost no registers */
     double *region_d = reinterpret_cast<double *>(smem + L.region_off);
     long long *red = reinterpret_cast<long long *>(smem + L.red_off);                 /* [warp][10] */
     int32_t *sh_coef = reinterpret_cast<int32_t *>(smem + L.coef_off);                /* [ncand] */
-    unsigned char *stage = smem + L.stage_off;
-    Front16Desc *desc = reinterpret_cast<Front16Desc *>(smem + L.desc_off);
     unsigned long long *bar = reinterpret_cast<unsigned long long *>(smem + L.bar_off);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t P = p.max_order, ncand = p.ncand, nch = p.nch;
     const uint32_t first_ch = (nch >= 2u) ? 2u : 0u;
     auto row_ptr = [&](uint32_t c) { return reinterpret_cast<short *>(smem + L.rows_off + c * L.row_bytes + 16u); };
 
-    /* thread 0: the three steps that bring the next job's records in without anybody waiting for a global load */
-    auto stage_job = [&](uint32_t job_id) {
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(p.jobs + job_id);
-        #pragma unroll
-        for (int k = 0; k < 5; ++k) { cp_async_8(stage + 8 * k, src + 8 * k); }
-        cp_async_commit();
-    };
-    auto stage_stream = [&]() {
-        cp_async_wait_all();
-        const uint32_t stream = *reinterpret_cast<const volatile uint32_t *>(stage);
-        const unsigned char *src = reinterpret_cast<const unsigned char *>(p.streams + stream);
-        cp_async_16(stage + 48, src); cp_async_16(stage + 64, src + 16); cp_async_16(stage + 80, src + 32);
-        cp_async_commit();
-    };
-    auto make_desc = [&](uint32_t slot) {
-        cp_async_wait_all();
-        const Job *j = reinterpret_cast<const Job *>(stage);
-        const StreamDev *st = reinterpret_cast<const StreamDev *>(stage + 48);
-        Front16Desc d;
-        d.job = *j;
-        d.a0 = reinterpret_cast<unsigned long long>(st->pcm) + 2ull * j->offset;
-        d.row_step = 2ull * st->stride;
-        d.lshift = p.use_fixed_lshift ? p.fixed_lshift : st->lshift;
-        d.bulk = (j->nsmpl > P && (j->nsmpl & 7u) == 0u && (d.a0 & 15ull) == 0ull && (nch < 2u || (d.row_step & 15ull) == 0ull)) ? 1u : 0u;
-        desc[slot] = d;
-    };
-    auto fetch_rows = [&](uint32_t slot) {
-        const Front16Desc &d = desc[slot];
-        if (d.bulk) {
-            /* the rows were last touched through the generic proxy: order those accesses before the asynchronous-proxy writes */
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t bytes = 2u * d.job.nsmpl;
-            mbar_expect_tx(bar, nch * bytes);
-            for (uint32_t c = 0; c < nch; ++c) { bulk_copy_g2s(row_ptr(c), reinterpret_cast<const void *>(d.a0 + c * d.row_step), bytes, bar); }
-        }
-    };
+    const uint32_t job_id = blockIdx.x;
+    const Job job = p.jobs[job_id];
+    const StreamDev &st = p.streams[job.stream];
+    const uint32_t n = job.nsmpl;
+    const uint32_t lshift = p.use_fixed_lshift ? p.fixed_lshift : st.lshift;
+    const unsigned long long a0 = reinterpret_cast<unsigned long long>(st.pcm) + 2ull * job.offset;     /* channel 0's first sample */
+    const unsigned long long row_step = 2ull * st.stride;
+    CandOut *out0 = p.cand + (size_t)job_id * ncand;
 
-    if (tid == 0) {
-        mbar_init(bar, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (blockIdx.x < p.num_jobs) { stage_job(blockIdx.x); stage_stream(); make_desc(0u); fetch_rows(0u); }
+    if (n <= P) {
+        /* RAW block (srla_encoder.c:777-779): nothing to analyse */
+        if ((uint32_t)tid < ncand) {
+            CandOut *out = out0 + tid;
+            int nz = 0;
+            if ((uint32_t)tid >= first_ch) { const short *g = reinterpret_cast<const short *>(a0 + ((uint32_t)tid - first_ch) * row_step); for (uint32_t i = 0; i < n; ++i) { nz |= (int)__ldg(g + i); } }
+            out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
+            out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
+            out->total_bits = 0; out->residual_bits = 0; out->pre_coef = 0; out->pre_prev = 0;
+        }
+        return;
+    }
+
+    /* ---- the rows: bulk copies when they are 16-byte aligned and a multiple of 8 samples, else plain loads ---- */
+    const bool bulk = (n & 7u) == 0u && (a0 & 15ull) == 0ull && (nch < 2u || (row_step & 15ull) == 0ull);
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(bar, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, nch * 2u * n);
+            for (uint32_t c = 0; c < nch; ++c) { bulk_copy_g2s(row_ptr(c), reinterpret_cast<const void *>(a0 + c * row_step), 2u * n, bar); }
+        }
+        __syncthreads();                                   /* the barrier is initialised before anybody polls it */
+        mbar_wait(bar, 0u);
+    } else {
+        for (uint32_t c = 0; c < nch; ++c) {
+            const short *g = reinterpret_cast<const short *>(a0 + c * row_step);
+            short *r = row_ptr(c);
+            for (uint32_t i = tid; i < n; i += kT) { r[i] = __ldg(g + i); }
+        }
+        __syncthreads();
+    }
+    if (lshift != 0u) {
+        /* the stream's common trailing zeros (srla_utility.c:177-203) come off once, in place */
+        for (uint32_t c = 0; c < nch; ++c) { short *r = row_ptr(c); for (uint32_t i = tid; i < n; i += kT) { r[i] = (short)asr32((int32_t)r[i], lshift); } }
+        __syncthreads();
+    }
+    if ((uint32_t)tid < nch) { short *r = row_ptr(tid); r[-1] = r[0]; }       /* filter memory of the pre-emphasis = the first sample */
+
+    /* ---- r0 = sum x^2, r1 = sum x[i] x[i+1] of every candidate as exact integers; OR of the plain channels ---- */
+    {
+        const short *L0 = row_ptr(0), *R0 = row_ptr((nch >= 2u) ? 1u : 0u);
+        long long s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };          /* M r0 r1, S r0 r1, left r0 r1, right r0 r1 */
+        uint32_t nzl = 0u, nzr = 0u;
+        const uint32_t nq = n >> 3;
+        for (uint32_t q = tid; q < nq; q += kT) {
+            const int4 a = *reinterpret_cast<const int4 *>(L0 + 8u * q), b = *reinterpret_cast<const int4 *>(R0 + 8u * q);
+            int32_t l[9] = { (int32_t)(short)(a.x & 0xffff), a.x >> 16, (int32_t)(short)(a.y & 0xffff), a.y >> 16,
+                             (int32_t)(short)(a.z & 0xffff), a.z >> 16, (int32_t)(short)(a.w & 0xffff), a.w >> 16, (int32_t)L0[8u * q + 8u] };
+            int32_t r[9] = { (int32_t)(short)(b.x & 0xffff), b.x >> 16, (int32_t)(short)(b.y & 0xffff), b.y >> 16,
+                             (int32_t)(short)(b.z & 0xffff), b.z >> 16, (int32_t)(short)(b.w & 0xffff), b.w >> 16, (int32_t)R0[8u * q + 8u] };
+            nzl |= (uint32_t)(a.x | a.y | a.z | a.w); nzr |= (uint32_t)(b.x | b.y | b.z | b.w);
+            if (8u * q + 8u >= n) { l[8] = 0; r[8] = 0; }                     /* no successor: the last product is dropped */
+            int32_t m[9], sd[9];
+            #pragma unroll
+            for (int t = 0; t < 9; ++t) { sd[t] = r[t] - l[t]; m[t] = l[t] + (sd[t] >> 1); }
+            #pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                s[0] += (long long)m[t] * m[t];   s[1] += (long long)m[t] * m[t + 1];
+                s[2] += (long long)sd[t] * sd[t]; s[3] += (long long)sd[t] * sd[t + 1];
+                s[4] += (long long)l[t] * l[t];   s[5] += (long long)l[t] * l[t + 1];
+                s[6] += (long long)r[t] * r[t];   s[7] += (long long)r[t] * r[t + 1];
+            }
+        }
+        for (uint32_t i = 8u * nq + tid; i < n; i += kT) {
+            const int32_t l0 = L0[i], r0 = R0[i];
+            const int32_t l1 = (i + 1u < n) ? (int32_t)L0[i + 1u] : 0, r1 = (i + 1u < n) ? (int32_t)R0[i + 1u] : 0;
+            const int32_t sd0 = r0 - l0, sd1 = r1 - l1, m0 = l0 + (sd0 >> 1), m1 = (i + 1u < n) ? l1 + (sd1 >> 1) : 0;
+            nzl |= (uint32_t)l0; nzr |= (uint32_t)r0;
+            s[0] += (long long)m0 * m0;   s[1] += (long long)m0 * m1;
+            s[2] += (long long)sd0 * sd0; s[3] += (long long)sd0 * sd1;
+            s[4] += (long long)l0 * l0;   s[5] += (long long)l0 * l1;
+            s[6] += (long long)r0 * r0;   s[7] += (long long)r0 * r1;
+        }
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] = warp_sum_ll_redux(s[k]); }
+        nzl = __reduce_or_sync(0xffffffffu, nzl); nzr = __reduce_or_sync(0xffffffffu, nzr);
+        if (lane == 0) {
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) { red[warp * 10 + k] = s[k]; }
+            red[warp * 10 + 8] = (long long)nzl; red[warp * 10 + 9] = (long long)nzr;
+        }
+    }
+    __syncthreads();
+    if ((uint32_t)tid < ncand) {
+        /* pre-emphasis coefficient of candidate tid (srla_utility.c:214-257): the sums are below 2^53, so the reference's
+         * double sums are exact as well and the quotient is the same double */
+        const uint32_t slot = (nch >= 2u) ? (uint32_t)tid : 2u;                 /* mono: the channel's sums sit in the `left` slot */
+        long long s0 = 0, s1 = 0, nz = 0;
+        #pragma unroll
+        for (int w = 0; w < kT / 32; ++w) { s0 += red[w * 10 + 2 * slot]; s1 += red[w * 10 + 2 * slot + 1]; nz |= red[w * 10 + 8 + (slot & 1u)]; }
+        int32_t c = 0;
+        if (s0 != 0) {
+            const double v = ((double)s1 / (double)s0) * 16.0;
+            c = (int32_t)round_half_away(v);
+            if (c < -16) { c = -16; }
+            if (c > 15) { c = 15; }
+        }
+        sh_coef[tid] = c;
+        const bool plain = (uint32_t)tid >= first_ch;
+        const int32_t l0 = row_ptr(0)[0], r0 = row_ptr((nch >= 2u) ? 1u : 0u)[0];
+        const int32_t first = plain ? (int32_t)row_ptr((uint32_t)tid - first_ch)[0] : ((tid == 1) ? r0 - l0 : l0 + ((r0 - l0) >> 1));
+        CandOut *out = out0 + tid;
+        out->nonzero = (plain && nz != 0) ? 1u : 0u; out->status = 0; out->order = 0; out->rshift = 0;
+        out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
+        out->total_bits = 0; out->residual_bits = 0; out->pre_coef = c; out->pre_prev = first;
     }
     __syncthreads();
 
-    if (p.tune & 4u) {
-        /* CTAs that share an SM start a third of a candidate apart, so their FP64-heavy and integer phases interleave */
-        const uint32_t r = (blockIdx.x / ((gridDim.x + 2u) / 3u)) % 3u;
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)r * (long long)(p.tune >> 8)) { }
-    }
-    uint32_t parity = 0u, it = 0u;
-    for (uint32_t job_id = blockIdx.x; job_id < p.num_jobs; job_id += gridDim.x, ++it) {
-        const uint32_t cur = kPersistent ? (it & 1u) : 0u, nxt = cur ^ 1u;
-        const Front16Desc &d = desc[cur];
-        const uint32_t n = d.job.nsmpl, lshift = d.lshift;
-        const double ac_scale = d.job.ac_scale, div_unit = d.job.welch_div * p.unit;
-        const uint32_t next_id = job_id + gridDim.x;
-        const bool have_next = kPersistent && next_id < p.num_jobs;
-        const bool is_bulk = d.bulk != 0u;
-        if (tid == 0 && have_next) { stage_job(next_id); }
-        CandOut *out0 = p.cand + (size_t)job_id * ncand;
-
-        if (n <= P) {
-            /* RAW block (srla_encoder.c:777-779): nothing to analyse */
-            if ((uint32_t)tid < ncand) {
-                CandOut *out = out0 + tid;
-                const bool plain = (uint32_t)tid >= first_ch;
-                int nz = 0;
-                if (plain) { const short *g = reinterpret_cast<const short *>(d.a0 + ((uint32_t)tid - first_ch) * d.row_step); for (uint32_t i = 0; i < n; ++i) { nz |= (int)__ldg(g + i); } }
-                out->nonzero = (nz != 0); out->status = 0; out->order = 0; out->rshift = 0;
-                out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
-                out->total_bits = 0; out->residual_bits = 0; out->pre_coef = 0; out->pre_prev = 0;
-            }
-            if (tid == 0 && have_next) { stage_stream(); make_desc(nxt); fetch_rows(nxt); }
-            __syncthreads();
-            continue;
-        }
-
-        /* ---- the rows ---- */
-        if (is_bulk) { mbar_wait(bar, parity); parity ^= 1u; }
-        else {
-            for (uint32_t c = 0; c < nch; ++c) {
-                const short *g = reinterpret_cast<const short *>(d.a0 + c * d.row_step);
-                short *r = row_ptr(c);
-                for (uint32_t i = tid; i < n; i += kT) { r[i] = __ldg(g + i); }
-            }
-            __syncthreads();
-        }
-        if (lshift != 0u) {
-            /* the stream's common trailing zeros (srla_utility.c:177-203) come off once, in place */
-            for (uint32_t c = 0; c < nch; ++c) { short *r = row_ptr(c); for (uint32_t i = tid; i < n; i += kT) { r[i] = (short)asr32((int32_t)r[i], lshift); } }
-            __syncthreads();
-        }
-        if ((uint32_t)tid < nch) { short *r = row_ptr(tid); r[-1] = r[0]; }       /* filter memory of the pre-emphasis = the first sample */
-
-        /* ---- r0 = sum x^2, r1 = sum x[i] x[i+1] of every candidate as exact integers; OR of the plain channels ---- */
-        {
-            const short *L0 = row_ptr(0), *R0 = row_ptr((nch >= 2u) ? 1u : 0u);
-            long long s[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };          /* M r0 r1, S r0 r1, left r0 r1, right r0 r1 */
-            uint32_t nzl = 0u, nzr = 0u;
-            const uint32_t nq = n >> 3;
-            for (uint32_t q = tid; q < nq; q += kT) {
-                const int4 a = *reinterpret_cast<const int4 *>(L0 + 8u * q), b = *reinterpret_cast<const int4 *>(R0 + 8u * q);
-                int32_t l[9] = { (int32_t)(short)(a.x & 0xffff), a.x >> 16, (int32_t)(short)(a.y & 0xffff), a.y >> 16,
-                                 (int32_t)(short)(a.z & 0xffff), a.z >> 16, (int32_t)(short)(a.w & 0xffff), a.w >> 16, (int32_t)L0[8u * q + 8u] };
-                int32_t r[9] = { (int32_t)(short)(b.x & 0xffff), b.x >> 16, (int32_t)(short)(b.y & 0xffff), b.y >> 16,
-                                 (int32_t)(short)(b.z & 0xffff), b.z >> 16, (int32_t)(short)(b.w & 0xffff), b.w >> 16, (int32_t)R0[8u * q + 8u] };
-                nzl |= (uint32_t)(a.x | a.y | a.z | a.w); nzr |= (uint32_t)(b.x | b.y | b.z | b.w);
-                if (8u * q + 8u >= n) { l[8] = 0; r[8] = 0; }                     /* no successor: the last product is dropped */
-                int32_t m[9], sd[9];
-                #pragma unroll
-                for (int t = 0; t < 9; ++t) { sd[t] = r[t] - l[t]; m[t] = l[t] + (sd[t] >> 1); }
-                #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    s[0] += (long long)m[t] * m[t];   s[1] += (long long)m[t] * m[t + 1];
-                    s[2] += (long long)sd[t] * sd[t]; s[3] += (long long)sd[t] * sd[t + 1];
-                    s[4] += (long long)l[t] * l[t];   s[5] += (long long)l[t] * l[t + 1];
-                    s[6] += (long long)r[t] * r[t];   s[7] += (long long)r[t] * r[t + 1];
-                }
-            }
-            for (uint32_t i = 8u * nq + tid; i < n; i += kT) {
-                const int32_t l0 = L0[i], r0 = R0[i];
-                const int32_t l1 = (i + 1u < n) ? (int32_t)L0[i + 1u] : 0, r1 = (i + 1u < n) ? (int32_t)R0[i + 1u] : 0;
-                const int32_t sd0 = r0 - l0, sd1 = r1 - l1, m0 = l0 + (sd0 >> 1), m1 = (i + 1u < n) ? l1 + (sd1 >> 1) : 0;
-                nzl |= (uint32_t)l0; nzr |= (uint32_t)r0;
-                s[0] += (long long)m0 * m0;   s[1] += (long long)m0 * m1;
-                s[2] += (long long)sd0 * sd0; s[3] += (long long)sd0 * sd1;
-                s[4] += (long long)l0 * l0;   s[5] += (long long)l0 * l1;
-                s[6] += (long long)r0 * r0;   s[7] += (long long)r0 * r1;
-            }
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) { s[k] = warp_sum_ll_redux(s[k]); }
-            nzl = __reduce_or_sync(0xffffffffu, nzl); nzr = __reduce_or_sync(0xffffffffu, nzr);
-            if (lane == 0) {
-                #pragma unroll
-                for (int k = 0; k < 8; ++k) { red[warp * 10 + k] = s[k]; }
-                red[warp * 10 + 8] = (long long)nzl; red[warp * 10 + 9] = (long long)nzr;
-            }
-        }
-        __syncthreads();
-        if ((uint32_t)tid < ncand) {
-            /* pre-emphasis coefficient of candidate tid (srla_utility.c:214-257): the sums are below 2^53, so the reference's
-             * double sums are exact as well and the quotient is the same double */
-            const uint32_t slot = (nch >= 2u) ? (uint32_t)tid : 2u;                 /* mono: the channel's sums sit in the `left` slot */
-            long long s0 = 0, s1 = 0, nz = 0;
-            #pragma unroll
-            for (int w = 0; w < kT / 32; ++w) { s0 += red[w * 10 + 2 * slot]; s1 += red[w * 10 + 2 * slot + 1]; nz |= red[w * 10 + 8 + (slot & 1u)]; }
-            int32_t c = 0;
-            if (s0 != 0) {
-                const double v = ((double)s1 / (double)s0) * 16.0;
-                c = (int32_t)round_half_away(v);
-                if (c < -16) { c = -16; }
-                if (c > 15) { c = 15; }
-            }
-            sh_coef[tid] = c;
-            const bool plain = (uint32_t)tid >= first_ch;
-            const int32_t l0 = row_ptr(0)[0], r0 = row_ptr((nch >= 2u) ? 1u : 0u)[0];
-            const int32_t first = plain ? (int32_t)row_ptr((uint32_t)tid - first_ch)[0] : ((tid == 1) ? r0 - l0 : l0 + ((r0 - l0) >> 1));
-            CandOut *out = out0 + tid;
-            out->nonzero = (plain && nz != 0) ? 1u : 0u; out->status = 0; out->order = 0; out->rshift = 0;
-            out->ltp_period = 0; out->ltp_coef[0] = 0; out->ltp_coef[1] = 0; out->ltp_coef[2] = 0;
-            out->total_bits = 0; out->residual_bits = 0; out->pre_coef = c; out->pre_prev = first;
-        }
-        __syncthreads();
-
-        /* ---- autocorrelation of every candidate (lpc.c:444-483) ---- */
-        if (P == 0u) {
-            if (tid == 0 && have_next) { stage_stream(); make_desc(nxt); fetch_rows(nxt); }
-            __syncthreads();
-            continue;
-        }
-        const uint32_t N = ceil_pow2_u32(n);
-        for (uint32_t c = 0; c < ncand; ++c) {
-            if (tid == 0 && have_next) {
-                if (ncand > 1u && c == 1u) { stage_stream(); }
-                if (c == ncand - 1u) { if (ncand == 1u) { stage_stream(); } make_desc(nxt); }
-            }
-            const bool ms = (nch >= 2u) && (c < 2u);
-            RowSource ws;
-            ws.kind = ms ? c : 2u;
-            ws.row0 = smem_addr(ms ? row_ptr(0) : row_ptr(c - first_ch));
-            ws.row1 = smem_addr(row_ptr((nch >= 2u) ? 1u : 0u));
-            ws.tune = p.tune;
-            ws.n = n; ws.half_n = n >> 1; ws.pc = (uint32_t)sh_coef[c];
-            ws.div = div_unit; ws.dn1 = (double)(int32_t)(n - 1u);
-            ws.full = (n == N) && (N >= 32u);
-            ws.wtab = (ws.full && n == p.win_n) ? p.win_tab : nullptr;
-            const uint32_t idx = job_id * ncand + c;
-            /* lags of 32 consecutive candidates are interleaved for the lpc kernel: [lag][candidate % 32] */
-            double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);
-            welch_autocorr_core<RowSource, false>(ws, n, region_d, g, 32u, P + 1u, ac_scale, p, nullptr, kPersistent && c == ncand - 1u,
-                                                  [&]() { if (tid == 0 && have_next) { fetch_rows(nxt); } });
-        }
-        if (!kPersistent) { break; }
+    /* ---- autocorrelation of every candidate (lpc.c:444-483) ---- */
+    if (P == 0u) { return; }
+    const uint32_t N = ceil_pow2_u32(n);
+    for (uint32_t c = 0; c < ncand; ++c) {
+        const bool ms = (nch >= 2u) && (c < 2u);
+        RowSource ws;
+        ws.kind = ms ? c : 2u;
+        ws.row0 = smem_addr(ms ? row_ptr(0) : row_ptr(c - first_ch));
+        ws.row1 = smem_addr(row_ptr((nch >= 2u) ? 1u : 0u));
+        ws.n = n; ws.half_n = n >> 1; ws.pc = (uint32_t)sh_coef[c];
+        ws.div = job.welch_div * p.unit; ws.dn1 = (double)(int32_t)(n - 1u);
+        ws.full = (n == N) && (N >= 32u);
+        const uint32_t idx = job_id * ncand + c;
+        /* lags of 32 consecutive candidates are interleaved for the lpc kernel: [lag][candidate % 32] */
+        double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);
+        welch_autocorr_core<RowSource, false>(ws, n, region_d, g, 32u, P + 1u, job.ac_scale, p, nullptr, false, NoHook());
     }
 }
 

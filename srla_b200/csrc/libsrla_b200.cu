@@ -177,9 +177,6 @@ struct DeviceCtx {
     int resid16 = 1;               /* SRLA_B200_RESID16=0: the one-CTA-per-candidate residual kernel for 16-bit PCM as well (tuning / A-B) */
     int front_occ = 3;             /* CTAs per SM front_kernel<128> is register-sized for (SRLA_B200_FRONT_OCC=3|4, tuning) */
     int front16 = 1;               /* SRLA_B200_FRONT16=0: front_kernel for 16-bit PCM as well (tuning / A-B) */
-    /* Welch window weights of full blocks for front16_kernel, one table per (block length, bits per sample) */
-    struct WinTab { uint32_t n = 0, bps = 0; DevBuf buf; };
-    std::vector<std::unique_ptr<WinTab>> win_tabs;
 };
 
 } // namespace
@@ -314,8 +311,6 @@ void ctx_destroy(DeviceCtx *c)
     DevBuf *bufs[] = { &c->tails, &c->tail_scratch, &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
                        &c->misc, &c->stream_begin, &c->pcm, &c->out, &c->raw };
     for (DevBuf *b : bufs) { b->release(); }
-    for (auto &w : c->win_tabs) { w->buf.release(); }
-    c->win_tabs.clear();
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release(); c->h_stage_out.release();
     if (c->own_stream) { cudaStreamDestroy(c->own_stream); }
 }
@@ -553,21 +548,6 @@ struct Runner {
         return true;
     }
 
-    /* front16_kernel's table of Welch window weights for blocks of n samples: w[s] = (div * unit) * s * (n - 1 - s), s < n / 2,
-     * filled on the device by the expression the kernels evaluate per sample (built once per (n, bits per sample)) */
-    const double2 *window_table(uint32_t n, uint32_t bps, cudaStream_t on)
-    {
-        for (auto &w : c->win_tabs) { if (w->n == n && w->bps == bps) { return (const double2 *)w->buf.p; } }
-        std::unique_ptr<DeviceCtx::WinTab> w(new DeviceCtx::WinTab());
-        if (!w->buf.reserve(sizeof(double) * (n / 2u + 2u))) { return nullptr; }
-        const double div_unit = len_cache.get(n).div * std::ldexp(1.0, -(int)(bps - 1));
-        window_table_kernel<<<(n / 2u + 255u) / 256u, 256, 0, on>>>((double *)w->buf.p, n, div_unit);
-        if (cudaStreamSynchronize(on) != cudaSuccess) { return nullptr; }          /* other lanes read it without an event */
-        w->n = n; w->bps = bps;
-        c->win_tabs.push_back(std::move(w));
-        return (const double2 *)c->win_tabs.back()->buf.p;
-    }
-
     uint32_t svr_grid(const LaunchParams &p) const
     {
         const SvrLayout SL = make_svr_layout(p.nmax, p.max_order);
@@ -617,22 +597,10 @@ struct Runner {
         }
         const Front16Layout F16 = make_front16_layout(p.nmax, p.fft_max, p.nch);
         if (p.fft_max <= 4096u && !ltp && pcm16_only && p.nch <= 2u && c->front16 && p.max_order > 0u) {
-            /* 16-bit PCM without LTP: persistent CTAs take a whole job at a time, rows staged by bulk asynchronous copies */
-            const uint32_t full_n = p.nmax;
-            if (const char *e = std::getenv("SRLA_B200_TUNE")) { p.tune = (uint32_t)std::strtoul(e, nullptr, 0); }
-            if (full_n >= 32u && (full_n & (full_n - 1u)) == 0u && !(p.tune & 1u)) {
-                p.win_tab = window_table(full_n, p.bps, on); p.win_n = full_n;
-                if (!p.win_tab) { return false; }
-            }
+            /* 16-bit PCM without LTP: one CTA per job, the rows of all channels staged once by bulk asynchronous copies */
             p.f16 = F16;
-            if (p.tune & 8u) {
-                if (!prep_kernel(front16_kernel<128, true>, F16.total, 3)) { return false; }
-                front16_kernel<128, true><<<std::min(p.num_jobs, (uint32_t)c->num_sms * 3u), 128, F16.total, on>>>(p);
-            } else {
-                /* one CTA per job: the hardware hands out the jobs, nothing is carried from one to the next */
-                if (!prep_kernel(front16_kernel<128, false>, F16.total, 3)) { return false; }
-                front16_kernel<128, false><<<p.num_jobs, 128, F16.total, on>>>(p);
-            }
+            if (!prep_kernel(front16_kernel<128>, F16.total, 3)) { return false; }
+            front16_kernel<128><<<p.num_jobs, 128, F16.total, on>>>(p);
         } else if (p.fft_max <= 4096u) {
             /* 128 threads: every thread owns one 16-point FFT work unit (2048 complex points / 16) */
             if (ltp) {

@@ -93,17 +93,10 @@ struct JobOut {
     unsigned long long out_offset;   /* byte offset of the block inside the output buffer   */
 };
 
-/* front16_kernel (persistent CTAs, 16-bit PCM without LTP, transforms of at most 4096 points): the FFT buffer, the int16
- * rows of ALL channels of the current job (16 bytes of padding in front of and behind each row; fetched by bulk asynchronous
- * copies one job ahead), reduction scratch, the staged records of the next job and the descriptors of the current / next job */
-struct Front16Desc {
-    Job job;                        /* the job record (welch_div, ac_scale are read from here)                      */
-    unsigned long long a0;          /* address of the first sample of channel 0                                      */
-    unsigned long long row_step;    /* bytes from a channel's row to the next channel's                              */
-    uint32_t lshift, bulk;          /* offset shift of the stream; the rows can be fetched by cp.async.bulk           */
-};
-static_assert(sizeof(Front16Desc) == 64, "descriptor slot");
-struct Front16Layout { uint32_t region_off, rows_off, row_bytes, red_off, coef_off, stage_off, desc_off, bar_off, total; };
+/* front16_kernel (one CTA per job, 16-bit PCM without LTP, transforms of at most 4096 points): the FFT buffer, the int16
+ * rows of ALL channels of the job (16 bytes of padding in front of and behind each row; fetched by bulk asynchronous
+ * copies), reduction scratch, the candidates' pre-emphasis coefficients, the copies' mbarrier */
+struct Front16Layout { uint32_t region_off, rows_off, row_bytes, red_off, coef_off, bar_off, total; };
 /* parameters shared by all jobs of a launch */
 struct LaunchParams {
     StreamDev       *streams;
@@ -142,9 +135,6 @@ struct LaunchParams {
     const double2  *tw_real;         /* per real size N: {wr,wi}[N/4] forward; inverse conjugates wi */
     uint32_t tw_complex_off[20];     /* [log2(ns)] -> offset in double2 units              */
     uint32_t tw_real_off[20];        /* [log2(N)]                                          */
-    const double2  *win_tab;         /* front16_kernel: Welch window weights of blocks of win_n samples, {w[2k], w[2k+1]}, k < win_n / 4 (or NULL) */
-    uint32_t win_n;
-    uint32_t tune;                   /* experiment switches of front16_kernel (SRLA_B200_TUNE) */
     Front16Layout f16;               /* front16_kernel's shared-memory layout (computed by the host: the offsets cost no registers) */
     const double   *rice_threshold;  /* [32] smallest mean with k >= j (plain Rice)        */
     const uint32_t *huff_code;       /* [2][256] plain, summed                             */
@@ -198,8 +188,6 @@ SRLA_HD inline Front16Layout make_front16_layout(uint32_t nmax, uint32_t fft_max
     L.rows_off = off; off += nch * L.row_bytes;
     L.red_off = off; off += 8u * 4u * 10u;                  /* four warps x (eight int64 sums + two flags) */
     L.coef_off = off; off += 16u * 4u;
-    L.stage_off = off; off += 48u + 48u;                    /* Job (40 bytes) | StreamDev (48 bytes), fetched with cp.async */
-    L.desc_off = off; off += 2u * 64u;
     L.bar_off = off; off += 16u;
     L.total = off;
     return L;
