@@ -287,7 +287,7 @@ __device__ __forceinline__ double int_to_double(int32_t x)
  * index: `stale` */
 template <bool kPre, bool kChain = false>
 struct WindowSource {
-    static constexpr bool kInlinePasses = false;
+    static constexpr uint32_t kFixedM = 0u, kFixedThreads = 0u;
     const int32_t *sig; uint32_t n, half_n, pc; double unit, div, dn1;
     double stale;
     bool full;                    /* n is the transform size: no zero padding, the window halves meet at n / 2 */
@@ -363,14 +363,15 @@ struct NoSource {
     __device__ __forceinline__ double2 element(uint32_t) const { return make_double2(0.0, 0.0); }
 };
 
-template <typename Src, bool kFromSamples>
+template <typename Src, bool kFromSamples, bool kAllActive = false>       /* kAllActive: the CTA has exactly M / 16 threads */
 __device__ __forceinline__ void fft_pair_pass_impl(double2 *x, const uint32_t M, const uint32_t nn, const uint32_t lgs,
                                                    const double2 *tw_a, const double2 *tw_b, const uint32_t need, const Src &src)
 {
+    /* called with literal M, nn, lgs (the *_fixed wrappers below) everything but the data path folds away */
     const uint32_t tid = threadIdx.x;
     const uint32_t units = M >> 4;
     const bool last_pair = (nn < 256u);          /* outputs feed the tail pass (or are final) */
-    const bool active = tid < units;
+    const bool active = kAllActive || tid < units;
     const uint32_t q = tid & ((1u << lgs) - 1u), p0 = tid >> lgs;
     const bool fast_load = ((M >> 4) & 127u) == 0u;
     double2 v[4][4];
@@ -468,6 +469,13 @@ __device__ __noinline__ void fft_pair_pass(double2 *x, const uint32_t M, const u
     fft_pair_pass_impl<Src, kFromSamples>(x, M, nn, lgs, tw_a, tw_b, need, src);
 }
 
+/* the same pass with the transform size, stage size and stride known at compile time (kNeedAll: every output is needed) */
+template <uint32_t kM, uint32_t kNN, uint32_t kLgs, bool kNeedAll>
+__device__ __noinline__ void fft_pair_pass_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b, const uint32_t need)
+{
+    fft_pair_pass_impl<NoSource, false, true>(x, kM, kNN, kLgs, tw_a, tw_b, kNeedAll ? kM : need, NoSource());
+}
+
 template <bool kPre, bool kChain>
 __device__ __forceinline__ void WindowSource<kPre, kChain>::first_pass(double2 *x, uint32_t M, uint32_t nn, uint32_t lgs, const double2 *tw_a, const double2 *tw_b, uint32_t need) const
 {
@@ -477,9 +485,9 @@ __device__ __forceinline__ void WindowSource<kPre, kChain>::first_pass(double2 *
 /* the stages left after the fused pairs: nn = 8 (radix-4 + radix-2), 4 (radix-4) or 2 (radix-2).  A tail unit
  * reads and writes exactly the same positions (u + k * s), so units are independent of each other: no barrier
  * between loads and stores, and a thread walks its units one at a time.  Units beyond `need` are skipped. */
-__device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const uint32_t nn, const double2 *tw8, const double2 *tw4, const uint32_t need)
+__device__ __forceinline__ void fft_tail_pass_impl(double2 *x, const uint32_t M, const uint32_t nn, const double2 *tw8, const double2 *tw4, const uint32_t need, const uint32_t T)
 {
-    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const uint32_t tid = threadIdx.x;
     if (nn == 8u) {
         /* radix-4 stage of size 8 (s = M/8) fused with the final radix-2 stage (fft.c:114-123) */
         const uint32_t s = M >> 3;
@@ -523,6 +531,15 @@ __device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const u
     }
     __syncthreads();
 }
+__device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const uint32_t nn, const double2 *tw8, const double2 *tw4, const uint32_t need)
+{
+    fft_tail_pass_impl(x, M, nn, tw8, tw4, need, blockDim.x);
+}
+template <uint32_t kM, uint32_t kNN, uint32_t kT, bool kNeedAll>
+__device__ __noinline__ void fft_tail_pass_fixed(double2 *x, const double2 *tw8, const uint32_t need)
+{
+    fft_tail_pass_impl(x, kM, kNN, tw8, nullptr, kNeedAll ? kM : need, kT);
+}
 
 /* Welch window (lpc.c:252-266) + autocorrelation through the FFT (lpc.c:330-376).
  * sig[n] int32 in shared memory -> lags[0..nlags) (lags >= N read as 0.0).  buf: N doubles.
@@ -532,13 +549,60 @@ __device__ __noinline__ void fft_tail_pass(double2 *x, const uint32_t M, const u
  * (lpc.c:211-213).  It supplies the stale middle sample of an odd-length window, receives the WHOLE inverse transform
  * of this call (no pruning), and the lags are read from it -- also those beyond the transform size, which the
  * reference copies from whatever earlier calls left there (lpc.c:371-373). */
-struct NoHook { __device__ __forceinline__ void operator()() const {} };
+/* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three only touch the element pair
+ * (i, N/2 - i).  The inverse split's outputs are stored CONJUGATED. */
+__device__ __forceinline__ void real_split_power(double2 *cx, const uint32_t N, const LaunchParams &p, const uint32_t tid, const uint32_t nthreads)
+{
+    const uint32_t M = N >> 1;
+    const uint32_t lgN = 31u - (uint32_t)__clz((int)N);
+    const double2 *tw = p.tw_real + p.tw_real_off[lgN];
+    const uint32_t quarter = N >> 2;
+    for (uint32_t i = 1u + tid; i <= quarter; i += nthreads) {
+        const double2 w = __ldg(tw + (i - 1u));
+        const double wr = w.x, wi_f = w.y, wi_b = -w.y;
+        const uint32_t lo = i, hi = M - i;
+        const double2 xl = cx[fft_slot(lo)], xh = cx[fft_slot(hi)];
+        /* forward, flag = -1: c2 = -0.5 */
+        double f1, f2, f3, f4;
+        {
+            const double c2 = -0.5;
+            const double h1r = 0.5 * (xl.x + xh.x);
+            const double h1i = 0.5 * (xl.y - xh.y);
+            const double h2r = -c2 * (xl.y + xh.y);
+            const double h2i = c2 * (xl.x - xh.x);
+            f1 = h1r + (wr * h2r) - (wi_f * h2i);
+            f2 = h1i + (wr * h2i) + (wi_f * h2r);
+            f3 = h1r - (wr * h2r) + (wi_f * h2i);
+            f4 = -h1i + (wr * h2i) + (wi_f * h2r);
+        }
+        /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
+        double p_lo, p_hi;
+        if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
+        else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
+        /* inverse, flag = +1: c2 = +0.5.  The power spectrum is real, so h1i and h2r of fft.c:171-184 are
+         * exact zeros and every term they enter only adds +-0.0: g1 = h1r - wi*h2i, g2 = g4 = wr*h2i,
+         * g3 = h1r + wi*h2i are the same values (up to the sign of a zero, which cannot reach a decision) */
+        {
+            const double h1r = 0.5 * (p_lo + p_hi);
+            const double h2i = 0.5 * (p_lo - p_hi);
+            const double t = wi_b * h2i, g2 = wr * h2i;
+            if (lo != hi) { cx[fft_slot(lo)] = make_double2(h1r - t, -g2); }
+            cx[fft_slot(hi)] = make_double2(h1r + t, -g2);
+        }
+    }
+    if (tid == 0) {
+        const double2 dc = cx[0];
+        const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
+        const double q0 = f0 * f0, q1 = f1 * f1;
+        cx[0] = make_double2(0.5 * (q0 + q1), -(0.5 * (q0 - q1)));
+    }
+    __syncthreads();
+}
 
-/* the transform chain itself for a sample source `ws` (n >= 2).  `after_window` runs (every thread calls it) once the
- * first pass has consumed the samples: front16_kernel starts the next job's row fetch there. */
-template <typename Src, bool kChain, typename Hook>
+/* the transform chain itself for a sample source `ws` (n >= 2) */
+template <typename Src, bool kChain>
 __device__ __forceinline__ void welch_autocorr_core(const Src &ws, const uint32_t n, double *buf, double *lags, const uint32_t lag_step, const uint32_t nlags,
-                                                    const double ac_scale, const LaunchParams &p, double *pbuf, const bool last_use_of_samples, Hook after_window);
+                                                    const double ac_scale, const LaunchParams &p, double *pbuf);
 
 template <bool kPre, bool kChain = false>
 __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const uint32_t n, double *buf, double *lags, const uint32_t lag_step, const uint32_t nlags,
@@ -566,18 +630,42 @@ __device__ void welch_autocorr(const int32_t *sig, const int32_t pre_coef, const
      * exactly (no subnormals: |w| >= 4 / n^2 * 2^-23), so the scale rides on the divisor and costs no multiply per sample */
     ws.sig = sig; ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.unit = 1.0; ws.div = div * unit; ws.dn1 = (double)(int32_t)(n - 1u);
     ws.full = (n == N) && (N >= 32u);
-    welch_autocorr_core<WindowSource<kPre, kChain>, kChain>(ws, n, buf, lags, lag_step, nlags, job.ac_scale, p, pbuf, false, NoHook());
+    welch_autocorr_core<WindowSource<kPre, kChain>, kChain>(ws, n, buf, lags, lag_step, nlags, job.ac_scale, p, pbuf);
 }
 
-template <typename Src, bool kChain, typename Hook>
+template <typename Src, bool kChain>
 __device__ __forceinline__ void welch_autocorr_core(const Src &ws, const uint32_t n, double *buf, double *lags, const uint32_t lag_step, const uint32_t nlags,
-                                                    const double ac_scale, const LaunchParams &p, double *pbuf, const bool last_use_of_samples, Hook after_window)
+                                                    const double ac_scale, const LaunchParams &p, double *pbuf)
 {
     const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
     const uint32_t N = ceil_pow2_u32(n);
     double2 *cx = reinterpret_cast<double2 *>(buf);
     const uint32_t M = N >> 1;
     const uint32_t want = kChain ? N : ((nlags < N) ? nlags : N);
+    if constexpr (Src::kFixedM != 0u) {
+        /* the usual transform size of this source: the same passes with every size, stride and trip count a literal, so the
+         * index arithmetic of the general code folds away (kernels that run with Src::kFixedThreads threads only) */
+        static_assert(Src::kFixedM == 2048u && Src::kFixedThreads == 128u && !kChain, "stage plan below: 2048 = 4^5 * 2, one 16-point unit per thread");
+        if (M == Src::kFixedM && ws.full) {                     /* a full block: n == 2 M */
+            constexpr uint32_t FM = Src::kFixedM, FT = Src::kFixedThreads;
+            const double2 *t11 = p.tw_complex + p.tw_complex_off[11], *t9 = p.tw_complex + p.tw_complex_off[9];
+            const double2 *t7 = p.tw_complex + p.tw_complex_off[7], *t5 = p.tw_complex + p.tw_complex_off[5], *t3 = p.tw_complex + p.tw_complex_off[3];
+            const uint32_t need = (want + 1u) >> 1;
+            ws.first_pass_fixed(cx, t11, t9);
+            fft_pair_pass_fixed<FM, 128u, 4u, true>(cx, t7, t5, FM);
+            fft_tail_pass_fixed<FM, 8u, FT, true>(cx, t3, FM);
+            real_split_power(cx, 2u * FM, p, tid, FT);
+            fft_pair_pass_fixed<FM, FM, 0u, true>(cx, t11, t9, FM);
+            fft_pair_pass_fixed<FM, 128u, 4u, false>(cx, t7, t5, need);
+            fft_tail_pass_fixed<FM, 8u, FT, false>(cx, t3, need);
+            for (uint32_t i = tid; i < nlags; i += FT) {
+                const double2 e = cx[fft_slot(i >> 1)];
+                lags[(size_t)i * lag_step] = (i < 2u * FM) ? ((i & 1u) ? -e.y : e.x) * ac_scale : 0.0;
+            }
+            __syncthreads();
+            return;
+        }
+    }
     /* dir 0: forward transform of the windowed samples; dir 1: the inverse transform, evaluated as the
      * conjugate of a forward transform of conjugated data (see butterfly4) so both directions share one
      * copy of the pass code */
@@ -594,59 +682,13 @@ __device__ __forceinline__ void welch_autocorr_core(const Src &ws, const uint32_
                 for (uint32_t c = tid; c < M; c += nthreads) { cx[fft_slot(c)] = ws.element(c); }
                 __syncthreads();
             }
-            if (last_use_of_samples) { after_window(); }
         } else {
-            /* forward split (fft.c:171-184), |X|^2 (lpc.c:355-362) and inverse split fused: all three only touch
-             * the element pair (i, N/2 - i).  The inverse split's outputs are stored CONJUGATED. */
-            const uint32_t lgN = 31u - (uint32_t)__clz((int)N);
-            const double2 *tw = p.tw_real + p.tw_real_off[lgN];
-            const uint32_t quarter = N >> 2;
-            for (uint32_t i = 1u + tid; i <= quarter; i += nthreads) {
-                const double2 w = __ldg(tw + (i - 1u));
-                const double wr = w.x, wi_f = w.y, wi_b = -w.y;
-                const uint32_t lo = i, hi = M - i;
-                const double2 xl = cx[fft_slot(lo)], xh = cx[fft_slot(hi)];
-                /* forward, flag = -1: c2 = -0.5 */
-                double f1, f2, f3, f4;
-                {
-                    const double c2 = -0.5;
-                    const double h1r = 0.5 * (xl.x + xh.x);
-                    const double h1i = 0.5 * (xl.y - xh.y);
-                    const double h2r = -c2 * (xl.y + xh.y);
-                    const double h2i = c2 * (xl.x - xh.x);
-                    f1 = h1r + (wr * h2r) - (wi_f * h2i);
-                    f2 = h1i + (wr * h2i) + (wi_f * h2r);
-                    f3 = h1r - (wr * h2r) + (wi_f * h2i);
-                    f4 = -h1i + (wr * h2i) + (wi_f * h2r);
-                }
-                /* for i == N/4 the pair is one element: the reference's second pair of stores wins */
-                double p_lo, p_hi;
-                if (lo == hi) { p_hi = f3 * f3 + f4 * f4; p_lo = p_hi; }
-                else { p_lo = f1 * f1 + f2 * f2; p_hi = f3 * f3 + f4 * f4; }
-                /* inverse, flag = +1: c2 = +0.5.  The power spectrum is real, so h1i and h2r of fft.c:171-184 are
-                 * exact zeros and every term they enter only adds +-0.0: g1 = h1r - wi*h2i, g2 = g4 = wr*h2i,
-                 * g3 = h1r + wi*h2i are the same values (up to the sign of a zero, which cannot reach a decision) */
-                {
-                    const double h1r = 0.5 * (p_lo + p_hi);
-                    const double h2i = 0.5 * (p_lo - p_hi);
-                    const double t = wi_b * h2i, g2 = wr * h2i;
-                    if (lo != hi) { cx[fft_slot(lo)] = make_double2(h1r - t, -g2); }
-                    cx[fft_slot(hi)] = make_double2(h1r + t, -g2);
-                }
-            }
-            if (tid == 0) {
-                const double2 dc = cx[0];
-                const double f0 = dc.x + dc.y, f1 = dc.x - dc.y;     /* forward DC / Nyquist */
-                const double q0 = f0 * f0, q1 = f1 * f1;
-                cx[0] = make_double2(0.5 * (q0 + q1), -(0.5 * (q0 - q1)));
-            }
-            __syncthreads();
+            real_split_power(cx, N, p, tid, nthreads);
         }
         #pragma unroll 1
         while (nn >= 16u) {
             const uint32_t lgn = 31u - (uint32_t)__clz((int)nn);
-            if constexpr (Src::kInlinePasses) { fft_pair_pass_impl<NoSource, false>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, NoSource()); }
-            else { fft_pair_pass<NoSource, false>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, NoSource()); }
+            fft_pair_pass<NoSource, false>(cx, M, nn, lgs, p.tw_complex + p.tw_complex_off[lgn], p.tw_complex + p.tw_complex_off[lgn - 2u], need, NoSource());
             nn >>= 4; lgs += 4;
         }
         fft_tail_pass(cx, M, nn, p.tw_complex + p.tw_complex_off[3], p.tw_complex + p.tw_complex_off[2], need);
@@ -2547,7 +2589,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm vol
 __device__ __forceinline__ int32_t lds_s16(uint32_t addr) { int32_t v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 struct RowSource {
-    static constexpr bool kInlinePasses = false;
+    static constexpr uint32_t kFixedM = 2048u, kFixedThreads = 128u;      /* blocks of 4096 samples, front16_kernel's CTA */
     uint32_t row0, row1;          /* SHARED-space addresses of the staged rows (offset shift applied, row[-1] == row[0]); row1 only for mid / side */
     uint32_t kind;                /* 0: mid, 1: side, 2: the channel in row0 as it is */
     uint32_t n, half_n, pc;
@@ -2585,6 +2627,7 @@ struct RowSource {
         return make_double2(one(i, c0, cm), one(i + 1u, c1, c0));
     }
     __device__ __forceinline__ void first_pass(double2 *x, uint32_t M, uint32_t nn, uint32_t lgs, const double2 *tw_a, const double2 *tw_b, uint32_t need) const;
+    __device__ __forceinline__ void first_pass_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b) const;
     /* the weights evaluated per sample from exact double arguments, as WindowSource::load_full does */
     __device__ __forceinline__ void load_full(double2 (&v)[4][4], const uint32_t tid, const uint32_t M) const
     {
@@ -2615,6 +2658,20 @@ __device__ __noinline__ void fft_first_pass_rows(double2 *x, const uint32_t M, c
     ws.row0 = row0; ws.row1 = row1; ws.kind = flags & 3u; ws.full = (flags >> 4) & 1u;
     ws.n = n; ws.half_n = n >> 1; ws.pc = pc; ws.div = div; ws.dn1 = (double)(int32_t)(n - 1u);
     fft_pair_pass_impl<RowSource, true>(x, M, nn, lgs, tw_a, tw_b, need, ws);
+}
+/* ... and with the transform size a literal (a full block: n == 2 kM) */
+template <uint32_t kM>
+__device__ __noinline__ void fft_first_pass_rows_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b, const uint32_t row0, const uint32_t row1,
+                                                       const uint32_t kind, const uint32_t pc, const double div)
+{
+    RowSource ws;
+    ws.row0 = row0; ws.row1 = row1; ws.kind = kind; ws.full = true;
+    ws.n = 2u * kM; ws.half_n = kM; ws.pc = pc; ws.div = div; ws.dn1 = (double)(int32_t)(2u * kM - 1u);
+    fft_pair_pass_impl<RowSource, true, true>(x, kM, kM, 0u, tw_a, tw_b, kM, ws);
+}
+__device__ __forceinline__ void RowSource::first_pass_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b) const
+{
+    fft_first_pass_rows_fixed<kFixedM>(x, tw_a, tw_b, row0, row1, kind, pc, div);
 }
 __device__ __forceinline__ void RowSource::first_pass(double2 *x, uint32_t M, uint32_t nn, uint32_t lgs, const double2 *tw_a, const double2 *tw_b, uint32_t need) const
 {
@@ -2777,7 +2834,7 @@ __global__ void __launch_bounds__(kT, 3) front16_kernel(const __grid_constant__ 
         const uint32_t idx = job_id * ncand + c;
         /* lags of 32 consecutive candidates are interleaved for the lpc kernel: [lag][candidate % 32] */
         double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);
-        welch_autocorr_core<RowSource, false>(ws, n, region_d, g, 32u, P + 1u, job.ac_scale, p, nullptr, false, NoHook());
+        welch_autocorr_core<RowSource, false>(ws, n, region_d, g, 32u, P + 1u, job.ac_scale, p, nullptr);
     }
 }
 
