@@ -461,12 +461,37 @@ def main() -> None:
         step_device()
         st = enc.stats()
         an_ms.append(st.ms_analyse); em_ms.append(st.ms_emit); launches += int(st.kernel_launches)
-        k_ms["front_kernel"].append(st.ms_front); k_ms["lpc_kernels(levinson+select)"].append(st.ms_lpc)
-        k_ms["residual_kernel"].append(st.ms_residual); k_ms["emit_kernel(+decide+scan)"].append(st.ms_emit)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    # ---- per-kernel durations: the default device-resident call runs as groups on several lanes whose kernels overlap, so
+    # the time between two of its events is not one kernel's.  A second handle created with SRLA_B200_SPLIT_DEVICE=0 runs
+    # the same call as ONE batch on one stream; its CUDA-event times are the kernels' own (and what ncu's launch list shows).
+    prev_split = os.environ.get("SRLA_B200_SPLIT_DEVICE")
+    os.environ["SRLA_B200_SPLIT_DEVICE"] = "0"
+    enc_serial = E.Encoder(max_channels=CHANNELS, max_block=BLOCK, device=local_rank)
+    if prev_split is None:
+        del os.environ["SRLA_B200_SPLIT_DEVICE"]
+    else:
+        os.environ["SRLA_B200_SPLIT_DEVICE"] = prev_split
+    assert enc_serial.set_parameter(CHANNELS, BITS, RATE, BLOCK, BLOCK, BLOCK, 0, PRESET) == E.OK
+    enc_serial.set_stream(stream.cuda_stream)
+    serial_steps = max(3, min(args.steps, 10))
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(args.warmup + serial_steps):
+        if i == args.warmup:
+            torch.cuda.synchronize()
+            s0.record(stream)
+        rc = lib.SRLAB200_EncodeStreamsDevice(enc_serial.handle, dev_desc, 1, d_out.data_ptr(), cap, offs)
+        assert rc == E.OK, rc
+        if i >= args.warmup:
+            sst = enc_serial.stats()
+            k_ms["front_kernel"].append(sst.ms_front); k_ms["lpc_kernels(levinson+select)"].append(sst.ms_lpc)
+            k_ms["residual_kernel"].append(sst.ms_residual); k_ms["emit_kernel(+decide+scan)"].append(sst.ms_emit)
+    s1.record(stream)
+    torch.cuda.synchronize()
+    serial_ms = [s0.elapsed_time(s1) / serial_steps]
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -579,14 +604,15 @@ def main() -> None:
     an = kernel_ms[dominant]
     achieved = alg_bytes / (an * 1e-3) / 1e9
     traffic = load_traffic()
-    ncu_dom = (traffic or {}).get(dominant) or {}
     floors = load_floors() or {}
-    floor_of = {"front_kernel": ["front_kernel"], "lpc_kernels(levinson+select)": ["lpc_levinson_kernel", "lpc_select_kernel"],
+    front_name = "front16_kernel" if "front16_kernel" in floors else "front_kernel"     # 16-bit PCM without LTP runs front16_kernel
+    floor_of = {"front_kernel": [front_name], "lpc_kernels(levinson+select)": ["lpc_levinson_kernel", "lpc_select_kernel"],
                 "residual_kernel": ["residual16_kernel"], "emit_kernel(+decide+scan)": ["decide_kernel", "scan_kernel", "emit_kernel"]}
+    ncu_dom = (traffic or {}).get(floor_of[dominant][0]) or {}
     issue_floor = {k: (round(sum(floors[n]["issue_floor_ms"] for n in names), 4) if all(n in floors for n in names) else None)
                    for k, names in floor_of.items()}
     step_floor = sum(v for v in issue_floor.values() if v) if all(issue_floor.values()) else None
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": floor_of[dominant][0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "issue_floor_ms": issue_floor.get(dominant),
                 "compute_frac": (issue_floor[dominant] / an) if issue_floor.get(dominant) else None,
                 "all_kernels_issue_floor_ms": issue_floor,
@@ -598,7 +624,11 @@ def main() -> None:
                 "traffic": ncu_dom.get("dram_bytes_per_launch"),
                 "ncu": {k: v for k, v in ncu_dom.items() if k != "dram_bytes_per_launch"} or None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": an,
-                "share_of_step": an / (ms_total / args.steps), "all_kernels_ms": kernel_ms,
+                "share_of_step": an / float(np.mean(serial_ms)), "all_kernels_ms": kernel_ms,
+                "kernel_ms_source": "CUDA events of a handle that runs the call as ONE batch on one stream (SRLA_B200_SPLIT_DEVICE=0): "
+                                    "the default call overlaps the kernels of its groups on several lanes, so only the unsplit call "
+                                    "has per-kernel times; `value` / `ms_per_step` are the default (overlapped) call",
+                "serial_ms_per_step": float(np.mean(serial_ms)), "overlap_gain": float(np.mean(serial_ms)) / (ms_total / args.steps),
                 "whole_step_achieved_gbs": alg_bytes / (ms_total / args.steps * 1e-3) / 1e9,
                 "note": "compute-bound path (bit-exact non-FMA FP64 FFT + int32 FIR + Rice search, ~100 ops per algorithmic byte): "
                         "the HBM fraction is low by construction; DESIGN.md section 3 gives the issue-rate ceilings that bind"}
