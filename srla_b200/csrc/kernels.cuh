@@ -1078,7 +1078,9 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
  * standing in for the scratch buffer (zeroed first: a handle on fresh memory, like the `srla` CLI's) and overwrites what
  * front_kernel wrote for the job's candidates.
  * ---------------------------------------------------------------------------------------------- */
-struct TailJob { uint32_t job; uint32_t first_of_stream; };     /* indices into LaunchParams.jobs_all */
+/* job / first: positions in the CALL LIST the kernel is given (the reference's analysis calls of the stream in order; a
+ * call's predecessors are searched from job - 1 down to first); out: the job's index in the launch's own job list */
+struct TailJob { uint32_t job; uint32_t first_of_stream; uint32_t out; };
 
 template <int kT, bool kLtp>
 __device__ void front_chain_step(const LaunchParams &p, const Job &job, const StreamDev &st, const uint32_t cand, const uint32_t lshift,
@@ -1145,24 +1147,55 @@ __global__ void __launch_bounds__(kT) front_tail_kernel(const __grid_constant__ 
     const uint32_t P = p.max_order;
     if (job.nsmpl <= P) { return; }
     for (uint32_t i = tid; i < pbuf_len; i += kT) { pbuf[i] = 0.0; }
-    /* the latest block in front of the tail that made calls: more samples than the order, not silent (srla_encoder.c:766-796) */
-    uint32_t pred = tj.job;
-    bool found = false;
-    while (!found && pred > tj.first_of_stream) {
-        pred--;
-        const Job pj = jobs_all[pred];
-        int nz = 0;
-        if (pj.nsmpl > P) {
-            for (uint32_t ch = 0; ch < p.nch; ++ch) { for (uint32_t i = tid; i < pj.nsmpl; i += kT) { nz |= load_sample(st, ch, pj.offset + i); } }
+    /* A call depends on what earlier calls left in the scratch buffer when its length is odd (the middle sample of the window)
+     * or, with LTP, when its transform is shorter than the 263 lags the pitch search reads.  What it finds there was written
+     * by the LATEST earlier call whose transform covers the index: a block with more samples than the order that is not
+     * silent (srla_encoder.c:766-796).  If that call depends on history itself (variable-block search: the clipped segments
+     * at the end of a stream follow one another), its own predecessor is looked up the same way: `chain` collects those
+     * calls, newest first, until one is reached that does not depend on anything (`seed`). */
+    auto depends = [&](const Job &j) { return (j.nsmpl & 1u) != 0u || (kLtp && ceil_pow2_u32(j.nsmpl) < (uint32_t)kLtpMaxPeriod + 1u); };
+    auto reach = [&](const Job &j) {                    /* the highest scratch index the call reads before writing it */
+        uint32_t r = (j.nsmpl & 1u) ? ((j.nsmpl - 1u) >> 1) : 0u;
+        if (kLtp && ceil_pow2_u32(j.nsmpl) < (uint32_t)kLtpMaxPeriod + 1u) { r = max(r, ceil_pow2_u32(j.nsmpl)); }
+        return r;
+    };
+    constexpr int kMaxChain = 12;
+    uint32_t chain[kMaxChain]; int depth = 0;
+    uint32_t seed = 0xffffffffu;
+    {
+        uint32_t pos = tj.job;
+        Job cur = job;
+        for (;;) {
+            const uint32_t need_idx = reach(cur);
+            uint32_t pred = pos;
+            bool found = false;
+            while (!found && pred > tj.first_of_stream) {
+                pred--;
+                const Job pj = jobs_all[pred];
+                int nz = 0;
+                if (pj.nsmpl > P && ceil_pow2_u32(pj.nsmpl) > need_idx) {
+                    for (uint32_t ch = 0; ch < p.nch; ++ch) { for (uint32_t i = tid; i < pj.nsmpl; i += kT) { nz |= load_sample(st, ch, pj.offset + i); } }
+                }
+                found = __syncthreads_or(nz) != 0;
+            }
+            if (!found) { break; }
+            const Job pj = jobs_all[pred];
+            if (!depends(pj) || depth == kMaxChain) { seed = pred; break; }
+            chain[depth++] = pred; pos = pred; cur = pj;
         }
-        found = __syncthreads_or(nz) != 0;
     }
-    if (found) {
+    if (seed != 0xffffffffu) {
         /* its last call: the last candidate (the reference analyses M, S first, then the channels in order) */
-        const Job pj = jobs_all[pred];
+        const Job pj = jobs_all[seed];
         front_chain_step<kT, kLtp>(p, pj, st, p.ncand - 1u, lshift, L, smem, pbuf, &scratch_out, pbuf + pbuf_len, 1u, red64, sh_i, sh_u);   /* lags to a dump area */
     }
-    const uint32_t rel = tj.job - group_first;
+    for (int d = depth - 1; d >= 0; --d) {
+        const Job cj = jobs_all[chain[d]];
+        for (uint32_t cand = 0; cand < p.ncand; ++cand) {
+            front_chain_step<kT, kLtp>(p, cj, st, cand, lshift, L, smem, pbuf, &scratch_out, pbuf + pbuf_len, 1u, red64, sh_i, sh_u);
+        }
+    }
+    const uint32_t rel = tj.out - group_first;
     for (uint32_t cand = 0; cand < p.ncand; ++cand) {
         const uint32_t idx = rel * p.ncand + cand;
         double *g = p.lags + (size_t)(idx >> 5) * p.lag_stride * 32u + (idx & 31u);

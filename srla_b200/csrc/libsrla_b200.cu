@@ -171,7 +171,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> ev_h2d, ev_grp, ev_d2h;
     std::vector<Job> jobs_scratch;
     std::vector<TailJob> tails_scratch;   /* tail blocks of the fixed tiling that need front_tail_kernel (odd, or short with LTP) */
-    DevBuf tails, tail_scratch;
+    DevBuf tails, tail_scratch, chain;   /* chain: variable blocks -- the reference's call list around a stream's end (front_tail_kernel) */
     std::vector<uint32_t> jobs_key;   /* stream lengths + block size of the fixed tiling that jobs_scratch and the device copy hold */
     bool jobs_cached = false;
     int max_smem_optin = 0;
@@ -310,7 +310,7 @@ void ctx_destroy(DeviceCtx *c)
     if (c->ev_begin) { cudaEventDestroy(c->ev_begin); }
     if (c->ev_end) { cudaEventDestroy(c->ev_end); }
     if (c->ev_upload) { cudaEventDestroy(c->ev_upload); }
-    DevBuf *bufs[] = { &c->tails, &c->tail_scratch, &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
+    DevBuf *bufs[] = { &c->chain, &c->tails, &c->tail_scratch, &c->tw_complex, &c->tw_real, &c->rice_thr, &c->huff_code, &c->huff_len, &c->streams, &c->jobs,
                        &c->misc, &c->stream_begin, &c->pcm, &c->out, &c->raw };
     for (DevBuf *b : bufs) { b->release(); }
     c->h_jobs.release(); c->h_small.release(); c->h_jobout.release(); c->h_result.release(); c->h_stage.release(); c->h_stage_out.release();
@@ -560,7 +560,7 @@ struct Runner {
     /* the three analysis kernels: front (autocorrelation) -> lpc (Levinson-Durbin) -> residual (FIR + Rice search) */
     /* tails [tail_lo, tail_hi) of c->tails_scratch lie in this launch's jobs, which start at index group_first of c->jobs */
     bool launch_analyse(const LaunchParams &p_in, size_t batch, cudaStream_t on, size_t tail_lo = 0, size_t tail_hi = 0, uint32_t group_first = 0,
-                        bool pcm16_only = false)
+                        bool pcm16_only = false, const Job *tail_list = nullptr)
     {
         LaunchParams p = p_in;
         const FrontLayout FL = make_front_layout(p.nmax, p.fft_max, p.ltp_order);
@@ -654,7 +654,7 @@ struct Runner {
                 if (!c->tail_scratch.reserve((size_t)nt * pbuf_bytes)) { return false; }
                 pbuf_global = (double *)c->tail_scratch.p;
             }
-            const Job *all = (const Job *)c->jobs.p;
+            const Job *all = tail_list ? tail_list : (const Job *)c->jobs.p;       /* the call list the tails' predecessors are looked up in */
             if (p.fft_max <= 4096u) {
                 if (ltp) { if (!prep_kernel(front_tail_kernel<128, true>, smem_tail)) { return false; } front_tail_kernel<128, true><<<nt, 128, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
                 else { if (!prep_kernel(front_tail_kernel<128, false>, smem_tail)) { return false; } front_tail_kernel<128, false><<<nt, 128, smem_tail, on>>>(p, d_tails, all, group_first, pbuf_len, pbuf_global); }
@@ -731,7 +731,7 @@ struct Runner {
      * scan_done: recorded once this group's scan has run. */
     bool run_batch(const Plan &pl, const Job *d_jobs, uint32_t count, uint32_t nmax, bool emit, uint8_t *d_out, uint64_t cap,
                    bool store_residual, size_t ev_idx, unsigned long long *h_mailbox, int ln = 0,
-                   cudaEvent_t scan_after = nullptr, cudaEvent_t scan_done = nullptr, bool with_tails = false)
+                   cudaEvent_t scan_after = nullptr, cudaEvent_t scan_done = nullptr, bool with_tails = false, const Job *tail_list = nullptr)
     {
         DeviceCtx::Lane &L = c->lane[ln];
         const cudaStream_t on = L.stream;
@@ -763,14 +763,14 @@ struct Runner {
             /* d_jobs points into the call's fixed tiling (c->jobs): the tails whose job lies in [group_first, group_first + count) */
             group_first = (uint32_t)(d_jobs - (const Job *)c->jobs.p);
             const std::vector<TailJob> &tv = c->tails_scratch;
-            tail_lo = std::lower_bound(tv.begin(), tv.end(), group_first, [](const TailJob &t, uint32_t v) { return t.job < v; }) - tv.begin();
-            tail_hi = std::lower_bound(tv.begin(), tv.end(), group_first + count, [](const TailJob &t, uint32_t v) { return t.job < v; }) - tv.begin();
+            tail_lo = std::lower_bound(tv.begin(), tv.end(), group_first, [](const TailJob &t, uint32_t v) { return t.out < v; }) - tv.begin();
+            tail_hi = std::lower_bound(tv.begin(), tv.end(), group_first + count, [](const TailJob &t, uint32_t v) { return t.out < v; }) - tv.begin();
         }
         bool pcm16_only = true;
         for (uint32_t s = 0; s < pl.num_streams && pcm16_only; s++) { pcm16_only = pl.streams[s].sample_bytes == 2u; }
-        p.replay_tails = with_tails ? 1u : 0u; p.group_first = group_first; p.jobs_all = (const Job *)c->jobs.p;     /* big-block path */
+        p.replay_tails = (with_tails && !pl.variable) ? 1u : 0u; p.group_first = group_first; p.jobs_all = (const Job *)c->jobs.p;     /* big-block path */
         p.serial_streams = (serial_streams && !pl.variable) ? 1u : 0u;
-        if (!launch_analyse(p, ev_idx, on, tail_lo, tail_hi, group_first, pcm16_only)) { return false; }
+        if (!launch_analyse(p, ev_idx, on, tail_lo, tail_hi, group_first, pcm16_only, tail_list)) { return false; }
         if (!mark(ev_idx, 3, on)) { return false; }
         decide_kernel<<<(count + 127) / 128, 128, 0, on>>>(p);
         launches++;
@@ -917,7 +917,7 @@ struct Runner {
                 }
                 const uint32_t last_n = jobs.back().nsmpl;
                 if (replay_tails && last_n > enc->max_order && ((last_n & 1u) || (ltp > 0u && ceil_pow2_host(last_n) < 263u))) {
-                    TailJob tj; tj.job = (uint32_t)jobs.size() - 1u; tj.first_of_stream = first;
+                    TailJob tj; tj.job = (uint32_t)jobs.size() - 1u; tj.first_of_stream = first; tj.out = tj.job;
                     c->tails_scratch.push_back(tj);
                 }
             }
@@ -1052,11 +1052,22 @@ struct Runner {
             if (!launch_lshift(pl, (const Job *)c->jobs.p, (uint32_t)jobs.size(), nullptr, c->stream, ingest)) { return SRLA_APIRESULT_NG; }
         }
 
+        bool var_final_tails = false;
         if (pl.variable) {
             /* pass 1: exact size of every candidate segment of every look-ahead chunk */
-            struct Chunk { uint32_t stream, at, len, nodes, first_job; };
+            struct Chunk { uint32_t stream, at, len, nodes, first_job, num_jobs, final_begin, final_end; };
             std::vector<Chunk> chunks; std::vector<Job> cand_jobs;
             const uint32_t step = enc->param.num_lookahead_samples;
+            /* The reference's stale-scratch corners (front_tail_kernel) with variable blocks: a candidate segment clipped at
+             * the end of a stream can be odd (or, with LTP, shorter than the 263 lags the pitch search reads), and then its
+             * analysis depends on the calls in front of it.  cand_jobs lists the segments of a chunk in the reference's
+             * call order (srla_encoder.c:352-388), so the predecessors of such a segment are the list entries in front of
+             * it; the blocks the chunk is finally coded with follow the same way behind the whole search (:1660-1690). */
+            const uint32_t ltp_order = enc->param.ltp_order;
+            const bool var_tails = (max_block & 1u) == 0u && (min_block & 1u) == 0u && (ltp_order == 0u || min_block >= 263u)
+                                   && enc->max_order > 0u && max_block <= (uint32_t)kMaxSharedBlock;
+            auto dependent = [&](uint32_t n) { return n > enc->max_order && ((n & 1u) || (ltp_order > 0u && ceil_pow2_host(n) < 263u)); };
+            c->tails_scratch.clear();
             for (uint32_t s = 0; s < pl.num_streams; s++) {
                 const uint32_t total = pl.streams[s].num_samples;
                 for (uint32_t at = 0; at < total; at += step) {
@@ -1067,18 +1078,32 @@ struct Runner {
                             uint32_t len = (j - i) * min_block;
                             if (len > max_block) { continue; }
                             if (len > ch.len - i * min_block) { len = ch.len - i * min_block; }
+                            if (var_tails && dependent(len)) {
+                                TailJob tj; tj.job = (uint32_t)cand_jobs.size(); tj.first_of_stream = ch.first_job; tj.out = tj.job;
+                                c->tails_scratch.push_back(tj);
+                            }
                             cand_jobs.push_back(make_job(s, at + i * min_block, len, 0u, len_cache));
                         }
                     }
+                    ch.num_jobs = (uint32_t)cand_jobs.size() - ch.first_job; ch.final_begin = ch.final_end = 0;
                     chunks.push_back(ch);
                 }
             }
             stt.num_analysed += cand_jobs.size();
             std::vector<uint32_t> est(cand_jobs.size());
             if (!upload_jobs(cand_jobs)) { return SRLA_APIRESULT_NG; }
+            auto upload_tails = [&]() {
+                if (c->tails_scratch.empty()) { return true; }
+                const size_t bytes = sizeof(TailJob) * c->tails_scratch.size();
+                if (!c->tails.reserve(bytes)) { return false; }
+                /* pageable source: the copy is staged by the driver before the call returns */
+                return cudaMemcpyAsync(c->tails.p, c->tails_scratch.data(), bytes, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+            };
+            if (!upload_tails()) { return SRLA_APIRESULT_NG; }
             for (size_t b = 0; b < cand_jobs.size(); b += per_batch) {
                 const uint32_t cnt = (uint32_t)std::min<size_t>(per_batch, cand_jobs.size() - b);
-                if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, max_block, false, nullptr, 0, false, ev_idx++, nullptr)) { return SRLA_APIRESULT_NG; }
+                if (!run_batch(pl, (const Job *)c->jobs.p + b, cnt, max_block, false, nullptr, 0, false, ev_idx++, nullptr, 0, nullptr, nullptr,
+                               !c->tails_scratch.empty())) { return SRLA_APIRESULT_NG; }
                 if (!c->h_jobout.reserve(sizeof(JobOut) * cnt)) { return SRLA_APIRESULT_NG; }
                 if (cudaMemcpyAsync(c->h_jobout.p, c->lane[0].jobout.p, sizeof(JobOut) * cnt, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess
                     || cudaStreamSynchronize(c->stream) != cudaSuccess) { std::fprintf(stderr, "[srla_b200] size pass failed: %s\n", cudaGetErrorString(cudaGetLastError())); return SRLA_APIRESULT_NG; }
@@ -1087,7 +1112,7 @@ struct Runner {
             }
             /* shortest path per chunk -> final block list */
             jobs.clear();
-            for (const Chunk &ch : chunks) {
+            for (Chunk &ch : chunks) {
                 std::vector<uint32_t> edge((size_t)ch.nodes * ch.nodes, 0u);
                 uint32_t k = ch.first_job;
                 for (uint32_t i = 0; i < ch.nodes; i++) {
@@ -1099,16 +1124,51 @@ struct Runner {
                 std::vector<uint32_t> parts;
                 shortest_partition(edge, ch.nodes, min_block, ch.len, parts);
                 uint32_t off = 0;
+                ch.final_begin = (uint32_t)jobs.size();
                 for (uint32_t len : parts) {
                     jobs.push_back(make_job(ch.stream, ch.at + off, len, (ch.at + off == 0) ? kJobFirstOfStream : 0u, len_cache));
                     off += len;
                 }
+                ch.final_end = (uint32_t)jobs.size();
+            }
+            /* the coded blocks that depend on earlier calls: the call list in front of such a block is the previous chunk's
+             * coded blocks, this chunk's whole search, and this chunk's coded blocks in front of it */
+            c->tails_scratch.clear();
+            std::vector<Job> call_list;
+            if (var_tails) {
+                for (size_t ci = 0; ci < chunks.size(); ci++) {
+                    const Chunk &ch = chunks[ci];
+                    bool any = false;
+                    for (uint32_t k = ch.final_begin; k < ch.final_end; k++) { any = any || dependent(jobs[k].nsmpl); }
+                    if (!any) { continue; }
+                    const uint32_t first = (uint32_t)call_list.size();
+                    if (ci > 0 && chunks[ci - 1].stream == ch.stream) {
+                        for (uint32_t k = chunks[ci - 1].final_begin; k < chunks[ci - 1].final_end; k++) { call_list.push_back(jobs[k]); }
+                    }
+                    for (uint32_t k = 0; k < ch.num_jobs; k++) { call_list.push_back(cand_jobs[ch.first_job + k]); }
+                    for (uint32_t k = ch.final_begin; k < ch.final_end; k++) {
+                        if (dependent(jobs[k].nsmpl)) {
+                            TailJob tj; tj.job = (uint32_t)call_list.size(); tj.first_of_stream = first; tj.out = k;
+                            c->tails_scratch.push_back(tj);
+                        }
+                        call_list.push_back(jobs[k]);
+                    }
+                }
             }
             if (!upload_jobs(jobs)) { return SRLA_APIRESULT_NG; }
+            if (!c->tails_scratch.empty()) {
+                const size_t bytes = sizeof(Job) * call_list.size();
+                if (!c->chain.reserve(bytes)) { return SRLA_APIRESULT_NG; }
+                if (cudaMemcpyAsync(c->chain.p, call_list.data(), bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess
+                    || cudaStreamSynchronize(c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }       /* call_list is a local */
+                if (!upload_tails()) { return SRLA_APIRESULT_NG; }
+                var_final_tails = true;
+            }
         }
         stt.num_analysed += jobs.size();
         stt.num_blocks = pl.size_only ? 0 : jobs.size();
         for (const Job &j : jobs) { nmax = std::max(nmax, j.nsmpl); }
+        if (var_final_tails) { nmax = max_block; }            /* the replayed search segments can be longer than any coded block */
 
         /* ---- groups: [lshift so far] -> analyse -> decide -> scan -> emit ---- */
         if (pl.variable) {                      /* the final block list replaces the fixed tiling */
@@ -1181,7 +1241,8 @@ struct Runner {
             const bool chain = lanes_now > 1;
             if (!run_batch(pl, (const Job *)c->jobs.p + j0, cnt, nmax, !pl.size_only, d_out, cap, !pl.size_only, ev_idx++,
                            pipelined ? mailbox + g : nullptr, ln,
-                           (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr, use_tails)) { return SRLA_APIRESULT_NG; }
+                           (chain && g > 0) ? c->ev_scan[g - 1] : nullptr, chain ? c->ev_scan[g] : nullptr, use_tails || var_final_tails,
+                           var_final_tails ? (const Job *)c->chain.p : nullptr)) { return SRLA_APIRESULT_NG; }
             if (pipelined && cudaEventRecord(grp_done[g], on) != cudaSuccess) { return SRLA_APIRESULT_NG; }
             if (c->trace) { host_launch.push_back(host_ms()); }
             if (pipelined) { recorded = g + 1; drain(false); }
@@ -1734,7 +1795,7 @@ SRLAApiResult SRLAB200_TestAnalyseChannel(
     const uint32_t ltp = encoder->param.ltp_order;
     const bool tail = (n & 1u) || (ltp > 0u && ceil_pow2_host(n) < 263u);
     if (tail) {
-        TailJob tj; tj.job = 0; tj.first_of_stream = 0;
+        TailJob tj; tj.job = 0; tj.first_of_stream = 0; tj.out = 0;
         c->tails_scratch.push_back(tj);
         if (!c->tails.reserve(sizeof(TailJob)) || cudaMemcpyAsync(c->tails.p, c->tails_scratch.data(), sizeof(TailJob), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { return SRLA_APIRESULT_NG; }
     }

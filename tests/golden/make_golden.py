@@ -63,6 +63,13 @@ def main():
     save("ltp_short_tail_4196_m4_b4096", synth_stereo(4196, seed=74), preset=4, max_block=4096, ltp=3)
     save("ltp_short_tail_odd_8391_m4_b4096", synth_stereo(8391, seed=75), preset=4, max_block=4096, ltp=3)
     save("odd9001_m4_v2_l4", synth_stereo(9001, seed=76), preset=4, max_block=4096, min_block=1024, lookahead=16384)
+    # the reference CLI's defaults (-m 4 -B 4096 -V 1 -L 4) on odd frame counts: the clipped segments at the end follow one another,
+    # a stream end inside the first segment of a chunk, a silent stretch in front of the end, LTP
+    save("odd50001_m4_v1_l4", synth_stereo(50001, seed=77), preset=4, max_block=4096, min_block=2048, lookahead=16384)
+    save("odd16385_m4_v1_l4", synth_stereo(16385, seed=78), preset=4, max_block=4096, min_block=2048, lookahead=16384)
+    quiet = synth_stereo(16384 + 3001, seed=81); quiet[:, 16384 - 100:16384 + 2048] = 0
+    save("odd19385_silence_m4_v1_l4", quiet, preset=4, max_block=4096, min_block=2048, lookahead=16384)
+    save("odd21385_m3_v2_l2_ltp3", synth_stereo(16384 + 5001, seed=82), preset=3, max_block=4096, min_block=1024, lookahead=8192, ltp=3)
     # blocks beyond 8192 samples (the reference CLI admits -B up to 65535; this implementation up to 16384)
     save("stereo16_m4_b16384", synth_stereo(16384 * 2 + 5001, seed=79), preset=4, max_block=16384)
     save("stereo24_m3_b16384_ltp3", synth_stereo(16384 + 9000, seed=80, bits=24), bps=24, preset=3, max_block=16384, ltp=3)
