@@ -2344,6 +2344,9 @@ __device__ __forceinline__ void residual_finish(const LaunchParams &p, CandOut *
  * Same arithmetic as residual_kernel (shared device functions); items a bulk copy cannot serve (rows that are not
  * 16-byte aligned or not a multiple of 8 samples, e.g. a stream's tail block) are loaded with plain loads.
  * ---------------------------------------------------------------------------------------------- */
+#ifndef SRLA_R16_OCC
+#define SRLA_R16_OCC 4
+#endif
 struct Resid16Desc {
     uint32_t n, skip, bulk, order, rshift, lshift, kind, two_rows;      /* kind 0: mid, 1: side, 2: a channel as it is */
     int32_t  pre_coef;
@@ -2392,7 +2395,7 @@ __device__ __forceinline__ int32_t cand16_filtered(const short *row0, const shor
     return (int32_t)((uint32_t)cur - (uint32_t)((int32_t)((uint32_t)prv * (uint32_t)d.pre_coef) >> 4));
 }
 
-__global__ void __launch_bounds__(kThreads, 4) residual16_kernel(const __grid_constant__ LaunchParams p)
+__global__ void __launch_bounds__(kThreads, SRLA_R16_OCC) residual16_kernel(const __grid_constant__ LaunchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const Resid16Layout L = make_resid16_layout(p.nmax, p.max_order);

@@ -686,7 +686,7 @@ struct Runner {
             /* 16-bit PCM without LTP: persistent CTAs, source rows staged one item ahead by bulk asynchronous copies */
             const Resid16Layout R16 = make_resid16_layout(p.nmax, p.max_order);
             if (!prep_kernel(residual16_kernel, R16.total)) { return false; }
-            const uint32_t per_sm = std::max(1u, std::min(4u, (uint32_t)(227u * 1024u) / (R16.total + 1024u)));
+            const uint32_t per_sm = std::max(1u, std::min((uint32_t)SRLA_R16_OCC, (uint32_t)(227u * 1024u) / (R16.total + 1024u)));
             residual16_kernel<<<std::min(ncands, (uint32_t)c->num_sms * per_sm), block, R16.total, on>>>(p);
         } else {
             if (!prep_kernel(residual_kernel, RL.total)) { return false; }

@@ -49,3 +49,19 @@ with D.Decoder() as dec:
     s = bytearray(E.encode(odd, preset=4, max_block=4096))
     s[30 + 9] = 0; s[30 + 10] = 0                      # first block announces zero samples
     print("zero-sample block ->", dec.decode_whole_rc(bytes(s), 2, odd.shape[1])[0])
+# ---- second half of round 2: front16_kernel (rows by cp.async.bulk, plain-load fallback, offset shift, mono), the lane split of a
+# device-resident-sized call, variable blocks on odd lengths (front_tail_kernel's call chains) ----
+sh = (synth_stereo(4096 * 2 + 37, seed=41) // 4) * 4                         # common trailing zeros: offset shift 2, ragged tail
+print("front16 shifted + ragged", E.encode(sh, preset=4, max_block=4096) == oracle_encode(sh, preset=4, max_block=4096))
+mono = synth_stereo(4096 * 2 + 100, seed=42)[:1]
+print("front16 mono", E.encode(mono, preset=4, max_block=4096) == oracle_encode(mono, preset=4, max_block=4096))
+for n, v in ((16384 + 2049, 1), (9001, 2), (777, 1)):
+    x = synth_stereo(n, seed=43 + n)
+    kw = dict(preset=4, max_block=4096, min_block=4096 >> v, lookahead=16384)
+    print("variable blocks, odd length", n, v, E.encode(x, **kw) == oracle_encode(x, **kw))
+long_ = synth_stereo(4096 * 2100, seed=44)                                    # >= 2048 blocks: three groups on three lanes
+with E.Encoder(max_channels=2, max_block=4096) as enc:
+    assert enc.set_parameter(2, 16, 48000, 4096, 4096, 4096, 0, 4) == E.OK
+    o, offs = enc.encode_streams_host([long_.astype(np.int16)])
+    import hashlib
+    print("lane split, 2100 blocks", len(o[:offs[1]]), hashlib.sha1(o[:offs[1]].tobytes()).hexdigest()[:12])
