@@ -245,7 +245,7 @@ bool ctx_init(DeviceCtx *c)
     if (const char *e = std::getenv("SRLA_B200_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= kMaxLanes) { c->lanes = v; } }
     if (const char *e = std::getenv("SRLA_B200_CARVE")) { if (e[0] == 'm') { c->sized_carveout = 0; } }
     if (const char *e = std::getenv("SRLA_B200_RAMP")) { c->ramp = std::atoi(e); }
-    c->feed_threads = (int)std::max(2u, std::min(16u, usable_cpus()));
+    { const unsigned cpus = usable_cpus(); c->feed_threads = (int)std::max(2u, std::min(16u, cpus >= 8u ? cpus - 2u : cpus)); }   /* two CPUs stay free for the caller's thread and the driver's: a full team sometimes loses a 3 ms time slice (measured) */
     if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->feed_threads = v; } }
     if (const char *e = std::getenv("SRLA_B200_TRACE")) { c->trace = std::atoi(e); }
     if (const char *e = std::getenv("SRLA_B200_RESID16")) { c->resid16 = std::atoi(e); }
