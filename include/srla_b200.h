@@ -128,7 +128,9 @@ SRLAApiResult SRLAEncoder_EncodeOptimalPartitionedBlock(
     uint8_t *data, uint32_t data_size, uint32_t *output_size);
 
 /* include/srla_encoder.h:77-81 (srla_encoder.c:1701-1788): header + all blocks of a stream.
- * input = planar host int32 PCM (sign-extended), num_samples per channel. */
+ * input = planar host int32 PCM (sign-extended), num_samples per channel.
+ * encode_callback: one call per block (per look-ahead chunk with variable blocks) in stream order, like
+ * srla_encoder.c:1780-1782; long inputs report while later blocks are still being encoded. */
 SRLAApiResult SRLAEncoder_EncodeWhole(
     struct SRLAEncoder *encoder, const int32_t *const *input, uint32_t num_samples,
     uint8_t *data, uint32_t data_size, uint32_t *output_size, SRLAEncoder_EncodeBlockCallback encode_callback);

@@ -482,6 +482,10 @@ struct Runner {
     LenCache len_cache;
     uint64_t launches = 0;
     bool narrow_overflow = false;      /* the feeder met a sample outside int16: the caller redoes the call with the int32 layout */
+    /* pipelined host path: called on the caller's thread whenever more encoded bytes have arrived in host memory --
+     * (where they can be read, how many of the stream's bytes are there).  EncodeWhole reports progress through it while
+     * the later groups are still being encoded (srla_encoder.c:1780-1782 calls back after every block). */
+    std::function<void(const uint8_t *, uint64_t)> on_ready;
     bool serial_streams = false;       /* odd block size: the analysis calls of a stream form one chain (front_big_kernel) */
 
     LaunchParams base_params(const Plan &pl, uint32_t nmax) const
@@ -1215,8 +1219,10 @@ struct Runner {
                 drained++;
             }
             if (staged) {
+                const size_t before = published;
                 while (published < drained && cudaEventQuery(c->ev_d2h[published]) == cudaSuccess) { feeder.out_ready.store(gend[published], std::memory_order_release); published++; }
                 (void)cudaGetLastError();                      /* cudaEventQuery's cudaErrorNotReady is not an error */
+                if (on_ready && published > before) { on_ready(h_dst, gend[published - 1]); }
             }
         };
         if (pipelined) { poll_d2h = [&] { drain(false); }; }
@@ -1580,12 +1586,35 @@ SRLAApiResult SRLAEncoder_EncodeWhole(
                   && c->h_stage.reserve(sizeof(int16_t) * stride * nch);
     uint64_t offs[2] = { 0, 0 };
     SRLAApiResult rc = SRLA_APIRESULT_NG;
+    /* progress callbacks, one per top-level step (srla_encoder.c:1756-1783): `report` walks the block headers of the bytes
+     * that exist so far and calls back for every step that is complete.  On the pipelined path it runs while later groups
+     * are still being encoded (a progress display moves during a long file); whatever is left is reported after the call. */
+    const uint32_t cb_step = pl.variable ? encoder->param.num_lookahead_samples : encoder->param.max_num_samples_per_block;
+    uint32_t cb_progress = 0; uint64_t cb_pos = SRLA_HEADER_SIZE;
+    auto report = [&](const uint8_t *bytes, uint64_t ready) {
+        if (encode_callback == NULL) { return; }
+        while (cb_progress < num_samples) {
+            const uint32_t todo = std::min(cb_step, num_samples - cb_progress);
+            uint32_t got = 0; uint64_t pos = cb_pos;
+            while (got < todo && pos + 11 <= ready) {
+                const uint32_t size = ((uint32_t)bytes[pos + 2] << 24) | ((uint32_t)bytes[pos + 3] << 16) | ((uint32_t)bytes[pos + 4] << 8) | bytes[pos + 5];
+                if (pos + 6ull + size > ready) { return; }                    /* the block is not complete yet */
+                got += ((uint32_t)bytes[pos + 9] << 8) | bytes[pos + 10];
+                pos += 6ull + size;
+            }
+            if (got < todo) { return; }
+            cb_progress += todo;
+            encode_callback(num_samples, cb_progress, bytes + cb_pos, (uint32_t)(pos - cb_pos));
+            cb_pos = pos;
+        }
+    };
     for (;;) {
         struct SRLAB200Stream desc;
         desc.pcm = c->pcm.p; desc.channel_stride = stride; desc.num_samples = num_samples; desc.sample_bytes = narrow ? 2u : 4u;
         HostIO io; io.streams = &hs; io.out = data; io.out_capacity = data_size; io.narrow = narrow;
         pl.streams = &desc;
         Runner r{ encoder, c };
+        if (encode_callback != NULL) { r.on_ready = report; }
         rc = r.run(pl, (uint8_t *)c->out.p, cap, offs, nullptr, &io);
         if (narrow && r.narrow_overflow) { narrow = false; continue; }       /* samples beyond 16 bits: int32 layout */
         break;
@@ -1593,22 +1622,7 @@ SRLAApiResult SRLAEncoder_EncodeWhole(
     if (rc != SRLA_APIRESULT_OK) { return rc; }
     *output_size = (uint32_t)offs[1];
     encoder->offset_lshift = data[24];                        /* the reference keeps it in its header (srla_encoder.c:1732) */
-    if (encode_callback != NULL) {
-        /* replay: one call per top-level step (srla_encoder.c:1756-1783) */
-        const uint32_t step = pl.variable ? encoder->param.num_lookahead_samples : encoder->param.max_num_samples_per_block;
-        uint32_t progress = 0; uint64_t pos = SRLA_HEADER_SIZE;
-        while (progress < num_samples && pos + 11 <= offs[1]) {
-            const uint32_t todo = std::min(step, num_samples - progress);
-            uint32_t got = 0; const uint64_t begin = pos;
-            while (got < todo && pos + 11 <= offs[1]) {
-                const uint32_t size = ((uint32_t)data[pos + 2] << 24) | ((uint32_t)data[pos + 3] << 16) | ((uint32_t)data[pos + 4] << 8) | data[pos + 5];
-                got += ((uint32_t)data[pos + 9] << 8) | data[pos + 10];
-                pos += 6ull + size;
-            }
-            progress += todo;
-            encode_callback(num_samples, progress, data + begin, (uint32_t)(pos - begin));
-        }
-    }
+    report(data, offs[1]);                                    /* the steps not reported while the call ran */
     return SRLA_APIRESULT_OK;
 }
 

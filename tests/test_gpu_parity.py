@@ -259,6 +259,27 @@ def test_callback_sequence():
     assert all(c[0] == 10000 for c in calls)
 
 
+def test_callbacks_of_a_long_stream_arrive_in_order_with_the_blocks_bytes():
+    """EncodeWhole on a stream long enough for the pipelined path (>= 2048 blocks): one callback per block, progress in steps
+    of the block size, and the bytes at the pointer are the block the finished stream holds at that place (on this path the
+    callbacks fire while later groups are still being encoded, srla_encoder.c:1780-1782)"""
+    import ctypes as C
+    pcm = np.tile(synth_stereo(4096 * 8, seed=29), (1, 270))[:, :4096 * 2100 + 1000]
+    calls = []
+
+    def cb(n, prog, ptr, size):
+        calls.append((n, prog, size, bytes(C.cast(ptr, C.POINTER(C.c_uint8 * 11)).contents)))
+
+    out = E.encode(pcm, preset=4, max_block=4096, callback=cb)
+    blocks = list(walk_blocks(out))
+    assert len(calls) == len(blocks) == 2101
+    assert [c[1] for c in calls] == [min(4096 * (k + 1), pcm.shape[1]) for k in range(2101)]
+    assert [c[2] for c in calls] == [6 + size for _pos, size, _t, _n in blocks]
+    assert all(c[3] == out[pos:pos + 11] for c, (pos, _size, _t, _n) in zip(calls, blocks))
+    want = oracle_encode(pcm, preset=4, max_block=4096)
+    assert out == want, _first_diff(out, want)
+
+
 def test_batch_host_api_matches_per_stream_encode():
     """SRLAB200_EncodeStreamsHost on int16 host buffers: every stream equals its own EncodeWhole"""
     streams = [synth_stereo(n, seed=200 + i) for i, n in enumerate((9000, 4096, 12345, 100))]
