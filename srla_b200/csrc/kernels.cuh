@@ -287,7 +287,9 @@ __device__ __forceinline__ double int_to_double(int32_t x)
  * index: `stale` */
 template <bool kPre, bool kChain = false>
 struct WindowSource {
-    static constexpr uint32_t kFixedM = 0u, kFixedThreads = 0u;
+    /* full blocks of 8192 samples in a CTA of 256 threads run the literal-size passes (see welch_autocorr_core) */
+    static constexpr uint32_t kFixedM = kChain ? 0u : 4096u, kFixedThreads = kChain ? 0u : 256u;
+    __device__ __forceinline__ void first_pass_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b) const;
     const int32_t *sig; uint32_t n, half_n, pc; double unit, div, dn1;
     double stale;
     bool full;                    /* n is the transform size: no zero padding, the window halves meet at n / 2 */
@@ -482,6 +484,21 @@ __device__ __forceinline__ void WindowSource<kPre, kChain>::first_pass(double2 *
     fft_pair_pass<WindowSource<kPre, kChain>, true>(x, M, nn, lgs, tw_a, tw_b, need, *this);
 }
 
+/* WindowSource's first pass with the transform size a literal (a full block: n == 2 kM); scalar arguments travel in registers */
+template <bool kPre, uint32_t kM>
+__device__ __noinline__ void fft_first_pass_sig_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b, const uint32_t sig_shared, const uint32_t pc, const double div)
+{
+    WindowSource<kPre, false> ws;
+    ws.sig = reinterpret_cast<const int32_t *>(__cvta_shared_to_generic((size_t)sig_shared));
+    ws.n = 2u * kM; ws.half_n = kM; ws.pc = pc; ws.unit = 1.0; ws.div = div; ws.dn1 = (double)(int32_t)(2u * kM - 1u); ws.stale = 0.0; ws.full = true;
+    fft_pair_pass_impl<WindowSource<kPre, false>, true, true>(x, kM, kM, 0u, tw_a, tw_b, kM, ws);
+}
+template <bool kPre, bool kChain>
+__device__ __forceinline__ void WindowSource<kPre, kChain>::first_pass_fixed(double2 *x, const double2 *tw_a, const double2 *tw_b) const
+{
+    if constexpr (!kChain) { fft_first_pass_sig_fixed<kPre, 4096u>(x, tw_a, tw_b, (uint32_t)__cvta_generic_to_shared(sig), pc, div); }
+}
+
 /* the stages left after the fused pairs: nn = 8 (radix-4 + radix-2), 4 (radix-4) or 2 (radix-2).  A tail unit
  * reads and writes exactly the same positions (u + k * s), so units are independent of each other: no barrier
  * between loads and stores, and a thread walks its units one at a time.  Units beyond `need` are skipped. */
@@ -645,19 +662,33 @@ __device__ __forceinline__ void welch_autocorr_core(const Src &ws, const uint32_
     if constexpr (Src::kFixedM != 0u) {
         /* the usual transform size of this source: the same passes with every size, stride and trip count a literal, so the
          * index arithmetic of the general code folds away (kernels that run with Src::kFixedThreads threads only) */
-        static_assert(Src::kFixedM == 2048u && Src::kFixedThreads == 128u && !kChain, "stage plan below: 2048 = 4^5 * 2, one 16-point unit per thread");
-        if (M == Src::kFixedM && ws.full) {                     /* a full block: n == 2 M */
+        static_assert(!kChain && ((Src::kFixedM == 2048u && Src::kFixedThreads == 128u) || (Src::kFixedM == 4096u && Src::kFixedThreads == 256u)),
+                      "stage plans below: 2048 = 4^5 * 2 and 4096 = 4^6, one 16-point unit per thread");
+        if (M == Src::kFixedM && ws.full && blockDim.x == Src::kFixedThreads) {                     /* a full block: n == 2 M */
             constexpr uint32_t FM = Src::kFixedM, FT = Src::kFixedThreads;
-            const double2 *t11 = p.tw_complex + p.tw_complex_off[11], *t9 = p.tw_complex + p.tw_complex_off[9];
-            const double2 *t7 = p.tw_complex + p.tw_complex_off[7], *t5 = p.tw_complex + p.tw_complex_off[5], *t3 = p.tw_complex + p.tw_complex_off[3];
             const uint32_t need = (want + 1u) >> 1;
-            ws.first_pass_fixed(cx, t11, t9);
-            fft_pair_pass_fixed<FM, 128u, 4u, true>(cx, t7, t5, FM);
-            fft_tail_pass_fixed<FM, 8u, FT, true>(cx, t3, FM);
-            real_split_power(cx, 2u * FM, p, tid, FT);
-            fft_pair_pass_fixed<FM, FM, 0u, true>(cx, t11, t9, FM);
-            fft_pair_pass_fixed<FM, 128u, 4u, false>(cx, t7, t5, need);
-            fft_tail_pass_fixed<FM, 8u, FT, false>(cx, t3, need);
+            if constexpr (FM == 2048u) {
+                const double2 *t11 = p.tw_complex + p.tw_complex_off[11], *t9 = p.tw_complex + p.tw_complex_off[9];
+                const double2 *t7 = p.tw_complex + p.tw_complex_off[7], *t5 = p.tw_complex + p.tw_complex_off[5], *t3 = p.tw_complex + p.tw_complex_off[3];
+                ws.first_pass_fixed(cx, t11, t9);
+                fft_pair_pass_fixed<FM, 128u, 4u, true>(cx, t7, t5, FM);
+                fft_tail_pass_fixed<FM, 8u, FT, true>(cx, t3, FM);
+                real_split_power(cx, 2u * FM, p, tid, FT);
+                fft_pair_pass_fixed<FM, FM, 0u, true>(cx, t11, t9, FM);
+                fft_pair_pass_fixed<FM, 128u, 4u, false>(cx, t7, t5, need);
+                fft_tail_pass_fixed<FM, 8u, FT, false>(cx, t3, need);
+            } else {
+                /* three fused pairs, no stage left behind them */
+                const double2 *t12 = p.tw_complex + p.tw_complex_off[12], *t10 = p.tw_complex + p.tw_complex_off[10], *t8 = p.tw_complex + p.tw_complex_off[8];
+                const double2 *t6 = p.tw_complex + p.tw_complex_off[6], *t4 = p.tw_complex + p.tw_complex_off[4], *t2 = p.tw_complex + p.tw_complex_off[2];
+                ws.first_pass_fixed(cx, t12, t10);
+                fft_pair_pass_fixed<FM, 256u, 4u, true>(cx, t8, t6, FM);
+                fft_pair_pass_fixed<FM, 16u, 8u, true>(cx, t4, t2, FM);
+                real_split_power(cx, 2u * FM, p, tid, FT);
+                fft_pair_pass_fixed<FM, FM, 0u, true>(cx, t12, t10, FM);
+                fft_pair_pass_fixed<FM, 256u, 4u, true>(cx, t8, t6, FM);
+                fft_pair_pass_fixed<FM, 16u, 8u, false>(cx, t4, t2, need);
+            }
             for (uint32_t i = tid; i < nlags; i += FT) {
                 const double2 e = cx[fft_slot(i >> 1)];
                 lags[(size_t)i * lag_step] = (i < 2u * FM) ? ((i & 1u) ? -e.y : e.x) * ac_scale : 0.0;
@@ -750,16 +781,70 @@ __device__ int detect_pitch(const double *r, uint32_t *period)
     return 0;
 }
 
+/* The same pick by ONE WARP (front_kernel: 255 other threads wait for it).  The three comparisons every lag enters -- rising
+ * zero crossing, falling zero crossing, local maximum -- are taken for all lags at once and kept as bit masks (`mask`: 27 words
+ * of shared memory); lane 0 then walks the segments with find-first-set instead of two loops over the lags, and only looks at
+ * the lags that ARE local maxima.  Same comparisons on the same values, same order of the candidates: the same period.
+ * Returns (in every lane) 0 / 1 like detect_pitch; *period is set in every lane. */
+__device__ int detect_pitch_warp(const double *r, uint32_t *period, uint32_t *mask, const uint32_t lane)
+{
+    const uint32_t lo = kLtpMinPeriod, hi = kLtpMaxPeriod;
+    for (uint32_t w = 0; w < 9u; ++w) {
+        const uint32_t j = 32u * w + lane;
+        bool up = false, down = false, top = false;
+        if (j >= 1u && j + 1u < (uint32_t)kLtpLags) {
+            const double a = r[j - 1u], b = r[j], c = r[j + 1u];
+            up = a < 0.0 && b > 0.0; down = b > 0.0 && c < 0.0; top = b > a && b > c;
+        }
+        const uint32_t mu = __ballot_sync(0xffffffffu, up), md = __ballot_sync(0xffffffffu, down), mt = __ballot_sync(0xffffffffu, top);
+        if (lane == 0u) { mask[w] = mu; mask[9u + w] = md; mask[18u + w] = mt; }
+    }
+    __syncwarp();
+    int found = 0; uint32_t result = 0;
+    if (lane == 0u) {
+        /* first set bit of a 288-bit mask at or behind `from`, or `none` */
+        auto next_bit = [&](const uint32_t *m, uint32_t from, uint32_t none) {
+            for (uint32_t w = from >> 5; w < 9u; ++w) {
+                uint32_t bits = m[w];
+                if (w == (from >> 5)) { bits &= 0xffffffffu << (from & 31u); }
+                if (bits) { return 32u * w + (uint32_t)__ffs((int)bits) - 1u; }
+            }
+            return none;
+        };
+        uint32_t cand[20], ncand = 0, i = lo;
+        double best_peak = 0.0;
+        while (i < hi && ncand < 20u) {
+            uint32_t start = next_bit(mask, i, hi);
+            if (start > hi) { start = hi; }
+            uint32_t end = (start + 1u < hi - 1u) ? next_bit(mask + 9, start + 1u, hi - 1u) : start + 1u;
+            if (start + 1u < hi - 1u && end > hi - 1u) { end = hi - 1u; }
+            uint32_t arg = 0; double peak = 0.0;
+            for (uint32_t j = next_bit(mask + 18, start, 0xffffffffu); j <= end; j = next_bit(mask + 18, j + 1u, 0xffffffffu)) {
+                if (r[j] > peak) { arg = j; peak = r[j]; }
+            }
+            if (arg) { cand[ncand++] = arg; if (peak > best_peak) { best_peak = peak; } }
+            i = end + 1u;
+        }
+        if (ncand && !(best_peak < 0.1 * r[0])) {
+            for (uint32_t k = 0; k < ncand; k++) { if (r[cand[k]] >= 0.9 * best_peak) { result = cand[k]; found = 1; break; } }
+        }
+    }
+    found = __shfl_sync(0xffffffffu, found, 0); result = __shfl_sync(0xffffffffu, result, 0);
+    *period = result;
+    return found;
+}
+
 /* 3-tap (or 1-tap) normal equations by Cholesky (lpc.c:573-631, 1558-1649) + 6-bit quantisation
- * (srla_encoder.c:1032-1047).  returns 0 ok / 1 the reference would fail.  serial, one thread. */
-__device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, int32_t *qcoef)
+ * (srla_encoder.c:1032-1047).  returns 0 ok / 1 the reference would fail.  serial, one thread.
+ * pitch: -1 = look for the pitch here (detect_pitch); 0 / 1 = the result of detect_pitch_warp, period in *period_out */
+__device__ int ltp_solve(double *r, const uint32_t order, uint32_t *period_out, int32_t *qcoef, const int pitch = -1)
 {
     double A[3][3], inv_diag[3], sol[3];
-    uint32_t period = 0;
+    uint32_t period = (pitch == 1) ? *period_out : 0u;
     const int dim = (int)order;
     *period_out = 0;
     if (fabs(r[0]) <= (double)FLT_MIN) { return 0; }                 /* lpc.c:1602 */
-    if (!detect_pitch(r, &period)) { return 0; }
+    if (pitch == 0 || (pitch < 0 && !detect_pitch(r, &period))) { return 0; }
     if (period < order / 2u + 1u) { return 0; }
     r[0] *= (1.0 + 1e-5);
     for (int i = 0; i < dim; i++) { for (int j = 0; j < dim; j++) { A[i][j] = r[(i > j) ? i - j : j - i]; } }
@@ -1051,11 +1136,15 @@ __global__ void __launch_bounds__(kT, kOcc) front_kernel(const __grid_constant__
 
     /* ---- long-term prediction (srla_encoder.c:1008-1058) ---- */
     welch_autocorr<false>(sig, 0, n, region_d, lags, 1u, kLtpLags, job, p);
+    /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
+    if ((uint32_t)tid < (uint32_t)kLtpLags - (kLtpMaxPeriod + 1u)) { lags[kLtpMaxPeriod + 1u + (uint32_t)tid] = 0.0; }
+    __syncthreads();
+    __shared__ uint32_t pitch_mask[27];
+    uint32_t period = 0; int pitch = 0;
+    if (tid < 32) { pitch = detect_pitch_warp(lags, &period, pitch_mask, (uint32_t)tid); }
     if (tid == 0) {
-        /* lags 0..262 come from the transform; 263.. are never written by the reference (zero pages) */
-        for (uint32_t i = kLtpMaxPeriod + 1u; i < (uint32_t)kLtpLags; ++i) { lags[i] = 0.0; }
-        uint32_t period = 0; int32_t q[3] = { 0, 0, 0 };
-        const int rc = ltp_solve(lags, p.ltp_order, &period, q);
+        int32_t q[3] = { 0, 0, 0 };
+        const int rc = ltp_solve(lags, p.ltp_order, &period, q, pitch);
         sh_u[0] = period; sh_u[1] = (uint32_t)rc; sh_i[1] = q[0]; sh_i[2] = q[1]; sh_i[3] = q[2];
         out->status = (uint32_t)rc;
         if (!rc && period > 0u) { out->ltp_period = period; out->ltp_coef[0] = q[0]; out->ltp_coef[1] = q[1]; out->ltp_coef[2] = q[2]; }

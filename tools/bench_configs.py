@@ -32,6 +32,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", type=int, default=128)
     ap.add_argument("--seconds", type=int, default=900, help="length of the config 3 / 4 streams (900 s = 86.4 M channel-samples)")
+    ap.add_argument("--only", type=str, default="", help="run only the configurations whose name starts with this (e.g. 3)")
     args = ap.parse_args()
     import torch
     from helpers import have_ref, ref_encode
@@ -50,6 +51,8 @@ def main() -> None:
         return pinned(np.ascontiguousarray(inter.astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3]).reshape(-1))
 
     def run(name, streams, bits, min_block, max_block, lookahead, ltp, ref_frames, svr=0):
+        if args.only and not name.startswith(args.only):
+            return
         with E.Encoder(max_channels=2, max_block=max_block, min_block=min_block, lookahead=lookahead) as enc:
             assert enc.set_parameter(2, bits, 48000, min_block, max_block, lookahead, ltp, 4, svr) == E.OK
             cap = sum(enc.max_encoded_size(s.shape[1]) for s in streams)
