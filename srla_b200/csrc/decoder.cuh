@@ -5,7 +5,8 @@
  * A stream decodes block by block and nothing crosses a block boundary (srla_decoder.c:633-799), so
  * a whole stream is two launches over all of its blocks.
  *   parse     (decode_parse_kernel) the bitstream of a block is serial (the second channel starts where
- *             the first one's codes end): one thread per block, a few blocks per warp, walks it -- side
+ *             the first one's codes end): one thread per block walks it, the lanes of a warp walk
+ *             different blocks in lockstep (one flat loop, one code per trip, branch-free refill) -- side
  *             information to a per-channel record, residual codes (srla_coder.c:596-690) straight into
  *             the output buffer.
  *   synthesis (decode_blocks_kernel) one CTA per block, one warp per channel.  Warp 0 sums the Fletcher-16
@@ -56,42 +57,69 @@ struct DecSideChannel {
 struct DecSide { uint32_t status, method; };
 
 /* ---- big-endian bit reader over global memory: 64-bit window, aligned 32-bit refills, one word prefetched.
- * After every operation more than 32 bits are valid, so any field of up to 32 bits and any code whose zero run,
- * stop bit and remainder fit 33 bits is taken from the window without touching memory. ---- */
+ * After every operation more than 32 bits are valid, so any field of up to 32 bits is taken from the window without
+ * touching memory, and a code whose zero run, stop bit and remainder fit 32 bits is taken from its upper half with
+ * 32-bit operations.  The lanes of a warp read different blocks in lockstep, so the refill has NO branch: the word is
+ * appended under a predicate and the next one is fetched by a predicated load. ---- */
+__device__ __forceinline__ uint32_t dec_load_if(const uint32_t *p, bool take, uint32_t otherwise)
+{
+    uint32_t v = otherwise;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((uint32_t)take));
+    return v;
+}
+
+__device__ __forceinline__ void dec_prefetch_if(const uint32_t *p, bool take)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q prefetch.global.L1 [%0];\n\t}" :: "l"(p), "r"((uint32_t)take));
+}
+
 struct DecBits {
-    const uint32_t *word;          /* next aligned word to fetch                                       */
-    const uint32_t *limit;         /* first word past the block                                        */
-    uint32_t ahead;                /* prefetched word (already byte-swapped)                           */
+    const uint32_t *base;          /* aligned word the block's first byte lies in                      */
+    uint32_t idx;                  /* next word to fetch, counted from base                            */
+    uint32_t limit;                /* first word past the block, counted from base                     */
+    uint32_t phase;                /* base's word position inside its 128-byte line                    */
+    uint32_t ahead;                /* prefetched word, still in memory byte order                      */
     unsigned long long win;        /* valid bits at the top                                            */
     int avail;
-    const uint32_t *base;          /* aligned word the block's first byte lies in                      */
-    int skip;                      /* bits of that word in front of the block                          */
-    __device__ __forceinline__ uint32_t fetch()
+    int skip;                      /* bits of the first word in front of the block                     */
+    /* under `take`: the next word (zero behind the block's end) becomes `ahead` */
+    __device__ __forceinline__ void fetch_if(bool take)
     {
-        const uint32_t v = (word < limit) ? __ldg(word) : 0u;
-        ++word;
-        return __byte_perm(v, 0u, 0x0123);
+        const bool inside = take && idx < limit;
+        const uint32_t *at = base + idx;
+        /* entering a 128-byte line: ask for the one behind it (one lane's miss would stall all the lanes walking with it);
+         * a prefetch has no result register, so nothing ever waits for it */
+        dec_prefetch_if(at + 32, inside && ((idx + phase) & 31u) == 0u && idx + 32u < limit);
+        ahead = dec_load_if(at, inside, take ? 0u : ahead);
+        idx += take ? 1u : 0u;
     }
     __device__ __forceinline__ void open(const uint8_t *p, const uint8_t *end)
     {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        word = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        limit = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(end) + 3) & ~(uintptr_t)3);
-        base = word;
+        base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        limit = (uint32_t)((((reinterpret_cast<uintptr_t>(end) + 3) & ~(uintptr_t)3) - (a & ~(uintptr_t)3)) >> 2);
+        phase = (uint32_t)(a >> 2) & 31u;
+        idx = 0u; ahead = 0u;
         skip = (int)(a & 3) * 8;
-        win = (unsigned long long)fetch() << 32;
+        dec_prefetch_if(base + (32u - phase), 32u - phase < limit);
+        fetch_if(true);
+        win = (unsigned long long)__byte_perm(ahead, 0u, 0x0123) << 32;
         win <<= skip;
         avail = 32 - skip;
-        ahead = fetch();
+        fetch_if(true);
         refill();
     }
     /* the reader ran past the end of the block (two words are always in flight): corrupt data */
-    __device__ __forceinline__ bool overrun() const { return word > limit + 3; }
+    __device__ __forceinline__ bool overrun() const { return idx > limit + 3u; }
     /* bits taken from the block so far: everything fetched minus what still waits in the window and the prefetched word */
-    __device__ __forceinline__ long long consumed_bits() const { return (long long)(word - base) * 32 - 32 - avail - skip; }
+    __device__ __forceinline__ long long consumed_bits() const { return (long long)idx * 32 - 32 - avail - skip; }
     __device__ __forceinline__ void refill()
     {
-        if (avail <= 32) { win |= (unsigned long long)ahead << (32 - avail); avail += 32; ahead = fetch(); }
+        const bool m = avail <= 32;
+        const unsigned long long add = (unsigned long long)__byte_perm(ahead, 0u, 0x0123) << ((32 - avail) & 63);
+        win |= m ? add : 0ull;
+        avail += m ? 32 : 0;
+        fetch_if(m);
     }
     __device__ __forceinline__ uint32_t get(uint32_t n)               /* n <= 32; 0 gives 0 (bit_stream.h: GetBits) */
     {
@@ -106,30 +134,12 @@ struct DecBits {
         uint32_t run = 0;
         for (;;) {
             const int z = __clzll((long long)win);                    /* 64 for an empty window */
-            if (z < avail) { win <<= (z + 1); avail -= z + 1; refill(); return run + (uint32_t)z; }
+            if (z < avail) { win = (win << z) << 1; avail -= z + 1; refill(); return run + (uint32_t)z; }
             run += (uint32_t)avail;
             win = 0; avail = 0;
             refill();
             if (overrun()) { return run; }
         }
-    }
-    /* zero run followed by a remainder of `low_bits(run)` bits, in one go when both lie in the window */
-    template <typename Low>
-    __device__ __forceinline__ void run_and_bits(Low low_bits, uint32_t *run_out, uint32_t *bits_out)
-    {
-        const int z = __clzll((long long)win);
-        const uint32_t nb = low_bits((uint32_t)z);
-        if (z + 1 + (int)nb <= avail && nb > 0u) {
-            const unsigned long long rest = win << (z + 1);
-            *run_out = (uint32_t)z;
-            *bits_out = (uint32_t)(rest >> (64 - nb));
-            win = rest << nb; avail -= z + 1 + (int)nb;
-            refill();
-            return;
-        }
-        const uint32_t run = zero_run();
-        *run_out = run;
-        *bits_out = get(low_bits(run));
     }
 };
 
@@ -144,9 +154,16 @@ struct DecChannel {
     uint32_t ltp_order, ltp_period;
     int32_t ltp_coef[4];
     int32_t cp[32 * kDecMaxTaps + 4];          /* cp[d] multiplies x[m - d], d = 1 .. order; 0 elsewhere */
+    int32_t rot[kDecMaxTaps][64];              /* rot[t][i] = cp[(i & 31) + 1 + 32 t]: in step s of a round lane L reads rot[t][31 + L - s],
+                                                  a fixed address per lane plus a literal in the unrolled round */
 };
 
-/* LPC synthesis of one channel by one warp, T accumulators per lane (order <= 32 T) */
+/* LPC synthesis of one channel by one warp, T accumulators per lane (order <= 32 T).  Lane L owns the outputs
+ * m = L (mod 32); in step s of a round of 32 samples lane s's candidate is final and is broadcast, and every lane
+ * adds the product with the tap that lies between that sample and its own next output.  Rounds that touch the
+ * warm-up samples (srla_lpc_synthesize.c:253-262) or the end of the block run the general loop; the full rounds
+ * behind the warm-up run unrolled: the tap of step s sits at a literal offset from a per-lane address, the owner
+ * test compares with a literal. */
 template <int T>
 __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const DecChannel &chn, uint32_t lane)
 {
@@ -157,10 +174,29 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
     for (int t = 0; t < T; ++t) { acc[t] = 0u; }
     uint32_t xprev = 0u, mine = 0u;
     uint32_t next_res = (lane < n) ? (uint32_t)x[lane] : 0u;
+    const int32_t *taps = &chn.rot[0][31u + lane];
     for (uint32_t base = 0; base < n; base += 32u) {
         const uint32_t own = base + lane;
         const uint32_t res = next_res;                                              /* this lane's output of the round */
         next_res = (own + 32u < n) ? (uint32_t)x[own + 32u] : 0u;                   /* fetched a round ahead */
+        if (base >= order && n - base >= 32u) {
+            #pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                const uint32_t cand = res - (uint32_t)((int32_t)(acc[0] + half) >> rshift);
+                const uint32_t xq = __shfl_sync(0xffffffffu, cand, s);
+                if (lane == (uint32_t)s) {
+                    mine = xq;
+                    #pragma unroll
+                    for (int t = 0; t + 1 < T; ++t) { acc[t] = acc[t + 1]; }
+                    acc[T - 1] = 0u;
+                }
+                #pragma unroll
+                for (int t = 0; t < T; ++t) { acc[t] += (uint32_t)taps[64 * t - s] * xq; }
+                xprev = xq;
+            }
+            x[own] = (int32_t)mine;
+            continue;
+        }
         const uint32_t steps = (n - base < 32u) ? n - base : 32u;
         for (uint32_t s = 0; s < steps; ++s) {
             const uint32_t q = base + s;
@@ -186,101 +222,167 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
     __syncwarp();
 }
 
-/* The serial walk over a compressed block (srla_decoder.c:436-540, srla_coder.c:596-690): ONE THREAD per block, a
- * few blocks per warp (the launch picks how many lanes of a warp work: more lanes share the instruction issue, fewer
- * lanes mean more warps to hide latency with).  Side information goes to p.side / p.side_ch, residuals straight into
- * the output buffer.  Header problems (sync, size, checksum, type) are judged by decode_blocks_kernel; blocks that
- * are not well-formed compressed blocks are skipped here. */
-__global__ void __launch_bounds__(32) decode_parse_kernel(const DecParams p)
+/* The serial walk over a compressed block (srla_decoder.c:436-540, srla_coder.c:596-690).  A block's bitstream is one
+ * chain of dependent operations per code (window -> zero run -> code length -> shifted window -> refill), and every
+ * block is walked by ONE thread; the lanes of a warp walk different blocks in LOCKSTEP: one flat loop whose trip is one
+ * code, taken from the upper half of the window without a branch (zero run, stop bit and remainder in at most 32
+ * bits; anything longer takes the general path).  Partition parameters and channel heads are read in a rarely taken
+ * branch -- partitions are power-of-two fractions of a block, so the lanes mostly take it in the same trip.  Side
+ * information goes to p.side / p.side_ch, residuals straight into the output buffer.  Header problems (sync, size,
+ * checksum, type) are judged by decode_blocks_kernel; blocks that are not well-formed compressed blocks are skipped
+ * here.
+ * Measured and dropped (round 2, config-2 stream, parse kernel alone): two blocks per thread with a branch-free trip for
+ * both (the two chains interleave in the SASS, but a trip then costs twice the instructions and takes 720 instead of
+ * 415 clocks: 3.0 ms against 1.7); a walk that keeps only a bit position and loads the two words under it for every
+ * code (40 % fewer instructions per code, but an L1 load on every trip of the chain and a reader to open between the
+ * partitions: 2.2 ms). */
+struct DecWalk {
+    DecBits br;
+    int32_t *out, *x;              /* the block's first channel / the channel being filled             */
+    uint32_t n, payload_bits;
+    uint32_t ch, i, in_part, parts, k, per, rec;
+    uint32_t status, method;
+    bool first, open, done, walked;
+};
+
+/* sync code, sizes, side information of every channel (srla_decoder.c:436-540); leaves the reader in front of the
+ * first channel's residual codes */
+__device__ __forceinline__ void dec_walk_head(DecWalk &w, const DecParams &p, uint32_t bi)
 {
-    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    w.status = 0u; w.method = 0u; w.done = true; w.walked = false;
+    w.ch = 0u; w.i = 0u; w.in_part = 0u; w.parts = 0u; w.k = 0u; w.per = 0u; w.rec = 0u; w.first = false; w.open = false;
+    w.n = 0u; w.payload_bits = 0u; w.out = p.out; w.x = p.out;
     if (bi >= p.num_blocks) { return; }
     const DecBlock blk = p.blocks[bi];
     const uint8_t *b = p.data + blk.offset;
     const uint32_t nch = p.nch, n = blk.nsmpl;
-    DecSide sd; sd.status = 0u; sd.method = 0u;
     const uint32_t size = ((uint32_t)b[2] << 24) | ((uint32_t)b[3] << 16) | ((uint32_t)b[4] << 8) | b[5];
     const bool walk = b[0] == 0xFFu && b[1] == 0xFFu && size >= 5u && size + 6u <= blk.bytes && b[8] == (uint8_t)kBlockCompress
                       && ((((uint32_t)b[9] << 8) | b[10]) == n) && n > 0u;
-    if (!walk) { p.side[bi] = sd; return; }
+    if (!walk) { return; }
     const uint8_t *payload = b + 11;
     const uint32_t payload_bytes = blk.bytes - 11u;
-    int32_t *out = p.out + blk.sample_offset;
+    w.walked = true; w.n = n; w.payload_bits = payload_bytes * 8u;
+    w.out = p.out + blk.sample_offset; w.x = w.out;
     DecSideChannel *chan = p.side_ch + (size_t)bi * nch;
-    {
-        DecBits br;
-        br.open(payload, payload + payload_bytes);
-        const uint16_t *tree0 = p.tree, *tree1 = p.tree + 512;
-        const uint32_t root0 = p.tree[1024], root1 = p.tree[1025];
-        uint32_t status = 0u;
-        sd.method = br.get(2);
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            chan[ch].head = dec_zigzag(br.get(p.bps + 1u));
-            chan[ch].pre_coef = dec_zigzag(br.get(5));
-        }
-        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
-            DecSideChannel &c = chan[ch];
-            const uint32_t order = br.get(8);
-            c.order = order; c.rshift = br.get(4);
-            const uint32_t use_sum = br.get(1);
-            int32_t prev = 0;
-            for (uint32_t i = 0; i < order; ++i) {
-                const uint16_t *tree = (use_sum && i > 0u) ? tree1 : tree0;
-                uint32_t node = (use_sum && i > 0u) ? root1 : root0;
-                do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u);
-                int32_t v = dec_zigzag(node & 255u);
-                if (use_sum && i > 0u) { v -= prev; }                                /* summed-neighbour table: coef[i] = code - coef[i-1] */
-                prev = v;
-                c.coef[i] = (int16_t)v;
-            }
-            if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
-        }
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            DecSideChannel &c = chan[ch];
-            uint32_t ltp_order = 0u, ltp_period = 0u;
-            if (br.get(1)) {
-                ltp_order = 2u * br.get(1) + 1u;
-                ltp_period = br.get(8) + (uint32_t)kLtpMinPeriod;
-                for (uint32_t i = 0; i < ltp_order; ++i) { c.ltp_coef[i] = dec_zigzag(br.get(6)); }
-            }
-            c.ltp_order = ltp_order; c.ltp_period = ltp_period;
-        }
-        /* residual codes (srla_coder.c:648-690) */
-        for (uint32_t ch = 0; ch < nch && !status; ++ch) {
-            int32_t *x = out + (size_t)ch * p.stride;
-            const uint32_t code = br.get(2);
-            if (code == (uint32_t)kCodeAllZero) { for (uint32_t i = 0; i < n; ++i) { x[i] = 0; } continue; }
-            if (code > (uint32_t)kCodeAllZero) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-            const uint32_t porder = br.get(10);
-            if (porder > (uint32_t)kLog2MaxParts) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-            const uint32_t per = n >> porder;
-            uint32_t k = 0;
-            for (uint32_t part = 0; part < (1u << porder); ++part) {
-                if (part == 0u) { k = br.get(5); }
-                else { k = (uint32_t)((int32_t)k + dec_zigzag(br.zero_run())); }
-                if (k > 31u) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-                int32_t *dst = x + (size_t)part * per;
-                if (code == (uint32_t)kCodeRice) {
-                    for (uint32_t i = 0; i < per; ++i) {
-                        uint32_t quot, low;
-                        br.run_and_bits([k](uint32_t) { return k; }, &quot, &low);
-                        dst[i] = dec_zigzag((quot << k) + low);
-                    }
-                } else {
-                    for (uint32_t i = 0; i < per; ++i) {
-                        uint32_t quot, low;
-                        br.run_and_bits([k](uint32_t run) { return k + (run ? 0u : 1u); }, &quot, &low);
-                        dst[i] = dec_zigzag(low | ((quot + (quot ? 1u : 0u)) << k));
-                    }
-                }
-                if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; break; }
-            }
-            for (uint32_t i = per << porder; i < n; ++i) { x[i] = 0; }              /* never happens for streams the encoder writes */
-        }
-        /* exact bound: a walk that took more bits than the block holds read its neighbour's bytes (corrupt data) */
-        if (!status && br.consumed_bits() > (long long)payload_bytes * 8) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
-        sd.status = status;
+    DecBits &br = w.br;
+    br.open(payload, payload + payload_bytes);
+    const uint16_t *tree0 = p.tree, *tree1 = p.tree + 512;
+    const uint32_t root0 = p.tree[1024], root1 = p.tree[1025];
+    uint32_t status = 0u;
+    w.method = br.get(2);
+    for (uint32_t ch = 0; ch < nch; ++ch) {
+        chan[ch].head = dec_zigzag(br.get(p.bps + 1u));
+        chan[ch].pre_coef = dec_zigzag(br.get(5));
     }
+    for (uint32_t ch = 0; ch < nch && !status; ++ch) {
+        DecSideChannel &c = chan[ch];
+        const uint32_t order = br.get(8);
+        c.order = order; c.rshift = br.get(4);
+        const uint32_t use_sum = br.get(1);
+        int32_t prev = 0;
+        for (uint32_t i = 0; i < order; ++i) {
+            const uint16_t *tree = (use_sum && i > 0u) ? tree1 : tree0;
+            uint32_t node = (use_sum && i > 0u) ? root1 : root0;
+            do { node = tree[br.get(1) * 256u + (node - 256u)]; } while (node >= 256u);
+            int32_t v = dec_zigzag(node & 255u);
+            if (use_sum && i > 0u) { v -= prev; }                                /* summed-neighbour table: coef[i] = code - coef[i-1] */
+            prev = v;
+            c.coef[i] = (int16_t)v;
+        }
+        if (br.overrun()) { status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+    }
+    for (uint32_t ch = 0; ch < nch; ++ch) {
+        DecSideChannel &c = chan[ch];
+        uint32_t ltp_order = 0u, ltp_period = 0u;
+        if (br.get(1)) {
+            ltp_order = 2u * br.get(1) + 1u;
+            ltp_period = br.get(8) + (uint32_t)kLtpMinPeriod;
+            for (uint32_t i = 0; i < ltp_order; ++i) { c.ltp_coef[i] = dec_zigzag(br.get(6)); }
+        }
+        c.ltp_order = ltp_order; c.ltp_period = ltp_period;
+    }
+    w.status = status;
+    w.done = status != 0u;
+}
+
+/* Between two partitions (srla_coder.c:648-690): the next partition's parameter, in front of it the next channel's
+ * code type and partition order, behind a channel's last partition the samples no partition covers (never for streams
+ * the encoder writes).  Returns with codes to read (in_part > 0) or with the walk finished. */
+__device__ __forceinline__ void dec_walk_between(DecWalk &w, const DecParams &p)
+{
+    DecBits &br = w.br;
+    const uint32_t n = w.n;
+    for (;;) {
+        if (w.parts == 0u) {
+            if (w.open) { for (; w.i < n; ++w.i) { w.x[w.i] = 0; } ++w.ch; w.open = false; }
+            if (w.ch >= p.nch) { w.done = true; return; }
+            w.x = w.out + (size_t)w.ch * p.stride; w.i = 0u;
+            const uint32_t code = br.get(2);
+            if (code == (uint32_t)kCodeAllZero) { for (uint32_t j = 0; j < n; ++j) { w.x[j] = 0; } ++w.ch; continue; }
+            if (code > (uint32_t)kCodeAllZero) { w.status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; w.done = true; return; }
+            const uint32_t porder = br.get(10);
+            if (porder > (uint32_t)kLog2MaxParts) { w.status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; w.done = true; return; }
+            w.per = n >> porder; w.parts = 1u << porder; w.first = true; w.open = true;
+            w.rec = (code == (uint32_t)kCodeRecursiveRice) ? 1u : 0u;
+        }
+        if (br.overrun()) { w.status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; w.done = true; return; }
+        w.k = w.first ? br.get(5) : (uint32_t)((int32_t)w.k + dec_zigzag(br.zero_run()));
+        w.first = false; --w.parts;
+        if (w.k > 31u) { w.status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; w.done = true; return; }
+        w.in_part = w.per;
+        if (w.per != 0u) { return; }                                                 /* else more partitions than samples: parameters only */
+    }
+}
+
+/* One code: Rice = unary quotient + k bits; recursive Rice = k + 1 bits behind an empty run, else k bits and the
+ * quotient one up (srla_coder.c:610-646).  dec_code_shape looks at the upper half of the window (all valid); a code
+ * of at most 32 bits is then taken without a branch. */
+struct DecShape { uint32_t hi, z, nb, need; };
+__device__ __forceinline__ DecShape dec_code_shape(const DecWalk &w)
+{
+    DecShape s;
+    s.hi = (uint32_t)(w.br.win >> 32);
+    s.z = (uint32_t)__clz((int)s.hi);                                                /* 32 for an empty half */
+    s.nb = w.k + (w.rec & (s.z == 0u ? 1u : 0u));
+    s.need = s.z + 1u + s.nb;
+    return s;
+}
+__device__ __forceinline__ void dec_put(DecWalk &w, uint32_t quot, uint32_t low)
+{
+    const uint32_t u = low + ((quot + (w.rec & (quot ? 1u : 0u))) << w.k);           /* low < 2^k whenever the quotient counts */
+    w.x[w.i] = dec_zigzag(u);
+    ++w.i; --w.in_part;
+}
+__device__ __forceinline__ void dec_code_short(DecWalk &w, const DecShape &s)         /* s.need <= 32 */
+{
+    const uint32_t low = __funnelshift_rc(__funnelshift_lc(0u, s.hi, s.z + 1u), 0u, 32u - s.nb);   /* (hi << (z + 1)) >> (32 - nb), shifts of 32 give 0 */
+    w.br.win = (w.br.win << (s.need - 1u)) << 1; w.br.avail -= (int)s.need;
+    w.br.refill();
+    dec_put(w, s.z, low);
+}
+__device__ __forceinline__ void dec_code_any(DecWalk &w)
+{
+    const DecShape s = dec_code_shape(w);
+    if (s.need <= 32u) { dec_code_short(w, s); return; }
+    const uint32_t quot = w.br.zero_run();
+    const uint32_t low = w.br.get(w.k + (w.rec & (quot == 0u ? 1u : 0u)));
+    dec_put(w, quot, low);
+}
+
+__global__ void __launch_bounds__(32) decode_parse_kernel(const DecParams p)
+{
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= p.num_blocks) { return; }
+    DecWalk w;
+    dec_walk_head(w, p, bi);
+    while (!w.done) {
+        if (w.in_part == 0u) { dec_walk_between(w, p); continue; }
+        dec_code_any(w);
+    }
+    /* exact bound: a walk that took more bits than the block holds read its neighbour's bytes (corrupt data) */
+    if (w.walked && !w.status && w.br.consumed_bits() > (long long)w.payload_bits) { w.status = SRLA_APIRESULT_DETECT_DATA_CORRUPTION; }
+    DecSide sd; sd.status = w.status; sd.method = w.method;
     p.side[bi] = sd;
 }
 
@@ -386,6 +488,8 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
             __syncwarp();
             const uint32_t order = min(g.order, (uint32_t)kMaxOrder);      /* the order field is 8 bits; never index past cp[] */
             for (uint32_t i = lane; i < order; i += 32u) { c.cp[order - i] = g.coef[i]; }
+            __syncwarp();
+            for (uint32_t i = lane; i < 64u * kDecMaxTaps; i += 32u) { c.rot[i >> 6][i & 63u] = c.cp[(i & 31u) + 1u + 32u * (i >> 6)]; }
             if (lane == 0u) {
                 c.head = g.head; c.pre_coef = g.pre_coef; c.order = order; c.rshift = g.rshift;
                 c.ltp_order = g.ltp_order; c.ltp_period = g.ltp_period;
@@ -487,7 +591,8 @@ struct DecoderCtx {
     int pipeline = -1;             /* SRLA_B200_DECODE_PIPELINE: 1 always, 0 never, default: from a handle's second long stream on */
     int long_calls = 0;
     DevBuf data, out, blocks, status, tree, side, side_ch;
-    int parse_lanes = 4;           /* SRLA_B200_DECODE_LANES: blocks walked per warp of decode_parse_kernel */
+    int parse_lanes = 0;           /* SRLA_B200_DECODE_LANES: blocks walked per warp of decode_parse_kernel; 0 = from the launch size */
+    int sms = 148;
     PinBuf h_blocks, h_status;
     float last_ms = 0.f;
 };
@@ -506,6 +611,17 @@ struct SRLADecoder {
 
 namespace {
 
+/* Blocks per warp of decode_parse_kernel.  The walk is a chain of dependent operations per code, so a launch wants
+ * a few warps on every scheduler before it fills the lanes of a warp (lanes in lockstep wait for each other's rare
+ * slow paths): about kParseWarpsPerSm warps per SM, then up to 32 lanes. */
+constexpr size_t kParseWarpsPerSm = 8;
+unsigned parse_lanes_for(const DecoderCtx *c, size_t blocks)
+{
+    if (c->parse_lanes > 0) { return (unsigned)c->parse_lanes; }
+    const size_t warps = (size_t)c->sms * kParseWarpsPerSm;
+    return (unsigned)std::min<size_t>(32, std::max<size_t>(1, (blocks + warps - 1) / warps));
+}
+
 bool decoder_ctx_init(DecoderCtx *c)
 {
     int count = 0;
@@ -516,6 +632,7 @@ bool decoder_ctx_init(DecoderCtx *c)
     if (g_device >= 0) { CU_TRY(cudaSetDevice(g_device)); }
     CU_TRY(cudaGetDevice(&c->device));
     if (!device_is_sm100(c->device)) { return false; }
+    CU_TRY(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, c->device));
     CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_TRY(cudaEventCreate(&c->ev0));
     CU_TRY(cudaEventCreate(&c->ev1));
@@ -526,7 +643,7 @@ bool decoder_ctx_init(DecoderCtx *c)
     c->host_threads = (int)std::max(2u, std::min(16u, usable_cpus()));
     if (const char *e = std::getenv("SRLA_B200_FEED_THREADS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) { c->host_threads = v; } }
     if (const char *e = std::getenv("SRLA_B200_DECODE_PIPELINE")) { c->pipeline = std::atoi(e) ? 1 : 0; }
-    if (const char *e = std::getenv("SRLA_B200_DECODE_LANES")) { const int v = std::atoi(e); if (v >= 1 && v <= 32) { c->parse_lanes = v; } }
+    if (const char *e = std::getenv("SRLA_B200_DECODE_LANES")) { const int v = std::atoi(e); if (v >= 0 && v <= 32) { c->parse_lanes = v; } }
     host::HuffTable plain, summed; host::HuffTree t0, t1;
     host::build_format_huffman(plain, summed, &t0, &t1);
     uint16_t tab[1026];
@@ -677,7 +794,8 @@ SRLAApiResult decoder_run_pipelined(struct SRLADecoder *d, const uint8_t *data, 
         p.blocks = (const DecBlock *)c->blocks.p + b0; p.status = (uint32_t *)c->status.p + b0;
         p.side = (DecSide *)c->side.p + b0; p.side_ch = (DecSideChannel *)c->side_ch.p + b0 * nch; p.num_blocks = (uint32_t)cnt;
         cudaEventRecord(c->ev_k0[g], on);
-        decode_parse_kernel<<<(unsigned)((cnt + c->parse_lanes - 1) / c->parse_lanes), c->parse_lanes, 0, on>>>(p);
+        const unsigned pl = parse_lanes_for(c, nb);                 /* the groups' kernels run side by side: the call's blocks count */
+        decode_parse_kernel<<<(unsigned)((cnt + pl - 1) / pl), pl, 0, on>>>(p);
         decode_blocks_kernel<<<(unsigned)cnt, 32u * std::max(1u, nch), nch * (sizeof(DecChannel) + sizeof(int32_t) * kDecStage), on>>>(p);
         cudaEventRecord(c->ev_k1[g], on);
         if (cudaGetLastError() != cudaSuccess || cudaStreamWaitEvent(c->copy_out, c->ev_k1[g], 0) != cudaSuccess) { return SRLA_APIRESULT_NG; }
@@ -740,7 +858,8 @@ SRLAApiResult decoder_run(struct SRLADecoder *d, const uint8_t *data, uint64_t d
     p.tree = (const uint16_t *)c->tree.p;
     p.side = (DecSide *)c->side.p; p.side_ch = (DecSideChannel *)c->side_ch.p; p.num_blocks = (uint32_t)nb; p.pad = 0;
     cudaEventRecord(c->ev0, c->stream);
-    decode_parse_kernel<<<(unsigned)((nb + c->parse_lanes - 1) / c->parse_lanes), c->parse_lanes, 0, c->stream>>>(p);
+    const unsigned pl = parse_lanes_for(c, nb);
+    decode_parse_kernel<<<(unsigned)((nb + pl - 1) / pl), pl, 0, c->stream>>>(p);
     decode_blocks_kernel<<<(unsigned)nb, 32u * std::max(1u, nch), nch * (sizeof(DecChannel) + sizeof(int32_t) * kDecStage), c->stream>>>(p);
     cudaEventRecord(c->ev1, c->stream);
     if (cudaGetLastError() != cudaSuccess) { return SRLA_APIRESULT_NG; }

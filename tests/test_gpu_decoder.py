@@ -238,3 +238,41 @@ def test_hostile_blocks_are_refused_without_touching_unwritten_records():
     with D.Decoder(check_checksum=False) as dec:
         rc, _out = dec.decode_whole_rc(cut, 2, pcm.shape[1])
         assert rc == E.DATA_CORRUPTION, rc
+
+
+@pytest.mark.parametrize("lanes", ["1", "5", "32", "0"])
+def test_lockstep_walk_of_unlike_blocks(lanes, monkeypatch):
+    """The lanes of a warp of decode_parse_kernel walk different blocks in lockstep: a stream whose neighbouring blocks
+    differ in everything the walk branches on -- music, silence (SILENT blocks), full-scale noise (RAW blocks), sparse
+    clicks on silence (codes longer than 32 bits: the general reader; tiny Rice parameters), a constant (all-zero
+    residual channels), a short odd tail -- decodes to the source with 1, 5 and 32 blocks per warp and with the
+    launch's own choice, on the one-launch path and on the pipelined one"""
+    rng = np.random.default_rng(77)
+    n = 1024
+    parts = []
+    for k in range(96):
+        kind = k % 6
+        if kind == 0:
+            seg = synth_stereo(n, seed=100 + k)
+        elif kind == 1:
+            seg = np.zeros((2, n), dtype=np.int32)
+        elif kind == 2:
+            seg = rng.integers(-32768, 32768, size=(2, n)).astype(np.int32)
+        elif kind == 3:
+            seg = np.zeros((2, n), dtype=np.int32)
+            seg[:, rng.integers(0, n, size=3)] = rng.integers(-30000, 30000, size=3)
+        elif kind == 4:
+            seg = np.full((2, n), 1234, dtype=np.int32); seg[1] = synth_stereo(n, seed=k)[1]
+        else:
+            seg = (synth_stereo(n, seed=300 + k) >> 6).astype(np.int32)
+        parts.append(seg)
+    parts.append(synth_stereo(333, seed=9))
+    pcm = np.ascontiguousarray(np.concatenate(parts, axis=1).astype(np.int32))
+    stream = E.encode(pcm, preset=4, max_block=n)
+    monkeypatch.setenv("SRLA_B200_DECODE_LANES", lanes)
+    for pipe in ("0", "1"):
+        monkeypatch.setenv("SRLA_B200_DECODE_PIPELINE", pipe)
+        with D.Decoder() as dec:
+            assert np.array_equal(dec.decode_whole(stream), pcm), (lanes, pipe)
+    if have_ref() and lanes == "0":
+        assert np.array_equal(ref_decode(stream), pcm)

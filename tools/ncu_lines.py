@@ -6,14 +6,15 @@ rep, pat = sys.argv[1], sys.argv[2]
 N = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 40
 by = "samples" if "--by" in sys.argv and sys.argv[sys.argv.index("--by") + 1] == "samples" else "inst"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-cur, hdr, data = None, None, collections.defaultdict(list)
+cur, hdr, data, hdrs = None, None, collections.defaultdict(list), {}
 for r in csv.reader(io.StringIO(out)):
     if not r: continue
     if r[0] in ("Kernel Name", "Function Name"): cur = r[1]; continue
-    if r[0] == "Line No": hdr = r; continue
+    if r[0] == "Line No": hdr = r; hdrs[cur] = r; continue      # the stall columns differ from kernel to kernel
     if hdr and r[0].isdigit() and len(r) > 8 and r[2] == '-': data[cur].append(r)
 for k, v in data.items():
     if k is None or pat not in k: continue
+    hdr = hdrs.get(k, hdr)
     ti = sum(int(r[7]) for r in v) or 1; ts = sum(int(r[4]) for r in v) or 1
     print("##", k, "warp-inst", ti, "samples", ts)
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
