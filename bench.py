@@ -355,6 +355,7 @@ def main() -> None:
     ap.add_argument("--blocks", type=int, default=10000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--files", type=int, default=1024, help="config 5: number of 30 s stereo files in the sharded batch (0: skip)")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decoder figures (N=1 only)")
     ap.add_argument("--no-pin", action="store_true", help="do not restrict the rank to the CPUs next to its GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -581,6 +582,47 @@ def main() -> None:
     same_bytes = bool(bytes(out_np[:size.value]) == bytes(h_out[:int(offs[1])].numpy().tobytes()))
     del pcm32
 
+    # ---- decoder on the stream the call above wrote: SRLADecoder_DecodeWhole, checked against the source PCM.
+    # Device time from a handle that decodes with ONE pair of launches (SRLA_B200_DECODE_PIPELINE=0: CUDA events around
+    # decode_parse_kernel + decode_blocks_kernel); end to end from a default handle, whose third and later long streams
+    # take the pipelined path (pageable stream in, pageable planar int32 out: 4 bytes per sample back over PCIe). ----
+    decode = None
+    if world == 1 and not args.no_decode:
+        from srla_b200 import decoder as D
+        stream = out_np[:size.value].tobytes()
+        got = np.zeros_like(pcm32)
+        saved_env = os.environ.get("SRLA_B200_DECODE_PIPELINE")
+        os.environ["SRLA_B200_DECODE_PIPELINE"] = "0"
+        try:
+            with D.Decoder() as dec:
+                dev_ms = None
+                for _ in range(3):
+                    dec.decode_whole(stream, got)
+                    dev_ms = dec.kernel_ms() if dev_ms is None else min(dev_ms, dec.kernel_ms())
+        finally:
+            if saved_env is None:
+                del os.environ["SRLA_B200_DECODE_PIPELINE"]
+            else:
+                os.environ["SRLA_B200_DECODE_PIPELINE"] = saved_env
+        identical = bool(np.array_equal(got, pcm32))
+        with D.Decoder() as dec:
+            best = None
+            for it in range(6):
+                got[:, :4096] = -1
+                t0 = time.perf_counter()
+                dec.decode_whole(stream, got)
+                dt = time.perf_counter() - t0
+                if it >= 2:
+                    best = dt if best is None else min(best, dt)
+        identical = identical and bool(np.array_equal(got, pcm32))
+        decode = {"device": {"value": samples_per_step / (dev_ms * 1e-3) / 1e6, "unit": "Msamples/s", "ms": dev_ms,
+                             "what": "decode_parse_kernel + decode_blocks_kernel over all blocks of the stream, CUDA events, stream resident in HBM"},
+                  "e2e": {"value": samples_per_step / best / 1e6, "unit": "Msamples/s", "ms": best * 1e3,
+                          "h2d_bytes": len(stream), "d2h_bytes": int(pcm32.nbytes),
+                          "api": "SRLADecoder_DecodeWhole (include/srla_decoder.h:46-49): pageable stream in, pageable planar int32 PCM out; wall clock, best of 4"},
+                  "identical_to_source": identical, "stream_bytes": len(stream)}
+        del got
+
     # ---- config 5 (BASELINE configs[4]): a batch of 30 s stereo files SHARDED over the ranks (strong scaling) ----
     config5 = None
     if args.files > 0:
@@ -671,6 +713,7 @@ def main() -> None:
                     "fraction_of_host_dram_ceiling": (e2e_value * (8.0 + 3.0 * d2h / float(samples_per_step))) / (feed_ceiling * 6.0)},
             "e2e_batch_api": batch_api,
             "config5": config5,
+            "decode": decode,
             "host_placement": placement,
             "gpu_launches": launches,
             "roofline": roofline,

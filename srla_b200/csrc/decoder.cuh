@@ -163,11 +163,16 @@ struct DecChannel {
  * adds the product with the tap that lies between that sample and its own next output.  Rounds that touch the
  * warm-up samples (srla_lpc_synthesize.c:253-262) or the end of the block run the general loop; the full rounds
  * behind the warm-up run unrolled: the tap of step s sits at a literal offset from a per-lane address, the owner
- * test compares with a literal. */
-template <int T>
+ * test compares with a literal.
+ * DE: the de-emphasis (srla_utility.c:361-378: y[i] = x[i] + ((y[i-1] c) >> 4), y[-1] = head) rides along -- every lane
+ * advances the chain with the broadcast sample (three instructions) and the owner keeps y instead of x; only without a
+ * long-term predictor, whose synthesis sits between the two in the reference's order. */
+template <int T, bool DE>
 __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const DecChannel &chn, uint32_t lane)
 {
     const uint32_t order = chn.order, rshift = chn.rshift;
+    const uint32_t pc = (uint32_t)chn.pre_coef;
+    uint32_t y = (uint32_t)chn.head;
     const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;     /* 1 << -1 on x86 */
     uint32_t acc[T];
     #pragma unroll
@@ -184,8 +189,9 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
             for (int s = 0; s < 32; ++s) {
                 const uint32_t cand = res - (uint32_t)((int32_t)(acc[0] + half) >> rshift);
                 const uint32_t xq = __shfl_sync(0xffffffffu, cand, s);
+                if (DE) { y = xq + (uint32_t)((int32_t)(y * pc) >> 4); }
                 if (lane == (uint32_t)s) {
-                    mine = xq;
+                    mine = DE ? y : xq;
                     #pragma unroll
                     for (int t = 0; t + 1 < T; ++t) { acc[t] = acc[t + 1]; }
                     acc[T - 1] = 0u;
@@ -206,8 +212,9 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
             else if (q < order) { cand = res + xprev; }
             else { cand = res - (uint32_t)((int32_t)(acc[0] + half) >> rshift); }
             const uint32_t xq = __shfl_sync(0xffffffffu, cand, (int)s);
+            if (DE) { y = xq + (uint32_t)((int32_t)(y * pc) >> 4); }
             if (lane == s) {
-                mine = xq;
+                mine = DE ? y : xq;
                 #pragma unroll
                 for (int t = 0; t + 1 < T; ++t) { acc[t] = acc[t + 1]; }
                 acc[T - 1] = 0u;
@@ -503,17 +510,21 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
     if (warp < nch && n > 0u) {
         int32_t *x = out + (size_t)warp * p.stride;
         const DecChannel &c = chan[warp];
+        const bool ltp = c.ltp_period > 0u && c.ltp_order > 0u;
+        bool deemphasised = false;
         if (c.order > 0u && n > c.order) {
-            if (c.order <= 32u) { dec_lpc_synthesize<1>(x, n, c, lane); }
-            else if (c.order <= 64u) { dec_lpc_synthesize<2>(x, n, c, lane); }
-            else if (c.order <= 128u) { dec_lpc_synthesize<4>(x, n, c, lane); }
-            else { dec_lpc_synthesize<8>(x, n, c, lane); }
+            if (!ltp && c.order <= 32u) { dec_lpc_synthesize<1, true>(x, n, c, lane); deemphasised = true; }
+            else if (!ltp && c.order <= 64u) { dec_lpc_synthesize<2, true>(x, n, c, lane); deemphasised = true; }
+            else if (c.order <= 32u) { dec_lpc_synthesize<1, false>(x, n, c, lane); }
+            else if (c.order <= 64u) { dec_lpc_synthesize<2, false>(x, n, c, lane); }
+            else if (c.order <= 128u) { dec_lpc_synthesize<4, false>(x, n, c, lane); }
+            else { dec_lpc_synthesize<8, false>(x, n, c, lane); }
         } else if (c.order > 0u) {
             /* a block no longer than the order is all warm-up (srla_lpc_synthesize.c:253-255): running sum */
             if (lane == 0u) { for (uint32_t i = 1; i < n && i < c.order; ++i) { x[i] = (int32_t)((uint32_t)x[i] + (uint32_t)x[i - 1]); } }
             __syncwarp();
         }
-        if (c.ltp_period > 0u && c.ltp_order > 0u) {
+        if (ltp) {
             /* srla_lpc_synthesize.c:264-327: x[s] += (16 + sum_j c[j] x[s - T - h + j]) >> 5 for s > T + h; a chunk shorter
              * than the shortest lag T - h never reads what it writes */
             const uint32_t h = c.ltp_order >> 1, T0 = c.ltp_period;
@@ -528,9 +539,10 @@ __global__ void __launch_bounds__(256) decode_blocks_kernel(const DecParams p)
                 __syncwarp();
             }
         }
-        {
+        if (!deemphasised) {
             /* de-emphasis (srla_utility.c:361-378): x[0] += (head c) >> 4, x[i] += (x[i-1] c) >> 4 -- a serial chain.  The
-             * warp moves 128 samples at a time through shared memory (coalesced both ways); lane 0 runs the chain there. */
+             * warp moves 128 samples at a time through shared memory (coalesced both ways); lane 0 runs the chain there.
+             * (Blocks without a long-term predictor and an order of at most 64 had it done inside the synthesis rounds.) */
             const uint32_t pc = (uint32_t)c.pre_coef;
             int32_t *st = stage + warp * kDecStage;
             uint32_t prev = (uint32_t)c.head;
