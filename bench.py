@@ -580,7 +580,6 @@ def main() -> None:
     h2d = CHANNELS * nsamp * 2          # the host feeder narrows the int32 input to int16 on its way into pinned staging
     d2h = int(size.value)
     same_bytes = bool(bytes(out_np[:size.value]) == bytes(h_out[:int(offs[1])].numpy().tobytes()))
-    del pcm32
 
     # ---- decoder on the stream the call above wrote: SRLADecoder_DecodeWhole, checked against the source PCM.
     # Device time from a handle that decodes with ONE pair of launches (SRLA_B200_DECODE_PIPELINE=0: CUDA events around
@@ -622,6 +621,7 @@ def main() -> None:
                           "api": "SRLADecoder_DecodeWhole (include/srla_decoder.h:46-49): pageable stream in, pageable planar int32 PCM out; wall clock, best of 4"},
                   "identical_to_source": identical, "stream_bytes": len(stream)}
         del got
+    del pcm32
 
     # ---- config 5 (BASELINE configs[4]): a batch of 30 s stereo files SHARDED over the ranks (strong scaling) ----
     config5 = None
