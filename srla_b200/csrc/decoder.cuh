@@ -176,7 +176,7 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
     const uint32_t half = (rshift > 0u) ? (1u << (rshift - 1u)) : 0x80000000u;     /* 1 << -1 on x86 */
     uint32_t acc[T];
     #pragma unroll
-    for (int t = 0; t < T; ++t) { acc[t] = 0u; }
+    for (int t = 0; t < T; ++t) { acc[t] = half; }                               /* the rounding term rides in the sums */
     uint32_t xprev = 0u, mine = 0u;
     uint32_t next_res = (lane < n) ? (uint32_t)x[lane] : 0u;
     const int32_t *taps = &chn.rot[0][31u + lane];
@@ -187,14 +187,14 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
         if (base >= order && n - base >= 32u) {
             #pragma unroll
             for (int s = 0; s < 32; ++s) {
-                const uint32_t cand = res - (uint32_t)((int32_t)(acc[0] + half) >> rshift);
+                const uint32_t cand = res - (uint32_t)((int32_t)acc[0] >> rshift);
                 const uint32_t xq = __shfl_sync(0xffffffffu, cand, s);
                 if (DE) { y = xq + (uint32_t)((int32_t)(y * pc) >> 4); }
                 if (lane == (uint32_t)s) {
                     mine = DE ? y : xq;
                     #pragma unroll
                     for (int t = 0; t + 1 < T; ++t) { acc[t] = acc[t + 1]; }
-                    acc[T - 1] = 0u;
+                    acc[T - 1] = half;
                 }
                 #pragma unroll
                 for (int t = 0; t < T; ++t) { acc[t] += (uint32_t)taps[64 * t - s] * xq; }
@@ -210,14 +210,14 @@ __device__ __forceinline__ void dec_lpc_synthesize(int32_t *x, uint32_t n, const
             uint32_t cand;
             if (q == 0u) { cand = res; }
             else if (q < order) { cand = res + xprev; }
-            else { cand = res - (uint32_t)((int32_t)(acc[0] + half) >> rshift); }
+            else { cand = res - (uint32_t)((int32_t)acc[0] >> rshift); }
             const uint32_t xq = __shfl_sync(0xffffffffu, cand, (int)s);
             if (DE) { y = xq + (uint32_t)((int32_t)(y * pc) >> 4); }
             if (lane == s) {
                 mine = DE ? y : xq;
                 #pragma unroll
                 for (int t = 0; t + 1 < T; ++t) { acc[t] = acc[t + 1]; }
-                acc[T - 1] = 0u;
+                acc[T - 1] = half;
             }
             xprev = xq;
             const uint32_t d0 = ((lane - s - 1u) & 31u) + 1u;                       /* distance to this lane's next output */
